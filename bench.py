@@ -1,0 +1,381 @@
+#!/usr/bin/env python
+"""Benchmark of the rs-sync loss engine on B200 (contract: see DESIGN.md §7).
+
+A "step" is one pass of the PreSync brute-force grid (offset x frame x feature loss
+evaluations, the body of pre_sync, core_private.cpp:61-90 of the reference) over the
+GX012440-shaped synthetic workload C2 of BASELINE.json: frames 3900..7199 (3300) x 200 rays x
+201 offsets (DebugPreSync's linspace grid, radius 200 ms).  With N > 1 GPUs every rank holds a
+replica of the inputs and evaluates its own 201-offset slice of a grid N times as wide
+(weak scaling, radius 0.2*N s, same 2 ms step); only the loss-curve slices are gathered (NCCL).
+
+    python bench.py --gpus N --steps K --warmup W            # the B200 engine
+    python bench.py --impl reference --steps K --warmup W    # the CPU path on the host cores
+"""
+from __future__ import annotations
+
+import argparse
+import importlib
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+FLOP_PER_CELL = 285.0     # algorithmic FP64 flop per (offset, frame, ray) cell
+OFFSETS_PER_GPU = 201
+METRIC = "presync_loss_evals_per_s"
+UNIT = "cells/s"
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="C2")
+    ap.add_argument("--no-sync", action="store_true", help="skip the syncpoints/s section")
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline section")
+    ap.add_argument("--cpu-seconds", type=float, default=12.0)
+    return ap.parse_args()
+
+
+def make_workload(name, n_gpus):
+    synth = importlib.import_module("rs-sync_b200.synth")
+    radius = 0.2 * n_gpus if name in ("C1", "C2") else None
+    w = synth.make_workload(name, radius=radius)
+    return w
+
+
+def grid_delays(w, n_gpus):
+    n = OFFSETS_PER_GPU * n_gpus
+    r = w.presync_radius
+    return np.array([0.0 - r + 2 * r * i / (n - 1) for i in range(n)])  # core_private.cpp:345
+
+
+def workload_name(w, n_gpus):
+    return (f"{w.name}: synthetic GoPro-shaped, frames {int(w.frame_ids[0])}..{int(w.frame_ids[-1])} "
+            f"({w.n_frames}) x {w.n_rays} rays x {OFFSETS_PER_GPU * n_gpus} offsets "
+            f"(DebugPreSync linspace, radius {w.presync_radius * 1e3:.0f} ms, {OFFSETS_PER_GPU} offsets per GPU)")
+
+
+# ------------------------------------------------------------------------------------------
+class ClockSampler:
+    FIELDS = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+              "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.lines = []
+        self.proc = None
+        self.index = index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits", "-lms", "100",
+                 "-i", str(self.index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            p = [x.strip() for x in ln.split(",")]
+            if len(p) < 8:
+                continue
+            try:
+                sm.append(float(p[0]))
+                mx.append(float(p[1]))
+            except ValueError:
+                continue
+            for nm, val in zip(names, p[4:8]):
+                if val.lower().startswith("active"):
+                    reasons.add(nm)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        top = sorted(sm)[len(sm) // 2:]  # samples under load are the upper half
+        return {"sm_mhz": float(np.median(top)), "sm_max_mhz": float(max(mx)), "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------
+def cpu_problem(w, threads, prefer_ref=True):
+    """The CPU arm: the unmodified reference compiled against the shim when oracle/_ref exists,
+    else the oracle port.  Returns (problem, kind)."""
+    from oracle import loader
+    if prefer_ref:
+        try:
+            from oracle import ref_loader
+            if ref_loader.available():
+                p = ref_loader.RefProblem(threads=threads, seed=100)
+                p.load(w)
+                return p, "reference"
+        except Exception:
+            pass
+    p = loader.OracleProblem(threads=threads, seed=100).load(w)
+    return p, "port"
+
+
+def cpu_sample_shape(w, delays, cells_per_s, seconds):
+    """frames x offsets sample of the workload that takes about `seconds` on the CPU arm."""
+    want = max(cells_per_s * seconds, 1.0)
+    n_off = int(max(1, min(len(delays), want // (w.n_frames * w.n_rays))))
+    return n_off
+
+
+def time_cpu(p, w, delays, n_off, call_no=0):
+    fb, fe = int(w.frame_ids[0]), int(w.frame_ids[-1]) + 1
+    idx = np.linspace(0, len(delays) - 1, n_off).astype(int)
+    t = time.perf_counter()
+    p.presync_grid(fb, fe, delays[idx], stream=2, call_no=call_no)
+    dt = time.perf_counter() - t
+    return n_off * w.n_frames * w.n_rays / dt, dt
+
+
+def cpu_baseline(w, delays, seconds):
+    threads = os.cpu_count() or 1
+    p, kind = cpu_problem(w, threads)
+    rate, _ = time_cpu(p, w, delays, 1)                     # calibration (also warms the caches)
+    n_off = cpu_sample_shape(w, delays, rate, seconds)
+    rate, dt = time_cpu(p, w, delays, n_off)
+    return {"value": rate, "unit": UNIT, "cores": threads, "kind": kind,
+            "sample": f"{n_off} of {len(delays)} offsets x all {w.n_frames} frames x {w.n_rays} rays "
+                      f"({n_off * w.n_frames * w.n_rays:.3g} cells, {dt:.1f} s)"}
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    w = make_workload(args.workload, args.gpus)
+    delays = grid_delays(w, args.gpus)
+    threads = os.cpu_count() or 1
+    p, kind = cpu_problem(w, threads)
+    rate, _ = time_cpu(p, w, delays, 1)
+    budget = min(20.0, 100.0 / max(1, args.steps + args.warmup))
+    n_off = cpu_sample_shape(w, delays, rate, budget)
+    for i in range(args.warmup):
+        time_cpu(p, w, delays, n_off, call_no=i)
+    t0 = time.perf_counter()
+    for i in range(args.steps):
+        time_cpu(p, w, delays, n_off, call_no=100 + i)
+    dt = time.perf_counter() - t0
+    cells = n_off * w.n_frames * w.n_rays * args.steps
+    value = cells / dt
+    sample = (f"{n_off} of {len(delays)} offsets x all {w.n_frames} frames x {w.n_rays} rays per step")
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": workload_name(w, args.gpus), "step": "bounded sample: " + sample},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": kind, "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }))
+
+
+# ------------------------------------------------------------------------------------------
+def run_b200(args):
+    import torch
+    import torch.distributed as dist
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    n_gpus = max(args.gpus, world)
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    pkg = importlib.import_module("rs-sync_b200")
+    w = make_workload(args.workload, n_gpus)
+    delays = grid_delays(w, n_gpus)
+    lo, hi = OFFSETS_PER_GPU * rank, OFFSETS_PER_GPU * (rank + 1)
+    if world == 1:
+        lo, hi = 0, len(delays)
+    fb, fe = int(w.frame_ids[0]), int(w.frame_ids[-1]) + 1
+    cells_per_step_rank = (hi - lo) * w.n_frames * w.n_rays
+    cells_per_step = len(delays) * w.n_frames * w.n_rays
+
+    stream = torch.cuda.current_stream()
+    prob = pkg.SyncProblem(seed=100)
+    prob.set_stream(stream.cuda_stream)
+    prob.set_kernel_timing(True)
+    prob.load(w, bulk=True)
+    prob.flush()
+
+    flush_buf = torch.empty(512 * 1024 * 1024 // 4, dtype=torch.float32, device=dev)  # 512 MB > 126 MB L2
+    gather_in = torch.empty(hi - lo, dtype=torch.float64, device=dev)
+    gather_out = [torch.empty(hi - lo, dtype=torch.float64, device=dev) for _ in range(world)]
+
+    def step(call_no):
+        costs = prob.presync_grid(fb, fe, delays[lo:hi], stream=pkg.STREAM_DEBUG, call_no=call_no,
+                                  offset_index_base=lo)
+        if world > 1:  # the only exchange: loss-curve slices
+            gather_in.copy_(torch.from_numpy(costs))
+            dist.all_gather(gather_out, gather_in)
+            curve = torch.cat(gather_out)
+        else:
+            curve = torch.from_numpy(costs)
+        return int(torch.argmin(curve))
+
+    for i in range(args.warmup):
+        flush_buf.zero_()
+        step(i)
+    fp64_peak = pkg.measure_fp64_peak()
+
+    sampler = ClockSampler(local)
+    launches0 = prob.stats()["kernel_launches"]
+    barrier()
+    sampler.start()
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    kernel_ms = []
+    for i in range(args.steps):
+        flush_buf.zero_()  # L2 flush between timed iterations (inputs, 50 MB, fit the 126 MB L2)
+        ev[i][0].record(stream)
+        step(1000 + i)
+        ev[i][1].record(stream)
+        kernel_ms.append(prob.stats()["last_grid_kernel_ms"])
+    barrier()
+    clocks = sampler.stop()
+    launches = prob.stats()["kernel_launches"] - launches0
+    step_ms = [a.elapsed_time(b) for a, b in ev]
+    t = torch.tensor([sum(step_ms) / args.steps, float(np.mean(kernel_ms))], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_per_step, kern_ms = float(t[0]), float(t[1])
+    value = cells_per_step / (ms_per_step * 1e-3)
+
+    # ---- end to end: host buffers in, curve out, through the C ABI --------------------------
+    e2e_steps = max(3, min(args.steps, 5))
+    counts = np.full(w.n_frames, w.n_rays)
+    st0 = prob.stats()
+    barrier()
+    t0 = time.perf_counter()
+    for i in range(e2e_steps):
+        prob.SetGyroQuaternions(w.quats, w.quats.shape[0], w.gyro_rate, w.gyro_t0)
+        prob.set_track_batch(w.frame_ids, counts, w.ts_a, w.ts_b, w.rays_a, w.rays_b)
+        step(2000 + i)
+    barrier()
+    e2e_s = (time.perf_counter() - t0) / e2e_steps
+    st1 = prob.stats()
+    te = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(te, op=dist.ReduceOp.MAX)
+    e2e = {"value": cells_per_step / float(te[0]), "unit": UNIT,
+           "h2d_bytes_per_step": (st1["h2d_bytes"] - st0["h2d_bytes"]) // e2e_steps,
+           "d2h_bytes_per_step": (st1["d2h_bytes"] - st0["d2h_bytes"]) // e2e_steps,
+           "ms_per_step": float(te[0]) * 1e3,
+           "what": "SetGyroQuaternions + SetTrackResult (bulk) from host buffers, grid through the C ABI, curve back on the host"}
+
+    # ---- roofline of the dominant kernel (presync_kernel) -------------------------------------
+    achieved = FLOP_PER_CELL * cells_per_step_rank / (kern_ms * 1e-3) / 1e12
+    input_bytes = w.n_frames * ((w.n_rays + 31) // 32 * 32) * 64 + w.quats.shape[0] * 128 + cells_per_step_rank // w.n_rays * 8
+    roofline = {"bound": "fp64", "achieved": achieved, "peak": fp64_peak, "unit": "TFLOP/s",
+                "frac": achieved / fp64_peak if fp64_peak > 0 else None,
+                "peak_source": "measured live: rssync_measure_fp64_peak (dependent DFMA chains, all SMs)",
+                "kernel": "presync_kernel", "kernel_ms": kern_ms, "flop_per_cell": FLOP_PER_CELL,
+                "traffic": None,
+                "hbm": {"algorithmic_bytes": int(input_bytes),
+                        "achieved_gbs": input_bytes / (kern_ms * 1e-3) / 1e9, "peak_gbs": read_peaks().get("hbm_gbs")}}
+
+    out = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": n_gpus, "steps": args.steps,
+           "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
+           "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+           "config": {"workload": workload_name(w, n_gpus), "l2": "flushed between timed steps (512 MB memset)",
+                      "parallelism": f"offset-sharded x{n_gpus}, inputs replicated"},
+           "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline}
+
+    # ---- Sync: syncpoints/s (PreSync on the window + 4 chained Sync, core_testcode.cpp:303-316)
+    if not args.no_sync:
+        out["sync"] = bench_sync(prob, w, rank, world, barrier, dev)
+
+    if rank == 0 and world >= 1 and not args.no_cpu and world == 1:
+        out["cpu_baseline"] = cpu_baseline(w, delays, args.cpu_seconds)
+    elif rank == 0 and not args.no_cpu:
+        out["cpu_baseline"] = None
+    if rank == 0:
+        print(json.dumps(out))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def bench_sync(prob, w, rank, world, barrier, dev):
+    import torch
+    import torch.distributed as dist
+    sps = w.syncpoints()
+    mine = sps[rank::world] if world > 1 else sps
+    win = w.sync_window
+
+    def run():
+        delays = []
+        for pos in mine:  # PreSync per syncpoint
+            delays.append(prob.PreSync(0.0, pos, pos + win, w.presync_step, 0.2)[1])
+        d = np.array(delays)
+        fbs = np.array(mine, dtype=np.int64)
+        for _ in range(4):  # 4 chained Sync calls per syncpoint, advanced in lock-step
+            _, d = prob.sync_batch(d, fbs, fbs + win, 0.0, 0.2)
+        return d
+
+    prob.set_rng(100, 0)
+    run()  # warm-up
+    prob.set_rng(100, 0)
+    barrier()
+    t0 = time.perf_counter()
+    d = run()
+    barrier()
+    dt = time.perf_counter() - t0
+    t = torch.tensor([dt], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    err = np.abs(d - np.array([w.true_delay[p - int(w.frame_ids[0])] for p in mine]))
+    return {"metric": "sync_syncpoints_per_s", "value": len(sps) / float(t[0]), "unit": "syncpoints/s",
+            "syncpoints": len(sps), "seconds": float(t[0]),
+            "what": "per syncpoint: PreSync(radius 200 ms, step 2 ms) on a 60-frame window + 4 chained Sync; Sync calls batched across syncpoints",
+            "mean_abs_delay_error_ms": float(np.mean(err) * 1e3)}
+
+
+def read_peaks():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return json.load(f)
+    except Exception:
+        return {}
+
+
+if __name__ == "__main__":
+    a = parse()
+    if a.impl == "reference":
+        run_reference(a)
+    else:
+        run_b200(a)

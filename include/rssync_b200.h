@@ -1,0 +1,150 @@
+/* rssync_b200.h — C ABI of the B200-native rs-sync synchronisation loss engine.
+ *
+ * This is the drop-in boundary: plain pointers and sizes, `int` status codes, no C++ or torch
+ * types.  Each entry point names the member of the reference's ISyncProblem interface
+ * (src/core/public/rssync.h in VladimirP1/rs-sync) that it replaces; argument meaning, units
+ * (seconds unless the name ends in _us) and buffer layouts are the reference's:
+ *   quaternions  count x 4 doubles, (w,x,y,z) per sample
+ *   rays         count x 3 doubles, xyz interleaved unit vectors
+ *   ts_a / ts_b  count doubles, camera-clock seconds incl. the rolling-shutter row offset
+ * Input buffers are borrowed for the duration of the call only (they are copied).
+ *
+ * Every function returns RSSYNC_OK (0) or an error code; rssync_last_error() gives the message
+ * (for the panic conditions it is the reference's panic.txt text, core_private.cpp:76-83,
+ * 159-162, 180-188, 199-202).  There is no CPU fallback: if no CUDA device is usable the calls
+ * fail with RSSYNC_E_CUDA.
+ *
+ * The C++ class in include/rssync.h (ISyncProblem / CreateSyncProblem, same vtable layout as the
+ * reference) is a thin veneer over this ABI and maps a non-zero status to the reference's
+ * panic convention (write ./panic.txt, exit(1)).
+ */
+#ifndef RSSYNC_B200_H
+#define RSSYNC_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct rssync_problem rssync_problem;
+
+enum {
+    RSSYNC_OK = 0,
+    RSSYNC_E_INVALID = 1,   /* bad argument / unsupported shape                          */
+    RSSYNC_E_NONFINITE = 2, /* a reference panic condition: non-finite data              */
+    RSSYNC_E_ORDER = 3,     /* a reference panic condition: timestamps out of order      */
+    RSSYNC_E_STATE = 4,     /* call protocol violated (e.g. PreSync before gyro is set)  */
+    RSSYNC_E_CUDA = 5       /* CUDA runtime / device failure                             */
+};
+
+/* CreateSyncProblem()            rssync.h:31.  Uses the calling thread's current CUDA device. */
+int rssync_create(rssync_problem** out);
+/* ISyncProblem::~ISyncProblem()  rssync.h:11 */
+void rssync_destroy(rssync_problem* p);
+const char* rssync_last_error(const rssync_problem* p);
+
+/* SetGyroQuaternions(const double*, size_t, double, double)        rssync.h:13-14 */
+int rssync_set_gyro_fixed(rssync_problem* p, const double* quats, size_t count, double sample_rate,
+                          double first_timestamp);
+/* SetGyroQuaternions(const int64_t*, const double*, size_t)        rssync.h:15-16 */
+int rssync_set_gyro_var(rssync_problem* p, const int64_t* timestamps_us, const double* quats,
+                        size_t count);
+/* SetTrackResult(...)                                              rssync.h:17-18 */
+int rssync_set_track(rssync_problem* p, int64_t frame, const double* ts_a, const double* ts_b,
+                     const double* rays_a, const double* rays_b, size_t count);
+/* Bulk form of SetTrackResult: n_frames frames in one call.  counts[i] rays for frames[i]; the
+ * ts / ray buffers are the per-frame buffers concatenated in order.  Equivalent to n_frames
+ * rssync_set_track calls. */
+int rssync_set_track_batch(rssync_problem* p, size_t n_frames, const int64_t* frames,
+                           const size_t* counts, const double* ts_a, const double* ts_b,
+                           const double* rays_a, const double* rays_b);
+/* PreSync(initial_delay, frame_begin, frame_end, search_step, search_radius) -> {cost, delay}
+ *                                                                  rssync.h:19-21 */
+int rssync_presync(rssync_problem* p, double initial_delay, int64_t frame_begin, int64_t frame_end,
+                   double search_step, double search_radius, double* out_cost, double* out_delay);
+/* Sync(initial_delay, frame_begin, frame_end, search_center, search_radius) -> {cost, delay}
+ *                                                                  rssync.h:22-24 */
+int rssync_sync(rssync_problem* p, double initial_delay, int64_t frame_begin, int64_t frame_end,
+                double search_center, double search_radius, double* out_cost, double* out_delay);
+/* DebugPreSync(initial_delay, frame_begin, frame_end, search_radius, delays, costs, point_count)
+ *                                                                  rssync.h:26-28 */
+int rssync_debug_presync(rssync_problem* p, double initial_delay, int64_t frame_begin,
+                         int64_t frame_end, double search_radius, double* delays, double* costs,
+                         int point_count);
+
+/* ---- extensions (no counterpart in the reference interface) ------------------------------- */
+
+/* Loss curve on an arbitrary delay list over frames [frame_begin, frame_end): the body of
+ * pre_sync's outer loop (core_private.cpp:69-88).  offset_index_base is the index of delays[0]
+ * in the caller's full grid (it keys the RNG), so a grid can be sharded across processes/GPUs
+ * and still reproduce the single-GPU curve bit for bit.  stream: 1 = PreSync, 2 = DebugPreSync.
+ * Does not advance the call counter. */
+int rssync_presync_grid(rssync_problem* p, int64_t frame_begin, int64_t frame_end,
+                        const double* delays, int n, int stream, uint64_t call_no,
+                        uint64_t offset_index_base, double* costs, unsigned* nonfinite_flags);
+/* pre_sync's delay grid (core_private.cpp:69-70, floating-point accumulation included).
+ * Returns the number of points; fills at most `cap` of them. */
+int rssync_presync_delays(double initial_delay, double search_step, double search_radius,
+                          double* out, int cap);
+
+/* n independent Sync calls advanced in lock-step on the device; result i equals what the i-th of
+ * n consecutive rssync_sync calls would return. */
+int rssync_sync_batch(rssync_problem* p, int n, const double* initial_delay,
+                      const int64_t* frame_begin, const int64_t* frame_end,
+                      const double* search_center, const double* search_radius, double* out_cost,
+                      double* out_delay);
+/* Per-iteration record of the most recent rssync_sync call (delay after the step, |step|), the
+ * two numbers the reference prints to stderr (core_private.cpp:330).  Returns entries written. */
+int rssync_last_sync_trace(const rssync_problem* p, double* delays, double* steps, int cap);
+
+/* Pinned RNG of the randomised translation estimator (replaces the reference's
+ * random_device-seeded mt19937, inline_utils.hpp:13-17).  Default seed 100, call counter 0; the
+ * counter advances by one per PreSync / DebugPreSync / Sync call. */
+int rssync_set_rng(rssync_problem* p, uint64_t seed, uint64_t call_no);
+uint64_t rssync_call_counter(const rssync_problem* p);
+
+/* Run the problem's kernels on the given cudaStream_t (default: the legacy default stream). */
+int rssync_set_stream(rssync_problem* p, void* cuda_stream);
+/* Record CUDA events around the PreSync grid kernel so rssync_get_stats can report its device
+ * time (default off). */
+int rssync_set_kernel_timing(rssync_problem* p, int enabled);
+/* Push any pending host-side ray / gyro data to the device now (otherwise done lazily by the
+ * first compute call). */
+int rssync_flush(rssync_problem* p);
+
+typedef struct rssync_stats {
+    uint64_t kernel_launches;  /* kernels launched by this library (process-wide)              */
+    uint64_t h2d_bytes;        /* bytes copied host->device by this problem                     */
+    uint64_t d2h_bytes;        /* bytes copied device->host by this problem                     */
+    uint64_t frames;           /* frames currently held                                         */
+    uint64_t rays;             /* rays currently held                                           */
+    uint64_t gyro_samples;     /* samples of the (resampled) gyro track                         */
+    uint64_t sync_outer_iters; /* outer iterations of the most recent Sync / Sync batch         */
+    uint64_t sync_lbfgs_evals; /* objective evaluations inside L-BFGS, most recent Sync / batch */
+    double last_grid_kernel_ms; /* device time of the most recent PreSync grid kernel (CUDA events
+                                   on the problem's stream), 0 if timing is off                  */
+} rssync_stats;
+int rssync_get_stats(const rssync_problem* p, rssync_stats* out);
+
+/* FP64 FMA throughput of the current device in TFLOP/s (FMA = 2 flop): the measured denominator
+ * of the FP64 roofline. */
+int rssync_measure_fp64_peak(double* tflops);
+
+/* ---- stage probes: expose intermediate results of the device path for parity tests -------- */
+int rssync_probe_gyro(const rssync_problem* p, double* sample_rate, double* first_timestamp,
+                      size_t* count, double* spline_records /* count*16 or NULL */);
+int rssync_probe_problem_matrix(rssync_problem* p, int64_t frame, double delay, double* rows);
+int rssync_probe_guess_motion(rssync_problem* p, int64_t frame, double delay, int iters, int stream,
+                              uint64_t call_no, uint64_t offset_index, double* m3, double* k);
+int rssync_probe_loss(rssync_problem* p, int64_t frame, double delay, const double* m3, double k,
+                      double* loss3, double* loss5, double* grad3);
+int rssync_probe_lbfgs(rssync_problem* p, int64_t frame, double delay, double* m3, double k,
+                       double* f, int* iters, int* evals);
+int rssync_probe_log1p(const double* x, int n, double* out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* RSSYNC_B200_H */

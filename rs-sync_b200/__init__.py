@@ -1,0 +1,318 @@
+"""rs-sync_b200 — B200-native synchronisation loss engine behind rs-sync's ISyncProblem API.
+
+Python host-side mirror of the reference interface (src/core/public/rssync.h:9-31 of
+VladimirP1/rs-sync) over the C ABI in include/rssync_b200.h.  The numerical work runs in
+hand-written sm_100a kernels inside lib/librssync_b200.so; this module only marshals buffers.
+There is no CPU fallback: if the library is missing or no B200 is present the calls raise.
+
+The directory name contains a hyphen, so import it with
+    importlib.import_module("rs-sync_b200")
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "lib", "librssync_b200.so")
+
+c_double_p = C.POINTER(C.c_double)
+c_i64_p = C.POINTER(C.c_int64)
+
+OK, E_INVALID, E_NONFINITE, E_ORDER, E_STATE, E_CUDA = range(6)
+STREAM_PRESYNC, STREAM_DEBUG, STREAM_SYNCINIT = 1, 2, 3
+
+# every symbol include/rssync_b200.h declares (checked by tests/test_abi.py)
+C_ABI_SYMBOLS = [
+    "rssync_create", "rssync_destroy", "rssync_last_error", "rssync_set_gyro_fixed",
+    "rssync_set_gyro_var", "rssync_set_track", "rssync_presync", "rssync_sync",
+    "rssync_debug_presync", "rssync_presync_grid", "rssync_presync_delays", "rssync_sync_batch",
+    "rssync_last_sync_trace", "rssync_set_rng", "rssync_call_counter", "rssync_set_stream",
+    "rssync_flush", "rssync_get_stats", "rssync_measure_fp64_peak", "rssync_probe_gyro",
+    "rssync_probe_problem_matrix", "rssync_probe_guess_motion", "rssync_probe_loss",
+    "rssync_probe_lbfgs", "rssync_probe_log1p", "rssync_set_track_batch", "rssync_set_kernel_timing",
+]
+# Itanium-ABI symbols of the C++ drop-in face (same set the reference's librssync_core exports)
+CXX_ABI_SYMBOLS = [
+    "_Z17CreateSyncProblemv", "_ZN12ISyncProblemD0Ev", "_ZN12ISyncProblemD1Ev",
+    "_ZN12ISyncProblemD2Ev", "_ZTV12ISyncProblem", "_ZTI12ISyncProblem", "_ZTS12ISyncProblem",
+]
+
+
+class Stats(C.Structure):
+    _fields_ = [(n, C.c_uint64) for n in (
+        "kernel_launches", "h2d_bytes", "d2h_bytes", "frames", "rays", "gyro_samples",
+        "sync_outer_iters", "sync_lbfgs_evals")] + [("last_grid_kernel_ms", C.c_double)]
+
+
+class RsSyncError(RuntimeError):
+    def __init__(self, code, message):
+        super().__init__(f"rssync status {code}: {message}")
+        self.code = code
+        self.message = message
+
+
+_lib = None
+
+
+def load_library():
+    """dlopen the engine.  Fails loudly if it was not built (run `make lib` / __graft_entry__.build())."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise RuntimeError(f"{LIB_PATH} is missing: build it with `make lib`; there is no fallback path")
+    L = C.CDLL(LIB_PATH)
+    P = C.c_void_p
+    L.rssync_create.argtypes = [C.POINTER(P)]
+    L.rssync_destroy.argtypes = [P]
+    L.rssync_destroy.restype = None
+    L.rssync_last_error.argtypes = [P]
+    L.rssync_last_error.restype = C.c_char_p
+    L.rssync_set_gyro_fixed.argtypes = [P, c_double_p, C.c_size_t, C.c_double, C.c_double]
+    L.rssync_set_gyro_var.argtypes = [P, c_i64_p, c_double_p, C.c_size_t]
+    L.rssync_set_track.argtypes = [P, C.c_int64, c_double_p, c_double_p, c_double_p, c_double_p, C.c_size_t]
+    L.rssync_set_track_batch.argtypes = [P, C.c_size_t, c_i64_p, C.POINTER(C.c_size_t), c_double_p, c_double_p,
+                                         c_double_p, c_double_p]
+    L.rssync_set_kernel_timing.argtypes = [P, C.c_int]
+    L.rssync_presync.argtypes = [P, C.c_double, C.c_int64, C.c_int64, C.c_double, C.c_double, c_double_p, c_double_p]
+    L.rssync_sync.argtypes = [P, C.c_double, C.c_int64, C.c_int64, C.c_double, C.c_double, c_double_p, c_double_p]
+    L.rssync_debug_presync.argtypes = [P, C.c_double, C.c_int64, C.c_int64, C.c_double, c_double_p, c_double_p, C.c_int]
+    L.rssync_presync_grid.argtypes = [P, C.c_int64, C.c_int64, c_double_p, C.c_int, C.c_int, C.c_uint64,
+                                      C.c_uint64, c_double_p, C.POINTER(C.c_uint)]
+    L.rssync_presync_delays.argtypes = [C.c_double, C.c_double, C.c_double, c_double_p, C.c_int]
+    L.rssync_sync_batch.argtypes = [P, C.c_int, c_double_p, c_i64_p, c_i64_p, c_double_p, c_double_p,
+                                    c_double_p, c_double_p]
+    L.rssync_last_sync_trace.argtypes = [P, c_double_p, c_double_p, C.c_int]
+    L.rssync_set_rng.argtypes = [P, C.c_uint64, C.c_uint64]
+    L.rssync_call_counter.argtypes = [P]
+    L.rssync_call_counter.restype = C.c_uint64
+    L.rssync_set_stream.argtypes = [P, C.c_void_p]
+    L.rssync_flush.argtypes = [P]
+    L.rssync_get_stats.argtypes = [P, C.POINTER(Stats)]
+    L.rssync_measure_fp64_peak.argtypes = [c_double_p]
+    L.rssync_probe_gyro.argtypes = [P, c_double_p, c_double_p, C.POINTER(C.c_size_t), c_double_p]
+    L.rssync_probe_problem_matrix.argtypes = [P, C.c_int64, C.c_double, c_double_p]
+    L.rssync_probe_guess_motion.argtypes = [P, C.c_int64, C.c_double, C.c_int, C.c_int, C.c_uint64,
+                                            C.c_uint64, c_double_p, c_double_p]
+    L.rssync_probe_loss.argtypes = [P, C.c_int64, C.c_double, c_double_p, C.c_double, c_double_p,
+                                    c_double_p, c_double_p]
+    L.rssync_probe_lbfgs.argtypes = [P, C.c_int64, C.c_double, c_double_p, C.c_double, c_double_p,
+                                     C.POINTER(C.c_int), C.POINTER(C.c_int)]
+    L.rssync_probe_log1p.argtypes = [c_double_p, C.c_int, c_double_p]
+    _lib = L
+    return L
+
+
+def _f64(a):
+    return np.ascontiguousarray(a, dtype=np.float64)
+
+
+def _dp(a):
+    return a.ctypes.data_as(c_double_p)
+
+
+def presync_delays(initial_delay, search_step, search_radius):
+    """pre_sync's delay grid (core_private.cpp:69-70), floating-point accumulation included."""
+    L = load_library()
+    n = L.rssync_presync_delays(initial_delay, search_step, search_radius, None, 0)
+    out = np.empty(n)
+    L.rssync_presync_delays(initial_delay, search_step, search_radius, _dp(out), n)
+    return out
+
+
+def measure_fp64_peak():
+    L = load_library()
+    v = C.c_double()
+    rc = L.rssync_measure_fp64_peak(C.byref(v))
+    if rc != OK:
+        raise RsSyncError(rc, "FP64 peak measurement failed (no CUDA device?)")
+    return v.value
+
+
+def probe_log1p(x):
+    L = load_library()
+    x = _f64(x)
+    out = np.empty_like(x)
+    rc = L.rssync_probe_log1p(_dp(x), x.size, _dp(out))
+    if rc != OK:
+        raise RsSyncError(rc, "log1p probe failed")
+    return out
+
+
+class SyncProblem:
+    """ISyncProblem (rssync.h:9-29): same method names, argument order and return values
+    ({cost, delay} pairs).  Errors that make the reference write panic.txt and exit raise
+    RsSyncError carrying the same message."""
+
+    def __init__(self, seed=100):
+        self.L = load_library()
+        self.h = C.c_void_p()
+        rc = self.L.rssync_create(C.byref(self.h))
+        if rc != OK:
+            msg = self.L.rssync_last_error(self.h).decode() if self.h else "no usable CUDA device (no CPU fallback)"
+            raise RsSyncError(rc, msg)
+        self.L.rssync_set_rng(self.h, seed, 0)
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.L.rssync_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, rc):
+        if rc != OK:
+            raise RsSyncError(rc, self.L.rssync_last_error(self.h).decode())
+
+    # ---- reference interface ----------------------------------------------------------------
+    def SetGyroQuaternions(self, *args):
+        """(data, count, sample_rate, first_timestamp)  rssync.h:13-14, or
+        (timestamps_us, quats, count)                 rssync.h:15-16."""
+        if len(args) == 4:
+            data, count, rate, first = args
+            data = _f64(data)
+            self._check(self.L.rssync_set_gyro_fixed(self.h, _dp(data), count, rate, first))
+        elif len(args) == 3:
+            ts, quats, count = args
+            ts = np.ascontiguousarray(ts, dtype=np.int64)
+            quats = _f64(quats)
+            self._check(self.L.rssync_set_gyro_var(self.h, ts.ctypes.data_as(c_i64_p), _dp(quats), count))
+        else:
+            raise TypeError("SetGyroQuaternions takes 3 or 4 arguments")
+
+    def SetTrackResult(self, frame, ts_a, ts_b, rays_a, rays_b, count):
+        a = [_f64(x) for x in (ts_a, ts_b, rays_a, rays_b)]
+        self._check(self.L.rssync_set_track(self.h, int(frame), _dp(a[0]), _dp(a[1]), _dp(a[2]), _dp(a[3]), count))
+
+    def PreSync(self, initial_delay, frame_begin, frame_end, search_step, search_radius):
+        c, d = C.c_double(), C.c_double()
+        self._check(self.L.rssync_presync(self.h, initial_delay, frame_begin, frame_end, search_step,
+                                          search_radius, C.byref(c), C.byref(d)))
+        return c.value, d.value
+
+    def Sync(self, initial_delay, frame_begin, frame_end, search_center, search_radius):
+        c, d = C.c_double(), C.c_double()
+        self._check(self.L.rssync_sync(self.h, initial_delay, frame_begin, frame_end, search_center,
+                                       search_radius, C.byref(c), C.byref(d)))
+        return c.value, d.value
+
+    def DebugPreSync(self, initial_delay, frame_begin, frame_end, search_radius, point_count):
+        delays = np.empty(point_count)
+        costs = np.empty(point_count)
+        self._check(self.L.rssync_debug_presync(self.h, initial_delay, frame_begin, frame_end, search_radius,
+                                                _dp(delays), _dp(costs), point_count))
+        return delays, costs
+
+    # ---- extensions -------------------------------------------------------------------------
+    def set_track_batch(self, frames, counts, ts_a, ts_b, rays_a, rays_b):
+        """Bulk SetTrackResult: per-frame buffers concatenated in `frames` order."""
+        frames = np.ascontiguousarray(frames, dtype=np.int64)
+        counts = np.ascontiguousarray(counts, dtype=np.uint64)
+        a = [_f64(x) for x in (ts_a, ts_b, rays_a, rays_b)]
+        self._check(self.L.rssync_set_track_batch(
+            self.h, frames.shape[0], frames.ctypes.data_as(c_i64_p),
+            counts.ctypes.data_as(C.POINTER(C.c_size_t)), _dp(a[0]), _dp(a[1]), _dp(a[2]), _dp(a[3])))
+
+    def load(self, w, bulk=False):
+        """Feed a synth.Workload the way core_testcode feeds a video (core_testcode.cpp:257-268)."""
+        self.SetGyroQuaternions(w.quats, w.quats.shape[0], w.gyro_rate, w.gyro_t0)
+        n = w.ts_a.shape[1]
+        if bulk:
+            self.set_track_batch(w.frame_ids, np.full(w.n_frames, n), w.ts_a, w.ts_b, w.rays_a, w.rays_b)
+            return self
+        for i, fid in enumerate(w.frame_ids):
+            self.SetTrackResult(int(fid), w.ts_a[i], w.ts_b[i], w.rays_a[i], w.rays_b[i], n)
+        return self
+
+    def set_kernel_timing(self, enabled=True):
+        self._check(self.L.rssync_set_kernel_timing(self.h, 1 if enabled else 0))
+
+    def set_rng(self, seed, call_no=0):
+        self._check(self.L.rssync_set_rng(self.h, seed, call_no))
+
+    def call_counter(self):
+        return self.L.rssync_call_counter(self.h)
+
+    def set_stream(self, cuda_stream):
+        self._check(self.L.rssync_set_stream(self.h, C.c_void_p(cuda_stream)))
+
+    def flush(self):
+        self._check(self.L.rssync_flush(self.h))
+
+    def presync_grid(self, frame_begin, frame_end, delays, stream=STREAM_PRESYNC, call_no=0,
+                     offset_index_base=0, return_flags=False):
+        delays = _f64(delays)
+        costs = np.empty(delays.shape[0])
+        flags = C.c_uint()
+        self._check(self.L.rssync_presync_grid(self.h, frame_begin, frame_end, _dp(delays), delays.shape[0],
+                                               stream, call_no, offset_index_base, _dp(costs), C.byref(flags)))
+        return (costs, flags.value) if return_flags else costs
+
+    def sync_batch(self, initial_delay, frame_begin, frame_end, search_center, search_radius):
+        ini = _f64(initial_delay)
+        n = ini.shape[0]
+        fb = np.ascontiguousarray(frame_begin, dtype=np.int64)
+        fe = np.ascontiguousarray(frame_end, dtype=np.int64)
+        cen = _f64(np.broadcast_to(search_center, (n,)))
+        rad = _f64(np.broadcast_to(search_radius, (n,)))
+        cost, delay = np.empty(n), np.empty(n)
+        self._check(self.L.rssync_sync_batch(self.h, n, _dp(ini), fb.ctypes.data_as(c_i64_p),
+                                             fe.ctypes.data_as(c_i64_p), _dp(cen), _dp(rad), _dp(cost), _dp(delay)))
+        return cost, delay
+
+    def last_sync_trace(self):
+        n = self.L.rssync_last_sync_trace(self.h, None, None, 0)
+        d, s = np.empty(n), np.empty(n)
+        self.L.rssync_last_sync_trace(self.h, _dp(d), _dp(s), n)
+        return d, s
+
+    def stats(self):
+        s = Stats()
+        self._check(self.L.rssync_get_stats(self.h, C.byref(s)))
+        return {k: getattr(s, k) for k, _ in Stats._fields_}
+
+    # ---- probes (parity tests) --------------------------------------------------------------
+    def probe_gyro(self):
+        sr, q0, n = C.c_double(), C.c_double(), C.c_size_t()
+        self._check(self.L.rssync_probe_gyro(self.h, C.byref(sr), C.byref(q0), C.byref(n), None))
+        rec = np.empty((n.value, 16))
+        self._check(self.L.rssync_probe_gyro(self.h, None, None, None, _dp(rec)))
+        return sr.value, q0.value, rec
+
+    def probe_problem_matrix(self, frame, delay, n):
+        P = np.empty((n, 3))
+        self._check(self.L.rssync_probe_problem_matrix(self.h, frame, delay, _dp(P)))
+        return P
+
+    def probe_guess_motion(self, frame, delay, iters, stream, call_no, offset_index):
+        m = np.empty(3)
+        k = C.c_double()
+        self._check(self.L.rssync_probe_guess_motion(self.h, frame, delay, iters, stream, call_no, offset_index,
+                                                     _dp(m), C.byref(k)))
+        return m, k.value
+
+    def probe_loss(self, frame, delay, m, k):
+        m = _f64(m)
+        l3, l5 = C.c_double(), C.c_double()
+        g = np.empty(3)
+        self._check(self.L.rssync_probe_loss(self.h, frame, delay, _dp(m), k, C.byref(l3), C.byref(l5), _dp(g)))
+        return l3.value, l5.value, g
+
+    def probe_lbfgs(self, frame, delay, m, k):
+        m = np.array(m, dtype=np.float64)
+        f = C.c_double()
+        it, ev = C.c_int(), C.c_int()
+        self._check(self.L.rssync_probe_lbfgs(self.h, frame, delay, _dp(m), k, C.byref(f), C.byref(it), C.byref(ev)))
+        return m, f.value, it.value, ev.value
+
+
+def CreateSyncProblem(seed=100):
+    """CreateSyncProblem(), rssync.h:31."""
+    return SyncProblem(seed=seed)

@@ -1,0 +1,790 @@
+// C ABI of the engine (include/rssync_b200.h): problem state, host->device staging, kernel
+// launches, and the host-side control loop of Sync.  Everything numerical on the hot path runs
+// in engine.cu; this file holds what the reference keeps in OptData / SyncProblemPrivate
+// (core_private.hpp:15-61) plus the solver's irregular iteration control, which stays on the
+// host (Backtrack, backtrack.cpp:3-13; momentum loop, core_private.cpp:298-331).
+#include "rssync_b200.h"
+
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+#include <map>
+#include <string>
+#include <vector>
+
+#include "engine.h"
+#include "host_ingest.h"
+#include "rng.h"
+
+using rs::FrameDesc;
+
+namespace {
+
+#define CUDA_TRY(p, expr)                                                                 \
+    do {                                                                                  \
+        cudaError_t e__ = (expr);                                                         \
+        if (e__ != cudaSuccess) {                                                         \
+            (p)->err = std::string("CUDA error: ") + cudaGetErrorString(e__) + " at " #expr; \
+            return RSSYNC_E_CUDA;                                                         \
+        }                                                                                 \
+    } while (0)
+
+// growable device buffer
+template <class T>
+struct DevBuf {
+    T* ptr = nullptr;
+    size_t cap = 0;
+    cudaError_t reserve(size_t n) {
+        if (n <= cap) return cudaSuccess;
+        if (ptr) cudaFree(ptr);
+        ptr = nullptr;
+        size_t want = std::max(n, cap * 2);
+        cudaError_t e = cudaMalloc((void**)&ptr, want * sizeof(T));
+        cap = (e == cudaSuccess) ? want : 0;
+        return e;
+    }
+    void release() {
+        if (ptr) cudaFree(ptr);
+        ptr = nullptr;
+        cap = 0;
+    }
+};
+
+// growable pinned host buffer
+template <class T>
+struct PinBuf {
+    T* ptr = nullptr;
+    size_t cap = 0;
+    cudaError_t reserve(size_t n, size_t keep = 0) {
+        if (n <= cap) return cudaSuccess;
+        size_t want = std::max(n, cap * 2);
+        T* np = nullptr;
+        cudaError_t e = cudaHostAlloc((void**)&np, want * sizeof(T), cudaHostAllocDefault);
+        if (e != cudaSuccess) return e;
+        if (ptr && keep) std::memcpy(np, ptr, keep * sizeof(T));
+        if (ptr) cudaFreeHost(ptr);
+        ptr = np;
+        cap = want;
+        return cudaSuccess;
+    }
+    void release() {
+        if (ptr) cudaFreeHost(ptr);
+        ptr = nullptr;
+        cap = 0;
+    }
+};
+
+bool all_finite(const double* p, size_t n) {
+    for (size_t i = 0; i < n; ++i)
+        if (!std::isfinite(p[i])) return false;
+    return true;
+}
+
+}  // namespace
+
+struct rssync_problem {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    std::string err;
+
+    // gyro spline (OptData::quats, quats_start, sample_rate)
+    std::vector<double> rec;
+    double q0 = 0.0, sr = 0.0;
+    size_t nq = 0;
+    bool gyro_dirty = false;
+    DevBuf<double> d_rec;
+
+    // ray arena: 8 SoA planes, frames appended in arrival order, each padded to 32 entries
+    PinBuf<double> h_plane[8];
+    DevBuf<double> d_plane[8];
+    size_t used = 0, uploaded = 0, garbage = 0;
+    bool rays_full_dirty = false;
+    std::map<int64_t, FrameDesc> frames;  // OptData::frame_data
+    size_t total_rays = 0;
+
+    uint64_t seed = 100, call_no = 0;
+
+    // scratch
+    DevBuf<FrameDesc> d_frames;
+    DevBuf<double> d_delays, d_framecost, d_costs;
+    DevBuf<unsigned> d_flags;
+    PinBuf<double> h_stage;
+    // sync scratch
+    DevBuf<rs::SyncTask> d_tasks;
+    DevBuf<int> d_sp_begin, d_lbfgs_stats;
+    DevBuf<double> d_m, d_k, d_task_scratch, d_sp_delay, d_sp_x0, d_trial_delay, d_out_v, d_out_g,
+        d_out_trials;
+    DevBuf<uint64_t> d_sp_callno;
+    DevBuf<unsigned char> d_sp_active;
+    DevBuf<double> d_probe;
+
+    std::vector<double> trace_delay, trace_step;
+    uint64_t h2d = 0, d2h = 0, sync_outer = 0, sync_evals = 0;
+    bool kernel_timing = false;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    double last_grid_ms = 0.0;
+
+    rs::DeviceData device_data() const {
+        rs::DeviceData dd;
+        dd.rec = d_rec.ptr;
+        dd.nq = (int)nq;
+        dd.q0 = q0;
+        dd.sr = sr;
+        for (int i = 0; i < 8; ++i) dd.plane[i] = d_plane[i].ptr;
+        return dd;
+    }
+};
+
+namespace {
+
+int h2d(rssync_problem* p, void* dst, const void* src, size_t bytes) {
+    if (!bytes) return RSSYNC_OK;
+    CUDA_TRY(p, cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, p->stream));
+    p->h2d += bytes;
+    return RSSYNC_OK;
+}
+int d2h(rssync_problem* p, void* dst, const void* src, size_t bytes) {
+    if (!bytes) return RSSYNC_OK;
+    CUDA_TRY(p, cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, p->stream));
+    p->d2h += bytes;
+    return RSSYNC_OK;
+}
+
+int flush(rssync_problem* p) {
+    CUDA_TRY(p, cudaSetDevice(p->device));
+    if (p->gyro_dirty) {
+        CUDA_TRY(p, p->d_rec.reserve(p->rec.size()));
+        // the spline vector is pageable; the copy is staged by the runtime
+        if (int rc = h2d(p, p->d_rec.ptr, p->rec.data(), p->rec.size() * sizeof(double))) return rc;
+        p->gyro_dirty = false;
+    }
+    if (p->used > p->uploaded || p->rays_full_dirty) {
+        bool regrow = p->d_plane[0].cap < p->used;
+        size_t from = (regrow || p->rays_full_dirty) ? 0 : p->uploaded;
+        for (int i = 0; i < 8; ++i) {
+            CUDA_TRY(p, p->d_plane[i].reserve(p->h_plane[i].cap));
+            if (int rc = h2d(p, p->d_plane[i].ptr + from, p->h_plane[i].ptr + from,
+                             (p->used - from) * sizeof(double)))
+                return rc;
+        }
+        p->uploaded = p->used;
+        p->rays_full_dirty = false;
+    }
+    return RSSYNC_OK;
+}
+
+// frames with begin <= id < end_exclusive, ascending id
+int select_frames(rssync_problem* p, int64_t begin, int64_t end_exclusive,
+                  std::vector<FrameDesc>& out, int& max_n, const char* who) {
+    out.clear();
+    max_n = 0;
+    for (auto it = p->frames.lower_bound(begin); it != p->frames.end() && it->first < end_exclusive; ++it) {
+        const FrameDesc& fd = it->second;
+        if (fd.n < 2) {
+            p->err = std::string(who) + ": frame " + std::to_string(fd.id) + " has fewer than 2 rays";
+            return RSSYNC_E_INVALID;
+        }
+        out.push_back(fd);
+        max_n = std::max(max_n, (int)fd.n);
+    }
+    return RSSYNC_OK;
+}
+
+int require_gyro(rssync_problem* p, const char* who) {
+    if (p->nq < 2) {
+        p->err = std::string(who) + ": gyro quaternions have not been set";
+        return RSSYNC_E_STATE;
+    }
+    return RSSYNC_OK;
+}
+
+int presync_grid_impl(rssync_problem* p, int64_t fb, int64_t fe, const double* delays, int n,
+                      uint64_t stream_id, uint64_t call_no, uint64_t idx_base, double* costs,
+                      unsigned* flags_out) {
+    if (int rc = require_gyro(p, "pre-sync")) return rc;
+    if (n < 0) { p->err = "pre-sync: negative delay count"; return RSSYNC_E_INVALID; }
+    if (flags_out) *flags_out = 0;
+    if (n == 0) return RSSYNC_OK;
+    std::vector<FrameDesc> sel;
+    int max_n = 0;
+    if (int rc = select_frames(p, fb, fe, sel, max_n, "pre-sync")) return rc;
+    if (int rc = flush(p)) return rc;
+    const int F = (int)sel.size();
+    if (F == 0) {  // the reference sums over no frames: cost 0 for every delay
+        std::fill(costs, costs + n, 0.0);
+        return RSSYNC_OK;
+    }
+    if ((long long)F * n > (1LL << 40)) { p->err = "pre-sync: grid too large"; return RSSYNC_E_INVALID; }
+    CUDA_TRY(p, p->d_frames.reserve(F));
+    CUDA_TRY(p, p->d_delays.reserve(n));
+    CUDA_TRY(p, p->d_framecost.reserve((size_t)F * n));
+    CUDA_TRY(p, p->d_costs.reserve(n));
+    CUDA_TRY(p, p->d_flags.reserve(1));
+    if (int rc = h2d(p, p->d_frames.ptr, sel.data(), sizeof(FrameDesc) * F)) return rc;
+    if (int rc = h2d(p, p->d_delays.ptr, delays, sizeof(double) * n)) return rc;
+    CUDA_TRY(p, cudaMemsetAsync(p->d_flags.ptr, 0, sizeof(unsigned), p->stream));
+    rs::launch_presync_grid(p->device_data(), p->d_frames.ptr, F, max_n, p->d_delays.ptr, n, p->seed,
+                            stream_id, call_no, idx_base, p->d_framecost.ptr, p->d_costs.ptr,
+                            p->d_flags.ptr, p->stream, p->kernel_timing ? p->ev0 : nullptr,
+                            p->kernel_timing ? p->ev1 : nullptr);
+    CUDA_TRY(p, cudaGetLastError());
+    unsigned flags = 0;
+    if (int rc = d2h(p, costs, p->d_costs.ptr, sizeof(double) * n)) return rc;
+    if (int rc = d2h(p, &flags, p->d_flags.ptr, sizeof(unsigned))) return rc;
+    CUDA_TRY(p, cudaStreamSynchronize(p->stream));
+    if (p->kernel_timing) {
+        float ms = 0.f;
+        if (cudaEventElapsedTime(&ms, p->ev0, p->ev1) == cudaSuccess) p->last_grid_ms = ms;
+    }
+    if (flags_out) *flags_out = flags;
+    return RSSYNC_OK;
+}
+
+// ---- Sync: host control loop over a batch of syncpoints ---------------------------------------
+struct SyncPointState {
+    double delay, v = 0.0, center, radius;
+    int converge = 0;
+    bool done = false;
+};
+
+int sync_batch_impl(rssync_problem* p, int n, const double* initial, const int64_t* fb,
+                    const int64_t* fe, const double* center, const double* radius, double* out_cost,
+                    double* out_delay, bool record_trace) {
+    if (int rc = require_gyro(p, "sync")) return rc;
+    if (n <= 0) return RSSYNC_OK;
+    // tasks: frames frame_begin <= f <= frame_end, INCLUSIVE (core_private.cpp:219)
+    std::vector<rs::SyncTask> tasks;
+    std::vector<int> sp_begin(n + 1, 0);
+    int max_n = 0;
+    std::vector<FrameDesc> sel;
+    for (int s = 0; s < n; ++s) {
+        int mn = 0;
+        if (fe[s] == INT64_MAX) { p->err = "sync: frame_end out of range"; return RSSYNC_E_INVALID; }
+        if (int rc = select_frames(p, fb[s], fe[s] + 1, sel, mn, "sync")) return rc;
+        max_n = std::max(max_n, mn);
+        for (const FrameDesc& fd : sel) tasks.push_back(rs::SyncTask{fd, s, 0});
+        sp_begin[s + 1] = (int)tasks.size();
+    }
+    if (int rc = flush(p)) return rc;
+    const int T = (int)tasks.size();
+    constexpr int kTrials = 10;  // Backtrack max_iterations, core_private.cpp:226
+    std::vector<uint64_t> callno(n);
+    for (int s = 0; s < n; ++s) callno[s] = p->call_no + (uint64_t)s;
+    p->call_no += (uint64_t)n;
+
+    CUDA_TRY(p, p->d_tasks.reserve(std::max(T, 1)));
+    CUDA_TRY(p, p->d_sp_begin.reserve(n + 1));
+    CUDA_TRY(p, p->d_m.reserve((size_t)std::max(T, 1) * 3));
+    CUDA_TRY(p, p->d_k.reserve(std::max(T, 1)));
+    CUDA_TRY(p, p->d_task_scratch.reserve((size_t)std::max(T, 1) * kTrials));
+    CUDA_TRY(p, p->d_lbfgs_stats.reserve((size_t)std::max(T, 1) * 2));
+    CUDA_TRY(p, p->d_sp_delay.reserve(n));
+    CUDA_TRY(p, p->d_sp_x0.reserve(n));
+    CUDA_TRY(p, p->d_sp_callno.reserve(n));
+    CUDA_TRY(p, p->d_sp_active.reserve(n));
+    CUDA_TRY(p, p->d_trial_delay.reserve((size_t)n * kTrials));
+    CUDA_TRY(p, p->d_out_v.reserve(n));
+    CUDA_TRY(p, p->d_out_g.reserve(n));
+    CUDA_TRY(p, p->d_out_trials.reserve((size_t)n * kTrials));
+    if (int rc = h2d(p, p->d_tasks.ptr, tasks.data(), sizeof(rs::SyncTask) * T)) return rc;
+    if (int rc = h2d(p, p->d_sp_begin.ptr, sp_begin.data(), sizeof(int) * (n + 1))) return rc;
+    if (int rc = h2d(p, p->d_sp_callno.ptr, callno.data(), sizeof(uint64_t) * n)) return rc;
+
+    rs::SyncBatchDev b;
+    b.tasks = p->d_tasks.ptr;
+    b.T = T;
+    b.max_n = max_n;
+    b.sp_begin = p->d_sp_begin.ptr;
+    b.S = n;
+    b.m = p->d_m.ptr;
+    b.k = p->d_k.ptr;
+    const rs::DeviceData dd = p->device_data();
+
+    std::vector<SyncPointState> st(n);
+    std::vector<double> h_delay(n), h_x0(n), h_v(n), h_g(n), h_trial((size_t)n * kTrials),
+        h_trial_out((size_t)n * kTrials);
+    std::vector<unsigned char> h_active(n, 1);
+    std::vector<int> h_stats((size_t)std::max(T, 1) * 2);
+    for (int s = 0; s < n; ++s) {
+        st[s].delay = initial[s];
+        st[s].center = center[s];
+        st[s].radius = radius[s];
+        h_delay[s] = initial[s];
+    }
+    if (record_trace) { p->trace_delay.clear(); p->trace_step.clear(); }
+    p->sync_outer = 0;
+    p->sync_evals = 0;
+
+    // GuessMotion / GuessK for every frame (core_private.cpp:218-223)
+    if (int rc = h2d(p, p->d_sp_delay.ptr, h_delay.data(), sizeof(double) * n)) return rc;
+    if (int rc = h2d(p, p->d_sp_active.ptr, h_active.data(), n)) return rc;
+    rs::launch_sync_init(dd, b, p->d_sp_delay.ptr, p->d_sp_callno.ptr, p->d_sp_active.ptr, p->seed,
+                         p->stream);
+    CUDA_TRY(p, cudaGetLastError());
+
+    const double delay_b = .3;  // :260
+    for (int it = 0; it < 400; ++it) {  // :309
+        int n_active = 0;
+        for (int s = 0; s < n; ++s) {
+            h_active[s] = st[s].done ? 0 : 1;
+            n_active += h_active[s];
+            h_delay[s] = st[s].delay;
+            h_x0[s] = st[s].delay - delay_b * st[s].v;  // :299
+        }
+        if (!n_active) break;
+        p->sync_outer++;
+        if (int rc = h2d(p, p->d_sp_delay.ptr, h_delay.data(), sizeof(double) * n)) return rc;
+        if (int rc = h2d(p, p->d_sp_x0.ptr, h_x0.data(), sizeof(double) * n)) return rc;
+        if (int rc = h2d(p, p->d_sp_active.ptr, h_active.data(), n)) return rc;
+        // do_opt_motion (:262-296) + f_and_grad at x0 (:228-240)
+        rs::launch_sync_motion_fgrad(dd, b, p->d_sp_delay.ptr, p->d_sp_x0.ptr, p->d_sp_active.ptr,
+                                     p->d_task_scratch.ptr, p->d_out_v.ptr, p->d_out_g.ptr,
+                                     p->d_lbfgs_stats.ptr, p->stream);
+        CUDA_TRY(p, cudaGetLastError());
+        if (int rc = d2h(p, h_v.data(), p->d_out_v.ptr, sizeof(double) * n)) return rc;
+        if (int rc = d2h(p, h_g.data(), p->d_out_g.ptr, sizeof(double) * n)) return rc;
+        if (int rc = d2h(p, h_stats.data(), p->d_lbfgs_stats.ptr, sizeof(int) * 2 * T)) return rc;
+        CUDA_TRY(p, cudaStreamSynchronize(p->stream));
+        for (int t = 0; t < T; ++t)
+            if (h_active[tasks[t].sp]) p->sync_evals += (uint64_t)h_stats[2 * t + 1];
+        // Backtrack::Step (backtrack.cpp:3-13): all trial points are known once the gradient
+        // is, so they are evaluated in one launch and the first that passes is taken.
+        for (int s = 0; s < n; ++s) {
+            double t = 1e-3;
+            for (int i = 0; i < kTrials; ++i) {
+                h_trial[(size_t)s * kTrials + i] = h_x0[s] - t * h_g[s];
+                t *= .1;
+            }
+        }
+        if (int rc = h2d(p, p->d_trial_delay.ptr, h_trial.data(), sizeof(double) * n * kTrials)) return rc;
+        rs::launch_sync_trials(dd, b, p->d_trial_delay.ptr, kTrials, p->d_sp_active.ptr,
+                               p->d_task_scratch.ptr, p->d_out_trials.ptr, p->stream);
+        CUDA_TRY(p, cudaGetLastError());
+        if (int rc = d2h(p, h_trial_out.data(), p->d_out_trials.ptr, sizeof(double) * n * kTrials)) return rc;
+        CUDA_TRY(p, cudaStreamSynchronize(p->stream));
+        for (int s = 0; s < n; ++s) {
+            if (st[s].done) continue;
+            const double v = h_v[s], g = h_g[s];
+            const double mm = g * g;
+            double t = 1e-3;
+            for (int i = 0; i < kTrials; ++i) {
+                const double v1 = h_trial_out[(size_t)s * kTrials + i];
+                if (v - v1 >= t * 2e-4 * mm) break;
+                t *= .1;
+            }
+            const double step = -t * g;
+            st[s].v = delay_b * st[s].v + step;  // :301
+            st[s].delay += st[s].v;              // :302
+            const double step_size = std::fabs(step);
+            if (record_trace && s == 0) {
+                p->trace_delay.push_back(st[s].delay);
+                p->trace_step.push_back(step_size);
+            }
+            if (step_size < 1e-4) st[s].converge++; else st[s].converge = 0;  // :316-320
+            if (st[s].converge > 5) st[s].done = true;                        // :322
+            if (std::fabs(st[s].delay - st[s].center) > st[s].radius) st[s].done = true;  // :326
+        }
+    }
+    // {simple_objective(gyro_delay), gyro_delay}  (:333)
+    for (int s = 0; s < n; ++s) { h_active[s] = 1; h_delay[s] = st[s].delay; }
+    if (int rc = h2d(p, p->d_sp_active.ptr, h_active.data(), n)) return rc;
+    if (int rc = h2d(p, p->d_trial_delay.ptr, h_delay.data(), sizeof(double) * n)) return rc;
+    rs::launch_sync_trials(dd, b, p->d_trial_delay.ptr, 1, p->d_sp_active.ptr, p->d_task_scratch.ptr,
+                           p->d_out_trials.ptr, p->stream);
+    CUDA_TRY(p, cudaGetLastError());
+    if (T > 0) {
+        if (int rc = d2h(p, out_cost, p->d_out_trials.ptr, sizeof(double) * n)) return rc;
+    } else {
+        std::fill(out_cost, out_cost + n, 0.0);
+    }
+    CUDA_TRY(p, cudaStreamSynchronize(p->stream));
+    for (int s = 0; s < n; ++s) {
+        if (sp_begin[s + 1] == sp_begin[s]) out_cost[s] = 0.0;
+        out_delay[s] = st[s].delay;
+    }
+    return RSSYNC_OK;
+}
+
+}  // namespace
+
+// =============================================================================================
+extern "C" {
+
+int rssync_create(rssync_problem** out) {
+    if (!out) return RSSYNC_E_INVALID;
+    *out = nullptr;
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return RSSYNC_E_CUDA;
+    int cc_major = 0;
+    if (cudaDeviceGetAttribute(&cc_major, cudaDevAttrComputeCapabilityMajor, dev) != cudaSuccess)
+        return RSSYNC_E_CUDA;
+    rssync_problem* p = new rssync_problem();
+    p->device = dev;
+    *out = p;
+    if (cc_major < 10) {
+        p->err = "rssync_b200 needs an sm_100a (Blackwell B200) device; there is no CPU or other-GPU fallback";
+        return RSSYNC_E_CUDA;
+    }
+    return RSSYNC_OK;
+}
+
+void rssync_destroy(rssync_problem* p) {
+    if (!p) return;
+    cudaSetDevice(p->device);
+    p->d_rec.release();
+    for (int i = 0; i < 8; ++i) { p->h_plane[i].release(); p->d_plane[i].release(); }
+    p->d_frames.release(); p->d_delays.release(); p->d_framecost.release(); p->d_costs.release();
+    p->d_flags.release(); p->h_stage.release(); p->d_tasks.release(); p->d_sp_begin.release();
+    p->d_lbfgs_stats.release(); p->d_m.release(); p->d_k.release(); p->d_task_scratch.release();
+    p->d_sp_delay.release(); p->d_sp_x0.release(); p->d_trial_delay.release(); p->d_out_v.release();
+    p->d_out_g.release(); p->d_out_trials.release(); p->d_sp_callno.release();
+    p->d_sp_active.release(); p->d_probe.release();
+    if (p->ev0) cudaEventDestroy(p->ev0);
+    if (p->ev1) cudaEventDestroy(p->ev1);
+    delete p;
+}
+
+const char* rssync_last_error(const rssync_problem* p) { return p ? p->err.c_str() : "null problem"; }
+
+int rssync_set_gyro_fixed(rssync_problem* p, const double* quats, size_t count, double sample_rate,
+                          double first_timestamp) {
+    if (!p || !quats) return RSSYNC_E_INVALID;
+    if (count < 2) { p->err = "set-gyro-quaternions: need at least 2 samples"; return RSSYNC_E_INVALID; }
+    if (count > (size_t)INT32_MAX) { p->err = "set-gyro-quaternions: too many samples"; return RSSYNC_E_INVALID; }
+    p->sr = sample_rate;       // core_private.cpp:137
+    p->q0 = first_timestamp;   // :138
+    rs::build_spline_records(quats, count, p->rec);  // :139
+    p->nq = count;
+    p->gyro_dirty = true;
+    return RSSYNC_OK;
+}
+
+int rssync_set_gyro_var(rssync_problem* p, const int64_t* ts, const double* quats, size_t count) {
+    if (!p || !ts || !quats) return RSSYNC_E_INVALID;
+    std::vector<double> rq;
+    double sr = 0, q0 = 0;
+    rs::IngestStatus s = rs::resample_variable_rate(ts, quats, count, rq, sr, q0, p->err);
+    if (s == rs::IngestStatus::Invalid) return RSSYNC_E_INVALID;
+    if (s == rs::IngestStatus::NonFinite) return RSSYNC_E_NONFINITE;
+    if (s == rs::IngestStatus::OutOfOrder) return RSSYNC_E_ORDER;
+    if (rq.size() / 4 > (size_t)INT32_MAX) { p->err = "set-gyro-quaternions: too many samples"; return RSSYNC_E_INVALID; }
+    p->sr = sr;
+    p->q0 = q0;
+    rs::build_spline_records(rq.data(), rq.size() / 4, p->rec);  // :189
+    p->nq = rq.size() / 4;
+    p->gyro_dirty = true;
+    return RSSYNC_OK;
+}
+
+int rssync_set_track(rssync_problem* p, int64_t frame, const double* ts_a, const double* ts_b,
+                     const double* rays_a, const double* rays_b, size_t count) {
+    if (!p) return RSSYNC_E_INVALID;
+    if (count && (!ts_a || !ts_b || !rays_a || !rays_b)) { p->err = "set-track-result: null buffer"; return RSSYNC_E_INVALID; }
+    if (count > (size_t)rs::kMaxRaysPerFrame) {
+        p->err = "set-track-result: more than " + std::to_string(rs::kMaxRaysPerFrame) + " rays in one frame is not supported";
+        return RSSYNC_E_INVALID;
+    }
+    // panic conditions, in the reference's order (core_private.cpp:199-202)
+    if (!all_finite(rays_a, 3 * count)) { p->err = "set-track-result: non-finite numbers in rays_a"; return RSSYNC_E_NONFINITE; }
+    if (!all_finite(rays_b, 3 * count)) { p->err = "set-track-result: non-finite numbers in rays_b"; return RSSYNC_E_NONFINITE; }
+    if (!all_finite(ts_a, count)) { p->err = "set-track-result: non-finite numbers in ts_a"; return RSSYNC_E_NONFINITE; }
+    if (!all_finite(ts_b, count)) { p->err = "set-track-result: non-finite numbers in ts_b"; return RSSYNC_E_NONFINITE; }
+    const size_t padded = (count + 31) / 32 * 32;
+    size_t off;
+    auto it = p->frames.find(frame);
+    if (it != p->frames.end() && (size_t)((it->second.n + 31) / 32 * 32) == padded) {
+        off = (size_t)it->second.off;  // replace in place
+        if (off < p->uploaded) p->rays_full_dirty = true;
+        p->total_rays -= (size_t)it->second.n;
+    } else {
+        if (it != p->frames.end()) {
+            p->garbage += (size_t)(it->second.n + 31) / 32 * 32;
+            p->total_rays -= (size_t)it->second.n;
+        }
+        off = p->used;
+        if (off + padded > (size_t)INT32_MAX) { p->err = "set-track-result: ray arena full"; return RSSYNC_E_INVALID; }
+        const size_t need = off + padded;
+        if (need > p->h_plane[0].cap) {
+            const size_t want = std::max<size_t>(need, std::max<size_t>(p->h_plane[0].cap * 2, 1u << 16));
+            cudaSetDevice(p->device);
+            for (int i = 0; i < 8; ++i) CUDA_TRY(p, p->h_plane[i].reserve(want, p->used));
+        }
+        p->used = need;
+    }
+    double* pl[8];
+    for (int i = 0; i < 8; ++i) pl[i] = p->h_plane[i].ptr + off;
+    for (size_t i = 0; i < count; ++i) {
+        pl[0][i] = ts_a[i];
+        pl[1][i] = ts_b[i];
+        pl[2][i] = rays_a[3 * i]; pl[3][i] = rays_a[3 * i + 1]; pl[4][i] = rays_a[3 * i + 2];
+        pl[5][i] = rays_b[3 * i]; pl[6][i] = rays_b[3 * i + 1]; pl[7][i] = rays_b[3 * i + 2];
+    }
+    for (size_t i = count; i < padded; ++i) {  // padding lanes: finite, masked out by n
+        pl[0][i] = count ? ts_a[0] : 0.0;
+        pl[1][i] = count ? ts_b[0] : 0.0;
+        for (int c = 2; c < 8; ++c) pl[c][i] = 0.0;
+    }
+    p->frames[frame] = FrameDesc{frame, (int32_t)off, (int32_t)count};
+    p->total_rays += count;
+    return RSSYNC_OK;
+}
+
+int rssync_set_track_batch(rssync_problem* p, size_t n_frames, const int64_t* frames,
+                           const size_t* counts, const double* ts_a, const double* ts_b,
+                           const double* rays_a, const double* rays_b) {
+    if (!p || (n_frames && (!frames || !counts))) return RSSYNC_E_INVALID;
+    size_t at = 0;
+    for (size_t i = 0; i < n_frames; ++i) {
+        if (int rc = rssync_set_track(p, frames[i], ts_a + at, ts_b + at, rays_a + 3 * at, rays_b + 3 * at, counts[i]))
+            return rc;
+        at += counts[i];
+    }
+    return RSSYNC_OK;
+}
+
+int rssync_set_kernel_timing(rssync_problem* p, int enabled) {
+    if (!p) return RSSYNC_E_INVALID;
+    if (enabled && !p->ev0) {
+        CUDA_TRY(p, cudaSetDevice(p->device));
+        CUDA_TRY(p, cudaEventCreate(&p->ev0));
+        CUDA_TRY(p, cudaEventCreate(&p->ev1));
+    }
+    p->kernel_timing = enabled != 0;
+    return RSSYNC_OK;
+}
+
+int rssync_presync_delays(double initial, double step, double radius, double* out, int cap) {
+    int n = 0;
+    for (double d = initial - radius; d < initial + radius; d += step) {  // core_private.cpp:69-70
+        if (out && n < cap) out[n] = d;
+        if (++n > (1 << 28)) break;
+    }
+    return n;
+}
+
+int rssync_presync(rssync_problem* p, double initial, int64_t fb, int64_t fe, double step,
+                   double radius, double* out_cost, double* out_delay) {
+    if (!p || !out_cost || !out_delay) return RSSYNC_E_INVALID;
+    if (!(step > 0) || !std::isfinite(radius) || !std::isfinite(initial)) {
+        p->err = "pre-sync: search_step must be > 0 and the search window finite";
+        return RSSYNC_E_INVALID;
+    }
+    const int n = rssync_presync_delays(initial, step, radius, nullptr, 0);
+    if (n <= 0 || n > (1 << 28)) { p->err = "pre-sync: empty or oversized delay grid"; return RSSYNC_E_INVALID; }
+    std::vector<double> delays(n), costs(n);
+    rssync_presync_delays(initial, step, radius, delays.data(), n);
+    const uint64_t call = p->call_no++;
+    unsigned flags = 0;
+    if (int rc = presync_grid_impl(p, fb, fe, delays.data(), n, rs::kStreamPreSync, call, 0, costs.data(), &flags))
+        return rc;
+    if (flags) {  // core_private.cpp:76-83
+        p->err = (flags & rs::kFlagP)   ? "pre-sync: non-finite numbers in P"
+                 : (flags & rs::kFlagM) ? "pre-sync: non-finite numbers in M"
+                 : (flags & rs::kFlagR) ? "pre-sync: non-finite r"
+                                        : "pre-sync: non-finite rho";
+        return RSSYNC_E_NONFINITE;
+    }
+    int best = 0;  // std::min_element over (cost, delay) pairs, :89
+    for (int i = 1; i < n; ++i)
+        if (costs[i] < costs[best] || (costs[i] == costs[best] && delays[i] < delays[best])) best = i;
+    *out_cost = costs[best];
+    *out_delay = delays[best];
+    return RSSYNC_OK;
+}
+
+int rssync_debug_presync(rssync_problem* p, double initial, int64_t fb, int64_t fe, double radius,
+                         double* delays, double* costs, int point_count) {
+    if (!p || (point_count > 0 && (!delays || !costs))) return RSSYNC_E_INVALID;
+    if (point_count <= 0) return RSSYNC_OK;
+    for (int i = 0; i < point_count; ++i)
+        delays[i] = initial - radius + 2 * radius * i / (point_count - 1);  // core_private.cpp:345
+    const uint64_t call = p->call_no++;
+    return presync_grid_impl(p, fb, fe, delays, point_count, rs::kStreamDebugPreSync, call, 0, costs, nullptr);
+}
+
+int rssync_presync_grid(rssync_problem* p, int64_t fb, int64_t fe, const double* delays, int n,
+                        int stream, uint64_t call_no, uint64_t idx_base, double* costs,
+                        unsigned* nonfinite_flags) {
+    if (!p || (n > 0 && (!delays || !costs))) return RSSYNC_E_INVALID;
+    return presync_grid_impl(p, fb, fe, delays, n, (uint64_t)stream, call_no, idx_base, costs, nonfinite_flags);
+}
+
+int rssync_sync(rssync_problem* p, double initial, int64_t fb, int64_t fe, double center,
+                double radius, double* out_cost, double* out_delay) {
+    if (!p || !out_cost || !out_delay) return RSSYNC_E_INVALID;
+    return sync_batch_impl(p, 1, &initial, &fb, &fe, &center, &radius, out_cost, out_delay, true);
+}
+
+int rssync_sync_batch(rssync_problem* p, int n, const double* initial, const int64_t* fb,
+                      const int64_t* fe, const double* center, const double* radius,
+                      double* out_cost, double* out_delay) {
+    if (!p || n < 0) return RSSYNC_E_INVALID;
+    if (n && (!initial || !fb || !fe || !center || !radius || !out_cost || !out_delay)) return RSSYNC_E_INVALID;
+    return sync_batch_impl(p, n, initial, fb, fe, center, radius, out_cost, out_delay, false);
+}
+
+int rssync_last_sync_trace(const rssync_problem* p, double* delays, double* steps, int cap) {
+    if (!p) return 0;
+    int n = (int)std::min<size_t>(p->trace_delay.size(), (size_t)std::max(cap, 0));
+    for (int i = 0; i < n; ++i) {
+        if (delays) delays[i] = p->trace_delay[i];
+        if (steps) steps[i] = p->trace_step[i];
+    }
+    return (delays || steps) ? n : (int)p->trace_delay.size();
+}
+
+int rssync_set_rng(rssync_problem* p, uint64_t seed, uint64_t call_no) {
+    if (!p) return RSSYNC_E_INVALID;
+    p->seed = seed;
+    p->call_no = call_no;
+    return RSSYNC_OK;
+}
+uint64_t rssync_call_counter(const rssync_problem* p) { return p ? p->call_no : 0; }
+
+int rssync_set_stream(rssync_problem* p, void* s) {
+    if (!p) return RSSYNC_E_INVALID;
+    p->stream = (cudaStream_t)s;
+    return RSSYNC_OK;
+}
+
+int rssync_flush(rssync_problem* p) {
+    if (!p) return RSSYNC_E_INVALID;
+    if (int rc = flush(p)) return rc;
+    CUDA_TRY(p, cudaStreamSynchronize(p->stream));
+    return RSSYNC_OK;
+}
+
+int rssync_get_stats(const rssync_problem* p, rssync_stats* out) {
+    if (!p || !out) return RSSYNC_E_INVALID;
+    out->kernel_launches = rs::launch_count();
+    out->h2d_bytes = p->h2d;
+    out->d2h_bytes = p->d2h;
+    out->frames = p->frames.size();
+    out->rays = p->total_rays;
+    out->gyro_samples = p->nq;
+    out->sync_outer_iters = p->sync_outer;
+    out->sync_lbfgs_evals = p->sync_evals;
+    out->last_grid_kernel_ms = p->last_grid_ms;
+    return RSSYNC_OK;
+}
+
+int rssync_measure_fp64_peak(double* tflops) {
+    if (!tflops) return RSSYNC_E_INVALID;
+    int dev = 0, sms = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return RSSYNC_E_CUDA;
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    double* sink = nullptr;
+    if (cudaMalloc((void**)&sink, 8) != cudaSuccess) return RSSYNC_E_CUDA;
+    const int blocks = sms * 8, threads = 256, iters = 1 << 16;
+    double best = 0.0;
+    for (int rep = 0; rep < 3; ++rep) {
+        float ms = rs::run_fp64_peak(blocks, threads, iters, sink, nullptr);
+        double flops = 2.0 * 8.0 * (double)iters * (double)blocks * (double)threads;
+        if (ms > 0) best = std::max(best, flops / (ms * 1e-3) / 1e12);
+    }
+    cudaFree(sink);
+    if (cudaGetLastError() != cudaSuccess) return RSSYNC_E_CUDA;
+    *tflops = best;
+    return RSSYNC_OK;
+}
+
+// ---- probes -----------------------------------------------------------------------------------
+int rssync_probe_gyro(const rssync_problem* p, double* sample_rate, double* first_timestamp,
+                      size_t* count, double* rec) {
+    if (!p) return RSSYNC_E_INVALID;
+    if (sample_rate) *sample_rate = p->sr;
+    if (first_timestamp) *first_timestamp = p->q0;
+    if (count) *count = p->nq;
+    if (rec) std::copy(p->rec.begin(), p->rec.end(), rec);
+    return RSSYNC_OK;
+}
+
+static int probe_frame(rssync_problem* p, int64_t frame, FrameDesc& fd) {
+    if (int rc = require_gyro(p, "probe")) return rc;
+    auto it = p->frames.find(frame);
+    if (it == p->frames.end()) { p->err = "probe: no such frame"; return RSSYNC_E_INVALID; }
+    fd = it->second;
+    if (fd.n < 2) { p->err = "probe: frame has fewer than 2 rays"; return RSSYNC_E_INVALID; }
+    return flush(p);
+}
+
+int rssync_probe_problem_matrix(rssync_problem* p, int64_t frame, double delay, double* rows) {
+    if (!p || !rows) return RSSYNC_E_INVALID;
+    FrameDesc fd;
+    if (int rc = probe_frame(p, frame, fd)) return rc;
+    CUDA_TRY(p, p->d_probe.reserve((size_t)fd.n * 3));
+    rs::launch_probe_problem_matrix(p->device_data(), fd, delay, p->d_probe.ptr, p->stream);
+    if (int rc = d2h(p, rows, p->d_probe.ptr, sizeof(double) * 3 * fd.n)) return rc;
+    CUDA_TRY(p, cudaStreamSynchronize(p->stream));
+    return RSSYNC_OK;
+}
+
+int rssync_probe_guess_motion(rssync_problem* p, int64_t frame, double delay, int iters, int stream,
+                              uint64_t call_no, uint64_t offset_index, double* m3, double* k) {
+    if (!p || !m3) return RSSYNC_E_INVALID;
+    FrameDesc fd;
+    if (int rc = probe_frame(p, frame, fd)) return rc;
+    CUDA_TRY(p, p->d_probe.reserve(8));
+    rs::launch_probe_guess(p->device_data(), fd, delay, iters,
+                           rs::rng_prefix(p->seed, (uint64_t)stream, call_no, offset_index), p->d_probe.ptr,
+                           p->stream);
+    double out[4];
+    if (int rc = d2h(p, out, p->d_probe.ptr, sizeof(out))) return rc;
+    CUDA_TRY(p, cudaStreamSynchronize(p->stream));
+    m3[0] = out[0]; m3[1] = out[1]; m3[2] = out[2];
+    if (k) *k = out[3];
+    return RSSYNC_OK;
+}
+
+int rssync_probe_loss(rssync_problem* p, int64_t frame, double delay, const double* m3, double k,
+                      double* loss3, double* loss5, double* grad3) {
+    if (!p || !m3) return RSSYNC_E_INVALID;
+    FrameDesc fd;
+    if (int rc = probe_frame(p, frame, fd)) return rc;
+    CUDA_TRY(p, p->d_probe.reserve(16));
+    if (int rc = h2d(p, p->d_probe.ptr + 8, m3, 3 * sizeof(double))) return rc;
+    rs::launch_probe_loss(p->device_data(), fd, delay, p->d_probe.ptr + 8, k, p->d_probe.ptr, p->stream);
+    double out[5];
+    if (int rc = d2h(p, out, p->d_probe.ptr, sizeof(out))) return rc;
+    CUDA_TRY(p, cudaStreamSynchronize(p->stream));
+    if (loss3) *loss3 = out[0];
+    if (loss5) *loss5 = out[1];
+    if (grad3) { grad3[0] = out[2]; grad3[1] = out[3]; grad3[2] = out[4]; }
+    return RSSYNC_OK;
+}
+
+int rssync_probe_lbfgs(rssync_problem* p, int64_t frame, double delay, double* m3, double k, double* f,
+                       int* iters, int* evals) {
+    if (!p || !m3) return RSSYNC_E_INVALID;
+    FrameDesc fd;
+    if (int rc = probe_frame(p, frame, fd)) return rc;
+    CUDA_TRY(p, p->d_probe.reserve(16));
+    if (int rc = h2d(p, p->d_probe.ptr, m3, 3 * sizeof(double))) return rc;
+    rs::launch_probe_lbfgs(p->device_data(), fd, delay, p->d_probe.ptr, k, p->d_probe.ptr + 4,
+                           (int*)(p->d_probe.ptr + 8), p->stream);
+    double out[5];
+    int st[2];
+    if (int rc = d2h(p, out, p->d_probe.ptr, sizeof(out))) return rc;
+    if (int rc = d2h(p, st, p->d_probe.ptr + 8, sizeof(st))) return rc;
+    CUDA_TRY(p, cudaStreamSynchronize(p->stream));
+    m3[0] = out[0]; m3[1] = out[1]; m3[2] = out[2];
+    if (f) *f = out[4];
+    if (iters) *iters = st[0];
+    if (evals) *evals = st[1];
+    return RSSYNC_OK;
+}
+
+int rssync_probe_log1p(const double* x, int n, double* out) {
+    if (n <= 0) return RSSYNC_OK;
+    double *dx = nullptr, *dy = nullptr;
+    if (cudaMalloc((void**)&dx, sizeof(double) * n) != cudaSuccess) return RSSYNC_E_CUDA;
+    if (cudaMalloc((void**)&dy, sizeof(double) * n) != cudaSuccess) { cudaFree(dx); return RSSYNC_E_CUDA; }
+    cudaMemcpy(dx, x, sizeof(double) * n, cudaMemcpyHostToDevice);
+    rs::launch_probe_log1p(dx, n, dy, nullptr);
+    cudaError_t e = cudaMemcpy(out, dy, sizeof(double) * n, cudaMemcpyDeviceToHost);
+    cudaFree(dx);
+    cudaFree(dy);
+    return e == cudaSuccess ? RSSYNC_OK : RSSYNC_E_CUDA;
+}
+
+}  // extern "C"

@@ -1,0 +1,198 @@
+// Device-side arithmetic of the rs-sync loss engine for sm_100a.
+//
+// Arithmetic contract: IEEE-754 binary64, round-to-nearest, compiled with
+// -fmad=false so that a fused multiply-add happens exactly where fma() is written; long sums go
+// through a double-double accumulator so their value does not depend on how the terms are
+// distributed over lanes.  Reference lines each function stands for are cited inline (paths
+// relative to the rs-sync repository).
+#pragma once
+#include <cstdint>
+#include <cuda_runtime.h>
+
+#include "rng.h"
+
+namespace rs {
+
+// ---- double-double accumulation (arma::accu / arma::sum / arma::norm inner sums) -------------
+struct DD {
+    double hi, lo;
+};
+__device__ __forceinline__ DD dd_zero() { return DD{0.0, 0.0}; }
+__device__ __forceinline__ void dd_add(DD& a, double x) {
+    double s = a.hi + x;
+    double bb = s - a.hi;
+    double e = (a.hi - (s - bb)) + (x - bb);
+    a.hi = s;
+    a.lo += e;
+}
+__device__ __forceinline__ void dd_merge(DD& a, const DD& b) {
+    double s = a.hi + b.hi;
+    double bb = s - a.hi;
+    double e = (a.hi - (s - bb)) + (b.hi - bb);
+    a.hi = s;
+    a.lo = (a.lo + b.lo) + e;
+}
+// butterfly over the warp; every lane ends with the same (hi, lo)
+__device__ __forceinline__ double warp_dd_sum(DD a) {
+#pragma unroll
+    for (int off = 16; off >= 1; off >>= 1) {
+        DD b;
+        b.hi = __shfl_xor_sync(0xffffffffu, a.hi, off);
+        b.lo = __shfl_xor_sync(0xffffffffu, a.lo, off);
+        dd_merge(a, b);
+    }
+    return a.hi + a.lo;
+}
+
+// ---- log1p on x >= 0 (arma::log1p at core_private.cpp:82,121,354; inline_utils.hpp:28-30) ----
+// Argument reduction 1+x = 2^k (1+f), s = f/(2+f), degree-7 polynomial in s^2; the operation
+// order is part of the contract (the CPU oracle evaluates the same expression tree).
+__device__ __forceinline__ double log1p_nonneg(double x) {
+    const double ln2_hi = 6.93147180369123816490e-01;
+    const double ln2_lo = 1.90821492927058770002e-10;
+    const double L1 = 6.666666666666735130e-01, L2 = 3.999999999940941908e-01,
+                 L3 = 2.857142874366239149e-01, L4 = 2.222219843214978396e-01,
+                 L5 = 1.818357216161805012e-01, L6 = 1.531383769920937332e-01,
+                 L7 = 1.479819860511658591e-01;
+    if (!(x < __longlong_as_double(0x7ff0000000000000LL))) return x;  // +inf, NaN
+    if (x < 0x1p-29) return x - (x * x) * 0.5;
+    int k = 0;
+    double f = x, c = 0.0;
+    unsigned hu = 1;
+    if (!(x < 0.41421356237309503)) {
+        double u;
+        if (x < 0x1p53) {
+            u = 1.0 + x;
+            hu = (unsigned)__double2hiint(u);
+            k = (int)(hu >> 20) - 1023;
+            c = (k > 0) ? 1.0 - (u - x) : x - (u - 1.0);
+            c = c / u;
+        } else {
+            u = x;
+            hu = (unsigned)__double2hiint(u);
+            k = (int)(hu >> 20) - 1023;
+            c = 0.0;
+        }
+        hu &= 0x000fffffu;
+        if (hu < 0x6a09eu) {
+            u = __hiloint2double((int)(hu | 0x3ff00000u), __double2loint(u));
+        } else {
+            k += 1;
+            u = __hiloint2double((int)(hu | 0x3fe00000u), __double2loint(u));
+            hu = (0x00100000u - hu) >> 2;
+        }
+        f = u - 1.0;
+    }
+    const double dk = (double)k;
+    const double hfsq = (0.5 * f) * f;
+    if (hu == 0) {
+        if (f == 0.0) {
+            if (k == 0) return 0.0;
+            c = fma(dk, ln2_lo, c);
+            return fma(dk, ln2_hi, c);
+        }
+        double R = hfsq * (1.0 - 0.66666666666666666 * f);
+        if (k == 0) return f - R;
+        return dk * ln2_hi - ((R - fma(dk, ln2_lo, c)) - f);
+    }
+    const double s = f / (2.0 + f);
+    const double z = s * s;
+    double R = fma(z, L7, L6);
+    R = fma(z, R, L5);
+    R = fma(z, R, L4);
+    R = fma(z, R, L3);
+    R = fma(z, R, L2);
+    R = fma(z, R, L1);
+    R = z * R;
+    if (k == 0) return f - (hfsq - s * (hfsq + R));
+    return dk * ln2_hi - ((hfsq - fma(s, hfsq + R, fma(dk, ln2_lo, c))) - f);
+}
+
+// ---- pinned counter-based RNG (replaces mtrand, inline_utils.hpp:13-17) ----------------------
+__device__ __forceinline__ uint32_t rng_index(uint64_t task_key, uint32_t iter, uint32_t k,
+                                              uint32_t n) {
+    uint64_t d = mix64(task_key ^ (((uint64_t)iter << 32) | (uint64_t)k));
+    return (uint32_t)__umul64hi(d, (uint64_t)n);
+}
+
+// ---- natural cubic spline on unit knots, 4 components (minispline.cpp:48-55, ndspline.cpp:21-27)
+// rec: n records of 16 doubles {y[4], b[4], c[4], d[4]}, 128-byte aligned.
+__device__ __forceinline__ void spline_eval4(const double* __restrict__ rec, int n, double x,
+                                             double q[4]) {
+    const double fl = floor(x);
+    const double idxf = fl < 0.0 ? 0.0 : (fl > (double)n ? (double)n : fl);
+    const double h = x - idxf;
+    int r = (int)idxf;
+    r = r > n - 1 ? n - 1 : r;
+    const bool extrap = (x < idxf) || (x > (double)(n - 1));
+    const double2* p = reinterpret_cast<const double2*>(rec + (size_t)r * 16);
+    const double2 y01 = __ldg(p + 0), y23 = __ldg(p + 1);
+    const double2 b01 = __ldg(p + 2), b23 = __ldg(p + 3);
+    const double2 c01 = __ldg(p + 4), c23 = __ldg(p + 5);
+    double2 d01 = __ldg(p + 6), d23 = __ldg(p + 7);
+    if (extrap) { d01.x = d01.y = d23.x = d23.y = 0.0; }
+    q[0] = fma(fma(fma(d01.x, h, c01.x), h, b01.x), h, y01.x);
+    q[1] = fma(fma(fma(d01.y, h, c01.y), h, b01.y), h, y01.y);
+    q[2] = fma(fma(fma(d23.x, h, c23.x), h, b23.x), h, y23.x);
+    q[3] = fma(fma(fma(d23.y, h, c23.y), h, b23.y), h, y23.y);
+}
+
+// ---- de-rotation by the conjugate of an un-normalised quaternion (quat.cpp:33-47) ------------
+//   |q|^2 * rot(conj(q/|q|), p) = (w^2 - u.u) p + 2 (u.p) u - 2 w (u x p)
+__device__ __forceinline__ void derotate_unnormalised(const double q[4], double p0, double p1,
+                                                      double p2, double out[3], double& n2) {
+    const double w = q[0], u0 = q[1], u1 = q[2], u2 = q[3];
+    const double uu = fma(u2, u2, fma(u1, u1, u0 * u0));
+    n2 = fma(w, w, uu);
+    const double e = fma(w, w, -uu);
+    const double up = fma(u2, p2, fma(u1, p1, u0 * p0));
+    const double up2 = up + up;
+    const double c0 = fma(u1, p2, -(u2 * p1));
+    const double c1 = fma(u2, p0, -(u0 * p2));
+    const double c2 = fma(u0, p1, -(u1 * p0));
+    const double w2 = w + w;
+    out[0] = fma(e, p0, fma(up2, u0, -(w2 * c0)));
+    out[1] = fma(e, p1, fma(up2, u1, -(w2 * c1)));
+    out[2] = fma(e, p2, fma(up2, u2, -(w2 * c2)));
+}
+
+// one row of opt_compute_problem (core_private.cpp:19-28)
+__device__ __forceinline__ void problem_row(const double* __restrict__ rec, int n, double q0,
+                                            double sr, double delay, double ts_a, double ts_b,
+                                            double ax, double ay, double az, double bx, double by,
+                                            double bz, double row[3]) {
+    const double xa = ((ts_a - q0) + delay) * sr;
+    const double xb = ((ts_b - q0) + delay) * sr;
+    double qa[4], qb[4], ar[3], br[3], na, nb;
+    spline_eval4(rec, n, xa, qa);
+    spline_eval4(rec, n, xb, qb);
+    derotate_unnormalised(qa, ax, ay, az, ar, na);
+    derotate_unnormalised(qb, bx, by, bz, br, nb);
+    const double s = 1.0 / (na * nb);
+    row[0] = fma(ar[1], br[2], -(ar[2] * br[1])) * s;
+    row[1] = fma(ar[2], br[0], -(ar[0] * br[2])) * s;
+    row[2] = fma(ar[0], br[1], -(ar[1] * br[0])) * s;
+}
+
+__device__ __forceinline__ double dot3(double a0, double a1, double a2, double b0, double b1,
+                                       double b2) {
+    return fma(a2, b2, fma(a1, b1, a0 * b0));
+}
+
+// safe_normalize (inline_utils.hpp:5-11)
+__device__ __forceinline__ void safe_normalize3(double v0, double v1, double v2, double out[3]) {
+    const double nrm = sqrt(dot3(v0, v1, v2, v0, v1, v2));
+    if (nrm < 1e-12) { out[0] = v0; out[1] = v1; out[2] = v2; return; }
+    const double inv = 1.0 / nrm;
+    out[0] = v0 * inv; out[1] = v1 * inv; out[2] = v2 * inv;
+}
+
+__device__ __forceinline__ double clamp_k(double k) {  // inline_utils.hpp:50
+    return (k < 1e1) ? 1e1 : ((1e3 < k) ? 1e3 : k);
+}
+
+__device__ __forceinline__ bool is_finite(double x) {
+    return (__double2hiint(x) & 0x7ff00000) != 0x7ff00000;
+}
+
+}  // namespace rs

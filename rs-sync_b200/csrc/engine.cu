@@ -1,0 +1,712 @@
+// sm_100a kernels of the rs-sync synchronisation loss engine.
+//
+// Decomposition: ONE WARP PER (delay, frame) TASK.  A frame carries N <= 512 rays; lane l owns rays
+// l, l+32, ... ("slots", compile-time SLOTS = ceil(N/32) rounded to {2,4,8,16}).  Everything a
+// task needs between its first load and its single output double stays in registers / the warp's
+// slice of shared memory:
+//   rays + timestamps (SoA planes, coalesced 256 B per plane per slot)  ->
+//   problem-matrix rows (opt_compute_problem, core_private.cpp:15-32)    ->
+//   randomised least-quartile plane fit (opt_guess_translational_motion, :34-59) ->
+//   robust loss (pre_sync body :79-85  /  FrameState::Loss :92-123).
+// Cross-lane work is warp shuffles / REDUX only; there is no block-level synchronisation in
+// the hot loops.  The arithmetic contract is described in device_math.cuh.
+#include "engine.h"
+
+#include <atomic>
+#include <cstdio>
+
+#include "device_math.cuh"
+
+namespace rs {
+
+namespace {
+
+constexpr unsigned FULL = 0xffffffffu;
+constexpr int kWarpsPerBlock = 8;
+constexpr unsigned long long kKeyMax = ~0ull;
+
+std::atomic<uint64_t> g_launches{0};
+
+// ------------------------------------------------------------------------------------------
+// rows of the problem matrix for this lane's slots; slots past the frame's end are zeroed
+template <int SLOTS>
+__device__ __forceinline__ void build_rows(const DeviceData& dd, const FrameDesc& fd, double delay,
+                                           int lane, double (&P)[SLOTS][3]) {
+#pragma unroll
+    for (int s = 0; s < SLOTS; ++s) {
+        P[s][0] = P[s][1] = P[s][2] = 0.0;
+        if (s * 32 < fd.n) {  // warp-uniform
+            const int i = s * 32 + lane;
+            const size_t g = (size_t)fd.off + i;  // planes are padded to a multiple of 32 per frame
+            const double tsa = __ldg(dd.plane[0] + g), tsb = __ldg(dd.plane[1] + g);
+            const double ax = __ldg(dd.plane[2] + g), ay = __ldg(dd.plane[3] + g),
+                         az = __ldg(dd.plane[4] + g);
+            const double bx = __ldg(dd.plane[5] + g), by = __ldg(dd.plane[6] + g),
+                         bz = __ldg(dd.plane[7] + g);
+            double row[3];
+            problem_row(dd.rec, dd.nq, dd.q0, dd.sr, delay, tsa, tsb, ax, ay, az, bx, by, bz, row);
+            if (i < fd.n) { P[s][0] = row[0]; P[s][1] = row[1]; P[s][2] = row[2]; }
+        }
+    }
+}
+
+// k-th smallest (0-based) of the warp's keys restricted to keys < hi_excl.  Keys are the bit
+// patterns of non-negative doubles (order-preserving); empty slots hold kKeyMax.
+template <int SLOTS>
+__device__ __forceinline__ unsigned long long warp_select(const unsigned long long (&key)[SLOTS],
+                                                          int kth, unsigned long long hi_excl) {
+    unsigned long long lo = 0ull, hi = hi_excl;
+    int round = 0;
+    for (;;) {
+        bool has = false;
+        unsigned long long cand = 0ull;
+#pragma unroll
+        for (int s = 0; s < SLOTS; ++s) {
+            const bool in = (key[s] >= lo) && (key[s] < hi);
+            if (in && !has) { cand = key[s]; has = true; }
+        }
+        const unsigned bal = __ballot_sync(FULL, has);
+        const int rot = (round * 11) & 31;
+        const unsigned rb = __funnelshift_r(bal, bal, rot);
+        const int src = (__ffs(rb) - 1 + rot) & 31;
+        const unsigned long long pivot = __shfl_sync(FULL, cand, src);
+        unsigned cl = 0, ce = 0;
+#pragma unroll
+        for (int s = 0; s < SLOTS; ++s) {
+            cl += (key[s] < pivot) ? 1u : 0u;
+            ce += (key[s] == pivot) ? 1u : 0u;
+        }
+        const unsigned packed = __reduce_add_sync(FULL, cl | (ce << 16));
+        const int nl = (int)(packed & 0xffffu), ne = (int)(packed >> 16);
+        if (kth < nl) hi = pivot;
+        else if (kth < nl + ne) return pivot;
+        else lo = pivot + 1;
+        ++round;
+    }
+}
+
+// opt_guess_translational_motion (core_private.cpp:34-59).  sP: this warp's raw rows in shared
+// memory, SoA [3][NP].  np: row-normalised rows in registers.  Hypotheses are generated 32 at a
+// time (lane j builds hypothesis j), then tested one after another by the whole warp; a
+// hypothesis wins iff at least n/4+1 of its squared residuals lie below the best quartile so far
+// (equivalent to `med < least_med`, :53), and only then is its exact quartile selected.
+template <int SLOTS>
+__device__ __forceinline__ void warp_ransac(const double* sP, int NP, int n, int iters,
+                                            uint64_t key, int lane, const double (&np)[SLOTS][3],
+                                            double M[3]) {
+    const int kth = n / 4;  // :52
+    unsigned long long least = kKeyMax;
+    M[0] = M[1] = M[2] = 0.0;
+    for (int j0 = 0; j0 < iters; j0 += 32) {
+        double v[3] = {0.0, 0.0, 0.0};
+        const int jj = j0 + lane;
+        if (jj < iters) {
+            const uint32_t a = rng_index(key, (uint32_t)jj, 0u, (uint32_t)n);  // :42
+            uint32_t b, kk = 1u;
+            do { b = rng_index(key, (uint32_t)jj, kk++, (uint32_t)n); } while (b == a);  // :43
+            const double a0 = sP[a], a1 = sP[NP + a], a2 = sP[2 * NP + a];
+            const double b0 = sP[b], b1 = sP[NP + b], b2 = sP[2 * NP + b];
+            const double c0 = fma(a1, b2, -(a2 * b1));
+            const double c1 = fma(a2, b0, -(a0 * b2));
+            const double c2 = fma(a0, b1, -(a1 * b0));
+            safe_normalize3(c0, c1, c2, v);  // :45-46
+        }
+        const int cnt = (iters - j0) < 32 ? (iters - j0) : 32;
+        for (int t = 0; t < cnt; ++t) {
+            const double vx = __shfl_sync(FULL, v[0], t);
+            const double vy = __shfl_sync(FULL, v[1], t);
+            const double vz = __shfl_sync(FULL, v[2], t);
+            unsigned long long keys[SLOTS];
+            unsigned below = 0;
+#pragma unroll
+            for (int s = 0; s < SLOTS; ++s) {
+                const double r = dot3(np[s][0], np[s][1], np[s][2], vx, vy, vz);  // :48
+                const double r2 = r * r;                                            // :49
+                const bool valid = (s * 32 + lane) < n;
+                keys[s] = valid ? (unsigned long long)__double_as_longlong(r2) : kKeyMax;
+                below += (keys[s] < least) ? 1u : 0u;
+            }
+            const int nbelow = (int)__reduce_add_sync(FULL, below);
+            if (nbelow > kth) {  // med < least_med
+                least = warp_select<SLOTS>(keys, kth, least);
+                M[0] = vx; M[1] = vy; M[2] = vz;
+            }
+        }
+    }
+}
+
+// spill this lane's rows to the warp's shared slice and return the normalised copy
+template <int SLOTS>
+__device__ __forceinline__ void stage_rows(const double (&P)[SLOTS][3], double* sP, int NP, int lane,
+                                           double (&np)[SLOTS][3]) {
+#pragma unroll
+    for (int s = 0; s < SLOTS; ++s) {
+        const int i = s * 32 + lane;
+        sP[i] = P[s][0];
+        sP[NP + i] = P[s][1];
+        sP[2 * NP + i] = P[s][2];
+        safe_normalize3(P[s][0], P[s][1], P[s][2], np[s]);  // :35-36
+    }
+    __syncwarp();
+}
+
+// arma::norm(P * M) over the warp (core_private.cpp:79,132); pm[] receives this lane's products
+template <int SLOTS>
+__device__ __forceinline__ double warp_norm_PM(const double (&P)[SLOTS][3], const double M[3],
+                                               double (&pm)[SLOTS]) {
+    DD ss = dd_zero();
+#pragma unroll
+    for (int s = 0; s < SLOTS; ++s) {
+        pm[s] = dot3(P[s][0], P[s][1], P[s][2], M[0], M[1], M[2]);
+        dd_add(ss, pm[s] * pm[s]);
+    }
+    return sqrt(warp_dd_sum(ss));
+}
+
+// FrameState::Loss 3-arg (core_private.cpp:117-123) on register rows
+template <int SLOTS>
+__device__ __forceinline__ double warp_loss3(const double (&P)[SLOTS][3], const double m[3],
+                                             double k) {
+    const double scale = k / sqrt(dot3(m[0], m[1], m[2], m[0], m[1], m[2]));
+    DD acc = dd_zero();
+#pragma unroll
+    for (int s = 0; s < SLOTS; ++s) {
+        const double r = dot3(P[s][0], P[s][1], P[s][2], m[0], m[1], m[2]) * scale;
+        dd_add(acc, log1p_nonneg(r * r));  // empty slots: P = 0 -> log1p(0) = 0
+    }
+    return warp_dd_sum(acc);
+}
+
+// FrameState::Loss 5-arg (core_private.cpp:92-115): value and d/dm in closed form
+template <int SLOTS>
+__device__ __forceinline__ double warp_loss5(const double (&P)[SLOTS][3], const double m[3],
+                                             double k, double g[3]) {
+    const double kk = k * k;
+    const double den = dot3(m[0], m[1], m[2], m[0], m[1], m[2]) / kk;
+    const double inv_den = 1.0 / den;
+    DD L = dd_zero(), g0 = dd_zero(), g1 = dd_zero(), g2 = dd_zero(), su = dd_zero();
+#pragma unroll
+    for (int s = 0; s < SLOTS; ++s) {
+        const double v1 = dot3(P[s][0], P[s][1], P[s][2], m[0], m[1], m[2]);
+        const double u = (v1 * v1) * inv_den;
+        dd_add(L, log1p_nonneg(u));
+        const double w = 1.0 / (1.0 + u);
+        const double wv = w * v1;
+        dd_add(g0, wv * P[s][0]);
+        dd_add(g1, wv * P[s][1]);
+        dd_add(g2, wv * P[s][2]);
+        dd_add(su, w * u);
+    }
+    const double Ls = warp_dd_sum(L);
+    const double G0 = warp_dd_sum(g0), G1 = warp_dd_sum(g1), G2 = warp_dd_sum(g2);
+    const double SU = warp_dd_sum(su);
+    const double c1 = 2.0 * inv_den;
+    const double c2 = (c1 / kk) * SU;
+    g[0] = c1 * G0 - c2 * m[0];
+    g[1] = c1 * G1 - c2 * m[1];
+    g[2] = c1 * G2 - c2 * m[2];
+    return Ls;
+}
+
+// ens::L_BFGS on a 3-vector (call site core_private.cpp:264-294); every lane runs the same scalar
+// control flow on identical values, the objective is evaluated cooperatively.
+template <int SLOTS>
+__device__ __forceinline__ double warp_lbfgs(const double (&P)[SLOTS][3], double x[3], double k,
+                                             int& n_iters, int& n_evals) {
+    constexpr int numBasis = 10, maxIterations = 200, maxTrials = 50;
+    const double minGradientNorm = 1e-4, armijo = 1e-4, wolfe = 0.9, factr = 1e-15,
+                 minStep = 1e-20, maxStep = 1e20;
+    double S[numBasis][3], Y[numBasis][3], rho[numBasis], alpha[numBasis];
+    double g[3], oldx[3], oldg[3], dir[3], trial[3];
+    double f = warp_loss5<SLOTS>(P, x, k, g);
+    n_evals = 1;
+    n_iters = 0;
+    for (int it = 0; it != maxIterations; ++it) {
+        const double prevf = f;
+        if (it > 0 && sqrt(dot3(g[0], g[1], g[2], g[0], g[1], g[2])) < minGradientNorm) break;
+        if (f != f) break;
+        double scaling;
+        if (it > 0) {
+            const int pp = (it - 1) % numBasis;
+            const double yy = dot3(Y[pp][0], Y[pp][1], Y[pp][2], Y[pp][0], Y[pp][1], Y[pp][2]);
+            const double denom = (yy >= 1e-10) ? yy : 1.0;
+            scaling = dot3(S[pp][0], S[pp][1], S[pp][2], Y[pp][0], Y[pp][1], Y[pp][2]) / denom;
+        } else {
+            const double gn = sqrt(dot3(g[0], g[1], g[2], g[0], g[1], g[2]));
+            scaling = (gn >= 1e-5) ? 1.0 / gn : 1.0;
+        }
+        if (scaling == 0.0 || !is_finite(scaling)) break;
+        dir[0] = g[0]; dir[1] = g[1]; dir[2] = g[2];
+        const int limit = (numBasis > it) ? 0 : (it - numBasis);
+        for (int i = it; i != limit; --i) {
+            const int tp = (i + (numBasis - 1)) % numBasis;
+            const double ys = dot3(Y[tp][0], Y[tp][1], Y[tp][2], S[tp][0], S[tp][1], S[tp][2]);
+            rho[it - i] = (ys != 0) ? (1.0 / ys) : 1.0;
+            alpha[it - i] = rho[it - i] * dot3(S[tp][0], S[tp][1], S[tp][2], dir[0], dir[1], dir[2]);
+            for (int c = 0; c < 3; ++c) dir[c] -= alpha[it - i] * Y[tp][c];
+        }
+        for (int c = 0; c < 3; ++c) dir[c] *= scaling;
+        for (int i = limit; i < it; ++i) {
+            const int tp = i % numBasis;
+            const double beta =
+                rho[it - i - 1] * dot3(Y[tp][0], Y[tp][1], Y[tp][2], dir[0], dir[1], dir[2]);
+            const double coef = alpha[it - i - 1] - beta;
+            for (int c = 0; c < 3; ++c) dir[c] += coef * S[tp][c];
+        }
+        for (int c = 0; c < 3; ++c) dir[c] = -dir[c];
+        for (int c = 0; c < 3; ++c) { oldx[c] = x[c]; oldg[c] = g[c]; }
+        double step = 1.0, bestStep = 1.0, bestObj = 1.7976931348623157e308;
+        const double init_dg = dot3(g[0], g[1], g[2], dir[0], dir[1], dir[2]);
+        if (init_dg > 0.0) break;
+        const double f0 = f;
+        const double lin = armijo * init_dg;
+        int trials = 0;
+        for (;;) {
+            for (int c = 0; c < 3; ++c) trial[c] = x[c] + step * dir[c];
+            f = warp_loss5<SLOTS>(P, trial, k, g);
+            n_evals++;
+            if (f < bestObj) { bestStep = step; bestObj = f; }
+            trials++;
+            double width;
+            if (f > f0 + step * lin) {
+                width = 0.5;
+            } else {
+                const double dg = dot3(g[0], g[1], g[2], dir[0], dir[1], dir[2]);
+                if (dg < wolfe * init_dg) width = 2.1;
+                else if (dg > -wolfe * init_dg) width = 0.5;
+                else break;
+            }
+            if (step < minStep || step > maxStep || trials >= maxTrials) break;
+            step *= width;
+        }
+        for (int c = 0; c < 3; ++c) x[c] += bestStep * dir[c];
+        n_iters++;
+        if (bestStep == 0.0) break;
+        const double denom = fmax(fmax(fabs(prevf), fabs(f)), 1.0);
+        if ((prevf - f) / denom <= factr) break;
+        const int op = it % numBasis;
+        for (int c = 0; c < 3; ++c) { S[op][c] = x[c] - oldx[c]; Y[op][c] = g[c] - oldg[c]; }
+    }
+    return f;
+}
+
+// ------------------------------------------------------------------------------------------
+// K1: PreSync / DebugPreSync grid.  task t -> (frame t / D, delay t % D): the 8 warps of a block
+// work on the same frame, so its ray planes and spline window are served from L1.
+template <int SLOTS>
+__global__ void __launch_bounds__(kWarpsPerBlock * 32)
+presync_kernel(DeviceData dd, const FrameDesc* __restrict__ frames, int F,
+               const double* __restrict__ delays, int D, uint64_t seed, uint64_t stream,
+               uint64_t call_no, uint64_t idx_base, double* __restrict__ framecost,
+               unsigned* __restrict__ flags) {
+    extern __shared__ double smem[];
+    constexpr int NP = SLOTS * 32;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    double* sP = smem + (size_t)warp * 3 * NP;
+    const long long total = (long long)F * D;
+    for (long long t = (long long)blockIdx.x * kWarpsPerBlock + warp; t < total;
+         t += (long long)gridDim.x * kWarpsPerBlock) {
+        const int fi = (int)(t / D), di = (int)(t % D);
+        const FrameDesc fd = frames[fi];
+        const double delay = delays[di];
+        unsigned bad = 0;
+        double np[SLOTS][3];
+        {
+            double P[SLOTS][3];
+            build_rows<SLOTS>(dd, fd, delay, lane, P);
+#pragma unroll
+            for (int s = 0; s < SLOTS; ++s)
+                if (!(is_finite(P[s][0]) && is_finite(P[s][1]) && is_finite(P[s][2]))) bad |= kFlagP;
+            __syncwarp();  // previous task's readers of sP are done
+            stage_rows<SLOTS>(P, sP, NP, lane, np);
+        }
+        const uint64_t key = rng_task_key(rng_prefix(seed, stream, call_no, idx_base + (uint64_t)di), fd.id);
+        double M[3];
+        warp_ransac<SLOTS>(sP, NP, fd.n, 20, key, lane, np, M);  // core_private.cpp:77
+        if (!(is_finite(M[0]) && is_finite(M[1]) && is_finite(M[2]))) bad |= kFlagM;
+        // :79-85
+        double pm[SLOTS];
+        DD ss = dd_zero();
+#pragma unroll
+        for (int s = 0; s < SLOTS; ++s) {
+            const int i = s * 32 + lane;
+            pm[s] = dot3(sP[i], sP[NP + i], sP[2 * NP + i], M[0], M[1], M[2]);
+            dd_add(ss, pm[s] * pm[s]);
+        }
+        const double k = clamp_k(1.0 / sqrt(warp_dd_sum(ss)) * 1e2);
+        const double scale = k / sqrt(dot3(M[0], M[1], M[2], M[0], M[1], M[2]));
+        DD acc = dd_zero();
+#pragma unroll
+        for (int s = 0; s < SLOTS; ++s) {
+            const double r = pm[s] * scale;
+            if (!is_finite(r)) bad |= kFlagR;
+            const double rho = log1p_nonneg(r * r);
+            if (!is_finite(rho)) bad |= kFlagRho;
+            dd_add(acc, sqrt(rho));
+        }
+        const double cost = sqrt(warp_dd_sum(acc));
+        if (lane == 0) framecost[(size_t)di * F + fi] = cost;
+        bad = __reduce_or_sync(FULL, bad);
+        if (bad && lane == 0) atomicOr(flags, bad);
+    }
+}
+
+// cost[d] = double-double sum over frames of framecost[d][.]  (the mutex-guarded `cost +=` of
+// core_private.cpp:84-85); one warp per delay.
+__global__ void reduce_rows_kernel(const double* __restrict__ in, int rows, int cols,
+                                   double* __restrict__ out) {
+    const int lane = threadIdx.x & 31;
+    const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (row >= rows) return;
+    DD acc = dd_zero();
+    for (int c = lane; c < cols; c += 32) dd_add(acc, in[(size_t)row * cols + c]);
+    const double v = warp_dd_sum(acc);
+    if (lane == 0) out[row] = v;
+}
+
+// ------------------------------------------------------------------------------------------
+// K4: Sync initialisation, GuessMotion (RANSAC-200) + GuessK per (syncpoint, frame) task
+template <int SLOTS>
+__global__ void __launch_bounds__(kWarpsPerBlock * 32)
+sync_init_kernel(DeviceData dd, SyncBatchDev b, const double* __restrict__ sp_delay,
+                 const uint64_t* __restrict__ sp_callno, const unsigned char* __restrict__ sp_active,
+                 uint64_t seed) {
+    extern __shared__ double smem[];
+    constexpr int NP = SLOTS * 32;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    double* sP = smem + (size_t)warp * 3 * NP;
+    for (int t = blockIdx.x * kWarpsPerBlock + warp; t < b.T; t += gridDim.x * kWarpsPerBlock) {
+        const SyncTask task = b.tasks[t];
+        if (!sp_active[task.sp]) continue;
+        const double delay = sp_delay[task.sp];
+        double P[SLOTS][3], np[SLOTS][3];
+        build_rows<SLOTS>(dd, task.fd, delay, lane, P);
+        __syncwarp();
+        stage_rows<SLOTS>(P, sP, NP, lane, np);
+        const uint64_t key =
+            rng_task_key(rng_prefix(seed, kStreamSyncInit, sp_callno[task.sp], 0), task.fd.id);
+        double M[3];
+        warp_ransac<SLOTS>(sP, NP, task.fd.n, 200, key, lane, np, M);  // core_private.cpp:127
+        double pm[SLOTS];
+        const double nrm = warp_norm_PM<SLOTS>(P, M, pm);
+        if (lane == 0) {
+            b.m[3 * t + 0] = M[0]; b.m[3 * t + 1] = M[1]; b.m[3 * t + 2] = M[2];
+            b.k[t] = clamp_k(1.0 / nrm * 1e2);  // :132
+        }
+    }
+}
+
+// K2+K3a: per task, L-BFGS refinement of m at the syncpoint's delay (do_opt_motion), then the
+// three objective values the delay step needs (Loss5 at x0, Loss3 at x0 -/+ h).
+template <int SLOTS>
+__global__ void __launch_bounds__(kWarpsPerBlock * 32)
+sync_motion_fgrad_kernel(DeviceData dd, SyncBatchDev b, const double* __restrict__ sp_delay,
+                         const double* __restrict__ sp_x0,
+                         const unsigned char* __restrict__ sp_active, double* __restrict__ scratch,
+                         int* __restrict__ stats) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (int t = blockIdx.x * kWarpsPerBlock + warp; t < b.T; t += gridDim.x * kWarpsPerBlock) {
+        const SyncTask task = b.tasks[t];
+        if (!sp_active[task.sp]) continue;
+        double P[SLOTS][3];
+        double m[3] = {b.m[3 * t], b.m[3 * t + 1], b.m[3 * t + 2]};
+        const double k = b.k[t];
+        build_rows<SLOTS>(dd, task.fd, sp_delay[task.sp], lane, P);
+        int it, ev;
+        warp_lbfgs<SLOTS>(P, m, k, it, ev);
+        if (lane == 0) {
+            b.m[3 * t] = m[0]; b.m[3 * t + 1] = m[1]; b.m[3 * t + 2] = m[2];
+            if (stats) { stats[2 * t] = it; stats[2 * t + 1] = ev; }
+        }
+        const double x0 = sp_x0[task.sp];
+        double g[3];
+        build_rows<SLOTS>(dd, task.fd, x0, lane, P);
+        const double v = warp_loss5<SLOTS>(P, m, k, g);
+        build_rows<SLOTS>(dd, task.fd, x0 - kNumericDiffStep, lane, P);
+        const double l = warp_loss3<SLOTS>(P, m, k);
+        build_rows<SLOTS>(dd, task.fd, x0 + kNumericDiffStep, lane, P);
+        const double r = warp_loss3<SLOTS>(P, m, k);
+        if (lane == 0) {
+            scratch[3 * t] = v;
+            scratch[3 * t + 1] = l;
+            scratch[3 * t + 2] = r;
+        }
+    }
+}
+
+// per syncpoint: cost = sum v, grad = sum (r - l)/2/h   (core_private.cpp:112, 236-237)
+__global__ void reduce_fgrad_kernel(SyncBatchDev b, const unsigned char* __restrict__ sp_active,
+                                    const double* __restrict__ scratch, double* __restrict__ out_v,
+                                    double* __restrict__ out_g) {
+    const int lane = threadIdx.x & 31;
+    const int sp = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (sp >= b.S || !sp_active[sp]) return;
+    DD av = dd_zero(), ag = dd_zero();
+    for (int t = b.sp_begin[sp] + lane; t < b.sp_begin[sp + 1]; t += 32) {
+        dd_add(av, scratch[3 * t]);
+        dd_add(ag, (scratch[3 * t + 2] - scratch[3 * t + 1]) / 2 / kNumericDiffStep);
+    }
+    const double v = warp_dd_sum(av), g = warp_dd_sum(ag);
+    if (lane == 0) { out_v[sp] = v; out_g[sp] = g; }
+}
+
+// K3b: Loss3 at ntrial delays per syncpoint (backtracking trial points / final objective)
+template <int SLOTS>
+__global__ void __launch_bounds__(kWarpsPerBlock * 32)
+sync_trials_kernel(DeviceData dd, SyncBatchDev b, const double* __restrict__ trial_delay, int ntrial,
+                   const unsigned char* __restrict__ sp_active, double* __restrict__ scratch) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const long long total = (long long)b.T * ntrial;
+    for (long long w = (long long)blockIdx.x * kWarpsPerBlock + warp; w < total;
+         w += (long long)gridDim.x * kWarpsPerBlock) {
+        const int t = (int)(w / ntrial), j = (int)(w % ntrial);
+        const SyncTask task = b.tasks[t];
+        if (!sp_active[task.sp]) continue;
+        double P[SLOTS][3];
+        const double m[3] = {b.m[3 * t], b.m[3 * t + 1], b.m[3 * t + 2]};
+        build_rows<SLOTS>(dd, task.fd, trial_delay[(size_t)task.sp * ntrial + j], lane, P);
+        const double v = warp_loss3<SLOTS>(P, m, b.k[t]);
+        if (lane == 0) scratch[(size_t)t * ntrial + j] = v;
+    }
+}
+
+__global__ void reduce_trials_kernel(SyncBatchDev b, int ntrial,
+                                     const unsigned char* __restrict__ sp_active,
+                                     const double* __restrict__ scratch, double* __restrict__ out) {
+    const int lane = threadIdx.x & 31;
+    const int w = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (w >= b.S * ntrial) return;
+    const int sp = w / ntrial, j = w % ntrial;
+    if (!sp_active[sp]) return;
+    DD acc = dd_zero();
+    for (int t = b.sp_begin[sp] + lane; t < b.sp_begin[sp + 1]; t += 32)
+        dd_add(acc, scratch[(size_t)t * ntrial + j]);
+    const double v = warp_dd_sum(acc);
+    if (lane == 0) out[(size_t)sp * ntrial + j] = v;
+}
+
+// ------------------------------------------------------------------------------------------
+// probes (tests only): one warp
+template <int SLOTS>
+__global__ void probe_problem_kernel(DeviceData dd, FrameDesc fd, double delay, double* out) {
+    const int lane = threadIdx.x & 31;
+    double P[SLOTS][3];
+    build_rows<SLOTS>(dd, fd, delay, lane, P);
+#pragma unroll
+    for (int s = 0; s < SLOTS; ++s) {
+        const int i = s * 32 + lane;
+        if (i < fd.n) { out[3 * i] = P[s][0]; out[3 * i + 1] = P[s][1]; out[3 * i + 2] = P[s][2]; }
+    }
+}
+__global__ void probe_log1p_kernel(const double* x, int n, double* out) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = log1p_nonneg(x[i]);
+}
+template <int SLOTS>
+__global__ void probe_loss_kernel(DeviceData dd, FrameDesc fd, double delay, const double* mp,
+                                  double k, double* out) {
+    const int lane = threadIdx.x & 31;
+    double P[SLOTS][3];
+    build_rows<SLOTS>(dd, fd, delay, lane, P);
+    const double m[3] = {mp[0], mp[1], mp[2]};
+    double g[3];
+    const double l3 = warp_loss3<SLOTS>(P, m, k);
+    const double l5 = warp_loss5<SLOTS>(P, m, k, g);
+    if (lane == 0) { out[0] = l3; out[1] = l5; out[2] = g[0]; out[3] = g[1]; out[4] = g[2]; }
+}
+template <int SLOTS>
+__global__ void probe_lbfgs_kernel(DeviceData dd, FrameDesc fd, double delay, double* mp, double k,
+                                   double* fout, int* stats) {
+    const int lane = threadIdx.x & 31;
+    double P[SLOTS][3];
+    build_rows<SLOTS>(dd, fd, delay, lane, P);
+    double m[3] = {mp[0], mp[1], mp[2]};
+    int it, ev;
+    const double f = warp_lbfgs<SLOTS>(P, m, k, it, ev);
+    if (lane == 0) {
+        mp[0] = m[0]; mp[1] = m[1]; mp[2] = m[2];
+        *fout = f;
+        stats[0] = it; stats[1] = ev;
+    }
+}
+template <int SLOTS>
+__global__ void probe_guess_kernel(DeviceData dd, FrameDesc fd, double delay, int iters,
+                                   uint64_t key_prefix, double* out) {
+    extern __shared__ double smem[];
+    constexpr int NP = SLOTS * 32;
+    const int lane = threadIdx.x & 31;
+    double P[SLOTS][3], np[SLOTS][3];
+    build_rows<SLOTS>(dd, fd, delay, lane, P);
+    stage_rows<SLOTS>(P, smem, NP, lane, np);
+    double M[3];
+    warp_ransac<SLOTS>(smem, NP, fd.n, iters, rng_task_key(key_prefix, fd.id), lane, np, M);
+    double pm[SLOTS];
+    const double nrm = warp_norm_PM<SLOTS>(P, M, pm);
+    if (lane == 0) { out[0] = M[0]; out[1] = M[1]; out[2] = M[2]; out[3] = clamp_k(1.0 / nrm * 1e2); }
+}
+
+__global__ void fp64_peak_kernel(int iters, double* sink) {
+    double a0 = threadIdx.x * 1e-9, a1 = a0 + 1, a2 = a0 + 2, a3 = a0 + 3, a4 = a0 + 4, a5 = a0 + 5,
+           a6 = a0 + 6, a7 = a0 + 7;
+    const double b = 1.0000001, c = 1e-9;
+    for (int i = 0; i < iters; ++i) {
+        a0 = fma(a0, b, c); a1 = fma(a1, b, c); a2 = fma(a2, b, c); a3 = fma(a3, b, c);
+        a4 = fma(a4, b, c); a5 = fma(a5, b, c); a6 = fma(a6, b, c); a7 = fma(a7, b, c);
+    }
+    const double s = ((a0 + a1) + (a2 + a3)) + ((a4 + a5) + (a6 + a7));
+    if (s == 12345.6789) sink[0] = s;
+}
+
+// ------------------------------------------------------------------------------------------
+int slots_for(int max_n) {
+    if (max_n <= 64) return 2;
+    if (max_n <= 128) return 4;
+    if (max_n <= 256) return 8;
+    return 16;
+}
+
+template <class K>
+int grid_for(K kernel, size_t smem, long long warps_needed) {
+    static int sm_count = 0;
+    if (!sm_count) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev);
+    }
+    int per_sm = 1;
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, kWarpsPerBlock * 32, smem);
+    if (per_sm < 1) per_sm = 1;
+    long long blocks_needed = (warps_needed + kWarpsPerBlock - 1) / kWarpsPerBlock;
+    long long cap = (long long)sm_count * per_sm;
+    long long g = blocks_needed < cap ? blocks_needed : cap;
+    return (int)(g < 1 ? 1 : g);
+}
+
+template <class K>
+void allow_smem(K kernel, size_t smem) {
+    cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+}
+
+#define RS_DISPATCH_SLOTS(max_n, ...)                              \
+    switch (slots_for(max_n)) {                                        \
+        case 2: { constexpr int SL = 2; __VA_ARGS__; } break;          \
+        case 4: { constexpr int SL = 4; __VA_ARGS__; } break;          \
+        case 8: { constexpr int SL = 8; __VA_ARGS__; } break;          \
+        default: { constexpr int SL = 16; __VA_ARGS__; } break;        \
+    }
+
+}  // namespace
+
+uint64_t launch_count() { return g_launches.load(); }
+
+void launch_presync_grid(const DeviceData& dd, const FrameDesc* d_frames, int F, int max_n,
+                         const double* d_delays, int D, uint64_t seed, uint64_t stream,
+                         uint64_t call_no, uint64_t idx_base, double* d_framecost, double* d_costs,
+                         unsigned* d_flags, cudaStream_t st, cudaEvent_t ev_begin, cudaEvent_t ev_end) {
+    if (F <= 0 || D <= 0) {
+        if (D > 0) cudaMemsetAsync(d_costs, 0, sizeof(double) * D, st);
+        return;
+    }
+    RS_DISPATCH_SLOTS(max_n, {
+        auto kern = presync_kernel<SL>;
+        const size_t smem = (size_t)kWarpsPerBlock * 3 * SL * 32 * sizeof(double);
+        allow_smem(kern, smem);
+        const int grid = grid_for(kern, smem, (long long)F * D);
+        if (ev_begin) cudaEventRecord(ev_begin, st);
+        kern<<<grid, kWarpsPerBlock * 32, smem, st>>>(dd, d_frames, F, d_delays, D, seed, stream,
+                                                      call_no, idx_base, d_framecost, d_flags);
+        if (ev_end) cudaEventRecord(ev_end, st);
+    });
+    reduce_rows_kernel<<<(D + 3) / 4, 128, 0, st>>>(d_framecost, D, F, d_costs);
+    g_launches += 2;
+}
+
+void launch_sync_init(const DeviceData& dd, const SyncBatchDev& b, const double* d_sp_delay,
+                      const uint64_t* d_sp_callno, const unsigned char* d_sp_active, uint64_t seed,
+                      cudaStream_t st) {
+    if (b.T <= 0) return;
+    RS_DISPATCH_SLOTS(b.max_n, {
+        auto kern = sync_init_kernel<SL>;
+        const size_t smem = (size_t)kWarpsPerBlock * 3 * SL * 32 * sizeof(double);
+        allow_smem(kern, smem);
+        const int grid = grid_for(kern, smem, b.T);
+        kern<<<grid, kWarpsPerBlock * 32, smem, st>>>(dd, b, d_sp_delay, d_sp_callno, d_sp_active, seed);
+    });
+    g_launches += 1;
+}
+
+void launch_sync_motion_fgrad(const DeviceData& dd, const SyncBatchDev& b, const double* d_sp_delay,
+                              const double* d_sp_x0, const unsigned char* d_sp_active,
+                              double* d_task_scratch, double* d_out_v, double* d_out_g,
+                              int* d_lbfgs_stats, cudaStream_t st) {
+    if (b.T <= 0) return;
+    RS_DISPATCH_SLOTS(b.max_n, {
+        auto kern = sync_motion_fgrad_kernel<SL>;
+        const int grid = grid_for(kern, 0, b.T);
+        kern<<<grid, kWarpsPerBlock * 32, 0, st>>>(dd, b, d_sp_delay, d_sp_x0, d_sp_active,
+                                                   d_task_scratch, d_lbfgs_stats);
+    });
+    reduce_fgrad_kernel<<<(b.S + 3) / 4, 128, 0, st>>>(b, d_sp_active, d_task_scratch, d_out_v, d_out_g);
+    g_launches += 2;
+}
+
+void launch_sync_trials(const DeviceData& dd, const SyncBatchDev& b, const double* d_trial_delay,
+                        int ntrial, const unsigned char* d_sp_active, double* d_task_scratch,
+                        double* d_out, cudaStream_t st) {
+    if (b.T <= 0 || ntrial <= 0) return;
+    RS_DISPATCH_SLOTS(b.max_n, {
+        auto kern = sync_trials_kernel<SL>;
+        const int grid = grid_for(kern, 0, (long long)b.T * ntrial);
+        kern<<<grid, kWarpsPerBlock * 32, 0, st>>>(dd, b, d_trial_delay, ntrial, d_sp_active, d_task_scratch);
+    });
+    reduce_trials_kernel<<<(b.S * ntrial + 3) / 4, 128, 0, st>>>(b, ntrial, d_sp_active, d_task_scratch, d_out);
+    g_launches += 2;
+}
+
+void launch_probe_problem_matrix(const DeviceData& dd, FrameDesc fd, double delay, double* d_P,
+                                 cudaStream_t st) {
+    RS_DISPATCH_SLOTS(fd.n, { probe_problem_kernel<SL><<<1, 32, 0, st>>>(dd, fd, delay, d_P); });
+    g_launches += 1;
+}
+void launch_probe_log1p(const double* d_x, int n, double* d_out, cudaStream_t st) {
+    probe_log1p_kernel<<<(n + 255) / 256, 256, 0, st>>>(d_x, n, d_out);
+    g_launches += 1;
+}
+void launch_probe_loss(const DeviceData& dd, FrameDesc fd, double delay, const double* d_m, double k,
+                       double* d_out, cudaStream_t st) {
+    RS_DISPATCH_SLOTS(fd.n, { probe_loss_kernel<SL><<<1, 32, 0, st>>>(dd, fd, delay, d_m, k, d_out); });
+    g_launches += 1;
+}
+void launch_probe_lbfgs(const DeviceData& dd, FrameDesc fd, double delay, double* d_m, double k,
+                        double* d_f, int* d_stats, cudaStream_t st) {
+    RS_DISPATCH_SLOTS(fd.n, { probe_lbfgs_kernel<SL><<<1, 32, 0, st>>>(dd, fd, delay, d_m, k, d_f, d_stats); });
+    g_launches += 1;
+}
+void launch_probe_guess(const DeviceData& dd, FrameDesc fd, double delay, int iters,
+                        uint64_t key_prefix, double* d_mk, cudaStream_t st) {
+    RS_DISPATCH_SLOTS(fd.n, {
+        auto kern = probe_guess_kernel<SL>;
+        const size_t smem = (size_t)3 * SL * 32 * sizeof(double);
+        kern<<<1, 32, smem, st>>>(dd, fd, delay, iters, key_prefix, d_mk);
+    });
+    g_launches += 1;
+}
+
+float run_fp64_peak(int blocks, int threads, int iters, double* d_sink, cudaStream_t st) {
+    cudaEvent_t e0, e1;
+    cudaEventCreate(&e0);
+    cudaEventCreate(&e1);
+    fp64_peak_kernel<<<blocks, threads, 0, st>>>(iters / 8 + 1, d_sink);  // warm-up
+    cudaEventRecord(e0, st);
+    fp64_peak_kernel<<<blocks, threads, 0, st>>>(iters, d_sink);
+    cudaEventRecord(e1, st);
+    cudaEventSynchronize(e1);
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, e0, e1);
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    g_launches += 2;
+    return ms;
+}
+
+}  // namespace rs

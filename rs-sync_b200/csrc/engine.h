@@ -1,0 +1,89 @@
+// Internal interface between the host side of the engine (capi.cpp, sync_solver.cpp) and the
+// sm_100a kernels (engine.cu).  Not part of the public boundary (include/rssync_b200.h is).
+#pragma once
+#include <cstdint>
+#include <cuda_runtime.h>
+
+namespace rs {
+
+constexpr int kMaxRaysPerFrame = 512;  // 16 slots x 32 lanes (one warp per frame task)
+constexpr double kNumericDiffStep = 1e-6;  // FrameState::kNumericDiffStep, core_private.hpp:38
+
+// One tracked frame inside the device arena (FrameData, core_private.hpp:8-13).
+struct FrameDesc {
+    int64_t id;   // caller's frame number (also an RNG key component)
+    int32_t off;  // index of the frame's first ray in every SoA plane (multiple of 32)
+    int32_t n;    // rays in the frame
+};
+
+// Read-only device state shared by all kernels (OptData, core_private.hpp:15-22).
+struct DeviceData {
+    const double* rec;  // gyro spline: nq records of {y[4], b[4], c[4], d[4]}
+    int nq;
+    double q0, sr;      // quats_start, sample_rate
+    // SoA ray planes: ts_a, ts_b, ra.x, ra.y, ra.z, rb.x, rb.y, rb.z
+    const double* plane[8];
+};
+
+enum RngStream : uint64_t { kStreamPreSync = 1, kStreamDebugPreSync = 2, kStreamSyncInit = 3 };
+
+// flags written by the PreSync kernel (panic conditions of core_private.cpp:76-83)
+enum : unsigned { kFlagP = 1u, kFlagM = 2u, kFlagR = 4u, kFlagRho = 8u };
+
+// ---- PreSync / DebugPreSync grid: cost[d] = sum_f framecost(d, f) -----------------------------
+// d_framecost: D x F scratch; d_costs: D outputs.  All pointers are device pointers.
+void launch_presync_grid(const DeviceData& dd, const FrameDesc* d_frames, int F, int max_n,
+                         const double* d_delays, int D, uint64_t seed, uint64_t stream,
+                         uint64_t call_no, uint64_t idx_base, double* d_framecost, double* d_costs,
+                         unsigned* d_flags, cudaStream_t st, cudaEvent_t ev_begin = nullptr,
+                         cudaEvent_t ev_end = nullptr);
+
+// ---- Sync: batched over syncpoints; tasks = (syncpoint, frame) --------------------------------
+struct SyncTask {
+    FrameDesc fd;
+    int32_t sp;   // syncpoint index inside the batch
+    int32_t pad;
+};
+struct SyncBatchDev {
+    const SyncTask* tasks;  // T tasks, grouped by syncpoint
+    int T;
+    int max_n;
+    const int* sp_begin;    // S+1 offsets into tasks
+    int S;
+    double* m;              // T x 3 translation directions (FrameState::motion_vec)
+    double* k;              // T   (FrameState::var_k)
+};
+// GuessMotion + GuessK at sp_delay[sp] (core_private.cpp:125-133, 218-223)
+void launch_sync_init(const DeviceData& dd, const SyncBatchDev& b, const double* d_sp_delay,
+                      const uint64_t* d_sp_callno, const unsigned char* d_sp_active, uint64_t seed,
+                      cudaStream_t st);
+// do_opt_motion (:262-296) at sp_delay, then Loss5 value at sp_x0 and Loss3 at sp_x0 -/+ h
+// (f_and_grad, :228-240); reduced per syncpoint into out_v[sp], out_g[sp].
+void launch_sync_motion_fgrad(const DeviceData& dd, const SyncBatchDev& b, const double* d_sp_delay,
+                              const double* d_sp_x0, const unsigned char* d_sp_active,
+                              double* d_task_scratch /* T x 3 */, double* d_out_v, double* d_out_g,
+                              int* d_lbfgs_stats /* T x 2 or null */, cudaStream_t st);
+// Loss3 summed per syncpoint at ntrial delays per syncpoint (simple_objective, :242-252)
+void launch_sync_trials(const DeviceData& dd, const SyncBatchDev& b, const double* d_trial_delay,
+                        int ntrial, const unsigned char* d_sp_active,
+                        double* d_task_scratch /* T x ntrial */, double* d_out /* S x ntrial */,
+                        cudaStream_t st);
+
+// ---- stage probes (tests only) ---------------------------------------------------------------
+void launch_probe_problem_matrix(const DeviceData& dd, FrameDesc fd, double delay, double* d_P,
+                                 cudaStream_t st);
+void launch_probe_log1p(const double* d_x, int n, double* d_out, cudaStream_t st);
+void launch_probe_loss(const DeviceData& dd, FrameDesc fd, double delay, const double* d_m, double k,
+                       double* d_out /* loss3, loss5, g0,g1,g2 */, cudaStream_t st);
+void launch_probe_lbfgs(const DeviceData& dd, FrameDesc fd, double delay, double* d_m, double k,
+                        double* d_f, int* d_stats, cudaStream_t st);
+void launch_probe_guess(const DeviceData& dd, FrameDesc fd, double delay, int iters, uint64_t key_prefix,
+                        double* d_mk /* m[3], k */, cudaStream_t st);
+
+// FP64 FMA peak microbenchmark: returns elapsed ms for `iters` x 8 dependent-chain FMAs per thread
+float run_fp64_peak(int blocks, int threads, int iters, double* d_sink, cudaStream_t st);
+
+// bookkeeping for gpu_launches reporting
+uint64_t launch_count();
+
+}  // namespace rs
