@@ -1,15 +1,24 @@
 // sm_100a kernels of the rs-sync synchronisation loss engine.
 //
-// Decomposition: ONE WARP PER (delay, frame) TASK.  A frame carries N <= 512 rays; lane l owns rays
-// l, l+32, ... ("slots", compile-time SLOTS = ceil(N/32) rounded to {2,4,8,16}).  Everything a
-// task needs between its first load and its single output double stays in registers / the warp's
-// slice of shared memory:
-//   rays + timestamps (SoA planes, coalesced 256 B per plane per slot)  ->
-//   problem-matrix rows (opt_compute_problem, core_private.cpp:15-32)    ->
-//   randomised least-quartile plane fit (opt_guess_translational_motion, :34-59) ->
-//   robust loss (pre_sync body :79-85  /  FrameState::Loss :92-123).
-// Cross-lane work is warp shuffles / REDUX only; there is no block-level synchronisation in
-// the hot loops.  The arithmetic contract is described in device_math.cuh.
+// Decomposition: ONE WARP PER (delay, frame) TASK.  A frame carries N <= 512 rays; lane l owns
+// rays l, l+32, ... ("slots").  A task runs in phases that each keep their working set where it
+// is cheapest:
+//   A  rows      rays + timestamps (SoA planes, coalesced 256 B per plane per slot) -> rows of
+//                the problem matrix (opt_compute_problem, core_private.cpp:15-32) -> the warp's
+//                slice of shared memory (raw rows + 1/|row|); a run-time loop over slots so the
+//                heavy body (2 spline evaluations, 2 de-rotations, 1 division) exists once in
+//                the instruction stream.
+//   B  hypotheses  lanes 0..19 each build one plane normal from two random rows
+//   C  test       normalised rows in registers (compile-time SLOTS), hypotheses broadcast by
+//                shuffle, quartile test by count + REDUX, exact quartile by a 32-bit-key
+//                quickselect only for hypotheses that win (opt_guess_translational_motion, :34-59)
+//   D  loss       robust loss of the winning normal, double-double warp sums (pre_sync body
+//                :79-85 / FrameState::Loss :92-123).
+// Cross-lane work is warp shuffles / REDUX only; there is no block-level synchronisation.
+// Instruction-cache footprint matters as much as FP64 issue here (the first version of this
+// kernel, fully unrolled over slots, was 91 KB of SASS and stalled 40 % of the time on
+// instruction fetch, profiles/r01_presync_v1.md): heavy bodies are written once, inside
+// run-time loops or __noinline__ functions.  The arithmetic contract is in device_math.cuh.
 #include "engine.h"
 
 #include <atomic>
@@ -23,79 +32,132 @@ namespace {
 
 constexpr unsigned FULL = 0xffffffffu;
 constexpr int kWarpsPerBlock = 8;
-constexpr unsigned long long kKeyMax = ~0ull;
+constexpr unsigned kNanHi = 0x7ff80000u;  // hi word of the canonical NaN: sorts above every r^2
 
 std::atomic<uint64_t> g_launches{0};
 
-// ------------------------------------------------------------------------------------------
-// rows of the problem matrix for this lane's slots; slots past the frame's end are zeroed
-template <int SLOTS>
-__device__ __forceinline__ void build_rows(const DeviceData& dd, const FrameDesc& fd, double delay,
-                                           int lane, double (&P)[SLOTS][3]) {
-#pragma unroll
-    for (int s = 0; s < SLOTS; ++s) {
-        P[s][0] = P[s][1] = P[s][2] = 0.0;
-        if (s * 32 < fd.n) {  // warp-uniform
-            const int i = s * 32 + lane;
-            const size_t g = (size_t)fd.off + i;  // planes are padded to a multiple of 32 per frame
-            const double tsa = __ldg(dd.plane[0] + g), tsb = __ldg(dd.plane[1] + g);
-            const double ax = __ldg(dd.plane[2] + g), ay = __ldg(dd.plane[3] + g),
-                         az = __ldg(dd.plane[4] + g);
-            const double bx = __ldg(dd.plane[5] + g), by = __ldg(dd.plane[6] + g),
-                         bz = __ldg(dd.plane[7] + g);
-            double row[3];
-            problem_row(dd.rec, dd.nq, dd.q0, dd.sr, delay, tsa, tsb, ax, ay, az, bx, by, bz, row);
-            if (i < fd.n) { P[s][0] = row[0]; P[s][1] = row[1]; P[s][2] = row[2]; }
-        }
-    }
+// per-warp shared-memory slice
+struct WarpSmem {
+    double* P;      // raw rows, SoA [3][NP]
+    double* inv;    // 1/|row| (1.0 where |row| < 1e-12, safe_normalize); reused for P.M in phase D
+    unsigned* key;  // hi words of the squared residuals during a select
+};
+__host__ __device__ constexpr size_t warp_smem_bytes(int NP, bool ransac) {
+    return ransac ? (size_t)NP * (3 * 8 + 8 + 4) : (size_t)NP * 3 * 8;
+}
+__device__ __forceinline__ WarpSmem warp_smem(unsigned char* base, int warp, int NP, bool ransac) {
+    unsigned char* p = base + (size_t)warp * warp_smem_bytes(NP, ransac);
+    WarpSmem w;
+    w.P = reinterpret_cast<double*>(p);
+    w.inv = w.P + 3 * NP;
+    w.key = reinterpret_cast<unsigned*>(w.inv + NP);
+    return w;
 }
 
-// k-th smallest (0-based) of the warp's keys restricted to keys < hi_excl.  Keys are the bit
-// patterns of non-negative doubles (order-preserving); empty slots hold kKeyMax.
+// ------------------------------------------------------------------------------------------
+// Phase A.  Rows of the problem matrix for the whole frame -> shared memory.  Entries past the
+// frame's last ray (up to NP) are zero rows with inv = NaN, which makes their residuals NaN in
+// phase C (sorted above everything) and their loss terms exactly 0 in phase D.
+template <bool WITH_INV>
+__device__ __forceinline__ unsigned build_rows_smem(const DeviceData& dd, const FrameDesc& fd,
+                                                    double delay, int lane, const WarpSmem& w,
+                                                    int NP) {
+    unsigned bad = 0;
+    const int nslots = (fd.n + 31) >> 5;
+    for (int s = 0; s < nslots; ++s) {
+        const int i = s * 32 + lane;
+        const size_t g = (size_t)fd.off + i;  // planes are padded to a multiple of 32 per frame
+        const double tsa = __ldg(dd.plane[0] + g), tsb = __ldg(dd.plane[1] + g);
+        const double ax = __ldg(dd.plane[2] + g), ay = __ldg(dd.plane[3] + g),
+                     az = __ldg(dd.plane[4] + g);
+        const double bx = __ldg(dd.plane[5] + g), by = __ldg(dd.plane[6] + g),
+                     bz = __ldg(dd.plane[7] + g);
+        double row[3];
+        problem_row(dd.rec, dd.nq, dd.q0, dd.sr, delay, tsa, tsb, ax, ay, az, bx, by, bz, row);
+        const bool valid = i < fd.n;
+        if (!valid) { row[0] = row[1] = row[2] = 0.0; }
+        if (!(is_finite(row[0]) && is_finite(row[1]) && is_finite(row[2]))) bad = kFlagP;
+        w.P[i] = row[0];
+        w.P[NP + i] = row[1];
+        w.P[2 * NP + i] = row[2];
+        if (WITH_INV) {
+            // safe_normalize (inline_utils.hpp:5-11): rows with |row| < 1e-12 stay unscaled
+            const double nrm = sqrt(dot3(row[0], row[1], row[2], row[0], row[1], row[2]));
+            double inv = (nrm < 1e-12) ? 1.0 : 1.0 / nrm;
+            if (!valid) inv = __longlong_as_double(0x7ff8000000000000LL);
+            w.inv[i] = inv;
+        }
+    }
+    for (int i = nslots * 32 + lane; i < NP; i += 32) {
+        w.P[i] = 0.0;
+        w.P[NP + i] = 0.0;
+        w.P[2 * NP + i] = 0.0;
+        if (WITH_INV) w.inv[i] = __longlong_as_double(0x7ff8000000000000LL);
+    }
+    __syncwarp();
+    return bad;
+}
+
+// ------------------------------------------------------------------------------------------
+// k-th smallest hi word (0-based) among the warp's keys, by quickselect over a per-lane bitmask
+// of still-active slots.  Returns H and, through cl / ce, count(h < H) and count(h == H).
 template <int SLOTS>
-__device__ __forceinline__ unsigned long long warp_select(const unsigned long long (&key)[SLOTS],
-                                                          int kth, unsigned long long hi_excl) {
-    unsigned long long lo = 0ull, hi = hi_excl;
+__device__ __forceinline__ unsigned warp_select_hi(const unsigned (&h)[SLOTS], const unsigned* skey,
+                                                   int kth, unsigned bound_hi, int lane, int& cl,
+                                                   int& ce) {
+    unsigned active = 0;
+#pragma unroll
+    for (int s = 0; s < SLOTS; ++s) active |= (h[s] <= bound_hi) ? (1u << s) : 0u;
+    int below = 0;  // elements already known to lie below the active range
     int round = 0;
     for (;;) {
-        bool has = false;
-        unsigned long long cand = 0ull;
-#pragma unroll
-        for (int s = 0; s < SLOTS; ++s) {
-            const bool in = (key[s] >= lo) && (key[s] < hi);
-            if (in && !has) { cand = key[s]; has = true; }
-        }
-        const unsigned bal = __ballot_sync(FULL, has);
-        const int rot = (round * 11) & 31;
+        const unsigned bal = __ballot_sync(FULL, active != 0u);
+        const int rot = (round * 11 + 5) & 31;
         const unsigned rb = __funnelshift_r(bal, bal, rot);
         const int src = (__ffs(rb) - 1 + rot) & 31;
-        const unsigned long long pivot = __shfl_sync(FULL, cand, src);
-        unsigned cl = 0, ce = 0;
+        const int slot = __shfl_sync(FULL, __ffs(active) - 1, src);
+        const unsigned pv = skey[slot * 32 + src];
+        unsigned lt = 0, eq = 0;
 #pragma unroll
         for (int s = 0; s < SLOTS; ++s) {
-            cl += (key[s] < pivot) ? 1u : 0u;
-            ce += (key[s] == pivot) ? 1u : 0u;
+            lt |= (h[s] < pv) ? (1u << s) : 0u;
+            eq |= (h[s] == pv) ? (1u << s) : 0u;
         }
-        const unsigned packed = __reduce_add_sync(FULL, cl | (ce << 16));
+        const unsigned packed =
+            __reduce_add_sync(FULL, (unsigned)__popc(lt & active) | ((unsigned)__popc(eq & active) << 16));
         const int nl = (int)(packed & 0xffffu), ne = (int)(packed >> 16);
-        if (kth < nl) hi = pivot;
-        else if (kth < nl + ne) return pivot;
-        else lo = pivot + 1;
+        if (kth < below + nl) {
+            active &= lt;
+        } else if (kth < below + nl + ne) {
+            cl = below + nl;
+            ce = ne;
+            return pv;
+        } else {
+            below += nl + ne;
+            active &= ~(lt | eq);
+        }
         ++round;
     }
 }
 
-// opt_guess_translational_motion (core_private.cpp:34-59).  sP: this warp's raw rows in shared
-// memory, SoA [3][NP].  np: row-normalised rows in registers.  Hypotheses are generated 32 at a
-// time (lane j builds hypothesis j), then tested one after another by the whole warp; a
-// hypothesis wins iff at least n/4+1 of its squared residuals lie below the best quartile so far
-// (equivalent to `med < least_med`, :53), and only then is its exact quartile selected.
+// Phases B + C: opt_guess_translational_motion (core_private.cpp:34-59).  A hypothesis wins iff
+// more than n/4 of its squared residuals lie below the best quartile so far (<=> `med <
+// least_med`, :53); only then is its exact quartile selected.  Residual keys are compared as
+// (hi word, lo word) pairs of the non-negative doubles, i.e. in exact double order.
 template <int SLOTS>
-__device__ __forceinline__ void warp_ransac(const double* sP, int NP, int n, int iters,
-                                            uint64_t key, int lane, const double (&np)[SLOTS][3],
-                                            double M[3]) {
+__device__ __forceinline__ void warp_ransac(const WarpSmem& w, int NP, int n, int iters,
+                                            uint64_t key, int lane, double M[3]) {
+    double np[SLOTS][3];
+#pragma unroll
+    for (int s = 0; s < SLOTS; ++s) {
+        const int i = s * 32 + lane;
+        const double inv = w.inv[i];  // :35-36
+        np[s][0] = w.P[i] * inv;
+        np[s][1] = w.P[NP + i] * inv;
+        np[s][2] = w.P[2 * NP + i] * inv;
+    }
     const int kth = n / 4;  // :52
-    unsigned long long least = kKeyMax;
+    unsigned least_hi = 0x7ff00000u, least_lo = 1u;  // just above +inf
     M[0] = M[1] = M[2] = 0.0;
     for (int j0 = 0; j0 < iters; j0 += 32) {
         double v[3] = {0.0, 0.0, 0.0};
@@ -104,8 +166,8 @@ __device__ __forceinline__ void warp_ransac(const double* sP, int NP, int n, int
             const uint32_t a = rng_index(key, (uint32_t)jj, 0u, (uint32_t)n);  // :42
             uint32_t b, kk = 1u;
             do { b = rng_index(key, (uint32_t)jj, kk++, (uint32_t)n); } while (b == a);  // :43
-            const double a0 = sP[a], a1 = sP[NP + a], a2 = sP[2 * NP + a];
-            const double b0 = sP[b], b1 = sP[NP + b], b2 = sP[2 * NP + b];
+            const double a0 = w.P[a], a1 = w.P[NP + a], a2 = w.P[2 * NP + a];
+            const double b0 = w.P[b], b1 = w.P[NP + b], b2 = w.P[2 * NP + b];
             const double c0 = fma(a1, b2, -(a2 * b1));
             const double c1 = fma(a2, b0, -(a0 * b2));
             const double c2 = fma(a0, b1, -(a1 * b0));
@@ -116,109 +178,122 @@ __device__ __forceinline__ void warp_ransac(const double* sP, int NP, int n, int
             const double vx = __shfl_sync(FULL, v[0], t);
             const double vy = __shfl_sync(FULL, v[1], t);
             const double vz = __shfl_sync(FULL, v[2], t);
-            unsigned long long keys[SLOTS];
-            unsigned below = 0;
+            double r2[SLOTS];
+            unsigned h[SLOTS];
+            unsigned below = 0, tie = 0;
 #pragma unroll
             for (int s = 0; s < SLOTS; ++s) {
                 const double r = dot3(np[s][0], np[s][1], np[s][2], vx, vy, vz);  // :48
-                const double r2 = r * r;                                            // :49
-                const bool valid = (s * 32 + lane) < n;
-                keys[s] = valid ? (unsigned long long)__double_as_longlong(r2) : kKeyMax;
-                below += (keys[s] < least) ? 1u : 0u;
+                r2[s] = r * r;                                                      // :49
+                h[s] = (unsigned)__double2hiint(r2[s]);
+                below += (h[s] < least_hi) ? 1u : 0u;
+                tie += (h[s] == least_hi) ? 1u : 0u;
             }
-            const int nbelow = (int)__reduce_add_sync(FULL, below);
-            if (nbelow > kth) {  // med < least_med
-                least = warp_select<SLOTS>(keys, kth, least);
+            unsigned packed = __reduce_add_sync(FULL, below | (tie << 16));
+            int nbelow = (int)(packed & 0xffffu);
+            if (packed >> 16) {  // hi-word ties with the threshold: settle them on the lo word
+                unsigned extra = 0;
+#pragma unroll
+                for (int s = 0; s < SLOTS; ++s)
+                    extra += (h[s] == least_hi && (unsigned)__double2loint(r2[s]) < least_lo) ? 1u : 0u;
+                nbelow += (int)__reduce_add_sync(FULL, extra);
+            }
+            if (nbelow > kth) {  // med < least_med: select the exact quartile
+#pragma unroll
+                for (int s = 0; s < SLOTS; ++s) w.key[s * 32 + lane] = h[s];
+                __syncwarp();
+                int cl, ce;
+                const unsigned H = warp_select_hi<SLOTS>(h, w.key, kth, least_hi, lane, cl, ce);
+                // rank (kth - cl) among the ce keys whose hi word is H, ordered by lo word
+                int rem = kth - cl;
+                unsigned cur = 0u, lo_ans = 0u;
+                for (;;) {
+                    unsigned mn = 0xffffffffu, c = 0u;
+#pragma unroll
+                    for (int s = 0; s < SLOTS; ++s) {
+                        const unsigned lo = (unsigned)__double2loint(r2[s]);
+                        if (h[s] == H && lo >= cur) mn = min(mn, lo);
+                    }
+                    mn = __reduce_min_sync(FULL, mn);
+#pragma unroll
+                    for (int s = 0; s < SLOTS; ++s)
+                        c += (h[s] == H && (unsigned)__double2loint(r2[s]) == mn) ? 1u : 0u;
+                    c = __reduce_add_sync(FULL, c);
+                    if (rem < (int)c) { lo_ans = mn; break; }
+                    rem -= (int)c;
+                    cur = mn + 1u;
+                }
+                least_hi = H;
+                least_lo = lo_ans;
                 M[0] = vx; M[1] = vy; M[2] = vz;
+                __syncwarp();
             }
         }
     }
 }
 
-// spill this lane's rows to the warp's shared slice and return the normalised copy
-template <int SLOTS>
-__device__ __forceinline__ void stage_rows(const double (&P)[SLOTS][3], double* sP, int NP, int lane,
-                                           double (&np)[SLOTS][3]) {
-#pragma unroll
-    for (int s = 0; s < SLOTS; ++s) {
-        const int i = s * 32 + lane;
-        sP[i] = P[s][0];
-        sP[NP + i] = P[s][1];
-        sP[2 * NP + i] = P[s][2];
-        safe_normalize3(P[s][0], P[s][1], P[s][2], np[s]);  // :35-36
-    }
-    __syncwarp();
-}
-
-// arma::norm(P * M) over the warp (core_private.cpp:79,132); pm[] receives this lane's products
-template <int SLOTS>
-__device__ __forceinline__ double warp_norm_PM(const double (&P)[SLOTS][3], const double M[3],
-                                               double (&pm)[SLOTS]) {
-    DD ss = dd_zero();
-#pragma unroll
-    for (int s = 0; s < SLOTS; ++s) {
-        pm[s] = dot3(P[s][0], P[s][1], P[s][2], M[0], M[1], M[2]);
-        dd_add(ss, pm[s] * pm[s]);
-    }
-    return sqrt(warp_dd_sum(ss));
-}
-
-// FrameState::Loss 3-arg (core_private.cpp:117-123) on register rows
-template <int SLOTS>
-__device__ __forceinline__ double warp_loss3(const double (&P)[SLOTS][3], const double m[3],
-                                             double k) {
-    const double scale = k / sqrt(dot3(m[0], m[1], m[2], m[0], m[1], m[2]));
+// ------------------------------------------------------------------------------------------
+// FrameState::Loss 3-arg (core_private.cpp:117-123) on the warp's shared rows
+__device__ __noinline__ double warp_loss3_smem(const double* __restrict__ sP, int NP, int nslots,
+                                               int lane, double m0, double m1, double m2, double k) {
+    const double scale = k / sqrt(dot3(m0, m1, m2, m0, m1, m2));
     DD acc = dd_zero();
-#pragma unroll
-    for (int s = 0; s < SLOTS; ++s) {
-        const double r = dot3(P[s][0], P[s][1], P[s][2], m[0], m[1], m[2]) * scale;
-        dd_add(acc, log1p_nonneg(r * r));  // empty slots: P = 0 -> log1p(0) = 0
+    for (int s = 0; s < nslots; ++s) {
+        const int i = s * 32 + lane;
+        const double r = dot3(sP[i], sP[NP + i], sP[2 * NP + i], m0, m1, m2) * scale;
+        dd_add(acc, log1p_nonneg(r * r));  // padding rows are 0 -> log1p(0) = 0
     }
     return warp_dd_sum(acc);
 }
 
-// FrameState::Loss 5-arg (core_private.cpp:92-115): value and d/dm in closed form
-template <int SLOTS>
-__device__ __forceinline__ double warp_loss5(const double (&P)[SLOTS][3], const double m[3],
-                                             double k, double g[3]) {
+// FrameState::Loss 5-arg (core_private.cpp:92-115): value and d/dm in closed form of the
+// forward-mode chain (inline_utils.hpp:19-48)
+struct Loss5 {
+    double f, g0, g1, g2;
+};
+__device__ __noinline__ Loss5 warp_loss5_smem(const double* __restrict__ sP, int NP, int nslots,
+                                              int lane, double m0, double m1, double m2, double k) {
     const double kk = k * k;
-    const double den = dot3(m[0], m[1], m[2], m[0], m[1], m[2]) / kk;
+    const double den = dot3(m0, m1, m2, m0, m1, m2) / kk;
     const double inv_den = 1.0 / den;
     DD L = dd_zero(), g0 = dd_zero(), g1 = dd_zero(), g2 = dd_zero(), su = dd_zero();
-#pragma unroll
-    for (int s = 0; s < SLOTS; ++s) {
-        const double v1 = dot3(P[s][0], P[s][1], P[s][2], m[0], m[1], m[2]);
+    for (int s = 0; s < nslots; ++s) {
+        const int i = s * 32 + lane;
+        const double p0 = sP[i], p1 = sP[NP + i], p2 = sP[2 * NP + i];
+        const double v1 = dot3(p0, p1, p2, m0, m1, m2);
         const double u = (v1 * v1) * inv_den;
         dd_add(L, log1p_nonneg(u));
-        const double w = 1.0 / (1.0 + u);
-        const double wv = w * v1;
-        dd_add(g0, wv * P[s][0]);
-        dd_add(g1, wv * P[s][1]);
-        dd_add(g2, wv * P[s][2]);
-        dd_add(su, w * u);
+        const double wgt = 1.0 / (1.0 + u);
+        const double wv = wgt * v1;
+        dd_add(g0, wv * p0);
+        dd_add(g1, wv * p1);
+        dd_add(g2, wv * p2);
+        dd_add(su, wgt * u);
     }
-    const double Ls = warp_dd_sum(L);
+    Loss5 out;
+    out.f = warp_dd_sum(L);
     const double G0 = warp_dd_sum(g0), G1 = warp_dd_sum(g1), G2 = warp_dd_sum(g2);
     const double SU = warp_dd_sum(su);
     const double c1 = 2.0 * inv_den;
     const double c2 = (c1 / kk) * SU;
-    g[0] = c1 * G0 - c2 * m[0];
-    g[1] = c1 * G1 - c2 * m[1];
-    g[2] = c1 * G2 - c2 * m[2];
-    return Ls;
+    out.g0 = c1 * G0 - c2 * m0;
+    out.g1 = c1 * G1 - c2 * m1;
+    out.g2 = c1 * G2 - c2 * m2;
+    return out;
 }
 
 // ens::L_BFGS on a 3-vector (call site core_private.cpp:264-294); every lane runs the same scalar
 // control flow on identical values, the objective is evaluated cooperatively.
-template <int SLOTS>
-__device__ __forceinline__ double warp_lbfgs(const double (&P)[SLOTS][3], double x[3], double k,
-                                             int& n_iters, int& n_evals) {
+__device__ __forceinline__ double warp_lbfgs(const double* sP, int NP, int nslots, int lane,
+                                             double x[3], double k, int& n_iters, int& n_evals) {
     constexpr int numBasis = 10, maxIterations = 200, maxTrials = 50;
     const double minGradientNorm = 1e-4, armijo = 1e-4, wolfe = 0.9, factr = 1e-15,
                  minStep = 1e-20, maxStep = 1e20;
     double S[numBasis][3], Y[numBasis][3], rho[numBasis], alpha[numBasis];
     double g[3], oldx[3], oldg[3], dir[3], trial[3];
-    double f = warp_loss5<SLOTS>(P, x, k, g);
+    Loss5 e = warp_loss5_smem(sP, NP, nslots, lane, x[0], x[1], x[2], k);
+    double f = e.f;
+    g[0] = e.g0; g[1] = e.g1; g[2] = e.g2;
     n_evals = 1;
     n_iters = 0;
     for (int it = 0; it != maxIterations; ++it) {
@@ -263,7 +338,9 @@ __device__ __forceinline__ double warp_lbfgs(const double (&P)[SLOTS][3], double
         int trials = 0;
         for (;;) {
             for (int c = 0; c < 3; ++c) trial[c] = x[c] + step * dir[c];
-            f = warp_loss5<SLOTS>(P, trial, k, g);
+            e = warp_loss5_smem(sP, NP, nslots, lane, trial[0], trial[1], trial[2], k);
+            f = e.f;
+            g[0] = e.g0; g[1] = e.g1; g[2] = e.g2;
             n_evals++;
             if (f < bestObj) { bestStep = step; bestObj = f; }
             trials++;
@@ -290,8 +367,21 @@ __device__ __forceinline__ double warp_lbfgs(const double (&P)[SLOTS][3], double
     return f;
 }
 
+// arma::norm(P * M) over the warp (core_private.cpp:79,132); P.M goes to pm_out[i]
+__device__ __forceinline__ double warp_norm_PM(const double* sP, int NP, int nslots, int lane,
+                                               const double M[3], double* pm_out) {
+    DD ss = dd_zero();
+    for (int s = 0; s < nslots; ++s) {
+        const int i = s * 32 + lane;
+        const double pm = dot3(sP[i], sP[NP + i], sP[2 * NP + i], M[0], M[1], M[2]);
+        if (pm_out) pm_out[i] = pm;
+        dd_add(ss, pm * pm);
+    }
+    return sqrt(warp_dd_sum(ss));
+}
+
 // ------------------------------------------------------------------------------------------
-// K1: PreSync / DebugPreSync grid.  task t -> (frame t / D, delay t % D): the 8 warps of a block
+// K1: PreSync / DebugPreSync grid.  task t -> (frame t / D, delay t % D): the warps of a block
 // work on the same frame, so its ray planes and spline window are served from L1.
 template <int SLOTS>
 __global__ void __launch_bounds__(kWarpsPerBlock * 32)
@@ -299,46 +389,29 @@ presync_kernel(DeviceData dd, const FrameDesc* __restrict__ frames, int F,
                const double* __restrict__ delays, int D, uint64_t seed, uint64_t stream,
                uint64_t call_no, uint64_t idx_base, double* __restrict__ framecost,
                unsigned* __restrict__ flags) {
-    extern __shared__ double smem[];
+    extern __shared__ __align__(16) unsigned char smem_raw[];
     constexpr int NP = SLOTS * 32;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    double* sP = smem + (size_t)warp * 3 * NP;
+    const WarpSmem w = warp_smem(smem_raw, warp, NP, true);
     const long long total = (long long)F * D;
     for (long long t = (long long)blockIdx.x * kWarpsPerBlock + warp; t < total;
          t += (long long)gridDim.x * kWarpsPerBlock) {
         const int fi = (int)(t / D), di = (int)(t % D);
         const FrameDesc fd = frames[fi];
-        const double delay = delays[di];
-        unsigned bad = 0;
-        double np[SLOTS][3];
-        {
-            double P[SLOTS][3];
-            build_rows<SLOTS>(dd, fd, delay, lane, P);
-#pragma unroll
-            for (int s = 0; s < SLOTS; ++s)
-                if (!(is_finite(P[s][0]) && is_finite(P[s][1]) && is_finite(P[s][2]))) bad |= kFlagP;
-            __syncwarp();  // previous task's readers of sP are done
-            stage_rows<SLOTS>(P, sP, NP, lane, np);
-        }
-        const uint64_t key = rng_task_key(rng_prefix(seed, stream, call_no, idx_base + (uint64_t)di), fd.id);
+        const int nslots = (fd.n + 31) >> 5;
+        __syncwarp();
+        unsigned bad = build_rows_smem<true>(dd, fd, delays[di], lane, w, NP);
+        const uint64_t key =
+            rng_task_key(rng_prefix(seed, stream, call_no, idx_base + (uint64_t)di), fd.id);
         double M[3];
-        warp_ransac<SLOTS>(sP, NP, fd.n, 20, key, lane, np, M);  // core_private.cpp:77
+        warp_ransac<SLOTS>(w, NP, fd.n, 20, key, lane, M);  // core_private.cpp:77
         if (!(is_finite(M[0]) && is_finite(M[1]) && is_finite(M[2]))) bad |= kFlagM;
         // :79-85
-        double pm[SLOTS];
-        DD ss = dd_zero();
-#pragma unroll
-        for (int s = 0; s < SLOTS; ++s) {
-            const int i = s * 32 + lane;
-            pm[s] = dot3(sP[i], sP[NP + i], sP[2 * NP + i], M[0], M[1], M[2]);
-            dd_add(ss, pm[s] * pm[s]);
-        }
-        const double k = clamp_k(1.0 / sqrt(warp_dd_sum(ss)) * 1e2);
+        const double k = clamp_k(1.0 / warp_norm_PM(w.P, NP, nslots, lane, M, w.inv) * 1e2);
         const double scale = k / sqrt(dot3(M[0], M[1], M[2], M[0], M[1], M[2]));
         DD acc = dd_zero();
-#pragma unroll
-        for (int s = 0; s < SLOTS; ++s) {
-            const double r = pm[s] * scale;
+        for (int s = 0; s < nslots; ++s) {
+            const double r = w.inv[s * 32 + lane] * scale;
             if (!is_finite(r)) bad |= kFlagR;
             const double rho = log1p_nonneg(r * r);
             if (!is_finite(rho)) bad |= kFlagRho;
@@ -371,24 +444,21 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32)
 sync_init_kernel(DeviceData dd, SyncBatchDev b, const double* __restrict__ sp_delay,
                  const uint64_t* __restrict__ sp_callno, const unsigned char* __restrict__ sp_active,
                  uint64_t seed) {
-    extern __shared__ double smem[];
+    extern __shared__ __align__(16) unsigned char smem_raw[];
     constexpr int NP = SLOTS * 32;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    double* sP = smem + (size_t)warp * 3 * NP;
+    const WarpSmem w = warp_smem(smem_raw, warp, NP, true);
     for (int t = blockIdx.x * kWarpsPerBlock + warp; t < b.T; t += gridDim.x * kWarpsPerBlock) {
         const SyncTask task = b.tasks[t];
         if (!sp_active[task.sp]) continue;
-        const double delay = sp_delay[task.sp];
-        double P[SLOTS][3], np[SLOTS][3];
-        build_rows<SLOTS>(dd, task.fd, delay, lane, P);
+        const int nslots = (task.fd.n + 31) >> 5;
         __syncwarp();
-        stage_rows<SLOTS>(P, sP, NP, lane, np);
+        build_rows_smem<true>(dd, task.fd, sp_delay[task.sp], lane, w, NP);
         const uint64_t key =
             rng_task_key(rng_prefix(seed, kStreamSyncInit, sp_callno[task.sp], 0), task.fd.id);
         double M[3];
-        warp_ransac<SLOTS>(sP, NP, task.fd.n, 200, key, lane, np, M);  // core_private.cpp:127
-        double pm[SLOTS];
-        const double nrm = warp_norm_PM<SLOTS>(P, M, pm);
+        warp_ransac<SLOTS>(w, NP, task.fd.n, 200, key, lane, M);  // core_private.cpp:127
+        const double nrm = warp_norm_PM(w.P, NP, nslots, lane, M, nullptr);
         if (lane == 0) {
             b.m[3 * t + 0] = M[0]; b.m[3 * t + 1] = M[1]; b.m[3 * t + 2] = M[2];
             b.k[t] = clamp_k(1.0 / nrm * 1e2);  // :132
@@ -396,40 +466,44 @@ sync_init_kernel(DeviceData dd, SyncBatchDev b, const double* __restrict__ sp_de
     }
 }
 
-// K2+K3a: per task, L-BFGS refinement of m at the syncpoint's delay (do_opt_motion), then the
-// three objective values the delay step needs (Loss5 at x0, Loss3 at x0 -/+ h).
-template <int SLOTS>
+// K2+K3a: per task, L-BFGS refinement of m at the syncpoint's delay (do_opt_motion, :262-296), then
+// the three objective values the delay step needs (Loss5 at x0, Loss3 at x0 -/+ h, :228-240).
 __global__ void __launch_bounds__(kWarpsPerBlock * 32)
-sync_motion_fgrad_kernel(DeviceData dd, SyncBatchDev b, const double* __restrict__ sp_delay,
+sync_motion_fgrad_kernel(DeviceData dd, SyncBatchDev b, int NP, const double* __restrict__ sp_delay,
                          const double* __restrict__ sp_x0,
                          const unsigned char* __restrict__ sp_active, double* __restrict__ scratch,
                          int* __restrict__ stats) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const WarpSmem w = warp_smem(smem_raw, warp, NP, false);
     for (int t = blockIdx.x * kWarpsPerBlock + warp; t < b.T; t += gridDim.x * kWarpsPerBlock) {
         const SyncTask task = b.tasks[t];
         if (!sp_active[task.sp]) continue;
-        double P[SLOTS][3];
+        const int nslots = (task.fd.n + 31) >> 5;
         double m[3] = {b.m[3 * t], b.m[3 * t + 1], b.m[3 * t + 2]};
         const double k = b.k[t];
-        build_rows<SLOTS>(dd, task.fd, sp_delay[task.sp], lane, P);
-        int it, ev;
-        warp_lbfgs<SLOTS>(P, m, k, it, ev);
-        if (lane == 0) {
-            b.m[3 * t] = m[0]; b.m[3 * t + 1] = m[1]; b.m[3 * t + 2] = m[2];
-            if (stats) { stats[2 * t] = it; stats[2 * t + 1] = ev; }
-        }
         const double x0 = sp_x0[task.sp];
-        double g[3];
-        build_rows<SLOTS>(dd, task.fd, x0, lane, P);
-        const double v = warp_loss5<SLOTS>(P, m, k, g);
-        build_rows<SLOTS>(dd, task.fd, x0 - kNumericDiffStep, lane, P);
-        const double l = warp_loss3<SLOTS>(P, m, k);
-        build_rows<SLOTS>(dd, task.fd, x0 + kNumericDiffStep, lane, P);
-        const double r = warp_loss3<SLOTS>(P, m, k);
-        if (lane == 0) {
-            scratch[3 * t] = v;
-            scratch[3 * t + 1] = l;
-            scratch[3 * t + 2] = r;
+        for (int j = 0; j < 4; ++j) {
+            const double delay = (j == 0)   ? sp_delay[task.sp]
+                                 : (j == 1) ? x0
+                                 : (j == 2) ? x0 - kNumericDiffStep
+                                            : x0 + kNumericDiffStep;
+            __syncwarp();
+            build_rows_smem<false>(dd, task.fd, delay, lane, w, NP);
+            if (j == 0) {
+                int it, ev;
+                warp_lbfgs(w.P, NP, nslots, lane, m, k, it, ev);
+                if (lane == 0) {
+                    b.m[3 * t] = m[0]; b.m[3 * t + 1] = m[1]; b.m[3 * t + 2] = m[2];
+                    if (stats) { stats[2 * t] = it; stats[2 * t + 1] = ev; }
+                }
+            } else if (j == 1) {
+                const Loss5 e = warp_loss5_smem(w.P, NP, nslots, lane, m[0], m[1], m[2], k);
+                if (lane == 0) scratch[3 * t] = e.f;
+            } else {
+                const double v = warp_loss3_smem(w.P, NP, nslots, lane, m[0], m[1], m[2], k);
+                if (lane == 0) scratch[3 * t + (j - 1)] = v;
+            }
         }
     }
 }
@@ -451,21 +525,24 @@ __global__ void reduce_fgrad_kernel(SyncBatchDev b, const unsigned char* __restr
 }
 
 // K3b: Loss3 at ntrial delays per syncpoint (backtracking trial points / final objective)
-template <int SLOTS>
 __global__ void __launch_bounds__(kWarpsPerBlock * 32)
-sync_trials_kernel(DeviceData dd, SyncBatchDev b, const double* __restrict__ trial_delay, int ntrial,
-                   const unsigned char* __restrict__ sp_active, double* __restrict__ scratch) {
+sync_trials_kernel(DeviceData dd, SyncBatchDev b, int NP, const double* __restrict__ trial_delay,
+                   int ntrial, const unsigned char* __restrict__ sp_active,
+                   double* __restrict__ scratch) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const WarpSmem w = warp_smem(smem_raw, warp, NP, false);
     const long long total = (long long)b.T * ntrial;
-    for (long long w = (long long)blockIdx.x * kWarpsPerBlock + warp; w < total;
-         w += (long long)gridDim.x * kWarpsPerBlock) {
-        const int t = (int)(w / ntrial), j = (int)(w % ntrial);
+    for (long long q = (long long)blockIdx.x * kWarpsPerBlock + warp; q < total;
+         q += (long long)gridDim.x * kWarpsPerBlock) {
+        const int t = (int)(q / ntrial), j = (int)(q % ntrial);
         const SyncTask task = b.tasks[t];
         if (!sp_active[task.sp]) continue;
-        double P[SLOTS][3];
-        const double m[3] = {b.m[3 * t], b.m[3 * t + 1], b.m[3 * t + 2]};
-        build_rows<SLOTS>(dd, task.fd, trial_delay[(size_t)task.sp * ntrial + j], lane, P);
-        const double v = warp_loss3<SLOTS>(P, m, b.k[t]);
+        const int nslots = (task.fd.n + 31) >> 5;
+        __syncwarp();
+        build_rows_smem<false>(dd, task.fd, trial_delay[(size_t)task.sp * ntrial + j], lane, w, NP);
+        const double v = warp_loss3_smem(w.P, NP, nslots, lane, b.m[3 * t], b.m[3 * t + 1],
+                                         b.m[3 * t + 2], b.k[t]);
         if (lane == 0) scratch[(size_t)t * ntrial + j] = v;
     }
 }
@@ -474,9 +551,9 @@ __global__ void reduce_trials_kernel(SyncBatchDev b, int ntrial,
                                      const unsigned char* __restrict__ sp_active,
                                      const double* __restrict__ scratch, double* __restrict__ out) {
     const int lane = threadIdx.x & 31;
-    const int w = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-    if (w >= b.S * ntrial) return;
-    const int sp = w / ntrial, j = w % ntrial;
+    const int q = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (q >= b.S * ntrial) return;
+    const int sp = q / ntrial, j = q % ntrial;
     if (!sp_active[sp]) return;
     DD acc = dd_zero();
     for (int t = b.sp_begin[sp] + lane; t < b.sp_begin[sp + 1]; t += 32)
@@ -487,42 +564,42 @@ __global__ void reduce_trials_kernel(SyncBatchDev b, int ntrial,
 
 // ------------------------------------------------------------------------------------------
 // probes (tests only): one warp
-template <int SLOTS>
-__global__ void probe_problem_kernel(DeviceData dd, FrameDesc fd, double delay, double* out) {
+__global__ void probe_problem_kernel(DeviceData dd, FrameDesc fd, int NP, double delay, double* out) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
     const int lane = threadIdx.x & 31;
-    double P[SLOTS][3];
-    build_rows<SLOTS>(dd, fd, delay, lane, P);
-#pragma unroll
-    for (int s = 0; s < SLOTS; ++s) {
-        const int i = s * 32 + lane;
-        if (i < fd.n) { out[3 * i] = P[s][0]; out[3 * i + 1] = P[s][1]; out[3 * i + 2] = P[s][2]; }
+    const WarpSmem w = warp_smem(smem_raw, 0, NP, false);
+    build_rows_smem<false>(dd, fd, delay, lane, w, NP);
+    for (int i = lane; i < fd.n; i += 32) {
+        out[3 * i] = w.P[i];
+        out[3 * i + 1] = w.P[NP + i];
+        out[3 * i + 2] = w.P[2 * NP + i];
     }
 }
 __global__ void probe_log1p_kernel(const double* x, int n, double* out) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) out[i] = log1p_nonneg(x[i]);
 }
-template <int SLOTS>
-__global__ void probe_loss_kernel(DeviceData dd, FrameDesc fd, double delay, const double* mp,
+__global__ void probe_loss_kernel(DeviceData dd, FrameDesc fd, int NP, double delay, const double* mp,
                                   double k, double* out) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
     const int lane = threadIdx.x & 31;
-    double P[SLOTS][3];
-    build_rows<SLOTS>(dd, fd, delay, lane, P);
-    const double m[3] = {mp[0], mp[1], mp[2]};
-    double g[3];
-    const double l3 = warp_loss3<SLOTS>(P, m, k);
-    const double l5 = warp_loss5<SLOTS>(P, m, k, g);
-    if (lane == 0) { out[0] = l3; out[1] = l5; out[2] = g[0]; out[3] = g[1]; out[4] = g[2]; }
+    const WarpSmem w = warp_smem(smem_raw, 0, NP, false);
+    const int nslots = (fd.n + 31) >> 5;
+    build_rows_smem<false>(dd, fd, delay, lane, w, NP);
+    const double l3 = warp_loss3_smem(w.P, NP, nslots, lane, mp[0], mp[1], mp[2], k);
+    const Loss5 e = warp_loss5_smem(w.P, NP, nslots, lane, mp[0], mp[1], mp[2], k);
+    if (lane == 0) { out[0] = l3; out[1] = e.f; out[2] = e.g0; out[3] = e.g1; out[4] = e.g2; }
 }
-template <int SLOTS>
-__global__ void probe_lbfgs_kernel(DeviceData dd, FrameDesc fd, double delay, double* mp, double k,
-                                   double* fout, int* stats) {
+__global__ void probe_lbfgs_kernel(DeviceData dd, FrameDesc fd, int NP, double delay, double* mp,
+                                   double k, double* fout, int* stats) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
     const int lane = threadIdx.x & 31;
-    double P[SLOTS][3];
-    build_rows<SLOTS>(dd, fd, delay, lane, P);
+    const WarpSmem w = warp_smem(smem_raw, 0, NP, false);
+    const int nslots = (fd.n + 31) >> 5;
+    build_rows_smem<false>(dd, fd, delay, lane, w, NP);
     double m[3] = {mp[0], mp[1], mp[2]};
     int it, ev;
-    const double f = warp_lbfgs<SLOTS>(P, m, k, it, ev);
+    const double f = warp_lbfgs(w.P, NP, nslots, lane, m, k, it, ev);
     if (lane == 0) {
         mp[0] = m[0]; mp[1] = m[1]; mp[2] = m[2];
         *fout = f;
@@ -532,16 +609,15 @@ __global__ void probe_lbfgs_kernel(DeviceData dd, FrameDesc fd, double delay, do
 template <int SLOTS>
 __global__ void probe_guess_kernel(DeviceData dd, FrameDesc fd, double delay, int iters,
                                    uint64_t key_prefix, double* out) {
-    extern __shared__ double smem[];
+    extern __shared__ __align__(16) unsigned char smem_raw[];
     constexpr int NP = SLOTS * 32;
     const int lane = threadIdx.x & 31;
-    double P[SLOTS][3], np[SLOTS][3];
-    build_rows<SLOTS>(dd, fd, delay, lane, P);
-    stage_rows<SLOTS>(P, smem, NP, lane, np);
+    const WarpSmem w = warp_smem(smem_raw, 0, NP, true);
+    const int nslots = (fd.n + 31) >> 5;
+    build_rows_smem<true>(dd, fd, delay, lane, w, NP);
     double M[3];
-    warp_ransac<SLOTS>(smem, NP, fd.n, iters, rng_task_key(key_prefix, fd.id), lane, np, M);
-    double pm[SLOTS];
-    const double nrm = warp_norm_PM<SLOTS>(P, M, pm);
+    warp_ransac<SLOTS>(w, NP, fd.n, iters, rng_task_key(key_prefix, fd.id), lane, M);
+    const double nrm = warp_norm_PM(w.P, NP, nslots, lane, M, nullptr);
     if (lane == 0) { out[0] = M[0]; out[1] = M[1]; out[2] = M[2]; out[3] = clamp_k(1.0 / nrm * 1e2); }
 }
 
@@ -609,7 +685,7 @@ void launch_presync_grid(const DeviceData& dd, const FrameDesc* d_frames, int F,
     }
     RS_DISPATCH_SLOTS(max_n, {
         auto kern = presync_kernel<SL>;
-        const size_t smem = (size_t)kWarpsPerBlock * 3 * SL * 32 * sizeof(double);
+        const size_t smem = (size_t)kWarpsPerBlock * warp_smem_bytes(SL * 32, true);
         allow_smem(kern, smem);
         const int grid = grid_for(kern, smem, (long long)F * D);
         if (ev_begin) cudaEventRecord(ev_begin, st);
@@ -627,7 +703,7 @@ void launch_sync_init(const DeviceData& dd, const SyncBatchDev& b, const double*
     if (b.T <= 0) return;
     RS_DISPATCH_SLOTS(b.max_n, {
         auto kern = sync_init_kernel<SL>;
-        const size_t smem = (size_t)kWarpsPerBlock * 3 * SL * 32 * sizeof(double);
+        const size_t smem = (size_t)kWarpsPerBlock * warp_smem_bytes(SL * 32, true);
         allow_smem(kern, smem);
         const int grid = grid_for(kern, smem, b.T);
         kern<<<grid, kWarpsPerBlock * 32, smem, st>>>(dd, b, d_sp_delay, d_sp_callno, d_sp_active, seed);
@@ -640,12 +716,12 @@ void launch_sync_motion_fgrad(const DeviceData& dd, const SyncBatchDev& b, const
                               double* d_task_scratch, double* d_out_v, double* d_out_g,
                               int* d_lbfgs_stats, cudaStream_t st) {
     if (b.T <= 0) return;
-    RS_DISPATCH_SLOTS(b.max_n, {
-        auto kern = sync_motion_fgrad_kernel<SL>;
-        const int grid = grid_for(kern, 0, b.T);
-        kern<<<grid, kWarpsPerBlock * 32, 0, st>>>(dd, b, d_sp_delay, d_sp_x0, d_sp_active,
-                                                   d_task_scratch, d_lbfgs_stats);
-    });
+    const int NP = slots_for(b.max_n) * 32;
+    const size_t smem = (size_t)kWarpsPerBlock * warp_smem_bytes(NP, false);
+    allow_smem(sync_motion_fgrad_kernel, smem);
+    const int grid = grid_for(sync_motion_fgrad_kernel, smem, b.T);
+    sync_motion_fgrad_kernel<<<grid, kWarpsPerBlock * 32, smem, st>>>(
+        dd, b, NP, d_sp_delay, d_sp_x0, d_sp_active, d_task_scratch, d_lbfgs_stats);
     reduce_fgrad_kernel<<<(b.S + 3) / 4, 128, 0, st>>>(b, d_sp_active, d_task_scratch, d_out_v, d_out_g);
     g_launches += 2;
 }
@@ -654,18 +730,20 @@ void launch_sync_trials(const DeviceData& dd, const SyncBatchDev& b, const doubl
                         int ntrial, const unsigned char* d_sp_active, double* d_task_scratch,
                         double* d_out, cudaStream_t st) {
     if (b.T <= 0 || ntrial <= 0) return;
-    RS_DISPATCH_SLOTS(b.max_n, {
-        auto kern = sync_trials_kernel<SL>;
-        const int grid = grid_for(kern, 0, (long long)b.T * ntrial);
-        kern<<<grid, kWarpsPerBlock * 32, 0, st>>>(dd, b, d_trial_delay, ntrial, d_sp_active, d_task_scratch);
-    });
+    const int NP = slots_for(b.max_n) * 32;
+    const size_t smem = (size_t)kWarpsPerBlock * warp_smem_bytes(NP, false);
+    allow_smem(sync_trials_kernel, smem);
+    const int grid = grid_for(sync_trials_kernel, smem, (long long)b.T * ntrial);
+    sync_trials_kernel<<<grid, kWarpsPerBlock * 32, smem, st>>>(dd, b, NP, d_trial_delay, ntrial,
+                                                                d_sp_active, d_task_scratch);
     reduce_trials_kernel<<<(b.S * ntrial + 3) / 4, 128, 0, st>>>(b, ntrial, d_sp_active, d_task_scratch, d_out);
     g_launches += 2;
 }
 
 void launch_probe_problem_matrix(const DeviceData& dd, FrameDesc fd, double delay, double* d_P,
                                  cudaStream_t st) {
-    RS_DISPATCH_SLOTS(fd.n, { probe_problem_kernel<SL><<<1, 32, 0, st>>>(dd, fd, delay, d_P); });
+    const int NP = slots_for(fd.n) * 32;
+    probe_problem_kernel<<<1, 32, warp_smem_bytes(NP, false), st>>>(dd, fd, NP, delay, d_P);
     g_launches += 1;
 }
 void launch_probe_log1p(const double* d_x, int n, double* d_out, cudaStream_t st) {
@@ -674,20 +752,21 @@ void launch_probe_log1p(const double* d_x, int n, double* d_out, cudaStream_t st
 }
 void launch_probe_loss(const DeviceData& dd, FrameDesc fd, double delay, const double* d_m, double k,
                        double* d_out, cudaStream_t st) {
-    RS_DISPATCH_SLOTS(fd.n, { probe_loss_kernel<SL><<<1, 32, 0, st>>>(dd, fd, delay, d_m, k, d_out); });
+    const int NP = slots_for(fd.n) * 32;
+    probe_loss_kernel<<<1, 32, warp_smem_bytes(NP, false), st>>>(dd, fd, NP, delay, d_m, k, d_out);
     g_launches += 1;
 }
 void launch_probe_lbfgs(const DeviceData& dd, FrameDesc fd, double delay, double* d_m, double k,
                         double* d_f, int* d_stats, cudaStream_t st) {
-    RS_DISPATCH_SLOTS(fd.n, { probe_lbfgs_kernel<SL><<<1, 32, 0, st>>>(dd, fd, delay, d_m, k, d_f, d_stats); });
+    const int NP = slots_for(fd.n) * 32;
+    probe_lbfgs_kernel<<<1, 32, warp_smem_bytes(NP, false), st>>>(dd, fd, NP, delay, d_m, k, d_f, d_stats);
     g_launches += 1;
 }
 void launch_probe_guess(const DeviceData& dd, FrameDesc fd, double delay, int iters,
                         uint64_t key_prefix, double* d_mk, cudaStream_t st) {
     RS_DISPATCH_SLOTS(fd.n, {
         auto kern = probe_guess_kernel<SL>;
-        const size_t smem = (size_t)3 * SL * 32 * sizeof(double);
-        kern<<<1, 32, smem, st>>>(dd, fd, delay, iters, key_prefix, d_mk);
+        kern<<<1, 32, warp_smem_bytes(SL * 32, true), st>>>(dd, fd, delay, iters, key_prefix, d_mk);
     });
     g_launches += 1;
 }

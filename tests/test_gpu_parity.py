@@ -197,7 +197,8 @@ def test_ragged_and_sparse_frames(rsb, oracle_loader):
 def test_variable_rate_ingest_matches_oracle(rsb, oracle_loader, w_tiny):
     w = w_tiny
     rng = np.random.default_rng(3)
-    ts = w.gyro_timestamps_us() + rng.integers(-150, 150, w.quats.shape[0])
+    # microsecond timestamps must be non-negative for the reference's unsigned arithmetic
+    ts = w.gyro_timestamps_us() + 10_000_000 + rng.integers(-150, 150, w.quats.shape[0])
     ts = np.sort(ts)
     g = rsb.SyncProblem()
     o = oracle_loader.OracleProblem()
