@@ -2,9 +2,10 @@
 NVCC     ?= /usr/local/cuda/bin/nvcc
 PKG      := rs-sync_b200
 SRC      := $(PKG)/csrc
-OUT      := $(PKG)/lib
+OUT      ?= $(PKG)/lib
+EXTRA    ?=
 ARCH     := -gencode arch=compute_100a,code=sm_100a
-NVFLAGS  := $(ARCH) -O3 -lineinfo -fmad=false -std=c++17 -Iinclude -I$(SRC) \
+NVFLAGS  := $(ARCH) -O3 -lineinfo -fmad=false -std=c++17 -Iinclude -I$(SRC) $(EXTRA) \
             -Xcompiler -fPIC,-ffp-contract=off,-Wall,-Wno-unused-function
 OBJS     := $(OUT)/engine.o $(OUT)/capi.o $(OUT)/host_ingest.o $(OUT)/cxx_dropin.o
 

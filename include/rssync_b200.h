@@ -95,6 +95,13 @@ int rssync_sync_batch(rssync_problem* p, int n, const double* initial_delay,
                       const int64_t* frame_begin, const int64_t* frame_end,
                       const double* search_center, const double* search_radius, double* out_cost,
                       double* out_delay);
+/* Same, with an explicit RNG call number per syncpoint (call_nos[i]) instead of consecutive values
+ * of the problem's counter, which is left untouched: lets several processes / GPUs each run a
+ * subset of a syncpoint list and reproduce exactly what one process would have computed. */
+int rssync_sync_batch_ex(rssync_problem* p, int n, const double* initial_delay,
+                         const int64_t* frame_begin, const int64_t* frame_end,
+                         const double* search_center, const double* search_radius,
+                         const uint64_t* call_nos, double* out_cost, double* out_delay);
 /* Per-iteration record of the most recent rssync_sync call (delay after the step, |step|), the
  * two numbers the reference prints to stderr (core_private.cpp:330).  Returns entries written. */
 int rssync_last_sync_trace(const rssync_problem* p, double* delays, double* steps, int cap);

@@ -114,6 +114,8 @@ class OracleProblem:
         self.h = C.c_void_p(self.L.orc_create())
         self.L.orc_set_threads(self.h, threads)
         self.L.orc_set_rng(self.h, seed, 0)
+        self._seed = seed
+        self._frames = set()
 
     def __del__(self):
         try:
@@ -126,6 +128,7 @@ class OracleProblem:
             raise OracleError(rc, self.L.orc_last_error(self.h).decode())
 
     def set_rng(self, seed, call_no=0):
+        self._seed = seed
         self.L.orc_set_rng(self.h, seed, call_no)
 
     def set_threads(self, n):
@@ -145,6 +148,7 @@ class OracleProblem:
     def SetTrackResult(self, frame, ts_a, ts_b, rays_a, rays_b, count):
         a = [np.ascontiguousarray(x, dtype=np.float64) for x in (ts_a, ts_b, rays_a, rays_b)]
         self._check(self.L.orc_set_track(self.h, int(frame), _dp(a[0]), _dp(a[1]), _dp(a[2]), _dp(a[3]), count))
+        self._frames.add(int(frame))
 
     def load(self, w):
         self.SetGyroQuaternions(w.quats, w.quats.shape[0], w.gyro_rate, w.gyro_t0)
@@ -175,7 +179,10 @@ class OracleProblem:
                                            _dp(td), _dp(ts), 400, C.byref(n), cnt))
         return c.value, d.value, td[:n.value].copy(), ts[:n.value].copy(), list(cnt)[:5]
 
-    def presync_grid(self, fb, fe, delays, stream=STREAM_PRESYNC, call_no=0, idx_base=0, frame_costs=False):
+    def presync_grid(self, fb, fe, delays, stream=STREAM_PRESYNC, call_no=0, offset_index_base=0,
+                     frame_costs=False, idx_base=None):
+        if idx_base is None:
+            idx_base = offset_index_base
         delays = np.ascontiguousarray(delays, dtype=np.float64)
         n = delays.shape[0]
         costs = np.empty(n)
@@ -189,7 +196,21 @@ class OracleProblem:
         return (costs, fc, flags.value) if frame_costs else costs
 
     def count_frames(self, fb, fe):
-        return sum(1 for f in getattr(self, "_frames", []) if fb <= f < fe) if hasattr(self, "_frames") else None
+        return sum(1 for f in self._frames if fb <= f < fe)
+
+    def sync_batch(self, initial_delay, frame_begin, frame_end, search_center, search_radius, call_nos=None):
+        """n independent Sync calls (the oracle runs them one after another)."""
+        n = len(initial_delay)
+        cen = np.broadcast_to(search_center, (n,))
+        rad = np.broadcast_to(search_radius, (n,))
+        cost, delay = np.empty(n), np.empty(n)
+        seed = self._seed
+        for i in range(n):
+            if call_nos is not None:
+                self.set_rng(seed, int(call_nos[i]))
+            cost[i], delay[i] = self.Sync(float(initial_delay[i]), int(frame_begin[i]), int(frame_end[i]),
+                                          float(cen[i]), float(rad[i]))
+        return cost, delay
 
     def problem_matrix(self, frame, delay, n):
         P = np.empty((n, 3))

@@ -16,7 +16,8 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "librssync_b200.so")
+# RSSYNC_B200_LIB selects an alternative build of the same library (kernel tuning experiments)
+LIB_PATH = os.environ.get("RSSYNC_B200_LIB") or os.path.join(_HERE, "lib", "librssync_b200.so")
 
 c_double_p = C.POINTER(C.c_double)
 c_i64_p = C.POINTER(C.c_int64)
@@ -33,6 +34,7 @@ C_ABI_SYMBOLS = [
     "rssync_flush", "rssync_get_stats", "rssync_measure_fp64_peak", "rssync_probe_gyro",
     "rssync_probe_problem_matrix", "rssync_probe_guess_motion", "rssync_probe_loss",
     "rssync_probe_lbfgs", "rssync_probe_log1p", "rssync_set_track_batch", "rssync_set_kernel_timing",
+    "rssync_sync_batch_ex",
 ]
 # Itanium-ABI symbols of the C++ drop-in face (same set the reference's librssync_core exports)
 CXX_ABI_SYMBOLS = [
@@ -85,6 +87,8 @@ def load_library():
     L.rssync_presync_delays.argtypes = [C.c_double, C.c_double, C.c_double, c_double_p, C.c_int]
     L.rssync_sync_batch.argtypes = [P, C.c_int, c_double_p, c_i64_p, c_i64_p, c_double_p, c_double_p,
                                     c_double_p, c_double_p]
+    L.rssync_sync_batch_ex.argtypes = [P, C.c_int, c_double_p, c_i64_p, c_i64_p, c_double_p, c_double_p,
+                                       C.POINTER(C.c_uint64), c_double_p, c_double_p]
     L.rssync_last_sync_trace.argtypes = [P, c_double_p, c_double_p, C.c_int]
     L.rssync_set_rng.argtypes = [P, C.c_uint64, C.c_uint64]
     L.rssync_call_counter.argtypes = [P]
@@ -255,7 +259,7 @@ class SyncProblem:
                                                stream, call_no, offset_index_base, _dp(costs), C.byref(flags)))
         return (costs, flags.value) if return_flags else costs
 
-    def sync_batch(self, initial_delay, frame_begin, frame_end, search_center, search_radius):
+    def sync_batch(self, initial_delay, frame_begin, frame_end, search_center, search_radius, call_nos=None):
         ini = _f64(initial_delay)
         n = ini.shape[0]
         fb = np.ascontiguousarray(frame_begin, dtype=np.int64)
@@ -263,6 +267,12 @@ class SyncProblem:
         cen = _f64(np.broadcast_to(search_center, (n,)))
         rad = _f64(np.broadcast_to(search_radius, (n,)))
         cost, delay = np.empty(n), np.empty(n)
+        if call_nos is not None:
+            cn = np.ascontiguousarray(call_nos, dtype=np.uint64)
+            self._check(self.L.rssync_sync_batch_ex(
+                self.h, n, _dp(ini), fb.ctypes.data_as(c_i64_p), fe.ctypes.data_as(c_i64_p), _dp(cen), _dp(rad),
+                cn.ctypes.data_as(C.POINTER(C.c_uint64)), _dp(cost), _dp(delay)))
+            return cost, delay
         self._check(self.L.rssync_sync_batch(self.h, n, _dp(ini), fb.ctypes.data_as(c_i64_p),
                                              fe.ctypes.data_as(c_i64_p), _dp(cen), _dp(rad), _dp(cost), _dp(delay)))
         return cost, delay

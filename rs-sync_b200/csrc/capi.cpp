@@ -94,9 +94,15 @@ struct rssync_problem {
     bool gyro_dirty = false;
     DevBuf<double> d_rec;
 
-    // ray arena: 8 SoA planes, frames appended in arrival order, each padded to 32 entries
+    // ray arena: 8 SoA planes + the original ray index, frames appended in arrival order, each
+    // padded to 32 entries.  Inside a frame the rays are stored sorted by ts_a, so the 32 lanes of
+    // a warp hit one or two spline records per load instead of ~11 (the rolling-shutter readout
+    // spans ~11 gyro samples); `orig` maps a stored ray back to the caller's index, which is what
+    // the RNG draws of the translation estimator refer to.
     PinBuf<double> h_plane[8];
     DevBuf<double> d_plane[8];
+    PinBuf<int32_t> h_orig;
+    DevBuf<int32_t> d_orig;
     size_t used = 0, uploaded = 0, garbage = 0;
     bool rays_full_dirty = false;
     std::map<int64_t, FrameDesc> frames;  // OptData::frame_data
@@ -118,6 +124,7 @@ struct rssync_problem {
     DevBuf<unsigned char> d_sp_active;
     DevBuf<double> d_probe;
 
+    std::vector<int32_t> sort_scratch;
     std::vector<double> trace_delay, trace_step;
     uint64_t h2d = 0, d2h = 0, sync_outer = 0, sync_evals = 0;
     bool kernel_timing = false;
@@ -131,6 +138,7 @@ struct rssync_problem {
         dd.q0 = q0;
         dd.sr = sr;
         for (int i = 0; i < 8; ++i) dd.plane[i] = d_plane[i].ptr;
+        dd.orig = d_orig.ptr;
         return dd;
     }
 };
@@ -167,6 +175,9 @@ int flush(rssync_problem* p) {
                              (p->used - from) * sizeof(double)))
                 return rc;
         }
+        CUDA_TRY(p, p->d_orig.reserve(p->h_orig.cap));
+        if (int rc = h2d(p, p->d_orig.ptr + from, p->h_orig.ptr + from, (p->used - from) * sizeof(int32_t)))
+            return rc;
         p->uploaded = p->used;
         p->rays_full_dirty = false;
     }
@@ -249,7 +260,7 @@ struct SyncPointState {
 
 int sync_batch_impl(rssync_problem* p, int n, const double* initial, const int64_t* fb,
                     const int64_t* fe, const double* center, const double* radius, double* out_cost,
-                    double* out_delay, bool record_trace) {
+                    double* out_delay, bool record_trace, const uint64_t* call_nos = nullptr) {
     if (int rc = require_gyro(p, "sync")) return rc;
     if (n <= 0) return RSSYNC_OK;
     // tasks: frames frame_begin <= f <= frame_end, INCLUSIVE (core_private.cpp:219)
@@ -269,8 +280,8 @@ int sync_batch_impl(rssync_problem* p, int n, const double* initial, const int64
     const int T = (int)tasks.size();
     constexpr int kTrials = 10;  // Backtrack max_iterations, core_private.cpp:226
     std::vector<uint64_t> callno(n);
-    for (int s = 0; s < n; ++s) callno[s] = p->call_no + (uint64_t)s;
-    p->call_no += (uint64_t)n;
+    for (int s = 0; s < n; ++s) callno[s] = call_nos ? call_nos[s] : p->call_no + (uint64_t)s;
+    if (!call_nos) p->call_no += (uint64_t)n;
 
     CUDA_TRY(p, p->d_tasks.reserve(std::max(T, 1)));
     CUDA_TRY(p, p->d_sp_begin.reserve(n + 1));
@@ -433,6 +444,7 @@ void rssync_destroy(rssync_problem* p) {
     cudaSetDevice(p->device);
     p->d_rec.release();
     for (int i = 0; i < 8; ++i) { p->h_plane[i].release(); p->d_plane[i].release(); }
+    p->h_orig.release(); p->d_orig.release();
     p->d_frames.release(); p->d_delays.release(); p->d_framecost.release(); p->d_costs.release();
     p->d_flags.release(); p->h_stage.release(); p->d_tasks.release(); p->d_sp_begin.release();
     p->d_lbfgs_stats.release(); p->d_m.release(); p->d_k.release(); p->d_task_scratch.release();
@@ -508,21 +520,30 @@ int rssync_set_track(rssync_problem* p, int64_t frame, const double* ts_a, const
             const size_t want = std::max<size_t>(need, std::max<size_t>(p->h_plane[0].cap * 2, 1u << 16));
             cudaSetDevice(p->device);
             for (int i = 0; i < 8; ++i) CUDA_TRY(p, p->h_plane[i].reserve(want, p->used));
+            CUDA_TRY(p, p->h_orig.reserve(want, p->used));
         }
         p->used = need;
     }
     double* pl[8];
     for (int i = 0; i < 8; ++i) pl[i] = p->h_plane[i].ptr + off;
-    for (size_t i = 0; i < count; ++i) {
-        pl[0][i] = ts_a[i];
-        pl[1][i] = ts_b[i];
-        pl[2][i] = rays_a[3 * i]; pl[3][i] = rays_a[3 * i + 1]; pl[4][i] = rays_a[3 * i + 2];
-        pl[5][i] = rays_b[3 * i]; pl[6][i] = rays_b[3 * i + 1]; pl[7][i] = rays_b[3 * i + 2];
+    int32_t* og = p->h_orig.ptr + off;
+    p->sort_scratch.resize(count);
+    for (size_t i = 0; i < count; ++i) p->sort_scratch[i] = (int32_t)i;
+    std::stable_sort(p->sort_scratch.begin(), p->sort_scratch.end(),
+                     [ts_a](int32_t a, int32_t b) { return ts_a[a] < ts_a[b]; });
+    for (size_t j = 0; j < count; ++j) {
+        const size_t i = (size_t)p->sort_scratch[j];
+        og[j] = (int32_t)i;
+        pl[0][j] = ts_a[i];
+        pl[1][j] = ts_b[i];
+        pl[2][j] = rays_a[3 * i]; pl[3][j] = rays_a[3 * i + 1]; pl[4][j] = rays_a[3 * i + 2];
+        pl[5][j] = rays_b[3 * i]; pl[6][j] = rays_b[3 * i + 1]; pl[7][j] = rays_b[3 * i + 2];
     }
-    for (size_t i = count; i < padded; ++i) {  // padding lanes: finite, masked out by n
-        pl[0][i] = count ? ts_a[0] : 0.0;
-        pl[1][i] = count ? ts_b[0] : 0.0;
-        for (int c = 2; c < 8; ++c) pl[c][i] = 0.0;
+    for (size_t j = count; j < padded; ++j) {  // padding lanes: finite, masked out by n
+        og[j] = (int32_t)j;
+        pl[0][j] = count ? pl[0][count - 1] : 0.0;
+        pl[1][j] = count ? pl[1][count - 1] : 0.0;
+        for (int c = 2; c < 8; ++c) pl[c][j] = 0.0;
     }
     p->frames[frame] = FrameDesc{frame, (int32_t)off, (int32_t)count};
     p->total_rays += count;
@@ -621,6 +642,14 @@ int rssync_sync_batch(rssync_problem* p, int n, const double* initial, const int
     if (!p || n < 0) return RSSYNC_E_INVALID;
     if (n && (!initial || !fb || !fe || !center || !radius || !out_cost || !out_delay)) return RSSYNC_E_INVALID;
     return sync_batch_impl(p, n, initial, fb, fe, center, radius, out_cost, out_delay, false);
+}
+
+int rssync_sync_batch_ex(rssync_problem* p, int n, const double* initial, const int64_t* fb,
+                         const int64_t* fe, const double* center, const double* radius,
+                         const uint64_t* call_nos, double* out_cost, double* out_delay) {
+    if (!p || n < 0) return RSSYNC_E_INVALID;
+    if (n && (!initial || !fb || !fe || !center || !radius || !out_cost || !out_delay)) return RSSYNC_E_INVALID;
+    return sync_batch_impl(p, n, initial, fb, fe, center, radius, out_cost, out_delay, false, call_nos);
 }
 
 int rssync_last_sync_trace(const rssync_problem* p, double* delays, double* steps, int cap) {

@@ -31,7 +31,13 @@ namespace rs {
 namespace {
 
 constexpr unsigned FULL = 0xffffffffu;
-constexpr int kWarpsPerBlock = 8;
+#ifndef RS_WPB
+#define RS_WPB 8
+#endif
+#ifndef RS_MINB
+#define RS_MINB 1
+#endif
+constexpr int kWarpsPerBlock = RS_WPB;
 constexpr unsigned kNanHi = 0x7ff80000u;  // hi word of the canonical NaN: sorts above every r^2
 
 std::atomic<uint64_t> g_launches{0};
@@ -77,15 +83,17 @@ __device__ __forceinline__ unsigned build_rows_smem(const DeviceData& dd, const 
         const bool valid = i < fd.n;
         if (!valid) { row[0] = row[1] = row[2] = 0.0; }
         if (!(is_finite(row[0]) && is_finite(row[1]) && is_finite(row[2]))) bad = kFlagP;
-        w.P[i] = row[0];
-        w.P[NP + i] = row[1];
-        w.P[2 * NP + i] = row[2];
+        // rays are stored sorted by ts_a; rows go back to the caller's order (RNG draws index it)
+        const int o = __ldg(dd.orig + g);
+        w.P[o] = row[0];
+        w.P[NP + o] = row[1];
+        w.P[2 * NP + o] = row[2];
         if (WITH_INV) {
             // safe_normalize (inline_utils.hpp:5-11): rows with |row| < 1e-12 stay unscaled
             const double nrm = sqrt(dot3(row[0], row[1], row[2], row[0], row[1], row[2]));
             double inv = (nrm < 1e-12) ? 1.0 : 1.0 / nrm;
             if (!valid) inv = __longlong_as_double(0x7ff8000000000000LL);
-            w.inv[i] = inv;
+            w.inv[o] = inv;
         }
     }
     for (int i = nslots * 32 + lane; i < NP; i += 32) {
@@ -180,16 +188,19 @@ __device__ __forceinline__ void warp_ransac(const WarpSmem& w, int NP, int n, in
             const double vz = __shfl_sync(FULL, v[2], t);
             double r2[SLOTS];
             unsigned h[SLOTS];
-            unsigned below = 0, tie = 0;
+            // hi words of r^2 (non-negative doubles, NaN = 0x7ff80000) are < 2^31, so the sign
+            // bit of (h - least_hi) is the `<` predicate and a zero difference flags a tie
+            unsigned below = 0, dmin = 0xffffffffu;
 #pragma unroll
             for (int s = 0; s < SLOTS; ++s) {
                 const double r = dot3(np[s][0], np[s][1], np[s][2], vx, vy, vz);  // :48
                 r2[s] = r * r;                                                      // :49
                 h[s] = (unsigned)__double2hiint(r2[s]);
-                below += (h[s] < least_hi) ? 1u : 0u;
-                tie += (h[s] == least_hi) ? 1u : 0u;
+                const unsigned d = h[s] - least_hi;
+                below += d >> 31;
+                dmin = min(dmin, d);
             }
-            unsigned packed = __reduce_add_sync(FULL, below | (tie << 16));
+            const unsigned packed = __reduce_add_sync(FULL, below | ((dmin == 0u ? 1u : 0u) << 16));
             int nbelow = (int)(packed & 0xffffu);
             if (packed >> 16) {  // hi-word ties with the threshold: settle them on the lo word
                 unsigned extra = 0;
@@ -384,7 +395,7 @@ __device__ __forceinline__ double warp_norm_PM(const double* sP, int NP, int nsl
 // K1: PreSync / DebugPreSync grid.  task t -> (frame t / D, delay t % D): the warps of a block
 // work on the same frame, so its ray planes and spline window are served from L1.
 template <int SLOTS>
-__global__ void __launch_bounds__(kWarpsPerBlock * 32)
+__global__ void __launch_bounds__(kWarpsPerBlock * 32, RS_MINB)
 presync_kernel(DeviceData dd, const FrameDesc* __restrict__ frames, int F,
                const double* __restrict__ delays, int D, uint64_t seed, uint64_t stream,
                uint64_t call_no, uint64_t idx_base, double* __restrict__ framecost,

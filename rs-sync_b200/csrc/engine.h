@@ -23,6 +23,7 @@ struct DeviceData {
     double q0, sr;      // quats_start, sample_rate
     // SoA ray planes: ts_a, ts_b, ra.x, ra.y, ra.z, rb.x, rb.y, rb.z
     const double* plane[8];
+    const int32_t* orig;  // caller's index of each stored ray (rays are stored sorted by ts_a)
 };
 
 enum RngStream : uint64_t { kStreamPreSync = 1, kStreamDebugPreSync = 2, kStreamSyncInit = 3 };

@@ -240,3 +240,22 @@ def test_error_conventions(rsb, w_tiny):
     with pytest.raises(rsb.RsSyncError) as e:
         g.PreSync(0.0, int(w.frame_ids[0]), int(w.frame_ids[0]) + 1, 0.005, 0.05)
     assert e.value.code == rsb.E_NONFINITE and e.value.message == "pre-sync: non-finite numbers in P"
+
+
+def test_golden_fixture(rsb, w_tiny):
+    """CUDA path against the committed golden vectors (tests/golden/tiny_curve.json)"""
+    import json, os
+    g = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "tiny_curve.json")))
+    w = w_tiny
+    p = rsb.SyncProblem(seed=100).load(w)
+    fb, fe = int(w.frame_ids[0]), int(w.frame_ids[-1]) + 1
+    delays = rsb.presync_delays(0.0, w.presync_step, w.presync_radius)
+    assert [float(d).hex() for d in delays] == g["delays_hex"]
+    costs = p.presync_grid(fb, fe, delays, call_no=0)
+    want = np.array([float.fromhex(h) for h in g["costs_hex"]])
+    assert rel_err(costs, want) <= TOL
+    assert int(np.argmin(costs)) == int(np.argmin(want))
+    p.set_rng(100, 1)
+    sc, sd = p.Sync(0.035, fb, fe - 1, 0.0, 0.2)
+    assert rel_err(sd, float.fromhex(g["sync_delay_hex"])) <= TOL
+    assert rel_err(sc, float.fromhex(g["sync_cost_hex"])) <= TOL

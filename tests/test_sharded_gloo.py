@@ -1,0 +1,69 @@
+"""world_size-2 gloo test of the multi-GPU host logic (rs-sync_b200/sharded.py) on CPU.  The
+compute backend is the oracle (tests may use it); what is under test is the sharding, RNG keying
+by global offset index / call number, the gather and the argmin."""
+import importlib
+import os
+import sys
+
+import numpy as np
+import torch.multiprocessing as mp
+
+from conftest import ROOT, workload
+
+
+def _worker(rank, world, port, q):
+    import torch.distributed as dist
+    sys.path.insert(0, ROOT)
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    sharded = importlib.import_module("rs-sync_b200.sharded")
+    synth = importlib.import_module("rs-sync_b200.synth")
+    from oracle import loader
+    w = synth.make_workload("tiny")
+    o = loader.OracleProblem(threads=1, seed=100).load(w)
+    fb, fe = int(w.frame_ids[0]), int(w.frame_ids[-1]) + 1
+    delays = loader.presync_delays(0.0, 0.005, 0.05)
+    curve = sharded.presync_grid_sharded(o, fb, fe, delays, stream=1, call_no=4, rank=rank, world=world)
+    best = sharded.presync_sharded(o, 0.0, fb, fe, 0.005, 0.05, delays, call_no=4, rank=rank, world=world)
+    ini = np.array([0.030, 0.034, 0.036])
+    fbs = np.array([fb, fb + 2, fb + 4])
+    c, d = sharded.sync_sharded(o, ini, fbs, fbs + 6, 0.0, 0.2, call_no_base=20, rank=rank, world=world)
+    if rank == 0:
+        q.put((curve, best, c, d))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_offset_and_syncpoint_sharding_world2(oracle_loader):
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29500 + os.getpid() % 2000
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    curve, best, c, d = q.get(timeout=240)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    # single-process answers
+    w = workload("tiny")
+    o = oracle_loader.OracleProblem(threads=2, seed=100).load(w)
+    fb, fe = int(w.frame_ids[0]), int(w.frame_ids[-1]) + 1
+    delays = oracle_loader.presync_delays(0.0, 0.005, 0.05)
+    whole = o.presync_grid(fb, fe, delays, call_no=4)
+    assert np.array_equal(curve, whole)
+    o.set_rng(100, 4)
+    assert best == o.PreSync(0.0, fb, fe, 0.005, 0.05)
+    o.set_rng(100, 20)
+    seq = [o.Sync(x, fb + 2 * i, fb + 2 * i + 6, 0.0, 0.2) for i, x in enumerate((0.030, 0.034, 0.036))]
+    assert np.array_equal(c, [s[0] for s in seq]) and np.array_equal(d, [s[1] for s in seq])
+
+
+def test_shard_range_partitions():
+    sharded = importlib.import_module("rs-sync_b200.sharded")
+    for n in (0, 1, 7, 200, 201, 2001):
+        for world in (1, 2, 3, 8):
+            parts = [sharded.shard_range(n, r, world) for r in range(world)]
+            assert parts[0][0] == 0 and parts[-1][1] == n
+            assert all(parts[i][1] == parts[i + 1][0] for i in range(world - 1))
