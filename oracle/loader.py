@@ -52,6 +52,7 @@ def lib():
     L.orc_destroy.argtypes = [C.c_void_p]
     L.orc_set_threads.argtypes = [C.c_void_p, C.c_int]
     L.orc_set_rng.argtypes = [C.c_void_p, C.c_uint64, C.c_uint64]
+    L.orc_set_strict.argtypes = [C.c_void_p, C.c_int, c_i64_p, C.c_int]
     L.orc_call_no.argtypes = [C.c_void_p]
     L.orc_call_no.restype = C.c_uint64
     L.orc_set_gyro_fixed.argtypes = [C.c_void_p, c_double_p, C.c_size_t, C.c_double, C.c_double]
@@ -133,6 +134,15 @@ class OracleProblem:
 
     def set_threads(self, n):
         self.L.orc_set_threads(self.h, n)
+
+    def set_strict(self, strict=True, frame_order=None):
+        """reference-order arithmetic (oracle_strict.hpp); frame_order = the reference's
+        unordered_map iteration order, so per-frame sums are accumulated in the same sequence"""
+        if frame_order is None:
+            self.L.orc_set_strict(self.h, 1 if strict else 0, None, 0)
+        else:
+            fo = np.ascontiguousarray(frame_order, dtype=np.int64)
+            self.L.orc_set_strict(self.h, 1 if strict else 0, fo.ctypes.data_as(c_i64_p), fo.shape[0])
 
     def SetGyroQuaternions(self, *args):
         if len(args) == 4:

@@ -12,6 +12,7 @@
 // reference seeds mt19937 from random_device) and ens::L_BFGS (un-vendored third-party code,
 // restated from its published algorithm).
 #include "oracle_math.hpp"
+#include "oracle_strict.hpp"
 
 #include <algorithm>
 #include <atomic>
@@ -41,6 +42,11 @@ struct Oracle {
     uint64_t seed = 100, call_no = 0;
     int threads = 1;
     std::string err;
+    // strict mode (oracle_strict.hpp): the reference's own expression order, plain sums, libm
+    // log1p, and frames visited in `frame_order` (the reference's unordered_map order) — used to
+    // compare control flow with the compiled reference bit for bit
+    bool strict = false;
+    std::vector<int64_t> frame_order;
 };
 
 enum { OK = 0, E_INVALID = 1, E_NONFINITE = 2, E_ORDER = 3, E_STATE = 4 };
@@ -81,6 +87,12 @@ void slerp(const double p[4], const double qin[4], double t, double out[4]) {
 
 // opt_compute_problem (core_private.cpp:15-32)
 void problem_matrix(const Oracle& o, const Frame& f, double delay, double* P) {
+    if (o.strict) {
+        for (int i = 0; i < f.n; ++i)
+            orc_strict::problem_row(o.rec.data(), o.nq, o.q0, o.sr, delay, f.ts_a[i], f.ts_b[i],
+                                    &f.ra[3 * i], &f.rb[3 * i], P + 3 * i);
+        return;
+    }
     for (int i = 0; i < f.n; ++i)
         problem_row(o.rec.data(), o.nq, o.q0, o.sr, delay, f.ts_a[i], f.ts_b[i], &f.ra[3 * i],
                     &f.rb[3 * i], P + 3 * i);
@@ -88,9 +100,30 @@ void problem_matrix(const Oracle& o, const Frame& f, double delay, double* P) {
 
 // opt_guess_translational_motion (core_private.cpp:34-59) with the pinned RNG.
 void guess_motion(const double* P, int n, int iters, uint64_t key, double best[3],
-                  std::vector<double>& nP, std::vector<double>& r2) {
+                  std::vector<double>& nP, std::vector<double>& r2, bool strict = false) {
     nP.resize((size_t)n * 3);
     r2.resize(n);
+    if (strict) {
+        for (int i = 0; i < n; ++i) orc_strict::safe_normalize3(P + 3 * i, &nP[3 * i]);
+        double least = std::numeric_limits<double>::infinity();
+        best[0] = best[1] = best[2] = 0.0;
+        for (int it = 0; it < iters; ++it) {
+            uint32_t a = rng_index(key, it, 0, n);
+            uint32_t b, k = 1;
+            do { b = rng_index(key, it, k++, n); } while (b == a);
+            double c[3], v[3];
+            orc_strict::cross3(P + 3 * a, P + 3 * b, c);
+            orc_strict::safe_normalize3(c, v);
+            for (int i = 0; i < n; ++i) {
+                double r = orc_strict::dot3(&nP[3 * i], v);
+                r2[i] = r * r;
+            }
+            std::nth_element(r2.begin(), r2.begin() + n / 4, r2.end());
+            double med = r2[n / 4];
+            if (med < least) { least = med; best[0] = v[0]; best[1] = v[1]; best[2] = v[2]; }
+        }
+        return;
+    }
     for (int i = 0; i < n; ++i) safe_normalize3(P + 3 * i, &nP[3 * i]);  // :35-36
     double least = std::numeric_limits<double>::infinity();
     best[0] = best[1] = best[2] = 0.0;
@@ -132,8 +165,18 @@ double presync_frame_cost(const Oracle& o, const Frame& f, double delay, uint64_
     problem_matrix(o, f, delay, P.data());
     if (flags && !all_finite(P.data(), P.size())) *flags |= 1;
     double M[3];
-    guess_motion(P.data(), f.n, 20, key, M, nP, r2);
+    guess_motion(P.data(), f.n, 20, key, M, nP, r2, o.strict);
     if (flags && !all_finite(M, 3)) *flags |= 2;
+    if (o.strict) {
+        double k = clamp_k(1 / orc_strict::norm_PM(P.data(), f.n, M) * 1e2);
+        double scale = k / orc_strict::norm_seq(M, 3);
+        double acc = 0.0;
+        for (int i = 0; i < f.n; ++i) {
+            double r = orc_strict::dot3(&P[3 * i], M) * scale;
+            acc += std::sqrt(std::log1p(r * r));
+        }
+        return std::sqrt(acc);
+    }
     double k = clamp_k(1.0 / norm_PM(P.data(), f.n, M) * 1e2);  // :79
     double scale = k / std::sqrt(dot3(M, M));                     // :80
     DD acc;
@@ -150,6 +193,13 @@ double presync_frame_cost(const Oracle& o, const Frame& f, double delay, uint64_
 std::vector<const std::pair<const int64_t, Frame>*> select_frames(const Oracle& o, int64_t fb,
                                                                   int64_t fe_exclusive) {
     std::vector<const std::pair<const int64_t, Frame>*> v;
+    if (!o.frame_order.empty()) {  // strict mode: the reference's unordered_map order
+        for (int64_t id : o.frame_order) {
+            auto it = o.frames.find(id);
+            if (it != o.frames.end() && id >= fb && id < fe_exclusive) v.push_back(&*it);
+        }
+        return v;
+    }
     for (auto& kv : o.frames)
         if (kv.first >= fb && kv.first < fe_exclusive) v.push_back(&kv);
     return v;
@@ -194,8 +244,13 @@ int presync_grid(Oracle& o, int64_t fb, int64_t fe, const double* delays, int nd
     int flags = 0;
     for (int d = 0; d < nd; ++d) {
         DD acc;
-        for (size_t j = 0; j < nf; ++j) { acc.add(fc[d * nf + j]); flags |= fl[d * nf + j]; }
-        costs[d] = acc.value();
+        double plain = 0.0;
+        for (size_t j = 0; j < nf; ++j) {
+            acc.add(fc[d * nf + j]);
+            plain += fc[d * nf + j];
+            flags |= fl[d * nf + j];
+        }
+        costs[d] = o.strict ? plain : acc.value();
     }
     if (frame_costs) std::copy(fc.begin(), fc.end(), frame_costs);
     if (flags_out) *flags_out = flags;
@@ -224,7 +279,7 @@ double loss3_P(const double* P, int n, const double m[3], double k) {
 double loss3(const Oracle& o, const Frame& f, double delay, const double m[3], double k) {
     std::vector<double> P((size_t)f.n * 3);
     problem_matrix(o, f, delay, P.data());
-    return loss3_P(P.data(), f.n, m, k);
+    return o.strict ? orc_strict::loss3_P(P.data(), f.n, m, k) : loss3_P(P.data(), f.n, m, k);
 }
 
 // FrameState::Loss, 5-argument form (core_private.cpp:92-115): value and d/dm in closed form
@@ -262,8 +317,10 @@ double loss5_P(const double* P, int n, const double m[3], double k, double grad[
 // overrides maxIterations=200, minGradientNorm=1e-4 (:265-266).  PARITY UNPINNED for this
 // function: ensmallen is not available to check against.
 struct LbfgsStats { int iters = 0, evals = 0; };
-template <class FG>
-double lbfgs3(FG&& fg, double x[3], LbfgsStats* st) {
+struct DotSpec { double operator()(const double* a, const double* b) const { return orc::dot3(a, b); } };
+struct DotStrict { double operator()(const double* a, const double* b) const { return orc_strict::dot3(a, b); } };
+template <class FG, class DOT = DotSpec>
+double lbfgs3(FG&& fg, double x[3], LbfgsStats* st, DOT dot3 = DOT()) {
     const int numBasis = 10, maxIterations = 200, maxTrials = 50;
     const double minGradientNorm = 1e-4, armijo = 1e-4, wolfe = 0.9, factr = 1e-15,
                  minStep = 1e-20, maxStep = 1e20;
@@ -356,22 +413,28 @@ int sync_impl(Oracle& o, double initial_delay, int64_t fb, int64_t fe, double ce
     if (o.nq < 2) { o.err = "gyro quaternions not set"; return E_STATE; }
     double delay = initial_delay;
     std::vector<FrameState> fs;
-    for (auto& kv : o.frames) {  // :218-223, inclusive frame_end
-        if (kv.first < fb || kv.first > fe) continue;
-        if (kv.second.n < 2) { o.err = "frame with fewer than 2 rays"; return E_INVALID; }
+    std::vector<int64_t> order;
+    if (!o.frame_order.empty()) order = o.frame_order;
+    else for (auto& kv : o.frames) order.push_back(kv.first);
+    for (int64_t id : order) {  // :218-223, inclusive frame_end
+        auto itf = o.frames.find(id);
+        if (itf == o.frames.end() || id < fb || id > fe) continue;
+        if (itf->second.n < 2) { o.err = "frame with fewer than 2 rays"; return E_INVALID; }
         FrameState s;
-        s.f = &kv.second;
-        s.id = kv.first;
+        s.f = &itf->second;
+        s.id = id;
         fs.push_back(s);
     }
+    const bool strict = o.strict;
     long n_build = 0, n_lbfgs_eval = 0, n_lbfgs_iter = 0, n_outer = 0;
     parallel_for(o.threads, fs.size(), [&](size_t j) {  // GuessMotion + GuessK, :125-133
         FrameState& s = fs[j];
         std::vector<double> P((size_t)s.f->n * 3), nP, r2;
         problem_matrix(o, *s.f, delay, P.data());
         uint64_t key = rng_task_key(o.seed, kStreamSyncInit, call_no, 0, s.id);
-        guess_motion(P.data(), s.f->n, 200, key, s.m, nP, r2);
-        s.k = clamp_k(1.0 / norm_PM(P.data(), s.f->n, s.m) * 1e2);
+        guess_motion(P.data(), s.f->n, 200, key, s.m, nP, r2, strict);
+        s.k = strict ? clamp_k(1 / orc_strict::norm_PM(P.data(), s.f->n, s.m) * 1e2)
+                     : clamp_k(1.0 / norm_PM(P.data(), s.f->n, s.m) * 1e2);
     });
     n_build += (long)fs.size();
 
@@ -379,6 +442,11 @@ int sync_impl(Oracle& o, double initial_delay, int64_t fb, int64_t fe, double ce
         std::vector<double> v(fs.size());
         parallel_for(o.threads, fs.size(),
                      [&](size_t j) { v[j] = loss3(o, *fs[j].f, x, fs[j].m, fs[j].k); });
+        if (strict) {
+            double acc = 0.0;
+            for (double t : v) acc += t;
+            return acc;
+        }
         DD acc;
         for (double t : v) acc.add(t);
         return acc.value();
@@ -391,10 +459,17 @@ int sync_impl(Oracle& o, double initial_delay, int64_t fb, int64_t fe, double ce
             std::vector<double> P((size_t)s.f->n * 3);
             double g[3];
             problem_matrix(o, *s.f, x, P.data());
-            v[j] = loss5_P(P.data(), s.f->n, s.m, s.k, g);
+            v[j] = strict ? orc_strict::loss5_P(P.data(), s.f->n, s.m, s.k, g)
+                          : loss5_P(P.data(), s.f->n, s.m, s.k, g);
             l[j] = loss3(o, *s.f, x - h, s.m, s.k);
             r[j] = loss3(o, *s.f, x + h, s.m, s.k);
         });
+        if (strict) {
+            double av = 0.0, ag = 0.0;
+            for (size_t j = 0; j < fs.size(); ++j) { av += v[j]; ag += (r[j] - l[j]) / 2 / h; }
+            grad = ag;
+            return av;
+        }
         DD av, ag;
         for (size_t j = 0; j < fs.size(); ++j) {
             av.add(v[j]);
@@ -417,8 +492,12 @@ int sync_impl(Oracle& o, double initial_delay, int64_t fb, int64_t fe, double ce
             problem_matrix(o, *s.f, delay, P.data());
             const int n = s.f->n;
             const double k = s.k;
-            lbfgs3([&](const double* x, double* g) { return loss5_P(P.data(), n, x, k, g); }, s.m,
-                   &st[j]);
+            if (strict)
+                lbfgs3([&](const double* x, double* g) { return orc_strict::loss5_P(P.data(), n, x, k, g); },
+                       s.m, &st[j], DotStrict());
+            else
+                lbfgs3([&](const double* x, double* g) { return loss5_P(P.data(), n, x, k, g); }, s.m,
+                       &st[j]);
         });
         for (auto& t : st) { n_lbfgs_eval += t.evals; n_lbfgs_iter += t.iters; }
         n_build += (long)fs.size();
@@ -466,6 +545,11 @@ void* orc_create() { return new Oracle(); }
 void orc_destroy(void* h) { delete (Oracle*)h; }
 const char* orc_last_error(void* h) { return ((Oracle*)h)->err.c_str(); }
 void orc_set_threads(void* h, int t) { ((Oracle*)h)->threads = t < 1 ? 1 : t; }
+void orc_set_strict(void* h, int strict, const int64_t* frame_order, int n) {
+    Oracle& o = *(Oracle*)h;
+    o.strict = strict != 0;
+    o.frame_order.assign(frame_order, frame_order + (frame_order ? n : 0));
+}
 void orc_set_rng(void* h, uint64_t seed, uint64_t call_no) {
     ((Oracle*)h)->seed = seed;
     ((Oracle*)h)->call_no = call_no;
@@ -661,8 +745,9 @@ int orc_guess_motion(void* h, int64_t frame, double delay, int iters, uint64_t s
     std::vector<double> P((size_t)f.n * 3), nP, r2;
     problem_matrix(o, f, delay, P.data());
     guess_motion(P.data(), f.n, iters, rng_task_key(o.seed, stream, call_no, offset_idx, frame), m,
-                 nP, r2);
-    if (k) *k = clamp_k(1.0 / norm_PM(P.data(), f.n, m) * 1e2);
+                 nP, r2, o.strict);
+    if (k) *k = o.strict ? clamp_k(1 / orc_strict::norm_PM(P.data(), f.n, m) * 1e2)
+                         : clamp_k(1.0 / norm_PM(P.data(), f.n, m) * 1e2);
     return OK;
 }
 int orc_loss3(void* h, int64_t frame, double delay, const double* m, double k, double* out) {
@@ -679,7 +764,8 @@ int orc_loss5(void* h, int64_t frame, double delay, const double* m, double k, d
     if (it == o.frames.end()) return E_INVALID;
     std::vector<double> P((size_t)it->second.n * 3);
     problem_matrix(o, it->second, delay, P.data());
-    *out = loss5_P(P.data(), it->second.n, m, k, grad);
+    *out = o.strict ? orc_strict::loss5_P(P.data(), it->second.n, m, k, grad)
+                    : loss5_P(P.data(), it->second.n, m, k, grad);
     return OK;
 }
 int orc_lbfgs(void* h, int64_t frame, double delay, double* m, double k, double* fout, int* iters,

@@ -1,0 +1,2 @@
+// oracle/shim: placeholder for an ensmallen header the reference includes (core_private.cpp:8-10); nothing from it is used.
+#pragma once
