@@ -6,10 +6,13 @@
 #include "rssync_b200.h"
 
 #include <algorithm>
+#include <atomic>
 #include <cmath>
 #include <cstring>
 #include <map>
 #include <string>
+#include <thread>
+#include <utility>
 #include <vector>
 
 #include "engine.h"
@@ -88,7 +91,7 @@ struct rssync_problem {
     std::string err;
 
     // gyro spline (OptData::quats, quats_start, sample_rate)
-    std::vector<double> rec;
+    PinBuf<double> rec;  // pinned: goes to the device with one async copy
     double q0 = 0.0, sr = 0.0;
     size_t nq = 0;
     bool gyro_dirty = false;
@@ -124,7 +127,7 @@ struct rssync_problem {
     DevBuf<unsigned char> d_sp_active;
     DevBuf<double> d_probe;
 
-    std::vector<int32_t> sort_scratch;
+    std::vector<std::pair<double, int32_t>> sort_scratch;
     std::vector<double> trace_delay, trace_step;
     uint64_t h2d = 0, d2h = 0, sync_outer = 0, sync_evals = 0;
     bool kernel_timing = false;
@@ -161,9 +164,8 @@ int d2h(rssync_problem* p, void* dst, const void* src, size_t bytes) {
 int flush(rssync_problem* p) {
     CUDA_TRY(p, cudaSetDevice(p->device));
     if (p->gyro_dirty) {
-        CUDA_TRY(p, p->d_rec.reserve(p->rec.size()));
-        // the spline vector is pageable; the copy is staged by the runtime
-        if (int rc = h2d(p, p->d_rec.ptr, p->rec.data(), p->rec.size() * sizeof(double))) return rc;
+        CUDA_TRY(p, p->d_rec.reserve(p->nq * 16));
+        if (int rc = h2d(p, p->d_rec.ptr, p->rec.ptr, p->nq * 16 * sizeof(double))) return rc;
         p->gyro_dirty = false;
     }
     if (p->used > p->uploaded || p->rays_full_dirty) {
@@ -443,6 +445,7 @@ void rssync_destroy(rssync_problem* p) {
     if (!p) return;
     cudaSetDevice(p->device);
     p->d_rec.release();
+    p->rec.release();
     for (int i = 0; i < 8; ++i) { p->h_plane[i].release(); p->d_plane[i].release(); }
     p->h_orig.release(); p->d_orig.release();
     p->d_frames.release(); p->d_delays.release(); p->d_framecost.release(); p->d_costs.release();
@@ -465,7 +468,9 @@ int rssync_set_gyro_fixed(rssync_problem* p, const double* quats, size_t count, 
     if (count > (size_t)INT32_MAX) { p->err = "set-gyro-quaternions: too many samples"; return RSSYNC_E_INVALID; }
     p->sr = sample_rate;       // core_private.cpp:137
     p->q0 = first_timestamp;   // :138
-    rs::build_spline_records(quats, count, p->rec);  // :139
+    cudaSetDevice(p->device);
+    CUDA_TRY(p, p->rec.reserve(count * 16));
+    rs::build_spline_records(quats, count, p->rec.ptr);  // :139
     p->nq = count;
     p->gyro_dirty = true;
     return RSSYNC_OK;
@@ -482,25 +487,32 @@ int rssync_set_gyro_var(rssync_problem* p, const int64_t* ts, const double* quat
     if (rq.size() / 4 > (size_t)INT32_MAX) { p->err = "set-gyro-quaternions: too many samples"; return RSSYNC_E_INVALID; }
     p->sr = sr;
     p->q0 = q0;
-    rs::build_spline_records(rq.data(), rq.size() / 4, p->rec);  // :189
+    cudaSetDevice(p->device);
+    CUDA_TRY(p, p->rec.reserve(rq.size() * 4));
+    rs::build_spline_records(rq.data(), rq.size() / 4, p->rec.ptr);  // :189
     p->nq = rq.size() / 4;
     p->gyro_dirty = true;
     return RSSYNC_OK;
 }
 
-int rssync_set_track(rssync_problem* p, int64_t frame, const double* ts_a, const double* ts_b,
-                     const double* rays_a, const double* rays_b, size_t count) {
-    if (!p) return RSSYNC_E_INVALID;
-    if (count && (!ts_a || !ts_b || !rays_a || !rays_b)) { p->err = "set-track-result: null buffer"; return RSSYNC_E_INVALID; }
-    if (count > (size_t)rs::kMaxRaysPerFrame) {
-        p->err = "set-track-result: more than " + std::to_string(rs::kMaxRaysPerFrame) + " rays in one frame is not supported";
-        return RSSYNC_E_INVALID;
-    }
-    // panic conditions, in the reference's order (core_private.cpp:199-202)
-    if (!all_finite(rays_a, 3 * count)) { p->err = "set-track-result: non-finite numbers in rays_a"; return RSSYNC_E_NONFINITE; }
-    if (!all_finite(rays_b, 3 * count)) { p->err = "set-track-result: non-finite numbers in rays_b"; return RSSYNC_E_NONFINITE; }
-    if (!all_finite(ts_a, count)) { p->err = "set-track-result: non-finite numbers in ts_a"; return RSSYNC_E_NONFINITE; }
-    if (!all_finite(ts_b, count)) { p->err = "set-track-result: non-finite numbers in ts_b"; return RSSYNC_E_NONFINITE; }
+}  // extern "C"
+
+namespace {
+
+// SetTrackResult, stage 1: the reference's panic conditions, in its order (core_private.cpp:199-202)
+int validate_track(const double* ts_a, const double* ts_b, const double* rays_a, const double* rays_b,
+                   size_t count, const char** msg) {
+    if (count && (!ts_a || !ts_b || !rays_a || !rays_b)) { *msg = "set-track-result: null buffer"; return RSSYNC_E_INVALID; }
+    if (count > (size_t)rs::kMaxRaysPerFrame) { *msg = "set-track-result: more than 512 rays in one frame is not supported"; return RSSYNC_E_INVALID; }
+    if (!all_finite(rays_a, 3 * count)) { *msg = "set-track-result: non-finite numbers in rays_a"; return RSSYNC_E_NONFINITE; }
+    if (!all_finite(rays_b, 3 * count)) { *msg = "set-track-result: non-finite numbers in rays_b"; return RSSYNC_E_NONFINITE; }
+    if (!all_finite(ts_a, count)) { *msg = "set-track-result: non-finite numbers in ts_a"; return RSSYNC_E_NONFINITE; }
+    if (!all_finite(ts_b, count)) { *msg = "set-track-result: non-finite numbers in ts_b"; return RSSYNC_E_NONFINITE; }
+    return RSSYNC_OK;
+}
+
+// stage 2 (serial bookkeeping): where the frame lives in the arena
+int place_track(rssync_problem* p, int64_t frame, size_t count, size_t* off_out) {
     const size_t padded = (count + 31) / 32 * 32;
     size_t off;
     auto it = p->frames.find(frame);
@@ -524,15 +536,25 @@ int rssync_set_track(rssync_problem* p, int64_t frame, const double* ts_a, const
         }
         p->used = need;
     }
+    p->frames[frame] = FrameDesc{frame, (int32_t)off, (int32_t)count};
+    p->total_rays += count;
+    *off_out = off;
+    return RSSYNC_OK;
+}
+
+// stage 3 (thread-safe, disjoint arena ranges): sort by ts_a, transpose AoS -> SoA planes
+void fill_track(rssync_problem* p, size_t off, const double* ts_a, const double* ts_b,
+                const double* rays_a, const double* rays_b, size_t count,
+                std::vector<std::pair<double, int32_t>>& scratch) {
+    const size_t padded = (count + 31) / 32 * 32;
     double* pl[8];
     for (int i = 0; i < 8; ++i) pl[i] = p->h_plane[i].ptr + off;
     int32_t* og = p->h_orig.ptr + off;
-    p->sort_scratch.resize(count);
-    for (size_t i = 0; i < count; ++i) p->sort_scratch[i] = (int32_t)i;
-    std::stable_sort(p->sort_scratch.begin(), p->sort_scratch.end(),
-                     [ts_a](int32_t a, int32_t b) { return ts_a[a] < ts_a[b]; });
+    scratch.resize(count);
+    for (size_t i = 0; i < count; ++i) scratch[i] = {ts_a[i], (int32_t)i};
+    std::sort(scratch.begin(), scratch.end());  // (ts_a, index): ties keep the caller's order
     for (size_t j = 0; j < count; ++j) {
-        const size_t i = (size_t)p->sort_scratch[j];
+        const size_t i = (size_t)scratch[j].second;
         og[j] = (int32_t)i;
         pl[0][j] = ts_a[i];
         pl[1][j] = ts_b[i];
@@ -545,23 +567,74 @@ int rssync_set_track(rssync_problem* p, int64_t frame, const double* ts_a, const
         pl[1][j] = count ? pl[1][count - 1] : 0.0;
         for (int c = 2; c < 8; ++c) pl[c][j] = 0.0;
     }
-    p->frames[frame] = FrameDesc{frame, (int32_t)off, (int32_t)count};
-    p->total_rays += count;
+}
+
+template <class F>
+void parallel_frames(size_t n, F&& fn) {
+    unsigned hw = std::thread::hardware_concurrency();
+    size_t threads = std::min<size_t>(hw ? hw : 1, std::min<size_t>(16, n / 64 + 1));
+    if (threads <= 1) {
+        for (size_t i = 0; i < n; ++i) fn(i, 0);
+        return;
+    }
+    std::atomic<size_t> next{0};
+    std::vector<std::thread> pool;
+    for (size_t t = 0; t < threads; ++t)
+        pool.emplace_back([&, t]() {
+            for (;;) {
+                const size_t lo = next.fetch_add(32);
+                if (lo >= n) break;
+                for (size_t i = lo; i < std::min(n, lo + 32); ++i) fn(i, t);
+            }
+        });
+    for (auto& th : pool) th.join();
+}
+
+}  // namespace
+
+extern "C" {
+
+int rssync_set_track(rssync_problem* p, int64_t frame, const double* ts_a, const double* ts_b,
+                     const double* rays_a, const double* rays_b, size_t count) {
+    if (!p) return RSSYNC_E_INVALID;
+    const char* msg = nullptr;
+    if (int rc = validate_track(ts_a, ts_b, rays_a, rays_b, count, &msg)) { p->err = msg; return rc; }
+    size_t off = 0;
+    if (int rc = place_track(p, frame, count, &off)) return rc;
+    fill_track(p, off, ts_a, ts_b, rays_a, rays_b, count, p->sort_scratch);
     return RSSYNC_OK;
 }
 
+// Bulk ingest: same result as n_frames rssync_set_track calls (frames after a failing one are
+// not applied), with validation and the sort/transpose spread over host threads.
 int rssync_set_track_batch(rssync_problem* p, size_t n_frames, const int64_t* frames,
                            const size_t* counts, const double* ts_a, const double* ts_b,
                            const double* rays_a, const double* rays_b) {
     if (!p || (n_frames && (!frames || !counts))) return RSSYNC_E_INVALID;
-    size_t at = 0;
-    for (size_t i = 0; i < n_frames; ++i) {
-        if (int rc = rssync_set_track(p, frames[i], ts_a + at, ts_b + at, rays_a + 3 * at, rays_b + 3 * at, counts[i]))
-            return rc;
-        at += counts[i];
-    }
+    std::vector<size_t> at(n_frames + 1, 0);
+    for (size_t i = 0; i < n_frames; ++i) at[i + 1] = at[i] + counts[i];
+    std::vector<int> rc(n_frames, 0);
+    std::vector<const char*> msg(n_frames, nullptr);
+    parallel_frames(n_frames, [&](size_t i, size_t) {
+        rc[i] = validate_track(ts_a + at[i], ts_b + at[i], rays_a + 3 * at[i], rays_b + 3 * at[i], counts[i], &msg[i]);
+    });
+    size_t n_ok = n_frames;
+    for (size_t i = 0; i < n_frames; ++i)
+        if (rc[i]) { n_ok = i; break; }
+    std::vector<size_t> off(n_ok);
+    for (size_t i = 0; i < n_ok; ++i)
+        if (int r = place_track(p, frames[i], counts[i], &off[i])) return r;
+    std::vector<std::vector<std::pair<double, int32_t>>> scratch(17);
+    parallel_frames(n_ok, [&](size_t i, size_t t) {
+        fill_track(p, off[i], ts_a + at[i], ts_b + at[i], rays_a + 3 * at[i], rays_b + 3 * at[i], counts[i], scratch[t]);
+    });
+    if (n_ok < n_frames) { p->err = msg[n_ok]; return rc[n_ok]; }
     return RSSYNC_OK;
 }
+
+}  // extern "C"
+
+extern "C" {
 
 int rssync_set_kernel_timing(rssync_problem* p, int enabled) {
     if (!p) return RSSYNC_E_INVALID;
@@ -724,7 +797,7 @@ int rssync_probe_gyro(const rssync_problem* p, double* sample_rate, double* firs
     if (sample_rate) *sample_rate = p->sr;
     if (first_timestamp) *first_timestamp = p->q0;
     if (count) *count = p->nq;
-    if (rec) std::copy(p->rec.begin(), p->rec.end(), rec);
+    if (rec) std::copy(p->rec.ptr, p->rec.ptr + p->nq * 16, rec);
     return RSSYNC_OK;
 }
 

@@ -35,7 +35,7 @@ constexpr unsigned FULL = 0xffffffffu;
 #define RS_WPB 8
 #endif
 #ifndef RS_MINB
-#define RS_MINB 1
+#define RS_MINB 3
 #endif
 constexpr int kWarpsPerBlock = RS_WPB;
 constexpr unsigned kNanHi = 0x7ff80000u;  // hi word of the canonical NaN: sorts above every r^2
@@ -113,36 +113,44 @@ template <int SLOTS>
 __device__ __forceinline__ unsigned warp_select_hi(const unsigned (&h)[SLOTS], const unsigned* skey,
                                                    int kth, unsigned bound_hi, int lane, int& cl,
                                                    int& ce) {
-    unsigned active = 0;
-#pragma unroll
-    for (int s = 0; s < SLOTS; ++s) active |= (h[s] <= bound_hi) ? (1u << s) : 0u;
-    int below = 0;  // elements already known to lie below the active range
+    // Quickselect on VALUE bounds: the answer lies in [L, U).  Keys are < 2^31, so the sign bit of a
+    // difference is the `<` predicate: two subtract + shift-add pairs per key count (h < pivot) and
+    // (h <= pivot) over ALL keys, no per-lane bookkeeping.  The pivot is any key inside [L, U),
+    // found by probing one 32-key batch of the shared copy at a time (a different batch first in
+    // each round).
+    unsigned L = 0u, U = bound_hi + 1u;
     int round = 0;
     for (;;) {
-        const unsigned bal = __ballot_sync(FULL, active != 0u);
-        const int rot = (round * 11 + 5) & 31;
-        const unsigned rb = __funnelshift_r(bal, bal, rot);
-        const int src = (__ffs(rb) - 1 + rot) & 31;
-        const int slot = __shfl_sync(FULL, __ffs(active) - 1, src);
-        const unsigned pv = skey[slot * 32 + src];
-        unsigned lt = 0, eq = 0;
+        unsigned pv = 0u;
+        for (int j = 0;; ++j) {
+            int sb = round + j;
+            sb -= (sb / SLOTS) * SLOTS;
+            const unsigned cand = skey[sb * 32 + lane];
+            const unsigned bal = __ballot_sync(FULL, (cand - L) < (U - L));
+            if (bal) {
+                const int rot = (round * 7 + 3) & 31;
+                const unsigned rb = __funnelshift_r(bal, bal, rot);
+                pv = __shfl_sync(FULL, cand, (__ffs(rb) - 1 + rot) & 31);
+                break;
+            }
+        }
+        const unsigned pv1 = pv + 1u;
+        unsigned c1 = 0, c2 = 0;
 #pragma unroll
         for (int s = 0; s < SLOTS; ++s) {
-            lt |= (h[s] < pv) ? (1u << s) : 0u;
-            eq |= (h[s] == pv) ? (1u << s) : 0u;
+            c1 += (h[s] - pv) >> 31;
+            c2 += (h[s] - pv1) >> 31;
         }
-        const unsigned packed =
-            __reduce_add_sync(FULL, (unsigned)__popc(lt & active) | ((unsigned)__popc(eq & active) << 16));
-        const int nl = (int)(packed & 0xffffu), ne = (int)(packed >> 16);
-        if (kth < below + nl) {
-            active &= lt;
-        } else if (kth < below + nl + ne) {
-            cl = below + nl;
-            ce = ne;
+        const unsigned packed = __reduce_add_sync(FULL, c1 | (c2 << 16));
+        const int nl = (int)(packed & 0xffffu), nle = (int)(packed >> 16);
+        if (kth < nl) {
+            U = pv;
+        } else if (kth < nle) {
+            cl = nl;
+            ce = nle - nl;
             return pv;
         } else {
-            below += nl + ne;
-            active &= ~(lt | eq);
+            L = pv1;
         }
         ++round;
     }
@@ -395,7 +403,7 @@ __device__ __forceinline__ double warp_norm_PM(const double* sP, int NP, int nsl
 // K1: PreSync / DebugPreSync grid.  task t -> (frame t / D, delay t % D): the warps of a block
 // work on the same frame, so its ray planes and spline window are served from L1.
 template <int SLOTS>
-__global__ void __launch_bounds__(kWarpsPerBlock * 32, RS_MINB)
+__global__ void __launch_bounds__(kWarpsPerBlock * 32, SLOTS <= 8 ? RS_MINB : 1)
 presync_kernel(DeviceData dd, const FrameDesc* __restrict__ frames, int F,
                const double* __restrict__ delays, int D, uint64_t seed, uint64_t stream,
                uint64_t call_no, uint64_t idx_base, double* __restrict__ framecost,
@@ -645,10 +653,11 @@ __global__ void fp64_peak_kernel(int iters, double* sink) {
 }
 
 // ------------------------------------------------------------------------------------------
-int slots_for(int max_n) {
-    if (max_n <= 64) return 2;
-    if (max_n <= 128) return 4;
-    if (max_n <= 256) return 8;
+int slots_for(int max_n) {  // compile-time SLOTS instantiated for the estimator kernels
+    const int need = (max_n + 31) / 32;
+    const int have[] = {2, 4, 6, 7, 8, 12, 16};
+    for (int v : have)
+        if (need <= v) return v;
     return 16;
 }
 
@@ -678,7 +687,10 @@ void allow_smem(K kernel, size_t smem) {
     switch (slots_for(max_n)) {                                        \
         case 2: { constexpr int SL = 2; __VA_ARGS__; } break;          \
         case 4: { constexpr int SL = 4; __VA_ARGS__; } break;          \
+        case 6: { constexpr int SL = 6; __VA_ARGS__; } break;          \
+        case 7: { constexpr int SL = 7; __VA_ARGS__; } break;          \
         case 8: { constexpr int SL = 8; __VA_ARGS__; } break;          \
+        case 12: { constexpr int SL = 12; __VA_ARGS__; } break;        \
         default: { constexpr int SL = 16; __VA_ARGS__; } break;        \
     }
 

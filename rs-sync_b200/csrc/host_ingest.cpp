@@ -8,6 +8,7 @@
 
 #include <algorithm>
 #include <cmath>
+#include <thread>
 
 namespace rs {
 
@@ -92,9 +93,13 @@ void slerp4(const double* p, const double* q_in, double t, double* out) {
 
 }  // namespace
 
-void build_spline_records(const double* quats, size_t n, std::vector<double>& rec) {
-    rec.assign(n * 16, 0.0);
-    for (int comp = 0; comp < 4; ++comp) solve_component(quats + comp, n, 4, comp, rec.data());
+void build_spline_records(const double* quats, size_t n, double* rec) {
+    // the four components are independent sequential solves: one host thread each
+    std::thread th[3];
+    for (int comp = 1; comp < 4; ++comp)
+        th[comp - 1] = std::thread([=]() { solve_component(quats + comp, n, 4, comp, rec); });
+    solve_component(quats, n, 4, 0, rec);
+    for (auto& t : th) t.join();
 }
 
 // SyncProblemPrivate::SetGyroQuaternions(const int64_t*, const double*, size_t),
