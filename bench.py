@@ -166,6 +166,24 @@ def cpu_baseline(w, delays, seconds):
                       f"({n_off * w.n_frames * w.n_rays:.3g} cells, {dt:.1f} s)"}
 
 
+def cpu_sync_baseline(w):
+    """syncpoints/s of the CPU arm on ONE syncpoint (PreSync on the window + 4 chained Sync, all host
+    threads over frames like the reference's par loops).  The oracle port is used: the reference
+    itself builds dense N x N Jacobian factors per evaluation (core_private.cpp:99-114) and needs
+    minutes per syncpoint at N = 200."""
+    from oracle import loader
+    threads = os.cpu_count() or 1
+    p = loader.OracleProblem(threads=threads, seed=100).load_range(w, w.syncpoints()[0], w.sync_window + 1)
+    pos = w.syncpoints()[0]
+    t = time.perf_counter()
+    d = p.PreSync(0.0, pos, pos + w.sync_window, w.presync_step, 0.2)[1]
+    for _ in range(4):
+        d = p.Sync(d, pos, pos + w.sync_window, 0.0, 0.2)[1]
+    dt = time.perf_counter() - t
+    return {"value": 1.0 / dt, "unit": "syncpoints/s", "cores": threads, "kind": "port",
+            "sample": f"1 of {len(w.syncpoints())} syncpoints ({dt:.2f} s)"}
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -249,15 +267,15 @@ def run_b200(args):
             curve = torch.from_numpy(costs)
         return int(torch.argmin(curve))
 
+    sampler = ClockSampler(local)
+    sampler.start()  # nvidia-smi takes a moment to start: begin before the warm-up, keep the loaded half
     for i in range(args.warmup):
         flush_buf.zero_()
         step(i)
     fp64_peak = pkg.measure_fp64_peak()
 
-    sampler = ClockSampler(local)
     launches0 = prob.stats()["kernel_launches"]
     barrier()
-    sampler.start()
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
     kernel_ms = []
     for i in range(args.steps):
@@ -305,7 +323,9 @@ def run_b200(args):
                 "frac": achieved / fp64_peak if fp64_peak > 0 else None,
                 "peak_source": "measured live: rssync_measure_fp64_peak (dependent DFMA chains, all SMs)",
                 "kernel": "presync_kernel", "kernel_ms": kern_ms, "flop_per_cell": FLOP_PER_CELL,
-                "traffic": None,
+                # dram__bytes_read.sum + dram__bytes_write.sum of one launch, ncu --set full
+                # (profiles/r01_presync_v2c.md): 57.7 MB + 2.6 MB = inputs once + the framecost scratch
+                "traffic": 60.4e6 if (w.name == "C2" and hi - lo == OFFSETS_PER_GPU) else None,
                 "hbm": {"algorithmic_bytes": int(input_bytes),
                         "achieved_gbs": input_bytes / (kern_ms * 1e-3) / 1e9, "peak_gbs": read_peaks().get("hbm_gbs")}}
 
@@ -322,6 +342,8 @@ def run_b200(args):
 
     if rank == 0 and world >= 1 and not args.no_cpu and world == 1:
         out["cpu_baseline"] = cpu_baseline(w, delays, args.cpu_seconds)
+        if not args.no_sync:
+            out["cpu_baseline"]["sync"] = cpu_sync_baseline(w)
     elif rank == 0 and not args.no_cpu:
         out["cpu_baseline"] = None
     if rank == 0:

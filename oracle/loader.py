@@ -166,6 +166,14 @@ class OracleProblem:
             self.SetTrackResult(int(fid), w.ts_a[i], w.ts_b[i], w.rays_a[i], w.rays_b[i], w.ts_a.shape[1])
         return self
 
+    def load_range(self, w, first_frame, n_frames):
+        """gyro + only the frames first_frame .. first_frame + n_frames - 1"""
+        self.SetGyroQuaternions(w.quats, w.quats.shape[0], w.gyro_rate, w.gyro_t0)
+        for i, fid in enumerate(w.frame_ids):
+            if first_frame <= int(fid) < first_frame + n_frames:
+                self.SetTrackResult(int(fid), w.ts_a[i], w.ts_b[i], w.rays_a[i], w.rays_b[i], w.ts_a.shape[1])
+        return self
+
     def PreSync(self, initial, fb, fe, step, radius):
         c, d = C.c_double(), C.c_double()
         self._check(self.L.orc_presync(self.h, initial, fb, fe, step, radius, C.byref(c), C.byref(d)))
