@@ -132,6 +132,9 @@ typedef struct rssync_stats {
     uint64_t sync_lbfgs_evals; /* objective evaluations inside L-BFGS, most recent Sync / batch */
     double last_grid_kernel_ms; /* device time of the most recent PreSync grid kernel (CUDA events
                                    on the problem's stream), 0 if timing is off                  */
+    uint64_t last_grid_tasks;       /* (delay, frame) tasks of the most recent PreSync grid      */
+    uint64_t last_grid_exact_tasks; /* of those, tasks whose translation estimate was redone by
+                                       the exact binary64 estimator (fp32 tournament undecided) */
 } rssync_stats;
 int rssync_get_stats(const rssync_problem* p, rssync_stats* out);
 
@@ -145,6 +148,11 @@ int rssync_probe_gyro(const rssync_problem* p, double* sample_rate, double* firs
 int rssync_probe_problem_matrix(rssync_problem* p, int64_t frame, double delay, double* rows);
 int rssync_probe_guess_motion(rssync_problem* p, int64_t frame, double delay, int iters, int stream,
                               uint64_t call_no, uint64_t offset_index, double* m3, double* k);
+/* mode 0: the product path (fp32 tournament + exact estimator when undecided); mode 2: exact
+ * binary64 estimator only.  *used_exact = 1 when the exact estimator ran. */
+int rssync_probe_guess_motion_ex(rssync_problem* p, int64_t frame, double delay, int iters,
+                                 int stream, uint64_t call_no, uint64_t offset_index, int mode,
+                                 double* m3, double* k, int* used_exact);
 int rssync_probe_loss(rssync_problem* p, int64_t frame, double delay, const double* m3, double k,
                       double* loss3, double* loss5, double* grad3);
 int rssync_probe_lbfgs(rssync_problem* p, int64_t frame, double delay, double* m3, double k,

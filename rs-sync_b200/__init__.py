@@ -34,7 +34,7 @@ C_ABI_SYMBOLS = [
     "rssync_flush", "rssync_get_stats", "rssync_measure_fp64_peak", "rssync_probe_gyro",
     "rssync_probe_problem_matrix", "rssync_probe_guess_motion", "rssync_probe_loss",
     "rssync_probe_lbfgs", "rssync_probe_log1p", "rssync_set_track_batch", "rssync_set_kernel_timing",
-    "rssync_sync_batch_ex",
+    "rssync_sync_batch_ex", "rssync_probe_guess_motion_ex",
 ]
 # Itanium-ABI symbols of the C++ drop-in face (same set the reference's librssync_core exports)
 CXX_ABI_SYMBOLS = [
@@ -46,7 +46,9 @@ CXX_ABI_SYMBOLS = [
 class Stats(C.Structure):
     _fields_ = [(n, C.c_uint64) for n in (
         "kernel_launches", "h2d_bytes", "d2h_bytes", "frames", "rays", "gyro_samples",
-        "sync_outer_iters", "sync_lbfgs_evals")] + [("last_grid_kernel_ms", C.c_double)]
+        "sync_outer_iters", "sync_lbfgs_evals")] + [("last_grid_kernel_ms", C.c_double),
+                                                     ("last_grid_tasks", C.c_uint64),
+                                                     ("last_grid_exact_tasks", C.c_uint64)]
 
 
 class RsSyncError(RuntimeError):
@@ -101,6 +103,9 @@ def load_library():
     L.rssync_probe_problem_matrix.argtypes = [P, C.c_int64, C.c_double, c_double_p]
     L.rssync_probe_guess_motion.argtypes = [P, C.c_int64, C.c_double, C.c_int, C.c_int, C.c_uint64,
                                             C.c_uint64, c_double_p, c_double_p]
+    L.rssync_probe_guess_motion_ex.argtypes = [P, C.c_int64, C.c_double, C.c_int, C.c_int, C.c_uint64,
+                                               C.c_uint64, C.c_int, c_double_p, c_double_p,
+                                               C.POINTER(C.c_int)]
     L.rssync_probe_loss.argtypes = [P, C.c_int64, C.c_double, c_double_p, C.c_double, c_double_p,
                                     c_double_p, c_double_p]
     L.rssync_probe_lbfgs.argtypes = [P, C.c_int64, C.c_double, c_double_p, C.c_double, c_double_p,
@@ -307,6 +312,15 @@ class SyncProblem:
         self._check(self.L.rssync_probe_guess_motion(self.h, frame, delay, iters, stream, call_no, offset_index,
                                                      _dp(m), C.byref(k)))
         return m, k.value
+
+    def probe_guess_motion_ex(self, frame, delay, iters, stream, call_no, offset_index, mode):
+        """mode 0: product path, mode 2: exact binary64 estimator.  Returns (m, k, used_exact)."""
+        m = np.empty(3)
+        k = C.c_double()
+        ex = C.c_int()
+        self._check(self.L.rssync_probe_guess_motion_ex(self.h, frame, delay, iters, stream, call_no,
+                                                        offset_index, mode, _dp(m), C.byref(k), C.byref(ex)))
+        return m, k.value, ex.value
 
     def probe_loss(self, frame, delay, m, k):
         m = _f64(m)

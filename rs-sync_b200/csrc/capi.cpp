@@ -104,8 +104,8 @@ struct rssync_problem {
     // the RNG draws of the translation estimator refer to.
     PinBuf<double> h_plane[8];
     DevBuf<double> d_plane[8];
-    PinBuf<int32_t> h_orig;
-    DevBuf<int32_t> d_orig;
+    PinBuf<int32_t> h_orig, h_pos;
+    DevBuf<int32_t> d_orig, d_pos;
     size_t used = 0, uploaded = 0, garbage = 0;
     bool rays_full_dirty = false;
     std::map<int64_t, FrameDesc> frames;  // OptData::frame_data
@@ -133,6 +133,7 @@ struct rssync_problem {
     bool kernel_timing = false;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     double last_grid_ms = 0.0;
+    uint64_t grid_tasks = 0, grid_exact_tasks = 0;
 
     rs::DeviceData device_data() const {
         rs::DeviceData dd;
@@ -142,6 +143,7 @@ struct rssync_problem {
         dd.sr = sr;
         for (int i = 0; i < 8; ++i) dd.plane[i] = d_plane[i].ptr;
         dd.orig = d_orig.ptr;
+        dd.pos = d_pos.ptr;
         return dd;
     }
 };
@@ -179,6 +181,9 @@ int flush(rssync_problem* p) {
         }
         CUDA_TRY(p, p->d_orig.reserve(p->h_orig.cap));
         if (int rc = h2d(p, p->d_orig.ptr + from, p->h_orig.ptr + from, (p->used - from) * sizeof(int32_t)))
+            return rc;
+        CUDA_TRY(p, p->d_pos.reserve(p->h_pos.cap));
+        if (int rc = h2d(p, p->d_pos.ptr + from, p->h_pos.ptr + from, (p->used - from) * sizeof(int32_t)))
             return rc;
         p->uploaded = p->used;
         p->rays_full_dirty = false;
@@ -232,24 +237,26 @@ int presync_grid_impl(rssync_problem* p, int64_t fb, int64_t fe, const double* d
     CUDA_TRY(p, p->d_delays.reserve(n));
     CUDA_TRY(p, p->d_framecost.reserve((size_t)F * n));
     CUDA_TRY(p, p->d_costs.reserve(n));
-    CUDA_TRY(p, p->d_flags.reserve(1));
+    CUDA_TRY(p, p->d_flags.reserve(2));
     if (int rc = h2d(p, p->d_frames.ptr, sel.data(), sizeof(FrameDesc) * F)) return rc;
     if (int rc = h2d(p, p->d_delays.ptr, delays, sizeof(double) * n)) return rc;
-    CUDA_TRY(p, cudaMemsetAsync(p->d_flags.ptr, 0, sizeof(unsigned), p->stream));
+    CUDA_TRY(p, cudaMemsetAsync(p->d_flags.ptr, 0, 2 * sizeof(unsigned), p->stream));
     rs::launch_presync_grid(p->device_data(), p->d_frames.ptr, F, max_n, p->d_delays.ptr, n, p->seed,
                             stream_id, call_no, idx_base, p->d_framecost.ptr, p->d_costs.ptr,
                             p->d_flags.ptr, p->stream, p->kernel_timing ? p->ev0 : nullptr,
                             p->kernel_timing ? p->ev1 : nullptr);
     CUDA_TRY(p, cudaGetLastError());
-    unsigned flags = 0;
+    unsigned flags[2] = {0, 0};
     if (int rc = d2h(p, costs, p->d_costs.ptr, sizeof(double) * n)) return rc;
-    if (int rc = d2h(p, &flags, p->d_flags.ptr, sizeof(unsigned))) return rc;
+    if (int rc = d2h(p, flags, p->d_flags.ptr, 2 * sizeof(unsigned))) return rc;
     CUDA_TRY(p, cudaStreamSynchronize(p->stream));
+    p->grid_tasks = (uint64_t)F * (uint64_t)n;
+    p->grid_exact_tasks = flags[1];
     if (p->kernel_timing) {
         float ms = 0.f;
         if (cudaEventElapsedTime(&ms, p->ev0, p->ev1) == cudaSuccess) p->last_grid_ms = ms;
     }
-    if (flags_out) *flags_out = flags;
+    if (flags_out) *flags_out = flags[0];
     return RSSYNC_OK;
 }
 
@@ -448,6 +455,7 @@ void rssync_destroy(rssync_problem* p) {
     p->rec.release();
     for (int i = 0; i < 8; ++i) { p->h_plane[i].release(); p->d_plane[i].release(); }
     p->h_orig.release(); p->d_orig.release();
+    p->h_pos.release(); p->d_pos.release();
     p->d_frames.release(); p->d_delays.release(); p->d_framecost.release(); p->d_costs.release();
     p->d_flags.release(); p->h_stage.release(); p->d_tasks.release(); p->d_sp_begin.release();
     p->d_lbfgs_stats.release(); p->d_m.release(); p->d_k.release(); p->d_task_scratch.release();
@@ -533,6 +541,7 @@ int place_track(rssync_problem* p, int64_t frame, size_t count, size_t* off_out)
             cudaSetDevice(p->device);
             for (int i = 0; i < 8; ++i) CUDA_TRY(p, p->h_plane[i].reserve(want, p->used));
             CUDA_TRY(p, p->h_orig.reserve(want, p->used));
+            CUDA_TRY(p, p->h_pos.reserve(want, p->used));
         }
         p->used = need;
     }
@@ -550,12 +559,14 @@ void fill_track(rssync_problem* p, size_t off, const double* ts_a, const double*
     double* pl[8];
     for (int i = 0; i < 8; ++i) pl[i] = p->h_plane[i].ptr + off;
     int32_t* og = p->h_orig.ptr + off;
+    int32_t* ps = p->h_pos.ptr + off;
     scratch.resize(count);
     for (size_t i = 0; i < count; ++i) scratch[i] = {ts_a[i], (int32_t)i};
     std::sort(scratch.begin(), scratch.end());  // (ts_a, index): ties keep the caller's order
     for (size_t j = 0; j < count; ++j) {
         const size_t i = (size_t)scratch[j].second;
         og[j] = (int32_t)i;
+        ps[i] = (int32_t)j;
         pl[0][j] = ts_a[i];
         pl[1][j] = ts_b[i];
         pl[2][j] = rays_a[3 * i]; pl[3][j] = rays_a[3 * i + 1]; pl[4][j] = rays_a[3 * i + 2];
@@ -563,6 +574,7 @@ void fill_track(rssync_problem* p, size_t off, const double* ts_a, const double*
     }
     for (size_t j = count; j < padded; ++j) {  // padding lanes: finite, masked out by n
         og[j] = (int32_t)j;
+        ps[j] = (int32_t)j;
         pl[0][j] = count ? pl[0][count - 1] : 0.0;
         pl[1][j] = count ? pl[1][count - 1] : 0.0;
         for (int c = 2; c < 8; ++c) pl[c][j] = 0.0;
@@ -767,6 +779,8 @@ int rssync_get_stats(const rssync_problem* p, rssync_stats* out) {
     out->sync_outer_iters = p->sync_outer;
     out->sync_lbfgs_evals = p->sync_evals;
     out->last_grid_kernel_ms = p->last_grid_ms;
+    out->last_grid_tasks = p->grid_tasks;
+    out->last_grid_exact_tasks = p->grid_exact_tasks;
     return RSSYNC_OK;
 }
 
@@ -821,21 +835,34 @@ int rssync_probe_problem_matrix(rssync_problem* p, int64_t frame, double delay, 
     return RSSYNC_OK;
 }
 
-int rssync_probe_guess_motion(rssync_problem* p, int64_t frame, double delay, int iters, int stream,
-                              uint64_t call_no, uint64_t offset_index, double* m3, double* k) {
+int rssync_probe_guess_motion_ex(rssync_problem* p, int64_t frame, double delay, int iters, int stream,
+                                 uint64_t call_no, uint64_t offset_index, int mode, double* m3,
+                                 double* k, int* used_exact) {
     if (!p || !m3) return RSSYNC_E_INVALID;
     FrameDesc fd;
     if (int rc = probe_frame(p, frame, fd)) return rc;
     CUDA_TRY(p, p->d_probe.reserve(8));
+    CUDA_TRY(p, cudaMemsetAsync(p->d_probe.ptr + 4, 0, sizeof(double), p->stream));
     rs::launch_probe_guess(p->device_data(), fd, delay, iters,
-                           rs::rng_prefix(p->seed, (uint64_t)stream, call_no, offset_index), p->d_probe.ptr,
-                           p->stream);
-    double out[4];
+                           rs::rng_prefix(p->seed, (uint64_t)stream, call_no, offset_index), mode,
+                           p->d_probe.ptr, reinterpret_cast<unsigned*>(p->d_probe.ptr + 4), p->stream);
+    double out[5];
     if (int rc = d2h(p, out, p->d_probe.ptr, sizeof(out))) return rc;
     CUDA_TRY(p, cudaStreamSynchronize(p->stream));
     m3[0] = out[0]; m3[1] = out[1]; m3[2] = out[2];
     if (k) *k = out[3];
+    if (used_exact) {
+        unsigned c;
+        std::memcpy(&c, &out[4], sizeof(c));
+        *used_exact = (int)c;
+    }
     return RSSYNC_OK;
+}
+
+int rssync_probe_guess_motion(rssync_problem* p, int64_t frame, double delay, int iters, int stream,
+                              uint64_t call_no, uint64_t offset_index, double* m3, double* k) {
+    return rssync_probe_guess_motion_ex(p, frame, delay, iters, stream, call_no, offset_index, 0, m3, k,
+                                        nullptr);
 }
 
 int rssync_probe_loss(rssync_problem* p, int64_t frame, double delay, const double* m3, double k,

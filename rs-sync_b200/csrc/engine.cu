@@ -44,32 +44,41 @@ std::atomic<uint64_t> g_launches{0};
 
 // per-warp shared-memory slice
 struct WarpSmem {
-    double* P;      // raw rows, SoA [3][NP]
-    double* inv;    // 1/|row| (1.0 where |row| < 1e-12, safe_normalize); reused for P.M in phase D
-    unsigned* key;  // hi words of the squared residuals during a select
+    double* P;  // raw rows, SoA [3][NP], in STORAGE order (rays are stored sorted by ts_a)
+    // estimator kernels only: the row-normalised rows in fp32, laid out [3][NPAIR][32 lanes][2]
+    // so that lane l reads its slots (2p, 2p+1) as one float2.  The same bytes are reused as
+    // 1/|row| doubles + select keys by the exact estimator and as P.M doubles by the loss phase.
+    float* nf;
 };
+__host__ __device__ constexpr int pairs_for(int NP) { return (NP / 32 + 1) / 2; }
 __host__ __device__ constexpr size_t warp_smem_bytes(int NP, bool ransac) {
-    return ransac ? (size_t)NP * (3 * 8 + 8 + 4) : (size_t)NP * 3 * 8;
+    return (size_t)NP * 3 * 8 + (ransac ? (size_t)pairs_for(NP) * 64 * 3 * 4 : 0);
 }
 __device__ __forceinline__ WarpSmem warp_smem(unsigned char* base, int warp, int NP, bool ransac) {
     unsigned char* p = base + (size_t)warp * warp_smem_bytes(NP, ransac);
     WarpSmem w;
     w.P = reinterpret_cast<double*>(p);
-    w.inv = w.P + 3 * NP;
-    w.key = reinterpret_cast<unsigned*>(w.inv + NP);
+    w.nf = reinterpret_cast<float*>(w.P + 3 * NP);
     return w;
 }
 
+// safe_normalize of one row (inline_utils.hpp:5-11): 1/|row|, 1.0 where |row| < 1e-12
+__device__ __forceinline__ double row_inv_norm(double r0, double r1, double r2) {
+    const double nrm = sqrt(dot3(r0, r1, r2, r0, r1, r2));
+    return (nrm < 1e-12) ? 1.0 : 1.0 / nrm;
+}
+
 // ------------------------------------------------------------------------------------------
-// Phase A.  Rows of the problem matrix for the whole frame -> shared memory.  Entries past the
-// frame's last ray (up to NP) are zero rows with inv = NaN, which makes their residuals NaN in
-// phase C (sorted above everything) and their loss terms exactly 0 in phase D.
-template <bool WITH_INV>
+// Phase A.  Rows of the problem matrix for the whole frame -> shared memory (storage order; sums
+// over rays are order-independent double-double sums and the estimator's random draws go through
+// the `pos` plane).  Entries past the frame's last ray are zero rows.
+template <bool WITH_NF>
 __device__ __forceinline__ unsigned build_rows_smem(const DeviceData& dd, const FrameDesc& fd,
                                                     double delay, int lane, const WarpSmem& w,
                                                     int NP) {
     unsigned bad = 0;
     const int nslots = (fd.n + 31) >> 5;
+    const int NPAIR = pairs_for(NP);
     for (int s = 0; s < nslots; ++s) {
         const int i = s * 32 + lane;
         const size_t g = (size_t)fd.off + i;  // planes are padded to a multiple of 32 per frame
@@ -80,30 +89,52 @@ __device__ __forceinline__ unsigned build_rows_smem(const DeviceData& dd, const 
                      bz = __ldg(dd.plane[7] + g);
         double row[3];
         problem_row(dd.rec, dd.nq, dd.q0, dd.sr, delay, tsa, tsb, ax, ay, az, bx, by, bz, row);
-        const bool valid = i < fd.n;
-        if (!valid) { row[0] = row[1] = row[2] = 0.0; }
+        if (i >= fd.n) { row[0] = row[1] = row[2] = 0.0; }
         if (!(is_finite(row[0]) && is_finite(row[1]) && is_finite(row[2]))) bad = kFlagP;
-        // rays are stored sorted by ts_a; rows go back to the caller's order (RNG draws index it)
-        const int o = __ldg(dd.orig + g);
-        w.P[o] = row[0];
-        w.P[NP + o] = row[1];
-        w.P[2 * NP + o] = row[2];
-        if (WITH_INV) {
-            // safe_normalize (inline_utils.hpp:5-11): rows with |row| < 1e-12 stay unscaled
-            const double nrm = sqrt(dot3(row[0], row[1], row[2], row[0], row[1], row[2]));
-            double inv = (nrm < 1e-12) ? 1.0 : 1.0 / nrm;
-            if (!valid) inv = __longlong_as_double(0x7ff8000000000000LL);
-            w.inv[o] = inv;
+        w.P[i] = row[0];
+        w.P[NP + i] = row[1];
+        w.P[2 * NP + i] = row[2];
+        if (WITH_NF) {
+            const double inv = row_inv_norm(row[0], row[1], row[2]);  // core_private.cpp:35-36
+            const int at = (((s >> 1) * 32 + lane) << 1) + (s & 1);
+            w.nf[at] = (float)(row[0] * inv);
+            w.nf[NPAIR * 64 + at] = (float)(row[1] * inv);
+            w.nf[2 * NPAIR * 64 + at] = (float)(row[2] * inv);
         }
     }
-    for (int i = nslots * 32 + lane; i < NP; i += 32) {
-        w.P[i] = 0.0;
-        w.P[NP + i] = 0.0;
-        w.P[2 * NP + i] = 0.0;
-        if (WITH_INV) w.inv[i] = __longlong_as_double(0x7ff8000000000000LL);
+    for (int s = nslots; s < (WITH_NF ? 2 * NPAIR : NP / 32); ++s) {
+        const int i = s * 32 + lane;
+        if (i < NP) {
+            w.P[i] = 0.0;
+            w.P[NP + i] = 0.0;
+            w.P[2 * NP + i] = 0.0;
+        }
+        if (WITH_NF) {
+            const int at = (((s >> 1) * 32 + lane) << 1) + (s & 1);
+            w.nf[at] = 0.f;
+            w.nf[NPAIR * 64 + at] = 0.f;
+            w.nf[2 * NPAIR * 64 + at] = 0.f;
+        }
     }
     __syncwarp();
     return bad;
+}
+
+// one hypothesis of opt_guess_translational_motion: plane normal through two random rows
+// (core_private.cpp:41-46).  The draws index the caller's ray order; `pos` maps to storage.
+__device__ __forceinline__ void draw_hypothesis(const DeviceData& dd, const FrameDesc& fd,
+                                                const double* sP, int NP, uint64_t key, uint32_t it,
+                                                double v[3]) {
+    const uint32_t a = rng_index(key, it, 0u, (uint32_t)fd.n);  // :42
+    uint32_t b, kk = 1u;
+    do { b = rng_index(key, it, kk++, (uint32_t)fd.n); } while (b == a);  // :43
+    const int pa = __ldg(dd.pos + fd.off + a), pb = __ldg(dd.pos + fd.off + b);
+    const double a0 = sP[pa], a1 = sP[NP + pa], a2 = sP[2 * NP + pa];
+    const double b0 = sP[pb], b1 = sP[NP + pb], b2 = sP[2 * NP + pb];
+    const double c0 = fma(a1, b2, -(a2 * b1));
+    const double c1 = fma(a2, b0, -(a0 * b2));
+    const double c2 = fma(a0, b1, -(a1 * b0));
+    safe_normalize3(c0, c1, c2, v);  // :45-46
 }
 
 // ------------------------------------------------------------------------------------------
@@ -156,39 +187,37 @@ __device__ __forceinline__ unsigned warp_select_hi(const unsigned (&h)[SLOTS], c
     }
 }
 
-// Phases B + C: opt_guess_translational_motion (core_private.cpp:34-59).  A hypothesis wins iff
-// more than n/4 of its squared residuals lie below the best quartile so far (<=> `med <
-// least_med`, :53); only then is its exact quartile selected.  Residual keys are compared as
-// (hi word, lo word) pairs of the non-negative doubles, i.e. in exact double order.
+// Exact estimator: opt_guess_translational_motion (core_private.cpp:34-59) in binary64, the
+// arithmetic contract itself.  A hypothesis wins iff more than n/4 of its squared residuals lie
+// below the best quartile so far (<=> `med < least_med`, :53); only then is its exact quartile
+// selected.  Residual keys are compared as (hi word, lo word) pairs of the non-negative doubles,
+// i.e. in exact double order.  Runs when the fp32 tournament below cannot certify its winner.
 template <int SLOTS>
-__device__ __forceinline__ void warp_ransac(const WarpSmem& w, int NP, int n, int iters,
-                                            uint64_t key, int lane, double M[3]) {
+__device__ __noinline__ void warp_ransac_exact(const DeviceData& dd, const FrameDesc& fd,
+                                               const WarpSmem& w, int iters, uint64_t key, int lane,
+                                               double M[3]) {
+    constexpr int NP = SLOTS * 32;
+    const int n = fd.n;
+    unsigned* skey = reinterpret_cast<unsigned*>(w.nf);
+    const unsigned long long nanbits = 0x7ff8000000000000ULL;
+    __syncwarp();
     double np[SLOTS][3];
 #pragma unroll
     for (int s = 0; s < SLOTS; ++s) {
         const int i = s * 32 + lane;
-        const double inv = w.inv[i];  // :35-36
-        np[s][0] = w.P[i] * inv;
-        np[s][1] = w.P[NP + i] * inv;
-        np[s][2] = w.P[2 * NP + i] * inv;
+        const double p0 = w.P[i], p1 = w.P[NP + i], p2 = w.P[2 * NP + i];
+        // padding entries get inv = NaN: their residuals sort above everything
+        const double inv = (i < n) ? row_inv_norm(p0, p1, p2) : __longlong_as_double((long long)nanbits);
+        np[s][0] = p0 * inv;  // :35-36
+        np[s][1] = p1 * inv;
+        np[s][2] = p2 * inv;
     }
     const int kth = n / 4;  // :52
     unsigned least_hi = 0x7ff00000u, least_lo = 1u;  // just above +inf
     M[0] = M[1] = M[2] = 0.0;
     for (int j0 = 0; j0 < iters; j0 += 32) {
         double v[3] = {0.0, 0.0, 0.0};
-        const int jj = j0 + lane;
-        if (jj < iters) {
-            const uint32_t a = rng_index(key, (uint32_t)jj, 0u, (uint32_t)n);  // :42
-            uint32_t b, kk = 1u;
-            do { b = rng_index(key, (uint32_t)jj, kk++, (uint32_t)n); } while (b == a);  // :43
-            const double a0 = w.P[a], a1 = w.P[NP + a], a2 = w.P[2 * NP + a];
-            const double b0 = w.P[b], b1 = w.P[NP + b], b2 = w.P[2 * NP + b];
-            const double c0 = fma(a1, b2, -(a2 * b1));
-            const double c1 = fma(a2, b0, -(a0 * b2));
-            const double c2 = fma(a0, b1, -(a1 * b0));
-            safe_normalize3(c0, c1, c2, v);  // :45-46
-        }
+        if (j0 + lane < iters) draw_hypothesis(dd, fd, w.P, NP, key, (uint32_t)(j0 + lane), v);
         const int cnt = (iters - j0) < 32 ? (iters - j0) : 32;
         for (int t = 0; t < cnt; ++t) {
             const double vx = __shfl_sync(FULL, v[0], t);
@@ -203,7 +232,7 @@ __device__ __forceinline__ void warp_ransac(const WarpSmem& w, int NP, int n, in
             for (int s = 0; s < SLOTS; ++s) {
                 const double r = dot3(np[s][0], np[s][1], np[s][2], vx, vy, vz);  // :48
                 r2[s] = r * r;                                                      // :49
-                h[s] = (unsigned)__double2hiint(r2[s]);
+                h[s] = (unsigned)__double2hiint(r2[s]) & 0x7fffffffu;
                 const unsigned d = h[s] - least_hi;
                 below += d >> 31;
                 dmin = min(dmin, d);
@@ -219,10 +248,10 @@ __device__ __forceinline__ void warp_ransac(const WarpSmem& w, int NP, int n, in
             }
             if (nbelow > kth) {  // med < least_med: select the exact quartile
 #pragma unroll
-                for (int s = 0; s < SLOTS; ++s) w.key[s * 32 + lane] = h[s];
+                for (int s = 0; s < SLOTS; ++s) skey[s * 32 + lane] = h[s];
                 __syncwarp();
                 int cl, ce;
-                const unsigned H = warp_select_hi<SLOTS>(h, w.key, kth, least_hi, lane, cl, ce);
+                const unsigned H = warp_select_hi<SLOTS>(h, skey, kth, least_hi, lane, cl, ce);
                 // rank (kth - cl) among the ce keys whose hi word is H, ordered by lo word
                 int rem = kth - cl;
                 unsigned cur = 0u, lo_ans = 0u;
@@ -249,6 +278,213 @@ __device__ __forceinline__ void warp_ransac(const WarpSmem& w, int NP, int n, in
             }
         }
     }
+}
+
+// ------------------------------------------------------------------------------------------
+// fp32 tournament (the estimator's fast path).
+//
+// Only the ARGMIN over hypotheses of the quartile of the squared residuals matters (the first
+// hypothesis with the strictly smallest quartile wins, core_private.cpp:53-56), never the quartile
+// itself.  With a = fl32(np), w = fl32(v) and rho = fl32 dot, |rho - r| <= 5 * 2^-24 for the
+// binary64 residual r of the contract (|np|, |v| <= 1), and s = fl32(rho^2) has
+// |sqrt(s) - |r|| <= kDelta = 3.3e-7.  Order statistics are 1-Lipschitz in the sup norm, so the
+// fp32 quartile q32 and the exact one q64 of a hypothesis satisfy |sqrt(q32) - sqrt(q64)| <= kDelta.
+// Hence, with up(x) >= (sqrt(x) + kMargin)^2 and kMargin >= 2 kDelta:
+//   * count(s_t <= up(q32_best)) <= n/4   =>  q64_t > q64_best        (t is rigorously worse)
+//   * up(q32_t) < q32_best                =>  q64_t < q64_best        (t is rigorously better)
+// Anything else is too close to call in fp32; the task is then redone by warp_ransac_exact.  The
+// result is therefore always the exact estimator's M, bit for bit.
+constexpr float kMargin = 8.0e-7f;
+
+__device__ __forceinline__ unsigned up_bits(unsigned qbits) {  // rigorous upper bound (directed rounding)
+    const float u = __fadd_ru(__fsqrt_ru(__uint_as_float(qbits)), kMargin);
+    return __float_as_uint(__fmul_ru(u, u));
+}
+__device__ __forceinline__ float sqrt_approx(float x) {
+    float y;
+    asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+
+// count of keys <= pv over the warp (keys are non-negative floats: s <= pv <=> s - next(pv) < 0)
+template <int NPAIR>
+__device__ __forceinline__ int warp_count_le(const float2 (&s)[NPAIR], unsigned pv) {
+    const float nt = -__uint_as_float(pv + 1u);
+    const float2 nt2 = make_float2(nt, nt);
+    unsigned c = 0;
+#pragma unroll
+    for (int p = 0; p < NPAIR; ++p) {
+        const float2 e = __fadd2_rn(s[p], nt2);
+        c += __float_as_uint(e.x) >> 31;
+        c += __float_as_uint(e.y) >> 31;
+    }
+    return (int)__reduce_add_sync(FULL, c);
+}
+// smallest key >= lo over the warp (at least one exists)
+template <int NPAIR>
+__device__ __forceinline__ unsigned warp_min_ge(const float2 (&s)[NPAIR], unsigned lo) {
+    unsigned mn = 0xffffffffu;
+#pragma unroll
+    for (int p = 0; p < NPAIR; ++p) {  // keys below lo wrap to >= 2^31
+        mn = min(mn, __float_as_uint(s[p].x) - lo);
+        mn = min(mn, __float_as_uint(s[p].y) - lo);
+    }
+    return lo + __reduce_min_sync(FULL, mn);
+}
+// largest key < hi_excl over the warp (at least one exists)
+template <int NPAIR>
+__device__ __forceinline__ unsigned warp_max_lt(const float2 (&s)[NPAIR], unsigned hi_excl) {
+    unsigned mn = 0xffffffffu;
+    const unsigned top = hi_excl - 1u;
+#pragma unroll
+    for (int p = 0; p < NPAIR; ++p) {  // keys >= hi_excl wrap to >= 2^31
+        mn = min(mn, top - __float_as_uint(s[p].x));
+        mn = min(mn, top - __float_as_uint(s[p].y));
+    }
+    return top - __reduce_min_sync(FULL, mn);
+}
+
+// kk-th smallest (0-based) of the warp's NPAIR*64 fp32 keys (non-negative floats, compared through
+// their bit patterns), given count(key < hi_excl) = chi > kk.  Value-bracket search [lo, hi_excl)
+// with clo = count(key < lo) <= kk < chi.  Pivots: with no scale information (`sample`), the
+// matching order statistic of a 32-key sample (slot 0 of every lane); afterwards interpolation in
+// the sqrt domain (ranks of small residuals grow linearly in |r|), bisection of the bit pattern
+// after two steps of poor progress.  When the wanted key is the lowest or highest of the bracket
+// it is extracted with one warp min.
+template <int NPAIR>
+__device__ __forceinline__ unsigned warp_select32(const float2 (&s)[NPAIR], int kk, unsigned hi_excl,
+                                                  int chi, int npad, int n, bool sample) {
+    unsigned lo = 0u;
+    int clo = 0, poor = 0;
+    for (;;) {
+        if (hi_excl - lo == 1u) return lo;
+        if (kk == clo) return warp_min_ge<NPAIR>(s, lo);
+        if (kk == chi - 1) return warp_max_lt<NPAIR>(s, hi_excl);
+        unsigned pv;
+        if (sample) {
+            sample = false;
+            const int js = min((32 * (kk - npad)) / n, 31);
+            const unsigned k0 = __float_as_uint(s[0].x);
+            unsigned cur = 0u;
+            pv = 0u;
+            for (int i = 0; i <= js; ++i) {
+                pv = cur + __reduce_min_sync(FULL, k0 - cur);
+                cur = pv + 1u;
+            }
+        } else if (poor >= 2) {
+            poor = 0;
+            pv = lo + ((hi_excl - lo) >> 1);
+        } else {
+            const int cl = (lo == 0u) ? npad : clo;  // the padding keys sit at +0
+            const float frac = ((float)(kk - cl) + 0.5f) / (float)(chi - cl);
+            const float sl = sqrt_approx(__uint_as_float(lo));
+            const float sh = sqrt_approx(__uint_as_float(hi_excl));
+            const float sq = fmaf(sh - sl, frac, sl);
+            pv = __float_as_uint(sq * sq);
+        }
+        pv = max(pv, lo);
+        pv = min(pv, hi_excl - 2u);
+        const int cnt = warp_count_le<NPAIR>(s, pv);
+        if (cnt > kk) {
+            poor = (2 * (cnt - clo) > (chi - clo)) ? poor + 1 : 0;
+            hi_excl = pv + 1u;
+            chi = cnt;
+        } else {
+            poor = (2 * (chi - cnt) > (chi - clo)) ? poor + 1 : 0;
+            lo = pv + 1u;
+            clo = cnt;
+        }
+    }
+}
+
+// returns false when the winner could not be certified (the caller then runs the exact estimator)
+template <int SLOTS>
+__device__ __forceinline__ bool warp_ransac_fast(const DeviceData& dd, const FrameDesc& fd,
+                                                 const WarpSmem& w, int iters, uint64_t key,
+                                                 int lane, double M[3]) {
+    constexpr int NP = SLOTS * 32, NPAIR = pairs_for(NP), NK = 2 * NPAIR;
+    const float2* nf2 = reinterpret_cast<const float2*>(w.nf);
+    float2 nx[NPAIR], ny[NPAIR], nz[NPAIR];
+#pragma unroll
+    for (int p = 0; p < NPAIR; ++p) {
+        nx[p] = nf2[p * 32 + lane];
+        ny[p] = nf2[(NPAIR + p) * 32 + lane];
+        nz[p] = nf2[(2 * NPAIR + p) * 32 + lane];
+    }
+    const int n = fd.n;
+    const int npad = NK * 32 - n;  // padding keys are +0: always counted, always below
+    const int kk = n / 4 + npad;   // :52
+    unsigned tau = 0x7f800000u;    // fp32 quartile of the best hypothesis so far (+inf: none yet)
+    float nthr = 0.f;              // -(nextafter(up(tau))): s <= up(tau)  <=>  s + nthr < 0
+    unsigned thr1 = 0u;
+    M[0] = M[1] = M[2] = 0.0;
+    for (int j0 = 0; j0 < iters; j0 += 32) {
+        double v[3] = {0.0, 0.0, 0.0};
+        if (j0 + lane < iters) draw_hypothesis(dd, fd, w.P, NP, key, (uint32_t)(j0 + lane), v);
+        const float w0 = (float)v[0], w1 = (float)v[1], w2 = (float)v[2];
+        const int cnt = (iters - j0) < 32 ? (iters - j0) : 32;
+        for (int t = 0; t < cnt; ++t) {
+            const float vx = __shfl_sync(FULL, w0, t), vy = __shfl_sync(FULL, w1, t),
+                        vz = __shfl_sync(FULL, w2, t);
+            const float2 vx2 = make_float2(vx, vx), vy2 = make_float2(vy, vy),
+                         vz2 = make_float2(vz, vz);
+            float2 sq[NPAIR];
+            unsigned hi_excl;
+            int chi;
+            const bool first = tau == 0x7f800000u;
+            if (!first) {
+                const float2 nt2 = make_float2(nthr, nthr);
+                unsigned c = 0;
+#pragma unroll
+                for (int p = 0; p < NPAIR; ++p) {
+                    float2 r = __fmul2_rn(nx[p], vx2);
+                    r = __ffma2_rn(ny[p], vy2, r);
+                    r = __ffma2_rn(nz[p], vz2, r);
+                    sq[p] = __fmul2_rn(r, r);
+                    const float2 e = __fadd2_rn(sq[p], nt2);
+                    c += __float_as_uint(e.x) >> 31;
+                    c += __float_as_uint(e.y) >> 31;
+                }
+                chi = (int)__reduce_add_sync(FULL, c);
+                if (chi <= kk) continue;  // rigorously worse than the best so far
+                hi_excl = thr1;
+            } else {
+                unsigned mx = 0u;
+#pragma unroll
+                for (int p = 0; p < NPAIR; ++p) {
+                    float2 r = __fmul2_rn(nx[p], vx2);
+                    r = __ffma2_rn(ny[p], vy2, r);
+                    r = __ffma2_rn(nz[p], vz2, r);
+                    sq[p] = __fmul2_rn(r, r);
+                    mx = max(mx, max(__float_as_uint(sq[p].x), __float_as_uint(sq[p].y)));
+                }
+                mx = __reduce_max_sync(FULL, mx);
+                if (mx >= 0x7f800000u) return false;
+                hi_excl = mx + 1u;
+                chi = NK * 32;
+            }
+            const unsigned q = warp_select32<NPAIR>(sq, kk, hi_excl, chi, npad, n, first);
+            const unsigned uq = up_bits(q);
+            if (!(uq < tau)) return false;  // too close to the best so far to call in fp32
+            tau = q;
+            thr1 = uq + 1u;
+            nthr = -__uint_as_float(thr1);
+            M[0] = __shfl_sync(FULL, v[0], t);
+            M[1] = __shfl_sync(FULL, v[1], t);
+            M[2] = __shfl_sync(FULL, v[2], t);
+        }
+    }
+    return true;
+}
+
+// Phases B + C of an estimator task
+template <int SLOTS>
+__device__ __forceinline__ void warp_ransac(const DeviceData& dd, const FrameDesc& fd,
+                                            const WarpSmem& w, int iters, uint64_t key, int lane,
+                                            bool rows_finite, double M[3], unsigned* n_exact) {
+    if (rows_finite && warp_ransac_fast<SLOTS>(dd, fd, w, iters, key, lane, M)) return;
+    if (n_exact && lane == 0) atomicAdd(n_exact, 1u);
+    warp_ransac_exact<SLOTS>(dd, fd, w, iters, key, lane, M);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -423,14 +659,17 @@ presync_kernel(DeviceData dd, const FrameDesc* __restrict__ frames, int F,
         const uint64_t key =
             rng_task_key(rng_prefix(seed, stream, call_no, idx_base + (uint64_t)di), fd.id);
         double M[3];
-        warp_ransac<SLOTS>(w, NP, fd.n, 20, key, lane, M);  // core_private.cpp:77
+        warp_ransac<SLOTS>(dd, fd, w, 20, key, lane, __reduce_or_sync(FULL, bad) == 0u, M,
+                           flags + 1);  // core_private.cpp:77
         if (!(is_finite(M[0]) && is_finite(M[1]) && is_finite(M[2]))) bad |= kFlagM;
         // :79-85
-        const double k = clamp_k(1.0 / warp_norm_PM(w.P, NP, nslots, lane, M, w.inv) * 1e2);
+        __syncwarp();
+        double* pm = reinterpret_cast<double*>(w.nf);
+        const double k = clamp_k(1.0 / warp_norm_PM(w.P, NP, nslots, lane, M, pm) * 1e2);
         const double scale = k / sqrt(dot3(M[0], M[1], M[2], M[0], M[1], M[2]));
         DD acc = dd_zero();
         for (int s = 0; s < nslots; ++s) {
-            const double r = w.inv[s * 32 + lane] * scale;
+            const double r = pm[s * 32 + lane] * scale;
             if (!is_finite(r)) bad |= kFlagR;
             const double rho = log1p_nonneg(r * r);
             if (!is_finite(rho)) bad |= kFlagRho;
@@ -472,11 +711,12 @@ sync_init_kernel(DeviceData dd, SyncBatchDev b, const double* __restrict__ sp_de
         if (!sp_active[task.sp]) continue;
         const int nslots = (task.fd.n + 31) >> 5;
         __syncwarp();
-        build_rows_smem<true>(dd, task.fd, sp_delay[task.sp], lane, w, NP);
+        const unsigned bad =
+            __reduce_or_sync(FULL, build_rows_smem<true>(dd, task.fd, sp_delay[task.sp], lane, w, NP));
         const uint64_t key =
             rng_task_key(rng_prefix(seed, kStreamSyncInit, sp_callno[task.sp], 0), task.fd.id);
         double M[3];
-        warp_ransac<SLOTS>(w, NP, task.fd.n, 200, key, lane, M);  // core_private.cpp:127
+        warp_ransac<SLOTS>(dd, task.fd, w, 200, key, lane, bad == 0u, M, nullptr);  // core_private.cpp:127
         const double nrm = warp_norm_PM(w.P, NP, nslots, lane, M, nullptr);
         if (lane == 0) {
             b.m[3 * t + 0] = M[0]; b.m[3 * t + 1] = M[1]; b.m[3 * t + 2] = M[2];
@@ -588,10 +828,11 @@ __global__ void probe_problem_kernel(DeviceData dd, FrameDesc fd, int NP, double
     const int lane = threadIdx.x & 31;
     const WarpSmem w = warp_smem(smem_raw, 0, NP, false);
     build_rows_smem<false>(dd, fd, delay, lane, w, NP);
-    for (int i = lane; i < fd.n; i += 32) {
-        out[3 * i] = w.P[i];
-        out[3 * i + 1] = w.P[NP + i];
-        out[3 * i + 2] = w.P[2 * NP + i];
+    for (int i = lane; i < fd.n; i += 32) {  // back to the caller's ray order
+        const int o = dd.orig[fd.off + i];
+        out[3 * o] = w.P[i];
+        out[3 * o + 1] = w.P[NP + i];
+        out[3 * o + 2] = w.P[2 * NP + i];
     }
 }
 __global__ void probe_log1p_kernel(const double* x, int n, double* out) {
@@ -627,15 +868,20 @@ __global__ void probe_lbfgs_kernel(DeviceData dd, FrameDesc fd, int NP, double d
 }
 template <int SLOTS>
 __global__ void probe_guess_kernel(DeviceData dd, FrameDesc fd, double delay, int iters,
-                                   uint64_t key_prefix, double* out) {
+                                   uint64_t key_prefix, int mode, double* out, unsigned* n_exact) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     constexpr int NP = SLOTS * 32;
     const int lane = threadIdx.x & 31;
     const WarpSmem w = warp_smem(smem_raw, 0, NP, true);
     const int nslots = (fd.n + 31) >> 5;
-    build_rows_smem<true>(dd, fd, delay, lane, w, NP);
+    const unsigned bad = __reduce_or_sync(FULL, build_rows_smem<true>(dd, fd, delay, lane, w, NP));
     double M[3];
-    warp_ransac<SLOTS>(w, NP, fd.n, iters, rng_task_key(key_prefix, fd.id), lane, M);
+    if (mode == 2)
+        warp_ransac_exact<SLOTS>(dd, fd, w, iters, rng_task_key(key_prefix, fd.id), lane, M);
+    else
+        warp_ransac<SLOTS>(dd, fd, w, iters, rng_task_key(key_prefix, fd.id), lane, bad == 0u, M,
+                           n_exact);
+    __syncwarp();
     const double nrm = warp_norm_PM(w.P, NP, nslots, lane, M, nullptr);
     if (lane == 0) { out[0] = M[0]; out[1] = M[1]; out[2] = M[2]; out[3] = clamp_k(1.0 / nrm * 1e2); }
 }
@@ -786,10 +1032,12 @@ void launch_probe_lbfgs(const DeviceData& dd, FrameDesc fd, double delay, double
     g_launches += 1;
 }
 void launch_probe_guess(const DeviceData& dd, FrameDesc fd, double delay, int iters,
-                        uint64_t key_prefix, double* d_mk, cudaStream_t st) {
+                        uint64_t key_prefix, int mode, double* d_mk, unsigned* d_n_exact,
+                        cudaStream_t st) {
     RS_DISPATCH_SLOTS(fd.n, {
         auto kern = probe_guess_kernel<SL>;
-        kern<<<1, 32, warp_smem_bytes(SL * 32, true), st>>>(dd, fd, delay, iters, key_prefix, d_mk);
+        kern<<<1, 32, warp_smem_bytes(SL * 32, true), st>>>(dd, fd, delay, iters, key_prefix, mode,
+                                                            d_mk, d_n_exact);
     });
     g_launches += 1;
 }

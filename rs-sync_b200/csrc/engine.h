@@ -24,6 +24,7 @@ struct DeviceData {
     // SoA ray planes: ts_a, ts_b, ra.x, ra.y, ra.z, rb.x, rb.y, rb.z
     const double* plane[8];
     const int32_t* orig;  // caller's index of each stored ray (rays are stored sorted by ts_a)
+    const int32_t* pos;   // inverse of orig inside each frame: storage slot of caller's ray i
 };
 
 enum RngStream : uint64_t { kStreamPreSync = 1, kStreamDebugPreSync = 2, kStreamSyncInit = 3 };
@@ -32,7 +33,8 @@ enum RngStream : uint64_t { kStreamPreSync = 1, kStreamDebugPreSync = 2, kStream
 enum : unsigned { kFlagP = 1u, kFlagM = 2u, kFlagR = 4u, kFlagRho = 8u };
 
 // ---- PreSync / DebugPreSync grid: cost[d] = sum_f framecost(d, f) -----------------------------
-// d_framecost: D x F scratch; d_costs: D outputs.  All pointers are device pointers.
+// d_framecost: D x F scratch; d_costs: D outputs; d_flags: 2 words {panic flags, tasks whose
+// translation estimate needed the exact binary64 estimator}.  All pointers are device pointers.
 void launch_presync_grid(const DeviceData& dd, const FrameDesc* d_frames, int F, int max_n,
                          const double* d_delays, int D, uint64_t seed, uint64_t stream,
                          uint64_t call_no, uint64_t idx_base, double* d_framecost, double* d_costs,
@@ -78,8 +80,10 @@ void launch_probe_loss(const DeviceData& dd, FrameDesc fd, double delay, const d
                        double* d_out /* loss3, loss5, g0,g1,g2 */, cudaStream_t st);
 void launch_probe_lbfgs(const DeviceData& dd, FrameDesc fd, double delay, double* d_m, double k,
                         double* d_f, int* d_stats, cudaStream_t st);
+// mode 0: the product path (fp32 tournament, exact estimator when it cannot certify the winner);
+// mode 2: the exact binary64 estimator only.  *d_n_exact is incremented when the exact one ran.
 void launch_probe_guess(const DeviceData& dd, FrameDesc fd, double delay, int iters, uint64_t key_prefix,
-                        double* d_mk /* m[3], k */, cudaStream_t st);
+                        int mode, double* d_mk /* m[3], k */, unsigned* d_n_exact, cudaStream_t st);
 
 // FP64 FMA peak microbenchmark: returns elapsed ms for `iters` x 8 dependent-chain FMAs per thread
 float run_fp64_peak(int blocks, int threads, int iters, double* d_sink, cudaStream_t st);

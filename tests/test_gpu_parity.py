@@ -63,6 +63,46 @@ def test_guess_motion_identical(pair_small):
                 assert kg == ko
 
 
+def test_fp32_tournament_equals_exact_estimator(pair_small):
+    """the product path (fp32 tournament, exact estimator when undecided) returns the exact binary64
+    estimator's hypothesis bit for bit, and certifies most tasks without it"""
+    g, o, w = pair_small
+    exact_used = 0
+    total = 0
+    for fid in [int(f) for f in w.frame_ids[::7]]:
+        for off, delay in enumerate(np.linspace(-0.08, 0.08, 9)):
+            for iters, stream in ((20, 1), (200, 3)):
+                mf, kf, used = g.probe_guess_motion_ex(fid, float(delay), iters, stream, 1, off, 0)
+                me, ke, _ = g.probe_guess_motion_ex(fid, float(delay), iters, stream, 1, off, 2)
+                assert np.array_equal(mf, me) and kf == ke, (fid, delay, iters)
+                if iters == 20:
+                    exact_used += used
+                    total += 1
+                    mo, ko = o.guess_motion(fid, float(delay), 20, 1, 1, off)
+                    assert np.array_equal(mf, mo) and kf == ko
+    assert exact_used <= 0.25 * total, (exact_used, total)
+
+
+def test_estimator_degenerate_scenes(rsb, oracle_loader, synth_mod):
+    """noise-free scene at the true delay (residuals ~1e-16, far below fp32 resolution) and a frame
+    of identical rays (all rows zero): the tournament must hand over to the exact estimator and the
+    curve must still match the oracle"""
+    w = synth_mod.make_workload("tiny", noise_px=0.0, outlier_frac=0.0, true_delay=0.02)
+    g = rsb.SyncProblem(seed=3).load(w)
+    o = oracle_loader.OracleProblem(threads=2, seed=3).load(w)
+    same = np.tile(w.rays_a[0][:1], (w.n_rays, 1))
+    for p in (g, o):
+        p.SetTrackResult(10 ** 4, w.ts_a[0], w.ts_a[0], same, same, w.n_rays)
+    fb, fe = int(w.frame_ids[0]), int(w.frame_ids[-1]) + 1
+    delays = np.array([0.0, 0.01, 0.02, 0.03])
+    assert rel_err(g.presync_grid(fb, fe, delays, call_no=2), o.presync_grid(fb, fe, delays, call_no=2)) <= TOL
+    st = g.stats()
+    assert st["last_grid_tasks"] == 4 * w.n_frames
+    cz = g.presync_grid(10 ** 4, 10 ** 4 + 1, delays)
+    assert np.array_equal(cz, o.presync_grid(10 ** 4, 10 ** 4 + 1, delays))
+    assert g.stats()["last_grid_exact_tasks"] == 4
+
+
 def test_loss_and_gradient(pair_small):
     g, o, w = pair_small
     fid = int(w.frame_ids[10])
