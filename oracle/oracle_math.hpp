@@ -15,6 +15,8 @@
 #include <cstring>
 #include <limits>
 
+#include "log1p_table.hpp"
+
 namespace orc {
 
 // ---------------------------------------------------------------------------------------------
@@ -48,9 +50,14 @@ struct DD {
 // ---------------------------------------------------------------------------------------------
 // log1p for x >= 0 (the only domain the engine uses: x = r*r, core_private.cpp:82,121,354;
 // inline_utils.hpp:28-30).  The reference calls libm's log1p through arma::log1p; libm results
-// are not reproducible across platforms, so the spec fixes the classic argument-reduction
-// algorithm (1+x = 2^k (1+f), s = f/(2+f), degree-7 minimax polynomial in s^2) with a stated
-// operation order.  Agreement with libm's log1p is <= 1 ulp (tests/test_oracle_math.py).
+// are not reproducible across platforms, so the spec fixes a division-free table algorithm with a
+// stated operation order:
+//   u = 1 + x, c = x - (u - 1) (the rounding error of u, exact);  u = 2^k m, m in [1, 2);
+//   i = top 8 mantissa bits of m, (invc, logc) = table[i] (invc ~ 1/centre of the interval,
+//   logc = -log(invc); entry 0 is (1, 0) so that small x keep full relative accuracy);
+//   r = fma(m, invc, -1), |r| <= 2^-8;  log1p(r) = r + r^2 Q(r) with the degree-7 Taylor series;
+//   c/u ~ c invc (1 - r) 2^-k;  result = (k ln2_hi + logc) + (log1p(r) + (k ln2_lo + c/u)).
+// Agreement with a 80-digit log1p is <= 2 ulp (tests/test_oracle_math.py).
 static inline uint32_t hi_word(double x) {
     uint64_t b;
     std::memcpy(&b, &x, 8);
@@ -68,62 +75,30 @@ static inline double with_hi_word(double x, uint32_t hw) {
 static inline double log1p_nonneg(double x) {
     const double ln2_hi = 6.93147180369123816490e-01;
     const double ln2_lo = 1.90821492927058770002e-10;
-    const double L1 = 6.666666666666735130e-01, L2 = 3.999999999940941908e-01,
-                 L3 = 2.857142874366239149e-01, L4 = 2.222219843214978396e-01,
-                 L5 = 1.818357216161805012e-01, L6 = 1.531383769920937332e-01,
-                 L7 = 1.479819860511658591e-01;
+    const double C2 = -0.5, C3 = 1.0 / 3.0, C4 = -0.25, C5 = 0.2, C6 = -1.0 / 6.0, C7 = 1.0 / 7.0;
     if (!(x < std::numeric_limits<double>::infinity())) return x;  // +inf, NaN
-    if (x < 0x1p-29) return x - (x * x) * 0.5;
-    int k = 0;
-    double f = x, c = 0.0;
-    uint32_t hu = 1;
-    if (!(x < 0.41421356237309503)) {  // 1+x >= sqrt(2): reduce
-        double u;
-        if (x < 0x1p53) {
-            u = 1.0 + x;
-            hu = hi_word(u);
-            k = (int)(hu >> 20) - 1023;
-            c = (k > 0) ? 1.0 - (u - x) : x - (u - 1.0);  // rounding error of 1+x
-            c = c / u;
-        } else {
-            u = x;
-            hu = hi_word(u);
-            k = (int)(hu >> 20) - 1023;
-            c = 0.0;
-        }
-        hu &= 0x000fffffu;
-        if (hu < 0x6a09eu) {
-            u = with_hi_word(u, hu | 0x3ff00000u);  // u in [1, sqrt2)
-        } else {
-            k += 1;
-            u = with_hi_word(u, hu | 0x3fe00000u);  // u in [sqrt2/2, 1)
-            hu = (0x00100000u - hu) >> 2;
-        }
-        f = u - 1.0;
-    }
+    const double u = 1.0 + x;
+    const double c = x - (u - 1.0);
+    const uint32_t hu = hi_word(u);
+    const int k = (int)(hu >> 20) - 1023;
+    const uint32_t i = (hu >> 12) & 0xffu;
+    const double m = with_hi_word(u, (hu & 0x000fffffu) | 0x3ff00000u);
+    const double invc = kLog1pTable[2 * i], logc = kLog1pTable[2 * i + 1];
+    const double r = fmad(m, invc, -1.0);
+    double q = fmad(r, C7, C6);
+    q = fmad(r, q, C5);
+    q = fmad(r, q, C4);
+    q = fmad(r, q, C3);
+    q = fmad(r, q, C2);
+    const double r2 = r * r;
+    const double p = fmad(r2, q, r);
+    double t = c * invc;
+    t = fmad(-r, t, t);
+    const double corr = t * with_hi_word(0.0, (uint32_t)(1023 - k) << 20);  // * 2^-k
     const double dk = (double)k;
-    const double hfsq = (0.5 * f) * f;
-    if (hu == 0) {  // |f| < 2^-20
-        if (f == 0.0) {
-            if (k == 0) return 0.0;
-            c = fmad(dk, ln2_lo, c);
-            return fmad(dk, ln2_hi, c);
-        }
-        double R = hfsq * (1.0 - 0.66666666666666666 * f);
-        if (k == 0) return f - R;
-        return dk * ln2_hi - ((R - fmad(dk, ln2_lo, c)) - f);
-    }
-    const double s = f / (2.0 + f);
-    const double z = s * s;
-    double R = fmad(z, L7, L6);
-    R = fmad(z, R, L5);
-    R = fmad(z, R, L4);
-    R = fmad(z, R, L3);
-    R = fmad(z, R, L2);
-    R = fmad(z, R, L1);
-    R = z * R;
-    if (k == 0) return f - (hfsq - s * (hfsq + R));
-    return dk * ln2_hi - ((hfsq - fmad(s, hfsq + R, fmad(dk, ln2_lo, c))) - f);
+    const double lo = fmad(dk, ln2_lo, corr);
+    const double hi = fmad(dk, ln2_hi, logc);
+    return hi + (p + lo);
 }
 
 // ---------------------------------------------------------------------------------------------

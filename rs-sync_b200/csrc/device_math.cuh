@@ -45,67 +45,52 @@ __device__ __forceinline__ double warp_dd_sum(DD a) {
 }
 
 // ---- log1p on x >= 0 (arma::log1p at core_private.cpp:82,121,354; inline_utils.hpp:28-30) ----
-// Argument reduction 1+x = 2^k (1+f), s = f/(2+f), degree-7 polynomial in s^2; the operation
-// order is part of the contract (the CPU oracle evaluates the same expression tree).
-__device__ __forceinline__ double log1p_nonneg(double x) {
+// Division-free table algorithm; the operation order is part of the contract (the CPU oracle
+// evaluates the same expression tree on the same table, csrc/log1p_table.h):
+//   u = 1 + x, c = x - (u - 1) (rounding error of u, exact);  u = 2^k m, m in [1, 2);
+//   (invc, logc) = table[top 8 mantissa bits of m]  (entry 0 is (1, 0): full relative accuracy for
+//   small x);  r = fma(m, invc, -1), |r| <= 2^-8;  log1p(r) = r + r^2 Q(r), degree-7 Taylor;
+//   c/u ~ c invc (1 - r) 2^-k;  result = (k ln2_hi + logc) + (log1p(r) + (k ln2_lo + c/u)).
+// `tab` is the block's shared-memory copy of the table (load_log1p_table).
+__device__ const double kLog1pTableDev[512] = {
+#define RS_LOG1P_TABLE_BODY
+#include "log1p_table.h"
+#undef RS_LOG1P_TABLE_BODY
+};
+constexpr int kLog1pTableBytes = 512 * 8;
+
+__device__ __forceinline__ void load_log1p_table(double* smem_tab) {
+    for (int i = threadIdx.x; i < 512; i += blockDim.x) smem_tab[i] = kLog1pTableDev[i];
+    __syncthreads();
+}
+
+__device__ __forceinline__ double log1p_nonneg(double x, const double* __restrict__ tab) {
     const double ln2_hi = 6.93147180369123816490e-01;
     const double ln2_lo = 1.90821492927058770002e-10;
-    const double L1 = 6.666666666666735130e-01, L2 = 3.999999999940941908e-01,
-                 L3 = 2.857142874366239149e-01, L4 = 2.222219843214978396e-01,
-                 L5 = 1.818357216161805012e-01, L6 = 1.531383769920937332e-01,
-                 L7 = 1.479819860511658591e-01;
-    if (!(x < __longlong_as_double(0x7ff0000000000000LL))) return x;  // +inf, NaN
-    if (x < 0x1p-29) return x - (x * x) * 0.5;
-    int k = 0;
-    double f = x, c = 0.0;
-    unsigned hu = 1;
-    if (!(x < 0.41421356237309503)) {
-        double u;
-        if (x < 0x1p53) {
-            u = 1.0 + x;
-            hu = (unsigned)__double2hiint(u);
-            k = (int)(hu >> 20) - 1023;
-            c = (k > 0) ? 1.0 - (u - x) : x - (u - 1.0);
-            c = c / u;
-        } else {
-            u = x;
-            hu = (unsigned)__double2hiint(u);
-            k = (int)(hu >> 20) - 1023;
-            c = 0.0;
-        }
-        hu &= 0x000fffffu;
-        if (hu < 0x6a09eu) {
-            u = __hiloint2double((int)(hu | 0x3ff00000u), __double2loint(u));
-        } else {
-            k += 1;
-            u = __hiloint2double((int)(hu | 0x3fe00000u), __double2loint(u));
-            hu = (0x00100000u - hu) >> 2;
-        }
-        f = u - 1.0;
-    }
+    const double C2 = -0.5, C3 = 1.0 / 3.0, C4 = -0.25, C5 = 0.2, C6 = -1.0 / 6.0, C7 = 1.0 / 7.0;
+    const double u = 1.0 + x;
+    const double c = x - (u - 1.0);
+    const unsigned hu = (unsigned)__double2hiint(u);
+    const int k = (int)(hu >> 20) - 1023;
+    const double m = __hiloint2double((int)((hu & 0x000fffffu) | 0x3ff00000u), __double2loint(u));
+    const double2 e = *reinterpret_cast<const double2*>(
+        reinterpret_cast<const char*>(tab) + ((hu >> 8) & 0xff0u));  // 16 B * (top 8 mantissa bits)
+    const double r = fma(m, e.x, -1.0);
+    double q = fma(r, C7, C6);
+    q = fma(r, q, C5);
+    q = fma(r, q, C4);
+    q = fma(r, q, C3);
+    q = fma(r, q, C2);
+    const double r2 = r * r;
+    const double p = fma(r2, q, r);
+    double t = c * e.x;
+    t = fma(-r, t, t);
+    const double corr = t * __hiloint2double((1023 - k) << 20, 0);  // * 2^-k
     const double dk = (double)k;
-    const double hfsq = (0.5 * f) * f;
-    if (hu == 0) {
-        if (f == 0.0) {
-            if (k == 0) return 0.0;
-            c = fma(dk, ln2_lo, c);
-            return fma(dk, ln2_hi, c);
-        }
-        double R = hfsq * (1.0 - 0.66666666666666666 * f);
-        if (k == 0) return f - R;
-        return dk * ln2_hi - ((R - fma(dk, ln2_lo, c)) - f);
-    }
-    const double s = f / (2.0 + f);
-    const double z = s * s;
-    double R = fma(z, L7, L6);
-    R = fma(z, R, L5);
-    R = fma(z, R, L4);
-    R = fma(z, R, L3);
-    R = fma(z, R, L2);
-    R = fma(z, R, L1);
-    R = z * R;
-    if (k == 0) return f - (hfsq - s * (hfsq + R));
-    return dk * ln2_hi - ((hfsq - fma(s, hfsq + R, fma(dk, ln2_lo, c))) - f);
+    const double lo = fma(dk, ln2_lo, corr);
+    const double hi = fma(dk, ln2_hi, e.y);
+    const double res = hi + (p + lo);
+    return (x < __longlong_as_double(0x7ff0000000000000LL)) ? res : x;  // +inf, NaN
 }
 
 // ---- pinned counter-based RNG (replaces mtrand, inline_utils.hpp:13-17) ----------------------
@@ -117,8 +102,10 @@ __device__ __forceinline__ uint32_t rng_index(uint64_t task_key, uint32_t iter, 
 
 // ---- natural cubic spline on unit knots, 4 components (minispline.cpp:48-55, ndspline.cpp:21-27)
 // rec: n records of 16 doubles {y[4], b[4], c[4], d[4]}, 128-byte aligned.
-__device__ __forceinline__ void spline_eval4(const double* __restrict__ rec, int n, double x,
-                                             double q[4]) {
+// General form: clamps, the linear extrapolation on both sides and the reference's right-side
+// quirk (idx = n for x >= n, so h restarts at 0).  Only reached when x leaves [0, n-1).
+__device__ __noinline__ void spline_eval4_edges(const double* __restrict__ rec, int n, double x,
+                                                double q[4]) {
     const double fl = floor(x);
     const double idxf = fl < 0.0 ? 0.0 : (fl > (double)n ? (double)n : fl);
     const double h = x - idxf;
@@ -131,6 +118,24 @@ __device__ __forceinline__ void spline_eval4(const double* __restrict__ rec, int
     const double2 c01 = __ldg(p + 4), c23 = __ldg(p + 5);
     double2 d01 = __ldg(p + 6), d23 = __ldg(p + 7);
     if (extrap) { d01.x = d01.y = d23.x = d23.y = 0.0; }
+    q[0] = fma(fma(fma(d01.x, h, c01.x), h, b01.x), h, y01.x);
+    q[1] = fma(fma(fma(d01.y, h, c01.y), h, b01.y), h, y01.y);
+    q[2] = fma(fma(fma(d23.x, h, c23.x), h, b23.x), h, y23.x);
+    q[3] = fma(fma(fma(d23.y, h, c23.y), h, b23.y), h, y23.y);
+}
+__device__ __forceinline__ void spline_eval4(const double* __restrict__ rec, int n, double x,
+                                             double q[4]) {
+    const int r = __double2int_rd(x);  // floor; saturates for huge |x|, 0 for NaN
+    if ((unsigned)r >= (unsigned)(n - 1)) {  // x outside [0, n-1): edges (and NaN, which has r = 0
+        spline_eval4_edges(rec, n, x, q);    // only when n = 1)
+        return;
+    }
+    const double h = x - (double)r;
+    const double2* p = reinterpret_cast<const double2*>(rec + (size_t)r * 16);
+    const double2 y01 = __ldg(p + 0), y23 = __ldg(p + 1);
+    const double2 b01 = __ldg(p + 2), b23 = __ldg(p + 3);
+    const double2 c01 = __ldg(p + 4), c23 = __ldg(p + 5);
+    const double2 d01 = __ldg(p + 6), d23 = __ldg(p + 7);
     q[0] = fma(fma(fma(d01.x, h, c01.x), h, b01.x), h, y01.x);
     q[1] = fma(fma(fma(d01.y, h, c01.y), h, b01.y), h, y01.y);
     q[2] = fma(fma(fma(d23.x, h, c23.x), h, b23.x), h, y23.x);

@@ -76,7 +76,7 @@ template <bool WITH_NF>
 __device__ __forceinline__ unsigned build_rows_smem(const DeviceData& dd, const FrameDesc& fd,
                                                     double delay, int lane, const WarpSmem& w,
                                                     int NP) {
-    unsigned bad = 0;
+    float fin = 0.f;  // stays finite iff every row is (rows and 1/|row| feed it)
     const int nslots = (fd.n + 31) >> 5;
     const int NPAIR = pairs_for(NP);
     for (int s = 0; s < nslots; ++s) {
@@ -90,16 +90,18 @@ __device__ __forceinline__ unsigned build_rows_smem(const DeviceData& dd, const 
         double row[3];
         problem_row(dd.rec, dd.nq, dd.q0, dd.sr, delay, tsa, tsb, ax, ay, az, bx, by, bz, row);
         if (i >= fd.n) { row[0] = row[1] = row[2] = 0.0; }
-        if (!(is_finite(row[0]) && is_finite(row[1]) && is_finite(row[2]))) bad = kFlagP;
         w.P[i] = row[0];
         w.P[NP + i] = row[1];
         w.P[2 * NP + i] = row[2];
         if (WITH_NF) {
             const double inv = row_inv_norm(row[0], row[1], row[2]);  // core_private.cpp:35-36
             const int at = (((s >> 1) * 32 + lane) << 1) + (s & 1);
-            w.nf[at] = (float)(row[0] * inv);
-            w.nf[NPAIR * 64 + at] = (float)(row[1] * inv);
-            w.nf[2 * NPAIR * 64 + at] = (float)(row[2] * inv);
+            const float f0 = (float)(row[0] * inv), f1 = (float)(row[1] * inv),
+                        f2 = (float)(row[2] * inv);
+            w.nf[at] = f0;
+            w.nf[NPAIR * 64 + at] = f1;
+            w.nf[2 * NPAIR * 64 + at] = f2;
+            fin += (fabsf(f0) + fabsf(f1)) + fabsf(f2);  // inf row -> inv = 0 -> NaN
         }
     }
     for (int s = nslots; s < (WITH_NF ? 2 * NPAIR : NP / 32); ++s) {
@@ -117,7 +119,7 @@ __device__ __forceinline__ unsigned build_rows_smem(const DeviceData& dd, const 
         }
     }
     __syncwarp();
-    return bad;
+    return (__float_as_uint(fin) & 0x7f800000u) == 0x7f800000u ? kFlagP : 0u;
 }
 
 // one hypothesis of opt_guess_translational_motion: plane normal through two random rows
@@ -490,13 +492,14 @@ __device__ __forceinline__ void warp_ransac(const DeviceData& dd, const FrameDes
 // ------------------------------------------------------------------------------------------
 // FrameState::Loss 3-arg (core_private.cpp:117-123) on the warp's shared rows
 __device__ __noinline__ double warp_loss3_smem(const double* __restrict__ sP, int NP, int nslots,
-                                               int lane, double m0, double m1, double m2, double k) {
+                                               int lane, double m0, double m1, double m2, double k,
+                                               const double* __restrict__ tab) {
     const double scale = k / sqrt(dot3(m0, m1, m2, m0, m1, m2));
     DD acc = dd_zero();
     for (int s = 0; s < nslots; ++s) {
         const int i = s * 32 + lane;
         const double r = dot3(sP[i], sP[NP + i], sP[2 * NP + i], m0, m1, m2) * scale;
-        dd_add(acc, log1p_nonneg(r * r));  // padding rows are 0 -> log1p(0) = 0
+        dd_add(acc, log1p_nonneg(r * r, tab));  // padding rows are 0 -> log1p(0) = 0
     }
     return warp_dd_sum(acc);
 }
@@ -507,7 +510,8 @@ struct Loss5 {
     double f, g0, g1, g2;
 };
 __device__ __noinline__ Loss5 warp_loss5_smem(const double* __restrict__ sP, int NP, int nslots,
-                                              int lane, double m0, double m1, double m2, double k) {
+                                              int lane, double m0, double m1, double m2, double k,
+                                              const double* __restrict__ tab) {
     const double kk = k * k;
     const double den = dot3(m0, m1, m2, m0, m1, m2) / kk;
     const double inv_den = 1.0 / den;
@@ -517,7 +521,7 @@ __device__ __noinline__ Loss5 warp_loss5_smem(const double* __restrict__ sP, int
         const double p0 = sP[i], p1 = sP[NP + i], p2 = sP[2 * NP + i];
         const double v1 = dot3(p0, p1, p2, m0, m1, m2);
         const double u = (v1 * v1) * inv_den;
-        dd_add(L, log1p_nonneg(u));
+        dd_add(L, log1p_nonneg(u, tab));
         const double wgt = 1.0 / (1.0 + u);
         const double wv = wgt * v1;
         dd_add(g0, wv * p0);
@@ -540,13 +544,14 @@ __device__ __noinline__ Loss5 warp_loss5_smem(const double* __restrict__ sP, int
 // ens::L_BFGS on a 3-vector (call site core_private.cpp:264-294); every lane runs the same scalar
 // control flow on identical values, the objective is evaluated cooperatively.
 __device__ __forceinline__ double warp_lbfgs(const double* sP, int NP, int nslots, int lane,
-                                             double x[3], double k, int& n_iters, int& n_evals) {
+                                             double x[3], double k, const double* tab, int& n_iters,
+                                             int& n_evals) {
     constexpr int numBasis = 10, maxIterations = 200, maxTrials = 50;
     const double minGradientNorm = 1e-4, armijo = 1e-4, wolfe = 0.9, factr = 1e-15,
                  minStep = 1e-20, maxStep = 1e20;
     double S[numBasis][3], Y[numBasis][3], rho[numBasis], alpha[numBasis];
     double g[3], oldx[3], oldg[3], dir[3], trial[3];
-    Loss5 e = warp_loss5_smem(sP, NP, nslots, lane, x[0], x[1], x[2], k);
+    Loss5 e = warp_loss5_smem(sP, NP, nslots, lane, x[0], x[1], x[2], k, tab);
     double f = e.f;
     g[0] = e.g0; g[1] = e.g1; g[2] = e.g2;
     n_evals = 1;
@@ -593,7 +598,7 @@ __device__ __forceinline__ double warp_lbfgs(const double* sP, int NP, int nslot
         int trials = 0;
         for (;;) {
             for (int c = 0; c < 3; ++c) trial[c] = x[c] + step * dir[c];
-            e = warp_loss5_smem(sP, NP, nslots, lane, trial[0], trial[1], trial[2], k);
+            e = warp_loss5_smem(sP, NP, nslots, lane, trial[0], trial[1], trial[2], k, tab);
             f = e.f;
             g[0] = e.g0; g[1] = e.g1; g[2] = e.g2;
             n_evals++;
@@ -635,6 +640,19 @@ __device__ __forceinline__ double warp_norm_PM(const double* sP, int NP, int nsl
     return sqrt(warp_dd_sum(ss));
 }
 
+// which of pre_sync's panic conditions (core_private.cpp:76-83) a task with a non-finite cost hit
+__device__ __noinline__ unsigned presync_diagnose(const double* pm, int nslots, int lane, double scale,
+                                                  const double M[3], const double* tab) {
+    unsigned bad = 0;
+    if (!(is_finite(M[0]) && is_finite(M[1]) && is_finite(M[2]))) bad |= kFlagM;
+    for (int s = 0; s < nslots; ++s) {
+        const double r = pm[s * 32 + lane] * scale;
+        if (!is_finite(r)) bad |= kFlagR;
+        if (!is_finite(log1p_nonneg(r * r, tab))) bad |= kFlagRho;
+    }
+    return bad;
+}
+
 // ------------------------------------------------------------------------------------------
 // K1: PreSync / DebugPreSync grid.  task t -> (frame t / D, delay t % D): the warps of a block
 // work on the same frame, so its ray planes and spline window are served from L1.
@@ -647,7 +665,9 @@ presync_kernel(DeviceData dd, const FrameDesc* __restrict__ frames, int F,
     extern __shared__ __align__(16) unsigned char smem_raw[];
     constexpr int NP = SLOTS * 32;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const WarpSmem w = warp_smem(smem_raw, warp, NP, true);
+    double* tab = reinterpret_cast<double*>(smem_raw);
+    load_log1p_table(tab);
+    const WarpSmem w = warp_smem(smem_raw + kLog1pTableBytes, warp, NP, true);
     const long long total = (long long)F * D;
     for (long long t = (long long)blockIdx.x * kWarpsPerBlock + warp; t < total;
          t += (long long)gridDim.x * kWarpsPerBlock) {
@@ -655,13 +675,12 @@ presync_kernel(DeviceData dd, const FrameDesc* __restrict__ frames, int F,
         const FrameDesc fd = frames[fi];
         const int nslots = (fd.n + 31) >> 5;
         __syncwarp();
-        unsigned bad = build_rows_smem<true>(dd, fd, delays[di], lane, w, NP);
+        unsigned bad =
+            __reduce_or_sync(FULL, build_rows_smem<true>(dd, fd, delays[di], lane, w, NP));
         const uint64_t key =
             rng_task_key(rng_prefix(seed, stream, call_no, idx_base + (uint64_t)di), fd.id);
         double M[3];
-        warp_ransac<SLOTS>(dd, fd, w, 20, key, lane, __reduce_or_sync(FULL, bad) == 0u, M,
-                           flags + 1);  // core_private.cpp:77
-        if (!(is_finite(M[0]) && is_finite(M[1]) && is_finite(M[2]))) bad |= kFlagM;
+        warp_ransac<SLOTS>(dd, fd, w, 20, key, lane, bad == 0u, M, flags + 1);  // core_private.cpp:77
         // :79-85
         __syncwarp();
         double* pm = reinterpret_cast<double*>(w.nf);
@@ -670,15 +689,17 @@ presync_kernel(DeviceData dd, const FrameDesc* __restrict__ frames, int F,
         DD acc = dd_zero();
         for (int s = 0; s < nslots; ++s) {
             const double r = pm[s * 32 + lane] * scale;
-            if (!is_finite(r)) bad |= kFlagR;
-            const double rho = log1p_nonneg(r * r);
-            if (!is_finite(rho)) bad |= kFlagRho;
-            dd_add(acc, sqrt(rho));
+            dd_add(acc, sqrt(log1p_nonneg(r * r, tab)));
         }
         const double cost = sqrt(warp_dd_sum(acc));
         if (lane == 0) framecost[(size_t)di * F + fi] = cost;
-        bad = __reduce_or_sync(FULL, bad);
-        if (bad && lane == 0) atomicOr(flags, bad);
+        // the panic conditions of :76-83: non-finite values propagate into the cost, so the stage
+        // that produced them is only looked for when the cost (or a row) is not finite
+        if (bad || !is_finite(cost)) {
+            bad |= presync_diagnose(pm, nslots, lane, scale, M, tab);
+            bad = __reduce_or_sync(FULL, bad);
+            if (bad && lane == 0) atomicOr(flags, bad);
+        }
     }
 }
 
@@ -734,7 +755,9 @@ sync_motion_fgrad_kernel(DeviceData dd, SyncBatchDev b, int NP, const double* __
                          int* __restrict__ stats) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const WarpSmem w = warp_smem(smem_raw, warp, NP, false);
+    double* tab = reinterpret_cast<double*>(smem_raw);
+    load_log1p_table(tab);
+    const WarpSmem w = warp_smem(smem_raw + kLog1pTableBytes, warp, NP, false);
     for (int t = blockIdx.x * kWarpsPerBlock + warp; t < b.T; t += gridDim.x * kWarpsPerBlock) {
         const SyncTask task = b.tasks[t];
         if (!sp_active[task.sp]) continue;
@@ -751,16 +774,16 @@ sync_motion_fgrad_kernel(DeviceData dd, SyncBatchDev b, int NP, const double* __
             build_rows_smem<false>(dd, task.fd, delay, lane, w, NP);
             if (j == 0) {
                 int it, ev;
-                warp_lbfgs(w.P, NP, nslots, lane, m, k, it, ev);
+                warp_lbfgs(w.P, NP, nslots, lane, m, k, tab, it, ev);
                 if (lane == 0) {
                     b.m[3 * t] = m[0]; b.m[3 * t + 1] = m[1]; b.m[3 * t + 2] = m[2];
                     if (stats) { stats[2 * t] = it; stats[2 * t + 1] = ev; }
                 }
             } else if (j == 1) {
-                const Loss5 e = warp_loss5_smem(w.P, NP, nslots, lane, m[0], m[1], m[2], k);
+                const Loss5 e = warp_loss5_smem(w.P, NP, nslots, lane, m[0], m[1], m[2], k, tab);
                 if (lane == 0) scratch[3 * t] = e.f;
             } else {
-                const double v = warp_loss3_smem(w.P, NP, nslots, lane, m[0], m[1], m[2], k);
+                const double v = warp_loss3_smem(w.P, NP, nslots, lane, m[0], m[1], m[2], k, tab);
                 if (lane == 0) scratch[3 * t + (j - 1)] = v;
             }
         }
@@ -790,7 +813,9 @@ sync_trials_kernel(DeviceData dd, SyncBatchDev b, int NP, const double* __restri
                    double* __restrict__ scratch) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const WarpSmem w = warp_smem(smem_raw, warp, NP, false);
+    double* tab = reinterpret_cast<double*>(smem_raw);
+    load_log1p_table(tab);
+    const WarpSmem w = warp_smem(smem_raw + kLog1pTableBytes, warp, NP, false);
     const long long total = (long long)b.T * ntrial;
     for (long long q = (long long)blockIdx.x * kWarpsPerBlock + warp; q < total;
          q += (long long)gridDim.x * kWarpsPerBlock) {
@@ -801,7 +826,7 @@ sync_trials_kernel(DeviceData dd, SyncBatchDev b, int NP, const double* __restri
         __syncwarp();
         build_rows_smem<false>(dd, task.fd, trial_delay[(size_t)task.sp * ntrial + j], lane, w, NP);
         const double v = warp_loss3_smem(w.P, NP, nslots, lane, b.m[3 * t], b.m[3 * t + 1],
-                                         b.m[3 * t + 2], b.k[t]);
+                                         b.m[3 * t + 2], b.k[t], tab);
         if (lane == 0) scratch[(size_t)t * ntrial + j] = v;
     }
 }
@@ -836,30 +861,36 @@ __global__ void probe_problem_kernel(DeviceData dd, FrameDesc fd, int NP, double
     }
 }
 __global__ void probe_log1p_kernel(const double* x, int n, double* out) {
+    __shared__ __align__(16) double tab[512];
+    load_log1p_table(tab);
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n) out[i] = log1p_nonneg(x[i]);
+    if (i < n) out[i] = log1p_nonneg(x[i], tab);
 }
 __global__ void probe_loss_kernel(DeviceData dd, FrameDesc fd, int NP, double delay, const double* mp,
                                   double k, double* out) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int lane = threadIdx.x & 31;
-    const WarpSmem w = warp_smem(smem_raw, 0, NP, false);
+    double* tab = reinterpret_cast<double*>(smem_raw);
+    load_log1p_table(tab);
+    const WarpSmem w = warp_smem(smem_raw + kLog1pTableBytes, 0, NP, false);
     const int nslots = (fd.n + 31) >> 5;
     build_rows_smem<false>(dd, fd, delay, lane, w, NP);
-    const double l3 = warp_loss3_smem(w.P, NP, nslots, lane, mp[0], mp[1], mp[2], k);
-    const Loss5 e = warp_loss5_smem(w.P, NP, nslots, lane, mp[0], mp[1], mp[2], k);
+    const double l3 = warp_loss3_smem(w.P, NP, nslots, lane, mp[0], mp[1], mp[2], k, tab);
+    const Loss5 e = warp_loss5_smem(w.P, NP, nslots, lane, mp[0], mp[1], mp[2], k, tab);
     if (lane == 0) { out[0] = l3; out[1] = e.f; out[2] = e.g0; out[3] = e.g1; out[4] = e.g2; }
 }
 __global__ void probe_lbfgs_kernel(DeviceData dd, FrameDesc fd, int NP, double delay, double* mp,
                                    double k, double* fout, int* stats) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int lane = threadIdx.x & 31;
-    const WarpSmem w = warp_smem(smem_raw, 0, NP, false);
+    double* tab = reinterpret_cast<double*>(smem_raw);
+    load_log1p_table(tab);
+    const WarpSmem w = warp_smem(smem_raw + kLog1pTableBytes, 0, NP, false);
     const int nslots = (fd.n + 31) >> 5;
     build_rows_smem<false>(dd, fd, delay, lane, w, NP);
     double m[3] = {mp[0], mp[1], mp[2]};
     int it, ev;
-    const double f = warp_lbfgs(w.P, NP, nslots, lane, m, k, it, ev);
+    const double f = warp_lbfgs(w.P, NP, nslots, lane, m, k, tab, it, ev);
     if (lane == 0) {
         mp[0] = m[0]; mp[1] = m[1]; mp[2] = m[2];
         *fout = f;
@@ -954,7 +985,7 @@ void launch_presync_grid(const DeviceData& dd, const FrameDesc* d_frames, int F,
     }
     RS_DISPATCH_SLOTS(max_n, {
         auto kern = presync_kernel<SL>;
-        const size_t smem = (size_t)kWarpsPerBlock * warp_smem_bytes(SL * 32, true);
+        const size_t smem = kLog1pTableBytes + (size_t)kWarpsPerBlock * warp_smem_bytes(SL * 32, true);
         allow_smem(kern, smem);
         const int grid = grid_for(kern, smem, (long long)F * D);
         if (ev_begin) cudaEventRecord(ev_begin, st);
@@ -986,7 +1017,7 @@ void launch_sync_motion_fgrad(const DeviceData& dd, const SyncBatchDev& b, const
                               int* d_lbfgs_stats, cudaStream_t st) {
     if (b.T <= 0) return;
     const int NP = slots_for(b.max_n) * 32;
-    const size_t smem = (size_t)kWarpsPerBlock * warp_smem_bytes(NP, false);
+    const size_t smem = kLog1pTableBytes + (size_t)kWarpsPerBlock * warp_smem_bytes(NP, false);
     allow_smem(sync_motion_fgrad_kernel, smem);
     const int grid = grid_for(sync_motion_fgrad_kernel, smem, b.T);
     sync_motion_fgrad_kernel<<<grid, kWarpsPerBlock * 32, smem, st>>>(
@@ -1000,7 +1031,7 @@ void launch_sync_trials(const DeviceData& dd, const SyncBatchDev& b, const doubl
                         double* d_out, cudaStream_t st) {
     if (b.T <= 0 || ntrial <= 0) return;
     const int NP = slots_for(b.max_n) * 32;
-    const size_t smem = (size_t)kWarpsPerBlock * warp_smem_bytes(NP, false);
+    const size_t smem = kLog1pTableBytes + (size_t)kWarpsPerBlock * warp_smem_bytes(NP, false);
     allow_smem(sync_trials_kernel, smem);
     const int grid = grid_for(sync_trials_kernel, smem, (long long)b.T * ntrial);
     sync_trials_kernel<<<grid, kWarpsPerBlock * 32, smem, st>>>(dd, b, NP, d_trial_delay, ntrial,
@@ -1022,13 +1053,13 @@ void launch_probe_log1p(const double* d_x, int n, double* d_out, cudaStream_t st
 void launch_probe_loss(const DeviceData& dd, FrameDesc fd, double delay, const double* d_m, double k,
                        double* d_out, cudaStream_t st) {
     const int NP = slots_for(fd.n) * 32;
-    probe_loss_kernel<<<1, 32, warp_smem_bytes(NP, false), st>>>(dd, fd, NP, delay, d_m, k, d_out);
+    probe_loss_kernel<<<1, 32, kLog1pTableBytes + warp_smem_bytes(NP, false), st>>>(dd, fd, NP, delay, d_m, k, d_out);
     g_launches += 1;
 }
 void launch_probe_lbfgs(const DeviceData& dd, FrameDesc fd, double delay, double* d_m, double k,
                         double* d_f, int* d_stats, cudaStream_t st) {
     const int NP = slots_for(fd.n) * 32;
-    probe_lbfgs_kernel<<<1, 32, warp_smem_bytes(NP, false), st>>>(dd, fd, NP, delay, d_m, k, d_f, d_stats);
+    probe_lbfgs_kernel<<<1, 32, kLog1pTableBytes + warp_smem_bytes(NP, false), st>>>(dd, fd, NP, delay, d_m, k, d_f, d_stats);
     g_launches += 1;
 }
 void launch_probe_guess(const DeviceData& dd, FrameDesc fd, double delay, int iters,

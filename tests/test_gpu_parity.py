@@ -52,6 +52,22 @@ def test_problem_matrix_bit_exact(pair_small):
             assert np.array_equal(Pg, Po), (fid, delay, rel_err(Pg, Po))
 
 
+def test_problem_matrix_outside_gyro_span(pair_small):
+    """timestamps + delay left of the first gyro sample, on the last spline segment, and beyond the
+    end (the reference's right-side extrapolation quirk, minispline.cpp:48-55)"""
+    g, o, w = pair_small
+    n = w.n_rays
+    nq = w.quats.shape[0]
+    fid = int(w.frame_ids[5])
+    t = float(w.ts_a[5].mean())
+    t_end = w.gyro_t0 + (nq - 1) / w.gyro_rate
+    for delay in (-1e3, w.gyro_t0 - t - 0.0004, w.gyro_t0 - t + 0.005, t_end - t - 0.02, t_end - t - 0.0101,
+                  t_end - t + 0.0004, t_end - t + 0.0013, 1e3, 1e12):
+        Pg = g.probe_problem_matrix(fid, delay, n)
+        Po = o.problem_matrix(fid, delay, n)
+        assert np.array_equal(Pg, Po, equal_nan=True), (delay, rel_err(Pg, Po))
+
+
 def test_guess_motion_identical(pair_small):
     g, o, w = pair_small
     for fid in (int(w.frame_ids[3]), int(w.frame_ids[40])):

@@ -47,7 +47,7 @@ def test_log1p_accuracy(oracle_loader):
     ref = np.log1p(x)
     fin = np.isfinite(ref) & (ref > 0)
     ulp = np.spacing(ref[fin])
-    assert np.max(np.abs(got[fin] - ref[fin]) / ulp) <= 1.0
+    assert np.max(np.abs(got[fin] - ref[fin]) / ulp) <= 2.0
     assert got[-2] == 0.0 and np.isinf(got[-1])
     assert np.isnan(oracle_loader.log1p(np.array([np.nan]))[0])
 
