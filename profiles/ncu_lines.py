@@ -35,6 +35,11 @@ def main():
     hdr = rows[1]
     body = rows[2:]
     ie, ns, src = hdr.index("Instructions Executed"), hdr.index("# Samples"), hdr.index("Source")
+    stall_cols = {n: hdr.index(n) for n in ("stall_long_sb", "stall_short_sb", "stall_wait", "stall_math",
+                                            "stall_branch_resolving", "stall_no_inst", "stall_dispatch",
+                                            "stall_lg", "stall_mio", "stall_barrier", "stall_sleep") if n in hdr}
+    stall_tot = collections.Counter()
+    per_line_stall = collections.defaultdict(collections.Counter)
     assert len(body) == len(sass), (len(body), len(sass))
     per_line = collections.defaultdict(lambda: [0, 0, collections.Counter()])
     tot_i = tot_s = 0
@@ -45,6 +50,10 @@ def main():
         per_line[loc][0] += e
         per_line[loc][1] += s
         per_line[loc][2][op] += e
+        for n, ci in stall_cols.items():
+            v = int(r[ci].replace(",", "") or 0)
+            stall_tot[n] += v
+            per_line_stall[loc][n] += v
         tot_i += e
         tot_s += s
     print(f"total warp instructions {tot_i:,}  samples {tot_s:,}")
@@ -52,6 +61,11 @@ def main():
     for loc, (e, s, ops) in sorted(per_line.items(), key=lambda kv: -kv[1][0])[:top]:
         o = " ".join(f"{k}:{v * 100 // max(e, 1)}%" for k, v in ops.most_common(4))
         print(f"{e / tot_i * 100:6.2f} {s / max(tot_s, 1) * 100:6.2f}  {loc[0]}:{loc[1]:<5d}  {o}")
+    if "--stalls" in sys.argv:
+        for n in ("stall_long_sb", "stall_short_sb", "stall_wait"):
+            print(f"-- top lines for {n} (total {stall_tot[n]:,} = {stall_tot[n] / max(tot_s, 1) * 100:.1f}% of samples)")
+            for loc, c in sorted(per_line_stall.items(), key=lambda kv: -kv[1][n])[:12]:
+                print(f"   {c[n] / max(stall_tot[n], 1) * 100:5.1f}%  {loc[0]}:{loc[1]}")
     # per-file line ranges given as file:a-b=label
     for a in sys.argv[4:]:
         m = re.match(r"([\w.]+):(\d+)-(\d+)=(.*)", a)

@@ -97,13 +97,16 @@ struct rssync_problem {
     bool gyro_dirty = false;
     DevBuf<double> d_rec;
 
-    // ray arena: 8 SoA planes + the original ray index, frames appended in arrival order, each
-    // padded to 32 entries.  Inside a frame the rays are stored sorted by ts_a, so the 32 lanes of
-    // a warp hit one or two spline records per load instead of ~11 (the rolling-shutter readout
-    // spans ~11 gyro samples); `orig` maps a stored ray back to the caller's index, which is what
-    // the RNG draws of the translation estimator refer to.
-    PinBuf<double> h_plane[8];
-    DevBuf<double> d_plane[8];
+    // ray arena (DeviceData::rays): frames appended in arrival order, each padded to a multiple of
+    // 32 rays; every group of 32 rays is one 2 KB tile [8 fields][32 rays] of doubles (fields ts_a,
+    // ts_b, ra.xyz, rb.xyz), so a frame is one contiguous run of tiles (one TMA bulk copy) and a
+    // warp's field loads are full coalesced 256-byte rows.  Inside a frame the rays are stored
+    // sorted by ts_a, so the 32 lanes of a warp hit one or two spline records per load instead of
+    // ~11 (the rolling-shutter readout spans ~11 gyro samples); `orig` maps a stored ray back to
+    // the caller's index and `pos` is its inverse (the estimator's random draws index the caller's
+    // order).
+    PinBuf<double> h_rays;
+    DevBuf<double> d_rays;
     PinBuf<int32_t> h_orig, h_pos;
     DevBuf<int32_t> d_orig, d_pos;
     size_t used = 0, uploaded = 0, garbage = 0;
@@ -141,7 +144,7 @@ struct rssync_problem {
         dd.nq = (int)nq;
         dd.q0 = q0;
         dd.sr = sr;
-        for (int i = 0; i < 8; ++i) dd.plane[i] = d_plane[i].ptr;
+        dd.rays = d_rays.ptr;
         dd.orig = d_orig.ptr;
         dd.pos = d_pos.ptr;
         return dd;
@@ -171,14 +174,12 @@ int flush(rssync_problem* p) {
         p->gyro_dirty = false;
     }
     if (p->used > p->uploaded || p->rays_full_dirty) {
-        bool regrow = p->d_plane[0].cap < p->used;
+        bool regrow = p->d_rays.cap < p->used * 8;
         size_t from = (regrow || p->rays_full_dirty) ? 0 : p->uploaded;
-        for (int i = 0; i < 8; ++i) {
-            CUDA_TRY(p, p->d_plane[i].reserve(p->h_plane[i].cap));
-            if (int rc = h2d(p, p->d_plane[i].ptr + from, p->h_plane[i].ptr + from,
-                             (p->used - from) * sizeof(double)))
-                return rc;
-        }
+        CUDA_TRY(p, p->d_rays.reserve(p->h_rays.cap));
+        if (int rc = h2d(p, p->d_rays.ptr + from * 8, p->h_rays.ptr + from * 8,
+                         (p->used - from) * 8 * sizeof(double)))
+            return rc;
         CUDA_TRY(p, p->d_orig.reserve(p->h_orig.cap));
         if (int rc = h2d(p, p->d_orig.ptr + from, p->h_orig.ptr + from, (p->used - from) * sizeof(int32_t)))
             return rc;
@@ -453,7 +454,7 @@ void rssync_destroy(rssync_problem* p) {
     cudaSetDevice(p->device);
     p->d_rec.release();
     p->rec.release();
-    for (int i = 0; i < 8; ++i) { p->h_plane[i].release(); p->d_plane[i].release(); }
+    p->h_rays.release(); p->d_rays.release();
     p->h_orig.release(); p->d_orig.release();
     p->h_pos.release(); p->d_pos.release();
     p->d_frames.release(); p->d_delays.release(); p->d_framecost.release(); p->d_costs.release();
@@ -520,7 +521,7 @@ int validate_track(const double* ts_a, const double* ts_b, const double* rays_a,
 }
 
 // stage 2 (serial bookkeeping): where the frame lives in the arena
-int place_track(rssync_problem* p, int64_t frame, size_t count, size_t* off_out) {
+int place_track(rssync_problem* p, int64_t frame, size_t count, FrameDesc** fd_out) {
     const size_t padded = (count + 31) / 32 * 32;
     size_t off;
     auto it = p->frames.find(frame);
@@ -536,49 +537,57 @@ int place_track(rssync_problem* p, int64_t frame, size_t count, size_t* off_out)
         off = p->used;
         if (off + padded > (size_t)INT32_MAX) { p->err = "set-track-result: ray arena full"; return RSSYNC_E_INVALID; }
         const size_t need = off + padded;
-        if (need > p->h_plane[0].cap) {
-            const size_t want = std::max<size_t>(need, std::max<size_t>(p->h_plane[0].cap * 2, 1u << 16));
+        if (need > p->h_orig.cap) {
+            const size_t want = std::max<size_t>(need, std::max<size_t>(p->h_orig.cap * 2, 1u << 16));
             cudaSetDevice(p->device);
-            for (int i = 0; i < 8; ++i) CUDA_TRY(p, p->h_plane[i].reserve(want, p->used));
+            CUDA_TRY(p, p->h_rays.reserve(want * 8, p->used * 8));
             CUDA_TRY(p, p->h_orig.reserve(want, p->used));
             CUDA_TRY(p, p->h_pos.reserve(want, p->used));
         }
         p->used = need;
     }
-    p->frames[frame] = FrameDesc{frame, (int32_t)off, (int32_t)count};
+    FrameDesc& fd = p->frames[frame];  // map nodes are stable: fill_track completes ts_lo / ts_hi
+    fd = FrameDesc{frame, (int32_t)off, (int32_t)count, 0.0, 0.0};
     p->total_rays += count;
-    *off_out = off;
+    *fd_out = &fd;
     return RSSYNC_OK;
 }
 
-// stage 3 (thread-safe, disjoint arena ranges): sort by ts_a, transpose AoS -> SoA planes
-void fill_track(rssync_problem* p, size_t off, const double* ts_a, const double* ts_b,
+// stage 3 (thread-safe, disjoint arena ranges): sort by ts_a, transpose AoS -> [8][32] tiles
+void fill_track(rssync_problem* p, FrameDesc* fd, const double* ts_a, const double* ts_b,
                 const double* rays_a, const double* rays_b, size_t count,
                 std::vector<std::pair<double, int32_t>>& scratch) {
+    const size_t off = (size_t)fd->off;
     const size_t padded = (count + 31) / 32 * 32;
-    double* pl[8];
-    for (int i = 0; i < 8; ++i) pl[i] = p->h_plane[i].ptr + off;
+    double* tiles = p->h_rays.ptr + off * 8;
     int32_t* og = p->h_orig.ptr + off;
     int32_t* ps = p->h_pos.ptr + off;
     scratch.resize(count);
     for (size_t i = 0; i < count; ++i) scratch[i] = {ts_a[i], (int32_t)i};
     std::sort(scratch.begin(), scratch.end());  // (ts_a, index): ties keep the caller's order
-    for (size_t j = 0; j < count; ++j) {
-        const size_t i = (size_t)scratch[j].second;
-        og[j] = (int32_t)i;
-        ps[i] = (int32_t)j;
-        pl[0][j] = ts_a[i];
-        pl[1][j] = ts_b[i];
-        pl[2][j] = rays_a[3 * i]; pl[3][j] = rays_a[3 * i + 1]; pl[4][j] = rays_a[3 * i + 2];
-        pl[5][j] = rays_b[3 * i]; pl[6][j] = rays_b[3 * i + 1]; pl[7][j] = rays_b[3 * i + 2];
+    double lo = count ? ts_a[0] : 0.0, hi = lo;
+    for (size_t j = 0; j < padded; ++j) {
+        double* t = tiles + (j >> 5) * 256 + (j & 31);
+        if (j < count) {
+            const size_t i = (size_t)scratch[j].second;
+            og[j] = (int32_t)i;
+            ps[i] = (int32_t)j;
+            t[0] = ts_a[i];
+            t[32] = ts_b[i];
+            t[64] = rays_a[3 * i]; t[96] = rays_a[3 * i + 1]; t[128] = rays_a[3 * i + 2];
+            t[160] = rays_b[3 * i]; t[192] = rays_b[3 * i + 1]; t[224] = rays_b[3 * i + 2];
+            lo = std::min(lo, std::min(ts_a[i], ts_b[i]));
+            hi = std::max(hi, std::max(ts_a[i], ts_b[i]));
+        } else {  // padding lanes: finite, masked out by n
+            og[j] = (int32_t)j;
+            ps[j] = (int32_t)j;
+            t[0] = count ? ts_a[(size_t)scratch[count - 1].second] : 0.0;
+            t[32] = count ? ts_b[(size_t)scratch[count - 1].second] : 0.0;
+            for (int c = 2; c < 8; ++c) t[c * 32] = 0.0;
+        }
     }
-    for (size_t j = count; j < padded; ++j) {  // padding lanes: finite, masked out by n
-        og[j] = (int32_t)j;
-        ps[j] = (int32_t)j;
-        pl[0][j] = count ? pl[0][count - 1] : 0.0;
-        pl[1][j] = count ? pl[1][count - 1] : 0.0;
-        for (int c = 2; c < 8; ++c) pl[c][j] = 0.0;
-    }
+    fd->ts_lo = lo;
+    fd->ts_hi = hi;
 }
 
 template <class F>
@@ -611,9 +620,9 @@ int rssync_set_track(rssync_problem* p, int64_t frame, const double* ts_a, const
     if (!p) return RSSYNC_E_INVALID;
     const char* msg = nullptr;
     if (int rc = validate_track(ts_a, ts_b, rays_a, rays_b, count, &msg)) { p->err = msg; return rc; }
-    size_t off = 0;
-    if (int rc = place_track(p, frame, count, &off)) return rc;
-    fill_track(p, off, ts_a, ts_b, rays_a, rays_b, count, p->sort_scratch);
+    FrameDesc* fd = nullptr;
+    if (int rc = place_track(p, frame, count, &fd)) return rc;
+    fill_track(p, fd, ts_a, ts_b, rays_a, rays_b, count, p->sort_scratch);
     return RSSYNC_OK;
 }
 
@@ -633,12 +642,12 @@ int rssync_set_track_batch(rssync_problem* p, size_t n_frames, const int64_t* fr
     size_t n_ok = n_frames;
     for (size_t i = 0; i < n_frames; ++i)
         if (rc[i]) { n_ok = i; break; }
-    std::vector<size_t> off(n_ok);
+    std::vector<FrameDesc*> fds(n_ok);
     for (size_t i = 0; i < n_ok; ++i)
-        if (int r = place_track(p, frames[i], counts[i], &off[i])) return r;
+        if (int r = place_track(p, frames[i], counts[i], &fds[i])) return r;
     std::vector<std::vector<std::pair<double, int32_t>>> scratch(17);
     parallel_frames(n_ok, [&](size_t i, size_t t) {
-        fill_track(p, off[i], ts_a + at[i], ts_b + at[i], rays_a + 3 * at[i], rays_b + 3 * at[i], counts[i], scratch[t]);
+        fill_track(p, fds[i], ts_a + at[i], ts_b + at[i], rays_a + 3 * at[i], rays_b + 3 * at[i], counts[i], scratch[t]);
     });
     if (n_ok < n_frames) { p->err = msg[n_ok]; return rc[n_ok]; }
     return RSSYNC_OK;

@@ -104,8 +104,10 @@ __device__ __forceinline__ uint32_t rng_index(uint64_t task_key, uint32_t iter, 
 // rec: n records of 16 doubles {y[4], b[4], c[4], d[4]}, 128-byte aligned.
 // General form: clamps, the linear extrapolation on both sides and the reference's right-side
 // quirk (idx = n for x >= n, so h restarts at 0).  Only reached when x leaves [0, n-1).
-__device__ __noinline__ void spline_eval4_edges(const double* __restrict__ rec, int n, double x,
-                                                double q[4]) {
+struct Quat4 {
+    double w, x, y, z;
+};
+__device__ __noinline__ Quat4 spline_eval4_edges(const double* __restrict__ rec, int n, double x) {
     const double fl = floor(x);
     const double idxf = fl < 0.0 ? 0.0 : (fl > (double)n ? (double)n : fl);
     const double h = x - idxf;
@@ -118,16 +120,19 @@ __device__ __noinline__ void spline_eval4_edges(const double* __restrict__ rec, 
     const double2 c01 = __ldg(p + 4), c23 = __ldg(p + 5);
     double2 d01 = __ldg(p + 6), d23 = __ldg(p + 7);
     if (extrap) { d01.x = d01.y = d23.x = d23.y = 0.0; }
-    q[0] = fma(fma(fma(d01.x, h, c01.x), h, b01.x), h, y01.x);
-    q[1] = fma(fma(fma(d01.y, h, c01.y), h, b01.y), h, y01.y);
-    q[2] = fma(fma(fma(d23.x, h, c23.x), h, b23.x), h, y23.x);
-    q[3] = fma(fma(fma(d23.y, h, c23.y), h, b23.y), h, y23.y);
+    Quat4 q;
+    q.w = fma(fma(fma(d01.x, h, c01.x), h, b01.x), h, y01.x);
+    q.x = fma(fma(fma(d01.y, h, c01.y), h, b01.y), h, y01.y);
+    q.y = fma(fma(fma(d23.x, h, c23.x), h, b23.x), h, y23.x);
+    q.z = fma(fma(fma(d23.y, h, c23.y), h, b23.y), h, y23.y);
+    return q;
 }
 __device__ __forceinline__ void spline_eval4(const double* __restrict__ rec, int n, double x,
                                              double q[4]) {
     const int r = __double2int_rd(x);  // floor; saturates for huge |x|, 0 for NaN
     if ((unsigned)r >= (unsigned)(n - 1)) {  // x outside [0, n-1): edges (and NaN, which has r = 0
-        spline_eval4_edges(rec, n, x, q);    // only when n = 1)
+        const Quat4 e = spline_eval4_edges(rec, n, x);  // only when n = 1)
+        q[0] = e.w; q[1] = e.x; q[2] = e.y; q[3] = e.z;
         return;
     }
     const double h = x - (double)r;

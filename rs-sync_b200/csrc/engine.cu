@@ -21,6 +21,7 @@
 // run-time loops or __noinline__ functions.  The arithmetic contract is in device_math.cuh.
 #include "engine.h"
 
+#include <algorithm>
 #include <atomic>
 #include <cstdio>
 
@@ -81,27 +82,28 @@ __device__ __forceinline__ unsigned build_rows_smem(const DeviceData& dd, const 
     const int NPAIR = pairs_for(NP);
     for (int s = 0; s < nslots; ++s) {
         const int i = s * 32 + lane;
-        const size_t g = (size_t)fd.off + i;  // planes are padded to a multiple of 32 per frame
-        const double tsa = __ldg(dd.plane[0] + g), tsb = __ldg(dd.plane[1] + g);
-        const double ax = __ldg(dd.plane[2] + g), ay = __ldg(dd.plane[3] + g),
-                     az = __ldg(dd.plane[4] + g);
-        const double bx = __ldg(dd.plane[5] + g), by = __ldg(dd.plane[6] + g),
-                     bz = __ldg(dd.plane[7] + g);
+        const double* t = dd.rays + ((size_t)fd.off + s * 32) * 8 + lane;  // tile [8 fields][32 rays]
+        const double tsa = __ldg(t), tsb = __ldg(t + 32);
+        const double ax = __ldg(t + 64), ay = __ldg(t + 96), az = __ldg(t + 128);
+        const double bx = __ldg(t + 160), by = __ldg(t + 192), bz = __ldg(t + 224);
         double row[3];
         problem_row(dd.rec, dd.nq, dd.q0, dd.sr, delay, tsa, tsb, ax, ay, az, bx, by, bz, row);
         if (i >= fd.n) { row[0] = row[1] = row[2] = 0.0; }
         w.P[i] = row[0];
         w.P[NP + i] = row[1];
         w.P[2 * NP + i] = row[2];
-        if (WITH_NF) {
-            const double inv = row_inv_norm(row[0], row[1], row[2]);  // core_private.cpp:35-36
+        if (WITH_NF) {  // fp32 normalised copy for the tournament, see build_rows_staged
+            const float n2 = (float)dot3(row[0], row[1], row[2], row[0], row[1], row[2]);
+            float rs;
+            asm("rsqrt.approx.f32 %0, %1;" : "=f"(rs) : "f"(n2));
+            if (i >= fd.n) rs = 0.f;
+            else if (n2 < 1e-24f) rs = __uint_as_float(0x7fc00000u);
             const int at = (((s >> 1) * 32 + lane) << 1) + (s & 1);
-            const float f0 = (float)(row[0] * inv), f1 = (float)(row[1] * inv),
-                        f2 = (float)(row[2] * inv);
+            const float f0 = (float)row[0] * rs, f1 = (float)row[1] * rs, f2 = (float)row[2] * rs;
             w.nf[at] = f0;
             w.nf[NPAIR * 64 + at] = f1;
             w.nf[2 * NPAIR * 64 + at] = f2;
-            fin += (fabsf(f0) + fabsf(f1)) + fabsf(f2);  // inf row -> inv = 0 -> NaN
+            fin += (fabsf(f0) + fabsf(f1)) + fabsf(f2);  // non-finite row -> NaN
         }
     }
     for (int s = nslots; s < (WITH_NF ? 2 * NPAIR : NP / 32); ++s) {
@@ -117,6 +119,117 @@ __device__ __forceinline__ unsigned build_rows_smem(const DeviceData& dd, const 
             w.nf[NPAIR * 64 + at] = 0.f;
             w.nf[2 * NPAIR * 64 + at] = 0.f;
         }
+    }
+    __syncwarp();
+    return (__float_as_uint(fin) & 0x7f800000u) == 0x7f800000u ? kFlagP : 0u;
+}
+
+// ---- TMA bulk copies + mbarrier (PTX, sm_90+) --------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+    return (uint32_t)__cvta_generic_to_shared(p);
+}
+__device__ __forceinline__ void mbar_init(unsigned long long* bar, unsigned count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(unsigned long long* bar, unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
+                 : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(unsigned long long* bar, unsigned parity) {
+    unsigned ok;
+    asm volatile(
+        "{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+    return ok != 0u;
+}
+// global -> shared bulk copy (bytes: multiple of 16, both addresses 16-byte aligned); completion is
+// signalled on `bar` as transaction bytes
+__device__ __forceinline__ void tma_load_1d(void* dst_smem, const void* src_gmem, unsigned bytes,
+                                            unsigned long long* bar) {
+    asm volatile(
+        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+            smem_u32(dst_smem)),
+        "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
+        : "memory");
+}
+
+// Phase A of the PreSync grid kernel: same arithmetic as build_rows_smem<true>, with the frame's ray
+// tiles (sTiles) and the spline records [rec_first, rec_first + rec_cnt) (sRec) staged in shared
+// memory by TMA.  An evaluation whose record is not in the window (cannot happen: the window is
+// computed from the frame's timestamp bounds with a record of slack) takes the global path.
+__device__ __forceinline__ void spline_eval4_staged(const DeviceData& dd, const double* __restrict__ sRec,
+                                                    int rec_first, int rec_cnt, double x, double q[4]) {
+    const int r = __double2int_rd(x);
+    const unsigned at = (unsigned)(r - rec_first);
+    if (at >= (unsigned)rec_cnt) {
+        spline_eval4(dd.rec, dd.nq, x, q);
+        return;
+    }
+    const double h = x - (double)r;
+    const double2* p = reinterpret_cast<const double2*>(sRec + (size_t)at * 16);
+    const double2 y01 = p[0], y23 = p[1], b01 = p[2], b23 = p[3];
+    const double2 c01 = p[4], c23 = p[5], d01 = p[6], d23 = p[7];
+    q[0] = fma(fma(fma(d01.x, h, c01.x), h, b01.x), h, y01.x);
+    q[1] = fma(fma(fma(d01.y, h, c01.y), h, b01.y), h, y01.y);
+    q[2] = fma(fma(fma(d23.x, h, c23.x), h, b23.x), h, y23.x);
+    q[3] = fma(fma(fma(d23.y, h, c23.y), h, b23.y), h, y23.y);
+}
+__device__ __forceinline__ unsigned build_rows_staged(const DeviceData& dd, const FrameDesc& fd,
+                                                      double delay, int lane, const WarpSmem& w, int NP,
+                                                      const double* __restrict__ sTiles,
+                                                      const double* __restrict__ sRec, int rec_first,
+                                                      int rec_cnt) {
+    float fin = 0.f;
+    const int nslots = (fd.n + 31) >> 5;
+    const int NPAIR = pairs_for(NP);
+    for (int s = 0; s < nslots; ++s) {
+        const int i = s * 32 + lane;
+        const double* t = sTiles + s * 256 + lane;
+        const double xa = ((t[0] - dd.q0) + delay) * dd.sr;   // core_private.cpp:19-20
+        const double xb = ((t[32] - dd.q0) + delay) * dd.sr;
+        double qa[4], qb[4], ar[3], br[3], na, nb;
+        spline_eval4_staged(dd, sRec, rec_first, rec_cnt, xa, qa);
+        spline_eval4_staged(dd, sRec, rec_first, rec_cnt, xb, qb);
+        derotate_unnormalised(qa, t[64], t[96], t[128], ar, na);
+        derotate_unnormalised(qb, t[160], t[192], t[224], br, nb);
+        const double sc = 1.0 / (na * nb);
+        double row[3];
+        row[0] = fma(ar[1], br[2], -(ar[2] * br[1])) * sc;
+        row[1] = fma(ar[2], br[0], -(ar[0] * br[2])) * sc;
+        row[2] = fma(ar[0], br[1], -(ar[1] * br[0])) * sc;
+        if (i >= fd.n) { row[0] = row[1] = row[2] = 0.0; }
+        w.P[i] = row[0];
+        w.P[NP + i] = row[1];
+        w.P[2 * NP + i] = row[2];
+        // fp32 copy of the row-normalised row for the tournament: any accuracy the margin covers
+        // will do, so the norm is taken with rsqrt.approx (rel. error <= 2^-22.4).  Rows that
+        // safe_normalize would leave unscaled (|row| < 1e-12, also out of fp32 range) poison `fin`
+        // and send the task to the exact estimator.
+        const float n2 = (float)dot3(row[0], row[1], row[2], row[0], row[1], row[2]);
+        float rs;
+        asm("rsqrt.approx.f32 %0, %1;" : "=f"(rs) : "f"(n2));
+        if (i >= fd.n) rs = 0.f;
+        else if (n2 < 1e-24f) rs = __uint_as_float(0x7fc00000u);
+        const int at = (((s >> 1) * 32 + lane) << 1) + (s & 1);
+        const float f0 = (float)row[0] * rs, f1 = (float)row[1] * rs, f2 = (float)row[2] * rs;
+        w.nf[at] = f0;
+        w.nf[NPAIR * 64 + at] = f1;
+        w.nf[2 * NPAIR * 64 + at] = f2;
+        fin += (fabsf(f0) + fabsf(f1)) + fabsf(f2);  // non-finite row -> NaN
+    }
+    for (int s = nslots; s < 2 * NPAIR; ++s) {
+        const int i = s * 32 + lane;
+        if (i < NP) {
+            w.P[i] = 0.0;
+            w.P[NP + i] = 0.0;
+            w.P[2 * NP + i] = 0.0;
+        }
+        const int at = (((s >> 1) * 32 + lane) << 1) + (s & 1);
+        w.nf[at] = 0.f;
+        w.nf[NPAIR * 64 + at] = 0.f;
+        w.nf[2 * NPAIR * 64 + at] = 0.f;
     }
     __syncwarp();
     return (__float_as_uint(fin) & 0x7f800000u) == 0x7f800000u ? kFlagP : 0u;
@@ -194,10 +307,13 @@ __device__ __forceinline__ unsigned warp_select_hi(const unsigned (&h)[SLOTS], c
 // below the best quartile so far (<=> `med < least_med`, :53); only then is its exact quartile
 // selected.  Residual keys are compared as (hi word, lo word) pairs of the non-negative doubles,
 // i.e. in exact double order.  Runs when the fp32 tournament below cannot certify its winner.
+struct Vec3 {
+    double x, y, z;
+};
 template <int SLOTS>
-__device__ __noinline__ void warp_ransac_exact(const DeviceData& dd, const FrameDesc& fd,
-                                               const WarpSmem& w, int iters, uint64_t key, int lane,
-                                               double M[3]) {
+__device__ __noinline__ Vec3 warp_ransac_exact(const DeviceData& dd, const FrameDesc& fd,
+                                               const WarpSmem& w, int iters, uint64_t key, int lane) {
+    double M[3];
     constexpr int NP = SLOTS * 32;
     const int n = fd.n;
     unsigned* skey = reinterpret_cast<unsigned*>(w.nf);
@@ -280,6 +396,7 @@ __device__ __noinline__ void warp_ransac_exact(const DeviceData& dd, const Frame
             }
         }
     }
+    return Vec3{M[0], M[1], M[2]};
 }
 
 // ------------------------------------------------------------------------------------------
@@ -287,16 +404,20 @@ __device__ __noinline__ void warp_ransac_exact(const DeviceData& dd, const Frame
 //
 // Only the ARGMIN over hypotheses of the quartile of the squared residuals matters (the first
 // hypothesis with the strictly smallest quartile wins, core_private.cpp:53-56), never the quartile
-// itself.  With a = fl32(np), w = fl32(v) and rho = fl32 dot, |rho - r| <= 5 * 2^-24 for the
-// binary64 residual r of the contract (|np|, |v| <= 1), and s = fl32(rho^2) has
-// |sqrt(s) - |r|| <= kDelta = 3.3e-7.  Order statistics are 1-Lipschitz in the sup norm, so the
-// fp32 quartile q32 and the exact one q64 of a hypothesis satisfy |sqrt(q32) - sqrt(q64)| <= kDelta.
-// Hence, with up(x) >= (sqrt(x) + kMargin)^2 and kMargin >= 2 kDelta:
+// itself.  Let np, v, r = np.v be the contract's binary64 normalised row, hypothesis and residual
+// (|np|, |v| <= 1).  The tournament uses a = fl32(row) * rsqrt.approx(fl32(|row|^2)), i.e.
+// a_i = np_i (1 + e) with |e| <= (1/2 + 4 + 1 + 1) 2^-24 (conversion of |row|^2 halved by the square
+// root, rsqrt.approx <= 2^-22, conversion of the row, product), w = fl32(v) and the fp32 fma chain
+// rho (3 roundings): |rho - r| <= (6.5 + 1 + 3) 2^-24, and s = fl32(rho^2) has
+// |sqrt(s) - |r|| <= kDelta = 11 * 2^-24 = 6.6e-7.  Order statistics are 1-Lipschitz in the sup
+// norm, so the fp32 quartile q32 and the exact one q64 of a hypothesis satisfy
+// |sqrt(q32) - sqrt(q64)| <= kDelta.  Hence, with up(x) >= (sqrt(x) + kMargin)^2 (directed
+// rounding) and kMargin >= 2 kDelta:
 //   * count(s_t <= up(q32_best)) <= n/4   =>  q64_t > q64_best        (t is rigorously worse)
 //   * up(q32_t) < q32_best                =>  q64_t < q64_best        (t is rigorously better)
 // Anything else is too close to call in fp32; the task is then redone by warp_ransac_exact.  The
 // result is therefore always the exact estimator's M, bit for bit.
-constexpr float kMargin = 8.0e-7f;
+constexpr float kMargin = 1.4e-6f;
 
 __device__ __forceinline__ unsigned up_bits(unsigned qbits) {  // rigorous upper bound (directed rounding)
     const float u = __fadd_ru(__fsqrt_ru(__uint_as_float(qbits)), kMargin);
@@ -486,7 +607,8 @@ __device__ __forceinline__ void warp_ransac(const DeviceData& dd, const FrameDes
                                             bool rows_finite, double M[3], unsigned* n_exact) {
     if (rows_finite && warp_ransac_fast<SLOTS>(dd, fd, w, iters, key, lane, M)) return;
     if (n_exact && lane == 0) atomicAdd(n_exact, 1u);
-    warp_ransac_exact<SLOTS>(dd, fd, w, iters, key, lane, M);
+    const Vec3 e = warp_ransac_exact<SLOTS>(dd, fd, w, iters, key, lane);
+    M[0] = e.x; M[1] = e.y; M[2] = e.z;
 }
 
 // ------------------------------------------------------------------------------------------
@@ -642,9 +764,9 @@ __device__ __forceinline__ double warp_norm_PM(const double* sP, int NP, int nsl
 
 // which of pre_sync's panic conditions (core_private.cpp:76-83) a task with a non-finite cost hit
 __device__ __noinline__ unsigned presync_diagnose(const double* pm, int nslots, int lane, double scale,
-                                                  const double M[3], const double* tab) {
+                                                  double m0, double m1, double m2, const double* tab) {
     unsigned bad = 0;
-    if (!(is_finite(M[0]) && is_finite(M[1]) && is_finite(M[2]))) bad |= kFlagM;
+    if (!(is_finite(m0) && is_finite(m1) && is_finite(m2))) bad |= kFlagM;
     for (int s = 0; s < nslots; ++s) {
         const double r = pm[s * 32 + lane] * scale;
         if (!is_finite(r)) bad |= kFlagR;
@@ -654,49 +776,163 @@ __device__ __noinline__ unsigned presync_diagnose(const double* pm, int nslots, 
 }
 
 // ------------------------------------------------------------------------------------------
-// K1: PreSync / DebugPreSync grid.  task t -> (frame t / D, delay t % D): the warps of a block
-// work on the same frame, so its ray planes and spline window are served from L1.
+// K1: PreSync / DebugPreSync grid.
+//
+// Work unit = (frame, chunk of up to W consecutive delays), W = warps per block; warp j of the block
+// takes delay j of the chunk.  A block walks a contiguous range of units, so consecutive units
+// share the frame.  What phase A reads is staged in shared memory by TMA bulk copies issued by one
+// thread: the frame's ray tiles (contiguous in the arena; reloaded only when the frame changes)
+// and the window of spline records the chunk can touch (from the frame's timestamp bounds and the
+// chunk's delay range).  The buffers are only live during phase A: the last warp to finish phase A
+// of unit u issues the copies for unit u + 1, which then overlap phases B-D of unit u.  (With
+// ~200 KB of the SM's 228 KB carved out as shared memory the L1 keeps ~13 KB: un-staged, the same
+// loads hit L1 28 % of the time and wait on L2, profiles/r01_presync_v3c.md.)
+constexpr int kRecMax = 64;  // spline records per window (8 KB)
 template <int SLOTS>
-__global__ void __launch_bounds__(kWarpsPerBlock * 32, SLOTS <= 8 ? RS_MINB : 1)
+struct PresyncCfg {
+    static constexpr int kWarps = SLOTS <= 8 ? 10 : 8;
+    static constexpr int kMinBlocks = SLOTS <= 8 ? 2 : 1;
+    static constexpr size_t kTileBytes = (size_t)SLOTS * 2048;
+    static constexpr size_t kCtlOff = kLog1pTableBytes;
+    static constexpr size_t kTileOff = kCtlOff + 128;
+    static constexpr size_t kRecOff = kTileOff + kTileBytes;
+    static constexpr size_t kWarpOff = kRecOff + (size_t)kRecMax * 128;
+    static constexpr size_t kSmem = kWarpOff + (size_t)kWarps * warp_smem_bytes(SLOTS * 32, true);
+};
+struct StageCtl {
+    unsigned long long full;  // mbarrier: the staged data of the next unit has landed
+    unsigned arrived;         // warps that finished phase A of the current unit
+    int rec_first, rec_cnt;   // staged spline window; rec_cnt = 0: not staged, phase A reads global
+    int frame_loaded;         // index (into `frames`) of the frame whose tiles are staged, -1: none
+};
+
+template <int SLOTS>
+__device__ __forceinline__ void presync_stage_unit(const DeviceData& dd, const FrameDesc* frames,
+                                                   const double* delays, int D, int chunk, int cpf,
+                                                   int u, StageCtl* ctl, double* sTiles, double* sRec) {
+    const int fi = u / cpf, d0 = (u % cpf) * chunk;
+    const int d1 = min(D, d0 + chunk);
+    const FrameDesc fd = frames[fi];
+    double dmin = delays[d0], dmax = dmin;
+    for (int d = d0 + 1; d < d1; ++d) {
+        dmin = fmin(dmin, delays[d]);
+        dmax = fmax(dmax, delays[d]);
+    }
+    // x = ((ts - q0) + delay) * sr is monotone in ts and in delay, roundings included
+    const double x_lo = ((fd.ts_lo - dd.q0) + dmin) * dd.sr, x_hi = ((fd.ts_hi - dd.q0) + dmax) * dd.sr;
+    const double r_lo = floor(x_lo) - 1.0, r_hi = floor(x_hi) + 2.0;  // a record of slack either side
+    const bool ok = r_lo >= 0.0 && r_hi <= (double)(dd.nq - 1) && (r_hi - r_lo) < (double)kRecMax;
+    // the buffers were read through the generic proxy; order those reads before the async writes
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    unsigned bytes = 0;
+    const int first = ok ? (int)r_lo : 0, cnt = ok ? (int)(r_hi - r_lo) + 1 : 0;
+    const bool tiles = ok && ctl->frame_loaded != fi;
+    ctl->rec_first = first;
+    ctl->rec_cnt = cnt;
+    const unsigned tile_bytes = (unsigned)((fd.n + 31) >> 5) * 2048u;
+    if (ok) bytes += (unsigned)cnt * 128u;
+    if (tiles) {
+        bytes += tile_bytes;
+        ctl->frame_loaded = fi;
+    }
+    mbar_arrive_expect_tx(&ctl->full, bytes);
+    if (ok) tma_load_1d(sRec, dd.rec + (size_t)first * 16, (unsigned)cnt * 128u, &ctl->full);
+    if (tiles) tma_load_1d(sTiles, dd.rays + (size_t)fd.off * 8, tile_bytes, &ctl->full);
+}
+
+template <int SLOTS>
+__global__ void __launch_bounds__(PresyncCfg<SLOTS>::kWarps * 32, PresyncCfg<SLOTS>::kMinBlocks)
 presync_kernel(DeviceData dd, const FrameDesc* __restrict__ frames, int F,
-               const double* __restrict__ delays, int D, uint64_t seed, uint64_t stream,
-               uint64_t call_no, uint64_t idx_base, double* __restrict__ framecost,
+               const double* __restrict__ delays, int D, int chunk, int cpf, uint64_t seed,
+               uint64_t stream, uint64_t call_no, uint64_t idx_base, double* __restrict__ framecost,
                unsigned* __restrict__ flags) {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
+    using Cfg = PresyncCfg<SLOTS>;
+    extern __shared__ __align__(128) unsigned char smem_raw[];
     constexpr int NP = SLOTS * 32;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     double* tab = reinterpret_cast<double*>(smem_raw);
-    load_log1p_table(tab);
-    const WarpSmem w = warp_smem(smem_raw + kLog1pTableBytes, warp, NP, true);
-    const long long total = (long long)F * D;
-    for (long long t = (long long)blockIdx.x * kWarpsPerBlock + warp; t < total;
-         t += (long long)gridDim.x * kWarpsPerBlock) {
-        const int fi = (int)(t / D), di = (int)(t % D);
+    StageCtl* ctl = reinterpret_cast<StageCtl*>(smem_raw + Cfg::kCtlOff);
+    double* sTiles = reinterpret_cast<double*>(smem_raw + Cfg::kTileOff);
+    double* sRec = reinterpret_cast<double*>(smem_raw + Cfg::kRecOff);
+    const WarpSmem w = warp_smem(smem_raw + Cfg::kWarpOff, warp, NP, true);
+    const long long U = (long long)F * cpf;
+    const int u_begin = (int)(U * blockIdx.x / gridDim.x), u_end = (int)(U * (blockIdx.x + 1) / gridDim.x);
+    if (threadIdx.x == 0) {
+        mbar_init(&ctl->full, 1);
+        ctl->arrived = 0;
+        ctl->frame_loaded = -1;
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    load_log1p_table(tab);  // ends with __syncthreads()
+    if (threadIdx.x == 0 && u_begin < u_end)
+        presync_stage_unit<SLOTS>(dd, frames, delays, D, chunk, cpf, u_begin, ctl, sTiles, sRec);
+    unsigned parity = 0;
+    for (int u = u_begin; u < u_end; ++u) {
+        const int fi = u / cpf, d0 = (u % cpf) * chunk;
+        const int di = d0 + warp;
+        const bool active = warp < chunk && di < D;
         const FrameDesc fd = frames[fi];
         const int nslots = (fd.n + 31) >> 5;
+        while (!mbar_try_wait(&ctl->full, parity)) __nanosleep(64);
+        parity ^= 1u;
+        const int rec_first = *(volatile int*)&ctl->rec_first, rec_cnt = *(volatile int*)&ctl->rec_cnt;
+        unsigned bad = 0;
+        double delay = 0.0;
+        if (active) {
+            delay = delays[di];
+            bad = rec_cnt ? build_rows_staged(dd, fd, delay, lane, w, NP, sTiles, sRec, rec_first, rec_cnt)
+                          : build_rows_smem<true>(dd, fd, delay, lane, w, NP);
+            bad = __reduce_or_sync(FULL, bad);
+        }
         __syncwarp();
-        unsigned bad =
-            __reduce_or_sync(FULL, build_rows_smem<true>(dd, fd, delays[di], lane, w, NP));
+        if (lane == 0) {  // phase A of this unit no longer needs the staging buffers
+            __threadfence_block();
+            if (atomicAdd(&ctl->arrived, 1u) == (unsigned)(Cfg::kWarps - 1)) {
+                ctl->arrived = 0;
+                if (u + 1 < u_end)
+                    presync_stage_unit<SLOTS>(dd, frames, delays, D, chunk, cpf, u + 1, ctl, sTiles, sRec);
+            }
+        }
+        if (!active) continue;
         const uint64_t key =
             rng_task_key(rng_prefix(seed, stream, call_no, idx_base + (uint64_t)di), fd.id);
         double M[3];
         warp_ransac<SLOTS>(dd, fd, w, 20, key, lane, bad == 0u, M, flags + 1);  // core_private.cpp:77
         // :79-85
         __syncwarp();
-        double* pm = reinterpret_cast<double*>(w.nf);
-        const double k = clamp_k(1.0 / warp_norm_PM(w.P, NP, nslots, lane, M, pm) * 1e2);
+        // rows past the frame's last ray are zero: they add 0 to the norm and log1p(0) = 0 to the loss
+        double pmv[SLOTS];
+#pragma unroll
+        for (int s = 0; s < SLOTS; ++s) {
+            const int i = s * 32 + lane;
+            pmv[s] = dot3(w.P[i], w.P[NP + i], w.P[2 * NP + i], M[0], M[1], M[2]);
+        }
+        DD ss = dd_zero();
+#pragma unroll
+        for (int s = 0; s < SLOTS; ++s) dd_add(ss, pmv[s] * pmv[s]);
+        const double k = clamp_k(1.0 / sqrt(warp_dd_sum(ss)) * 1e2);  // arma::norm(P * M), :79
         const double scale = k / sqrt(dot3(M[0], M[1], M[2], M[0], M[1], M[2]));
         DD acc = dd_zero();
-        for (int s = 0; s < nslots; ++s) {
-            const double r = pm[s * 32 + lane] * scale;
-            dd_add(acc, sqrt(log1p_nonneg(r * r, tab)));
+        {
+            double rho[SLOTS];
+#pragma unroll
+            for (int s = 0; s < SLOTS; ++s) {
+                const double r = pmv[s] * scale;
+                rho[s] = sqrt(log1p_nonneg(r * r, tab));
+            }
+#pragma unroll
+            for (int s = 0; s < SLOTS; ++s) dd_add(acc, rho[s]);
         }
         const double cost = sqrt(warp_dd_sum(acc));
         if (lane == 0) framecost[(size_t)di * F + fi] = cost;
         // the panic conditions of :76-83: non-finite values propagate into the cost, so the stage
         // that produced them is only looked for when the cost (or a row) is not finite
         if (bad || !is_finite(cost)) {
-            bad |= presync_diagnose(pm, nslots, lane, scale, M, tab);
+            double* pm = reinterpret_cast<double*>(w.nf);
+#pragma unroll
+            for (int s = 0; s < SLOTS; ++s) pm[s * 32 + lane] = pmv[s];
+            __syncwarp();
+            bad |= presync_diagnose(pm, nslots, lane, scale, M[0], M[1], M[2], tab);
             bad = __reduce_or_sync(FULL, bad);
             if (bad && lane == 0) atomicOr(flags, bad);
         }
@@ -907,9 +1143,10 @@ __global__ void probe_guess_kernel(DeviceData dd, FrameDesc fd, double delay, in
     const int nslots = (fd.n + 31) >> 5;
     const unsigned bad = __reduce_or_sync(FULL, build_rows_smem<true>(dd, fd, delay, lane, w, NP));
     double M[3];
-    if (mode == 2)
-        warp_ransac_exact<SLOTS>(dd, fd, w, iters, rng_task_key(key_prefix, fd.id), lane, M);
-    else
+    if (mode == 2) {
+        const Vec3 e = warp_ransac_exact<SLOTS>(dd, fd, w, iters, rng_task_key(key_prefix, fd.id), lane);
+        M[0] = e.x; M[1] = e.y; M[2] = e.z;
+    } else
         warp_ransac<SLOTS>(dd, fd, w, iters, rng_task_key(key_prefix, fd.id), lane, bad == 0u, M,
                            n_exact);
     __syncwarp();
@@ -984,13 +1221,26 @@ void launch_presync_grid(const DeviceData& dd, const FrameDesc* d_frames, int F,
         return;
     }
     RS_DISPATCH_SLOTS(max_n, {
+        using Cfg = PresyncCfg<SL>;
         auto kern = presync_kernel<SL>;
-        const size_t smem = kLog1pTableBytes + (size_t)kWarpsPerBlock * warp_smem_bytes(SL * 32, true);
-        allow_smem(kern, smem);
-        const int grid = grid_for(kern, smem, (long long)F * D);
+        allow_smem(kern, Cfg::kSmem);
+        // chunks of delays per frame, balanced: cpf = ceil(D / W), chunk = ceil(D / cpf) <= W
+        const int cpf = (D + Cfg::kWarps - 1) / Cfg::kWarps;
+        const int chunk = (D + cpf - 1) / cpf;
+        static int sm_count = 0;
+        if (!sm_count) {
+            int dev = 0;
+            cudaGetDevice(&dev);
+            cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev);
+        }
+        int per_sm = 1;
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, Cfg::kWarps * 32, Cfg::kSmem);
+        const long long units = (long long)F * ((D + chunk - 1) / chunk);
+        const int grid = (int)std::max<long long>(1, std::min<long long>(units, (long long)sm_count * std::max(per_sm, 1)));
         if (ev_begin) cudaEventRecord(ev_begin, st);
-        kern<<<grid, kWarpsPerBlock * 32, smem, st>>>(dd, d_frames, F, d_delays, D, seed, stream,
-                                                      call_no, idx_base, d_framecost, d_flags);
+        kern<<<grid, Cfg::kWarps * 32, Cfg::kSmem, st>>>(dd, d_frames, F, d_delays, D, chunk,
+                                                         (D + chunk - 1) / chunk, seed, stream, call_no,
+                                                         idx_base, d_framecost, d_flags);
         if (ev_end) cudaEventRecord(ev_end, st);
     });
     reduce_rows_kernel<<<(D + 3) / 4, 128, 0, st>>>(d_framecost, D, F, d_costs);

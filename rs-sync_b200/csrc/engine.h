@@ -12,8 +12,9 @@ constexpr double kNumericDiffStep = 1e-6;  // FrameState::kNumericDiffStep, core
 // One tracked frame inside the device arena (FrameData, core_private.hpp:8-13).
 struct FrameDesc {
     int64_t id;   // caller's frame number (also an RNG key component)
-    int32_t off;  // index of the frame's first ray in every SoA plane (multiple of 32)
+    int32_t off;  // index of the frame's first ray in the arena (multiple of 32)
     int32_t n;    // rays in the frame
+    double ts_lo, ts_hi;  // smallest / largest of the frame's ts_a, ts_b (bounds the spline window)
 };
 
 // Read-only device state shared by all kernels (OptData, core_private.hpp:15-22).
@@ -21,8 +22,9 @@ struct DeviceData {
     const double* rec;  // gyro spline: nq records of {y[4], b[4], c[4], d[4]}
     int nq;
     double q0, sr;      // quats_start, sample_rate
-    // SoA ray planes: ts_a, ts_b, ra.x, ra.y, ra.z, rb.x, rb.y, rb.z
-    const double* plane[8];
+    // ray arena: one 2 KB tile [8 fields][32 rays] of doubles per group of 32 rays; fields ts_a,
+    // ts_b, ra.x, ra.y, ra.z, rb.x, rb.y, rb.z.  Ray i of the arena is rays[(i/32)*256 + f*32 + i%32].
+    const double* rays;
     const int32_t* orig;  // caller's index of each stored ray (rays are stored sorted by ts_a)
     const int32_t* pos;   // inverse of orig inside each frame: storage slot of caller's ray i
 };
