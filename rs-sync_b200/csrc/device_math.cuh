@@ -32,8 +32,9 @@ __device__ __forceinline__ void dd_merge(DD& a, const DD& b) {
     a.hi = s;
     a.lo = (a.lo + b.lo) + e;
 }
-// butterfly over the warp; every lane ends with the same (hi, lo)
-__device__ __forceinline__ double warp_dd_sum(DD a) {
+// butterfly over the warp; every lane ends with the same (hi, lo).  Out of line: one copy of the
+// 5-step butterfly instead of one per call site (instruction-cache footprint).
+__device__ __noinline__ double warp_dd_sum(DD a) {
 #pragma unroll
     for (int off = 16; off >= 1; off >>= 1) {
         DD b;
@@ -145,6 +146,12 @@ __device__ __forceinline__ void spline_eval4(const double* __restrict__ rec, int
     q[1] = fma(fma(fma(d01.y, h, c01.y), h, b01.y), h, y01.y);
     q[2] = fma(fma(fma(d23.x, h, c23.x), h, b23.x), h, y23.x);
     q[3] = fma(fma(fma(d23.y, h, c23.y), h, b23.y), h, y23.y);
+}
+
+__device__ __noinline__ Quat4 spline_eval4_cold(const double* __restrict__ rec, int n, double x) {
+    double q[4];
+    spline_eval4(rec, n, x, q);
+    return Quat4{q[0], q[1], q[2], q[3]};
 }
 
 // ---- de-rotation by the conjugate of an un-normalised quaternion (quat.cpp:33-47) ------------

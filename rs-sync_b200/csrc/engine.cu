@@ -124,6 +124,13 @@ __device__ __forceinline__ unsigned build_rows_smem(const DeviceData& dd, const 
     return (__float_as_uint(fin) & 0x7f800000u) == 0x7f800000u ? kFlagP : 0u;
 }
 
+// out-of-line copy for kernels whose hot path is the staged variant below
+__device__ __noinline__ unsigned build_rows_global_cold(const DeviceData& dd, const FrameDesc& fd,
+                                                        double delay, int lane, const WarpSmem& w,
+                                                        int NP) {
+    return build_rows_smem<true>(dd, fd, delay, lane, w, NP);
+}
+
 // ---- TMA bulk copies + mbarrier (PTX, sm_90+) --------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
     return (uint32_t)__cvta_generic_to_shared(p);
@@ -164,7 +171,8 @@ __device__ __forceinline__ void spline_eval4_staged(const DeviceData& dd, const 
     const int r = __double2int_rd(x);
     const unsigned at = (unsigned)(r - rec_first);
     if (at >= (unsigned)rec_cnt) {
-        spline_eval4(dd.rec, dd.nq, x, q);
+        const Quat4 e = spline_eval4_cold(dd.rec, dd.nq, x);
+        q[0] = e.w; q[1] = e.x; q[2] = e.y; q[3] = e.z;
         return;
     }
     const double h = x - (double)r;
@@ -807,7 +815,7 @@ struct StageCtl {
 };
 
 template <int SLOTS>
-__device__ __forceinline__ void presync_stage_unit(const DeviceData& dd, const FrameDesc* frames,
+__device__ __noinline__ void presync_stage_unit(const DeviceData& dd, const FrameDesc* frames,
                                                    const double* delays, int D, int chunk, int cpf,
                                                    int u, StageCtl* ctl, double* sTiles, double* sRec) {
     const int fi = u / cpf, d0 = (u % cpf) * chunk;
@@ -881,7 +889,7 @@ presync_kernel(DeviceData dd, const FrameDesc* __restrict__ frames, int F,
         if (active) {
             delay = delays[di];
             bad = rec_cnt ? build_rows_staged(dd, fd, delay, lane, w, NP, sTiles, sRec, rec_first, rec_cnt)
-                          : build_rows_smem<true>(dd, fd, delay, lane, w, NP);
+                          : build_rows_global_cold(dd, fd, delay, lane, w, NP);
             bad = __reduce_or_sync(FULL, bad);
         }
         __syncwarp();

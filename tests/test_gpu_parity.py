@@ -250,6 +250,34 @@ def test_ragged_and_sparse_frames(rsb, oracle_loader):
     assert rel_err(rg[1], ro[1]) <= TOL and rel_err(rg[0], ro[0]) <= TOL
 
 
+@pytest.mark.parametrize("rays", [33, 64, 130, 224, 300, 500, 512])
+def test_presync_ray_counts(rsb, oracle_loader, synth_mod, rays):
+    """every SLOTS instantiation of the grid kernel (2..16 slots of 32 rays), ragged last slot"""
+    w = synth_mod.make_workload("tiny", frames=6, rays=rays)
+    g = rsb.SyncProblem(seed=11).load(w, bulk=True)
+    o = oracle_loader.OracleProblem(threads=4, seed=11).load(w)
+    fb, fe = int(w.frame_ids[0]), int(w.frame_ids[-1]) + 1
+    delays = np.linspace(-0.03, 0.05, 23)
+    cg = g.presync_grid(fb, fe, delays, call_no=4)
+    co = o.presync_grid(fb, fe, delays, call_no=4)
+    assert rel_err(cg, co) <= TOL
+    assert int(np.argmin(cg)) == int(np.argmin(co))
+
+
+def test_presync_wide_delay_steps_use_global_path(rsb, oracle_loader, w_tiny):
+    """delays 50 ms apart: the chunk's spline window does not fit the staging buffer, so phase A
+    reads global memory; a 10 s offset leaves the gyro span entirely (spline edges)"""
+    w = w_tiny
+    g = rsb.SyncProblem(seed=5).load(w)
+    o = oracle_loader.OracleProblem(threads=2, seed=5).load(w)
+    fb, fe = int(w.frame_ids[0]), int(w.frame_ids[-1]) + 1
+    delays = np.concatenate([np.arange(-0.3, 0.31, 0.05), [-10.0, 10.0]])
+    cg, flags = g.presync_grid(fb, fe, delays, call_no=1, return_flags=True)
+    co = o.presync_grid(fb, fe, delays, call_no=1)
+    assert flags == 0
+    assert rel_err(cg, co) <= TOL
+
+
 def test_variable_rate_ingest_matches_oracle(rsb, oracle_loader, w_tiny):
     w = w_tiny
     rng = np.random.default_rng(3)
