@@ -8,8 +8,11 @@
 #include <algorithm>
 #include <atomic>
 #include <cmath>
+#include <condition_variable>
 #include <cstring>
+#include <functional>
 #include <map>
+#include <mutex>
 #include <string>
 #include <thread>
 #include <utility>
@@ -95,6 +98,15 @@ struct rssync_problem {
     double q0 = 0.0, sr = 0.0;
     size_t nq = 0;
     bool gyro_dirty = false;
+    // The spline coefficient solve (4 sequential recurrences, ~2.5 ms per minute of 1 kHz gyro) runs
+    // on a worker thread so that it overlaps the caller's SetTrackResult calls; it is joined by the
+    // first thing that needs the records.
+    std::thread gyro_worker;
+    std::vector<double> gyro_copy;
+    // eager host->device copies issued by the bulk track ingest; host writes to the pinned arena
+    // wait for them
+    cudaEvent_t ev_arena = nullptr;
+    bool arena_copy_pending = false;
     DevBuf<double> d_rec;
 
     // ray arena (DeviceData::rays): frames appended in arrival order, each padded to a multiple of
@@ -166,8 +178,20 @@ int d2h(rssync_problem* p, void* dst, const void* src, size_t bytes) {
     return RSSYNC_OK;
 }
 
+void join_gyro(rssync_problem* p) {
+    if (p->gyro_worker.joinable()) p->gyro_worker.join();
+}
+int wait_arena_copies(rssync_problem* p) {
+    if (p->arena_copy_pending) {
+        CUDA_TRY(p, cudaEventSynchronize(p->ev_arena));
+        p->arena_copy_pending = false;
+    }
+    return RSSYNC_OK;
+}
+
 int flush(rssync_problem* p) {
     CUDA_TRY(p, cudaSetDevice(p->device));
+    join_gyro(p);
     if (p->gyro_dirty) {
         CUDA_TRY(p, p->d_rec.reserve(p->nq * 16));
         if (int rc = h2d(p, p->d_rec.ptr, p->rec.ptr, p->nq * 16 * sizeof(double))) return rc;
@@ -452,6 +476,9 @@ int rssync_create(rssync_problem** out) {
 void rssync_destroy(rssync_problem* p) {
     if (!p) return;
     cudaSetDevice(p->device);
+    join_gyro(p);
+    if (p->arena_copy_pending) cudaEventSynchronize(p->ev_arena);
+    if (p->ev_arena) cudaEventDestroy(p->ev_arena);
     p->d_rec.release();
     p->rec.release();
     p->h_rays.release(); p->d_rays.release();
@@ -475,13 +502,18 @@ int rssync_set_gyro_fixed(rssync_problem* p, const double* quats, size_t count, 
     if (!p || !quats) return RSSYNC_E_INVALID;
     if (count < 2) { p->err = "set-gyro-quaternions: need at least 2 samples"; return RSSYNC_E_INVALID; }
     if (count > (size_t)INT32_MAX) { p->err = "set-gyro-quaternions: too many samples"; return RSSYNC_E_INVALID; }
+    join_gyro(p);
     p->sr = sample_rate;       // core_private.cpp:137
     p->q0 = first_timestamp;   // :138
     cudaSetDevice(p->device);
+    if (p->gyro_dirty == false && p->nq) CUDA_TRY(p, cudaStreamSynchronize(p->stream));  // records in flight
     CUDA_TRY(p, p->rec.reserve(count * 16));
-    rs::build_spline_records(quats, count, p->rec.ptr);  // :139
+    p->gyro_copy.assign(quats, quats + 4 * count);  // the caller's buffer is only borrowed
     p->nq = count;
     p->gyro_dirty = true;
+    double* rec = p->rec.ptr;
+    const double* src = p->gyro_copy.data();
+    p->gyro_worker = std::thread([=]() { rs::build_spline_records(src, count, rec); });  // :139
     return RSSYNC_OK;
 }
 
@@ -494,13 +526,19 @@ int rssync_set_gyro_var(rssync_problem* p, const int64_t* ts, const double* quat
     if (s == rs::IngestStatus::NonFinite) return RSSYNC_E_NONFINITE;
     if (s == rs::IngestStatus::OutOfOrder) return RSSYNC_E_ORDER;
     if (rq.size() / 4 > (size_t)INT32_MAX) { p->err = "set-gyro-quaternions: too many samples"; return RSSYNC_E_INVALID; }
+    join_gyro(p);
     p->sr = sr;
     p->q0 = q0;
     cudaSetDevice(p->device);
+    if (p->gyro_dirty == false && p->nq) CUDA_TRY(p, cudaStreamSynchronize(p->stream));
     CUDA_TRY(p, p->rec.reserve(rq.size() * 4));
-    rs::build_spline_records(rq.data(), rq.size() / 4, p->rec.ptr);  // :189
-    p->nq = rq.size() / 4;
+    p->gyro_copy.swap(rq);
+    const size_t n_out = p->gyro_copy.size() / 4;
+    p->nq = n_out;
     p->gyro_dirty = true;
+    double* rec = p->rec.ptr;
+    const double* src = p->gyro_copy.data();
+    p->gyro_worker = std::thread([=]() { rs::build_spline_records(src, n_out, rec); });  // :189
     return RSSYNC_OK;
 }
 
@@ -590,25 +628,83 @@ void fill_track(rssync_problem* p, FrameDesc* fd, const double* ts_a, const doub
     fd->ts_hi = hi;
 }
 
-template <class F>
-void parallel_frames(size_t n, F&& fn) {
-    unsigned hw = std::thread::hardware_concurrency();
-    size_t threads = std::min<size_t>(hw ? hw : 1, std::min<size_t>(16, n / 64 + 1));
-    if (threads <= 1) {
+// Persistent host worker pool for the bulk ingest (validation, sort + transpose).  Creating
+// std::threads per call costs ~30 us each, which is milliseconds per batch at 16 threads x several
+// parallel regions; the pool's threads sleep on a condition variable between regions.
+class WorkerPool {
+public:
+    static WorkerPool& get() {
+        static WorkerPool pool;
+        return pool;
+    }
+    size_t size() const { return threads_.size() + 1; }
+    // fn(i, t) for i in [0, n), t = worker index; blocks of 16 items are handed out dynamically
+    void run(size_t n, const std::function<void(size_t, size_t)>& fn) {
+        if (n == 0) return;
+        std::unique_lock<std::mutex> lk(m_);
+        fn_ = &fn;
+        n_ = n;
+        next_.store(0);
+        pending_ = threads_.size();
+        ++generation_;
+        cv_.notify_all();
+        lk.unlock();
+        work(0);
+        lk.lock();
+        done_.wait(lk, [&] { return pending_ == 0; });
+        fn_ = nullptr;
+    }
+
+private:
+    WorkerPool() {
+        unsigned hw = std::thread::hardware_concurrency();
+        const size_t n = std::min<size_t>(hw ? hw : 1, 16);
+        for (size_t t = 1; t < n; ++t)
+            threads_.emplace_back([this, t]() {
+                uint64_t seen = 0;
+                for (;;) {
+                    std::unique_lock<std::mutex> lk(m_);
+                    cv_.wait(lk, [&] { return generation_ != seen || stop_; });
+                    if (stop_) return;
+                    seen = generation_;
+                    lk.unlock();
+                    work(t);
+                    lk.lock();
+                    if (--pending_ == 0) done_.notify_one();
+                }
+            });
+    }
+    ~WorkerPool() {
+        {
+            std::lock_guard<std::mutex> lk(m_);
+            stop_ = true;
+        }
+        cv_.notify_all();
+        for (auto& th : threads_) th.join();
+    }
+    void work(size_t t) {
+        for (;;) {
+            const size_t lo = next_.fetch_add(16);
+            if (lo >= n_) break;
+            for (size_t i = lo; i < std::min(n_, lo + 16); ++i) (*fn_)(i, t);
+        }
+    }
+    std::vector<std::thread> threads_;
+    std::mutex m_;
+    std::condition_variable cv_, done_;
+    const std::function<void(size_t, size_t)>* fn_ = nullptr;
+    size_t n_ = 0, pending_ = 0;
+    std::atomic<size_t> next_{0};
+    uint64_t generation_ = 0;
+    bool stop_ = false;
+};
+
+void parallel_frames(size_t n, const std::function<void(size_t, size_t)>& fn) {
+    if (n < 64) {
         for (size_t i = 0; i < n; ++i) fn(i, 0);
         return;
     }
-    std::atomic<size_t> next{0};
-    std::vector<std::thread> pool;
-    for (size_t t = 0; t < threads; ++t)
-        pool.emplace_back([&, t]() {
-            for (;;) {
-                const size_t lo = next.fetch_add(32);
-                if (lo >= n) break;
-                for (size_t i = lo; i < std::min(n, lo + 32); ++i) fn(i, t);
-            }
-        });
-    for (auto& th : pool) th.join();
+    WorkerPool::get().run(n, fn);
 }
 
 }  // namespace
@@ -620,6 +716,7 @@ int rssync_set_track(rssync_problem* p, int64_t frame, const double* ts_a, const
     if (!p) return RSSYNC_E_INVALID;
     const char* msg = nullptr;
     if (int rc = validate_track(ts_a, ts_b, rays_a, rays_b, count, &msg)) { p->err = msg; return rc; }
+    if (int rc = wait_arena_copies(p)) return rc;
     FrameDesc* fd = nullptr;
     if (int rc = place_track(p, frame, count, &fd)) return rc;
     fill_track(p, fd, ts_a, ts_b, rays_a, rays_b, count, p->sort_scratch);
@@ -642,13 +739,56 @@ int rssync_set_track_batch(rssync_problem* p, size_t n_frames, const int64_t* fr
     size_t n_ok = n_frames;
     for (size_t i = 0; i < n_frames; ++i)
         if (rc[i]) { n_ok = i; break; }
+    if (int r = wait_arena_copies(p)) return r;
+    const size_t used0 = p->used, uploaded0 = p->uploaded;
+    const bool clean0 = p->uploaded == p->used && !p->rays_full_dirty;
     std::vector<FrameDesc*> fds(n_ok);
-    for (size_t i = 0; i < n_ok; ++i)
+    bool run = true;  // the batch occupies one contiguous run of the arena, in order
+    for (size_t i = 0; i < n_ok; ++i) {
         if (int r = place_track(p, frames[i], counts[i], &fds[i])) return r;
+        run = run && (i == 0 || (size_t)fds[i]->off == (size_t)fds[i - 1]->off + (counts[i - 1] + 31) / 32 * 32);
+    }
+    // Eager upload: when the batch is one contiguous run of the arena (an append, or the same
+    // frames set again in place) and nothing else is pending, the arena range of each chunk of
+    // frames is copied to the device as soon as the chunk is filled, so the copy of chunk k
+    // overlaps the sort/transpose of chunk k + 1.
+    bool eager = run && clean0 && n_ok >= 64 && (size_t)fds[0]->off <= uploaded0;
+    if (eager) {
+        cudaSetDevice(p->device);
+        p->rays_full_dirty = false;  // place_track flags in-place replacement; handled here
+        const bool regrow = p->d_rays.cap < p->used * 8 || p->d_orig.cap < p->used || p->d_pos.cap < p->used;
+        if (regrow && used0 > 0) {
+            p->rays_full_dirty = true;
+            eager = false;  // growing the device arena drops what is there: the lazy path re-uploads all
+        } else {
+            CUDA_TRY(p, p->d_rays.reserve(p->h_rays.cap));
+            CUDA_TRY(p, p->d_orig.reserve(p->h_orig.cap));
+            CUDA_TRY(p, p->d_pos.reserve(p->h_pos.cap));
+            if (!p->ev_arena) CUDA_TRY(p, cudaEventCreateWithFlags(&p->ev_arena, cudaEventDisableTiming));
+        }
+    }
     std::vector<std::vector<std::pair<double, int32_t>>> scratch(17);
-    parallel_frames(n_ok, [&](size_t i, size_t t) {
-        fill_track(p, fds[i], ts_a + at[i], ts_b + at[i], rays_a + 3 * at[i], rays_b + 3 * at[i], counts[i], scratch[t]);
-    });
+    const size_t n_chunks = eager ? 6 : 1;
+    for (size_t c = 0; c < n_chunks; ++c) {
+        const size_t lo = n_ok * c / n_chunks, hi = n_ok * (c + 1) / n_chunks;
+        if (lo == hi) continue;
+        parallel_frames(hi - lo, [&](size_t k, size_t t) {
+            const size_t i = lo + k;
+            fill_track(p, fds[i], ts_a + at[i], ts_b + at[i], rays_a + 3 * at[i], rays_b + 3 * at[i], counts[i], scratch[t]);
+        });
+        if (eager) {
+            const size_t a = (size_t)fds[lo]->off;
+            const size_t b = (hi < n_ok) ? (size_t)fds[hi]->off : p->used;
+            if (int r = h2d(p, p->d_rays.ptr + a * 8, p->h_rays.ptr + a * 8, (b - a) * 8 * sizeof(double))) return r;
+            if (int r = h2d(p, p->d_orig.ptr + a, p->h_orig.ptr + a, (b - a) * sizeof(int32_t))) return r;
+            if (int r = h2d(p, p->d_pos.ptr + a, p->h_pos.ptr + a, (b - a) * sizeof(int32_t))) return r;
+            p->uploaded = std::max(p->uploaded, b);
+        }
+    }
+    if (eager) {
+        CUDA_TRY(p, cudaEventRecord(p->ev_arena, p->stream));
+        p->arena_copy_pending = true;
+    }
     if (n_ok < n_frames) { p->err = msg[n_ok]; return rc[n_ok]; }
     return RSSYNC_OK;
 }
@@ -820,7 +960,10 @@ int rssync_probe_gyro(const rssync_problem* p, double* sample_rate, double* firs
     if (sample_rate) *sample_rate = p->sr;
     if (first_timestamp) *first_timestamp = p->q0;
     if (count) *count = p->nq;
-    if (rec) std::copy(p->rec.ptr, p->rec.ptr + p->nq * 16, rec);
+    if (rec) {
+        join_gyro(const_cast<rssync_problem*>(p));
+        std::copy(p->rec.ptr, p->rec.ptr + p->nq * 16, rec);
+    }
     return RSSYNC_OK;
 }
 
