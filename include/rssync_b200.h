@@ -106,6 +106,27 @@ int rssync_sync_batch_ex(rssync_problem* p, int n, const double* initial_delay,
  * two numbers the reference prints to stderr (core_private.cpp:330).  Returns entries written. */
 int rssync_last_sync_trace(const rssync_problem* p, double* delays, double* steps, int cap);
 
+/* The caller-side step before SetGyroQuaternions, optdata_fill_gyro (core_testcode.cpp:37-53):
+ * q_0 = identity, q_i = normalise(quat_from_aa(w_i (t_i - t_{i-1})) (x) q_{i-1}).  gyro_xyz: count x 3
+ * rad/s; timestamps in seconds; quats_out: count x 4 (w,x,y,z).  orientation: a gyro_orientation
+ * string of the reference's config (core_testcode.cpp:186-190) or NULL for "XYZ"; character i names
+ * the input axis routed to output axis i, lower case flips its sign.  (The reference delegates
+ * this mapping to the third-party telemetry-parser crate; the convention here is ours.)  Host code. */
+int rssync_integrate_gyro(const double* timestamps_s, const double* gyro_xyz, size_t count,
+                          const char* orientation, double* quats_out);
+/* The orientation search the reference keeps commented out in core_testcode.cpp:184-233 (README.md:
+ * 47-48, guess_orient): for each of n_orient gyro_orientation strings, integrate the raw gyro,
+ * ingest it through the variable-rate SetGyroQuaternions (timestamps truncated to integer
+ * microseconds, :47-50) and run PreSync(initial_delay, frame_begin, frame_end, step, radius).
+ * out_cost[i], out_delay[i] = the i-th PreSync result; sort by cost to rank the variants (:226).
+ * Equivalent to that sequence of calls on this problem, RNG call counter included; the problem
+ * is left holding the last variant's gyro. */
+int rssync_orientation_search(rssync_problem* p, const double* timestamps_s, const double* gyro_xyz,
+                              size_t count, const char* const* orientations, int n_orient,
+                              double initial_delay, int64_t frame_begin, int64_t frame_end,
+                              double search_step, double search_radius, double* out_cost,
+                              double* out_delay);
+
 /* Pinned RNG of the randomised translation estimator (replaces the reference's
  * random_device-seeded mt19937, inline_utils.hpp:13-17).  Default seed 100, call counter 0; the
  * counter advances by one per PreSync / DebugPreSync / Sync call. */

@@ -87,6 +87,7 @@ def lib():
     L.orc_lbfgs.argtypes = [C.c_void_p, C.c_int64, C.c_double, c_double_p, C.c_double, c_double_p,
                             C.POINTER(C.c_int), C.POINTER(C.c_int)]
     L.orc_log1p.argtypes = [c_double_p, C.c_int, c_double_p]
+    L.orc_integrate_gyro.argtypes = [c_double_p, c_double_p, C.c_size_t, C.c_char_p, c_double_p]
     L.orc_slerp.argtypes = [c_double_p, c_double_p, C.c_double, c_double_p]
     L.orc_rng_index.argtypes = [C.c_uint64, C.c_uint64, C.c_uint64, C.c_uint64, C.c_int64, C.c_uint32,
                                 C.c_uint32, C.c_uint32]
@@ -131,6 +132,15 @@ class OracleProblem:
     def set_rng(self, seed, call_no=0):
         self._seed = seed
         self.L.orc_set_rng(self.h, seed, call_no)
+
+    @property
+    def seed(self):
+        return self._seed
+
+    def call_counter(self):
+        self.L.orc_call_no.restype = C.c_uint64
+        self.L.orc_call_no.argtypes = [C.c_void_p]
+        return int(self.L.orc_call_no(self.h))
 
     def set_threads(self, n):
         self.L.orc_set_threads(self.h, n)
@@ -278,6 +288,30 @@ class OracleProblem:
         out = np.empty((x.shape[0], 4))
         self.L.orc_spline_eval(self.h, _dp(x), x.shape[0], _dp(out))
         return out
+
+
+def integrate_gyro(timestamps_s, gyro_xyz, orientation=None):
+    """optdata_fill_gyro (core_testcode.cpp:37-53): raw gyro -> orientation quaternions"""
+    ts = np.ascontiguousarray(timestamps_s, dtype=np.float64)
+    g = np.ascontiguousarray(gyro_xyz, dtype=np.float64)
+    out = np.empty((ts.shape[0], 4))
+    rc = lib().orc_integrate_gyro(_dp(ts), _dp(g), ts.shape[0], orientation.encode() if orientation else None, _dp(out))
+    if rc:
+        raise OracleError(rc, "malformed orientation")
+    return out
+
+
+def orientation_search(problem, timestamps_s, gyro_xyz, orientations, initial, fb, fe, step, radius):
+    """the loop of core_testcode.cpp:212-224 on an OracleProblem: per variant integrate, ingest through
+    the variable-rate SetGyroQuaternions (timestamps truncated to integer microseconds), PreSync"""
+    ts = np.ascontiguousarray(timestamps_s, dtype=np.float64)
+    ts_us = (ts * 1000000).astype(np.int64)  # :47-50 (truncation)
+    out = []
+    for o in orientations:
+        q = integrate_gyro(ts, gyro_xyz, o)
+        problem.SetGyroQuaternions(ts_us, q, len(ts_us))
+        out.append(problem.PreSync(initial, fb, fe, step, radius))
+    return np.array([c for c, _ in out]), np.array([d for _, d in out])
 
 
 def presync_delays(initial, step, radius):

@@ -783,6 +783,51 @@ int orc_lbfgs(void* h, int64_t frame, double delay, double* m, double k, double*
     if (evals) *evals = st.evals;
     return OK;
 }
+// optdata_fill_gyro, core_testcode.cpp:37-53 (the caller-side gyro integration), with the
+// gyro_orientation axis mapping of the product documented in include/rssync_b200.h
+int orc_integrate_gyro(const double* ts, const double* gyro, size_t count, const char* orient, double* out) {
+    int src[3] = {0, 1, 2};
+    double sgn[3] = {1, 1, 1};
+    if (orient) {
+        if (std::string(orient).size() != 3) return 1;
+        for (int i = 0; i < 3; ++i) {
+            const char c = orient[i];
+            const std::string axes = "xyzXYZ";
+            const size_t at = axes.find(c);
+            if (at == std::string::npos) return 1;
+            src[i] = (int)(at % 3);
+            sgn[i] = at < 3 ? -1.0 : 1.0;
+        }
+    }
+    double q[4] = {1, 0, 0, 0};
+    for (size_t i = 0; i < count; ++i) {
+        if (i > 0) {
+            const double dt = ts[i] - ts[i - 1];                            // :44
+            double aa[3];
+            for (int c = 0; c < 3; ++c) aa[c] = sgn[c] * gyro[3 * i + src[c]] * dt;
+            const double theta_squared = (aa[0] * aa[0] + aa[1] * aa[1]) + aa[2] * aa[2];  // quat.cpp:6
+            double d[4];
+            if (theta_squared > 0.) {                                        // quat.cpp:8-12
+                const double theta = std::sqrt(theta_squared);
+                const double half_theta = theta * 0.5;
+                const double k = std::sin(half_theta) / theta;
+                d[0] = std::cos(half_theta); d[1] = aa[0] * k; d[2] = aa[1] * k; d[3] = aa[2] * k;
+            } else {                                                         // quat.cpp:13-16
+                d[0] = 1.; d[1] = aa[0] * 0.5; d[2] = aa[1] * 0.5; d[3] = aa[2] * 0.5;
+            }
+            const double p0 = d[0], p1 = d[1], p2 = d[2], p3 = d[3];
+            const double r0 = p0 * q[0] - p1 * q[1] - p2 * q[2] - p3 * q[3];  // quat.cpp:34-37
+            const double r1 = p0 * q[1] + p1 * q[0] + p2 * q[3] - p3 * q[2];
+            const double r2 = p0 * q[2] - p1 * q[3] + p2 * q[0] + p3 * q[1];
+            const double r3 = p0 * q[3] + p1 * q[2] - p2 * q[1] + p3 * q[0];
+            const double nrm = std::sqrt(r0 * r0 + r1 * r1 + r2 * r2 + r3 * r3);
+            q[0] = r0 / nrm; q[1] = r1 / nrm; q[2] = r2 / nrm; q[3] = r3 / nrm;  // :45
+        }
+        for (int c = 0; c < 4; ++c) out[4 * i + c] = q[c];
+    }
+    return 0;
+}
+
 void orc_log1p(const double* x, int n, double* out) {
     for (int i = 0; i < n; ++i) out[i] = log1p_nonneg(x[i]);
 }

@@ -34,7 +34,8 @@ C_ABI_SYMBOLS = [
     "rssync_flush", "rssync_get_stats", "rssync_measure_fp64_peak", "rssync_probe_gyro",
     "rssync_probe_problem_matrix", "rssync_probe_guess_motion", "rssync_probe_loss",
     "rssync_probe_lbfgs", "rssync_probe_log1p", "rssync_set_track_batch", "rssync_set_kernel_timing",
-    "rssync_sync_batch_ex", "rssync_probe_guess_motion_ex",
+    "rssync_sync_batch_ex", "rssync_probe_guess_motion_ex", "rssync_integrate_gyro",
+    "rssync_orientation_search",
 ]
 # Itanium-ABI symbols of the C++ drop-in face (same set the reference's librssync_core exports)
 CXX_ABI_SYMBOLS = [
@@ -111,6 +112,10 @@ def load_library():
     L.rssync_probe_lbfgs.argtypes = [P, C.c_int64, C.c_double, c_double_p, C.c_double, c_double_p,
                                      C.POINTER(C.c_int), C.POINTER(C.c_int)]
     L.rssync_probe_log1p.argtypes = [c_double_p, C.c_int, c_double_p]
+    L.rssync_integrate_gyro.argtypes = [c_double_p, c_double_p, C.c_size_t, C.c_char_p, c_double_p]
+    L.rssync_orientation_search.argtypes = [P, c_double_p, c_double_p, C.c_size_t, C.POINTER(C.c_char_p),
+                                            C.c_int, C.c_double, C.c_int64, C.c_int64, C.c_double,
+                                            C.c_double, c_double_p, c_double_p]
     _lib = L
     return L
 
@@ -129,6 +134,18 @@ def presync_delays(initial_delay, search_step, search_radius):
     n = L.rssync_presync_delays(initial_delay, search_step, search_radius, None, 0)
     out = np.empty(n)
     L.rssync_presync_delays(initial_delay, search_step, search_radius, _dp(out), n)
+    return out
+
+
+def integrate_gyro(timestamps_s, gyro_xyz, orientation=None):
+    """optdata_fill_gyro (core_testcode.cpp:37-53): raw gyro (count x 3 rad/s) -> quaternions (count x 4)."""
+    ts = _f64(timestamps_s)
+    g = _f64(gyro_xyz)
+    out = np.empty((ts.shape[0], 4))
+    rc = load_library().rssync_integrate_gyro(_dp(ts), _dp(g), ts.shape[0],
+                                              orientation.encode() if orientation else None, _dp(out))
+    if rc:
+        raise RsSyncError(rc, f"malformed gyro_orientation {orientation!r}")
     return out
 
 
@@ -164,6 +181,7 @@ class SyncProblem:
             msg = self.L.rssync_last_error(self.h).decode() if self.h else "no usable CUDA device (no CPU fallback)"
             raise RsSyncError(rc, msg)
         self.L.rssync_set_rng(self.h, seed, 0)
+        self.seed = seed
 
     def close(self):
         if getattr(self, "h", None):
@@ -240,11 +258,25 @@ class SyncProblem:
             self.SetTrackResult(int(fid), w.ts_a[i], w.ts_b[i], w.rays_a[i], w.rays_b[i], n)
         return self
 
+    def orientation_search(self, timestamps_s, gyro_xyz, orientations, initial_delay, frame_begin, frame_end,
+                           search_step, search_radius):
+        """core_testcode.cpp:184-233: PreSync under every gyro_orientation variant.  Returns (costs, delays)."""
+        ts = _f64(timestamps_s)
+        g = _f64(gyro_xyz)
+        n = len(orientations)
+        arr = (C.c_char_p * n)(*[o.encode() for o in orientations])
+        costs, delays = np.empty(n), np.empty(n)
+        self._check(self.L.rssync_orientation_search(self.h, _dp(ts), _dp(g), ts.shape[0], arr, n, initial_delay,
+                                                     frame_begin, frame_end, search_step, search_radius,
+                                                     _dp(costs), _dp(delays)))
+        return costs, delays
+
     def set_kernel_timing(self, enabled=True):
         self._check(self.L.rssync_set_kernel_timing(self.h, 1 if enabled else 0))
 
     def set_rng(self, seed, call_no=0):
         self._check(self.L.rssync_set_rng(self.h, seed, call_no))
+        self.seed = seed
 
     def call_counter(self):
         return self.L.rssync_call_counter(self.h)

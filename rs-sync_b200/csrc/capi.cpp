@@ -639,11 +639,12 @@ public:
     }
     size_t size() const { return threads_.size() + 1; }
     // fn(i, t) for i in [0, n), t = worker index; blocks of 16 items are handed out dynamically
-    void run(size_t n, const std::function<void(size_t, size_t)>& fn) {
+    void run(size_t n, const std::function<void(size_t, size_t)>& fn, size_t grain = 16) {
         if (n == 0) return;
         std::unique_lock<std::mutex> lk(m_);
         fn_ = &fn;
         n_ = n;
+        grain_ = grain ? grain : 1;
         next_.store(0);
         pending_ = threads_.size();
         ++generation_;
@@ -684,16 +685,16 @@ private:
     }
     void work(size_t t) {
         for (;;) {
-            const size_t lo = next_.fetch_add(16);
+            const size_t lo = next_.fetch_add(grain_);
             if (lo >= n_) break;
-            for (size_t i = lo; i < std::min(n_, lo + 16); ++i) (*fn_)(i, t);
+            for (size_t i = lo; i < std::min(n_, lo + grain_); ++i) (*fn_)(i, t);
         }
     }
     std::vector<std::thread> threads_;
     std::mutex m_;
     std::condition_variable cv_, done_;
     const std::function<void(size_t, size_t)>* fn_ = nullptr;
-    size_t n_ = 0, pending_ = 0;
+    size_t n_ = 0, pending_ = 0, grain_ = 16;
     std::atomic<size_t> next_{0};
     uint64_t generation_ = 0;
     bool stop_ = false;
@@ -862,6 +863,78 @@ int rssync_presync_grid(rssync_problem* p, int64_t fb, int64_t fe, const double*
                         unsigned* nonfinite_flags) {
     if (!p || (n > 0 && (!delays || !costs))) return RSSYNC_E_INVALID;
     return presync_grid_impl(p, fb, fe, delays, n, (uint64_t)stream, call_no, idx_base, costs, nonfinite_flags);
+}
+
+int rssync_integrate_gyro(const double* timestamps_s, const double* gyro_xyz, size_t count,
+                          const char* orientation, double* quats_out) {
+    if (count && (!timestamps_s || !gyro_xyz || !quats_out)) return RSSYNC_E_INVALID;
+    return rs::integrate_gyro(timestamps_s, gyro_xyz, count, orientation, quats_out) ? RSSYNC_OK
+                                                                                      : RSSYNC_E_INVALID;
+}
+
+// The orientation search of core_testcode.cpp:184-233: for every gyro_orientation variant, integrate
+// the raw gyro (optdata_fill_gyro, :37-53), ingest it through the variable-rate SetGyroQuaternions
+// and run PreSync over the frame range.  The per-variant host work (integration, resampling,
+// spline solve) is spread over the worker pool; the 48 loss grids run back to back on the device.
+int rssync_orientation_search(rssync_problem* p, const double* timestamps_s, const double* gyro_xyz,
+                              size_t count, const char* const* orientations, int n_orient,
+                              double initial_delay, int64_t fb, int64_t fe, double step, double radius,
+                              double* out_cost, double* out_delay) {
+    if (!p || n_orient < 0) return RSSYNC_E_INVALID;
+    if (n_orient == 0) return RSSYNC_OK;
+    if (!timestamps_s || !gyro_xyz || !orientations || !out_cost || !out_delay) return RSSYNC_E_INVALID;
+    struct Prep {
+        std::vector<double> rec;
+        double sr = 0, q0 = 0;
+        size_t nq = 0;
+        int rc = RSSYNC_OK;
+        std::string err;
+    };
+    std::vector<Prep> prep((size_t)n_orient);
+    std::vector<int64_t> ts_us(count);
+    for (size_t i = 0; i < count; ++i) ts_us[i] = (int64_t)(timestamps_s[i] * 1000000);  // :47-50
+    auto prepare = [&](size_t k, size_t) {
+        Prep& pr = prep[k];
+        std::vector<double> quats(count * 4), rq;
+        if (!rs::integrate_gyro(timestamps_s, gyro_xyz, count, orientations[k], quats.data())) {
+            pr.rc = RSSYNC_E_INVALID;
+            pr.err = std::string("orientation-search: malformed gyro_orientation '") +
+                     (orientations[k] ? orientations[k] : "(null)") + "'";
+            return;
+        }
+        rs::IngestStatus st = rs::resample_variable_rate(ts_us.data(), quats.data(), count, rq, pr.sr, pr.q0, pr.err);
+        if (st != rs::IngestStatus::Ok) {
+            pr.rc = st == rs::IngestStatus::NonFinite ? RSSYNC_E_NONFINITE
+                    : st == rs::IngestStatus::OutOfOrder ? RSSYNC_E_ORDER : RSSYNC_E_INVALID;
+            return;
+        }
+        pr.nq = rq.size() / 4;
+        pr.rec.resize(pr.nq * 16);
+        rs::build_spline_records(rq.data(), pr.nq, pr.rec.data(), false);
+    };
+    if (n_orient >= 4) {
+        std::function<void(size_t, size_t)> fn = prepare;
+        WorkerPool::get().run((size_t)n_orient, fn, 1);
+    } else {
+        for (int k = 0; k < n_orient; ++k) prepare((size_t)k, 0);
+    }
+    for (int k = 0; k < n_orient; ++k) {
+        Prep& pr = prep[(size_t)k];
+        if (pr.rc) { p->err = pr.err; return pr.rc; }
+        if (pr.nq > (size_t)INT32_MAX) { p->err = "set-gyro-quaternions: too many samples"; return RSSYNC_E_INVALID; }
+        join_gyro(p);
+        cudaSetDevice(p->device);
+        if (p->gyro_dirty == false && p->nq) CUDA_TRY(p, cudaStreamSynchronize(p->stream));
+        CUDA_TRY(p, p->rec.reserve(pr.rec.size()));
+        std::memcpy(p->rec.ptr, pr.rec.data(), pr.rec.size() * sizeof(double));
+        p->sr = pr.sr;
+        p->q0 = pr.q0;
+        p->nq = pr.nq;
+        p->gyro_dirty = true;
+        std::vector<double>().swap(pr.rec);
+        if (int rc = rssync_presync(p, initial_delay, fb, fe, step, radius, &out_cost[k], &out_delay[k])) return rc;
+    }
+    return RSSYNC_OK;
 }
 
 int rssync_sync(rssync_problem* p, double initial, int64_t fb, int64_t fe, double center,

@@ -93,13 +93,62 @@ void slerp4(const double* p, const double* q_in, double t, double* out) {
 
 }  // namespace
 
-void build_spline_records(const double* quats, size_t n, double* rec) {
+void build_spline_records(const double* quats, size_t n, double* rec, bool one_thread_per_component) {
+    if (!one_thread_per_component) {
+        for (int comp = 0; comp < 4; ++comp) solve_component(quats + comp, n, 4, comp, rec);
+        return;
+    }
     // the four components are independent sequential solves: one host thread each
     std::thread th[3];
     for (int comp = 1; comp < 4; ++comp)
         th[comp - 1] = std::thread([=]() { solve_component(quats + comp, n, 4, comp, rec); });
     solve_component(quats, n, 4, 0, rec);
     for (auto& t : th) t.join();
+}
+
+bool integrate_gyro(const double* ts, const double* gyro, size_t count, const char* orient,
+                    double* out) {
+    int src[3] = {0, 1, 2};
+    double sgn[3] = {1.0, 1.0, 1.0};
+    if (orient) {
+        for (int i = 0; i < 3; ++i) {
+            const char ch = orient[i];
+            const char lo = (char)(ch | 0x20);
+            if (lo < 'x' || lo > 'z') return false;
+            src[i] = lo - 'x';
+            sgn[i] = (ch == lo) ? -1.0 : 1.0;
+        }
+        if (orient[3] != 0) return false;
+    }
+    if (count == 0) return true;
+    double q[4] = {1.0, 0.0, 0.0, 0.0};
+    out[0] = 1.0; out[1] = 0.0; out[2] = 0.0; out[3] = 0.0;
+    for (size_t i = 1; i < count; ++i) {
+        const double dt = ts[i] - ts[i - 1];
+        const double a0 = sgn[0] * gyro[3 * i + src[0]] * dt, a1 = sgn[1] * gyro[3 * i + src[1]] * dt,
+                     a2 = sgn[2] * gyro[3 * i + src[2]] * dt;
+        // quat_from_aa, quat.cpp:5-17
+        const double th2 = (a0 * a0 + a1 * a1) + a2 * a2;
+        double d[4];
+        if (th2 > 0.) {
+            const double th = std::sqrt(th2), half = th * 0.5, k = std::sin(half) / th;
+            d[0] = std::cos(half); d[1] = a0 * k; d[2] = a1 * k; d[3] = a2 * k;
+        } else {
+            d[0] = 1.; d[1] = a0 * 0.5; d[2] = a1 * 0.5; d[3] = a2 * 0.5;
+        }
+        // quat_prod(d, q), quat.cpp:33-38, then arma::normalise
+        double r[4];
+        r[0] = ((d[0] * q[0] - d[1] * q[1]) - d[2] * q[2]) - d[3] * q[3];
+        r[1] = ((d[0] * q[1] + d[1] * q[0]) + d[2] * q[3]) - d[3] * q[2];
+        r[2] = ((d[0] * q[2] - d[1] * q[3]) + d[2] * q[0]) + d[3] * q[1];
+        r[3] = ((d[0] * q[3] + d[1] * q[2]) - d[2] * q[1]) + d[3] * q[0];
+        const double nrm = std::sqrt(((r[0] * r[0] + r[1] * r[1]) + r[2] * r[2]) + r[3] * r[3]);
+        for (int c = 0; c < 4; ++c) {
+            q[c] = r[c] / nrm;
+            out[4 * i + c] = q[c];
+        }
+    }
+    return true;
 }
 
 // SyncProblemPrivate::SetGyroQuaternions(const int64_t*, const double*, size_t),

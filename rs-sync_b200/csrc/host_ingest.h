@@ -11,12 +11,21 @@ enum class IngestStatus { Ok = 0, Invalid = 1, NonFinite = 2, OutOfOrder = 3 };
 
 // ndspline::make (ndspline.cpp:13-19): n quaternions (w,x,y,z) -> n records of 16 doubles
 // {y[4], b[4], c[4], d[4]}.
-void build_spline_records(const double* quats, size_t n, double* rec /* n * 16 doubles */);
+void build_spline_records(const double* quats, size_t n, double* rec /* n * 16 doubles */,
+                          bool one_thread_per_component = true);
 
 // variable-rate SetGyroQuaternions (core_private.cpp:142-190): resample onto the uniform
 // integer-microsecond grid by slerp.
 IngestStatus resample_variable_rate(const int64_t* ts_us, const double* quats, size_t count,
                                     std::vector<double>& out_quats, double& sample_rate,
                                     double& first_timestamp, std::string& err);
+
+// optdata_fill_gyro (core_testcode.cpp:37-53), the step before SetGyroQuaternions: q_0 = identity,
+// q_i = normalise(quat_from_aa(w_i (t_i - t_{i-1})) (x) q_{i-1}) (quat.cpp:5-17, 33-38).  `orient`
+// is a 3-character gyro_orientation string (core_testcode.cpp:186-190) or null for "XYZ":
+// character i names the input axis routed to output axis i, lower case flips its sign.
+// Returns false for a malformed orientation string.
+bool integrate_gyro(const double* timestamps_s, const double* gyro_xyz, size_t count,
+                    const char* orient, double* quats_out /* count * 4 */);
 
 }  // namespace rs

@@ -93,3 +93,28 @@ def sync_sharded(problem, initial_delay, frame_begin, frame_end, search_center, 
     outc[order] = allc
     outd[order] = alld
     return outc, outd
+
+
+def orientation_search_sharded(problem, search_fn, orientations, *, seed, call_no_base=0, rank=0, world=1,
+                               device="cpu"):
+    """The 48-variant orientation search (core_testcode.cpp:184-233) with variant k on rank k % world.
+    `search_fn(problem, [orientation])` runs one variant (integrate, ingest, PreSync) and returns
+    ([cost], [delay]); the RNG call number of variant k is call_no_base + k on every rank, so the
+    gathered result equals the single-process loop.  Every rank returns all (cost, delay) pairs."""
+    n = len(orientations)
+    mine = list(range(rank, n, world))
+    cost, delay = np.empty(len(mine)), np.empty(len(mine))
+    for j, k in enumerate(mine):
+        problem.set_rng(seed, call_no_base + k)
+        c, d = search_fn(problem, [orientations[k]])
+        cost[j], delay[j] = c[0], d[0]
+    if world == 1:
+        return cost, delay
+    import torch.distributed as dist
+    allc = _gather_variable(cost, world, device, dist)
+    alld = _gather_variable(delay, world, device, dist)
+    order = np.concatenate([np.arange(r, n, world) for r in range(world)])
+    outc, outd = np.empty(n), np.empty(n)
+    outc[order] = allc
+    outd[order] = alld
+    return outc, outd

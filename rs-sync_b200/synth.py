@@ -192,8 +192,11 @@ class Workload:
 
     def syncpoints(self):
         """`auto` syncpoint list, core_testcode.cpp:270-273."""
-        f0, f1 = int(self.frame_ids[0]), int(self.frame_ids[-1]) + 1
+        f0, f1 = self.meta.get("span", (int(self.frame_ids[0]), int(self.frame_ids[-1]) + 1))
         return list(range(f0, f1 - self.sync_window, self.syncpoint_distance))
+
+    def true_delay_at(self, frame):
+        return float(self.true_delay[int(np.searchsorted(self.frame_ids, frame))])
 
     def gyro_timestamps_us(self):
         return np.round((self.gyro_t0 + np.arange(self.quats.shape[0]) / self.gyro_rate) * 1e6).astype(np.int64)
@@ -218,12 +221,17 @@ def camera_centre(t):
 
 def make_workload(name="C1", *, frames=None, rays=None, first_frame=None, seed=1, fps=60.0,
                   gyro_rate=1000.0, radius=None, step=None, true_delay=0.037, drift=None,
-                  noise_px=0.3, outlier_frac=0.10, sync_window=60, syncpoint_distance=120):
+                  noise_px=0.3, outlier_frac=0.10, sync_window=60, syncpoint_distance=120,
+                  windows_only=None):
     presets = {
         "C1": dict(frames=300, rays=100, first_frame=0, radius=0.2, step=0.002),
         "C2": dict(frames=3300, rays=200, first_frame=3900, radius=0.2, step=0.002),
         "C3": dict(frames=10000, rays=500, first_frame=0, radius=1.0, step=0.001),
         "C4": dict(frames=108000, rays=200, first_frame=0, radius=0.2, step=0.002),
+        # C4 as the syncpoint loop sees it: a 30-minute 60 fps trace, a syncpoint every 1000 frames
+        # (107 of them), only the frames inside the sync windows tracked (README.md:66: frames may
+        # be skipped), delay drifting -45 -> -40 ms
+        "C4s": dict(frames=108000, rays=200, first_frame=0, radius=0.2, step=0.002),
         "tiny": dict(frames=12, rays=40, first_frame=5, radius=0.05, step=0.005),
         "small": dict(frames=64, rays=100, first_frame=100, radius=0.1, step=0.002),
     }
@@ -233,8 +241,11 @@ def make_workload(name="C1", *, frames=None, rays=None, first_frame=None, seed=1
     if first_frame is not None: p["first_frame"] = first_frame
     if radius is not None: p["radius"] = radius
     if step is not None: p["step"] = step
-    if name == "C4" and drift is None:
+    if name in ("C4", "C4s") and drift is None:
         drift = (-0.045, -0.040)  # linear drift, thesis Fig. 8
+    if name == "C4s":
+        syncpoint_distance = 1000 if syncpoint_distance == 120 else syncpoint_distance
+        windows_only = True if windows_only is None else windows_only
     F, N, f0 = p["frames"], p["rays"], p["first_frame"]
 
     frame_ids = np.arange(f0, f0 + F, dtype=np.int64)
@@ -244,6 +255,13 @@ def make_workload(name="C1", *, frames=None, rays=None, first_frame=None, seed=1
         dtrue = np.linspace(drift[0], drift[1], F)
     else:
         dtrue = np.full(F, float(true_delay))
+    span_frames = F
+    if windows_only:  # keep the frames pos .. pos + sync_window of every `auto` syncpoint
+        keep = np.zeros(F, dtype=bool)
+        for pos in range(0, F - sync_window, syncpoint_distance):
+            keep[pos:pos + sync_window + 1] = True
+        frame_ids, dtrue = frame_ids[keep], dtrue[keep]
+        F = int(frame_ids.shape[0])
     pad = p["radius"] + 1.0 + float(np.max(np.abs(dtrue)))
     g0 = np.floor((t_first - pad) * gyro_rate) / gyro_rate
     ng = int(np.ceil((t_last + 1.0 / fps + pad - g0) * gyro_rate)) + 1
@@ -296,7 +314,8 @@ def make_workload(name="C1", *, frames=None, rays=None, first_frame=None, seed=1
                     rays_b=np.ascontiguousarray(rays_b), true_delay=dtrue,
                     presync_radius=p["radius"], presync_step=p["step"], sync_window=sync_window,
                     syncpoint_distance=syncpoint_distance,
-                    meta=dict(seed=seed, noise_px=noise_px, outlier_frac=outlier_frac))
+                    meta=dict(seed=seed, noise_px=noise_px, outlier_frac=outlier_frac,
+                              span=(int(f0), int(f0 + span_frames))))
 
 
 # the 48 axis permutation / sign variants of core_testcode.cpp:186-190.  Our mapping (the

@@ -278,6 +278,48 @@ def test_presync_wide_delay_steps_use_global_path(rsb, oracle_loader, w_tiny):
     assert rel_err(cg, co) <= TOL
 
 
+def test_orientation_search_matches_oracle(rsb, oracle_loader, synth_mod):
+    """core_testcode.cpp:184-233: PreSync under gyro_orientation variants; the true one wins"""
+    w = workload("tiny", first_frame=200)  # non-negative microsecond timestamps (SURVEY a3)
+    ts = w.gyro_t0 + np.arange(w.quats.shape[0]) / w.gyro_rate
+    orients = ["yXz", "XYZ", "ZXY", "xyz", "XZy", "Yxz"]
+    g = rsb.SyncProblem(seed=9).load(w)
+    o = oracle_loader.OracleProblem(threads=2, seed=9).load(w)
+    fb, fe = int(w.frame_ids[0]), int(w.frame_ids[-1]) + 1
+    g.set_rng(9, 3)
+    o.set_rng(9, 3)
+    cg, dg = g.orientation_search(ts, w.omega, orients, 0.0, fb, fe, 0.005, 0.05)
+    co, do = oracle_loader.orientation_search(o, ts, w.omega, orients, 0.0, fb, fe, 0.005, 0.05)
+    assert np.array_equal(dg, do)
+    assert rel_err(cg, co) <= TOL
+    assert int(np.argmin(cg)) == 1
+    assert g.call_counter() == 3 + len(orients)
+    with pytest.raises(rsb.RsSyncError):
+        g.orientation_search(ts, w.omega, ["XYZ", "XQZ"], 0.0, fb, fe, 0.005, 0.05)
+
+
+def test_syncpoint_driver_matches_oracle(rsb, oracle_loader, w_small, tmp_path):
+    """core_testcode's syncpoint loop (PreSync + 4 x Sync per syncpoint): the engine's batched,
+    lock-step execution against the oracle issuing the reference's sequential calls"""
+    import importlib
+    driver = importlib.import_module("rs-sync_b200.driver")
+    w = w_small
+    cfg = driver.default_config(w, csv_path=str(tmp_path / "gpu.csv"))
+    cfg["params"].update(sync_window=20, syncpoint_distance=20)
+    cfg["input"].update(simple_presync_radius=60.0, simple_presync_step=4.0)
+    g = rsb.SyncProblem(seed=100).load(w, bulk=True)
+    o = oracle_loader.OracleProblem(threads=8, seed=100).load(w)
+    rg = driver.run(g, cfg, mode="batched", debug_csv=str(tmp_path / "dbg.csv"), presync_delays=rsb.presync_delays)
+    ro = driver.run(o, cfg, mode="sequential", debug_csv=None)
+    assert len(rg["syncpoints"]) == 3
+    assert rel_err(rg["delay_ms"], ro["delay_ms"]) <= TOL
+    assert rel_err(rg["cost"], ro["cost"]) <= TOL
+    assert g.call_counter() == o.call_counter() + 0
+    g2 = rsb.SyncProblem(seed=100).load(w, bulk=True)
+    rs_ = driver.run(g2, cfg, mode="sequential", debug_csv=None)
+    assert np.array_equal(rs_["delay_ms"], rg["delay_ms"])
+
+
 def test_variable_rate_ingest_matches_oracle(rsb, oracle_loader, w_tiny):
     w = w_tiny
     rng = np.random.default_rng(3)

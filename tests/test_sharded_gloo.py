@@ -29,8 +29,16 @@ def _worker(rank, world, port, q):
     ini = np.array([0.030, 0.034, 0.036])
     fbs = np.array([fb, fb + 2, fb + 4])
     c, d = sharded.sync_sharded(o, ini, fbs, fbs + 6, 0.0, 0.2, call_no_base=20, rank=rank, world=world)
+    # orientation search, variant k on rank k % world
+    # (a later first frame: the variable-rate ingest needs non-negative microsecond timestamps)
+    w2 = synth.make_workload("tiny", first_frame=200)
+    ts = w2.gyro_t0 + np.arange(w2.quats.shape[0]) / w2.gyro_rate
+    o2 = loader.OracleProblem(threads=1, seed=100).load(w2)
+    oc, od = sharded.orientation_search_sharded(
+        o2, lambda pr, ors: loader.orientation_search(pr, ts, w2.omega, ors, 0.0, 200, 212, 0.01, 0.05),
+        ["XYZ", "yXz", "ZXY"], seed=100, call_no_base=7, rank=rank, world=world)
     if rank == 0:
-        q.put((curve, best, c, d))
+        q.put((curve, best, c, d, oc, od))
     dist.barrier()
     dist.destroy_process_group()
 
@@ -42,7 +50,7 @@ def test_offset_and_syncpoint_sharding_world2(oracle_loader):
     procs = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
     for p in procs:
         p.start()
-    curve, best, c, d = q.get(timeout=240)
+    curve, best, c, d, oc, od = q.get(timeout=120)
     for p in procs:
         p.join(timeout=60)
         assert p.exitcode == 0
@@ -58,6 +66,14 @@ def test_offset_and_syncpoint_sharding_world2(oracle_loader):
     o.set_rng(100, 20)
     seq = [o.Sync(x, fb + 2 * i, fb + 2 * i + 6, 0.0, 0.2) for i, x in enumerate((0.030, 0.034, 0.036))]
     assert np.array_equal(c, [s[0] for s in seq]) and np.array_equal(d, [s[1] for s in seq])
+    # orientation search: equals the single-process loop (call numbers 7, 8, 9)
+    w2 = workload("tiny", first_frame=200)
+    ts = w2.gyro_t0 + np.arange(w2.quats.shape[0]) / w2.gyro_rate
+    o = oracle_loader.OracleProblem(threads=2, seed=100).load(w2)
+    o.set_rng(100, 7)
+    wc, wd = oracle_loader.orientation_search(o, ts, w2.omega, ["XYZ", "yXz", "ZXY"], 0.0, 200, 212, 0.01, 0.05)
+    assert np.array_equal(oc, wc) and np.array_equal(od, wd)
+    assert int(np.argmin(oc)) == 0  # the true orientation has the lowest cost
 
 
 def test_shard_range_partitions():
