@@ -310,13 +310,13 @@ def test_syncpoint_driver_matches_oracle(rsb, oracle_loader, w_small, tmp_path):
     g = rsb.SyncProblem(seed=100).load(w, bulk=True)
     o = oracle_loader.OracleProblem(threads=8, seed=100).load(w)
     rg = driver.run(g, cfg, mode="batched", debug_csv=str(tmp_path / "dbg.csv"), presync_delays=rsb.presync_delays)
-    ro = driver.run(o, cfg, mode="sequential", debug_csv=None)
+    ro = driver.run(o, cfg, mode="sequential", debug_csv=str(tmp_path / "dbg_o.csv"))
     assert len(rg["syncpoints"]) == 3
     assert rel_err(rg["delay_ms"], ro["delay_ms"]) <= TOL
     assert rel_err(rg["cost"], ro["cost"]) <= TOL
-    assert g.call_counter() == o.call_counter() + 0
+    assert g.call_counter() == o.call_counter() == 1 + 3 * 5
     g2 = rsb.SyncProblem(seed=100).load(w, bulk=True)
-    rs_ = driver.run(g2, cfg, mode="sequential", debug_csv=None)
+    rs_ = driver.run(g2, cfg, mode="sequential", debug_csv=str(tmp_path / "dbg2.csv"))
     assert np.array_equal(rs_["delay_ms"], rg["delay_ms"])
 
 
