@@ -671,17 +671,105 @@ __device__ __noinline__ Loss5 warp_loss5_smem(const double* __restrict__ sP, int
     return out;
 }
 
+// Register-resident variants for the Sync kernels: the frame's rows stay in registers across all
+// objective evaluations of one L-BFGS run (the delay, hence P, is fixed during it), the slot loops
+// are compile-time so independent log1p / division chains interleave, and the five double-double
+// sums of an evaluation share one butterfly.  Same per-lane order of operations as the
+// shared-memory variants above, hence the same bits (rows past the frame's end are zero and add
+// exact zeros).
+template <int SLOTS>
+__device__ __forceinline__ void load_rows(const double* __restrict__ sP, int NP, int lane,
+                                          double (&p)[SLOTS][3]) {
+#pragma unroll
+    for (int s = 0; s < SLOTS; ++s) {
+        const int i = s * 32 + lane;
+        p[s][0] = sP[i];
+        p[s][1] = sP[NP + i];
+        p[s][2] = sP[2 * NP + i];
+    }
+}
+template <int N>
+__device__ __forceinline__ void warp_dd_sum_n(DD (&a)[N], double (&out)[N]) {
+#pragma unroll
+    for (int off = 16; off >= 1; off >>= 1) {
+        DD b[N];
+#pragma unroll
+        for (int j = 0; j < N; ++j) {
+            b[j].hi = __shfl_xor_sync(FULL, a[j].hi, off);
+            b[j].lo = __shfl_xor_sync(FULL, a[j].lo, off);
+        }
+#pragma unroll
+        for (int j = 0; j < N; ++j) dd_merge(a[j], b[j]);
+    }
+#pragma unroll
+    for (int j = 0; j < N; ++j) out[j] = a[j].hi + a[j].lo;
+}
+template <int SLOTS>
+__device__ __forceinline__ Loss5 warp_loss5_reg(const double (&p)[SLOTS][3], double m0, double m1,
+                                                double m2, double k, const double* __restrict__ tab) {
+    const double kk = k * k;
+    const double den = dot3(m0, m1, m2, m0, m1, m2) / kk;
+    const double inv_den = 1.0 / den;
+    double v1[SLOTS], u[SLOTS], lg[SLOTS], wgt[SLOTS];
+#pragma unroll
+    for (int s = 0; s < SLOTS; ++s) {
+        v1[s] = dot3(p[s][0], p[s][1], p[s][2], m0, m1, m2);
+        u[s] = (v1[s] * v1[s]) * inv_den;
+    }
+#pragma unroll
+    for (int s = 0; s < SLOTS; ++s) {
+        lg[s] = log1p_nonneg(u[s], tab);
+        wgt[s] = 1.0 / (1.0 + u[s]);
+    }
+    DD acc[5] = {dd_zero(), dd_zero(), dd_zero(), dd_zero(), dd_zero()};  // L, g0, g1, g2, su
+#pragma unroll
+    for (int s = 0; s < SLOTS; ++s) {
+        const double wv = wgt[s] * v1[s];
+        dd_add(acc[0], lg[s]);
+        dd_add(acc[1], wv * p[s][0]);
+        dd_add(acc[2], wv * p[s][1]);
+        dd_add(acc[3], wv * p[s][2]);
+        dd_add(acc[4], wgt[s] * u[s]);
+    }
+    double r[5];
+    warp_dd_sum_n<5>(acc, r);
+    Loss5 out;
+    out.f = r[0];
+    const double c1 = 2.0 * inv_den;
+    const double c2 = (c1 / kk) * r[4];
+    out.g0 = c1 * r[1] - c2 * m0;
+    out.g1 = c1 * r[2] - c2 * m1;
+    out.g2 = c1 * r[3] - c2 * m2;
+    return out;
+}
+template <int SLOTS>
+__device__ __forceinline__ double warp_loss3_reg(const double (&p)[SLOTS][3], double m0, double m1,
+                                                 double m2, double k, const double* __restrict__ tab) {
+    const double scale = k / sqrt(dot3(m0, m1, m2, m0, m1, m2));
+    double lg[SLOTS];
+#pragma unroll
+    for (int s = 0; s < SLOTS; ++s) {
+        const double r = dot3(p[s][0], p[s][1], p[s][2], m0, m1, m2) * scale;
+        lg[s] = log1p_nonneg(r * r, tab);
+    }
+    DD acc[1] = {dd_zero()};
+#pragma unroll
+    for (int s = 0; s < SLOTS; ++s) dd_add(acc[0], lg[s]);
+    double out[1];
+    warp_dd_sum_n<1>(acc, out);
+    return out[0];
+}
+
 // ens::L_BFGS on a 3-vector (call site core_private.cpp:264-294); every lane runs the same scalar
 // control flow on identical values, the objective is evaluated cooperatively.
-__device__ __forceinline__ double warp_lbfgs(const double* sP, int NP, int nslots, int lane,
-                                             double x[3], double k, const double* tab, int& n_iters,
-                                             int& n_evals) {
+template <class EvalF>
+__device__ __forceinline__ double warp_lbfgs(EvalF&& eval, double x[3], int& n_iters, int& n_evals) {
     constexpr int numBasis = 10, maxIterations = 200, maxTrials = 50;
     const double minGradientNorm = 1e-4, armijo = 1e-4, wolfe = 0.9, factr = 1e-15,
                  minStep = 1e-20, maxStep = 1e20;
     double S[numBasis][3], Y[numBasis][3], rho[numBasis], alpha[numBasis];
     double g[3], oldx[3], oldg[3], dir[3], trial[3];
-    Loss5 e = warp_loss5_smem(sP, NP, nslots, lane, x[0], x[1], x[2], k, tab);
+    Loss5 e = eval(x[0], x[1], x[2]);
     double f = e.f;
     g[0] = e.g0; g[1] = e.g1; g[2] = e.g2;
     n_evals = 1;
@@ -728,7 +816,7 @@ __device__ __forceinline__ double warp_lbfgs(const double* sP, int NP, int nslot
         int trials = 0;
         for (;;) {
             for (int c = 0; c < 3; ++c) trial[c] = x[c] + step * dir[c];
-            e = warp_loss5_smem(sP, NP, nslots, lane, trial[0], trial[1], trial[2], k, tab);
+            e = eval(trial[0], trial[1], trial[2]);
             f = e.f;
             g[0] = e.g0; g[1] = e.g1; g[2] = e.g2;
             n_evals++;
@@ -992,12 +1080,14 @@ sync_init_kernel(DeviceData dd, SyncBatchDev b, const double* __restrict__ sp_de
 
 // K2+K3a: per task, L-BFGS refinement of m at the syncpoint's delay (do_opt_motion, :262-296), then
 // the three objective values the delay step needs (Loss5 at x0, Loss3 at x0 -/+ h, :228-240).
+template <int SLOTS>
 __global__ void __launch_bounds__(kWarpsPerBlock * 32)
-sync_motion_fgrad_kernel(DeviceData dd, SyncBatchDev b, int NP, const double* __restrict__ sp_delay,
+sync_motion_fgrad_kernel(DeviceData dd, SyncBatchDev b, const double* __restrict__ sp_delay,
                          const double* __restrict__ sp_x0,
                          const unsigned char* __restrict__ sp_active, double* __restrict__ scratch,
                          int* __restrict__ stats) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
+    constexpr int NP = SLOTS * 32;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     double* tab = reinterpret_cast<double*>(smem_raw);
     load_log1p_table(tab);
@@ -1005,7 +1095,6 @@ sync_motion_fgrad_kernel(DeviceData dd, SyncBatchDev b, int NP, const double* __
     for (int t = blockIdx.x * kWarpsPerBlock + warp; t < b.T; t += gridDim.x * kWarpsPerBlock) {
         const SyncTask task = b.tasks[t];
         if (!sp_active[task.sp]) continue;
-        const int nslots = (task.fd.n + 31) >> 5;
         double m[3] = {b.m[3 * t], b.m[3 * t + 1], b.m[3 * t + 2]};
         const double k = b.k[t];
         const double x0 = sp_x0[task.sp];
@@ -1016,18 +1105,21 @@ sync_motion_fgrad_kernel(DeviceData dd, SyncBatchDev b, int NP, const double* __
                                             : x0 + kNumericDiffStep;
             __syncwarp();
             build_rows_smem<false>(dd, task.fd, delay, lane, w, NP);
+            double p[SLOTS][3];
+            load_rows<SLOTS>(w.P, NP, lane, p);
             if (j == 0) {
                 int it, ev;
-                warp_lbfgs(w.P, NP, nslots, lane, m, k, tab, it, ev);
+                warp_lbfgs([&](double a0, double a1, double a2) { return warp_loss5_reg<SLOTS>(p, a0, a1, a2, k, tab); },
+                           m, it, ev);
                 if (lane == 0) {
                     b.m[3 * t] = m[0]; b.m[3 * t + 1] = m[1]; b.m[3 * t + 2] = m[2];
                     if (stats) { stats[2 * t] = it; stats[2 * t + 1] = ev; }
                 }
             } else if (j == 1) {
-                const Loss5 e = warp_loss5_smem(w.P, NP, nslots, lane, m[0], m[1], m[2], k, tab);
+                const Loss5 e = warp_loss5_reg<SLOTS>(p, m[0], m[1], m[2], k, tab);
                 if (lane == 0) scratch[3 * t] = e.f;
             } else {
-                const double v = warp_loss3_smem(w.P, NP, nslots, lane, m[0], m[1], m[2], k, tab);
+                const double v = warp_loss3_reg<SLOTS>(p, m[0], m[1], m[2], k, tab);
                 if (lane == 0) scratch[3 * t + (j - 1)] = v;
             }
         }
@@ -1134,7 +1226,9 @@ __global__ void probe_lbfgs_kernel(DeviceData dd, FrameDesc fd, int NP, double d
     build_rows_smem<false>(dd, fd, delay, lane, w, NP);
     double m[3] = {mp[0], mp[1], mp[2]};
     int it, ev;
-    const double f = warp_lbfgs(w.P, NP, nslots, lane, m, k, tab, it, ev);
+    const double f = warp_lbfgs(
+        [&](double a0, double a1, double a2) { return warp_loss5_smem(w.P, NP, nslots, lane, a0, a1, a2, k, tab); },
+        m, it, ev);
     if (lane == 0) {
         mp[0] = m[0]; mp[1] = m[1]; mp[2] = m[2];
         *fout = f;
@@ -1274,12 +1368,14 @@ void launch_sync_motion_fgrad(const DeviceData& dd, const SyncBatchDev& b, const
                               double* d_task_scratch, double* d_out_v, double* d_out_g,
                               int* d_lbfgs_stats, cudaStream_t st) {
     if (b.T <= 0) return;
-    const int NP = slots_for(b.max_n) * 32;
-    const size_t smem = kLog1pTableBytes + (size_t)kWarpsPerBlock * warp_smem_bytes(NP, false);
-    allow_smem(sync_motion_fgrad_kernel, smem);
-    const int grid = grid_for(sync_motion_fgrad_kernel, smem, b.T);
-    sync_motion_fgrad_kernel<<<grid, kWarpsPerBlock * 32, smem, st>>>(
-        dd, b, NP, d_sp_delay, d_sp_x0, d_sp_active, d_task_scratch, d_lbfgs_stats);
+    RS_DISPATCH_SLOTS(b.max_n, {
+        auto kern = sync_motion_fgrad_kernel<SL>;
+        const size_t smem = kLog1pTableBytes + (size_t)kWarpsPerBlock * warp_smem_bytes(SL * 32, false);
+        allow_smem(kern, smem);
+        const int grid = grid_for(kern, smem, b.T);
+        kern<<<grid, kWarpsPerBlock * 32, smem, st>>>(dd, b, d_sp_delay, d_sp_x0, d_sp_active, d_task_scratch,
+                                                      d_lbfgs_stats);
+    });
     reduce_fgrad_kernel<<<(b.S + 3) / 4, 128, 0, st>>>(b, d_sp_active, d_task_scratch, d_out_v, d_out_g);
     g_launches += 2;
 }
