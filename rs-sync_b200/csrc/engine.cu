@@ -31,6 +31,8 @@ namespace rs {
 
 namespace {
 
+#define RS_PRAGMA_(x) _Pragma(#x)
+#define RS_PRAGMA(x) RS_PRAGMA_(x)
 constexpr unsigned FULL = 0xffffffffu;
 #ifndef RS_WPB
 #define RS_WPB 8
@@ -192,6 +194,9 @@ __device__ __forceinline__ unsigned build_rows_staged(const DeviceData& dd, cons
     float fin = 0.f;
     const int nslots = (fd.n + 31) >> 5;
     const int NPAIR = pairs_for(NP);
+#ifdef RS_UNROLL_A
+    RS_PRAGMA(unroll RS_UNROLL_A)
+#endif
     for (int s = 0; s < nslots; ++s) {
         const int i = s * 32 + lane;
         const double* t = sTiles + s * 256 + lane;
@@ -407,6 +412,54 @@ __device__ __noinline__ Vec3 warp_ransac_exact(const DeviceData& dd, const Frame
     return Vec3{M[0], M[1], M[2]};
 }
 
+// Exact (binary64, the contract's arithmetic) quartile of the squared residuals of ONE hypothesis,
+// returned as the bit pattern of the non-negative double (bit patterns order like the values).
+// Used by the tournament below to settle a comparison that fp32 cannot call.
+template <int SLOTS>
+__device__ __noinline__ unsigned long long warp_exact_quartile(const WarpSmem& w, int n, int lane,
+                                                               double vx, double vy, double vz) {
+    constexpr int NP = SLOTS * 32;
+    unsigned* skey = reinterpret_cast<unsigned*>(w.nf);
+    const unsigned long long nanbits = 0x7ff8000000000000ULL;
+    double r2[SLOTS];
+    unsigned h[SLOTS];
+    __syncwarp();
+#pragma unroll
+    for (int s = 0; s < SLOTS; ++s) {
+        const int i = s * 32 + lane;
+        const double p0 = w.P[i], p1 = w.P[NP + i], p2 = w.P[2 * NP + i];
+        const double inv = (i < n) ? row_inv_norm(p0, p1, p2) : __longlong_as_double((long long)nanbits);
+        const double r = dot3(p0 * inv, p1 * inv, p2 * inv, vx, vy, vz);  // :35-36, :48
+        r2[s] = r * r;                                                    // :49
+        h[s] = (unsigned)__double2hiint(r2[s]) & 0x7fffffffu;
+        skey[i] = h[s];
+    }
+    __syncwarp();
+    const int kth = n / 4;  // :52
+    int cl, ce;
+    const unsigned H = warp_select_hi<SLOTS>(h, skey, kth, 0x7ff80000u, lane, cl, ce);
+    int rem = kth - cl;  // rank among the ce keys whose hi word is H, ordered by lo word
+    unsigned cur = 0u, lo_ans = 0u;
+    for (;;) {
+        unsigned mn = 0xffffffffu, c = 0u;
+#pragma unroll
+        for (int s = 0; s < SLOTS; ++s) {
+            const unsigned lo = (unsigned)__double2loint(r2[s]);
+            if (h[s] == H && lo >= cur) mn = min(mn, lo);
+        }
+        mn = __reduce_min_sync(FULL, mn);
+#pragma unroll
+        for (int s = 0; s < SLOTS; ++s)
+            c += (h[s] == H && (unsigned)__double2loint(r2[s]) == mn) ? 1u : 0u;
+        c = __reduce_add_sync(FULL, c);
+        if (rem < (int)c) { lo_ans = mn; break; }
+        rem -= (int)c;
+        cur = mn + 1u;
+    }
+    __syncwarp();
+    return ((unsigned long long)H << 32) | lo_ans;
+}
+
 // ------------------------------------------------------------------------------------------
 // fp32 tournament (the estimator's fast path).
 //
@@ -423,8 +476,10 @@ __device__ __noinline__ Vec3 warp_ransac_exact(const DeviceData& dd, const Frame
 // rounding) and kMargin >= 2 kDelta:
 //   * count(s_t <= up(q32_best)) <= n/4   =>  q64_t > q64_best        (t is rigorously worse)
 //   * up(q32_t) < q32_best                =>  q64_t < q64_best        (t is rigorously better)
-// Anything else is too close to call in fp32; the task is then redone by warp_ransac_exact.  The
-// result is therefore always the exact estimator's M, bit for bit.
+// Anything else is too close to call in fp32: that one comparison is settled with the exact
+// binary64 quartiles of the two hypotheses (warp_exact_quartile; ties keep the earlier one), so the
+// winner is always the exact estimator's M, bit for bit.  Only non-finite data sends the whole
+// task to warp_ransac_exact.
 constexpr float kMargin = 1.4e-6f;
 
 __device__ __forceinline__ unsigned up_bits(unsigned qbits) {  // rigorous upper bound (directed rounding)
@@ -532,7 +587,7 @@ __device__ __forceinline__ unsigned warp_select32(const float2 (&s)[NPAIR], int 
 template <int SLOTS>
 __device__ __forceinline__ bool warp_ransac_fast(const DeviceData& dd, const FrameDesc& fd,
                                                  const WarpSmem& w, int iters, uint64_t key,
-                                                 int lane, double M[3]) {
+                                                 int lane, double M[3], int* settled) {
     constexpr int NP = SLOTS * 32, NPAIR = pairs_for(NP), NK = 2 * NPAIR;
     const float2* nf2 = reinterpret_cast<const float2*>(w.nf);
     float2 nx[NPAIR], ny[NPAIR], nz[NPAIR];
@@ -554,55 +609,82 @@ __device__ __forceinline__ bool warp_ransac_fast(const DeviceData& dd, const Fra
         if (j0 + lane < iters) draw_hypothesis(dd, fd, w.P, NP, key, (uint32_t)(j0 + lane), v);
         const float w0 = (float)v[0], w1 = (float)v[1], w2 = (float)v[2];
         const int cnt = (iters - j0) < 32 ? (iters - j0) : 32;
-        for (int t = 0; t < cnt; ++t) {
-            const float vx = __shfl_sync(FULL, w0, t), vy = __shfl_sync(FULL, w1, t),
-                        vz = __shfl_sync(FULL, w2, t);
-            const float2 vx2 = make_float2(vx, vx), vy2 = make_float2(vy, vy),
-                         vz2 = make_float2(vz, vz);
-            float2 sq[NPAIR];
-            unsigned hi_excl;
-            int chi;
-            const bool first = tau == 0x7f800000u;
-            if (!first) {
-                const float2 nt2 = make_float2(nthr, nthr);
-                unsigned c = 0;
+        int t = 0;
+        while (t < cnt) {
+            // hot loop: runs until the batch is done or a comparison cannot be called in fp32
+            int t_amb = -1;
+            unsigned q_amb = 0u, uq_amb = 0u;
+            for (; t < cnt; ++t) {
+                const float vx = __shfl_sync(FULL, w0, t), vy = __shfl_sync(FULL, w1, t),
+                            vz = __shfl_sync(FULL, w2, t);
+                const float2 vx2 = make_float2(vx, vx), vy2 = make_float2(vy, vy),
+                             vz2 = make_float2(vz, vz);
+                float2 sq[NPAIR];
+                unsigned hi_excl;
+                int chi;
+                const bool first = tau == 0x7f800000u;
+                if (!first) {
+                    const float2 nt2 = make_float2(nthr, nthr);
+                    unsigned c = 0;
 #pragma unroll
-                for (int p = 0; p < NPAIR; ++p) {
-                    float2 r = __fmul2_rn(nx[p], vx2);
-                    r = __ffma2_rn(ny[p], vy2, r);
-                    r = __ffma2_rn(nz[p], vz2, r);
-                    sq[p] = __fmul2_rn(r, r);
-                    const float2 e = __fadd2_rn(sq[p], nt2);
-                    c += __float_as_uint(e.x) >> 31;
-                    c += __float_as_uint(e.y) >> 31;
-                }
-                chi = (int)__reduce_add_sync(FULL, c);
-                if (chi <= kk) continue;  // rigorously worse than the best so far
-                hi_excl = thr1;
-            } else {
-                unsigned mx = 0u;
+                    for (int p = 0; p < NPAIR; ++p) {
+                        float2 r = __fmul2_rn(nx[p], vx2);
+                        r = __ffma2_rn(ny[p], vy2, r);
+                        r = __ffma2_rn(nz[p], vz2, r);
+                        sq[p] = __fmul2_rn(r, r);
+                        const float2 e = __fadd2_rn(sq[p], nt2);
+                        c += __float_as_uint(e.x) >> 31;
+                        c += __float_as_uint(e.y) >> 31;
+                    }
+                    chi = (int)__reduce_add_sync(FULL, c);
+                    if (chi <= kk) continue;  // rigorously worse than the best so far
+                    hi_excl = thr1;
+                } else {
+                    unsigned mx = 0u;
 #pragma unroll
-                for (int p = 0; p < NPAIR; ++p) {
-                    float2 r = __fmul2_rn(nx[p], vx2);
-                    r = __ffma2_rn(ny[p], vy2, r);
-                    r = __ffma2_rn(nz[p], vz2, r);
-                    sq[p] = __fmul2_rn(r, r);
-                    mx = max(mx, max(__float_as_uint(sq[p].x), __float_as_uint(sq[p].y)));
+                    for (int p = 0; p < NPAIR; ++p) {
+                        float2 r = __fmul2_rn(nx[p], vx2);
+                        r = __ffma2_rn(ny[p], vy2, r);
+                        r = __ffma2_rn(nz[p], vz2, r);
+                        sq[p] = __fmul2_rn(r, r);
+                        mx = max(mx, max(__float_as_uint(sq[p].x), __float_as_uint(sq[p].y)));
+                    }
+                    mx = __reduce_max_sync(FULL, mx);
+                    if (mx >= 0x7f800000u) return false;
+                    hi_excl = mx + 1u;
+                    chi = NK * 32;
                 }
-                mx = __reduce_max_sync(FULL, mx);
-                if (mx >= 0x7f800000u) return false;
-                hi_excl = mx + 1u;
-                chi = NK * 32;
+                const unsigned q = warp_select32<NPAIR>(sq, kk, hi_excl, chi, npad, n, first);
+                const unsigned uq = up_bits(q);
+                if (!(uq < tau)) {  // too close to the best so far to call in fp32
+                    t_amb = t;
+                    q_amb = q;
+                    uq_amb = uq;
+                    break;
+                }
+                tau = q;
+                thr1 = uq + 1u;
+                nthr = -__uint_as_float(thr1);
+                M[0] = __shfl_sync(FULL, v[0], t);
+                M[1] = __shfl_sync(FULL, v[1], t);
+                M[2] = __shfl_sync(FULL, v[2], t);
             }
-            const unsigned q = warp_select32<NPAIR>(sq, kk, hi_excl, chi, npad, n, first);
-            const unsigned uq = up_bits(q);
-            if (!(uq < tau)) return false;  // too close to the best so far to call in fp32
-            tau = q;
-            thr1 = uq + 1u;
-            nthr = -__uint_as_float(thr1);
-            M[0] = __shfl_sync(FULL, v[0], t);
-            M[1] = __shfl_sync(FULL, v[1], t);
-            M[2] = __shfl_sync(FULL, v[2], t);
+            if (t_amb < 0) break;
+            // cold: settle this one comparison with the exact binary64 quartiles of the two
+            // hypotheses (a tie keeps the earlier one, core_private.cpp:53), then resume
+            const double tx = __shfl_sync(FULL, v[0], t_amb), ty = __shfl_sync(FULL, v[1], t_amb),
+                         tz = __shfl_sync(FULL, v[2], t_amb);
+            const unsigned long long qt = warp_exact_quartile<SLOTS>(w, n, lane, tx, ty, tz);
+            const unsigned long long qb = warp_exact_quartile<SLOTS>(w, n, lane, M[0], M[1], M[2]);
+            if (qt >= 0x7ff0000000000000ULL || qb >= 0x7ff0000000000000ULL) return false;
+            if (settled) ++*settled;
+            if (qt < qb) {
+                tau = q_amb;
+                thr1 = uq_amb + 1u;
+                nthr = -__uint_as_float(thr1);
+                M[0] = tx; M[1] = ty; M[2] = tz;
+            }
+            t = t_amb + 1;
         }
     }
     return true;
@@ -613,8 +695,14 @@ template <int SLOTS>
 __device__ __forceinline__ void warp_ransac(const DeviceData& dd, const FrameDesc& fd,
                                             const WarpSmem& w, int iters, uint64_t key, int lane,
                                             bool rows_finite, double M[3], unsigned* n_exact) {
-    if (rows_finite && warp_ransac_fast<SLOTS>(dd, fd, w, iters, key, lane, M)) return;
-    if (n_exact && lane == 0) atomicAdd(n_exact, 1u);
+    int settled = 0;
+    const bool ok = rows_finite && warp_ransac_fast<SLOTS>(dd, fd, w, iters, key, lane, M, &settled);
+    if (n_exact && settled && lane == 0) atomicAdd(n_exact, 1u);  // tasks that needed binary64
+    if (ok) return;
+#ifdef RS_EXPERIMENT_NO_COLD  // timing experiment only: wrong results for undecided tasks
+    return;
+#endif
+    if (n_exact && !settled && lane == 0) atomicAdd(n_exact, 1u);
     const Vec3 e = warp_ransac_exact<SLOTS>(dd, fd, w, iters, key, lane);
     M[0] = e.x; M[1] = e.y; M[2] = e.z;
 }
@@ -883,11 +971,20 @@ __device__ __noinline__ unsigned presync_diagnose(const double* pm, int nslots, 
 // of unit u issues the copies for unit u + 1, which then overlap phases B-D of unit u.  (With
 // ~200 KB of the SM's 228 KB carved out as shared memory the L1 keeps ~13 KB: un-staged, the same
 // loads hit L1 28 % of the time and wait on L2, profiles/r01_presync_v3c.md.)
-constexpr int kRecMax = 64;  // spline records per window (8 KB)
+#ifndef RS_REC_MAX
+#define RS_REC_MAX 64
+#endif
+constexpr int kRecMax = RS_REC_MAX;  // spline records per window (8 KB)
 template <int SLOTS>
 struct PresyncCfg {
-    static constexpr int kWarps = SLOTS <= 8 ? 10 : 8;
-    static constexpr int kMinBlocks = SLOTS <= 8 ? 2 : 1;
+#ifndef RS_PRESYNC_WARPS
+#define RS_PRESYNC_WARPS 8
+#endif
+#ifndef RS_PRESYNC_MINB
+#define RS_PRESYNC_MINB 2
+#endif
+    static constexpr int kWarps = SLOTS <= 8 ? RS_PRESYNC_WARPS : 8;
+    static constexpr int kMinBlocks = SLOTS <= 8 ? RS_PRESYNC_MINB : 1;
     static constexpr size_t kTileBytes = (size_t)SLOTS * 2048;
     static constexpr size_t kCtlOff = kLog1pTableBytes;
     static constexpr size_t kTileOff = kCtlOff + 128;
@@ -976,8 +1073,12 @@ presync_kernel(DeviceData dd, const FrameDesc* __restrict__ frames, int F,
         double delay = 0.0;
         if (active) {
             delay = delays[di];
+#ifdef RS_EXPERIMENT_NO_COLD
+            bad = build_rows_staged(dd, fd, delay, lane, w, NP, sTiles, sRec, rec_first, rec_cnt);
+#else
             bad = rec_cnt ? build_rows_staged(dd, fd, delay, lane, w, NP, sTiles, sRec, rec_first, rec_cnt)
                           : build_rows_global_cold(dd, fd, delay, lane, w, NP);
+#endif
             bad = __reduce_or_sync(FULL, bad);
         }
         __syncwarp();

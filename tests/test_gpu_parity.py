@@ -385,3 +385,61 @@ def test_golden_fixture(rsb, w_tiny):
     sc, sd = p.Sync(0.035, fb, fe - 1, 0.0, 0.2)
     assert rel_err(sd, float.fromhex(g["sync_delay_hex"])) <= TOL
     assert rel_err(sc, float.fromhex(g["sync_cost_hex"])) <= TOL
+
+
+def test_cxx_dropin_runs_like_the_c_abi(rsb, w_tiny, tmp_path):
+    """a C++ caller written against the reference's ISyncProblem interface (include/rssync.h), run
+    on the GPU through CreateSyncProblem's vtable, returns what the C ABI returns"""
+    import os, struct, subprocess
+    from conftest import ROOT
+    w = w_tiny
+    blob = tmp_path / "workload.bin"
+    with open(blob, "wb") as f:
+        f.write(struct.pack("<qqqdd", w.quats.shape[0], w.n_frames, w.n_rays, w.gyro_rate, w.gyro_t0))
+        f.write(np.ascontiguousarray(w.quats).tobytes())
+        f.write(np.ascontiguousarray(w.frame_ids).tobytes())
+        for a in (w.ts_a, w.ts_b, w.rays_a, w.rays_b):
+            f.write(np.ascontiguousarray(a).tobytes())
+    src = tmp_path / "caller.cpp"
+    src.write_text(r'''
+#include <rssync.h>
+#include <cstdio>
+#include <cstdint>
+#include <memory>
+#include <vector>
+int main(int, char** argv) {
+    FILE* f = std::fopen(argv[1], "rb");
+    int64_t nq, nf, nr; double rate, t0;
+    if (!f || std::fread(&nq, 8, 1, f) != 1 || std::fread(&nf, 8, 1, f) != 1 || std::fread(&nr, 8, 1, f) != 1 ||
+        std::fread(&rate, 8, 1, f) != 1 || std::fread(&t0, 8, 1, f) != 1) return 2;
+    std::vector<double> q(4 * nq), tsa(nf * nr), tsb(nf * nr), ra(3 * nf * nr), rb(3 * nf * nr);
+    std::vector<int64_t> ids(nf);
+    if (std::fread(q.data(), 8, q.size(), f) != q.size() || std::fread(ids.data(), 8, nf, f) != (size_t)nf ||
+        std::fread(tsa.data(), 8, tsa.size(), f) != tsa.size() || std::fread(tsb.data(), 8, tsb.size(), f) != tsb.size() ||
+        std::fread(ra.data(), 8, ra.size(), f) != ra.size() || std::fread(rb.data(), 8, rb.size(), f) != rb.size()) return 3;
+    std::unique_ptr<ISyncProblem> sp{CreateSyncProblem()};   // core_testcode.cpp:248
+    sp->SetGyroQuaternions(q.data(), (size_t)nq, rate, t0);
+    for (int64_t i = 0; i < nf; ++i)
+        sp->SetTrackResult(ids[i], &tsa[i * nr], &tsb[i * nr], &ra[3 * i * nr], &rb[3 * i * nr], (size_t)nr);
+    std::vector<double> dd(11), cc(11);
+    sp->DebugPreSync(0.0, ids[0], ids[0] + nf, 0.05, dd.data(), cc.data(), 11);
+    auto p = sp->PreSync(0.0, ids[0], ids[0] + nf, 0.005, 0.05);
+    auto s = sp->Sync(p.second, ids[0], ids[0] + nf - 1, 0.0, 0.05);
+    std::printf("%a %a %a %a %a %a\n", p.first, p.second, s.first, s.second, dd[3], cc[3]);
+    return 0;
+}
+''')
+    exe = tmp_path / "caller"
+    libdir = os.path.dirname(rsb.LIB_PATH)
+    r = subprocess.run(["g++", "-std=c++17", f"-I{ROOT}/include", str(src), "-o", str(exe), f"-L{libdir}",
+                        "-lrssync_b200", f"-Wl,-rpath,{libdir}"], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    r = subprocess.run([str(exe), str(blob)], capture_output=True, text=True, cwd=tmp_path)
+    assert r.returncode == 0, r.stderr
+    got = [float.fromhex(x) for x in r.stdout.split()]
+    g = rsb.SyncProblem(seed=100).load(w)
+    fb, nf = int(w.frame_ids[0]), w.n_frames
+    dd, cc = g.DebugPreSync(0.0, fb, fb + nf, 0.05, 11)
+    p = g.PreSync(0.0, fb, fb + nf, 0.005, 0.05)
+    s = g.Sync(p[1], fb, fb + nf - 1, 0.0, 0.05)
+    assert got == [p[0], p[1], s[0], s[1], dd[3], cc[3]]

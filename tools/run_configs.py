@@ -18,6 +18,9 @@ if world > 1:
     torch.cuda.set_device(int(os.environ.get("LOCAL_RANK", "0")))
     dist.init_process_group("nccl")
     dev = torch.device("cuda", int(os.environ.get("LOCAL_RANK", "0")))
+    warm = torch.zeros(1, device=dev)
+    dist.all_reduce(warm)  # NCCL builds its communicator on the first collective: keep that out of the timings
+    torch.cuda.synchronize()
 
 
 def emit(d):
