@@ -362,11 +362,9 @@ def bench_sync(prob, w, rank, world, barrier, dev):
     win = w.sync_window
 
     def run():
-        delays = []
-        for pos in mine:  # PreSync per syncpoint
-            delays.append(prob.PreSync(0.0, pos, pos + win, w.presync_step, 0.2)[1])
-        d = np.array(delays)
         fbs = np.array(mine, dtype=np.int64)
+        # PreSync of every syncpoint window, one grid launch
+        d = prob.presync_windows(0.0, fbs, fbs + win, w.presync_step, 0.2)[1]
         for _ in range(4):  # 4 chained Sync calls per syncpoint, advanced in lock-step
             _, d = prob.sync_batch(d, fbs, fbs + win, 0.0, 0.2)
         return d

@@ -84,6 +84,14 @@ int rssync_debug_presync(rssync_problem* p, double initial_delay, int64_t frame_
 int rssync_presync_grid(rssync_problem* p, int64_t frame_begin, int64_t frame_end,
                         const double* delays, int n, int stream, uint64_t call_no,
                         uint64_t offset_index_base, double* costs, unsigned* nonfinite_flags);
+/* n PreSync calls — frame windows [frame_begin[i], frame_end[i]), one shared (initial_delay,
+ * search_step, search_radius) — evaluated as one grid launch; the syncpoint loop of
+ * core_testcode.cpp:303-312 issues them one by one.  Result i equals the i-th of n consecutive
+ * rssync_presync calls.  call_nos[i] keys the RNG of window i; NULL = consecutive values of the
+ * problem's counter, which then advances by n. */
+int rssync_presync_windows(rssync_problem* p, int n, double initial_delay, const int64_t* frame_begin,
+                           const int64_t* frame_end, double search_step, double search_radius,
+                           const uint64_t* call_nos, double* out_cost, double* out_delay);
 /* pre_sync's delay grid (core_private.cpp:69-70, floating-point accumulation included).
  * Returns the number of points; fills at most `cap` of them. */
 int rssync_presync_delays(double initial_delay, double search_step, double search_radius,

@@ -35,7 +35,7 @@ C_ABI_SYMBOLS = [
     "rssync_probe_problem_matrix", "rssync_probe_guess_motion", "rssync_probe_loss",
     "rssync_probe_lbfgs", "rssync_probe_log1p", "rssync_set_track_batch", "rssync_set_kernel_timing",
     "rssync_sync_batch_ex", "rssync_probe_guess_motion_ex", "rssync_integrate_gyro",
-    "rssync_orientation_search",
+    "rssync_orientation_search", "rssync_presync_windows",
 ]
 # Itanium-ABI symbols of the C++ drop-in face (same set the reference's librssync_core exports)
 CXX_ABI_SYMBOLS = [
@@ -88,6 +88,8 @@ def load_library():
     L.rssync_presync_grid.argtypes = [P, C.c_int64, C.c_int64, c_double_p, C.c_int, C.c_int, C.c_uint64,
                                       C.c_uint64, c_double_p, C.POINTER(C.c_uint)]
     L.rssync_presync_delays.argtypes = [C.c_double, C.c_double, C.c_double, c_double_p, C.c_int]
+    L.rssync_presync_windows.argtypes = [P, C.c_int, C.c_double, c_i64_p, c_i64_p, C.c_double, C.c_double,
+                                         C.POINTER(C.c_uint64), c_double_p, c_double_p]
     L.rssync_sync_batch.argtypes = [P, C.c_int, c_double_p, c_i64_p, c_i64_p, c_double_p, c_double_p,
                                     c_double_p, c_double_p]
     L.rssync_sync_batch_ex.argtypes = [P, C.c_int, c_double_p, c_i64_p, c_i64_p, c_double_p, c_double_p,
@@ -295,6 +297,21 @@ class SyncProblem:
         self._check(self.L.rssync_presync_grid(self.h, frame_begin, frame_end, _dp(delays), delays.shape[0],
                                                stream, call_no, offset_index_base, _dp(costs), C.byref(flags)))
         return (costs, flags.value) if return_flags else costs
+
+    def presync_windows(self, initial_delay, frame_begin, frame_end, search_step, search_radius, call_nos=None):
+        """n PreSync calls (one per frame window, shared delay grid) as one grid launch -> (costs, delays)"""
+        fb = np.ascontiguousarray(frame_begin, dtype=np.int64)
+        fe = np.ascontiguousarray(frame_end, dtype=np.int64)
+        n = fb.shape[0]
+        cn = None
+        if call_nos is not None:
+            cn_arr = np.ascontiguousarray(call_nos, dtype=np.uint64)
+            cn = cn_arr.ctypes.data_as(C.POINTER(C.c_uint64))
+        costs, delays = np.empty(n), np.empty(n)
+        self._check(self.L.rssync_presync_windows(self.h, n, initial_delay, fb.ctypes.data_as(c_i64_p),
+                                                  fe.ctypes.data_as(c_i64_p), search_step, search_radius, cn,
+                                                  _dp(costs), _dp(delays)))
+        return costs, delays
 
     def sync_batch(self, initial_delay, frame_begin, frame_end, search_center, search_radius, call_nos=None):
         ini = _f64(initial_delay)

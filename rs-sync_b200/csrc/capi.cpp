@@ -131,6 +131,8 @@ struct rssync_problem {
     // scratch
     DevBuf<FrameDesc> d_frames;
     DevBuf<double> d_delays, d_framecost, d_costs;
+    DevBuf<uint64_t> d_frame_call;
+    DevBuf<int> d_win_begin;
     DevBuf<unsigned> d_flags;
     PinBuf<double> h_stage;
     // sync scratch
@@ -485,6 +487,7 @@ void rssync_destroy(rssync_problem* p) {
     p->h_orig.release(); p->d_orig.release();
     p->h_pos.release(); p->d_pos.release();
     p->d_frames.release(); p->d_delays.release(); p->d_framecost.release(); p->d_costs.release();
+    p->d_frame_call.release(); p->d_win_begin.release();
     p->d_flags.release(); p->h_stage.release(); p->d_tasks.release(); p->d_sp_begin.release();
     p->d_lbfgs_stats.release(); p->d_m.release(); p->d_k.release(); p->d_task_scratch.release();
     p->d_sp_delay.release(); p->d_sp_x0.release(); p->d_trial_delay.release(); p->d_out_v.release();
@@ -845,6 +848,83 @@ int rssync_presync(rssync_problem* p, double initial, int64_t fb, int64_t fe, do
         if (costs[i] < costs[best] || (costs[i] == costs[best] && delays[i] < delays[best])) best = i;
     *out_cost = costs[best];
     *out_delay = delays[best];
+    return RSSYNC_OK;
+}
+
+// n PreSync calls over n frame windows with one shared delay grid, evaluated as ONE grid launch
+// (the syncpoint loop of core_testcode.cpp:303-312 issues them one by one).  Result i equals the
+// i-th of n consecutive rssync_presync calls; call_nos (or the problem's counter) key the RNG.
+int rssync_presync_windows(rssync_problem* p, int n, double initial, const int64_t* fb, const int64_t* fe,
+                           double step, double radius, const uint64_t* call_nos, double* out_cost,
+                           double* out_delay) {
+    if (!p || n < 0) return RSSYNC_E_INVALID;
+    if (n == 0) return RSSYNC_OK;
+    if (!fb || !fe || !out_cost || !out_delay) return RSSYNC_E_INVALID;
+    if (int rc = require_gyro(p, "pre-sync")) return rc;
+    if (!(step > 0) || !std::isfinite(radius) || !std::isfinite(initial)) {
+        p->err = "pre-sync: search_step must be > 0 and the search window finite";
+        return RSSYNC_E_INVALID;
+    }
+    const int D = rssync_presync_delays(initial, step, radius, nullptr, 0);
+    if (D <= 0 || D > (1 << 28)) { p->err = "pre-sync: empty or oversized delay grid"; return RSSYNC_E_INVALID; }
+    std::vector<double> delays(D);
+    rssync_presync_delays(initial, step, radius, delays.data(), D);
+    std::vector<FrameDesc> all, sel;
+    std::vector<uint64_t> fcall;
+    std::vector<int> wbeg(n + 1, 0);
+    int max_n = 0;
+    for (int i = 0; i < n; ++i) {
+        int mn = 0;
+        if (int rc = select_frames(p, fb[i], fe[i], sel, mn, "pre-sync")) return rc;
+        max_n = std::max(max_n, mn);
+        const uint64_t call = call_nos ? call_nos[i] : p->call_no + (uint64_t)i;
+        for (const FrameDesc& fd : sel) { all.push_back(fd); fcall.push_back(call); }
+        wbeg[i + 1] = (int)all.size();
+    }
+    if (!call_nos) p->call_no += (uint64_t)n;
+    if (int rc = flush(p)) return rc;
+    const int F = (int)all.size();
+    std::vector<double> costs((size_t)n * D, 0.0);
+    unsigned flags[2] = {0, 0};
+    if (F > 0) {
+        if ((long long)F * D > (1LL << 40)) { p->err = "pre-sync: grid too large"; return RSSYNC_E_INVALID; }
+        CUDA_TRY(p, p->d_frames.reserve(F));
+        CUDA_TRY(p, p->d_delays.reserve(D));
+        CUDA_TRY(p, p->d_framecost.reserve((size_t)F * D));
+        CUDA_TRY(p, p->d_costs.reserve((size_t)n * D));
+        CUDA_TRY(p, p->d_flags.reserve(2));
+        CUDA_TRY(p, p->d_frame_call.reserve(F));
+        CUDA_TRY(p, p->d_win_begin.reserve(n + 1));
+        if (int rc = h2d(p, p->d_frames.ptr, all.data(), sizeof(FrameDesc) * F)) return rc;
+        if (int rc = h2d(p, p->d_delays.ptr, delays.data(), sizeof(double) * D)) return rc;
+        if (int rc = h2d(p, p->d_frame_call.ptr, fcall.data(), sizeof(uint64_t) * F)) return rc;
+        if (int rc = h2d(p, p->d_win_begin.ptr, wbeg.data(), sizeof(int) * (n + 1))) return rc;
+        CUDA_TRY(p, cudaMemsetAsync(p->d_flags.ptr, 0, 2 * sizeof(unsigned), p->stream));
+        rs::launch_presync_grid(p->device_data(), p->d_frames.ptr, F, max_n, p->d_delays.ptr, D, p->seed,
+                                rs::kStreamPreSync, 0, 0, p->d_framecost.ptr, p->d_costs.ptr, p->d_flags.ptr,
+                                p->stream, nullptr, nullptr, p->d_frame_call.ptr, p->d_win_begin.ptr, n);
+        CUDA_TRY(p, cudaGetLastError());
+        if (int rc = d2h(p, costs.data(), p->d_costs.ptr, sizeof(double) * n * D)) return rc;
+        if (int rc = d2h(p, flags, p->d_flags.ptr, 2 * sizeof(unsigned))) return rc;
+        CUDA_TRY(p, cudaStreamSynchronize(p->stream));
+        p->grid_tasks = (uint64_t)F * (uint64_t)D;
+        p->grid_exact_tasks = flags[1];
+    }
+    if (flags[0]) {  // core_private.cpp:76-83
+        p->err = (flags[0] & rs::kFlagP)   ? "pre-sync: non-finite numbers in P"
+                 : (flags[0] & rs::kFlagM) ? "pre-sync: non-finite numbers in M"
+                 : (flags[0] & rs::kFlagR) ? "pre-sync: non-finite r"
+                                           : "pre-sync: non-finite rho";
+        return RSSYNC_E_NONFINITE;
+    }
+    for (int i = 0; i < n; ++i) {
+        const double* c = &costs[(size_t)i * D];
+        int best = 0;  // std::min_element over (cost, delay) pairs, :89
+        for (int d = 1; d < D; ++d)
+            if (c[d] < c[best] || (c[d] == c[best] && delays[d] < delays[best])) best = d;
+        out_cost[i] = c[best];
+        out_delay[i] = delays[best];
+    }
     return RSSYNC_OK;
 }
 

@@ -1037,8 +1037,8 @@ template <int SLOTS>
 __global__ void __launch_bounds__(PresyncCfg<SLOTS>::kWarps * 32, PresyncCfg<SLOTS>::kMinBlocks)
 presync_kernel(DeviceData dd, const FrameDesc* __restrict__ frames, int F,
                const double* __restrict__ delays, int D, int chunk, int cpf, uint64_t seed,
-               uint64_t stream, uint64_t call_no, uint64_t idx_base, double* __restrict__ framecost,
-               unsigned* __restrict__ flags) {
+               uint64_t stream, uint64_t call_no, const uint64_t* __restrict__ frame_call_no,
+               uint64_t idx_base, double* __restrict__ framecost, unsigned* __restrict__ flags) {
     using Cfg = PresyncCfg<SLOTS>;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     constexpr int NP = SLOTS * 32;
@@ -1092,7 +1092,9 @@ presync_kernel(DeviceData dd, const FrameDesc* __restrict__ frames, int F,
         }
         if (!active) continue;
         const uint64_t key =
-            rng_task_key(rng_prefix(seed, stream, call_no, idx_base + (uint64_t)di), fd.id);
+            rng_task_key(rng_prefix(seed, stream, frame_call_no ? frame_call_no[fi] : call_no,
+                                    idx_base + (uint64_t)di),
+                         fd.id);
         double M[3];
         warp_ransac<SLOTS>(dd, fd, w, 20, key, lane, bad == 0u, M, flags + 1);  // core_private.cpp:77
         // :79-85
@@ -1147,6 +1149,21 @@ __global__ void reduce_rows_kernel(const double* __restrict__ in, int rows, int 
     for (int c = lane; c < cols; c += 32) dd_add(acc, in[(size_t)row * cols + c]);
     const double v = warp_dd_sum(acc);
     if (lane == 0) out[row] = v;
+}
+
+// several PreSync windows in one grid: cost[w][d] = double-double sum of framecost[d][f] over the
+// window's frames f in [win_begin[w], win_begin[w + 1]); one warp per (window, delay)
+__global__ void reduce_windows_kernel(const double* __restrict__ in, int D, int F,
+                                      const int* __restrict__ win_begin, int W,
+                                      double* __restrict__ out) {
+    const int lane = threadIdx.x & 31;
+    const int q = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (q >= W * D) return;
+    const int wi = q / D, d = q % D;
+    DD acc = dd_zero();
+    for (int f = win_begin[wi] + lane; f < win_begin[wi + 1]; f += 32) dd_add(acc, in[(size_t)d * F + f]);
+    const double v = warp_dd_sum(acc);
+    if (lane == 0) out[q] = v;
 }
 
 // ------------------------------------------------------------------------------------------
@@ -1418,9 +1435,10 @@ uint64_t launch_count() { return g_launches.load(); }
 void launch_presync_grid(const DeviceData& dd, const FrameDesc* d_frames, int F, int max_n,
                          const double* d_delays, int D, uint64_t seed, uint64_t stream,
                          uint64_t call_no, uint64_t idx_base, double* d_framecost, double* d_costs,
-                         unsigned* d_flags, cudaStream_t st, cudaEvent_t ev_begin, cudaEvent_t ev_end) {
+                         unsigned* d_flags, cudaStream_t st, cudaEvent_t ev_begin, cudaEvent_t ev_end,
+                         const uint64_t* d_frame_call_no, const int* d_win_begin, int n_windows) {
     if (F <= 0 || D <= 0) {
-        if (D > 0) cudaMemsetAsync(d_costs, 0, sizeof(double) * D, st);
+        if (D > 0) cudaMemsetAsync(d_costs, 0, sizeof(double) * D * (d_win_begin ? n_windows : 1), st);
         return;
     }
     RS_DISPATCH_SLOTS(max_n, {
@@ -1443,10 +1461,14 @@ void launch_presync_grid(const DeviceData& dd, const FrameDesc* d_frames, int F,
         if (ev_begin) cudaEventRecord(ev_begin, st);
         kern<<<grid, Cfg::kWarps * 32, Cfg::kSmem, st>>>(dd, d_frames, F, d_delays, D, chunk,
                                                          (D + chunk - 1) / chunk, seed, stream, call_no,
-                                                         idx_base, d_framecost, d_flags);
+                                                         d_frame_call_no, idx_base, d_framecost, d_flags);
         if (ev_end) cudaEventRecord(ev_end, st);
     });
-    reduce_rows_kernel<<<(D + 3) / 4, 128, 0, st>>>(d_framecost, D, F, d_costs);
+    if (d_win_begin)
+        reduce_windows_kernel<<<(n_windows * D + 3) / 4, 128, 0, st>>>(d_framecost, D, F, d_win_begin,
+                                                                      n_windows, d_costs);
+    else
+        reduce_rows_kernel<<<(D + 3) / 4, 128, 0, st>>>(d_framecost, D, F, d_costs);
     g_launches += 2;
 }
 

@@ -41,7 +41,12 @@ void launch_presync_grid(const DeviceData& dd, const FrameDesc* d_frames, int F,
                          const double* d_delays, int D, uint64_t seed, uint64_t stream,
                          uint64_t call_no, uint64_t idx_base, double* d_framecost, double* d_costs,
                          unsigned* d_flags, cudaStream_t st, cudaEvent_t ev_begin = nullptr,
-                         cudaEvent_t ev_end = nullptr);
+                         cudaEvent_t ev_end = nullptr,
+                         // several windows in one grid: the F frames are the windows' frames
+                         // concatenated, frame f belongs to the call d_frame_call_no[f], window w
+                         // covers frames [d_win_begin[w], d_win_begin[w+1]); d_costs is W x D
+                         const uint64_t* d_frame_call_no = nullptr, const int* d_win_begin = nullptr,
+                         int n_windows = 0);
 
 // ---- Sync: batched over syncpoints; tasks = (syncpoint, frame) --------------------------------
 struct SyncTask {

@@ -94,10 +94,17 @@ def run(problem, config, *, mode="batched", rank=0, world=1, device="cpu", debug
         from . import sharded
         mine = list(range(rank, n, world))
         if use_presync:
-            grid = np.asarray(presync_delays(initial, step, radius))
-            for i in mine:
-                curve = problem.presync_grid(sps[i], sps[i] + window, grid, stream=1, call_no=base + per_sp * i)
-                delays[i] = grid[sharded.argmin_cost_delay(curve, grid)]
+            if hasattr(problem, "presync_windows") and mine:  # all of this rank's windows in one grid launch
+                idx = np.asarray(mine)
+                wb = np.asarray(sps, dtype=np.int64)[idx]
+                _, d = problem.presync_windows(initial, wb, wb + window, step, radius,
+                                               call_nos=(base + per_sp * idx).astype(np.uint64))
+                delays[idx] = d
+            else:
+                grid = np.asarray(presync_delays(initial, step, radius))
+                for i in mine:
+                    curve = problem.presync_grid(sps[i], sps[i] + window, grid, stream=1, call_no=base + per_sp * i)
+                    delays[i] = grid[sharded.argmin_cost_delay(curve, grid)]
             if world > 1:
                 import torch.distributed as dist
                 loc = np.array([delays[i] for i in mine])

@@ -298,6 +298,26 @@ def test_orientation_search_matches_oracle(rsb, oracle_loader, synth_mod):
         g.orientation_search(ts, w.omega, ["XYZ", "XQZ"], 0.0, fb, fe, 0.005, 0.05)
 
 
+def test_presync_windows_equals_sequence(pair_small):
+    """several PreSync windows in one grid launch == the same PreSync calls one by one"""
+    g, o, w = pair_small
+    f0 = int(w.frame_ids[0])
+    fbs = np.array([f0, f0 + 10, f0 + 25, f0 + 10, 10 ** 6])  # overlapping, repeated and empty windows
+    fes = fbs + np.array([20, 30, 12, 30, 5])
+    g.set_rng(100, 40)
+    seq = [g.PreSync(0.0, int(a), int(b), 0.004, 0.08) for a, b in zip(fbs, fes)]
+    g.set_rng(100, 40)
+    c, d = g.presync_windows(0.0, fbs, fes, 0.004, 0.08)
+    assert np.array_equal(c, [s[0] for s in seq]) and np.array_equal(d, [s[1] for s in seq])
+    assert g.call_counter() == 45
+    c3, d3 = g.presync_windows(0.0, fbs[:2], fes[:2], 0.004, 0.08, call_nos=np.array([40, 41], dtype=np.uint64))
+    assert np.array_equal(c3, c[:2]) and np.array_equal(d3, d[:2])
+    assert g.call_counter() == 45
+    o.set_rng(100, 40)
+    so = [o.PreSync(0.0, int(a), int(b), 0.004, 0.08) for a, b in zip(fbs[:3], fes[:3])]
+    assert np.array_equal(d[:3], [x[1] for x in so]) and rel_err(c[:3], [x[0] for x in so]) <= TOL
+
+
 def test_syncpoint_driver_matches_oracle(rsb, oracle_loader, w_small, tmp_path):
     """core_testcode's syncpoint loop (PreSync + 4 x Sync per syncpoint): the engine's batched,
     lock-step execution against the oracle issuing the reference's sequential calls"""

@@ -13,7 +13,7 @@ for rep in range(3):
     p.set_rng(100, 0)
     l0 = p.stats()["kernel_launches"]
     t0 = time.perf_counter()
-    d = np.array([p.PreSync(0.0, pos, pos + win, w.presync_step, 0.2)[1] for pos in sps])
+    d = p.presync_windows(0.0, fbs, fbs + win, w.presync_step, 0.2)[1]
     t1 = time.perf_counter()
     its = []
     for i in range(4):
