@@ -9,6 +9,8 @@
 #include <atomic>
 #include <cmath>
 #include <condition_variable>
+#include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <functional>
 #include <map>
@@ -392,8 +394,17 @@ int sync_batch_impl(rssync_problem* p, int n, const double* initial, const int64
         if (int rc = d2h(p, h_g.data(), p->d_out_g.ptr, sizeof(double) * n)) return rc;
         if (int rc = d2h(p, h_stats.data(), p->d_lbfgs_stats.ptr, sizeof(int) * 2 * T)) return rc;
         CUDA_TRY(p, cudaStreamSynchronize(p->stream));
+        int dbg_max_ev = 0, dbg_max_it = 0;
         for (int t = 0; t < T; ++t)
-            if (h_active[tasks[t].sp]) p->sync_evals += (uint64_t)h_stats[2 * t + 1];
+            if (h_active[tasks[t].sp]) {
+                p->sync_evals += (uint64_t)h_stats[2 * t + 1];
+                dbg_max_ev = std::max(dbg_max_ev, h_stats[2 * t + 1]);
+                dbg_max_it = std::max(dbg_max_it, h_stats[2 * t]);
+            }
+        static const bool dbg = std::getenv("RSSYNC_DEBUG_SYNC") != nullptr;
+        if (dbg)
+            std::fprintf(stderr, "sync it %d: active %d, L-BFGS max iters %d, max evals %d\n", it, n_active,
+                         dbg_max_it, dbg_max_ev);
         // Backtrack::Step (backtrack.cpp:3-13): all trial points are known once the gradient
         // is, so they are evaluated in one launch and the first that passes is taken.
         for (int s = 0; s < n; ++s) {

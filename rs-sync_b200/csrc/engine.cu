@@ -856,6 +856,10 @@ __device__ __forceinline__ double warp_lbfgs(EvalF&& eval, double x[3], int& n_i
     const double minGradientNorm = 1e-4, armijo = 1e-4, wolfe = 0.9, factr = 1e-15,
                  minStep = 1e-20, maxStep = 1e20;
     double S[numBasis][3], Y[numBasis][3], rho[numBasis], alpha[numBasis];
+    // 1 / (y.s) of each stored pair: the two-loop recursion recomputes this division for every pair
+    // at every iteration; the value only depends on the pair, so it is computed once when the pair
+    // is stored (same expression, same bits) -- it is the longest dependent chain of an iteration
+    double rho_pair[numBasis];
     double g[3], oldx[3], oldg[3], dir[3], trial[3];
     Loss5 e = eval(x[0], x[1], x[2]);
     double f = e.f;
@@ -881,8 +885,7 @@ __device__ __forceinline__ double warp_lbfgs(EvalF&& eval, double x[3], int& n_i
         const int limit = (numBasis > it) ? 0 : (it - numBasis);
         for (int i = it; i != limit; --i) {
             const int tp = (i + (numBasis - 1)) % numBasis;
-            const double ys = dot3(Y[tp][0], Y[tp][1], Y[tp][2], S[tp][0], S[tp][1], S[tp][2]);
-            rho[it - i] = (ys != 0) ? (1.0 / ys) : 1.0;
+            rho[it - i] = rho_pair[tp];
             alpha[it - i] = rho[it - i] * dot3(S[tp][0], S[tp][1], S[tp][2], dir[0], dir[1], dir[2]);
             for (int c = 0; c < 3; ++c) dir[c] -= alpha[it - i] * Y[tp][c];
         }
@@ -929,6 +932,8 @@ __device__ __forceinline__ double warp_lbfgs(EvalF&& eval, double x[3], int& n_i
         if ((prevf - f) / denom <= factr) break;
         const int op = it % numBasis;
         for (int c = 0; c < 3; ++c) { S[op][c] = x[c] - oldx[c]; Y[op][c] = g[c] - oldg[c]; }
+        const double ys = dot3(Y[op][0], Y[op][1], Y[op][2], S[op][0], S[op][1], S[op][2]);
+        rho_pair[op] = (ys != 0) ? (1.0 / ys) : 1.0;
     }
     return f;
 }
