@@ -51,6 +51,22 @@ struct DevBuf {
         cap = (e == cudaSuccess) ? want : 0;
         return e;
     }
+    // grow to at least n elements keeping the first `keep` (device-to-device copy on `st`)
+    cudaError_t grow(size_t n, size_t keep, cudaStream_t st) {
+        if (n <= cap) return cudaSuccess;
+        size_t want = std::max(n, cap * 2);
+        T* np = nullptr;
+        cudaError_t e = cudaMalloc((void**)&np, want * sizeof(T));
+        if (e != cudaSuccess) return e;
+        if (ptr && keep) e = cudaMemcpyAsync(np, ptr, std::min(keep, cap) * sizeof(T), cudaMemcpyDeviceToDevice, st);
+        if (e == cudaSuccess && ptr) {
+            e = cudaStreamSynchronize(st);
+            cudaFree(ptr);
+        }
+        ptr = np;
+        cap = want;
+        return e;
+    }
     void release() {
         if (ptr) cudaFree(ptr);
         ptr = nullptr;
@@ -123,8 +139,12 @@ struct rssync_problem {
     DevBuf<double> d_rays;
     PinBuf<int32_t> h_orig, h_pos;
     DevBuf<int32_t> d_orig, d_pos;
-    size_t used = 0, uploaded = 0, garbage = 0;
-    bool rays_full_dirty = false;
+    size_t used = 0, garbage = 0;
+    // arena ranges [first, last) (in rays) whose pinned host copy is newer than the device's; frames
+    // ingested on the device (rssync_set_track_pixels) never appear here, so the device arena is
+    // the one complete copy and grows with its contents preserved
+    std::vector<std::pair<size_t, size_t>> pending;
+    size_t dev_used = 0;  // extent of the device arena holding data
     std::map<int64_t, FrameDesc> frames;  // OptData::frame_data
     size_t total_rays = 0;
 
@@ -193,6 +213,26 @@ int wait_arena_copies(rssync_problem* p) {
     return RSSYNC_OK;
 }
 
+// device arena large enough for `used` rays, contents preserved
+int reserve_device_arena(rssync_problem* p) {
+    const size_t want = std::max(p->used, p->h_orig.cap);
+    CUDA_TRY(p, p->d_rays.grow(want * 8, p->dev_used * 8, p->stream));
+    CUDA_TRY(p, p->d_orig.grow(want, p->dev_used, p->stream));
+    CUDA_TRY(p, p->d_pos.grow(want, p->dev_used, p->stream));
+    return RSSYNC_OK;
+}
+int upload_arena_range(rssync_problem* p, size_t a, size_t b) {
+    if (int rc = h2d(p, p->d_rays.ptr + a * 8, p->h_rays.ptr + a * 8, (b - a) * 8 * sizeof(double))) return rc;
+    if (int rc = h2d(p, p->d_orig.ptr + a, p->h_orig.ptr + a, (b - a) * sizeof(int32_t))) return rc;
+    if (int rc = h2d(p, p->d_pos.ptr + a, p->h_pos.ptr + a, (b - a) * sizeof(int32_t))) return rc;
+    p->dev_used = std::max(p->dev_used, b);
+    return RSSYNC_OK;
+}
+void add_pending(rssync_problem* p, size_t a, size_t b) {
+    if (!p->pending.empty() && p->pending.back().second == a) p->pending.back().second = b;
+    else p->pending.emplace_back(a, b);
+}
+
 int flush(rssync_problem* p) {
     CUDA_TRY(p, cudaSetDevice(p->device));
     join_gyro(p);
@@ -201,21 +241,11 @@ int flush(rssync_problem* p) {
         if (int rc = h2d(p, p->d_rec.ptr, p->rec.ptr, p->nq * 16 * sizeof(double))) return rc;
         p->gyro_dirty = false;
     }
-    if (p->used > p->uploaded || p->rays_full_dirty) {
-        bool regrow = p->d_rays.cap < p->used * 8;
-        size_t from = (regrow || p->rays_full_dirty) ? 0 : p->uploaded;
-        CUDA_TRY(p, p->d_rays.reserve(p->h_rays.cap));
-        if (int rc = h2d(p, p->d_rays.ptr + from * 8, p->h_rays.ptr + from * 8,
-                         (p->used - from) * 8 * sizeof(double)))
-            return rc;
-        CUDA_TRY(p, p->d_orig.reserve(p->h_orig.cap));
-        if (int rc = h2d(p, p->d_orig.ptr + from, p->h_orig.ptr + from, (p->used - from) * sizeof(int32_t)))
-            return rc;
-        CUDA_TRY(p, p->d_pos.reserve(p->h_pos.cap));
-        if (int rc = h2d(p, p->d_pos.ptr + from, p->h_pos.ptr + from, (p->used - from) * sizeof(int32_t)))
-            return rc;
-        p->uploaded = p->used;
-        p->rays_full_dirty = false;
+    if (!p->pending.empty()) {
+        if (int rc = reserve_device_arena(p)) return rc;
+        for (const auto& r : p->pending)
+            if (int rc = upload_arena_range(p, r.first, r.second)) return rc;
+        p->pending.clear();
     }
     return RSSYNC_OK;
 }
@@ -579,7 +609,6 @@ int place_track(rssync_problem* p, int64_t frame, size_t count, FrameDesc** fd_o
     auto it = p->frames.find(frame);
     if (it != p->frames.end() && (size_t)((it->second.n + 31) / 32 * 32) == padded) {
         off = (size_t)it->second.off;  // replace in place
-        if (off < p->uploaded) p->rays_full_dirty = true;
         p->total_rays -= (size_t)it->second.n;
     } else {
         if (it != p->frames.end()) {
@@ -735,6 +764,7 @@ int rssync_set_track(rssync_problem* p, int64_t frame, const double* ts_a, const
     FrameDesc* fd = nullptr;
     if (int rc = place_track(p, frame, count, &fd)) return rc;
     fill_track(p, fd, ts_a, ts_b, rays_a, rays_b, count, p->sort_scratch);
+    add_pending(p, (size_t)fd->off, (size_t)fd->off + (count + 31) / 32 * 32);
     return RSSYNC_OK;
 }
 
@@ -755,32 +785,22 @@ int rssync_set_track_batch(rssync_problem* p, size_t n_frames, const int64_t* fr
     for (size_t i = 0; i < n_frames; ++i)
         if (rc[i]) { n_ok = i; break; }
     if (int r = wait_arena_copies(p)) return r;
-    const size_t used0 = p->used, uploaded0 = p->uploaded;
-    const bool clean0 = p->uploaded == p->used && !p->rays_full_dirty;
     std::vector<FrameDesc*> fds(n_ok);
     bool run = true;  // the batch occupies one contiguous run of the arena, in order
     for (size_t i = 0; i < n_ok; ++i) {
         if (int r = place_track(p, frames[i], counts[i], &fds[i])) return r;
         run = run && (i == 0 || (size_t)fds[i]->off == (size_t)fds[i - 1]->off + (counts[i - 1] + 31) / 32 * 32);
     }
+    auto frame_end = [&](size_t i) { return (size_t)fds[i]->off + (counts[i] + 31) / 32 * 32; };
     // Eager upload: when the batch is one contiguous run of the arena (an append, or the same
-    // frames set again in place) and nothing else is pending, the arena range of each chunk of
-    // frames is copied to the device as soon as the chunk is filled, so the copy of chunk k
-    // overlaps the sort/transpose of chunk k + 1.
-    bool eager = run && clean0 && n_ok >= 64 && (size_t)fds[0]->off <= uploaded0;
+    // frames set again in place), the arena range of each chunk of frames is copied to the device
+    // as soon as the chunk is filled, so the copy of chunk k overlaps the sort/transpose of
+    // chunk k + 1.  Otherwise the ranges are left for the next flush.
+    bool eager = run && n_ok >= 64;
     if (eager) {
         cudaSetDevice(p->device);
-        p->rays_full_dirty = false;  // place_track flags in-place replacement; handled here
-        const bool regrow = p->d_rays.cap < p->used * 8 || p->d_orig.cap < p->used || p->d_pos.cap < p->used;
-        if (regrow && used0 > 0) {
-            p->rays_full_dirty = true;
-            eager = false;  // growing the device arena drops what is there: the lazy path re-uploads all
-        } else {
-            CUDA_TRY(p, p->d_rays.reserve(p->h_rays.cap));
-            CUDA_TRY(p, p->d_orig.reserve(p->h_orig.cap));
-            CUDA_TRY(p, p->d_pos.reserve(p->h_pos.cap));
-            if (!p->ev_arena) CUDA_TRY(p, cudaEventCreateWithFlags(&p->ev_arena, cudaEventDisableTiming));
-        }
+        if (int r = reserve_device_arena(p)) return r;
+        if (!p->ev_arena) CUDA_TRY(p, cudaEventCreateWithFlags(&p->ev_arena, cudaEventDisableTiming));
     }
     std::vector<std::vector<std::pair<double, int32_t>>> scratch(17);
     const size_t n_chunks = eager ? 6 : 1;
@@ -792,12 +812,9 @@ int rssync_set_track_batch(rssync_problem* p, size_t n_frames, const int64_t* fr
             fill_track(p, fds[i], ts_a + at[i], ts_b + at[i], rays_a + 3 * at[i], rays_b + 3 * at[i], counts[i], scratch[t]);
         });
         if (eager) {
-            const size_t a = (size_t)fds[lo]->off;
-            const size_t b = (hi < n_ok) ? (size_t)fds[hi]->off : p->used;
-            if (int r = h2d(p, p->d_rays.ptr + a * 8, p->h_rays.ptr + a * 8, (b - a) * 8 * sizeof(double))) return r;
-            if (int r = h2d(p, p->d_orig.ptr + a, p->h_orig.ptr + a, (b - a) * sizeof(int32_t))) return r;
-            if (int r = h2d(p, p->d_pos.ptr + a, p->h_pos.ptr + a, (b - a) * sizeof(int32_t))) return r;
-            p->uploaded = std::max(p->uploaded, b);
+            if (int r = upload_arena_range(p, (size_t)fds[lo]->off, frame_end(hi - 1))) return r;
+        } else {
+            for (size_t i = lo; i < hi; ++i) add_pending(p, (size_t)fds[i]->off, frame_end(i));
         }
     }
     if (eager) {

@@ -1039,7 +1039,11 @@ __device__ __noinline__ void presync_stage_unit(const DeviceData& dd, const Fram
 }
 
 template <int SLOTS>
+#ifdef RS_PRESYNC_MAXNREG
+__global__ void __maxnreg__(RS_PRESYNC_MAXNREG)
+#else
 __global__ void __launch_bounds__(PresyncCfg<SLOTS>::kWarps * 32, PresyncCfg<SLOTS>::kMinBlocks)
+#endif
 presync_kernel(DeviceData dd, const FrameDesc* __restrict__ frames, int F,
                const double* __restrict__ delays, int D, int chunk, int cpf, uint64_t seed,
                uint64_t stream, uint64_t call_no, const uint64_t* __restrict__ frame_call_no,
