@@ -60,6 +60,22 @@ int rssync_set_track(rssync_problem* p, int64_t frame, const double* ts_a, const
 int rssync_set_track_batch(rssync_problem* p, size_t n_frames, const int64_t* frames,
                            const size_t* counts, const double* ts_a, const double* ts_b,
                            const double* rays_a, const double* rays_b);
+/* Lens profile: Lens (core_testcode.cpp:55-61), the numbers of one line of the lens file
+ * `<name> <readout_s> fx fy cx cy k1 k2 k3 k4` (README.md:52-60, lens_load :164-181). */
+typedef struct rssync_lens {
+    double readout, fx, fy, cx, cy, k1, k2, k3, k4;
+} rssync_lens;
+/* The per-frame tail of track_frames (core_testcode.cpp:134-161) followed by SetTrackResult, for
+ * n_frames frames, computed on the device: points_a / points_b are the tracked pixel pairs
+ * (sum(counts) x 2 doubles, x then y), frame_ts_a / frame_ts_b the two frames' timestamps in
+ * seconds (cur_ts / 1000, next_ts / 1000).  Per pair: lens_undistort_point (:63-95) on both points,
+ * ts = frame_ts + readout * (y / image_rows) (:144-145), unit rays (x', y', 1) / |.| (:147-154).
+ * Equivalent to computing those on the host and calling rssync_set_track for each frame, up to
+ * the rounding of tan / cos (CUDA's instead of libm's, <= 2 ulp). */
+int rssync_set_track_pixels(rssync_problem* p, size_t n_frames, const int64_t* frames,
+                            const size_t* counts, const double* frame_ts_a, const double* frame_ts_b,
+                            const double* points_a, const double* points_b, const rssync_lens* lens,
+                            double image_rows);
 /* PreSync(initial_delay, frame_begin, frame_end, search_step, search_radius) -> {cost, delay}
  *                                                                  rssync.h:19-21 */
 int rssync_presync(rssync_problem* p, double initial_delay, int64_t frame_begin, int64_t frame_end,

@@ -35,7 +35,7 @@ C_ABI_SYMBOLS = [
     "rssync_probe_problem_matrix", "rssync_probe_guess_motion", "rssync_probe_loss",
     "rssync_probe_lbfgs", "rssync_probe_log1p", "rssync_set_track_batch", "rssync_set_kernel_timing",
     "rssync_sync_batch_ex", "rssync_probe_guess_motion_ex", "rssync_integrate_gyro",
-    "rssync_orientation_search", "rssync_presync_windows",
+    "rssync_orientation_search", "rssync_presync_windows", "rssync_set_track_pixels",
 ]
 # Itanium-ABI symbols of the C++ drop-in face (same set the reference's librssync_core exports)
 CXX_ABI_SYMBOLS = [
@@ -50,6 +50,11 @@ class Stats(C.Structure):
         "sync_outer_iters", "sync_lbfgs_evals")] + [("last_grid_kernel_ms", C.c_double),
                                                      ("last_grid_tasks", C.c_uint64),
                                                      ("last_grid_exact_tasks", C.c_uint64)]
+
+
+class Lens(C.Structure):
+    """rssync_lens: readout_s fx fy cx cy k1 k2 k3 k4 (one line of the reference's lens file)"""
+    _fields_ = [(n, C.c_double) for n in ("readout", "fx", "fy", "cx", "cy", "k1", "k2", "k3", "k4")]
 
 
 class RsSyncError(RuntimeError):
@@ -82,6 +87,8 @@ def load_library():
     L.rssync_set_track_batch.argtypes = [P, C.c_size_t, c_i64_p, C.POINTER(C.c_size_t), c_double_p, c_double_p,
                                          c_double_p, c_double_p]
     L.rssync_set_kernel_timing.argtypes = [P, C.c_int]
+    L.rssync_set_track_pixels.argtypes = [P, C.c_size_t, c_i64_p, C.POINTER(C.c_size_t), c_double_p, c_double_p,
+                                          c_double_p, c_double_p, C.POINTER(Lens), C.c_double]
     L.rssync_presync.argtypes = [P, C.c_double, C.c_int64, C.c_int64, C.c_double, C.c_double, c_double_p, c_double_p]
     L.rssync_sync.argtypes = [P, C.c_double, C.c_int64, C.c_int64, C.c_double, C.c_double, c_double_p, c_double_p]
     L.rssync_debug_presync.argtypes = [P, C.c_double, C.c_int64, C.c_int64, C.c_double, c_double_p, c_double_p, C.c_int]
@@ -248,6 +255,16 @@ class SyncProblem:
         self._check(self.L.rssync_set_track_batch(
             self.h, frames.shape[0], frames.ctypes.data_as(c_i64_p),
             counts.ctypes.data_as(C.POINTER(C.c_size_t)), _dp(a[0]), _dp(a[1]), _dp(a[2]), _dp(a[3])))
+
+    def set_track_pixels(self, frames, counts, frame_ts_a, frame_ts_b, points_a, points_b, lens, image_rows):
+        """track_frames' per-frame tail (core_testcode.cpp:134-161) on the device: pixel pairs -> rays"""
+        fr = np.ascontiguousarray(frames, dtype=np.int64)
+        cn = np.ascontiguousarray(counts, dtype=np.uint64)
+        ta, tb, pa, pb = _f64(frame_ts_a), _f64(frame_ts_b), _f64(points_a), _f64(points_b)
+        lens_c = lens if isinstance(lens, Lens) else Lens(*[float(x) for x in lens])
+        self._check(self.L.rssync_set_track_pixels(self.h, fr.shape[0], fr.ctypes.data_as(c_i64_p),
+                                                   cn.ctypes.data_as(C.POINTER(C.c_size_t)), _dp(ta), _dp(tb),
+                                                   _dp(pa), _dp(pb), C.byref(lens_c), float(image_rows)))
 
     def load(self, w, bulk=False):
         """Feed a synth.Workload the way core_testcode feeds a video (core_testcode.cpp:257-268)."""

@@ -154,6 +154,10 @@ struct rssync_problem {
     DevBuf<FrameDesc> d_frames;
     DevBuf<double> d_delays, d_framecost, d_costs;
     DevBuf<uint64_t> d_frame_call;
+    // pixel front end staging
+    PinBuf<double> h_pix;
+    DevBuf<double> d_pix;
+    DevBuf<rs::PixelFrame> d_pixframes;
     DevBuf<int> d_win_begin;
     DevBuf<unsigned> d_flags;
     PinBuf<double> h_stage;
@@ -529,6 +533,7 @@ void rssync_destroy(rssync_problem* p) {
     p->h_pos.release(); p->d_pos.release();
     p->d_frames.release(); p->d_delays.release(); p->d_framecost.release(); p->d_costs.release();
     p->d_frame_call.release(); p->d_win_begin.release();
+    p->h_pix.release(); p->d_pix.release(); p->d_pixframes.release();
     p->d_flags.release(); p->h_stage.release(); p->d_tasks.release(); p->d_sp_begin.release();
     p->d_lbfgs_stats.release(); p->d_m.release(); p->d_k.release(); p->d_task_scratch.release();
     p->d_sp_delay.release(); p->d_sp_x0.release(); p->d_trial_delay.release(); p->d_out_v.release();
@@ -828,6 +833,69 @@ int rssync_set_track_batch(rssync_problem* p, size_t n_frames, const int64_t* fr
 }  // extern "C"
 
 extern "C" {
+
+// The per-frame tail of track_frames (core_testcode.cpp:134-161) on the device: pixel pairs in,
+// rays + rolling-shutter timestamps straight into the device arena (no host sort / transpose, half
+// the host->device bytes of the ray form).
+int rssync_set_track_pixels(rssync_problem* p, size_t n_frames, const int64_t* frames, const size_t* counts,
+                            const double* frame_ts_a, const double* frame_ts_b, const double* points_a,
+                            const double* points_b, const rssync_lens* lens, double image_rows) {
+    if (!p) return RSSYNC_E_INVALID;
+    if (n_frames == 0) return RSSYNC_OK;
+    if (!frames || !counts || !frame_ts_a || !frame_ts_b || !points_a || !points_b || !lens) return RSSYNC_E_INVALID;
+    const double lv[9] = {lens->readout, lens->fx, lens->fy, lens->cx, lens->cy, lens->k1, lens->k2, lens->k3, lens->k4};
+    if (!all_finite(lv, 9) || !(image_rows > 0) || !std::isfinite(image_rows) || lens->fx == 0 || lens->fy == 0) {
+        p->err = "set-track-pixels: bad lens profile or image height";
+        return RSSYNC_E_INVALID;
+    }
+    std::vector<size_t> at(n_frames + 1, 0);
+    for (size_t i = 0; i < n_frames; ++i) {
+        if (counts[i] > (size_t)rs::kMaxRaysPerFrame) {
+            p->err = "set-track-result: more than 512 rays in one frame is not supported";
+            return RSSYNC_E_INVALID;
+        }
+        at[i + 1] = at[i] + counts[i];
+    }
+    const size_t total = at[n_frames];
+    if (!all_finite(points_a, 2 * total)) { p->err = "set-track-result: non-finite numbers in rays_a"; return RSSYNC_E_NONFINITE; }
+    if (!all_finite(points_b, 2 * total)) { p->err = "set-track-result: non-finite numbers in rays_b"; return RSSYNC_E_NONFINITE; }
+    if (!all_finite(frame_ts_a, n_frames)) { p->err = "set-track-result: non-finite numbers in ts_a"; return RSSYNC_E_NONFINITE; }
+    if (!all_finite(frame_ts_b, n_frames)) { p->err = "set-track-result: non-finite numbers in ts_b"; return RSSYNC_E_NONFINITE; }
+    if (int rc = wait_arena_copies(p)) return rc;
+    cudaSetDevice(p->device);
+    std::vector<rs::PixelFrame> pf(n_frames);
+    for (size_t i = 0; i < n_frames; ++i) {
+        FrameDesc* fd = nullptr;
+        if (int rc = place_track(p, frames[i], counts[i], &fd)) return rc;
+        // timestamp bounds, with the device's expression (core_testcode.cpp:144-145)
+        double lo = 0.0, hi = 0.0;
+        for (size_t k = 0; k < counts[i]; ++k) {
+            const double ta = frame_ts_a[i] + lens->readout * (points_a[2 * (at[i] + k) + 1] / image_rows);
+            const double tb = frame_ts_b[i] + lens->readout * (points_b[2 * (at[i] + k) + 1] / image_rows);
+            if (k == 0) { lo = std::min(ta, tb); hi = std::max(ta, tb); }
+            lo = std::min(lo, std::min(ta, tb));
+            hi = std::max(hi, std::max(ta, tb));
+        }
+        fd->ts_lo = lo;
+        fd->ts_hi = hi;
+        pf[i] = rs::PixelFrame{fd->off, fd->n, (int64_t)at[i], frame_ts_a[i], frame_ts_b[i]};
+    }
+    if (int rc = reserve_device_arena(p)) return rc;
+    CUDA_TRY(p, p->h_pix.reserve(4 * total + 1));
+    CUDA_TRY(p, p->d_pix.reserve(4 * total + 1));
+    CUDA_TRY(p, p->d_pixframes.reserve(n_frames));
+    std::memcpy(p->h_pix.ptr, points_a, 2 * total * sizeof(double));
+    std::memcpy(p->h_pix.ptr + 2 * total, points_b, 2 * total * sizeof(double));
+    if (int rc = h2d(p, p->d_pix.ptr, p->h_pix.ptr, 4 * total * sizeof(double))) return rc;
+    if (int rc = h2d(p, p->d_pixframes.ptr, pf.data(), n_frames * sizeof(rs::PixelFrame))) return rc;
+    CUDA_TRY(p, cudaStreamSynchronize(p->stream));  // pf is a local; the pinned staging buffer is reused
+    rs::LensDev L{lens->readout, lens->fx, lens->fy, lens->cx, lens->cy, lens->k1, lens->k2, lens->k3, lens->k4};
+    rs::launch_ingest_pixels(p->d_pixframes.ptr, (int)n_frames, p->d_pix.ptr, p->d_pix.ptr + 2 * total, L,
+                             image_rows, p->d_rays.ptr, p->d_orig.ptr, p->d_pos.ptr, p->stream);
+    CUDA_TRY(p, cudaGetLastError());
+    p->dev_used = std::max(p->dev_used, p->used);
+    return RSSYNC_OK;
+}
 
 int rssync_set_kernel_timing(rssync_problem* p, int enabled) {
     if (!p) return RSSYNC_E_INVALID;

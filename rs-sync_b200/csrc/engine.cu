@@ -1310,6 +1310,98 @@ __global__ void reduce_trials_kernel(SyncBatchDev b, int ntrial,
 }
 
 // ------------------------------------------------------------------------------------------
+// K6: pixel -> ray front end.  lens_undistort_point (core_testcode.cpp:63-95): fisheye model
+// theta_d = theta (1 + k1 theta^2 + ...), inverted by 9 Newton steps from pi/4 -- including the
+// reference's derivative coefficient 8 k4 (:80; 9 k4 would be the exact one, it only changes the
+// convergence speed) and its halving loop that keeps theta inside (0, pi/2).
+__device__ __forceinline__ void undistort_point(const LensDev& L, double px, double py, double& ux,
+                                                double& uy) {
+    if (sqrt(px * px + py * py) < 1e-8) { ux = 0.0; uy = 0.0; return; }  // :64
+    const double x_ = (px - L.cx) / L.fx, y_ = (py - L.cy) / L.fy;
+    const double theta_ = sqrt(x_ * x_ + y_ * y_);
+    const double kPi = 3.14159265358979323846;
+    double theta = kPi / 4.;
+    for (int i = 0; i < 9; ++i) {
+        const double t2 = theta * theta, t3 = t2 * theta, t4 = t2 * t2, t5 = t2 * t3, t6 = t3 * t3,
+                     t7 = t3 * t4, t8 = t4 * t4, t9 = t4 * t5;
+        const double cur = theta + L.k1 * t3 + L.k2 * t5 + L.k3 * t7 + L.k4 * t9;
+        const double dcur = 1 + 3 * L.k1 * t2 + 5 * L.k2 * t4 + 7 * L.k3 * t6 + 8 * L.k4 * t8;
+        const double err = cur - theta_;
+        double nt = theta - err * (1. / dcur);
+        for (int guard = 0; (nt >= kPi / 2. || nt <= 0.) && guard < 2048; ++guard) nt = (nt + theta) / 2.;
+        theta = nt;
+    }
+    const double r = tan(theta), inv_cos = 1. / cos(theta);
+    const double s = (theta_ < 1e-9) ? inv_cos : r / theta_;
+    ux = x_ * s;
+    uy = y_ * s;
+}
+
+constexpr int kIngestThreads = 256;
+__global__ void __launch_bounds__(kIngestThreads)
+ingest_pixels_kernel(const PixelFrame* __restrict__ frames, const double* __restrict__ pa,
+                     const double* __restrict__ pb, LensDev L, double rows, double* __restrict__ rays,
+                     int32_t* __restrict__ orig, int32_t* __restrict__ pos) {
+    __shared__ double s_ts[kMaxRaysPerFrame];  // ts_a of point i (sort key)
+    __shared__ int s_idx[kMaxRaysPerFrame];    // permutation being sorted
+    __shared__ double s_val[7][kMaxRaysPerFrame];  // ts_b, ra.xyz, rb.xyz of point i
+    const PixelFrame f = frames[blockIdx.x];
+    for (int i = threadIdx.x; i < kMaxRaysPerFrame; i += kIngestThreads) {
+        s_idx[i] = i;
+        if (i < f.n) {
+            const double ax = pa[2 * (f.src + i)], ay = pa[2 * (f.src + i) + 1];
+            const double bx = pb[2 * (f.src + i)], by = pb[2 * (f.src + i) + 1];
+            double ua, va, ub, vb;
+            undistort_point(L, ax, ay, ua, va);
+            undistort_point(L, bx, by, ub, vb);
+            s_ts[i] = f.ts_a + L.ro * (ay / rows);  // :144
+            s_val[0][i] = f.ts_b + L.ro * (by / rows);  // :145
+            const double na = sqrt(ua * ua + va * va + 1.0), nb = sqrt(ub * ub + vb * vb + 1.0);
+            s_val[1][i] = ua / na; s_val[2][i] = va / na; s_val[3][i] = 1.0 / na;  // :153
+            s_val[4][i] = ub / nb; s_val[5][i] = vb / nb; s_val[6][i] = 1.0 / nb;  // :154
+        } else {
+            s_ts[i] = __longlong_as_double(0x7ff0000000000000LL);  // padding sorts last
+        }
+    }
+    __syncthreads();
+    // bitonic sort of the index permutation by (ts_a, index): the order std::sort gives the host path
+    for (int k = 2; k <= kMaxRaysPerFrame; k <<= 1)
+        for (int j = k >> 1; j > 0; j >>= 1) {
+            for (int i = threadIdx.x; i < kMaxRaysPerFrame; i += kIngestThreads) {
+                const int l = i ^ j;
+                if (l > i) {
+                    const int a = s_idx[i], b = s_idx[l];
+                    const double ta = s_ts[a], tb = s_ts[b];
+                    const bool a_first = ta < tb || (ta == tb && a < b);
+                    const bool up = (i & k) == 0;
+                    if (a_first != up) { s_idx[i] = b; s_idx[l] = a; }
+                }
+            }
+            __syncthreads();
+        }
+    const int padded = (f.n + 31) / 32 * 32;
+    for (int j = threadIdx.x; j < padded; j += kIngestThreads) {
+        double* t = rays + ((size_t)f.off + (j & ~31)) * 8 + (j & 31);
+        if (j < f.n) {
+            const int i = s_idx[j];
+            orig[f.off + j] = i;
+            pos[f.off + i] = j;
+            t[0] = s_ts[i];
+#pragma unroll
+            for (int c = 0; c < 7; ++c) t[32 * (c + 1)] = s_val[c][i];
+        } else {  // padding lanes: finite, masked out by n (same fill as the host path)
+            const int last = s_idx[f.n - 1];
+            orig[f.off + j] = j;
+            pos[f.off + j] = j;
+            t[0] = s_ts[last];
+            t[32] = s_val[0][last];
+#pragma unroll
+            for (int c = 2; c < 8; ++c) t[32 * c] = 0.0;
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------
 // probes (tests only): one warp
 __global__ void probe_problem_kernel(DeviceData dd, FrameDesc fd, int NP, double delay, double* out) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -1556,6 +1648,15 @@ void launch_probe_guess(const DeviceData& dd, FrameDesc fd, double delay, int it
         kern<<<1, 32, warp_smem_bytes(SL * 32, true), st>>>(dd, fd, delay, iters, key_prefix, mode,
                                                             d_mk, d_n_exact);
     });
+    g_launches += 1;
+}
+
+void launch_ingest_pixels(const PixelFrame* d_frames, int n_frames, const double* d_points_a,
+                          const double* d_points_b, LensDev lens, double image_rows, double* d_rays,
+                          int32_t* d_orig, int32_t* d_pos, cudaStream_t st) {
+    if (n_frames <= 0) return;
+    ingest_pixels_kernel<<<n_frames, kIngestThreads, 0, st>>>(d_frames, d_points_a, d_points_b, lens,
+                                                               image_rows, d_rays, d_orig, d_pos);
     g_launches += 1;
 }
 

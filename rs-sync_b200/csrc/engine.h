@@ -79,6 +79,23 @@ void launch_sync_trials(const DeviceData& dd, const SyncBatchDev& b, const doubl
                         double* d_task_scratch /* T x ntrial */, double* d_out /* S x ntrial */,
                         cudaStream_t st);
 
+// ---- pixel -> ray front end (track_frames' per-frame tail, core_testcode.cpp:134-161) --------
+struct LensDev {  // Lens, core_testcode.cpp:55-61
+    double ro, fx, fy, cx, cy, k1, k2, k3, k4;
+};
+struct PixelFrame {
+    int32_t off;     // frame's first ray in the arena
+    int32_t n;       // points in the frame
+    int64_t src;     // index of the frame's first point in the pixel buffers
+    double ts_a, ts_b;  // start-of-exposure timestamps of the two frames, seconds
+};
+// One block per frame: undistort both points of every pair (lens_undistort_point, :63-95),
+// rolling-shutter timestamps (:144-145), unit rays (:153-154), sort by ts_a (ties keep the caller's
+// order) and write the frame's tiles and orig / pos planes straight into the device arena.
+void launch_ingest_pixels(const PixelFrame* d_frames, int n_frames, const double* d_points_a,
+                          const double* d_points_b, LensDev lens, double image_rows, double* d_rays,
+                          int32_t* d_orig, int32_t* d_pos, cudaStream_t st);
+
 // ---- stage probes (tests only) ---------------------------------------------------------------
 void launch_probe_problem_matrix(const DeviceData& dd, FrameDesc fd, double delay, double* d_P,
                                  cudaStream_t st);

@@ -144,6 +144,9 @@ def undistort(px, py):
     return x_ * s, y_ * s
 
 
+LENS = (READOUT, FX, FY, CX, CY, K1, K2, K3, K4)  # rssync_lens field order
+
+
 def pixel_to_ray(px, py):
     ux, uy = undistort(px, py)
     v = np.stack([ux, uy, np.ones_like(ux)], axis=-1)
@@ -181,6 +184,8 @@ class Workload:
     sync_window: int = 60
     syncpoint_distance: int = 120
     meta: dict = field(default_factory=dict)
+    px_a: np.ndarray = None    # (F, N, 2) tracked pixel positions in frame f (x, y)
+    px_b: np.ndarray = None    # (F, N, 2) ... and in frame f + 1
 
     @property
     def n_frames(self):
@@ -315,7 +320,9 @@ def make_workload(name="C1", *, frames=None, rays=None, first_frame=None, seed=1
                     presync_radius=p["radius"], presync_step=p["step"], sync_window=sync_window,
                     syncpoint_distance=syncpoint_distance,
                     meta=dict(seed=seed, noise_px=noise_px, outlier_frac=outlier_frac,
-                              span=(int(f0), int(f0 + span_frames))))
+                              span=(int(f0), int(f0 + span_frames))),
+                    px_a=np.ascontiguousarray(np.stack([pa_x, pa_y], axis=-1)),
+                    px_b=np.ascontiguousarray(np.stack([pb_x, pb_y], axis=-1)))
 
 
 # the 48 axis permutation / sign variants of core_testcode.cpp:186-190.  Our mapping (the

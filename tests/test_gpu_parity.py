@@ -463,3 +463,38 @@ int main(int, char** argv) {
     p = g.PreSync(0.0, fb, fb + nf, 0.005, 0.05)
     s = g.Sync(p[1], fb, fb + nf - 1, 0.0, 0.05)
     assert got == [p[0], p[1], s[0], s[1], dd[3], cc[3]]
+
+
+def test_pixel_front_end_matches_host_rays(rsb, oracle_loader, synth_mod):
+    """rssync_set_track_pixels (undistort + rolling-shutter timestamps + unit rays + sort on the device,
+    core_testcode.cpp:63-95,134-161) against the same frames fed as host-computed rays: identical
+    timestamps / ordering, rays equal up to the rounding of tan / cos"""
+    w = synth_mod.make_workload("tiny", rays=130)
+    counts = np.full(w.n_frames, w.n_rays)
+    ta, tb = w.frame_ids / w.fps, (w.frame_ids + 1) / w.fps
+    assert np.array_equal(w.ts_a, ta[:, None] + synth_mod.READOUT * (w.px_a[..., 1] / synth_mod.HEIGHT))
+    ref = rsb.SyncProblem(seed=21).load(w, bulk=True)
+    pix = rsb.SyncProblem(seed=21)
+    pix.SetGyroQuaternions(w.quats, w.quats.shape[0], w.gyro_rate, w.gyro_t0)
+    half = w.n_frames // 2  # two calls: the second grows the device arena, contents preserved
+    for sl in (slice(0, half), slice(half, None)):
+        pix.set_track_pixels(w.frame_ids[sl], counts[sl], ta[sl], tb[sl], w.px_a[sl], w.px_b[sl], synth_mod.LENS,
+                             synth_mod.HEIGHT)
+    assert pix.stats()["frames"] == w.n_frames and pix.stats()["rays"] == w.n_frames * w.n_rays
+    for fid in (int(w.frame_ids[0]), int(w.frame_ids[-1])):
+        a = ref.probe_problem_matrix(fid, 0.02, w.n_rays)
+        b = pix.probe_problem_matrix(fid, 0.02, w.n_rays)
+        assert np.max(np.abs(a - b)) <= 1e-13 * np.max(np.abs(a))
+    fb, fe = int(w.frame_ids[0]), int(w.frame_ids[-1]) + 1
+    delays = np.linspace(-0.04, 0.06, 26)
+    ca = ref.presync_grid(fb, fe, delays, call_no=2)
+    cb = pix.presync_grid(fb, fe, delays, call_no=2)
+    assert rel_err(cb, ca) <= TOL and int(np.argmin(ca)) == int(np.argmin(cb))
+    # a host-side ray frame may replace / follow device-ingested ones
+    pix.SetTrackResult(int(w.frame_ids[1]), w.ts_a[1], w.ts_b[1], w.rays_a[1], w.rays_b[1], w.n_rays)
+    assert rel_err(pix.presync_grid(fb, fe, delays, call_no=2), ca) <= TOL
+    o = oracle_loader.OracleProblem(threads=2, seed=21).load(w)
+    assert rel_err(cb, o.presync_grid(fb, fe, delays, call_no=2)) <= TOL
+    with pytest.raises(rsb.RsSyncError):
+        pix.set_track_pixels(w.frame_ids[:1], counts[:1], ta[:1], tb[:1], w.px_a[:1], w.px_b[:1],
+                             (0.01, 0.0, 1.0, 0, 0, 0, 0, 0, 0), synth_mod.HEIGHT)
