@@ -857,35 +857,50 @@ int rssync_set_track_pixels(rssync_problem* p, size_t n_frames, const int64_t* f
         at[i + 1] = at[i] + counts[i];
     }
     const size_t total = at[n_frames];
-    if (!all_finite(points_a, 2 * total)) { p->err = "set-track-result: non-finite numbers in rays_a"; return RSSYNC_E_NONFINITE; }
-    if (!all_finite(points_b, 2 * total)) { p->err = "set-track-result: non-finite numbers in rays_b"; return RSSYNC_E_NONFINITE; }
     if (!all_finite(frame_ts_a, n_frames)) { p->err = "set-track-result: non-finite numbers in ts_a"; return RSSYNC_E_NONFINITE; }
     if (!all_finite(frame_ts_b, n_frames)) { p->err = "set-track-result: non-finite numbers in ts_b"; return RSSYNC_E_NONFINITE; }
     if (int rc = wait_arena_copies(p)) return rc;
     cudaSetDevice(p->device);
+    CUDA_TRY(p, p->h_pix.reserve(4 * total + 1));
+    // per frame (worker pool): validate, copy into the pinned staging buffer, timestamp bounds with
+    // the device's expression (core_testcode.cpp:144-145)
+    std::vector<int> bad(n_frames, 0);
+    std::vector<double> lo(n_frames, 0.0), hi(n_frames, 0.0);
+    parallel_frames(n_frames, [&](size_t i, size_t) {
+        const double* a = points_a + 2 * at[i];
+        const double* b = points_b + 2 * at[i];
+        const size_t n = counts[i];
+        if (!all_finite(a, 2 * n)) { bad[i] = 1; return; }
+        if (!all_finite(b, 2 * n)) { bad[i] = 2; return; }
+        std::memcpy(p->h_pix.ptr + 2 * at[i], a, 2 * n * sizeof(double));
+        std::memcpy(p->h_pix.ptr + 2 * total + 2 * at[i], b, 2 * n * sizeof(double));
+        double l = 0.0, h = 0.0;
+        for (size_t k = 0; k < n; ++k) {
+            const double ta = frame_ts_a[i] + lens->readout * (a[2 * k + 1] / image_rows);
+            const double tb = frame_ts_b[i] + lens->readout * (b[2 * k + 1] / image_rows);
+            if (k == 0) { l = std::min(ta, tb); h = std::max(ta, tb); }
+            l = std::min(l, std::min(ta, tb));
+            h = std::max(h, std::max(ta, tb));
+        }
+        lo[i] = l;
+        hi[i] = h;
+    });
+    for (size_t i = 0; i < n_frames; ++i)
+        if (bad[i]) {
+            p->err = bad[i] == 1 ? "set-track-result: non-finite numbers in rays_a" : "set-track-result: non-finite numbers in rays_b";
+            return RSSYNC_E_NONFINITE;
+        }
     std::vector<rs::PixelFrame> pf(n_frames);
     for (size_t i = 0; i < n_frames; ++i) {
         FrameDesc* fd = nullptr;
         if (int rc = place_track(p, frames[i], counts[i], &fd)) return rc;
-        // timestamp bounds, with the device's expression (core_testcode.cpp:144-145)
-        double lo = 0.0, hi = 0.0;
-        for (size_t k = 0; k < counts[i]; ++k) {
-            const double ta = frame_ts_a[i] + lens->readout * (points_a[2 * (at[i] + k) + 1] / image_rows);
-            const double tb = frame_ts_b[i] + lens->readout * (points_b[2 * (at[i] + k) + 1] / image_rows);
-            if (k == 0) { lo = std::min(ta, tb); hi = std::max(ta, tb); }
-            lo = std::min(lo, std::min(ta, tb));
-            hi = std::max(hi, std::max(ta, tb));
-        }
-        fd->ts_lo = lo;
-        fd->ts_hi = hi;
+        fd->ts_lo = lo[i];
+        fd->ts_hi = hi[i];
         pf[i] = rs::PixelFrame{fd->off, fd->n, (int64_t)at[i], frame_ts_a[i], frame_ts_b[i]};
     }
     if (int rc = reserve_device_arena(p)) return rc;
-    CUDA_TRY(p, p->h_pix.reserve(4 * total + 1));
     CUDA_TRY(p, p->d_pix.reserve(4 * total + 1));
     CUDA_TRY(p, p->d_pixframes.reserve(n_frames));
-    std::memcpy(p->h_pix.ptr, points_a, 2 * total * sizeof(double));
-    std::memcpy(p->h_pix.ptr + 2 * total, points_b, 2 * total * sizeof(double));
     if (int rc = h2d(p, p->d_pix.ptr, p->h_pix.ptr, 4 * total * sizeof(double))) return rc;
     if (int rc = h2d(p, p->d_pixframes.ptr, pf.data(), n_frames * sizeof(rs::PixelFrame))) return rc;
     CUDA_TRY(p, cudaStreamSynchronize(p->stream));  // pf is a local; the pinned staging buffer is reused
