@@ -156,8 +156,9 @@ struct rssync_problem {
     DevBuf<uint64_t> d_frame_call;
     // pixel front end staging
     PinBuf<double> h_pix;
-    DevBuf<double> d_pix;
+    DevBuf<double> d_pix, d_stage;
     DevBuf<rs::PixelFrame> d_pixframes;
+    std::vector<rs::PixelFrame> pixframes_host;  // source of an async copy: lives with the problem
     DevBuf<int> d_win_begin;
     DevBuf<unsigned> d_flags;
     PinBuf<double> h_stage;
@@ -533,7 +534,7 @@ void rssync_destroy(rssync_problem* p) {
     p->h_pos.release(); p->d_pos.release();
     p->d_frames.release(); p->d_delays.release(); p->d_framecost.release(); p->d_costs.release();
     p->d_frame_call.release(); p->d_win_begin.release();
-    p->h_pix.release(); p->d_pix.release(); p->d_pixframes.release();
+    p->h_pix.release(); p->d_pix.release(); p->d_pixframes.release(); p->d_stage.release();
     p->d_flags.release(); p->h_stage.release(); p->d_tasks.release(); p->d_sp_begin.release();
     p->d_lbfgs_stats.release(); p->d_m.release(); p->d_k.release(); p->d_task_scratch.release();
     p->d_sp_delay.release(); p->d_sp_x0.release(); p->d_trial_delay.release(); p->d_out_v.release();
@@ -791,40 +792,64 @@ int rssync_set_track_batch(rssync_problem* p, size_t n_frames, const int64_t* fr
         if (rc[i]) { n_ok = i; break; }
     if (int r = wait_arena_copies(p)) return r;
     std::vector<FrameDesc*> fds(n_ok);
-    bool run = true;  // the batch occupies one contiguous run of the arena, in order
-    for (size_t i = 0; i < n_ok; ++i) {
+    for (size_t i = 0; i < n_ok; ++i)
         if (int r = place_track(p, frames[i], counts[i], &fds[i])) return r;
-        run = run && (i == 0 || (size_t)fds[i]->off == (size_t)fds[i - 1]->off + (counts[i - 1] + 31) / 32 * 32);
-    }
     auto frame_end = [&](size_t i) { return (size_t)fds[i]->off + (counts[i] + 31) / 32 * 32; };
-    // Eager upload: when the batch is one contiguous run of the arena (an append, or the same
-    // frames set again in place), the arena range of each chunk of frames is copied to the device
-    // as soon as the chunk is filled, so the copy of chunk k overlaps the sort/transpose of
-    // chunk k + 1.  Otherwise the ranges are left for the next flush.
-    bool eager = run && n_ok >= 64;
-    if (eager) {
+    if (n_ok >= 64) {
+        // Large batch: the sort by ts_a and the transpose into tiles run on the device
+        // (ingest_rays_kernel).  The host only copies the caller's buffers into pinned staging
+        // memory and takes the per-frame timestamp bounds; each sixth of the batch is copied to the
+        // device and ingested as soon as it is staged, overlapping the staging of the next.
         cudaSetDevice(p->device);
+        const size_t total = at[n_ok];
         if (int r = reserve_device_arena(p)) return r;
+        CUDA_TRY(p, p->h_stage.reserve(8 * total + 1));
+        CUDA_TRY(p, p->d_stage.reserve(8 * total + 1));
+        CUDA_TRY(p, p->d_pixframes.reserve(n_ok));
         if (!p->ev_arena) CUDA_TRY(p, cudaEventCreateWithFlags(&p->ev_arena, cudaEventDisableTiming));
-    }
-    std::vector<std::vector<std::pair<double, int32_t>>> scratch(17);
-    const size_t n_chunks = eager ? 6 : 1;
-    for (size_t c = 0; c < n_chunks; ++c) {
-        const size_t lo = n_ok * c / n_chunks, hi = n_ok * (c + 1) / n_chunks;
-        if (lo == hi) continue;
-        parallel_frames(hi - lo, [&](size_t k, size_t t) {
-            const size_t i = lo + k;
-            fill_track(p, fds[i], ts_a + at[i], ts_b + at[i], rays_a + 3 * at[i], rays_b + 3 * at[i], counts[i], scratch[t]);
-        });
-        if (eager) {
-            if (int r = upload_arena_range(p, (size_t)fds[lo]->off, frame_end(hi - 1))) return r;
-        } else {
-            for (size_t i = lo; i < hi; ++i) add_pending(p, (size_t)fds[i]->off, frame_end(i));
+        std::vector<rs::PixelFrame>& pf = p->pixframes_host;
+        pf.resize(n_ok);
+        for (size_t i = 0; i < n_ok; ++i) pf[i] = rs::PixelFrame{fds[i]->off, fds[i]->n, (int64_t)at[i], 0.0, 0.0};
+        if (int r = h2d(p, p->d_pixframes.ptr, pf.data(), n_ok * sizeof(rs::PixelFrame))) return r;
+        double* hs = p->h_stage.ptr;
+        double* ds = p->d_stage.ptr;
+        const size_t n_chunks = 6;
+        for (size_t c = 0; c < n_chunks; ++c) {
+            const size_t lo = n_ok * c / n_chunks, hi = n_ok * (c + 1) / n_chunks;
+            if (lo == hi) continue;
+            parallel_frames(hi - lo, [&](size_t k, size_t) {
+                const size_t i = lo + k, n = counts[i], a = at[i];
+                std::memcpy(hs + a, ts_a + a, n * sizeof(double));
+                std::memcpy(hs + total + a, ts_b + a, n * sizeof(double));
+                std::memcpy(hs + 2 * total + 3 * a, rays_a + 3 * a, 3 * n * sizeof(double));
+                std::memcpy(hs + 5 * total + 3 * a, rays_b + 3 * a, 3 * n * sizeof(double));
+                double l = n ? ts_a[a] : 0.0, h = l;
+                for (size_t j = 0; j < n; ++j) {
+                    l = std::min(l, std::min(ts_a[a + j], ts_b[a + j]));
+                    h = std::max(h, std::max(ts_a[a + j], ts_b[a + j]));
+                }
+                fds[i]->ts_lo = l;
+                fds[i]->ts_hi = h;
+            });
+            const size_t a = at[lo], n = at[hi] - at[lo];
+            if (int r = h2d(p, ds + a, hs + a, n * sizeof(double))) return r;
+            if (int r = h2d(p, ds + total + a, hs + total + a, n * sizeof(double))) return r;
+            if (int r = h2d(p, ds + 2 * total + 3 * a, hs + 2 * total + 3 * a, 3 * n * sizeof(double))) return r;
+            if (int r = h2d(p, ds + 5 * total + 3 * a, hs + 5 * total + 3 * a, 3 * n * sizeof(double))) return r;
+            rs::launch_ingest_rays(p->d_pixframes.ptr + lo, (int)(hi - lo), ds, ds + total, ds + 2 * total,
+                                   ds + 5 * total, p->d_rays.ptr, p->d_orig.ptr, p->d_pos.ptr, p->stream);
+            CUDA_TRY(p, cudaGetLastError());
         }
-    }
-    if (eager) {
+        p->dev_used = std::max(p->dev_used, p->used);
+        // the staging buffers are reused by the next ingest call, which waits for this event
         CUDA_TRY(p, cudaEventRecord(p->ev_arena, p->stream));
         p->arena_copy_pending = true;
+    } else {
+        std::vector<std::pair<double, int32_t>> scratch;
+        for (size_t i = 0; i < n_ok; ++i) {
+            fill_track(p, fds[i], ts_a + at[i], ts_b + at[i], rays_a + 3 * at[i], rays_b + 3 * at[i], counts[i], scratch);
+            add_pending(p, (size_t)fds[i]->off, frame_end(i));
+        }
     }
     if (n_ok < n_frames) { p->err = msg[n_ok]; return rc[n_ok]; }
     return RSSYNC_OK;

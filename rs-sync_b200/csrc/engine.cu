@@ -1338,6 +1338,49 @@ __device__ __forceinline__ void undistort_point(const LensDev& L, double px, dou
 }
 
 constexpr int kIngestThreads = 256;
+// block-wide: sort the frame's points by (ts_a, caller index) -- the order std::sort gives the host
+// path -- and write the frame's tiles [8 fields][32 rays] and its orig / pos planes to the arena
+__device__ __forceinline__ void ingest_sort_and_store(const PixelFrame& f, const double* s_ts, int* s_idx,
+                                                      const double (*s_val)[kMaxRaysPerFrame],
+                                                      double* __restrict__ rays, int32_t* __restrict__ orig,
+                                                      int32_t* __restrict__ pos) {
+    int nsort = 32;  // power of two covering the frame
+    while (nsort < f.n) nsort <<= 1;
+    for (int k = 2; k <= nsort; k <<= 1)
+        for (int j = k >> 1; j > 0; j >>= 1) {
+            for (int i = threadIdx.x; i < nsort; i += kIngestThreads) {
+                const int l = i ^ j;
+                if (l > i) {
+                    const int a = s_idx[i], b = s_idx[l];
+                    const double ta = s_ts[a], tb = s_ts[b];
+                    const bool a_first = ta < tb || (ta == tb && a < b);
+                    const bool up = (i & k) == 0;
+                    if (a_first != up) { s_idx[i] = b; s_idx[l] = a; }
+                }
+            }
+            __syncthreads();
+        }
+    const int padded = (f.n + 31) / 32 * 32;
+    for (int j = threadIdx.x; j < padded; j += kIngestThreads) {
+        double* t = rays + ((size_t)f.off + (j & ~31)) * 8 + (j & 31);
+        if (j < f.n) {
+            const int i = s_idx[j];
+            orig[f.off + j] = i;
+            pos[f.off + i] = j;
+            t[0] = s_ts[i];
+#pragma unroll
+            for (int c = 0; c < 7; ++c) t[32 * (c + 1)] = s_val[c][i];
+        } else {  // padding lanes: finite, masked out by n (same fill as the host path)
+            const int last = f.n ? s_idx[f.n - 1] : 0;
+            orig[f.off + j] = j;
+            pos[f.off + j] = j;
+            t[0] = f.n ? s_ts[last] : 0.0;
+            t[32] = f.n ? s_val[0][last] : 0.0;
+#pragma unroll
+            for (int c = 2; c < 8; ++c) t[32 * c] = 0.0;
+        }
+    }
+}
 __global__ void __launch_bounds__(kIngestThreads)
 ingest_pixels_kernel(const PixelFrame* __restrict__ frames, const double* __restrict__ pa,
                      const double* __restrict__ pb, LensDev L, double rows, double* __restrict__ rays,
@@ -1364,41 +1407,33 @@ ingest_pixels_kernel(const PixelFrame* __restrict__ frames, const double* __rest
         }
     }
     __syncthreads();
-    // bitonic sort of the index permutation by (ts_a, index): the order std::sort gives the host path
-    for (int k = 2; k <= kMaxRaysPerFrame; k <<= 1)
-        for (int j = k >> 1; j > 0; j >>= 1) {
-            for (int i = threadIdx.x; i < kMaxRaysPerFrame; i += kIngestThreads) {
-                const int l = i ^ j;
-                if (l > i) {
-                    const int a = s_idx[i], b = s_idx[l];
-                    const double ta = s_ts[a], tb = s_ts[b];
-                    const bool a_first = ta < tb || (ta == tb && a < b);
-                    const bool up = (i & k) == 0;
-                    if (a_first != up) { s_idx[i] = b; s_idx[l] = a; }
-                }
-            }
-            __syncthreads();
-        }
-    const int padded = (f.n + 31) / 32 * 32;
-    for (int j = threadIdx.x; j < padded; j += kIngestThreads) {
-        double* t = rays + ((size_t)f.off + (j & ~31)) * 8 + (j & 31);
-        if (j < f.n) {
-            const int i = s_idx[j];
-            orig[f.off + j] = i;
-            pos[f.off + i] = j;
-            t[0] = s_ts[i];
-#pragma unroll
-            for (int c = 0; c < 7; ++c) t[32 * (c + 1)] = s_val[c][i];
-        } else {  // padding lanes: finite, masked out by n (same fill as the host path)
-            const int last = s_idx[f.n - 1];
-            orig[f.off + j] = j;
-            pos[f.off + j] = j;
-            t[0] = s_ts[last];
-            t[32] = s_val[0][last];
-#pragma unroll
-            for (int c = 2; c < 8; ++c) t[32 * c] = 0.0;
+    ingest_sort_and_store(f, s_ts, s_idx, s_val, rays, orig, pos);
+}
+
+// the same with the rays already computed by the caller (SetTrackResult's layouts)
+__global__ void __launch_bounds__(kIngestThreads)
+ingest_rays_kernel(const PixelFrame* __restrict__ frames, const double* __restrict__ ts_a,
+                   const double* __restrict__ ts_b, const double* __restrict__ ra,
+                   const double* __restrict__ rb, double* __restrict__ rays, int32_t* __restrict__ orig,
+                   int32_t* __restrict__ pos) {
+    __shared__ double s_ts[kMaxRaysPerFrame];
+    __shared__ int s_idx[kMaxRaysPerFrame];
+    __shared__ double s_val[7][kMaxRaysPerFrame];
+    const PixelFrame f = frames[blockIdx.x];
+    for (int i = threadIdx.x; i < kMaxRaysPerFrame; i += kIngestThreads) {
+        s_idx[i] = i;
+        if (i < f.n) {
+            const size_t g = (size_t)f.src + i;
+            s_ts[i] = ts_a[g];
+            s_val[0][i] = ts_b[g];
+            s_val[1][i] = ra[3 * g]; s_val[2][i] = ra[3 * g + 1]; s_val[3][i] = ra[3 * g + 2];
+            s_val[4][i] = rb[3 * g]; s_val[5][i] = rb[3 * g + 1]; s_val[6][i] = rb[3 * g + 2];
+        } else {
+            s_ts[i] = __longlong_as_double(0x7ff0000000000000LL);
         }
     }
+    __syncthreads();
+    ingest_sort_and_store(f, s_ts, s_idx, s_val, rays, orig, pos);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -1657,6 +1692,15 @@ void launch_ingest_pixels(const PixelFrame* d_frames, int n_frames, const double
     if (n_frames <= 0) return;
     ingest_pixels_kernel<<<n_frames, kIngestThreads, 0, st>>>(d_frames, d_points_a, d_points_b, lens,
                                                                image_rows, d_rays, d_orig, d_pos);
+    g_launches += 1;
+}
+
+void launch_ingest_rays(const PixelFrame* d_frames, int n_frames, const double* d_ts_a,
+                        const double* d_ts_b, const double* d_rays_a, const double* d_rays_b,
+                        double* d_rays, int32_t* d_orig, int32_t* d_pos, cudaStream_t st) {
+    if (n_frames <= 0) return;
+    ingest_rays_kernel<<<n_frames, kIngestThreads, 0, st>>>(d_frames, d_ts_a, d_ts_b, d_rays_a, d_rays_b,
+                                                             d_rays, d_orig, d_pos);
     g_launches += 1;
 }
 

@@ -96,6 +96,14 @@ void launch_ingest_pixels(const PixelFrame* d_frames, int n_frames, const double
                           const double* d_points_b, LensDev lens, double image_rows, double* d_rays,
                           int32_t* d_orig, int32_t* d_pos, cudaStream_t st);
 
+// SetTrackResult for a batch of frames with the sort + transpose on the device: the callers' buffers
+// (ts_a, ts_b: n doubles; rays_a, rays_b: n x 3 doubles, concatenated over frames) are staged as they
+// are; one block per frame sorts by (ts_a, caller index) and writes tiles + orig / pos planes.
+// PixelFrame::src is the index of the frame's first ray in the staged buffers; ts_a / ts_b unused.
+void launch_ingest_rays(const PixelFrame* d_frames, int n_frames, const double* d_ts_a,
+                        const double* d_ts_b, const double* d_rays_a, const double* d_rays_b,
+                        double* d_rays, int32_t* d_orig, int32_t* d_pos, cudaStream_t st);
+
 // ---- stage probes (tests only) ---------------------------------------------------------------
 void launch_probe_problem_matrix(const DeviceData& dd, FrameDesc fd, double delay, double* d_P,
                                  cudaStream_t st);
