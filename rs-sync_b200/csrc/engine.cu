@@ -3,22 +3,23 @@
 // Decomposition: ONE WARP PER (delay, frame) TASK.  A frame carries N <= 512 rays; lane l owns
 // rays l, l+32, ... ("slots").  A task runs in phases that each keep their working set where it
 // is cheapest:
-//   A  rows      rays + timestamps (SoA planes, coalesced 256 B per plane per slot) -> rows of
-//                the problem matrix (opt_compute_problem, core_private.cpp:15-32) -> the warp's
-//                slice of shared memory (raw rows + 1/|row|); a run-time loop over slots so the
-//                heavy body (2 spline evaluations, 2 de-rotations, 1 division) exists once in
-//                the instruction stream.
+//   A  rows      ray tiles + the spline window (PreSync: staged in shared memory by TMA bulk
+//                copies; Sync: global loads) -> rows of the problem matrix (opt_compute_problem,
+//                core_private.cpp:15-32) -> the warp's slice of shared memory (binary64 rows, and
+//                for the estimator an fp32 row-normalised copy); a run-time loop over slots so the
+//                heavy body (2 spline evaluations, 2 de-rotations, 1 division) exists once in the
+//                instruction stream.
 //   B  hypotheses  lanes 0..19 each build one plane normal from two random rows
-//   C  test       normalised rows in registers (compile-time SLOTS), hypotheses broadcast by
-//                shuffle, quartile test by count + REDUX, exact quartile by a 32-bit-key
-//                quickselect only for hypotheses that win (opt_guess_translational_motion, :34-59)
+//   C  estimator  opt_guess_translational_motion (:34-59) as an fp32x2 tournament with a rigorous
+//                error margin; comparisons it cannot call are settled in binary64
 //   D  loss       robust loss of the winning normal, double-double warp sums (pre_sync body
 //                :79-85 / FrameState::Loss :92-123).
-// Cross-lane work is warp shuffles / REDUX only; there is no block-level synchronisation.
-// Instruction-cache footprint matters as much as FP64 issue here (the first version of this
-// kernel, fully unrolled over slots, was 91 KB of SASS and stalled 40 % of the time on
-// instruction fetch, profiles/r01_presync_v1.md): heavy bodies are written once, inside
-// run-time loops or __noinline__ functions.  The arithmetic contract is in device_math.cuh.
+// Cross-lane work is warp shuffles / REDUX only; the one block-level mechanism is the mbarrier
+// pipeline that stages phase A's inputs (presync_kernel).
+// Instruction fetch matters as much as FP64 issue here (the first version of this kernel, fully
+// unrolled over slots, was 91 KB of SASS and stalled 40 % of the time on instruction fetch,
+// profiles/r01_presync_v1.md; unrolling phase A by two still costs 12 %): heavy bodies are written
+// once, cold paths are __noinline__.  The arithmetic contract is in device_math.cuh.
 #include "engine.h"
 
 #include <algorithm>
@@ -31,8 +32,6 @@ namespace rs {
 
 namespace {
 
-#define RS_PRAGMA_(x) _Pragma(#x)
-#define RS_PRAGMA(x) RS_PRAGMA_(x)
 constexpr unsigned FULL = 0xffffffffu;
 #ifndef RS_WPB
 #define RS_WPB 8
@@ -41,7 +40,6 @@ constexpr unsigned FULL = 0xffffffffu;
 #define RS_MINB 3
 #endif
 constexpr int kWarpsPerBlock = RS_WPB;
-constexpr unsigned kNanHi = 0x7ff80000u;  // hi word of the canonical NaN: sorts above every r^2
 
 std::atomic<uint64_t> g_launches{0};
 
@@ -194,9 +192,6 @@ __device__ __forceinline__ unsigned build_rows_staged(const DeviceData& dd, cons
     float fin = 0.f;
     const int nslots = (fd.n + 31) >> 5;
     const int NPAIR = pairs_for(NP);
-#ifdef RS_UNROLL_A
-    RS_PRAGMA(unroll RS_UNROLL_A)
-#endif
     for (int s = 0; s < nslots; ++s) {
         const int i = s * 32 + lane;
         const double* t = sTiles + s * 256 + lane;
@@ -699,9 +694,6 @@ __device__ __forceinline__ void warp_ransac(const DeviceData& dd, const FrameDes
     const bool ok = rows_finite && warp_ransac_fast<SLOTS>(dd, fd, w, iters, key, lane, M, &settled);
     if (n_exact && settled && lane == 0) atomicAdd(n_exact, 1u);  // tasks that needed binary64
     if (ok) return;
-#ifdef RS_EXPERIMENT_NO_COLD  // timing experiment only: wrong results for undecided tasks
-    return;
-#endif
     if (n_exact && !settled && lane == 0) atomicAdd(n_exact, 1u);
     const Vec3 e = warp_ransac_exact<SLOTS>(dd, fd, w, iters, key, lane);
     M[0] = e.x; M[1] = e.y; M[2] = e.z;
@@ -1039,11 +1031,7 @@ __device__ __noinline__ void presync_stage_unit(const DeviceData& dd, const Fram
 }
 
 template <int SLOTS>
-#ifdef RS_PRESYNC_MAXNREG
-__global__ void __maxnreg__(RS_PRESYNC_MAXNREG)
-#else
 __global__ void __launch_bounds__(PresyncCfg<SLOTS>::kWarps * 32, PresyncCfg<SLOTS>::kMinBlocks)
-#endif
 presync_kernel(DeviceData dd, const FrameDesc* __restrict__ frames, int F,
                const double* __restrict__ delays, int D, int chunk, int cpf, uint64_t seed,
                uint64_t stream, uint64_t call_no, const uint64_t* __restrict__ frame_call_no,
@@ -1082,12 +1070,8 @@ presync_kernel(DeviceData dd, const FrameDesc* __restrict__ frames, int F,
         double delay = 0.0;
         if (active) {
             delay = delays[di];
-#ifdef RS_EXPERIMENT_NO_COLD
-            bad = build_rows_staged(dd, fd, delay, lane, w, NP, sTiles, sRec, rec_first, rec_cnt);
-#else
             bad = rec_cnt ? build_rows_staged(dd, fd, delay, lane, w, NP, sTiles, sRec, rec_first, rec_cnt)
                           : build_rows_global_cold(dd, fd, delay, lane, w, NP);
-#endif
             bad = __reduce_or_sync(FULL, bad);
         }
         __syncwarp();
