@@ -166,6 +166,23 @@ def cpu_baseline(w, delays, seconds):
                       f"({n_off * w.n_frames * w.n_rays:.3g} cells, {dt:.1f} s)"}
 
 
+def full_size_parity(prob, w, delays, pkg):
+    """The checker at the bench's full frame count: a few offsets of the timed grid recomputed by the
+    oracle port (same arithmetic contract and RNG keys) and compared with the engine's values."""
+    from oracle import loader
+    threads = os.cpu_count() or 1
+    o = loader.OracleProblem(threads=threads, seed=100).load(w)
+    fb, fe = int(w.frame_ids[0]), int(w.frame_ids[-1]) + 1
+    pick = [0, len(delays) // 2, len(delays) - 1]
+    worst = 0.0
+    for i in pick:
+        g = prob.presync_grid(fb, fe, delays[i:i + 1], stream=pkg.STREAM_DEBUG, call_no=77, offset_index_base=i)
+        c = o.presync_grid(fb, fe, delays[i:i + 1], stream=2, call_no=77, offset_index_base=i)
+        worst = max(worst, abs(float(g[0]) - float(c[0])) / abs(float(c[0])))
+    return {"offsets_checked": len(pick), "frames": w.n_frames, "max_rel_err_vs_oracle": worst, "tolerance": 1e-9,
+            "ok": bool(worst <= 1e-9)}
+
+
 def cpu_sync_baseline(w):
     """syncpoints/s of the CPU arm on ONE syncpoint (PreSync on the window + 4 chained Sync, all host
     threads over frames like the reference's par loops).  The oracle port is used: the reference
@@ -344,6 +361,7 @@ def run_b200(args):
 
     if rank == 0 and world >= 1 and not args.no_cpu and world == 1:
         out["cpu_baseline"] = cpu_baseline(w, delays, args.cpu_seconds)
+        out["cpu_baseline"]["parity"] = full_size_parity(prob, w, delays, pkg)
         if not args.no_sync:
             out["cpu_baseline"]["sync"] = cpu_sync_baseline(w)
     elif rank == 0 and not args.no_cpu:
