@@ -30,6 +30,28 @@ namespace {
 struct Frame {
     int n = 0;
     std::vector<double> ts_a, ts_b, ra, rb;  // ra/rb: xyz interleaved, 3*n
+    std::vector<int> order;  // ray indices sorted by (ts_a, index): the spec's summation order
+};
+
+// Sums over the rays of one frame (the spec; stands in for arma::accu / arma::sum / arma::norm's
+// inner sum, core_private.cpp:79,85,122; inline_utils.hpp:32-36, whose order is Armadillo's
+// business).  The rays are visited in the order (ts_a, caller index); ray j of that order is added
+// to partial sum j % 32, and the 32 partial sums are combined by an xor butterfly (strides 16, 8,
+// 4, 2, 1).  A fixed order, so the value is reproducible bit for bit -- it is the order in which a
+// warp whose lane l owns rays l, l + 32, ... adds them up.
+struct RaySum {
+    double lane[32];
+    RaySum() { for (double& x : lane) x = 0.0; }
+    inline void add(int j, double x) { lane[j & 31] += x; }
+    double value() const {
+        double a[32], b[32];
+        for (int l = 0; l < 32; ++l) a[l] = lane[l];
+        for (int off = 16; off >= 1; off >>= 1) {
+            for (int l = 0; l < 32; ++l) b[l] = a[l] + a[l ^ off];
+            for (int l = 0; l < 32; ++l) a[l] = b[l];
+        }
+        return a[0];
+    }
 };
 
 struct Oracle {
@@ -150,11 +172,11 @@ void guess_motion(const double* P, int n, int iters, uint64_t key, double best[3
     }
 }
 
-double norm_PM(const double* P, int n, const double m[3]) {  // arma::norm(P * M)
-    DD ss;
-    for (int i = 0; i < n; ++i) {
-        double pm = dot3(P + 3 * i, m);
-        ss.add(pm * pm);
+double norm_PM(const double* P, int n, const int* order, const double m[3]) {  // arma::norm(P * M)
+    RaySum ss;
+    for (int j = 0; j < n; ++j) {
+        double pm = dot3(P + 3 * order[j], m);
+        ss.add(j, pm * pm);
     }
     return std::sqrt(ss.value());
 }
@@ -177,15 +199,15 @@ double presync_frame_cost(const Oracle& o, const Frame& f, double delay, uint64_
         }
         return std::sqrt(acc);
     }
-    double k = clamp_k(1.0 / norm_PM(P.data(), f.n, M) * 1e2);  // :79
-    double scale = k / std::sqrt(dot3(M, M));                     // :80
-    DD acc;
-    for (int i = 0; i < f.n; ++i) {
-        double r = dot3(&P[3 * i], M) * scale;
+    double k = clamp_k(1.0 / norm_PM(P.data(), f.n, f.order.data(), M) * 1e2);  // :79
+    double scale = k / std::sqrt(dot3(M, M));                                      // :80
+    RaySum acc;
+    for (int j = 0; j < f.n; ++j) {
+        double r = dot3(&P[3 * f.order[j]], M) * scale;
         if (flags && !std::isfinite(r)) *flags |= 4;
         double rho = log1p_nonneg(r * r);  // :82
         if (flags && !std::isfinite(rho)) *flags |= 8;
-        acc.add(std::sqrt(rho));
+        acc.add(j, std::sqrt(rho));
     }
     return std::sqrt(acc.value());  // :85
 }
@@ -267,41 +289,41 @@ struct FrameState {
 };
 
 // FrameState::Loss, 3-argument form (core_private.cpp:117-123), on a prebuilt P.
-double loss3_P(const double* P, int n, const double m[3], double k) {
+double loss3_P(const double* P, int n, const int* order, const double m[3], double k) {
     double scale = k / std::sqrt(dot3(m, m));
-    DD acc;
-    for (int i = 0; i < n; ++i) {
-        double r = dot3(P + 3 * i, m) * scale;
-        acc.add(log1p_nonneg(r * r));
+    RaySum acc;
+    for (int j = 0; j < n; ++j) {
+        double r = dot3(P + 3 * order[j], m) * scale;
+        acc.add(j, log1p_nonneg(r * r));
     }
     return acc.value();
 }
 double loss3(const Oracle& o, const Frame& f, double delay, const double m[3], double k) {
     std::vector<double> P((size_t)f.n * 3);
     problem_matrix(o, f, delay, P.data());
-    return o.strict ? orc_strict::loss3_P(P.data(), f.n, m, k) : loss3_P(P.data(), f.n, m, k);
+    return o.strict ? orc_strict::loss3_P(P.data(), f.n, m, k) : loss3_P(P.data(), f.n, f.order.data(), m, k);
 }
 
 // FrameState::Loss, 5-argument form (core_private.cpp:92-115): value and d/dm in closed form
 // of the forward-mode chain (inline_utils.hpp:19-48):
 //   v1 = P m, den = |m|^2 / k^2, u_i = v1_i^2 / den, loss = sum log1p(u_i)
 //   grad = sum_i 1/(1+u_i) * ( (2 v1_i / den) P_i - (v1_i^2 / den^2) (1/k^2) (2 m) )
-double loss5_P(const double* P, int n, const double m[3], double k, double grad[3]) {
+double loss5_P(const double* P, int n, const int* order, const double m[3], double k, double grad[3]) {
     const double kk = k * k;
     const double den = dot3(m, m) / kk;
     const double inv_den = 1.0 / den;
-    DD L, g0, g1, g2, su;
-    for (int i = 0; i < n; ++i) {
-        const double* p = P + 3 * i;
+    RaySum L, g0, g1, g2, su;
+    for (int j = 0; j < n; ++j) {
+        const double* p = P + 3 * order[j];
         double v1 = dot3(p, m);
         double u = (v1 * v1) * inv_den;
-        L.add(log1p_nonneg(u));
+        L.add(j, log1p_nonneg(u));
         double w = 1.0 / (1.0 + u);
         double wv = w * v1;
-        g0.add(wv * p[0]);
-        g1.add(wv * p[1]);
-        g2.add(wv * p[2]);
-        su.add(w * u);
+        g0.add(j, wv * p[0]);
+        g1.add(j, wv * p[1]);
+        g2.add(j, wv * p[2]);
+        su.add(j, w * u);
     }
     const double c1 = 2.0 * inv_den;
     const double c2 = (c1 / kk) * su.value();
@@ -434,7 +456,7 @@ int sync_impl(Oracle& o, double initial_delay, int64_t fb, int64_t fe, double ce
         uint64_t key = rng_task_key(o.seed, kStreamSyncInit, call_no, 0, s.id);
         guess_motion(P.data(), s.f->n, 200, key, s.m, nP, r2, strict);
         s.k = strict ? clamp_k(1 / orc_strict::norm_PM(P.data(), s.f->n, s.m) * 1e2)
-                     : clamp_k(1.0 / norm_PM(P.data(), s.f->n, s.m) * 1e2);
+                     : clamp_k(1.0 / norm_PM(P.data(), s.f->n, s.f->order.data(), s.m) * 1e2);
     });
     n_build += (long)fs.size();
 
@@ -460,7 +482,7 @@ int sync_impl(Oracle& o, double initial_delay, int64_t fb, int64_t fe, double ce
             double g[3];
             problem_matrix(o, *s.f, x, P.data());
             v[j] = strict ? orc_strict::loss5_P(P.data(), s.f->n, s.m, s.k, g)
-                          : loss5_P(P.data(), s.f->n, s.m, s.k, g);
+                          : loss5_P(P.data(), s.f->n, s.f->order.data(), s.m, s.k, g);
             l[j] = loss3(o, *s.f, x - h, s.m, s.k);
             r[j] = loss3(o, *s.f, x + h, s.m, s.k);
         });
@@ -496,7 +518,7 @@ int sync_impl(Oracle& o, double initial_delay, int64_t fb, int64_t fe, double ce
                 lbfgs3([&](const double* x, double* g) { return orc_strict::loss5_P(P.data(), n, x, k, g); },
                        s.m, &st[j], DotStrict());
             else
-                lbfgs3([&](const double* x, double* g) { return loss5_P(P.data(), n, x, k, g); }, s.m,
+                lbfgs3([&](const double* x, double* g) { return loss5_P(P.data(), n, s.f->order.data(), x, k, g); }, s.m,
                        &st[j]);
         });
         for (auto& t : st) { n_lbfgs_eval += t.evals; n_lbfgs_iter += t.iters; }
@@ -633,6 +655,11 @@ int orc_set_track(void* h, int64_t frame, const double* ts_a, const double* ts_b
     f.ts_b.assign(ts_b, ts_b + count);
     f.ra.assign(rays_a, rays_a + 3 * count);
     f.rb.assign(rays_b, rays_b + 3 * count);
+    f.order.resize(count);
+    for (size_t i = 0; i < count; ++i) f.order[i] = (int)i;
+    std::sort(f.order.begin(), f.order.end(), [&](int a, int b) {
+        return f.ts_a[a] < f.ts_a[b] || (f.ts_a[a] == f.ts_a[b] && a < b);
+    });
     return OK;
 }
 
@@ -747,7 +774,7 @@ int orc_guess_motion(void* h, int64_t frame, double delay, int iters, uint64_t s
     guess_motion(P.data(), f.n, iters, rng_task_key(o.seed, stream, call_no, offset_idx, frame), m,
                  nP, r2, o.strict);
     if (k) *k = o.strict ? clamp_k(1 / orc_strict::norm_PM(P.data(), f.n, m) * 1e2)
-                         : clamp_k(1.0 / norm_PM(P.data(), f.n, m) * 1e2);
+                         : clamp_k(1.0 / norm_PM(P.data(), f.n, f.order.data(), m) * 1e2);
     return OK;
 }
 int orc_loss3(void* h, int64_t frame, double delay, const double* m, double k, double* out) {
@@ -765,7 +792,7 @@ int orc_loss5(void* h, int64_t frame, double delay, const double* m, double k, d
     std::vector<double> P((size_t)it->second.n * 3);
     problem_matrix(o, it->second, delay, P.data());
     *out = o.strict ? orc_strict::loss5_P(P.data(), it->second.n, m, k, grad)
-                    : loss5_P(P.data(), it->second.n, m, k, grad);
+                    : loss5_P(P.data(), it->second.n, it->second.order.data(), m, k, grad);
     return OK;
 }
 int orc_lbfgs(void* h, int64_t frame, double delay, double* m, double k, double* fout, int* iters,
@@ -777,7 +804,7 @@ int orc_lbfgs(void* h, int64_t frame, double delay, double* m, double k, double*
     std::vector<double> P((size_t)f.n * 3);
     problem_matrix(o, f, delay, P.data());
     LbfgsStats st;
-    double v = lbfgs3([&](const double* x, double* g) { return loss5_P(P.data(), f.n, x, k, g); }, m, &st);
+    double v = lbfgs3([&](const double* x, double* g) { return loss5_P(P.data(), f.n, f.order.data(), x, k, g); }, m, &st);
     if (fout) *fout = v;
     if (iters) *iters = st.iters;
     if (evals) *evals = st.evals;

@@ -13,7 +13,9 @@
 
 namespace rs {
 
-// ---- double-double accumulation (arma::accu / arma::sum / arma::norm inner sums) -------------
+// ---- double-double accumulation: the sums over FRAMES (the mutex-guarded `cost +=` of
+// core_private.cpp:84-85, 235-237, 248-249), whose value must not depend on how frames are spread
+// over warps, blocks or GPUs ----------------------------------------------------------------------
 struct DD {
     double hi, lo;
 };
@@ -43,6 +45,29 @@ __device__ __noinline__ double warp_dd_sum(DD a) {
         dd_merge(a, b);
     }
     return a.hi + a.lo;
+}
+
+// ---- sums over the rays of one frame (arma::accu / arma::sum / arma::norm inner sums) ----------
+// Contract: the frame's rays in storage order (sorted by (ts_a, caller index)); ray j is added to
+// partial sum j % 32 -- lane l of the warp, which owns rays l, l + 32, ... and adds them in that
+// order starting from 0.0 -- and the 32 partial sums are combined by this xor butterfly (strides 16,
+// 8, 4, 2, 1; a + b == b + a, so every lane ends with the same value).  The oracle adds in the same
+// order (RaySum).
+__device__ __forceinline__ double warp_sum(double a) {
+#pragma unroll
+    for (int off = 16; off >= 1; off >>= 1) a = a + __shfl_xor_sync(0xffffffffu, a, off);
+    return a;
+}
+template <int N>
+__device__ __forceinline__ void warp_sum_n(double (&a)[N]) {
+#pragma unroll
+    for (int off = 16; off >= 1; off >>= 1) {
+        double b[N];
+#pragma unroll
+        for (int j = 0; j < N; ++j) b[j] = __shfl_xor_sync(0xffffffffu, a[j], off);
+#pragma unroll
+        for (int j = 0; j < N; ++j) a[j] = a[j] + b[j];
+    }
 }
 
 // ---- log1p on x >= 0 (arma::log1p at core_private.cpp:82,121,354; inline_utils.hpp:28-30) ----

@@ -705,13 +705,13 @@ __device__ __noinline__ double warp_loss3_smem(const double* __restrict__ sP, in
                                                int lane, double m0, double m1, double m2, double k,
                                                const double* __restrict__ tab) {
     const double scale = k / sqrt(dot3(m0, m1, m2, m0, m1, m2));
-    DD acc = dd_zero();
+    double acc = 0.0;
     for (int s = 0; s < nslots; ++s) {
         const int i = s * 32 + lane;
         const double r = dot3(sP[i], sP[NP + i], sP[2 * NP + i], m0, m1, m2) * scale;
-        dd_add(acc, log1p_nonneg(r * r, tab));  // padding rows are 0 -> log1p(0) = 0
+        acc = acc + log1p_nonneg(r * r, tab);  // padding rows are 0 -> log1p(0) = 0
     }
-    return warp_dd_sum(acc);
+    return warp_sum(acc);
 }
 
 // FrameState::Loss 5-arg (core_private.cpp:92-115): value and d/dm in closed form of the
@@ -725,24 +725,25 @@ __device__ __noinline__ Loss5 warp_loss5_smem(const double* __restrict__ sP, int
     const double kk = k * k;
     const double den = dot3(m0, m1, m2, m0, m1, m2) / kk;
     const double inv_den = 1.0 / den;
-    DD L = dd_zero(), g0 = dd_zero(), g1 = dd_zero(), g2 = dd_zero(), su = dd_zero();
+    double acc[5] = {0.0, 0.0, 0.0, 0.0, 0.0};  // L, g0, g1, g2, su
     for (int s = 0; s < nslots; ++s) {
         const int i = s * 32 + lane;
         const double p0 = sP[i], p1 = sP[NP + i], p2 = sP[2 * NP + i];
         const double v1 = dot3(p0, p1, p2, m0, m1, m2);
         const double u = (v1 * v1) * inv_den;
-        dd_add(L, log1p_nonneg(u, tab));
+        acc[0] = acc[0] + log1p_nonneg(u, tab);
         const double wgt = 1.0 / (1.0 + u);
         const double wv = wgt * v1;
-        dd_add(g0, wv * p0);
-        dd_add(g1, wv * p1);
-        dd_add(g2, wv * p2);
-        dd_add(su, wgt * u);
+        acc[1] = acc[1] + wv * p0;
+        acc[2] = acc[2] + wv * p1;
+        acc[3] = acc[3] + wv * p2;
+        acc[4] = acc[4] + wgt * u;
     }
+    warp_sum_n<5>(acc);
     Loss5 out;
-    out.f = warp_dd_sum(L);
-    const double G0 = warp_dd_sum(g0), G1 = warp_dd_sum(g1), G2 = warp_dd_sum(g2);
-    const double SU = warp_dd_sum(su);
+    out.f = acc[0];
+    const double G0 = acc[1], G1 = acc[2], G2 = acc[3];
+    const double SU = acc[4];
     const double c1 = 2.0 * inv_den;
     const double c2 = (c1 / kk) * SU;
     out.g0 = c1 * G0 - c2 * m0;
@@ -753,10 +754,9 @@ __device__ __noinline__ Loss5 warp_loss5_smem(const double* __restrict__ sP, int
 
 // Register-resident variants for the Sync kernels: the frame's rows stay in registers across all
 // objective evaluations of one L-BFGS run (the delay, hence P, is fixed during it), the slot loops
-// are compile-time so independent log1p / division chains interleave, and the five double-double
-// sums of an evaluation share one butterfly.  Same per-lane order of operations as the
-// shared-memory variants above, hence the same bits (rows past the frame's end are zero and add
-// exact zeros).
+// are compile-time so independent log1p / division chains interleave, and the five sums of an
+// evaluation share one butterfly.  Same per-lane order of operations as the shared-memory variants
+// above, hence the same bits (rows past the frame's end are zero and add exact zeros).
 template <int SLOTS>
 __device__ __forceinline__ void load_rows(const double* __restrict__ sP, int NP, int lane,
                                           double (&p)[SLOTS][3]) {
@@ -767,22 +767,6 @@ __device__ __forceinline__ void load_rows(const double* __restrict__ sP, int NP,
         p[s][1] = sP[NP + i];
         p[s][2] = sP[2 * NP + i];
     }
-}
-template <int N>
-__device__ __forceinline__ void warp_dd_sum_n(DD (&a)[N], double (&out)[N]) {
-#pragma unroll
-    for (int off = 16; off >= 1; off >>= 1) {
-        DD b[N];
-#pragma unroll
-        for (int j = 0; j < N; ++j) {
-            b[j].hi = __shfl_xor_sync(FULL, a[j].hi, off);
-            b[j].lo = __shfl_xor_sync(FULL, a[j].lo, off);
-        }
-#pragma unroll
-        for (int j = 0; j < N; ++j) dd_merge(a[j], b[j]);
-    }
-#pragma unroll
-    for (int j = 0; j < N; ++j) out[j] = a[j].hi + a[j].lo;
 }
 template <int SLOTS>
 __device__ __forceinline__ Loss5 warp_loss5_reg(const double (&p)[SLOTS][3], double m0, double m1,
@@ -801,18 +785,17 @@ __device__ __forceinline__ Loss5 warp_loss5_reg(const double (&p)[SLOTS][3], dou
         lg[s] = log1p_nonneg(u[s], tab);
         wgt[s] = 1.0 / (1.0 + u[s]);
     }
-    DD acc[5] = {dd_zero(), dd_zero(), dd_zero(), dd_zero(), dd_zero()};  // L, g0, g1, g2, su
+    double r[5] = {0.0, 0.0, 0.0, 0.0, 0.0};  // L, g0, g1, g2, su
 #pragma unroll
     for (int s = 0; s < SLOTS; ++s) {
         const double wv = wgt[s] * v1[s];
-        dd_add(acc[0], lg[s]);
-        dd_add(acc[1], wv * p[s][0]);
-        dd_add(acc[2], wv * p[s][1]);
-        dd_add(acc[3], wv * p[s][2]);
-        dd_add(acc[4], wgt[s] * u[s]);
+        r[0] = r[0] + lg[s];
+        r[1] = r[1] + wv * p[s][0];
+        r[2] = r[2] + wv * p[s][1];
+        r[3] = r[3] + wv * p[s][2];
+        r[4] = r[4] + wgt[s] * u[s];
     }
-    double r[5];
-    warp_dd_sum_n<5>(acc, r);
+    warp_sum_n<5>(r);
     Loss5 out;
     out.f = r[0];
     const double c1 = 2.0 * inv_den;
@@ -832,12 +815,10 @@ __device__ __forceinline__ double warp_loss3_reg(const double (&p)[SLOTS][3], do
         const double r = dot3(p[s][0], p[s][1], p[s][2], m0, m1, m2) * scale;
         lg[s] = log1p_nonneg(r * r, tab);
     }
-    DD acc[1] = {dd_zero()};
+    double acc = 0.0;
 #pragma unroll
-    for (int s = 0; s < SLOTS; ++s) dd_add(acc[0], lg[s]);
-    double out[1];
-    warp_dd_sum_n<1>(acc, out);
-    return out[0];
+    for (int s = 0; s < SLOTS; ++s) acc = acc + lg[s];
+    return warp_sum(acc);
 }
 
 // ens::L_BFGS on a 3-vector (call site core_private.cpp:264-294); every lane runs the same scalar
@@ -933,14 +914,14 @@ __device__ __forceinline__ double warp_lbfgs(EvalF&& eval, double x[3], int& n_i
 // arma::norm(P * M) over the warp (core_private.cpp:79,132); P.M goes to pm_out[i]
 __device__ __forceinline__ double warp_norm_PM(const double* sP, int NP, int nslots, int lane,
                                                const double M[3], double* pm_out) {
-    DD ss = dd_zero();
+    double ss = 0.0;
     for (int s = 0; s < nslots; ++s) {
         const int i = s * 32 + lane;
         const double pm = dot3(sP[i], sP[NP + i], sP[2 * NP + i], M[0], M[1], M[2]);
         if (pm_out) pm_out[i] = pm;
-        dd_add(ss, pm * pm);
+        ss = ss + pm * pm;
     }
-    return sqrt(warp_dd_sum(ss));
+    return sqrt(warp_sum(ss));
 }
 
 // which of pre_sync's panic conditions (core_private.cpp:76-83) a task with a non-finite cost hit
@@ -1099,12 +1080,12 @@ presync_kernel(DeviceData dd, const FrameDesc* __restrict__ frames, int F,
             const int i = s * 32 + lane;
             pmv[s] = dot3(w.P[i], w.P[NP + i], w.P[2 * NP + i], M[0], M[1], M[2]);
         }
-        DD ss = dd_zero();
+        double ss = 0.0;
 #pragma unroll
-        for (int s = 0; s < SLOTS; ++s) dd_add(ss, pmv[s] * pmv[s]);
-        const double k = clamp_k(1.0 / sqrt(warp_dd_sum(ss)) * 1e2);  // arma::norm(P * M), :79
+        for (int s = 0; s < SLOTS; ++s) ss = ss + pmv[s] * pmv[s];
+        const double k = clamp_k(1.0 / sqrt(warp_sum(ss)) * 1e2);  // arma::norm(P * M), :79
         const double scale = k / sqrt(dot3(M[0], M[1], M[2], M[0], M[1], M[2]));
-        DD acc = dd_zero();
+        double acc = 0.0;
         {
             double rho[SLOTS];
 #pragma unroll
@@ -1113,9 +1094,9 @@ presync_kernel(DeviceData dd, const FrameDesc* __restrict__ frames, int F,
                 rho[s] = sqrt(log1p_nonneg(r * r, tab));
             }
 #pragma unroll
-            for (int s = 0; s < SLOTS; ++s) dd_add(acc, rho[s]);
+            for (int s = 0; s < SLOTS; ++s) acc = acc + rho[s];
         }
-        const double cost = sqrt(warp_dd_sum(acc));
+        const double cost = sqrt(warp_sum(acc));
         if (lane == 0) framecost[(size_t)di * F + fi] = cost;
         // the panic conditions of :76-83: non-finite values propagate into the cost, so the stage
         // that produced them is only looked for when the cost (or a row) is not finite
