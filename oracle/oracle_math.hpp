@@ -6,8 +6,8 @@
 // reference lines it follows (paths relative to /root/reference).  The arithmetic contract
 // ("the spec") is: IEEE-754 binary64, round-to-nearest, NO implicit contraction
 // (build with -ffp-contract=off); a fused multiply-add happens exactly where fma() is written;
-// long sums are accumulated in double-double so their value does not depend on the order of
-// the terms.  The CUDA kernels implement the same contract, which is what makes bit-level
+// sums over a frame's rays are taken in a fixed order (RaySum, rssync_oracle.cpp), sums over
+// frames in double-double so their value does not depend on the order of the terms.  The CUDA kernels implement the same contract, which is what makes bit-level
 // parity checks possible.
 #pragma once
 #include <cmath>

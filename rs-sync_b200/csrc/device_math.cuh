@@ -1,9 +1,9 @@
 // Device-side arithmetic of the rs-sync loss engine for sm_100a.
 //
 // Arithmetic contract: IEEE-754 binary64, round-to-nearest, compiled with
-// -fmad=false so that a fused multiply-add happens exactly where fma() is written; long sums go
-// through a double-double accumulator so their value does not depend on how the terms are
-// distributed over lanes.  Reference lines each function stands for are cited inline (paths
+// -fmad=false so that a fused multiply-add happens exactly where fma() is written; sums over
+// a frame's rays are taken in a fixed order (warp_sum), sums over frames go through a
+// double-double accumulator so their value does not depend on how frames are distributed.  Reference lines each function stands for are cited inline (paths
 // relative to the rs-sync repository).
 #pragma once
 #include <cstdint>
