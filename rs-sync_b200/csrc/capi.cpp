@@ -106,6 +106,51 @@ bool all_finite(const double* p, size_t n) {
 
 }  // namespace
 
+namespace {
+struct SyncPointState {
+    double delay = 0.0, v = 0.0, center = 0.0, radius = 0.0;
+    int converge = 0;
+    bool done = false;
+};
+// One lane of the Sync batch driver (sync_batch_impl): a contiguous group of syncpoints with its
+// own stream, device scratch and pinned I/O blocks.
+struct SyncLane {
+    enum Phase { Running, Final, Done };
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev = nullptr;
+    int s0 = 0, n = 0, t0 = 0, T = 0, iters = 0;
+    Phase phase = Done;
+    DevBuf<rs::SyncTask> d_tasks;
+    DevBuf<int> d_sp_begin, d_lbfgs_stats;
+    DevBuf<double> d_m, d_k, d_task_scratch, d_trial_delay, d_in, d_out;
+    DevBuf<uint64_t> d_sp_callno;
+    PinBuf<double> h_in, h_out;
+    size_t in_doubles = 0, out_doubles = 0;
+    rs::SyncBatchDev b{};
+    std::vector<SyncPointState> st;
+    std::vector<int> h_stats, local_sp;
+    const unsigned char* h_active = nullptr;
+    // one outer iteration (copy in, four kernels, copy out) as an instantiated CUDA graph; valid as
+    // long as every captured argument (graph_key) is unchanged, which holds across chained Sync calls
+    cudaGraphExec_t graph_exec = nullptr;
+    std::vector<unsigned char> graph_key;
+    unsigned char* active_dev() const { return reinterpret_cast<unsigned char*>(d_in.ptr + 2 * (size_t)n); }
+    unsigned long long* evals_dev() const { return reinterpret_cast<unsigned long long*>(d_out.ptr + out_doubles - 1); }
+    void release() {
+        d_tasks.release(); d_sp_begin.release(); d_lbfgs_stats.release(); d_m.release(); d_k.release();
+        d_task_scratch.release(); d_trial_delay.release(); d_in.release(); d_out.release();
+        d_sp_callno.release(); h_in.release(); h_out.release();
+        if (graph_exec) cudaGraphExecDestroy(graph_exec);
+        graph_exec = nullptr;
+        if (ev) cudaEventDestroy(ev);
+        if (stream) cudaStreamDestroy(stream);
+        ev = nullptr;
+        stream = nullptr;
+    }
+};
+
+}  // namespace
+
 struct rssync_problem {
     int device = 0;
     cudaStream_t stream = nullptr;
@@ -162,13 +207,9 @@ struct rssync_problem {
     DevBuf<int> d_win_begin;
     DevBuf<unsigned> d_flags;
     PinBuf<double> h_stage;
-    // sync scratch
-    DevBuf<rs::SyncTask> d_tasks;
-    DevBuf<int> d_sp_begin, d_lbfgs_stats;
-    DevBuf<double> d_m, d_k, d_task_scratch, d_sp_delay, d_sp_x0, d_trial_delay, d_out_v, d_out_g,
-        d_out_trials;
-    DevBuf<uint64_t> d_sp_callno;
-    DevBuf<unsigned char> d_sp_active;
+    // sync: per-lane scratch (sync_batch_impl)
+    std::vector<SyncLane> lanes;
+    cudaEvent_t ev_sync_ready = nullptr;
     DevBuf<double> d_probe;
 
     std::vector<std::pair<double, int32_t>> sort_scratch;
@@ -325,11 +366,216 @@ int presync_grid_impl(rssync_problem* p, int64_t fb, int64_t fe, const double* d
 }
 
 // ---- Sync: host control loop over a batch of syncpoints ---------------------------------------
-struct SyncPointState {
-    double delay, v = 0.0, center, radius;
-    int converge = 0;
-    bool done = false;
-};
+// The outer loop of Sync (core_private.cpp:298-331) stays on the host: per iteration one launch
+// sequence (L-BFGS of every frame + objective at x0, x0 -/+ h; the per-syncpoint sums, which also
+// form Backtrack's trial points on the device; the trial losses; their sums) and one read-back.
+// A frame whose L-BFGS runs to its 200-iteration cap takes ~0.3 ms of dependent scalar FP64 work on
+// one warp against ~20 us for the typical frame, and every syncpoint needs all of its frames before
+// it can step.  Syncpoints are independent of each other, so the batch is cut into LANES
+// (contiguous groups of syncpoints), each with its own stream, scratch and pinned I/O blocks; one
+// host thread drives all lanes as state machines and polls their events, so a lane waiting for a
+// straggler does not hold up the others and their kernels overlap on the device.  The result of a
+// syncpoint does not depend on the lane it runs in.
+constexpr int kTrials = 10;  // Backtrack max_iterations, core_private.cpp:226
+
+int sync_lane_count(int n) {
+    static const int cfg = [] {
+        const char* e = std::getenv("RSSYNC_SYNC_LANES");
+        const int v = e ? std::atoi(e) : 0;
+        return v > 0 ? v : 8;
+    }();
+    return std::max(1, std::min(n, cfg));
+}
+
+// stream-ordered setup of one lane: buffers, task upload, GuessMotion / GuessK (:218-223)
+int sync_lane_begin(rssync_problem* p, SyncLane& L, const rs::DeviceData& dd, const std::vector<rs::SyncTask>& tasks,
+                    const std::vector<int>& sp_begin, const std::vector<uint64_t>& callno, int max_n,
+                    const double* initial, bool dbg) {
+    const int n = L.n, T = L.T;
+    if (!L.stream) CUDA_TRY(p, cudaStreamCreateWithFlags(&L.stream, cudaStreamNonBlocking));
+    if (!L.ev) CUDA_TRY(p, cudaEventCreateWithFlags(&L.ev, cudaEventDisableTiming));
+    CUDA_TRY(p, L.d_tasks.reserve(std::max(T, 1)));
+    CUDA_TRY(p, L.d_sp_begin.reserve(n + 1));
+    CUDA_TRY(p, L.d_m.reserve((size_t)std::max(T, 1) * 3));
+    CUDA_TRY(p, L.d_k.reserve(std::max(T, 1)));
+    CUDA_TRY(p, L.d_task_scratch.reserve((size_t)std::max(T, 1) * kTrials));
+    CUDA_TRY(p, L.d_lbfgs_stats.reserve((size_t)std::max(T, 1) * 2));
+    CUDA_TRY(p, L.d_sp_callno.reserve(n));
+    CUDA_TRY(p, L.d_trial_delay.reserve((size_t)n * kTrials));
+    // per-iteration traffic: one pinned block each way (one async copy in, one out)
+    //   in : delay[n], x0[n] (doubles), active[n] (bytes); host block 0 serves the iterations (it
+    //        is rewritten only after the previous iteration's event), block 1 the initialisation
+    //   out: v[n], g[n], trial losses[n x kTrials] (doubles), objective evaluations so far (u64)
+    L.in_doubles = 2 * (size_t)n + ((size_t)n + 7) / 8;
+    L.out_doubles = (2 + (size_t)kTrials) * n + 1;
+    CUDA_TRY(p, L.d_in.reserve(L.in_doubles));
+    CUDA_TRY(p, L.h_in.reserve(2 * L.in_doubles));
+    CUDA_TRY(p, L.d_out.reserve(L.out_doubles));
+    CUDA_TRY(p, L.h_out.reserve(L.out_doubles));
+    // everything queued on the problem's stream so far (gyro records, ray arena) precedes this lane
+    CUDA_TRY(p, cudaStreamWaitEvent(L.stream, p->ev_sync_ready, 0));
+    CUDA_TRY(p, cudaMemcpyAsync(L.d_tasks.ptr, tasks.data() + L.t0, sizeof(rs::SyncTask) * T, cudaMemcpyHostToDevice, L.stream));
+    CUDA_TRY(p, cudaMemcpyAsync(L.d_sp_begin.ptr, sp_begin.data(), sizeof(int) * (n + 1), cudaMemcpyHostToDevice, L.stream));
+    CUDA_TRY(p, cudaMemcpyAsync(L.d_sp_callno.ptr, callno.data() + L.s0, sizeof(uint64_t) * n, cudaMemcpyHostToDevice, L.stream));
+    p->h2d += sizeof(rs::SyncTask) * T + sizeof(int) * (n + 1) + sizeof(uint64_t) * n;
+    CUDA_TRY(p, cudaMemsetAsync(L.evals_dev(), 0, sizeof(unsigned long long), L.stream));
+    L.b.tasks = L.d_tasks.ptr;
+    L.b.T = T;
+    L.b.max_n = max_n;
+    L.b.sp_begin = L.d_sp_begin.ptr;
+    L.b.S = n;
+    L.b.m = L.d_m.ptr;
+    L.b.k = L.d_k.ptr;
+    L.st.assign(n, SyncPointState());
+    L.iters = 0;
+    L.phase = SyncLane::Running;
+    if (dbg) L.h_stats.resize((size_t)std::max(T, 1) * 2);
+    double* hd = L.h_in.ptr + L.in_doubles;  // host block 1: the iterations use block 0
+    for (int s = 0; s < n; ++s) {
+        L.st[s].delay = initial[L.s0 + s];
+        hd[s] = L.st[s].delay;
+        hd[n + s] = L.st[s].delay;
+        reinterpret_cast<unsigned char*>(hd + 2 * n)[s] = 1;
+    }
+    CUDA_TRY(p, cudaMemcpyAsync(L.d_in.ptr, hd, L.in_doubles * sizeof(double), cudaMemcpyHostToDevice, L.stream));
+    p->h2d += L.in_doubles * sizeof(double);
+    rs::launch_sync_init(dd, L.b, L.d_in.ptr, L.d_sp_callno.ptr, L.active_dev(), p->seed, L.stream);
+    CUDA_TRY(p, cudaGetLastError());
+    return RSSYNC_OK;
+}
+
+// the launch sequence of one outer iteration on the lane's stream (also what the graph captures)
+int sync_lane_enqueue_iteration(rssync_problem* p, SyncLane& L, const rs::DeviceData& dd, bool dbg) {
+    const int n = L.n;
+    double* d_delay = L.d_in.ptr;
+    double* d_x0 = d_delay + n;
+    CUDA_TRY(p, cudaMemcpyAsync(L.d_in.ptr, L.h_in.ptr, L.in_doubles * sizeof(double), cudaMemcpyHostToDevice, L.stream));
+    // do_opt_motion (:262-296) + f_and_grad at x0 (:228-240), then Backtrack::Step
+    // (backtrack.cpp:3-13): all trial points x0 - t g are known once the gradient is, so the
+    // device forms them and evaluates them in one launch; the host takes the first that passes.
+    rs::launch_sync_motion_fgrad(dd, L.b, d_delay, d_x0, L.active_dev(), L.d_task_scratch.ptr, L.d_out.ptr,
+                                 L.d_out.ptr + n, L.d_trial_delay.ptr, kTrials,
+                                 dbg ? L.d_lbfgs_stats.ptr : nullptr, L.evals_dev(), L.stream);
+    if (dbg)
+        CUDA_TRY(p, cudaMemcpyAsync(L.h_stats.data(), L.d_lbfgs_stats.ptr, sizeof(int) * 2 * L.T, cudaMemcpyDeviceToHost, L.stream));
+    rs::launch_sync_trials(dd, L.b, L.d_trial_delay.ptr, kTrials, L.active_dev(), L.d_task_scratch.ptr,
+                           L.d_out.ptr + 2 * n, L.stream);
+    CUDA_TRY(p, cudaGetLastError());
+    CUDA_TRY(p, cudaMemcpyAsync(L.h_out.ptr, L.d_out.ptr, L.out_doubles * sizeof(double), cudaMemcpyDeviceToHost, L.stream));
+    return RSSYNC_OK;
+}
+
+// queue one outer iteration of the lane (or, when all its syncpoints are done, the final objective)
+int sync_lane_launch(rssync_problem* p, SyncLane& L, const rs::DeviceData& dd, bool dbg) {
+    static const bool use_graphs = std::getenv("RSSYNC_NO_GRAPHS") == nullptr;
+    const int n = L.n;
+    double* hd = L.h_in.ptr;
+    unsigned char* ha = reinterpret_cast<unsigned char*>(hd + 2 * n);
+    int n_active = 0;
+    for (int s = 0; s < n; ++s) {
+        ha[s] = L.st[s].done ? 0 : 1;
+        n_active += ha[s];
+        hd[s] = L.st[s].delay;
+        hd[n + s] = L.st[s].delay - .3 * L.st[s].v;  // x0 = delay - delay_b * v, :299 (delay_b :260)
+    }
+    L.h_active = ha;
+    const bool finish = n_active == 0 || L.iters >= 400;  // :309
+    if (finish) {
+        // {simple_objective(gyro_delay), gyro_delay}  (:333)
+        for (int s = 0; s < n; ++s) ha[s] = 1;
+        CUDA_TRY(p, cudaMemcpyAsync(L.d_in.ptr, hd, L.in_doubles * sizeof(double), cudaMemcpyHostToDevice, L.stream));
+        rs::launch_sync_trials(dd, L.b, L.d_in.ptr, 1, L.active_dev(), L.d_task_scratch.ptr, L.d_out.ptr + 2 * n, L.stream);
+        CUDA_TRY(p, cudaGetLastError());
+        CUDA_TRY(p, cudaMemcpyAsync(L.h_out.ptr, L.d_out.ptr, L.out_doubles * sizeof(double), cudaMemcpyDeviceToHost, L.stream));
+        L.phase = SyncLane::Final;
+    } else {
+        L.iters++;
+        // every argument the iteration's launches capture
+        struct Key {
+            rs::DeviceData dd;
+            rs::SyncBatchDev b;
+            const void* ptr[8];
+            size_t in_doubles, out_doubles;
+        } key;
+        std::memset(&key, 0, sizeof(key));
+        key.dd = dd;
+        key.b = L.b;
+        const void* ptrs[8] = {L.d_in.ptr, L.d_out.ptr, L.d_task_scratch.ptr, L.d_trial_delay.ptr,
+                               L.h_in.ptr, L.h_out.ptr, L.stream, nullptr};
+        std::memcpy(key.ptr, ptrs, sizeof(ptrs));
+        key.in_doubles = L.in_doubles;
+        key.out_doubles = L.out_doubles;
+        const bool key_ok = L.graph_exec && L.graph_key.size() == sizeof(key) &&
+                            std::memcmp(L.graph_key.data(), &key, sizeof(key)) == 0;
+        if (!use_graphs || dbg || (!key_ok && L.iters == 1)) {
+            // plain launches: debugging, and the first iteration of a new configuration (it also
+            // performs the launchers' one-time attribute / occupancy calls outside any capture)
+            if (int rc = sync_lane_enqueue_iteration(p, L, dd, dbg)) return rc;
+        } else {
+            if (!key_ok) {
+                if (L.graph_exec) { cudaGraphExecDestroy(L.graph_exec); L.graph_exec = nullptr; }
+                cudaGraph_t graph = nullptr;
+                CUDA_TRY(p, cudaStreamBeginCapture(L.stream, cudaStreamCaptureModeThreadLocal));
+                const int rc = sync_lane_enqueue_iteration(p, L, dd, false);
+                const cudaError_t e = cudaStreamEndCapture(L.stream, &graph);
+                rs::count_launches((uint64_t)-4);  // the launchers counted kernels that were only captured
+                if (rc) { if (graph) cudaGraphDestroy(graph); return rc; }
+                CUDA_TRY(p, e);
+                const cudaError_t ei = cudaGraphInstantiate(&L.graph_exec, graph, 0);
+                cudaGraphDestroy(graph);
+                CUDA_TRY(p, ei);
+                L.graph_key.assign(reinterpret_cast<unsigned char*>(&key), reinterpret_cast<unsigned char*>(&key) + sizeof(key));
+            }
+            CUDA_TRY(p, cudaGraphLaunch(L.graph_exec, L.stream));
+            rs::count_launches(4);
+        }
+    }
+    p->h2d += L.in_doubles * sizeof(double);
+    p->d2h += L.out_doubles * sizeof(double);
+    CUDA_TRY(p, cudaEventRecord(L.ev, L.stream));
+    return RSSYNC_OK;
+}
+
+// host half of one outer iteration: Backtrack's acceptance test, momentum, stopping rules
+void sync_lane_step(rssync_problem* p, SyncLane& L, bool record_trace, bool dbg) {
+    const int n = L.n;
+    const double* h_v = L.h_out.ptr;
+    const double* h_g = h_v + n;
+    const double* h_trial_out = h_g + n;
+    if (dbg) {
+        int max_ev = 0, max_it = 0;
+        for (int t = 0; t < L.T; ++t)
+            if (L.h_active[L.local_sp[t]]) {
+                max_ev = std::max(max_ev, L.h_stats[2 * t + 1]);
+                max_it = std::max(max_it, L.h_stats[2 * t]);
+            }
+        std::fprintf(stderr, "sync lane %d it %d: L-BFGS max iters %d, max evals %d\n", L.s0, L.iters, max_it, max_ev);
+    }
+    const double delay_b = .3;  // :260
+    for (int s = 0; s < n; ++s) {
+        SyncPointState& st = L.st[s];
+        if (st.done) continue;
+        const double v = h_v[s], g = h_g[s];
+        const double mm = g * g;
+        double t = 1e-3;
+        for (int i = 0; i < kTrials; ++i) {
+            const double v1 = h_trial_out[(size_t)s * kTrials + i];
+            if (v - v1 >= t * 2e-4 * mm) break;
+            t *= .1;
+        }
+        const double step = -t * g;
+        st.v = delay_b * st.v + step;  // :301
+        st.delay += st.v;              // :302
+        const double step_size = std::fabs(step);
+        if (record_trace && L.s0 + s == 0) {
+            p->trace_delay.push_back(st.delay);
+            p->trace_step.push_back(step_size);
+        }
+        if (step_size < 1e-4) st.converge++; else st.converge = 0;  // :316-320
+        if (st.converge > 5) st.done = true;                        // :322
+        if (std::fabs(st.delay - st.center) > st.radius) st.done = true;  // :326
+    }
+}
 
 int sync_batch_impl(rssync_problem* p, int n, const double* initial, const int64_t* fb,
                     const int64_t* fe, const double* center, const double* radius, double* out_cost,
@@ -338,162 +584,80 @@ int sync_batch_impl(rssync_problem* p, int n, const double* initial, const int64
     if (n <= 0) return RSSYNC_OK;
     // tasks: frames frame_begin <= f <= frame_end, INCLUSIVE (core_private.cpp:219)
     std::vector<rs::SyncTask> tasks;
-    std::vector<int> sp_begin(n + 1, 0);
-    int max_n = 0;
+    std::vector<int> sp_first(n + 1, 0);
+    std::vector<int> sp_max_n(n, 0);
     std::vector<FrameDesc> sel;
     for (int s = 0; s < n; ++s) {
-        int mn = 0;
         if (fe[s] == INT64_MAX) { p->err = "sync: frame_end out of range"; return RSSYNC_E_INVALID; }
-        if (int rc = select_frames(p, fb[s], fe[s] + 1, sel, mn, "sync")) return rc;
-        max_n = std::max(max_n, mn);
+        if (int rc = select_frames(p, fb[s], fe[s] + 1, sel, sp_max_n[s], "sync")) return rc;
         for (const FrameDesc& fd : sel) tasks.push_back(rs::SyncTask{fd, s, 0});
-        sp_begin[s + 1] = (int)tasks.size();
+        sp_first[s + 1] = (int)tasks.size();
     }
     if (int rc = flush(p)) return rc;
-    const int T = (int)tasks.size();
-    constexpr int kTrials = 10;  // Backtrack max_iterations, core_private.cpp:226
     std::vector<uint64_t> callno(n);
     for (int s = 0; s < n; ++s) callno[s] = call_nos ? call_nos[s] : p->call_no + (uint64_t)s;
     if (!call_nos) p->call_no += (uint64_t)n;
-
-    CUDA_TRY(p, p->d_tasks.reserve(std::max(T, 1)));
-    CUDA_TRY(p, p->d_sp_begin.reserve(n + 1));
-    CUDA_TRY(p, p->d_m.reserve((size_t)std::max(T, 1) * 3));
-    CUDA_TRY(p, p->d_k.reserve(std::max(T, 1)));
-    CUDA_TRY(p, p->d_task_scratch.reserve((size_t)std::max(T, 1) * kTrials));
-    CUDA_TRY(p, p->d_lbfgs_stats.reserve((size_t)std::max(T, 1) * 2));
-    CUDA_TRY(p, p->d_sp_delay.reserve(n));
-    CUDA_TRY(p, p->d_sp_x0.reserve(n));
-    CUDA_TRY(p, p->d_sp_callno.reserve(n));
-    CUDA_TRY(p, p->d_sp_active.reserve(n));
-    CUDA_TRY(p, p->d_trial_delay.reserve((size_t)n * kTrials));
-    CUDA_TRY(p, p->d_out_v.reserve(n));
-    CUDA_TRY(p, p->d_out_g.reserve(n));
-    CUDA_TRY(p, p->d_out_trials.reserve((size_t)n * kTrials));
-    if (int rc = h2d(p, p->d_tasks.ptr, tasks.data(), sizeof(rs::SyncTask) * T)) return rc;
-    if (int rc = h2d(p, p->d_sp_begin.ptr, sp_begin.data(), sizeof(int) * (n + 1))) return rc;
-    if (int rc = h2d(p, p->d_sp_callno.ptr, callno.data(), sizeof(uint64_t) * n)) return rc;
-
-    rs::SyncBatchDev b;
-    b.tasks = p->d_tasks.ptr;
-    b.T = T;
-    b.max_n = max_n;
-    b.sp_begin = p->d_sp_begin.ptr;
-    b.S = n;
-    b.m = p->d_m.ptr;
-    b.k = p->d_k.ptr;
-    const rs::DeviceData dd = p->device_data();
-
-    std::vector<SyncPointState> st(n);
-    std::vector<double> h_delay(n), h_x0(n), h_v(n), h_g(n), h_trial((size_t)n * kTrials),
-        h_trial_out((size_t)n * kTrials);
-    std::vector<unsigned char> h_active(n, 1);
-    std::vector<int> h_stats((size_t)std::max(T, 1) * 2);
-    for (int s = 0; s < n; ++s) {
-        st[s].delay = initial[s];
-        st[s].center = center[s];
-        st[s].radius = radius[s];
-        h_delay[s] = initial[s];
-    }
+    static const bool dbg = std::getenv("RSSYNC_DEBUG_SYNC") != nullptr;
     if (record_trace) { p->trace_delay.clear(); p->trace_step.clear(); }
     p->sync_outer = 0;
     p->sync_evals = 0;
 
-    // GuessMotion / GuessK for every frame (core_private.cpp:218-223)
-    if (int rc = h2d(p, p->d_sp_delay.ptr, h_delay.data(), sizeof(double) * n)) return rc;
-    if (int rc = h2d(p, p->d_sp_active.ptr, h_active.data(), n)) return rc;
-    rs::launch_sync_init(dd, b, p->d_sp_delay.ptr, p->d_sp_callno.ptr, p->d_sp_active.ptr, p->seed,
-                         p->stream);
-    CUDA_TRY(p, cudaGetLastError());
-
-    const double delay_b = .3;  // :260
-    for (int it = 0; it < 400; ++it) {  // :309
-        int n_active = 0;
-        for (int s = 0; s < n; ++s) {
-            h_active[s] = st[s].done ? 0 : 1;
-            n_active += h_active[s];
-            h_delay[s] = st[s].delay;
-            h_x0[s] = st[s].delay - delay_b * st[s].v;  // :299
+    if (!p->ev_sync_ready) CUDA_TRY(p, cudaEventCreateWithFlags(&p->ev_sync_ready, cudaEventDisableTiming));
+    CUDA_TRY(p, cudaEventRecord(p->ev_sync_ready, p->stream));
+    const rs::DeviceData dd = p->device_data();
+    const int G = sync_lane_count(n);
+    if ((int)p->lanes.size() < G) p->lanes.resize(G);
+    std::vector<std::vector<int>> lane_sp_begin(G);
+    for (int g = 0; g < G; ++g) {
+        SyncLane& L = p->lanes[g];
+        L.s0 = (int)((long long)n * g / G);
+        L.n = (int)((long long)n * (g + 1) / G) - L.s0;
+        L.t0 = sp_first[L.s0];
+        L.T = sp_first[L.s0 + L.n] - L.t0;
+        int max_n = 0;
+        lane_sp_begin[g].resize(L.n + 1);
+        for (int s = 0; s <= L.n; ++s) lane_sp_begin[g][s] = sp_first[L.s0 + s] - L.t0;
+        for (int s = 0; s < L.n; ++s) max_n = std::max(max_n, sp_max_n[L.s0 + s]);
+        L.local_sp.resize(L.T);
+        for (int t = 0; t < L.T; ++t) {
+            tasks[L.t0 + t].sp -= L.s0;  // syncpoint index inside the lane
+            L.local_sp[t] = tasks[L.t0 + t].sp;
         }
-        if (!n_active) break;
-        p->sync_outer++;
-        if (int rc = h2d(p, p->d_sp_delay.ptr, h_delay.data(), sizeof(double) * n)) return rc;
-        if (int rc = h2d(p, p->d_sp_x0.ptr, h_x0.data(), sizeof(double) * n)) return rc;
-        if (int rc = h2d(p, p->d_sp_active.ptr, h_active.data(), n)) return rc;
-        // do_opt_motion (:262-296) + f_and_grad at x0 (:228-240)
-        rs::launch_sync_motion_fgrad(dd, b, p->d_sp_delay.ptr, p->d_sp_x0.ptr, p->d_sp_active.ptr,
-                                     p->d_task_scratch.ptr, p->d_out_v.ptr, p->d_out_g.ptr,
-                                     p->d_lbfgs_stats.ptr, p->stream);
-        CUDA_TRY(p, cudaGetLastError());
-        if (int rc = d2h(p, h_v.data(), p->d_out_v.ptr, sizeof(double) * n)) return rc;
-        if (int rc = d2h(p, h_g.data(), p->d_out_g.ptr, sizeof(double) * n)) return rc;
-        if (int rc = d2h(p, h_stats.data(), p->d_lbfgs_stats.ptr, sizeof(int) * 2 * T)) return rc;
-        CUDA_TRY(p, cudaStreamSynchronize(p->stream));
-        int dbg_max_ev = 0, dbg_max_it = 0;
-        for (int t = 0; t < T; ++t)
-            if (h_active[tasks[t].sp]) {
-                p->sync_evals += (uint64_t)h_stats[2 * t + 1];
-                dbg_max_ev = std::max(dbg_max_ev, h_stats[2 * t + 1]);
-                dbg_max_it = std::max(dbg_max_it, h_stats[2 * t]);
-            }
-        static const bool dbg = std::getenv("RSSYNC_DEBUG_SYNC") != nullptr;
-        if (dbg)
-            std::fprintf(stderr, "sync it %d: active %d, L-BFGS max iters %d, max evals %d\n", it, n_active,
-                         dbg_max_it, dbg_max_ev);
-        // Backtrack::Step (backtrack.cpp:3-13): all trial points are known once the gradient
-        // is, so they are evaluated in one launch and the first that passes is taken.
-        for (int s = 0; s < n; ++s) {
-            double t = 1e-3;
-            for (int i = 0; i < kTrials; ++i) {
-                h_trial[(size_t)s * kTrials + i] = h_x0[s] - t * h_g[s];
-                t *= .1;
-            }
+        if (int rc = sync_lane_begin(p, L, dd, tasks, lane_sp_begin[g], callno, max_n, initial, dbg)) return rc;
+        for (int s = 0; s < L.n; ++s) {
+            L.st[s].center = center[L.s0 + s];
+            L.st[s].radius = radius[L.s0 + s];
         }
-        if (int rc = h2d(p, p->d_trial_delay.ptr, h_trial.data(), sizeof(double) * n * kTrials)) return rc;
-        rs::launch_sync_trials(dd, b, p->d_trial_delay.ptr, kTrials, p->d_sp_active.ptr,
-                               p->d_task_scratch.ptr, p->d_out_trials.ptr, p->stream);
-        CUDA_TRY(p, cudaGetLastError());
-        if (int rc = d2h(p, h_trial_out.data(), p->d_out_trials.ptr, sizeof(double) * n * kTrials)) return rc;
-        CUDA_TRY(p, cudaStreamSynchronize(p->stream));
-        for (int s = 0; s < n; ++s) {
-            if (st[s].done) continue;
-            const double v = h_v[s], g = h_g[s];
-            const double mm = g * g;
-            double t = 1e-3;
-            for (int i = 0; i < kTrials; ++i) {
-                const double v1 = h_trial_out[(size_t)s * kTrials + i];
-                if (v - v1 >= t * 2e-4 * mm) break;
-                t *= .1;
-            }
-            const double step = -t * g;
-            st[s].v = delay_b * st[s].v + step;  // :301
-            st[s].delay += st[s].v;              // :302
-            const double step_size = std::fabs(step);
-            if (record_trace && s == 0) {
-                p->trace_delay.push_back(st[s].delay);
-                p->trace_step.push_back(step_size);
-            }
-            if (step_size < 1e-4) st[s].converge++; else st[s].converge = 0;  // :316-320
-            if (st[s].converge > 5) st[s].done = true;                        // :322
-            if (std::fabs(st[s].delay - st[s].center) > st[s].radius) st[s].done = true;  // :326
-        }
+        if (int rc = sync_lane_launch(p, L, dd, dbg)) return rc;
     }
-    // {simple_objective(gyro_delay), gyro_delay}  (:333)
-    for (int s = 0; s < n; ++s) { h_active[s] = 1; h_delay[s] = st[s].delay; }
-    if (int rc = h2d(p, p->d_sp_active.ptr, h_active.data(), n)) return rc;
-    if (int rc = h2d(p, p->d_trial_delay.ptr, h_delay.data(), sizeof(double) * n)) return rc;
-    rs::launch_sync_trials(dd, b, p->d_trial_delay.ptr, 1, p->d_sp_active.ptr, p->d_task_scratch.ptr,
-                           p->d_out_trials.ptr, p->stream);
-    CUDA_TRY(p, cudaGetLastError());
-    if (T > 0) {
-        if (int rc = d2h(p, out_cost, p->d_out_trials.ptr, sizeof(double) * n)) return rc;
-    } else {
-        std::fill(out_cost, out_cost + n, 0.0);
-    }
-    CUDA_TRY(p, cudaStreamSynchronize(p->stream));
-    for (int s = 0; s < n; ++s) {
-        if (sp_begin[s + 1] == sp_begin[s]) out_cost[s] = 0.0;
-        out_delay[s] = st[s].delay;
+    // drive the lanes: whichever has its iteration back on the host steps and is relaunched
+    int running = G;
+    while (running > 0) {
+        bool progressed = false;
+        for (int g = 0; g < G; ++g) {
+            SyncLane& L = p->lanes[g];
+            if (L.phase == SyncLane::Done) continue;
+            const cudaError_t q = cudaEventQuery(L.ev);
+            if (q == cudaErrorNotReady) continue;
+            CUDA_TRY(p, q);
+            progressed = true;
+            if (L.phase == SyncLane::Final) {
+                const double* h_cost = L.h_out.ptr + 2 * L.n;
+                for (int s = 0; s < L.n; ++s) {
+                    const bool empty = lane_sp_begin[g][s + 1] == lane_sp_begin[g][s];
+                    out_cost[L.s0 + s] = empty ? 0.0 : h_cost[s];
+                    out_delay[L.s0 + s] = L.st[s].delay;
+                }
+                p->sync_evals += (uint64_t)*reinterpret_cast<const unsigned long long*>(L.h_out.ptr + L.out_doubles - 1);
+                p->sync_outer = std::max<uint64_t>(p->sync_outer, (uint64_t)L.iters);
+                L.phase = SyncLane::Done;
+                --running;
+                continue;
+            }
+            sync_lane_step(p, L, record_trace, dbg);
+            if (int rc = sync_lane_launch(p, L, dd, dbg)) return rc;
+        }
+        if (!progressed) std::this_thread::yield();
     }
     return RSSYNC_OK;
 }
@@ -535,11 +699,9 @@ void rssync_destroy(rssync_problem* p) {
     p->d_frames.release(); p->d_delays.release(); p->d_framecost.release(); p->d_costs.release();
     p->d_frame_call.release(); p->d_win_begin.release();
     p->h_pix.release(); p->d_pix.release(); p->d_pixframes.release(); p->d_stage.release();
-    p->d_flags.release(); p->h_stage.release(); p->d_tasks.release(); p->d_sp_begin.release();
-    p->d_lbfgs_stats.release(); p->d_m.release(); p->d_k.release(); p->d_task_scratch.release();
-    p->d_sp_delay.release(); p->d_sp_x0.release(); p->d_trial_delay.release(); p->d_out_v.release();
-    p->d_out_g.release(); p->d_out_trials.release(); p->d_sp_callno.release();
-    p->d_sp_active.release(); p->d_probe.release();
+    p->d_flags.release(); p->h_stage.release(); p->d_probe.release();
+    for (SyncLane& L : p->lanes) L.release();
+    if (p->ev_sync_ready) cudaEventDestroy(p->ev_sync_ready);
     if (p->ev0) cudaEventDestroy(p->ev0);
     if (p->ev1) cudaEventDestroy(p->ev1);
     delete p;

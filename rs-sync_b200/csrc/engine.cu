@@ -25,6 +25,9 @@
 #include <algorithm>
 #include <atomic>
 #include <cstdio>
+#include <map>
+#include <mutex>
+#include <utility>
 
 #include "device_math.cuh"
 
@@ -164,18 +167,15 @@ __device__ __forceinline__ void tma_load_1d(void* dst_smem, const void* src_gmem
 
 // Phase A of the PreSync grid kernel: same arithmetic as build_rows_smem<true>, with the frame's ray
 // tiles (sTiles) and the spline records [rec_first, rec_first + rec_cnt) (sRec) staged in shared
-// memory by TMA.  An evaluation whose record is not in the window (cannot happen: the window is
-// computed from the frame's timestamp bounds with a record of slack) takes the global path.
-__device__ __forceinline__ void spline_eval4_staged(const DeviceData& dd, const double* __restrict__ sRec,
-                                                    int rec_first, int rec_cnt, double x, double q[4]) {
-    const int r = __double2int_rd(x);
-    const unsigned at = (unsigned)(r - rec_first);
-    if (at >= (unsigned)rec_cnt) {
-        const Quat4 e = spline_eval4_cold(dd.rec, dd.nq, x);
-        q[0] = e.w; q[1] = e.x; q[2] = e.y; q[3] = e.z;
-        return;
-    }
-    const double h = x - (double)r;
+// memory by TMA.  The window is computed from the frame's timestamp bounds with a record of slack, so
+// every evaluation lands inside it and 0 <= x < 2^31 holds; the loop body is therefore branch-free
+// (both spline evaluations of a ray issue their sixteen loads together and their eight Horner chains
+// interleave): floor(x) is x + 2^52 rounded down, whose low word is the record index and whose
+// difference from 2^52 is the exact (double)floor(x) of the contract's h = x - floor(x).  An index
+// outside the window is clamped and remembered; such a task (none has been observed) is recomputed
+// through the general path.
+__device__ __forceinline__ void spline_eval4_staged(const double* __restrict__ sRec, unsigned at,
+                                                    double h, double q[4]) {
     const double2* p = reinterpret_cast<const double2*>(sRec + (size_t)at * 16);
     const double2 y01 = p[0], y23 = p[1], b01 = p[2], b23 = p[3];
     const double2 c01 = p[4], c23 = p[5], d01 = p[6], d23 = p[7];
@@ -192,14 +192,21 @@ __device__ __forceinline__ unsigned build_rows_staged(const DeviceData& dd, cons
     float fin = 0.f;
     const int nslots = (fd.n + 31) >> 5;
     const int NPAIR = pairs_for(NP);
+    const double kTwo52 = 4503599627370496.0;
+    const unsigned last = (unsigned)(rec_cnt - 1);
+    unsigned outside = 0u;
     for (int s = 0; s < nslots; ++s) {
         const int i = s * 32 + lane;
         const double* t = sTiles + s * 256 + lane;
         const double xa = ((t[0] - dd.q0) + delay) * dd.sr;   // core_private.cpp:19-20
         const double xb = ((t[32] - dd.q0) + delay) * dd.sr;
+        const double fa = __dadd_rd(xa, kTwo52), fb = __dadd_rd(xb, kTwo52);
+        const unsigned ia = (unsigned)(__double2loint(fa) - rec_first);
+        const unsigned ib = (unsigned)(__double2loint(fb) - rec_first);
+        outside |= (ia > last ? 1u : 0u) | (ib > last ? 1u : 0u);
         double qa[4], qb[4], ar[3], br[3], na, nb;
-        spline_eval4_staged(dd, sRec, rec_first, rec_cnt, xa, qa);
-        spline_eval4_staged(dd, sRec, rec_first, rec_cnt, xb, qb);
+        spline_eval4_staged(sRec, min(ia, last), xa - (fa - kTwo52), qa);
+        spline_eval4_staged(sRec, min(ib, last), xb - (fb - kTwo52), qb);
         derotate_unnormalised(qa, t[64], t[96], t[128], ar, na);
         derotate_unnormalised(qb, t[160], t[192], t[224], br, nb);
         const double sc = 1.0 / (na * nb);
@@ -227,6 +234,7 @@ __device__ __forceinline__ unsigned build_rows_staged(const DeviceData& dd, cons
         w.nf[2 * NPAIR * 64 + at] = f2;
         fin += (fabsf(f0) + fabsf(f1)) + fabsf(f2);  // non-finite row -> NaN
     }
+    if (__any_sync(FULL, outside != 0u)) return build_rows_global_cold(dd, fd, delay, lane, w, NP);
     for (int s = nslots; s < 2 * NPAIR; ++s) {
         const int i = s * 32 + lane;
         if (i < NP) {
@@ -828,11 +836,11 @@ __device__ __forceinline__ double warp_lbfgs(EvalF&& eval, double x[3], int& n_i
     constexpr int numBasis = 10, maxIterations = 200, maxTrials = 50;
     const double minGradientNorm = 1e-4, armijo = 1e-4, wolfe = 0.9, factr = 1e-15,
                  minStep = 1e-20, maxStep = 1e20;
-    double S[numBasis][3], Y[numBasis][3], rho[numBasis], alpha[numBasis];
+    double S[numBasis][3] = {}, Y[numBasis][3] = {}, alpha[numBasis];
     // 1 / (y.s) of each stored pair: the two-loop recursion recomputes this division for every pair
     // at every iteration; the value only depends on the pair, so it is computed once when the pair
     // is stored (same expression, same bits) -- it is the longest dependent chain of an iteration
-    double rho_pair[numBasis];
+    double rho_pair[numBasis] = {};
     double g[3], oldx[3], oldg[3], dir[3], trial[3];
     Loss5 e = eval(x[0], x[1], x[2]);
     double f = e.f;
@@ -843,32 +851,52 @@ __device__ __forceinline__ double warp_lbfgs(EvalF&& eval, double x[3], int& n_i
         const double prevf = f;
         if (it > 0 && sqrt(dot3(g[0], g[1], g[2], g[0], g[1], g[2])) < minGradientNorm) break;
         if (f != f) break;
+        // The two-loop recursion is a chain of dependent scalar FP64 operations (6 per stored pair
+        // and loop); a frame that runs to maxIterations spends ~0.3 ms in it and the whole lock-step
+        // batch waits.  The next pair is therefore loaded (local memory, indices independent of the
+        // chain) while the current one is being applied.
+        const int cnt = (numBasis > it) ? it : numBasis;  // stored pairs in use
+        int tp = (it + (numBasis - 1)) % numBasis;        // newest pair
+        double s0 = S[tp][0], s1 = S[tp][1], s2 = S[tp][2];
+        double y0 = Y[tp][0], y1 = Y[tp][1], y2 = Y[tp][2];
+        double rp = rho_pair[tp];
         double scaling;
         if (it > 0) {
-            const int pp = (it - 1) % numBasis;
-            const double yy = dot3(Y[pp][0], Y[pp][1], Y[pp][2], Y[pp][0], Y[pp][1], Y[pp][2]);
+            const double yy = dot3(y0, y1, y2, y0, y1, y2);
             const double denom = (yy >= 1e-10) ? yy : 1.0;
-            scaling = dot3(S[pp][0], S[pp][1], S[pp][2], Y[pp][0], Y[pp][1], Y[pp][2]) / denom;
+            scaling = dot3(s0, s1, s2, y0, y1, y2) / denom;
         } else {
             const double gn = sqrt(dot3(g[0], g[1], g[2], g[0], g[1], g[2]));
             scaling = (gn >= 1e-5) ? 1.0 / gn : 1.0;
         }
         if (scaling == 0.0 || !is_finite(scaling)) break;
         dir[0] = g[0]; dir[1] = g[1]; dir[2] = g[2];
-        const int limit = (numBasis > it) ? 0 : (it - numBasis);
-        for (int i = it; i != limit; --i) {
-            const int tp = (i + (numBasis - 1)) % numBasis;
-            rho[it - i] = rho_pair[tp];
-            alpha[it - i] = rho[it - i] * dot3(S[tp][0], S[tp][1], S[tp][2], dir[0], dir[1], dir[2]);
-            for (int c = 0; c < 3; ++c) dir[c] -= alpha[it - i] * Y[tp][c];
+        for (int j = 0; j < cnt; ++j) {  // pairs it-1, it-2, ..., newest first
+            const int tn = (tp == 0) ? numBasis - 1 : tp - 1;
+            const double ns0 = S[tn][0], ns1 = S[tn][1], ns2 = S[tn][2];
+            const double ny0 = Y[tn][0], ny1 = Y[tn][1], ny2 = Y[tn][2];
+            const double nrp = rho_pair[tn];
+            const double a = rp * dot3(s0, s1, s2, dir[0], dir[1], dir[2]);
+            alpha[j] = a;
+            dir[0] -= a * y0; dir[1] -= a * y1; dir[2] -= a * y2;
+            s0 = ns0; s1 = ns1; s2 = ns2; y0 = ny0; y1 = ny1; y2 = ny2; rp = nrp;
+            tp = tn;
         }
         for (int c = 0; c < 3; ++c) dir[c] *= scaling;
-        for (int i = limit; i < it; ++i) {
-            const int tp = i % numBasis;
-            const double beta =
-                rho[it - i - 1] * dot3(Y[tp][0], Y[tp][1], Y[tp][2], dir[0], dir[1], dir[2]);
-            const double coef = alpha[it - i - 1] - beta;
-            for (int c = 0; c < 3; ++c) dir[c] += coef * S[tp][c];
+        tp = (it - cnt) % numBasis;  // oldest pair in use
+        s0 = S[tp][0]; s1 = S[tp][1]; s2 = S[tp][2];
+        y0 = Y[tp][0]; y1 = Y[tp][1]; y2 = Y[tp][2];
+        rp = rho_pair[tp];
+        for (int j = cnt - 1; j >= 0; --j) {  // oldest first
+            const int tn = (tp == numBasis - 1) ? 0 : tp + 1;
+            const double ns0 = S[tn][0], ns1 = S[tn][1], ns2 = S[tn][2];
+            const double ny0 = Y[tn][0], ny1 = Y[tn][1], ny2 = Y[tn][2];
+            const double nrp = rho_pair[tn];
+            const double beta = rp * dot3(y0, y1, y2, dir[0], dir[1], dir[2]);
+            const double coef = alpha[j] - beta;
+            dir[0] += coef * s0; dir[1] += coef * s1; dir[2] += coef * s2;
+            s0 = ns0; s1 = ns1; s2 = ns2; y0 = ny0; y1 = ny1; y2 = ny2; rp = nrp;
+            tp = tn;
         }
         for (int c = 0; c < 3; ++c) dir[c] = -dir[c];
         for (int c = 0; c < 3; ++c) { oldx[c] = x[c]; oldg[c] = g[c]; }
@@ -1172,12 +1200,15 @@ sync_init_kernel(DeviceData dd, SyncBatchDev b, const double* __restrict__ sp_de
 
 // K2+K3a: per task, L-BFGS refinement of m at the syncpoint's delay (do_opt_motion, :262-296), then
 // the three objective values the delay step needs (Loss5 at x0, Loss3 at x0 -/+ h, :228-240).
+#ifndef RS_SYNC_MINB
+#define RS_SYNC_MINB 1
+#endif
 template <int SLOTS>
-__global__ void __launch_bounds__(kWarpsPerBlock * 32)
+__global__ void __launch_bounds__(kWarpsPerBlock * 32, SLOTS <= 8 ? RS_SYNC_MINB : 1)
 sync_motion_fgrad_kernel(DeviceData dd, SyncBatchDev b, const double* __restrict__ sp_delay,
                          const double* __restrict__ sp_x0,
                          const unsigned char* __restrict__ sp_active, double* __restrict__ scratch,
-                         int* __restrict__ stats) {
+                         int* __restrict__ stats, unsigned long long* __restrict__ evals_total) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     constexpr int NP = SLOTS * 32;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -1206,6 +1237,7 @@ sync_motion_fgrad_kernel(DeviceData dd, SyncBatchDev b, const double* __restrict
                 if (lane == 0) {
                     b.m[3 * t] = m[0]; b.m[3 * t + 1] = m[1]; b.m[3 * t + 2] = m[2];
                     if (stats) { stats[2 * t] = it; stats[2 * t + 1] = ev; }
+                    if (evals_total) atomicAdd(evals_total, (unsigned long long)ev);
                 }
             } else if (j == 1) {
                 const Loss5 e = warp_loss5_reg<SLOTS>(p, m[0], m[1], m[2], k, tab);
@@ -1218,10 +1250,16 @@ sync_motion_fgrad_kernel(DeviceData dd, SyncBatchDev b, const double* __restrict
     }
 }
 
+// sum over the frame's rays of NVAL per-ray terms held one ray per thread (block of SLOTS warps), in
+// the contract's order: lane partial sums over the slots from 0.0, then the xor butterfly
 // per syncpoint: cost = sum v, grad = sum (r - l)/2/h   (core_private.cpp:112, 236-237)
+// and the trial points of Backtrack::Step (backtrack.cpp:5-12: t = initial_step, then t *= decay),
+// x0 - t g with the hyper-parameters of core_private.cpp:226: every trial point is known once the
+// gradient is, so the trial kernel follows in the stream without a host round trip
 __global__ void reduce_fgrad_kernel(SyncBatchDev b, const unsigned char* __restrict__ sp_active,
-                                    const double* __restrict__ scratch, double* __restrict__ out_v,
-                                    double* __restrict__ out_g) {
+                                    const double* __restrict__ scratch, const double* __restrict__ sp_x0,
+                                    double* __restrict__ out_v, double* __restrict__ out_g,
+                                    double* __restrict__ trial_delay, int ntrial) {
     const int lane = threadIdx.x & 31;
     const int sp = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (sp >= b.S || !sp_active[sp]) return;
@@ -1231,7 +1269,16 @@ __global__ void reduce_fgrad_kernel(SyncBatchDev b, const unsigned char* __restr
         dd_add(ag, (scratch[3 * t + 2] - scratch[3 * t + 1]) / 2 / kNumericDiffStep);
     }
     const double v = warp_dd_sum(av), g = warp_dd_sum(ag);
-    if (lane == 0) { out_v[sp] = v; out_g[sp] = g; }
+    if (lane == 0) {
+        out_v[sp] = v;
+        out_g[sp] = g;
+        const double x0 = sp_x0[sp];
+        double t = 1e-3;
+        for (int i = 0; i < ntrial; ++i) {
+            trial_delay[(size_t)sp * ntrial + i] = x0 - t * g;
+            t *= .1;
+        }
+    }
 }
 
 // K3b: Loss3 at ntrial delays per syncpoint (backtracking trial points / final objective)
@@ -1504,9 +1551,20 @@ int grid_for(K kernel, size_t smem, long long warps_needed) {
         cudaGetDevice(&dev);
         cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev);
     }
-    int per_sm = 1;
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, kWarpsPerBlock * 32, smem);
-    if (per_sm < 1) per_sm = 1;
+    // one occupancy query per (kernel, shared memory size): the Sync driver launches thousands of
+    // small kernels per second
+    static std::mutex mu;
+    static std::map<std::pair<const void*, size_t>, int> cache;
+    int per_sm = 0;
+    {
+        std::lock_guard<std::mutex> lk(mu);
+        int& slot = cache[{reinterpret_cast<const void*>(kernel), smem}];
+        if (!slot) {
+            cudaOccupancyMaxActiveBlocksPerMultiprocessor(&slot, kernel, kWarpsPerBlock * 32, smem);
+            if (slot < 1) slot = 1;
+        }
+        per_sm = slot;
+    }
     long long blocks_needed = (warps_needed + kWarpsPerBlock - 1) / kWarpsPerBlock;
     long long cap = (long long)sm_count * per_sm;
     long long g = blocks_needed < cap ? blocks_needed : cap;
@@ -1515,7 +1573,13 @@ int grid_for(K kernel, size_t smem, long long warps_needed) {
 
 template <class K>
 void allow_smem(K kernel, size_t smem) {
+    static std::mutex mu;
+    static std::map<const void*, size_t> allowed;  // per kernel: the largest size already granted
+    std::lock_guard<std::mutex> lk(mu);
+    size_t& have = allowed[reinterpret_cast<const void*>(kernel)];
+    if (smem <= have) return;
     cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    have = smem;
 }
 
 #define RS_DISPATCH_SLOTS(max_n, ...)                              \
@@ -1532,6 +1596,7 @@ void allow_smem(K kernel, size_t smem) {
 }  // namespace
 
 uint64_t launch_count() { return g_launches.load(); }
+void count_launches(uint64_t n) { g_launches += n; }
 
 void launch_presync_grid(const DeviceData& dd, const FrameDesc* d_frames, int F, int max_n,
                          const double* d_delays, int D, uint64_t seed, uint64_t stream,
@@ -1590,7 +1655,8 @@ void launch_sync_init(const DeviceData& dd, const SyncBatchDev& b, const double*
 void launch_sync_motion_fgrad(const DeviceData& dd, const SyncBatchDev& b, const double* d_sp_delay,
                               const double* d_sp_x0, const unsigned char* d_sp_active,
                               double* d_task_scratch, double* d_out_v, double* d_out_g,
-                              int* d_lbfgs_stats, cudaStream_t st) {
+                              double* d_trial_delay, int ntrial, int* d_lbfgs_stats,
+                              unsigned long long* d_evals_total, cudaStream_t st) {
     if (b.T <= 0) return;
     RS_DISPATCH_SLOTS(b.max_n, {
         auto kern = sync_motion_fgrad_kernel<SL>;
@@ -1598,9 +1664,10 @@ void launch_sync_motion_fgrad(const DeviceData& dd, const SyncBatchDev& b, const
         allow_smem(kern, smem);
         const int grid = grid_for(kern, smem, b.T);
         kern<<<grid, kWarpsPerBlock * 32, smem, st>>>(dd, b, d_sp_delay, d_sp_x0, d_sp_active, d_task_scratch,
-                                                      d_lbfgs_stats);
+                                                      d_lbfgs_stats, d_evals_total);
     });
-    reduce_fgrad_kernel<<<(b.S + 3) / 4, 128, 0, st>>>(b, d_sp_active, d_task_scratch, d_out_v, d_out_g);
+    reduce_fgrad_kernel<<<(b.S + 3) / 4, 128, 0, st>>>(b, d_sp_active, d_task_scratch, d_sp_x0, d_out_v,
+                                                       d_out_g, d_trial_delay, ntrial);
     g_launches += 2;
 }
 

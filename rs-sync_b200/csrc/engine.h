@@ -68,11 +68,15 @@ void launch_sync_init(const DeviceData& dd, const SyncBatchDev& b, const double*
                       const uint64_t* d_sp_callno, const unsigned char* d_sp_active, uint64_t seed,
                       cudaStream_t st);
 // do_opt_motion (:262-296) at sp_delay, then Loss5 value at sp_x0 and Loss3 at sp_x0 -/+ h
-// (f_and_grad, :228-240); reduced per syncpoint into out_v[sp], out_g[sp].
+// (f_and_grad, :228-240); reduced per syncpoint into out_v[sp], out_g[sp], and the ntrial trial
+// points of Backtrack::Step (backtrack.cpp:5-12), x0 - t g with t = 1e-3, 1e-4, ..., into
+// d_trial_delay[sp * ntrial + i].  *d_evals_total accumulates the objective evaluations.
 void launch_sync_motion_fgrad(const DeviceData& dd, const SyncBatchDev& b, const double* d_sp_delay,
                               const double* d_sp_x0, const unsigned char* d_sp_active,
                               double* d_task_scratch /* T x 3 */, double* d_out_v, double* d_out_g,
-                              int* d_lbfgs_stats /* T x 2 or null */, cudaStream_t st);
+                              double* d_trial_delay /* S x ntrial */, int ntrial,
+                              int* d_lbfgs_stats /* T x 2 or null */,
+                              unsigned long long* d_evals_total /* or null */, cudaStream_t st);
 // Loss3 summed per syncpoint at ntrial delays per syncpoint (simple_objective, :242-252)
 void launch_sync_trials(const DeviceData& dd, const SyncBatchDev& b, const double* d_trial_delay,
                         int ntrial, const unsigned char* d_sp_active,
@@ -122,5 +126,7 @@ float run_fp64_peak(int blocks, int threads, int iters, double* d_sink, cudaStre
 
 // bookkeeping for gpu_launches reporting
 uint64_t launch_count();
+// kernels launched through a replayed CUDA graph (the launchers only run at capture time)
+void count_launches(uint64_t n);
 
 }  // namespace rs
