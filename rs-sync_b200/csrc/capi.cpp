@@ -1413,7 +1413,8 @@ int rssync_probe_gyro(const rssync_problem* p, double* sample_rate, double* firs
     if (count) *count = p->nq;
     if (rec) {
         join_gyro(const_cast<rssync_problem*>(p));
-        std::copy(p->rec.ptr, p->rec.ptr + p->nq * 16, rec);
+        for (size_t i = 0; i < p->nq; ++i)  // back from the device's swizzled group order
+            for (size_t j = 0; j < 16; ++j) rec[i * 16 + j] = p->rec.ptr[i * 16 + (j ^ ((i & 3) * 4))];
     }
     return RSSYNC_OK;
 }

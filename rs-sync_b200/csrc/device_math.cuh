@@ -127,12 +127,31 @@ __device__ __forceinline__ uint32_t rng_index(uint64_t task_key, uint32_t iter, 
 }
 
 // ---- natural cubic spline on unit knots, 4 components (minispline.cpp:48-55, ndspline.cpp:21-27)
-// rec: n records of 16 doubles {y[4], b[4], c[4], d[4]}, 128-byte aligned.
+// rec: n records of 16 doubles {y[4], b[4], c[4], d[4]}, 128-byte aligned, groups swizzled (below).
 // General form: clamps, the linear extrapolation on both sides and the reference's right-side
 // quirk (idx = n for x >= n, so h restarts at 0).  Only reached when x leaves [0, n-1).
+// Record layout: the four 32-byte groups {y[4]}, {b[4]}, {c[4]}, {d[4]} of record i are stored at
+// group position g ^ (i & 3) inside the 128-byte record.  Lanes of a warp touch two or three
+// CONSECUTIVE records (the rays of a frame are sorted by timestamp); with the plain layout the same
+// group of different records falls into the same shared-memory banks (records are 128 bytes = all
+// 32 banks apart) and every coefficient load is a 2-3-way bank conflict; with the swizzle the groups
+// of up to four consecutive records sit in four different bank octets.
 struct Quat4 {
     double w, x, y, z;
 };
+struct RecGroups {
+    const double2 *y, *b, *c, *d;
+};
+// record: address of record r (128-byte aligned, so or-ing / xor-ing bits 5-6 selects the group)
+__device__ __forceinline__ RecGroups rec_groups(const double* record, unsigned r) {
+    const uintptr_t a = reinterpret_cast<uintptr_t>(record) | ((r & 3u) << 5);
+    RecGroups g;
+    g.y = reinterpret_cast<const double2*>(a);
+    g.b = reinterpret_cast<const double2*>(a ^ 32u);
+    g.c = reinterpret_cast<const double2*>(a ^ 64u);
+    g.d = reinterpret_cast<const double2*>(a ^ 96u);
+    return g;
+}
 __device__ __noinline__ Quat4 spline_eval4_edges(const double* __restrict__ rec, int n, double x) {
     const double fl = floor(x);
     const double idxf = fl < 0.0 ? 0.0 : (fl > (double)n ? (double)n : fl);
@@ -140,11 +159,11 @@ __device__ __noinline__ Quat4 spline_eval4_edges(const double* __restrict__ rec,
     int r = (int)idxf;
     r = r > n - 1 ? n - 1 : r;
     const bool extrap = (x < idxf) || (x > (double)(n - 1));
-    const double2* p = reinterpret_cast<const double2*>(rec + (size_t)r * 16);
-    const double2 y01 = __ldg(p + 0), y23 = __ldg(p + 1);
-    const double2 b01 = __ldg(p + 2), b23 = __ldg(p + 3);
-    const double2 c01 = __ldg(p + 4), c23 = __ldg(p + 5);
-    double2 d01 = __ldg(p + 6), d23 = __ldg(p + 7);
+    const RecGroups p = rec_groups(rec + (size_t)r * 16, (unsigned)r);
+    const double2 y01 = __ldg(p.y), y23 = __ldg(p.y + 1);
+    const double2 b01 = __ldg(p.b), b23 = __ldg(p.b + 1);
+    const double2 c01 = __ldg(p.c), c23 = __ldg(p.c + 1);
+    double2 d01 = __ldg(p.d), d23 = __ldg(p.d + 1);
     if (extrap) { d01.x = d01.y = d23.x = d23.y = 0.0; }
     Quat4 q;
     q.w = fma(fma(fma(d01.x, h, c01.x), h, b01.x), h, y01.x);
@@ -162,11 +181,11 @@ __device__ __forceinline__ void spline_eval4(const double* __restrict__ rec, int
         return;
     }
     const double h = x - (double)r;
-    const double2* p = reinterpret_cast<const double2*>(rec + (size_t)r * 16);
-    const double2 y01 = __ldg(p + 0), y23 = __ldg(p + 1);
-    const double2 b01 = __ldg(p + 2), b23 = __ldg(p + 3);
-    const double2 c01 = __ldg(p + 4), c23 = __ldg(p + 5);
-    const double2 d01 = __ldg(p + 6), d23 = __ldg(p + 7);
+    const RecGroups p = rec_groups(rec + (size_t)r * 16, (unsigned)r);
+    const double2 y01 = __ldg(p.y), y23 = __ldg(p.y + 1);
+    const double2 b01 = __ldg(p.b), b23 = __ldg(p.b + 1);
+    const double2 c01 = __ldg(p.c), c23 = __ldg(p.c + 1);
+    const double2 d01 = __ldg(p.d), d23 = __ldg(p.d + 1);
     q[0] = fma(fma(fma(d01.x, h, c01.x), h, b01.x), h, y01.x);
     q[1] = fma(fma(fma(d01.y, h, c01.y), h, b01.y), h, y01.y);
     q[2] = fma(fma(fma(d23.x, h, c23.x), h, b23.x), h, y23.x);

@@ -174,11 +174,20 @@ __device__ __forceinline__ void tma_load_1d(void* dst_smem, const void* src_gmem
 // difference from 2^52 is the exact (double)floor(x) of the contract's h = x - floor(x).  An index
 // outside the window is clamped and remembered; such a task (none has been observed) is recomputed
 // through the general path.
-__device__ __forceinline__ void spline_eval4_staged(const double* __restrict__ sRec, unsigned at,
-                                                    double h, double q[4]) {
-    const double2* p = reinterpret_cast<const double2*>(sRec + (size_t)at * 16);
-    const double2 y01 = p[0], y23 = p[1], b01 = p[2], b23 = p[3];
-    const double2 c01 = p[4], c23 = p[5], d01 = p[6], d23 = p[7];
+__device__ __forceinline__ double2 lds_f64x2(uint32_t addr) {
+    double2 v;
+    asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "r"(addr));
+    return v;
+}
+__device__ __forceinline__ void spline_eval4_staged(uint32_t sRecAddr, unsigned at, unsigned r, double h,
+                                                    double q[4]) {
+    // the staged copy keeps the global layout: record r's groups are swizzled by r & 3 (rec_groups,
+    // device_math.cuh).  Explicit shared-space loads: address arithmetic with xor hides the address
+    // space from the compiler, which would fall back to generic loads.
+    const uint32_t ay = (sRecAddr + at * 128u) | ((r & 3u) << 5);
+    const uint32_t ab = ay ^ 32u, ac = ay ^ 64u, ad = ay ^ 96u;
+    const double2 y01 = lds_f64x2(ay), y23 = lds_f64x2(ay + 16u), b01 = lds_f64x2(ab), b23 = lds_f64x2(ab + 16u);
+    const double2 c01 = lds_f64x2(ac), c23 = lds_f64x2(ac + 16u), d01 = lds_f64x2(ad), d23 = lds_f64x2(ad + 16u);
     q[0] = fma(fma(fma(d01.x, h, c01.x), h, b01.x), h, y01.x);
     q[1] = fma(fma(fma(d01.y, h, c01.y), h, b01.y), h, y01.y);
     q[2] = fma(fma(fma(d23.x, h, c23.x), h, b23.x), h, y23.x);
@@ -194,6 +203,7 @@ __device__ __forceinline__ unsigned build_rows_staged(const DeviceData& dd, cons
     const int NPAIR = pairs_for(NP);
     const double kTwo52 = 4503599627370496.0;
     const unsigned last = (unsigned)(rec_cnt - 1);
+    const uint32_t sRecAddr = smem_u32(sRec);
     unsigned outside = 0u;
     for (int s = 0; s < nslots; ++s) {
         const int i = s * 32 + lane;
@@ -204,9 +214,10 @@ __device__ __forceinline__ unsigned build_rows_staged(const DeviceData& dd, cons
         const unsigned ia = (unsigned)(__double2loint(fa) - rec_first);
         const unsigned ib = (unsigned)(__double2loint(fb) - rec_first);
         outside |= (ia > last ? 1u : 0u) | (ib > last ? 1u : 0u);
+        const unsigned ca = min(ia, last), cb = min(ib, last);
         double qa[4], qb[4], ar[3], br[3], na, nb;
-        spline_eval4_staged(sRec, min(ia, last), xa - (fa - kTwo52), qa);
-        spline_eval4_staged(sRec, min(ib, last), xb - (fb - kTwo52), qb);
+        spline_eval4_staged(sRecAddr, ca, ca + (unsigned)rec_first, xa - (fa - kTwo52), qa);
+        spline_eval4_staged(sRecAddr, cb, cb + (unsigned)rec_first, xb - (fb - kTwo52), qb);
         derotate_unnormalised(qa, t[64], t[96], t[128], ar, na);
         derotate_unnormalised(qb, t[160], t[192], t[224], br, nb);
         const double sc = 1.0 / (na * nb);

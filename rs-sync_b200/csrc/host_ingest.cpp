@@ -52,6 +52,9 @@ void solve_component(const double* y, size_t n, size_t stride, int comp, double*
     double c_prev = 0.0, b_prev = 0.0, d_prev = 0.0;
     double c_i = row[0].rhs / row[0].diag;
     for (size_t i = 0; i < n; ++i) {
+        // group g of record i (y, b, c, d = 0..3) lives at group position g ^ (i & 3): see
+        // rec_groups in device_math.cuh
+        const size_t sw = (i & 3) * 4;
         double* out = rec + i * 16 + comp;
         const double yi = y[i * stride];
         double b, d;
@@ -59,13 +62,13 @@ void solve_component(const double* y, size_t n, size_t stride, int comp, double*
             const double c_next = row[i + 1].rhs / row[i + 1].diag;
             d = 1.0 / 3.0 * (c_next - c_i);
             b = (y[(i + 1) * stride] - yi) - 1.0 / 3.0 * (2.0 * c_i + c_next);
-            out[0] = yi; out[4] = b; out[8] = c_i; out[12] = d;
+            out[0 ^ sw] = yi; out[4 ^ sw] = b; out[8 ^ sw] = c_i; out[12 ^ sw] = d;
             c_prev = c_i; b_prev = b; d_prev = d;
             c_i = c_next;
         } else {
             d = 0.0;
             b = (3.0 * d_prev + 2.0 * c_prev) + b_prev;
-            out[0] = yi; out[4] = b; out[8] = c_i; out[12] = d;
+            out[0 ^ sw] = yi; out[4 ^ sw] = b; out[8 ^ sw] = c_i; out[12 ^ sw] = d;
         }
     }
 }
