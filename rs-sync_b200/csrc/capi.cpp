@@ -7,6 +7,7 @@
 
 #include <algorithm>
 #include <atomic>
+#include <chrono>
 #include <cmath>
 #include <condition_variable>
 #include <cstdio>
@@ -98,6 +99,20 @@ struct PinBuf {
     }
 };
 
+// RSSYNC_DEBUG_TIMING=1: wall-clock marks of the host-side ingest on stderr
+struct DebugTimer {
+    bool on;
+    std::chrono::steady_clock::time_point t0;
+    const char* who;
+    explicit DebugTimer(const char* w) : on(std::getenv("RSSYNC_DEBUG_TIMING") != nullptr), t0(std::chrono::steady_clock::now()), who(w) {}
+    void mark(const char* what) {
+        if (!on) return;
+        const auto t = std::chrono::steady_clock::now();
+        std::fprintf(stderr, "[%s] %s +%.3f ms\n", who, what, std::chrono::duration<double, std::milli>(t - t0).count());
+        t0 = t;
+    }
+};
+
 bool all_finite(const double* p, size_t n) {
     for (size_t i = 0; i < n; ++i)
         if (!std::isfinite(p[i])) return false;
@@ -166,6 +181,12 @@ struct rssync_problem {
     // first thing that needs the records.
     std::thread gyro_worker;
     std::vector<double> gyro_copy;
+    // the worker also starts the records' host->device copy on its own stream as soon as they are
+    // built; the problem's stream waits for ev_gyro before the first kernel that reads them
+    cudaStream_t gyro_stream = nullptr;
+    cudaEvent_t ev_gyro = nullptr;
+    bool gyro_copy_queued = false;    // written by the worker, read after join
+    cudaError_t gyro_copy_err = cudaSuccess;
     // eager host->device copies issued by the bulk track ingest; host writes to the pinned arena
     // wait for them
     cudaEvent_t ev_arena = nullptr;
@@ -260,8 +281,8 @@ int wait_arena_copies(rssync_problem* p) {
 }
 
 // device arena large enough for `used` rays, contents preserved
-int reserve_device_arena(rssync_problem* p) {
-    const size_t want = std::max(p->used, p->h_orig.cap);
+int reserve_device_arena(rssync_problem* p, size_t at_least = 0) {
+    const size_t want = std::max(std::max(p->used, p->h_orig.cap), at_least);
     CUDA_TRY(p, p->d_rays.grow(want * 8, p->dev_used * 8, p->stream));
     CUDA_TRY(p, p->d_orig.grow(want, p->dev_used, p->stream));
     CUDA_TRY(p, p->d_pos.grow(want, p->dev_used, p->stream));
@@ -280,11 +301,20 @@ void add_pending(rssync_problem* p, size_t a, size_t b) {
 }
 
 int flush(rssync_problem* p) {
+    DebugTimer tm("flush");
     CUDA_TRY(p, cudaSetDevice(p->device));
     join_gyro(p);
+    tm.mark("join gyro");
     if (p->gyro_dirty) {
-        CUDA_TRY(p, p->d_rec.reserve(p->nq * 16));
-        if (int rc = h2d(p, p->d_rec.ptr, p->rec.ptr, p->nq * 16 * sizeof(double))) return rc;
+        if (p->gyro_copy_queued) {  // the worker already queued the copy on gyro_stream
+            p->gyro_copy_queued = false;
+            CUDA_TRY(p, p->gyro_copy_err);
+            CUDA_TRY(p, cudaStreamWaitEvent(p->stream, p->ev_gyro, 0));
+            p->h2d += p->nq * 16 * sizeof(double);
+        } else {
+            CUDA_TRY(p, p->d_rec.reserve(p->nq * 16));
+            if (int rc = h2d(p, p->d_rec.ptr, p->rec.ptr, p->nq * 16 * sizeof(double))) return rc;
+        }
         p->gyro_dirty = false;
     }
     if (!p->pending.empty()) {
@@ -310,6 +340,27 @@ int select_frames(rssync_problem* p, int64_t begin, int64_t end_exclusive,
         out.push_back(fd);
         max_n = std::max(max_n, (int)fd.n);
     }
+    return RSSYNC_OK;
+}
+
+// Build the spline records of `count` quaternions at `src` into the pinned buffer on a worker thread
+// and start their copy to the device from there (ndspline::make, core_private.cpp:139 / :189).
+int start_gyro_worker(rssync_problem* p, const double* src, size_t count) {
+    CUDA_TRY(p, p->d_rec.reserve(count * 16));
+    if (!p->gyro_stream) CUDA_TRY(p, cudaStreamCreateWithFlags(&p->gyro_stream, cudaStreamNonBlocking));
+    if (!p->ev_gyro) CUDA_TRY(p, cudaEventCreateWithFlags(&p->ev_gyro, cudaEventDisableTiming));
+    double* rec = p->rec.ptr;
+    double* d_rec = p->d_rec.ptr;
+    p->gyro_copy_queued = false;
+    p->gyro_worker = std::thread([=]() {
+        rs::build_spline_records(src, count, rec);
+        cudaError_t e = cudaSetDevice(p->device);
+        if (e == cudaSuccess)
+            e = cudaMemcpyAsync(d_rec, rec, count * 16 * sizeof(double), cudaMemcpyHostToDevice, p->gyro_stream);
+        if (e == cudaSuccess) e = cudaEventRecord(p->ev_gyro, p->gyro_stream);
+        p->gyro_copy_err = e;
+        p->gyro_copy_queued = true;
+    });
     return RSSYNC_OK;
 }
 
@@ -691,6 +742,8 @@ void rssync_destroy(rssync_problem* p) {
     join_gyro(p);
     if (p->arena_copy_pending) cudaEventSynchronize(p->ev_arena);
     if (p->ev_arena) cudaEventDestroy(p->ev_arena);
+    if (p->gyro_stream) { cudaStreamSynchronize(p->gyro_stream); cudaStreamDestroy(p->gyro_stream); }
+    if (p->ev_gyro) cudaEventDestroy(p->ev_gyro);
     p->d_rec.release();
     p->rec.release();
     p->h_rays.release(); p->d_rays.release();
@@ -719,14 +772,12 @@ int rssync_set_gyro_fixed(rssync_problem* p, const double* quats, size_t count, 
     p->q0 = first_timestamp;   // :138
     cudaSetDevice(p->device);
     if (p->gyro_dirty == false && p->nq) CUDA_TRY(p, cudaStreamSynchronize(p->stream));  // records in flight
+    if (p->gyro_stream) CUDA_TRY(p, cudaStreamSynchronize(p->gyro_stream));  // a copy never waited for
     CUDA_TRY(p, p->rec.reserve(count * 16));
     p->gyro_copy.assign(quats, quats + 4 * count);  // the caller's buffer is only borrowed
     p->nq = count;
     p->gyro_dirty = true;
-    double* rec = p->rec.ptr;
-    const double* src = p->gyro_copy.data();
-    p->gyro_worker = std::thread([=]() { rs::build_spline_records(src, count, rec); });  // :139
-    return RSSYNC_OK;
+    return start_gyro_worker(p, p->gyro_copy.data(), count);  // :139
 }
 
 int rssync_set_gyro_var(rssync_problem* p, const int64_t* ts, const double* quats, size_t count) {
@@ -743,15 +794,13 @@ int rssync_set_gyro_var(rssync_problem* p, const int64_t* ts, const double* quat
     p->q0 = q0;
     cudaSetDevice(p->device);
     if (p->gyro_dirty == false && p->nq) CUDA_TRY(p, cudaStreamSynchronize(p->stream));
+    if (p->gyro_stream) CUDA_TRY(p, cudaStreamSynchronize(p->gyro_stream));
     CUDA_TRY(p, p->rec.reserve(rq.size() * 4));
     p->gyro_copy.swap(rq);
     const size_t n_out = p->gyro_copy.size() / 4;
     p->nq = n_out;
     p->gyro_dirty = true;
-    double* rec = p->rec.ptr;
-    const double* src = p->gyro_copy.data();
-    p->gyro_worker = std::thread([=]() { rs::build_spline_records(src, n_out, rec); });  // :189
-    return RSSYNC_OK;
+    return start_gyro_worker(p, p->gyro_copy.data(), n_out);  // :189
 }
 
 }  // extern "C"
@@ -767,6 +816,42 @@ int validate_track(const double* ts_a, const double* ts_b, const double* rays_a,
     if (!all_finite(rays_b, 3 * count)) { *msg = "set-track-result: non-finite numbers in rays_b"; return RSSYNC_E_NONFINITE; }
     if (!all_finite(ts_a, count)) { *msg = "set-track-result: non-finite numbers in ts_a"; return RSSYNC_E_NONFINITE; }
     if (!all_finite(ts_b, count)) { *msg = "set-track-result: non-finite numbers in ts_b"; return RSSYNC_E_NONFINITE; }
+    return RSSYNC_OK;
+}
+
+// copy n doubles, report whether all are finite, and fold them into [lo, hi] when asked to:
+// x * 0.0 is +-0 for finite x and NaN otherwise, so one accumulator carries the check
+inline bool copy_checked(double* dst, const double* src, size_t n, double* lo, double* hi) {
+    double acc = 0.0, l = lo ? *lo : 0.0, h = hi ? *hi : 0.0;
+    for (size_t i = 0; i < n; ++i) {
+        const double v = src[i];
+        dst[i] = v;
+        acc += v * 0.0;
+        if (lo) { l = v < l ? v : l; h = v > h ? v : h; }
+    }
+    if (lo) { *lo = l; *hi = h; }
+    return acc == 0.0;
+}
+
+// SetTrackResult, stage 1 of the bulk form: validate_track fused with the copy into the staging
+// buffers and with the frame's timestamp bounds (one pass over the caller's data)
+int stage_track(const double* ts_a, const double* ts_b, const double* rays_a, const double* rays_b,
+                size_t count, double* s_ts_a, double* s_ts_b, double* s_rays_a, double* s_rays_b,
+                double& ts_lo, double& ts_hi, const char** msg) {
+    if (count && (!ts_a || !ts_b || !rays_a || !rays_b)) { *msg = "set-track-result: null buffer"; return RSSYNC_E_INVALID; }
+    if (count > (size_t)rs::kMaxRaysPerFrame) { *msg = "set-track-result: more than 512 rays in one frame is not supported"; return RSSYNC_E_INVALID; }
+    double lo = count ? ts_a[0] : 0.0, hi = lo;
+    const bool ok_ra = copy_checked(s_rays_a, rays_a, 3 * count, nullptr, nullptr);
+    const bool ok_rb = copy_checked(s_rays_b, rays_b, 3 * count, nullptr, nullptr);
+    const bool ok_ta = copy_checked(s_ts_a, ts_a, count, &lo, &hi);
+    const bool ok_tb = copy_checked(s_ts_b, ts_b, count, &lo, &hi);
+    ts_lo = lo;
+    ts_hi = hi;
+    // the reference's order of checks (core_private.cpp:199-202)
+    if (!ok_ra) { *msg = "set-track-result: non-finite numbers in rays_a"; return RSSYNC_E_NONFINITE; }
+    if (!ok_rb) { *msg = "set-track-result: non-finite numbers in rays_b"; return RSSYNC_E_NONFINITE; }
+    if (!ok_ta) { *msg = "set-track-result: non-finite numbers in ts_a"; return RSSYNC_E_NONFINITE; }
+    if (!ok_tb) { *msg = "set-track-result: non-finite numbers in ts_b"; return RSSYNC_E_NONFINITE; }
     return RSSYNC_OK;
 }
 
@@ -942,76 +1027,89 @@ int rssync_set_track_batch(rssync_problem* p, size_t n_frames, const int64_t* fr
                            const size_t* counts, const double* ts_a, const double* ts_b,
                            const double* rays_a, const double* rays_b) {
     if (!p || (n_frames && (!frames || !counts))) return RSSYNC_E_INVALID;
+    DebugTimer tm("set_track_batch");
     std::vector<size_t> at(n_frames + 1, 0);
     for (size_t i = 0; i < n_frames; ++i) at[i + 1] = at[i] + counts[i];
     std::vector<int> rc(n_frames, 0);
     std::vector<const char*> msg(n_frames, nullptr);
-    parallel_frames(n_frames, [&](size_t i, size_t) {
-        rc[i] = validate_track(ts_a + at[i], ts_b + at[i], rays_a + 3 * at[i], rays_b + 3 * at[i], counts[i], &msg[i]);
-    });
-    size_t n_ok = n_frames;
-    for (size_t i = 0; i < n_frames; ++i)
-        if (rc[i]) { n_ok = i; break; }
-    if (int r = wait_arena_copies(p)) return r;
-    std::vector<FrameDesc*> fds(n_ok);
-    for (size_t i = 0; i < n_ok; ++i)
-        if (int r = place_track(p, frames[i], counts[i], &fds[i])) return r;
-    auto frame_end = [&](size_t i) { return (size_t)fds[i]->off + (counts[i] + 31) / 32 * 32; };
-    if (n_ok >= 64) {
+    if (n_frames >= 64) {
         // Large batch: the sort by ts_a and the transpose into tiles run on the device
-        // (ingest_rays_kernel).  The host only copies the caller's buffers into pinned staging
-        // memory and takes the per-frame timestamp bounds; each sixth of the batch is copied to the
-        // device and ingested as soon as it is staged, overlapping the staging of the next.
+        // (ingest_rays_kernel).  The host makes ONE pass over the caller's buffers: each value is
+        // checked (the reference's panic conditions, core_private.cpp:199-202) while it is copied
+        // into pinned staging memory, and the per-frame timestamp bounds are taken on the way.
+        // Each sixth of the batch is placed, copied to the device and ingested as soon as it is
+        // staged, overlapping the staging of the next.
         cudaSetDevice(p->device);
-        const size_t total = at[n_ok];
-        if (int r = reserve_device_arena(p)) return r;
+        if (int r = wait_arena_copies(p)) return r;
+        const size_t total = at[n_frames];
         CUDA_TRY(p, p->h_stage.reserve(8 * total + 1));
         CUDA_TRY(p, p->d_stage.reserve(8 * total + 1));
-        CUDA_TRY(p, p->d_pixframes.reserve(n_ok));
+        CUDA_TRY(p, p->d_pixframes.reserve(n_frames));
         if (!p->ev_arena) CUDA_TRY(p, cudaEventCreateWithFlags(&p->ev_arena, cudaEventDisableTiming));
         std::vector<rs::PixelFrame>& pf = p->pixframes_host;
-        pf.resize(n_ok);
-        for (size_t i = 0; i < n_ok; ++i) pf[i] = rs::PixelFrame{fds[i]->off, fds[i]->n, (int64_t)at[i], 0.0, 0.0};
-        if (int r = h2d(p, p->d_pixframes.ptr, pf.data(), n_ok * sizeof(rs::PixelFrame))) return r;
+        pf.resize(n_frames);
+        std::vector<double> lo_ts(n_frames), hi_ts(n_frames);
+        // room for the whole batch appended at the end of the arena (the most it can take)
+        size_t padded_total = 0;
+        for (size_t i = 0; i < n_frames; ++i) padded_total += (counts[i] + 31) / 32 * 32;
+        if (int r = reserve_device_arena(p, p->used + padded_total)) return r;
+        tm.mark("reserve");
         double* hs = p->h_stage.ptr;
         double* ds = p->d_stage.ptr;
         const size_t n_chunks = 6;
-        for (size_t c = 0; c < n_chunks; ++c) {
-            const size_t lo = n_ok * c / n_chunks, hi = n_ok * (c + 1) / n_chunks;
+        size_t n_ok = n_frames;
+        for (size_t c = 0; c < n_chunks && n_ok == n_frames; ++c) {
+            const size_t lo = n_frames * c / n_chunks, hi = n_frames * (c + 1) / n_chunks;
             if (lo == hi) continue;
             parallel_frames(hi - lo, [&](size_t k, size_t) {
                 const size_t i = lo + k, n = counts[i], a = at[i];
-                std::memcpy(hs + a, ts_a + a, n * sizeof(double));
-                std::memcpy(hs + total + a, ts_b + a, n * sizeof(double));
-                std::memcpy(hs + 2 * total + 3 * a, rays_a + 3 * a, 3 * n * sizeof(double));
-                std::memcpy(hs + 5 * total + 3 * a, rays_b + 3 * a, 3 * n * sizeof(double));
-                double l = n ? ts_a[a] : 0.0, h = l;
-                for (size_t j = 0; j < n; ++j) {
-                    l = std::min(l, std::min(ts_a[a + j], ts_b[a + j]));
-                    h = std::max(h, std::max(ts_a[a + j], ts_b[a + j]));
-                }
-                fds[i]->ts_lo = l;
-                fds[i]->ts_hi = h;
+                rc[i] = stage_track(ts_a + a, ts_b + a, rays_a + 3 * a, rays_b + 3 * a, n, hs + a, hs + total + a,
+                                    hs + 2 * total + 3 * a, hs + 5 * total + 3 * a, lo_ts[i], hi_ts[i], &msg[i]);
             });
-            const size_t a = at[lo], n = at[hi] - at[lo];
+            tm.mark("stage + validate chunk");
+            size_t end = hi;
+            for (size_t i = lo; i < hi; ++i)
+                if (rc[i]) { end = i; n_ok = i; break; }
+            for (size_t i = lo; i < end; ++i) {
+                FrameDesc* fd = nullptr;
+                if (int r = place_track(p, frames[i], counts[i], &fd)) return r;
+                fd->ts_lo = lo_ts[i];
+                fd->ts_hi = hi_ts[i];
+                pf[i] = rs::PixelFrame{fd->off, fd->n, (int64_t)at[i], 0.0, 0.0};
+            }
+            if (end == lo) break;
+            if (int r = reserve_device_arena(p)) return r;
+            tm.mark("place chunk");
+            const size_t a = at[lo], n = at[end] - at[lo];
+            if (int r = h2d(p, p->d_pixframes.ptr + lo, pf.data() + lo, (end - lo) * sizeof(rs::PixelFrame))) return r;
             if (int r = h2d(p, ds + a, hs + a, n * sizeof(double))) return r;
             if (int r = h2d(p, ds + total + a, hs + total + a, n * sizeof(double))) return r;
             if (int r = h2d(p, ds + 2 * total + 3 * a, hs + 2 * total + 3 * a, 3 * n * sizeof(double))) return r;
             if (int r = h2d(p, ds + 5 * total + 3 * a, hs + 5 * total + 3 * a, 3 * n * sizeof(double))) return r;
-            rs::launch_ingest_rays(p->d_pixframes.ptr + lo, (int)(hi - lo), ds, ds + total, ds + 2 * total,
+            rs::launch_ingest_rays(p->d_pixframes.ptr + lo, (int)(end - lo), ds, ds + total, ds + 2 * total,
                                    ds + 5 * total, p->d_rays.ptr, p->d_orig.ptr, p->d_pos.ptr, p->stream);
             CUDA_TRY(p, cudaGetLastError());
+            p->dev_used = std::max(p->dev_used, p->used);  // a later growth of the arena keeps this chunk
+            tm.mark("enqueue chunk");
         }
-        p->dev_used = std::max(p->dev_used, p->used);
         // the staging buffers are reused by the next ingest call, which waits for this event
         CUDA_TRY(p, cudaEventRecord(p->ev_arena, p->stream));
         p->arena_copy_pending = true;
-    } else {
-        std::vector<std::pair<double, int32_t>> scratch;
-        for (size_t i = 0; i < n_ok; ++i) {
-            fill_track(p, fds[i], ts_a + at[i], ts_b + at[i], rays_a + 3 * at[i], rays_b + 3 * at[i], counts[i], scratch);
-            add_pending(p, (size_t)fds[i]->off, frame_end(i));
-        }
+        if (n_ok < n_frames) { p->err = msg[n_ok]; return rc[n_ok]; }
+        return RSSYNC_OK;
+    }
+    size_t n_ok = n_frames;
+    for (size_t i = 0; i < n_frames; ++i) {
+        rc[i] = validate_track(ts_a + at[i], ts_b + at[i], rays_a + 3 * at[i], rays_b + 3 * at[i], counts[i], &msg[i]);
+        if (rc[i]) { n_ok = i; break; }
+    }
+    if (int r = wait_arena_copies(p)) return r;
+    std::vector<std::pair<double, int32_t>> scratch;
+    for (size_t i = 0; i < n_ok; ++i) {
+        FrameDesc* fd = nullptr;
+        if (int r = place_track(p, frames[i], counts[i], &fd)) return r;
+        fill_track(p, fd, ts_a + at[i], ts_b + at[i], rays_a + 3 * at[i], rays_b + 3 * at[i], counts[i], scratch);
+        add_pending(p, (size_t)fd->off, (size_t)fd->off + (counts[i] + 31) / 32 * 32);
     }
     if (n_ok < n_frames) { p->err = msg[n_ok]; return rc[n_ok]; }
     return RSSYNC_OK;
@@ -1288,7 +1386,7 @@ int rssync_orientation_search(rssync_problem* p, const double* timestamps_s, con
         }
         pr.nq = rq.size() / 4;
         pr.rec.resize(pr.nq * 16);
-        rs::build_spline_records(rq.data(), pr.nq, pr.rec.data(), false);
+        rs::build_spline_records(rq.data(), pr.nq, pr.rec.data());
     };
     if (n_orient >= 4) {
         std::function<void(size_t, size_t)> fn = prepare;
@@ -1303,6 +1401,8 @@ int rssync_orientation_search(rssync_problem* p, const double* timestamps_s, con
         join_gyro(p);
         cudaSetDevice(p->device);
         if (p->gyro_dirty == false && p->nq) CUDA_TRY(p, cudaStreamSynchronize(p->stream));
+        if (p->gyro_stream) CUDA_TRY(p, cudaStreamSynchronize(p->gyro_stream));
+        p->gyro_copy_queued = false;
         CUDA_TRY(p, p->rec.reserve(pr.rec.size()));
         std::memcpy(p->rec.ptr, pr.rec.data(), pr.rec.size() * sizeof(double));
         p->sr = pr.sr;

@@ -8,70 +8,146 @@
 
 #include <algorithm>
 #include <cmath>
+#include <memory>
+#include <mutex>
 #include <thread>
 
 namespace rs {
 
 namespace {
 
-struct TriRow {
-    double sub, diag, sup, rhs;
+// ndspline::make (ndspline.cpp:13-19) = spline::set_points (minispline.cpp:3-46) per component:
+// unit-spaced knots; interior rows [1/3, 4/3, 1/3] with rhs y[i+1] - 2 y[i] + y[i-1], natural
+// boundary rows [., 2, 0] / [0, 2, .] with rhs 0; eliminate downwards (:22-26), then upwards
+// (:28-32), divide (:34), then d and b per interval (:38-44).
+//
+// The matrix entries and both elimination factors do not depend on the data, only on n, so they are
+// computed once for the four components -- by the same operations on the same values as the
+// reference's per-component loop, hence the same bits.  The interior rows start out identical, so
+// the elimination state reaches a floating-point fixed point after a few dozen rows; from there on
+// every row repeats it exactly and the (division-bound) recurrence is not re-evaluated.  What
+// remains sequential per component is rhs[i+1] -= rhs[i] * f[i] and its mirror image, which run
+// for the four components side by side.
+struct Elimination {
+    std::vector<double> f_down;  // f_down[i]: factor with which row i is subtracted from row i + 1
+    std::vector<double> f_up;    // f_up[i]:   factor with which row i is subtracted from row i - 1
+    std::vector<double> diag;    // diagonal after both sweeps
 };
 
-// One component of ndspline::make (ndspline.cpp:13-19): spline::set_points, minispline.cpp:3-46.
-// Unit-spaced knots; interior rows [1/3, 4/3, 1/3] with rhs y[i+1] - 2 y[i] + y[i-1], natural
-// boundary rows [., 2, 0] / [0, 2, .] with rhs 0; eliminate downwards, then upwards, divide.
-void solve_component(const double* y, size_t n, size_t stride, int comp, double* rec) {
-    std::vector<TriRow> row(n);
-    row[0] = TriRow{0.0, 2.0, 0.0, 0.0};
-    row[n - 1] = TriRow{0.0, 2.0, 0.0, 0.0};
-    for (size_t i = 1; i + 1 < n; ++i) {
-        const double yi = y[i * stride];
-        row[i].sub = 1.0 / 3.0;
-        row[i].diag = 2.0 / 3.0 * 2.0;
-        row[i].sup = 1.0 / 3.0;
-        row[i].rhs = (y[(i + 1) * stride] - 2 * yi) + y[(i - 1) * stride];
+Elimination eliminate(size_t n) {
+    Elimination e;
+    e.f_down.assign(n, 0.0);
+    e.f_up.assign(n, 0.0);
+    e.diag.assign(n, 2.0 / 3.0 * 2.0);
+    std::vector<double> sub(n, 1.0 / 3.0), sup(n, 1.0 / 3.0);
+    std::vector<double>& diag = e.diag;
+    sub[0] = 0.0; diag[0] = 2.0; sup[0] = 0.0;
+    sub[n - 1] = 0.0; diag[n - 1] = 2.0; sup[n - 1] = 0.0;
+    // downwards, minispline.cpp:22-26: row i clears the sub-diagonal of row i + 1, for i + 2 < n
+    size_t steady = n;  // rows steady .. n-2 leave this sweep in the same state
+    for (size_t i = 0; i + 2 < n; ++i) {
+        const double f = 1. / diag[i] * sub[i + 1];
+        sub[i + 1] -= diag[i] * f;
+        diag[i + 1] -= sup[i] * f;
+        e.f_down[i] = f;
+        // row i + 1 came out exactly like row i (both interior): the rows below start out like
+        // row i + 1 did, so each repeats this step with the same operands
+        if (i >= 1 && sub[i + 1] == sub[i] && diag[i + 1] == diag[i] && f == e.f_down[i - 1]) {
+            for (size_t j = i + 1; j + 2 < n; ++j) {
+                sub[j + 1] = sub[i];
+                diag[j + 1] = diag[i];
+                e.f_down[j] = f;
+            }
+            steady = i;
+            break;
+        }
     }
-    for (size_t i = 0; i + 2 < n; ++i) {  // minispline.cpp:22-26
-        TriRow& cur = row[i];
-        TriRow& nxt = row[i + 1];
-        const double f = 1. / cur.diag * nxt.sub;
-        nxt.sub -= cur.diag * f;
-        nxt.diag -= cur.sup * f;
-        nxt.rhs -= cur.rhs * f;
+    // upwards, :28-32: row i clears the super-diagonal of row i - 1, for i > 1
+    for (size_t i = n - 1; i > 1; --i) {
+        const double f = 1. / diag[i] * sup[i - 1];
+        diag[i - 1] -= sub[i] * f;
+        sup[i - 1] -= diag[i] * f;
+        e.f_up[i] = f;
+        // rows i - 1 and i entered this sweep in the same state (both in the steady range, as is
+        // row i + 1, whose sub-diagonal entered step i + 1) and row i - 1 left it with row i's
+        // diagonal: step i - 1 therefore sees the operands of step i, and so on up to `steady`
+        if (i + 1 <= n - 2 && i - 1 > steady && diag[i - 1] == diag[i]) {
+            for (size_t j = i - 1; j > steady; --j) {  // step j writes row j - 1 >= steady
+                diag[j - 1] = diag[i - 1];
+                sup[j - 1] = sup[i - 1];
+                e.f_up[j] = f;
+            }
+            i = steady + 1;  // the loop continues with step `steady`
+        }
     }
-    for (size_t i = n - 1; i > 1; --i) {  // :28-32
-        TriRow& cur = row[i];
-        TriRow& prv = row[i - 1];
-        const double f = 1. / cur.diag * prv.sup;
-        prv.diag -= cur.sub * f;
-        prv.sup -= cur.diag * f;
-        prv.rhs -= cur.rhs * f;
+    return e;
+}
+
+}  // namespace
+
+void build_spline_records(const double* quats, size_t n, double* rec) {
+    // the elimination only depends on n: the orientation search builds 48 splines of one length
+    static std::mutex mu;
+    static std::shared_ptr<const Elimination> cached;
+    static size_t cached_n = 0;
+    std::shared_ptr<const Elimination> ep;
+    {
+        std::lock_guard<std::mutex> lk(mu);
+        if (cached && cached_n == n) ep = cached;
     }
-    // second-derivative coefficients c, then d and b per interval (:34-44)
-    double c_prev = 0.0, b_prev = 0.0, d_prev = 0.0;
-    double c_i = row[0].rhs / row[0].diag;
+    if (!ep) {
+        ep = std::make_shared<const Elimination>(eliminate(n));
+        std::lock_guard<std::mutex> lk(mu);
+        cached = ep;
+        cached_n = n;
+    }
+    const Elimination& e = *ep;
+    // right-hand sides of the four components, interleaved like the input.  They live in the last
+    // quarter of the output buffer: the final pass writes record i (doubles 16 i .. 16 i + 15) after
+    // reading rhs[4 (i + 1) ..], which sits at 12 n + 4 i + 4 >= 16 i + 16 for every i <= n - 1.
+    double* rhs = rec + 12 * n;
+    for (int c = 0; c < 4; ++c) rhs[c] = rhs[4 * (n - 1) + c] = 0.0;
+    for (size_t i = 1; i + 1 < n; ++i)
+        for (int c = 0; c < 4; ++c)
+            rhs[4 * i + c] = (quats[4 * (i + 1) + c] - 2 * quats[4 * i + c]) + quats[4 * (i - 1) + c];
+    for (size_t i = 0; i + 2 < n; ++i) {  // :25
+        const double f = e.f_down[i];
+        for (int c = 0; c < 4; ++c) rhs[4 * (i + 1) + c] -= rhs[4 * i + c] * f;
+    }
+    for (size_t i = n - 1; i > 1; --i) {  // :31
+        const double f = e.f_up[i];
+        for (int c = 0; c < 4; ++c) rhs[4 * (i - 1) + c] -= rhs[4 * i + c] * f;
+    }
+    // second-derivative coefficients c (:34), then d and b per interval (:38-44); group g of record i
+    // (y, b, c, d = 0..3) lives at group position g ^ (i & 3): see rec_groups in device_math.cuh
+    // (one pass over the records, the four components of a record together: whole cache lines)
+    double c_prev[4] = {0, 0, 0, 0}, b_prev[4] = {0, 0, 0, 0}, d_prev[4] = {0, 0, 0, 0}, c_i[4];
+    for (int c = 0; c < 4; ++c) c_i[c] = rhs[c] / e.diag[0];
     for (size_t i = 0; i < n; ++i) {
-        // group g of record i (y, b, c, d = 0..3) lives at group position g ^ (i & 3): see
-        // rec_groups in device_math.cuh
         const size_t sw = (i & 3) * 4;
-        double* out = rec + i * 16 + comp;
-        const double yi = y[i * stride];
-        double b, d;
+        double* out = rec + i * 16;
         if (i + 1 < n) {
-            const double c_next = row[i + 1].rhs / row[i + 1].diag;
-            d = 1.0 / 3.0 * (c_next - c_i);
-            b = (y[(i + 1) * stride] - yi) - 1.0 / 3.0 * (2.0 * c_i + c_next);
-            out[0 ^ sw] = yi; out[4 ^ sw] = b; out[8 ^ sw] = c_i; out[12 ^ sw] = d;
-            c_prev = c_i; b_prev = b; d_prev = d;
-            c_i = c_next;
+            const double dg = e.diag[i + 1];
+            for (int c = 0; c < 4; ++c) {
+                const double yi = quats[4 * i + c];
+                const double c_next = rhs[4 * (i + 1) + c] / dg;
+                const double d = 1.0 / 3.0 * (c_next - c_i[c]);
+                const double b = (quats[4 * (i + 1) + c] - yi) - 1.0 / 3.0 * (2.0 * c_i[c] + c_next);
+                out[(0 ^ sw) + c] = yi; out[(4 ^ sw) + c] = b; out[(8 ^ sw) + c] = c_i[c]; out[(12 ^ sw) + c] = d;
+                c_prev[c] = c_i[c]; b_prev[c] = b; d_prev[c] = d;
+                c_i[c] = c_next;
+            }
         } else {
-            d = 0.0;
-            b = (3.0 * d_prev + 2.0 * c_prev) + b_prev;
-            out[0 ^ sw] = yi; out[4 ^ sw] = b; out[8 ^ sw] = c_i; out[12 ^ sw] = d;
+            for (int c = 0; c < 4; ++c) {
+                const double d = 0.0;
+                const double b = (3.0 * d_prev[c] + 2.0 * c_prev[c]) + b_prev[c];
+                out[(0 ^ sw) + c] = quats[4 * i + c]; out[(4 ^ sw) + c] = b; out[(8 ^ sw) + c] = c_i[c]; out[(12 ^ sw) + c] = d;
+            }
         }
     }
 }
+
+namespace {
 
 // quat_slerp, quat.cpp:55-74
 void slerp4(const double* p, const double* q_in, double t, double* out) {
@@ -95,19 +171,6 @@ void slerp4(const double* p, const double* q_in, double t, double* out) {
 }
 
 }  // namespace
-
-void build_spline_records(const double* quats, size_t n, double* rec, bool one_thread_per_component) {
-    if (!one_thread_per_component) {
-        for (int comp = 0; comp < 4; ++comp) solve_component(quats + comp, n, 4, comp, rec);
-        return;
-    }
-    // the four components are independent sequential solves: one host thread each
-    std::thread th[3];
-    for (int comp = 1; comp < 4; ++comp)
-        th[comp - 1] = std::thread([=]() { solve_component(quats + comp, n, 4, comp, rec); });
-    solve_component(quats, n, 4, 0, rec);
-    for (auto& t : th) t.join();
-}
 
 bool integrate_gyro(const double* ts, const double* gyro, size_t count, const char* orient,
                     double* out) {

@@ -12,8 +12,7 @@ enum class IngestStatus { Ok = 0, Invalid = 1, NonFinite = 2, OutOfOrder = 3 };
 // ndspline::make (ndspline.cpp:13-19): n quaternions (w,x,y,z) -> n records of 16 doubles
 // {y[4], b[4], c[4], d[4]}, the four 32-byte groups of record i stored at group position
 // g ^ (i & 3) (the device layout, device_math.cuh rec_groups).
-void build_spline_records(const double* quats, size_t n, double* rec /* n * 16 doubles */,
-                          bool one_thread_per_component = true);
+void build_spline_records(const double* quats, size_t n, double* rec /* n * 16 doubles */);
 
 // variable-rate SetGyroQuaternions (core_private.cpp:142-190): resample onto the uniform
 // integer-microsecond grid by slerp.

@@ -264,6 +264,21 @@ def test_presync_ray_counts(rsb, oracle_loader, synth_mod, rays):
     assert int(np.argmin(cg)) == int(np.argmin(co))
 
 
+def test_bulk_ingest_into_a_fresh_arena_that_grows(rsb, synth_mod):
+    """a first bulk load larger than the arena's initial capacity (65 536 rays): the device arena
+    grows while the batch's chunks are being ingested and must keep the chunks already there"""
+    w = synth_mod.make_workload("tiny", frames=700, rays=200)
+    a = rsb.SyncProblem(seed=3).load(w, bulk=True)
+    b = rsb.SyncProblem(seed=3).load(w)  # frame by frame: host sort / transpose, one upload
+    delays = np.linspace(-0.02, 0.02, 9)
+    for lo in (0, 120, 350, 690):
+        fb = int(w.frame_ids[lo])
+        ca, fa = a.presync_grid(fb, fb + 8, delays, call_no=2, return_flags=True)
+        cb, fl = b.presync_grid(fb, fb + 8, delays, call_no=2, return_flags=True)
+        assert fa == 0 and fl == 0
+        assert np.array_equal(ca, cb)
+
+
 def test_presync_wide_delay_steps_use_global_path(rsb, oracle_loader, w_tiny):
     """delays 50 ms apart: the chunk's spline window does not fit the staging buffer, so phase A
     reads global memory; a 10 s offset leaves the gyro span entirely (spline edges)"""
