@@ -172,7 +172,11 @@ struct rssync_problem {
     std::string err;
 
     // gyro spline (OptData::quats, quats_start, sample_rate)
-    PinBuf<double> rec;  // pinned: goes to the device with one async copy
+    // pinned staging of one SetGyroQuaternions call: the samples (nq x 4), and the eliminated spline
+    // system the worker builds from them, rhs (nq x 4) and diag (nq); one async copy, then the
+    // records are finished on the device (launch_spline_finish)
+    PinBuf<double> h_gyro;
+    DevBuf<double> d_gyro;
     double q0 = 0.0, sr = 0.0;
     size_t nq = 0;
     bool gyro_dirty = false;
@@ -180,17 +184,28 @@ struct rssync_problem {
     // on a worker thread so that it overlaps the caller's SetTrackResult calls; it is joined by the
     // first thing that needs the records.
     std::thread gyro_worker;
-    std::vector<double> gyro_copy;
     // the worker also starts the records' host->device copy on its own stream as soon as they are
     // built; the problem's stream waits for ev_gyro before the first kernel that reads them
     cudaStream_t gyro_stream = nullptr;
     cudaEvent_t ev_gyro = nullptr;
-    bool gyro_copy_queued = false;    // written by the worker, read after join
-    cudaError_t gyro_copy_err = cudaSuccess;
+    cudaError_t gyro_copy_err = cudaSuccess;  // written by the worker, read after join
     // eager host->device copies issued by the bulk track ingest; host writes to the pinned arena
     // wait for them
     cudaEvent_t ev_arena = nullptr;
     bool arena_copy_pending = false;
+    // The bulk ingest runs on its own stream, one event per chunk of frames: a PreSync grid that
+    // follows evaluates the frames of a chunk as soon as that chunk has landed instead of waiting
+    // for the whole upload (the upload of C2 takes 2 ms at the 24 GB/s this host's PCIe delivers,
+    // the grid 4.5 ms).  in_flight lists the arena ranges (in rays) still being written, in stream
+    // order; anything else that touches the arena waits for all of them first.
+    struct InFlight {
+        size_t lo, hi;
+        cudaEvent_t ev;
+    };
+    cudaStream_t copy_stream = nullptr;
+    std::vector<InFlight> in_flight;
+    std::vector<cudaEvent_t> ev_pool;
+    cudaEvent_t ev_order = nullptr;
     DevBuf<double> d_rec;
 
     // ray arena (DeviceData::rays): frames appended in arrival order, each padded to a multiple of
@@ -280,9 +295,29 @@ int wait_arena_copies(rssync_problem* p) {
     return RSSYNC_OK;
 }
 
+// the problem's stream waits (on the device) for every bulk-ingest chunk still in flight
+int wait_in_flight(rssync_problem* p, size_t upto = (size_t)-1) {
+    size_t n = std::min(upto, p->in_flight.size());
+    if (n == 0) return RSSYNC_OK;
+    // the chunks were queued on one stream: the last event covers the earlier ones
+    CUDA_TRY(p, cudaStreamWaitEvent(p->stream, p->in_flight[n - 1].ev, 0));
+    for (size_t i = 0; i < n; ++i) p->ev_pool.push_back(p->in_flight[i].ev);
+    p->in_flight.erase(p->in_flight.begin(), p->in_flight.begin() + (long)n);
+    return RSSYNC_OK;
+}
+// host-side: nothing of the bulk ingest is running any more
+int drain_in_flight(rssync_problem* p) {
+    if (p->copy_stream) CUDA_TRY(p, cudaStreamSynchronize(p->copy_stream));
+    for (const auto& f : p->in_flight) p->ev_pool.push_back(f.ev);
+    p->in_flight.clear();
+    return RSSYNC_OK;
+}
+
 // device arena large enough for `used` rays, contents preserved
 int reserve_device_arena(rssync_problem* p, size_t at_least = 0) {
     const size_t want = std::max(std::max(p->used, p->h_orig.cap), at_least);
+    if (want > p->d_orig.cap || want * 8 > p->d_rays.cap)  // growing moves the arena
+        if (int rc = drain_in_flight(p)) return rc;
     CUDA_TRY(p, p->d_rays.grow(want * 8, p->dev_used * 8, p->stream));
     CUDA_TRY(p, p->d_orig.grow(want, p->dev_used, p->stream));
     CUDA_TRY(p, p->d_pos.grow(want, p->dev_used, p->stream));
@@ -300,23 +335,21 @@ void add_pending(rssync_problem* p, size_t a, size_t b) {
     else p->pending.emplace_back(a, b);
 }
 
-int flush(rssync_problem* p) {
+// keep_in_flight: the caller (the PreSync grid) orders itself against the bulk-ingest chunks
+int flush(rssync_problem* p, bool keep_in_flight = false) {
     DebugTimer tm("flush");
     CUDA_TRY(p, cudaSetDevice(p->device));
     join_gyro(p);
     tm.mark("join gyro");
-    if (p->gyro_dirty) {
-        if (p->gyro_copy_queued) {  // the worker already queued the copy on gyro_stream
-            p->gyro_copy_queued = false;
-            CUDA_TRY(p, p->gyro_copy_err);
-            CUDA_TRY(p, cudaStreamWaitEvent(p->stream, p->ev_gyro, 0));
-            p->h2d += p->nq * 16 * sizeof(double);
-        } else {
-            CUDA_TRY(p, p->d_rec.reserve(p->nq * 16));
-            if (int rc = h2d(p, p->d_rec.ptr, p->rec.ptr, p->nq * 16 * sizeof(double))) return rc;
-        }
+    if (p->gyro_dirty) {  // the worker queued the copy and the finishing kernel on gyro_stream
+        CUDA_TRY(p, p->gyro_copy_err);
+        CUDA_TRY(p, cudaStreamWaitEvent(p->stream, p->ev_gyro, 0));
+        p->h2d += p->nq * 9 * sizeof(double);
         p->gyro_dirty = false;
     }
+    // frames set one by one after a bulk ingest are newer than it: their upload follows it
+    if (!keep_in_flight || !p->pending.empty())
+        if (int rc = wait_in_flight(p)) return rc;
     if (!p->pending.empty()) {
         if (int rc = reserve_device_arena(p)) return rc;
         for (const auto& r : p->pending)
@@ -343,23 +376,28 @@ int select_frames(rssync_problem* p, int64_t begin, int64_t end_exclusive,
     return RSSYNC_OK;
 }
 
-// Build the spline records of `count` quaternions at `src` into the pinned buffer on a worker thread
-// and start their copy to the device from there (ndspline::make, core_private.cpp:139 / :189).
-int start_gyro_worker(rssync_problem* p, const double* src, size_t count) {
+// SetGyroQuaternions' spline build (ndspline::make, core_private.cpp:139 / :189) for the `count`
+// samples already copied to the head of the pinned staging block: a worker thread eliminates the
+// tridiagonal system (sequential, host_ingest.cpp), then queues the copy of samples + system and the
+// kernel that finishes the records on gyro_stream.  The caller's thread goes on ingesting tracks.
+int start_gyro_worker(rssync_problem* p, size_t count) {
     CUDA_TRY(p, p->d_rec.reserve(count * 16));
+    CUDA_TRY(p, p->d_gyro.reserve(count * 9));
     if (!p->gyro_stream) CUDA_TRY(p, cudaStreamCreateWithFlags(&p->gyro_stream, cudaStreamNonBlocking));
     if (!p->ev_gyro) CUDA_TRY(p, cudaEventCreateWithFlags(&p->ev_gyro, cudaEventDisableTiming));
-    double* rec = p->rec.ptr;
+    double* h = p->h_gyro.ptr;
+    double* d = p->d_gyro.ptr;
     double* d_rec = p->d_rec.ptr;
-    p->gyro_copy_queued = false;
     p->gyro_worker = std::thread([=]() {
-        rs::build_spline_records(src, count, rec);
+        rs::build_spline_system(h, count, h + 4 * count, h + 8 * count);
         cudaError_t e = cudaSetDevice(p->device);
-        if (e == cudaSuccess)
-            e = cudaMemcpyAsync(d_rec, rec, count * 16 * sizeof(double), cudaMemcpyHostToDevice, p->gyro_stream);
+        if (e == cudaSuccess) e = cudaMemcpyAsync(d, h, count * 9 * sizeof(double), cudaMemcpyHostToDevice, p->gyro_stream);
+        if (e == cudaSuccess) {
+            rs::launch_spline_finish(d, d + 4 * count, d + 8 * count, (int)count, d_rec, p->gyro_stream);
+            e = cudaGetLastError();
+        }
         if (e == cudaSuccess) e = cudaEventRecord(p->ev_gyro, p->gyro_stream);
         p->gyro_copy_err = e;
-        p->gyro_copy_queued = true;
     });
     return RSSYNC_OK;
 }
@@ -382,7 +420,9 @@ int presync_grid_impl(rssync_problem* p, int64_t fb, int64_t fe, const double* d
     std::vector<FrameDesc> sel;
     int max_n = 0;
     if (int rc = select_frames(p, fb, fe, sel, max_n, "pre-sync")) return rc;
-    if (int rc = flush(p)) return rc;
+    DebugTimer tm("presync_grid");
+    if (int rc = flush(p, /*keep_in_flight=*/true)) return rc;
+    tm.mark("flush");
     const int F = (int)sel.size();
     if (F == 0) {  // the reference sums over no frames: cost 0 for every delay
         std::fill(costs, costs + n, 0.0);
@@ -397,15 +437,57 @@ int presync_grid_impl(rssync_problem* p, int64_t fb, int64_t fe, const double* d
     if (int rc = h2d(p, p->d_frames.ptr, sel.data(), sizeof(FrameDesc) * F)) return rc;
     if (int rc = h2d(p, p->d_delays.ptr, delays, sizeof(double) * n)) return rc;
     CUDA_TRY(p, cudaMemsetAsync(p->d_flags.ptr, 0, 2 * sizeof(unsigned), p->stream));
-    rs::launch_presync_grid(p->device_data(), p->d_frames.ptr, F, max_n, p->d_delays.ptr, n, p->seed,
-                            stream_id, call_no, idx_base, p->d_framecost.ptr, p->d_costs.ptr,
-                            p->d_flags.ptr, p->stream, p->kernel_timing ? p->ev0 : nullptr,
-                            p->kernel_timing ? p->ev1 : nullptr);
+    // Frames still being uploaded by a bulk ingest: cut the frame list into runs by the ingest chunk
+    // they wait for, and launch each run behind that chunk's event, so the grid works on the first
+    // chunks while the last ones are on the bus.  (Frame costs do not depend on how frames are
+    // grouped into launches.)  dep[f] = 1 + index of the last in-flight chunk overlapping frame f.
+    std::vector<int> run_end, run_dep;
+    if (!p->in_flight.empty()) {
+        int cur = -1;
+        for (int f = 0; f < F; ++f) {
+            const size_t a = (size_t)sel[f].off, b = a + (size_t)(sel[f].n + 31) / 32 * 32;
+            int dep = 0;
+            for (size_t k = p->in_flight.size(); k-- > 0;)
+                if (a < p->in_flight[k].hi && p->in_flight[k].lo < b) { dep = (int)k + 1; break; }
+            dep = std::max(dep, cur < 0 ? 0 : run_dep.back());  // events complete in order: keep runs monotone
+            if (dep != cur) {
+                if (cur >= 0) run_end.push_back(f);
+                run_dep.push_back(dep);
+                cur = dep;
+            }
+        }
+        run_end.push_back(F);
+        if (run_end.size() > 16) { run_end.assign(1, F); run_dep.assign(1, (int)p->in_flight.size()); }
+    } else {
+        run_end.assign(1, F);
+        run_dep.assign(1, 0);
+    }
+    const rs::DeviceData dd = p->device_data();
+    if (p->kernel_timing) CUDA_TRY(p, cudaEventRecord(p->ev0, p->stream));
+    int f0 = 0, waited = 0;
+    for (size_t r = 0; r < run_end.size(); ++r) {
+        if (run_dep[r] > waited) {
+            CUDA_TRY(p, cudaStreamWaitEvent(p->stream, p->in_flight[(size_t)run_dep[r] - 1].ev, 0));
+            waited = run_dep[r];
+        }
+        rs::launch_presync_tasks(dd, p->d_frames.ptr + f0, run_end[r] - f0, max_n, p->d_delays.ptr, n, p->seed,
+                                 stream_id, call_no, idx_base, p->d_framecost.ptr + f0, F, p->d_flags.ptr,
+                                 p->stream);
+        f0 = run_end[r];
+    }
+    if (p->kernel_timing) CUDA_TRY(p, cudaEventRecord(p->ev1, p->stream));
+    rs::launch_presync_reduce(p->d_framecost.ptr, F, n, p->d_costs.ptr, p->stream);
     CUDA_TRY(p, cudaGetLastError());
+    if (tm.on) std::fprintf(stderr, "[presync_grid] %zu launch(es) behind %d in-flight chunk(s)\n", run_end.size(), waited);
+    tm.mark("launch");
+    // the chunks this call waited for are done with; later ones (frames outside this call) stay
+    for (int k = 0; k < waited; ++k) p->ev_pool.push_back(p->in_flight[(size_t)k].ev);
+    p->in_flight.erase(p->in_flight.begin(), p->in_flight.begin() + waited);
     unsigned flags[2] = {0, 0};
     if (int rc = d2h(p, costs, p->d_costs.ptr, sizeof(double) * n)) return rc;
     if (int rc = d2h(p, flags, p->d_flags.ptr, 2 * sizeof(unsigned))) return rc;
     CUDA_TRY(p, cudaStreamSynchronize(p->stream));
+    tm.mark("wait for the device");
     p->grid_tasks = (uint64_t)F * (uint64_t)n;
     p->grid_exact_tasks = flags[1];
     if (p->kernel_timing) {
@@ -742,10 +824,15 @@ void rssync_destroy(rssync_problem* p) {
     join_gyro(p);
     if (p->arena_copy_pending) cudaEventSynchronize(p->ev_arena);
     if (p->ev_arena) cudaEventDestroy(p->ev_arena);
+    if (p->copy_stream) { cudaStreamSynchronize(p->copy_stream); cudaStreamDestroy(p->copy_stream); }
+    for (const auto& fl : p->in_flight) cudaEventDestroy(fl.ev);
+    for (cudaEvent_t e : p->ev_pool) cudaEventDestroy(e);
+    if (p->ev_order) cudaEventDestroy(p->ev_order);
     if (p->gyro_stream) { cudaStreamSynchronize(p->gyro_stream); cudaStreamDestroy(p->gyro_stream); }
     if (p->ev_gyro) cudaEventDestroy(p->ev_gyro);
     p->d_rec.release();
-    p->rec.release();
+    p->h_gyro.release();
+    p->d_gyro.release();
     p->h_rays.release(); p->d_rays.release();
     p->h_orig.release(); p->d_orig.release();
     p->h_pos.release(); p->d_pos.release();
@@ -773,11 +860,11 @@ int rssync_set_gyro_fixed(rssync_problem* p, const double* quats, size_t count, 
     cudaSetDevice(p->device);
     if (p->gyro_dirty == false && p->nq) CUDA_TRY(p, cudaStreamSynchronize(p->stream));  // records in flight
     if (p->gyro_stream) CUDA_TRY(p, cudaStreamSynchronize(p->gyro_stream));  // a copy never waited for
-    CUDA_TRY(p, p->rec.reserve(count * 16));
-    p->gyro_copy.assign(quats, quats + 4 * count);  // the caller's buffer is only borrowed
+    CUDA_TRY(p, p->h_gyro.reserve(count * 9));
+    std::memcpy(p->h_gyro.ptr, quats, 4 * count * sizeof(double));  // the caller's buffer is only borrowed
     p->nq = count;
     p->gyro_dirty = true;
-    return start_gyro_worker(p, p->gyro_copy.data(), count);  // :139
+    return start_gyro_worker(p, count);  // :139
 }
 
 int rssync_set_gyro_var(rssync_problem* p, const int64_t* ts, const double* quats, size_t count) {
@@ -795,12 +882,12 @@ int rssync_set_gyro_var(rssync_problem* p, const int64_t* ts, const double* quat
     cudaSetDevice(p->device);
     if (p->gyro_dirty == false && p->nq) CUDA_TRY(p, cudaStreamSynchronize(p->stream));
     if (p->gyro_stream) CUDA_TRY(p, cudaStreamSynchronize(p->gyro_stream));
-    CUDA_TRY(p, p->rec.reserve(rq.size() * 4));
-    p->gyro_copy.swap(rq);
-    const size_t n_out = p->gyro_copy.size() / 4;
+    const size_t n_out = rq.size() / 4;
+    CUDA_TRY(p, p->h_gyro.reserve(n_out * 9));
+    std::memcpy(p->h_gyro.ptr, rq.data(), rq.size() * sizeof(double));
     p->nq = n_out;
     p->gyro_dirty = true;
-    return start_gyro_worker(p, p->gyro_copy.data(), n_out);  // :189
+    return start_gyro_worker(p, n_out);  // :189
 }
 
 }  // extern "C"
@@ -1041,6 +1128,15 @@ int rssync_set_track_batch(rssync_problem* p, size_t n_frames, const int64_t* fr
         // staged, overlapping the staging of the next.
         cudaSetDevice(p->device);
         if (int r = wait_arena_copies(p)) return r;
+        if (!p->copy_stream) CUDA_TRY(p, cudaStreamCreateWithFlags(&p->copy_stream, cudaStreamNonBlocking));
+        if (!p->ev_order) CUDA_TRY(p, cudaEventCreateWithFlags(&p->ev_order, cudaEventDisableTiming));
+        // frames set one by one before this call are older than it: their upload goes first
+        if (!p->pending.empty())
+            if (int r = flush(p)) return r;
+        // the ingest stream follows whatever the problem's stream has queued on the arena
+        CUDA_TRY(p, cudaEventRecord(p->ev_order, p->stream));
+        CUDA_TRY(p, cudaStreamWaitEvent(p->copy_stream, p->ev_order, 0));
+        cudaStream_t cs = p->copy_stream;
         const size_t total = at[n_frames];
         CUDA_TRY(p, p->h_stage.reserve(8 * total + 1));
         CUDA_TRY(p, p->d_stage.reserve(8 * total + 1));
@@ -1081,19 +1177,37 @@ int rssync_set_track_batch(rssync_problem* p, size_t n_frames, const int64_t* fr
             if (int r = reserve_device_arena(p)) return r;
             tm.mark("place chunk");
             const size_t a = at[lo], n = at[end] - at[lo];
-            if (int r = h2d(p, p->d_pixframes.ptr + lo, pf.data() + lo, (end - lo) * sizeof(rs::PixelFrame))) return r;
-            if (int r = h2d(p, ds + a, hs + a, n * sizeof(double))) return r;
-            if (int r = h2d(p, ds + total + a, hs + total + a, n * sizeof(double))) return r;
-            if (int r = h2d(p, ds + 2 * total + 3 * a, hs + 2 * total + 3 * a, 3 * n * sizeof(double))) return r;
-            if (int r = h2d(p, ds + 5 * total + 3 * a, hs + 5 * total + 3 * a, 3 * n * sizeof(double))) return r;
+            auto up = [&](void* dst, const void* src, size_t bytes) {
+                p->h2d += bytes;
+                return cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, cs);
+            };
+            CUDA_TRY(p, up(p->d_pixframes.ptr + lo, pf.data() + lo, (end - lo) * sizeof(rs::PixelFrame)));
+            CUDA_TRY(p, up(ds + a, hs + a, n * sizeof(double)));
+            CUDA_TRY(p, up(ds + total + a, hs + total + a, n * sizeof(double)));
+            CUDA_TRY(p, up(ds + 2 * total + 3 * a, hs + 2 * total + 3 * a, 3 * n * sizeof(double)));
+            CUDA_TRY(p, up(ds + 5 * total + 3 * a, hs + 5 * total + 3 * a, 3 * n * sizeof(double)));
             rs::launch_ingest_rays(p->d_pixframes.ptr + lo, (int)(end - lo), ds, ds + total, ds + 2 * total,
-                                   ds + 5 * total, p->d_rays.ptr, p->d_orig.ptr, p->d_pos.ptr, p->stream);
+                                   ds + 5 * total, p->d_rays.ptr, p->d_orig.ptr, p->d_pos.ptr, cs);
             CUDA_TRY(p, cudaGetLastError());
             p->dev_used = std::max(p->dev_used, p->used);  // a later growth of the arena keeps this chunk
+            // the arena range this chunk writes, and the event that says it has
+            rssync_problem::InFlight fl{(size_t)-1, 0, nullptr};
+            for (size_t i = lo; i < end; ++i) {
+                fl.lo = std::min(fl.lo, (size_t)pf[i].off);
+                fl.hi = std::max(fl.hi, (size_t)pf[i].off + (counts[i] + 31) / 32 * 32);
+            }
+            if (p->ev_pool.empty()) {
+                CUDA_TRY(p, cudaEventCreateWithFlags(&fl.ev, cudaEventDisableTiming));
+            } else {
+                fl.ev = p->ev_pool.back();
+                p->ev_pool.pop_back();
+            }
+            CUDA_TRY(p, cudaEventRecord(fl.ev, cs));
+            p->in_flight.push_back(fl);
             tm.mark("enqueue chunk");
         }
         // the staging buffers are reused by the next ingest call, which waits for this event
-        CUDA_TRY(p, cudaEventRecord(p->ev_arena, p->stream));
+        CUDA_TRY(p, cudaEventRecord(p->ev_arena, cs));
         p->arena_copy_pending = true;
         if (n_ok < n_frames) { p->err = msg[n_ok]; return rc[n_ok]; }
         return RSSYNC_OK;
@@ -1146,6 +1260,7 @@ int rssync_set_track_pixels(rssync_problem* p, size_t n_frames, const int64_t* f
     if (!all_finite(frame_ts_b, n_frames)) { p->err = "set-track-result: non-finite numbers in ts_b"; return RSSYNC_E_NONFINITE; }
     if (int rc = wait_arena_copies(p)) return rc;
     cudaSetDevice(p->device);
+    if (int rc = wait_in_flight(p)) return rc;  // this ingest runs on the problem's stream
     CUDA_TRY(p, p->h_pix.reserve(4 * total + 1));
     // per frame (worker pool): validate, copy into the pinned staging buffer, timestamp bounds with
     // the device's expression (core_testcode.cpp:144-145)
@@ -1360,7 +1475,7 @@ int rssync_orientation_search(rssync_problem* p, const double* timestamps_s, con
     if (n_orient == 0) return RSSYNC_OK;
     if (!timestamps_s || !gyro_xyz || !orientations || !out_cost || !out_delay) return RSSYNC_E_INVALID;
     struct Prep {
-        std::vector<double> rec;
+        std::vector<double> sys;  // samples (nq x 4), rhs (nq x 4), diag (nq): the staging block's layout
         double sr = 0, q0 = 0;
         size_t nq = 0;
         int rc = RSSYNC_OK;
@@ -1385,8 +1500,9 @@ int rssync_orientation_search(rssync_problem* p, const double* timestamps_s, con
             return;
         }
         pr.nq = rq.size() / 4;
-        pr.rec.resize(pr.nq * 16);
-        rs::build_spline_records(rq.data(), pr.nq, pr.rec.data());
+        pr.sys.resize(pr.nq * 9);
+        std::copy(rq.begin(), rq.end(), pr.sys.begin());
+        rs::build_spline_system(pr.sys.data(), pr.nq, pr.sys.data() + 4 * pr.nq, pr.sys.data() + 8 * pr.nq);
     };
     if (n_orient >= 4) {
         std::function<void(size_t, size_t)> fn = prepare;
@@ -1400,16 +1516,21 @@ int rssync_orientation_search(rssync_problem* p, const double* timestamps_s, con
         if (pr.nq > (size_t)INT32_MAX) { p->err = "set-gyro-quaternions: too many samples"; return RSSYNC_E_INVALID; }
         join_gyro(p);
         cudaSetDevice(p->device);
-        if (p->gyro_dirty == false && p->nq) CUDA_TRY(p, cudaStreamSynchronize(p->stream));
+        CUDA_TRY(p, cudaStreamSynchronize(p->stream));  // records / staging block in use
         if (p->gyro_stream) CUDA_TRY(p, cudaStreamSynchronize(p->gyro_stream));
-        p->gyro_copy_queued = false;
-        CUDA_TRY(p, p->rec.reserve(pr.rec.size()));
-        std::memcpy(p->rec.ptr, pr.rec.data(), pr.rec.size() * sizeof(double));
+        CUDA_TRY(p, p->h_gyro.reserve(pr.sys.size()));
+        CUDA_TRY(p, p->d_gyro.reserve(pr.sys.size()));
+        CUDA_TRY(p, p->d_rec.reserve(pr.nq * 16));
+        std::memcpy(p->h_gyro.ptr, pr.sys.data(), pr.sys.size() * sizeof(double));
         p->sr = pr.sr;
         p->q0 = pr.q0;
         p->nq = pr.nq;
-        p->gyro_dirty = true;
-        std::vector<double>().swap(pr.rec);
+        p->gyro_dirty = false;  // queued right here, on the problem's stream
+        if (int rc = h2d(p, p->d_gyro.ptr, p->h_gyro.ptr, pr.sys.size() * sizeof(double))) return rc;
+        rs::launch_spline_finish(p->d_gyro.ptr, p->d_gyro.ptr + 4 * pr.nq, p->d_gyro.ptr + 8 * pr.nq, (int)pr.nq,
+                                 p->d_rec.ptr, p->stream);
+        CUDA_TRY(p, cudaGetLastError());
+        std::vector<double>().swap(pr.sys);
         if (int rc = rssync_presync(p, initial_delay, fb, fe, step, radius, &out_cost[k], &out_delay[k])) return rc;
     }
     return RSSYNC_OK;
@@ -1511,10 +1632,14 @@ int rssync_probe_gyro(const rssync_problem* p, double* sample_rate, double* firs
     if (sample_rate) *sample_rate = p->sr;
     if (first_timestamp) *first_timestamp = p->q0;
     if (count) *count = p->nq;
-    if (rec) {
-        join_gyro(const_cast<rssync_problem*>(p));
-        for (size_t i = 0; i < p->nq; ++i)  // back from the device's swizzled group order
-            for (size_t j = 0; j < 16; ++j) rec[i * 16 + j] = p->rec.ptr[i * 16 + (j ^ ((i & 3) * 4))];
+    if (rec && p->nq) {  // read the finished records back, out of the device's swizzled group order
+        rssync_problem* q = const_cast<rssync_problem*>(p);
+        if (int rc = flush(q)) return rc;
+        std::vector<double> tmp(p->nq * 16);
+        if (int rc = d2h(q, tmp.data(), p->d_rec.ptr, tmp.size() * sizeof(double))) return rc;
+        CUDA_TRY(q, cudaStreamSynchronize(p->stream));
+        for (size_t i = 0; i < p->nq; ++i)
+            for (size_t j = 0; j < 16; ++j) rec[i * 16 + j] = tmp[i * 16 + (j ^ ((i & 3) * 4))];
     }
     return RSSYNC_OK;
 }

@@ -1055,7 +1055,8 @@ __global__ void __launch_bounds__(PresyncCfg<SLOTS>::kWarps * 32, PresyncCfg<SLO
 presync_kernel(DeviceData dd, const FrameDesc* __restrict__ frames, int F,
                const double* __restrict__ delays, int D, int chunk, int cpf, uint64_t seed,
                uint64_t stream, uint64_t call_no, const uint64_t* __restrict__ frame_call_no,
-               uint64_t idx_base, double* __restrict__ framecost, unsigned* __restrict__ flags) {
+               uint64_t idx_base, double* __restrict__ framecost, int cost_stride,
+               unsigned* __restrict__ flags) {
     using Cfg = PresyncCfg<SLOTS>;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     constexpr int NP = SLOTS * 32;
@@ -1136,7 +1137,7 @@ presync_kernel(DeviceData dd, const FrameDesc* __restrict__ frames, int F,
             for (int s = 0; s < SLOTS; ++s) acc = acc + rho[s];
         }
         const double cost = sqrt(warp_sum(acc));
-        if (lane == 0) framecost[(size_t)di * F + fi] = cost;
+        if (lane == 0) framecost[(size_t)di * cost_stride + fi] = cost;
         // the panic conditions of :76-83: non-finite values propagate into the cost, so the stage
         // that produced them is only looked for when the cost (or a row) is not finite
         if (bad || !is_finite(cost)) {
@@ -1460,6 +1461,40 @@ ingest_rays_kernel(const PixelFrame* __restrict__ frames, const double* __restri
 }
 
 // ------------------------------------------------------------------------------------------
+// K7: the parallel half of ndspline::make (ndspline.cpp:13-19 / minispline.cpp:34-44).  The host
+// eliminates the tridiagonal system (two sequential sweeps, host_ingest.cpp) and sends what is left
+// of it -- rhs and diag, 5 doubles per sample instead of the 16 of a finished record -- with the
+// samples themselves; one thread per (sample, component) divides (:34), forms b and d of the
+// interval (:38-44, the reference's expressions; IEEE operations without contraction, so the bits
+// of the host evaluation) and writes the record in the device's swizzled group order (rec_groups).
+__global__ void spline_finish_kernel(const double* __restrict__ y, const double* __restrict__ rhs,
+                                     const double* __restrict__ diag, int n, double* __restrict__ rec) {
+    const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= 4LL * n) return;
+    const int i = (int)(t >> 2), c = (int)(t & 3);
+    const double yi = y[4 * (size_t)i + c];
+    const double ci = rhs[4 * (size_t)i + c] / diag[i];
+    double b, d;
+    if (i + 1 < n) {
+        const double cn = rhs[4 * (size_t)(i + 1) + c] / diag[i + 1];
+        d = 1.0 / 3.0 * (cn - ci);                                              // :40
+        b = (y[4 * (size_t)(i + 1) + c] - yi) - 1.0 / 3.0 * (2.0 * ci + cn);   // :41
+    } else {  // last sample (:43-44), from the coefficients of the interval before it
+        const double cp = rhs[4 * (size_t)(i - 1) + c] / diag[i - 1];
+        const double dp = 1.0 / 3.0 * (ci - cp);
+        const double bp = (yi - y[4 * (size_t)(i - 1) + c]) - 1.0 / 3.0 * (2.0 * cp + ci);
+        d = 0.0;
+        b = (3.0 * dp + 2.0 * cp) + bp;
+    }
+    double* out = rec + (size_t)i * 16 + c;
+    const int sw = (i & 3) * 4;
+    out[0 ^ sw] = yi;
+    out[4 ^ sw] = b;
+    out[8 ^ sw] = ci;
+    out[12 ^ sw] = d;
+}
+
+// ------------------------------------------------------------------------------------------
 // probes (tests only): one warp
 __global__ void probe_problem_kernel(DeviceData dd, FrameDesc fd, int NP, double delay, double* out) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -1609,15 +1644,11 @@ void allow_smem(K kernel, size_t smem) {
 uint64_t launch_count() { return g_launches.load(); }
 void count_launches(uint64_t n) { g_launches += n; }
 
-void launch_presync_grid(const DeviceData& dd, const FrameDesc* d_frames, int F, int max_n,
-                         const double* d_delays, int D, uint64_t seed, uint64_t stream,
-                         uint64_t call_no, uint64_t idx_base, double* d_framecost, double* d_costs,
-                         unsigned* d_flags, cudaStream_t st, cudaEvent_t ev_begin, cudaEvent_t ev_end,
-                         const uint64_t* d_frame_call_no, const int* d_win_begin, int n_windows) {
-    if (F <= 0 || D <= 0) {
-        if (D > 0) cudaMemsetAsync(d_costs, 0, sizeof(double) * D * (d_win_begin ? n_windows : 1), st);
-        return;
-    }
+void launch_presync_tasks(const DeviceData& dd, const FrameDesc* d_frames, int F, int max_n,
+                          const double* d_delays, int D, uint64_t seed, uint64_t stream, uint64_t call_no,
+                          uint64_t idx_base, double* d_framecost, int cost_stride, unsigned* d_flags,
+                          cudaStream_t st, const uint64_t* d_frame_call_no) {
+    if (F <= 0 || D <= 0) return;
     RS_DISPATCH_SLOTS(max_n, {
         using Cfg = PresyncCfg<SL>;
         auto kern = presync_kernel<SL>;
@@ -1631,22 +1662,46 @@ void launch_presync_grid(const DeviceData& dd, const FrameDesc* d_frames, int F,
             cudaGetDevice(&dev);
             cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev);
         }
-        int per_sm = 1;
-        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, Cfg::kWarps * 32, Cfg::kSmem);
+        static int per_sm = 0;  // per SLOTS instantiation (the lambda body is instantiated per case)
+        if (!per_sm) {
+            cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, Cfg::kWarps * 32, Cfg::kSmem);
+            if (per_sm < 1) per_sm = 1;
+        }
         const long long units = (long long)F * ((D + chunk - 1) / chunk);
-        const int grid = (int)std::max<long long>(1, std::min<long long>(units, (long long)sm_count * std::max(per_sm, 1)));
-        if (ev_begin) cudaEventRecord(ev_begin, st);
+        const int grid = (int)std::max<long long>(1, std::min<long long>(units, (long long)sm_count * per_sm));
         kern<<<grid, Cfg::kWarps * 32, Cfg::kSmem, st>>>(dd, d_frames, F, d_delays, D, chunk,
                                                          (D + chunk - 1) / chunk, seed, stream, call_no,
-                                                         d_frame_call_no, idx_base, d_framecost, d_flags);
-        if (ev_end) cudaEventRecord(ev_end, st);
+                                                         d_frame_call_no, idx_base, d_framecost, cost_stride,
+                                                         d_flags);
     });
+    g_launches += 1;
+}
+
+void launch_presync_reduce(const double* d_framecost, int F, int D, double* d_costs, cudaStream_t st,
+                           const int* d_win_begin, int n_windows) {
+    if (D <= 0) return;
+    if (F <= 0) {
+        cudaMemsetAsync(d_costs, 0, sizeof(double) * D * (d_win_begin ? n_windows : 1), st);
+        return;
+    }
     if (d_win_begin)
         reduce_windows_kernel<<<(n_windows * D + 3) / 4, 128, 0, st>>>(d_framecost, D, F, d_win_begin,
                                                                       n_windows, d_costs);
     else
         reduce_rows_kernel<<<(D + 3) / 4, 128, 0, st>>>(d_framecost, D, F, d_costs);
-    g_launches += 2;
+    g_launches += 1;
+}
+
+void launch_presync_grid(const DeviceData& dd, const FrameDesc* d_frames, int F, int max_n,
+                         const double* d_delays, int D, uint64_t seed, uint64_t stream,
+                         uint64_t call_no, uint64_t idx_base, double* d_framecost, double* d_costs,
+                         unsigned* d_flags, cudaStream_t st, cudaEvent_t ev_begin, cudaEvent_t ev_end,
+                         const uint64_t* d_frame_call_no, const int* d_win_begin, int n_windows) {
+    if (ev_begin && F > 0 && D > 0) cudaEventRecord(ev_begin, st);
+    launch_presync_tasks(dd, d_frames, F, max_n, d_delays, D, seed, stream, call_no, idx_base, d_framecost, F,
+                         d_flags, st, d_frame_call_no);
+    if (ev_end && F > 0 && D > 0) cudaEventRecord(ev_end, st);
+    launch_presync_reduce(d_framecost, F, D, d_costs, st, d_win_begin, n_windows);
 }
 
 void launch_sync_init(const DeviceData& dd, const SyncBatchDev& b, const double* d_sp_delay,
@@ -1744,6 +1799,14 @@ void launch_ingest_rays(const PixelFrame* d_frames, int n_frames, const double* 
     if (n_frames <= 0) return;
     ingest_rays_kernel<<<n_frames, kIngestThreads, 0, st>>>(d_frames, d_ts_a, d_ts_b, d_rays_a, d_rays_b,
                                                              d_rays, d_orig, d_pos);
+    g_launches += 1;
+}
+
+void launch_spline_finish(const double* d_quats, const double* d_rhs, const double* d_diag, int n,
+                          double* d_rec, cudaStream_t st) {
+    if (n <= 0) return;
+    const long long threads = 4LL * n;
+    spline_finish_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, st>>>(d_quats, d_rhs, d_diag, n, d_rec);
     g_launches += 1;
 }
 

@@ -48,6 +48,18 @@ void launch_presync_grid(const DeviceData& dd, const FrameDesc* d_frames, int F,
                          const uint64_t* d_frame_call_no = nullptr, const int* d_win_begin = nullptr,
                          int n_windows = 0);
 
+// The two halves of launch_presync_grid, for callers that evaluate the frames in several launches
+// (capi.cpp runs the frames of each upload chunk as soon as that chunk has landed): the task kernel
+// over F frames writes framecost[d * cost_stride + f] for f in [0, F) -- pass d_framecost offset by
+// the sub-range's first frame and the whole grid's frame count as cost_stride -- and the reduction
+// sums the whole D x F scratch.
+void launch_presync_tasks(const DeviceData& dd, const FrameDesc* d_frames, int F, int max_n,
+                          const double* d_delays, int D, uint64_t seed, uint64_t stream, uint64_t call_no,
+                          uint64_t idx_base, double* d_framecost, int cost_stride, unsigned* d_flags,
+                          cudaStream_t st, const uint64_t* d_frame_call_no = nullptr);
+void launch_presync_reduce(const double* d_framecost, int F, int D, double* d_costs, cudaStream_t st,
+                           const int* d_win_begin = nullptr, int n_windows = 0);
+
 // ---- Sync: batched over syncpoints; tasks = (syncpoint, frame) --------------------------------
 struct SyncTask {
     FrameDesc fd;
@@ -82,6 +94,12 @@ void launch_sync_trials(const DeviceData& dd, const SyncBatchDev& b, const doubl
                         int ntrial, const unsigned char* d_sp_active,
                         double* d_task_scratch /* T x ntrial */, double* d_out /* S x ntrial */,
                         cudaStream_t st);
+
+// ---- gyro spline: finish the records on the device (host_ingest.h build_spline_system) ---------
+// d_quats: n x 4 samples; d_rhs: n x 4, d_diag: n (the eliminated system); d_rec: n records of 16
+// doubles in the layout of DeviceData::rec.  n >= 2.
+void launch_spline_finish(const double* d_quats, const double* d_rhs, const double* d_diag, int n,
+                          double* d_rec, cudaStream_t st);
 
 // ---- pixel -> ray front end (track_frames' per-frame tail, core_testcode.cpp:134-161) --------
 struct LensDev {  // Lens, core_testcode.cpp:55-61

@@ -85,7 +85,7 @@ Elimination eliminate(size_t n) {
 
 }  // namespace
 
-void build_spline_records(const double* quats, size_t n, double* rec) {
+void build_spline_system(const double* quats, size_t n, double* rhs, double* diag) {
     // the elimination only depends on n: the orientation search builds 48 splines of one length
     static std::mutex mu;
     static std::shared_ptr<const Elimination> cached;
@@ -102,48 +102,20 @@ void build_spline_records(const double* quats, size_t n, double* rec) {
         cached_n = n;
     }
     const Elimination& e = *ep;
-    // right-hand sides of the four components, interleaved like the input.  They live in the last
-    // quarter of the output buffer: the final pass writes record i (doubles 16 i .. 16 i + 15) after
-    // reading rhs[4 (i + 1) ..], which sits at 12 n + 4 i + 4 >= 16 i + 16 for every i <= n - 1.
-    double* rhs = rec + 12 * n;
+    std::copy(e.diag.begin(), e.diag.end(), diag);
+    // right-hand sides of the four components, interleaved like the input; the downward sweep (:25)
+    // consumes each row right after it is formed
     for (int c = 0; c < 4; ++c) rhs[c] = rhs[4 * (n - 1) + c] = 0.0;
-    for (size_t i = 1; i + 1 < n; ++i)
-        for (int c = 0; c < 4; ++c)
-            rhs[4 * i + c] = (quats[4 * (i + 1) + c] - 2 * quats[4 * i + c]) + quats[4 * (i - 1) + c];
-    for (size_t i = 0; i + 2 < n; ++i) {  // :25
-        const double f = e.f_down[i];
-        for (int c = 0; c < 4; ++c) rhs[4 * (i + 1) + c] -= rhs[4 * i + c] * f;
+    for (size_t i = 1; i + 1 < n; ++i) {
+        const double f = e.f_down[i - 1];
+        for (int c = 0; c < 4; ++c) {
+            const double r = (quats[4 * (i + 1) + c] - 2 * quats[4 * i + c]) + quats[4 * (i - 1) + c];
+            rhs[4 * i + c] = r - rhs[4 * (i - 1) + c] * f;
+        }
     }
     for (size_t i = n - 1; i > 1; --i) {  // :31
         const double f = e.f_up[i];
         for (int c = 0; c < 4; ++c) rhs[4 * (i - 1) + c] -= rhs[4 * i + c] * f;
-    }
-    // second-derivative coefficients c (:34), then d and b per interval (:38-44); group g of record i
-    // (y, b, c, d = 0..3) lives at group position g ^ (i & 3): see rec_groups in device_math.cuh
-    // (one pass over the records, the four components of a record together: whole cache lines)
-    double c_prev[4] = {0, 0, 0, 0}, b_prev[4] = {0, 0, 0, 0}, d_prev[4] = {0, 0, 0, 0}, c_i[4];
-    for (int c = 0; c < 4; ++c) c_i[c] = rhs[c] / e.diag[0];
-    for (size_t i = 0; i < n; ++i) {
-        const size_t sw = (i & 3) * 4;
-        double* out = rec + i * 16;
-        if (i + 1 < n) {
-            const double dg = e.diag[i + 1];
-            for (int c = 0; c < 4; ++c) {
-                const double yi = quats[4 * i + c];
-                const double c_next = rhs[4 * (i + 1) + c] / dg;
-                const double d = 1.0 / 3.0 * (c_next - c_i[c]);
-                const double b = (quats[4 * (i + 1) + c] - yi) - 1.0 / 3.0 * (2.0 * c_i[c] + c_next);
-                out[(0 ^ sw) + c] = yi; out[(4 ^ sw) + c] = b; out[(8 ^ sw) + c] = c_i[c]; out[(12 ^ sw) + c] = d;
-                c_prev[c] = c_i[c]; b_prev[c] = b; d_prev[c] = d;
-                c_i[c] = c_next;
-            }
-        } else {
-            for (int c = 0; c < 4; ++c) {
-                const double d = 0.0;
-                const double b = (3.0 * d_prev[c] + 2.0 * c_prev[c]) + b_prev[c];
-                out[(0 ^ sw) + c] = quats[4 * i + c]; out[(4 ^ sw) + c] = b; out[(8 ^ sw) + c] = c_i[c]; out[(12 ^ sw) + c] = d;
-            }
-        }
     }
 }
 

@@ -9,10 +9,13 @@ namespace rs {
 
 enum class IngestStatus { Ok = 0, Invalid = 1, NonFinite = 2, OutOfOrder = 3 };
 
-// ndspline::make (ndspline.cpp:13-19): n quaternions (w,x,y,z) -> n records of 16 doubles
-// {y[4], b[4], c[4], d[4]}, the four 32-byte groups of record i stored at group position
-// g ^ (i & 3) (the device layout, device_math.cuh rec_groups).
-void build_spline_records(const double* quats, size_t n, double* rec /* n * 16 doubles */);
+// ndspline::make (ndspline.cpp:13-19), the sequential half: the tridiagonal system of the natural
+// cubic spline on unit knots (minispline.cpp:3-32) for the four quaternion components, eliminated
+// downwards and upwards.  rhs (4 n doubles, interleaved like the input) and diag (n doubles) are what
+// is left of it: the second-derivative coefficient of sample i, component c is rhs[4 i + c] / diag[i]
+// (:34).  The divisions and the b / d coefficients (:38-44) are independent per sample and are
+// finished on the device (launch_spline_finish, engine.h).
+void build_spline_system(const double* quats, size_t n, double* rhs /* 4 n */, double* diag /* n */);
 
 // variable-rate SetGyroQuaternions (core_private.cpp:142-190): resample onto the uniform
 // integer-microsecond grid by slerp.

@@ -279,6 +279,41 @@ def test_bulk_ingest_into_a_fresh_arena_that_grows(rsb, synth_mod):
         assert np.array_equal(ca, cb)
 
 
+def test_bulk_ingest_ordering_against_single_frame_updates(rsb, synth_mod):
+    """the bulk ingest runs on its own stream and the grid starts on the chunks that have landed:
+    a frame set again after (before) the bulk call must win (lose), and grids over part of the
+    frames must not disturb the rest"""
+    w = synth_mod.make_workload("tiny", frames=130, rays=100)
+    n = w.n_rays
+    counts = np.full(w.n_frames, n)
+    delays = np.linspace(-0.02, 0.02, 7)
+    ids = [int(v) for v in w.frame_ids]
+    k = 70  # the frame that is set twice, with frame 3's rays the second time
+    # reference: frame by frame, final contents
+    ref = rsb.SyncProblem(seed=9).load(w)
+    ref.SetTrackResult(ids[k], w.ts_a[k], w.ts_b[k], w.rays_a[3], w.rays_b[3], n)
+    want = ref.presync_grid(ids[0], ids[-1] + 1, delays, call_no=5)
+    # bulk, then the single update
+    a = rsb.SyncProblem(seed=9)
+    a.SetGyroQuaternions(w.quats, w.quats.shape[0], w.gyro_rate, w.gyro_t0)
+    a.set_track_batch(w.frame_ids, counts, w.ts_a, w.ts_b, w.rays_a, w.rays_b)
+    a.SetTrackResult(ids[k], w.ts_a[k], w.ts_b[k], w.rays_a[3], w.rays_b[3], n)
+    assert np.array_equal(a.presync_grid(ids[0], ids[-1] + 1, delays, call_no=5), want)
+    # the single (stale) version first, then the bulk with the final contents
+    ra, rb = w.rays_a.copy(), w.rays_b.copy()
+    ra[k], rb[k] = w.rays_a[3], w.rays_b[3]
+    b = rsb.SyncProblem(seed=9)
+    b.SetGyroQuaternions(w.quats, w.quats.shape[0], w.gyro_rate, w.gyro_t0)
+    b.SetTrackResult(ids[k], w.ts_a[k], w.ts_b[k], w.rays_a[k], w.rays_b[k], n)
+    b.set_track_batch(w.frame_ids, counts, w.ts_a, w.ts_b, ra, rb)
+    # grids over parts of the range, the last chunks first
+    hi = b.presync_grid(ids[100], ids[-1] + 1, delays, call_no=5)
+    lo = b.presync_grid(ids[0], ids[100], delays, call_no=5)
+    assert np.array_equal(hi, ref.presync_grid(ids[100], ids[-1] + 1, delays, call_no=5))
+    assert np.array_equal(lo, ref.presync_grid(ids[0], ids[100], delays, call_no=5))
+    assert np.array_equal(b.presync_grid(ids[0], ids[-1] + 1, delays, call_no=5), want)
+
+
 def test_presync_wide_delay_steps_use_global_path(rsb, oracle_loader, w_tiny):
     """delays 50 ms apart: the chunk's spline window does not fit the staging buffer, so phase A
     reads global memory; a 10 s offset leaves the gyro span entirely (spline edges)"""
