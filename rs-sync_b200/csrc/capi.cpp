@@ -1021,47 +1021,67 @@ public:
         return pool;
     }
     size_t size() const { return threads_.size() + 1; }
-    // fn(i, t) for i in [0, n), t = worker index; blocks of 16 items are handed out dynamically
+    // fn(i, t) for i in [0, n), t = worker index; blocks of `grain` items are handed out dynamically
     void run(size_t n, const std::function<void(size_t, size_t)>& fn, size_t grain = 16) {
         if (n == 0) return;
-        std::unique_lock<std::mutex> lk(m_);
-        fn_ = &fn;
-        n_ = n;
-        grain_ = grain ? grain : 1;
-        next_.store(0);
-        pending_ = threads_.size();
-        ++generation_;
+        {
+            std::lock_guard<std::mutex> lk(m_);
+            fn_ = &fn;
+            n_ = n;
+            grain_ = grain ? grain : 1;
+            next_.store(0);
+            pending_.store(threads_.size());
+            generation_.fetch_add(1, std::memory_order_release);
+        }
         cv_.notify_all();
-        lk.unlock();
         work(0);
-        lk.lock();
-        done_.wait(lk, [&] { return pending_ == 0; });
+        // the regions of one ingest call follow each other within microseconds: spin briefly before
+        // sleeping (a condition-variable wake-up costs 30-50 us, six regions per call)
+        if (!spin_until([&] { return pending_.load(std::memory_order_acquire) == 0; })) {
+            std::unique_lock<std::mutex> lk(m_);
+            done_.wait(lk, [&] { return pending_.load() == 0; });
+        }
         fn_ = nullptr;
     }
 
 private:
+    template <class Pred>
+    static bool spin_until(Pred&& pred) {
+        const auto t0 = std::chrono::steady_clock::now();
+        for (int i = 0;; ++i) {
+            if (pred()) return true;
+            if ((i & 63) == 63 && std::chrono::steady_clock::now() - t0 > std::chrono::microseconds(150)) return false;
+#if defined(__x86_64__) || defined(__i386__)
+            __builtin_ia32_pause();
+#endif
+        }
+    }
     WorkerPool() {
         unsigned hw = std::thread::hardware_concurrency();
-        const size_t n = std::min<size_t>(hw ? hw : 1, 16);
+        // one core is left to the gyro worker thread, which runs beside the track ingest
+        const size_t n = std::min<size_t>(hw > 2 ? hw - 1 : 1, 16);
         for (size_t t = 1; t < n; ++t)
             threads_.emplace_back([this, t]() {
                 uint64_t seen = 0;
                 for (;;) {
-                    std::unique_lock<std::mutex> lk(m_);
-                    cv_.wait(lk, [&] { return generation_ != seen || stop_; });
-                    if (stop_) return;
-                    seen = generation_;
-                    lk.unlock();
+                    if (!spin_until([&] { return generation_.load(std::memory_order_acquire) != seen || stop_.load(); })) {
+                        std::unique_lock<std::mutex> lk(m_);
+                        cv_.wait(lk, [&] { return generation_.load() != seen || stop_.load(); });
+                    }
+                    if (stop_.load()) return;
+                    seen = generation_.load(std::memory_order_acquire);
                     work(t);
-                    lk.lock();
-                    if (--pending_ == 0) done_.notify_one();
+                    if (pending_.fetch_sub(1, std::memory_order_acq_rel) == 1) {
+                        std::lock_guard<std::mutex> lk(m_);
+                        done_.notify_one();
+                    }
                 }
             });
     }
     ~WorkerPool() {
         {
             std::lock_guard<std::mutex> lk(m_);
-            stop_ = true;
+            stop_.store(true);
         }
         cv_.notify_all();
         for (auto& th : threads_) th.join();
@@ -1077,10 +1097,10 @@ private:
     std::mutex m_;
     std::condition_variable cv_, done_;
     const std::function<void(size_t, size_t)>* fn_ = nullptr;
-    size_t n_ = 0, pending_ = 0, grain_ = 16;
-    std::atomic<size_t> next_{0};
-    uint64_t generation_ = 0;
-    bool stop_ = false;
+    size_t n_ = 0, grain_ = 16;
+    std::atomic<size_t> next_{0}, pending_{0};
+    std::atomic<uint64_t> generation_{0};
+    std::atomic<bool> stop_{false};
 };
 
 void parallel_frames(size_t n, const std::function<void(size_t, size_t)>& fn) {
@@ -1124,7 +1144,7 @@ int rssync_set_track_batch(rssync_problem* p, size_t n_frames, const int64_t* fr
         // (ingest_rays_kernel).  The host makes ONE pass over the caller's buffers: each value is
         // checked (the reference's panic conditions, core_private.cpp:199-202) while it is copied
         // into pinned staging memory, and the per-frame timestamp bounds are taken on the way.
-        // Each sixth of the batch is placed, copied to the device and ingested as soon as it is
+        // Each eighth of the batch (RSSYNC_INGEST_CHUNKS) is placed, copied to the device and ingested as soon as it is
         // staged, overlapping the staging of the next.
         cudaSetDevice(p->device);
         if (int r = wait_arena_copies(p)) return r;
@@ -1152,7 +1172,11 @@ int rssync_set_track_batch(rssync_problem* p, size_t n_frames, const int64_t* fr
         tm.mark("reserve");
         double* hs = p->h_stage.ptr;
         double* ds = p->d_stage.ptr;
-        const size_t n_chunks = 6;
+        static const size_t n_chunks = [] {
+            const char* e = std::getenv("RSSYNC_INGEST_CHUNKS");
+            const int v = e ? std::atoi(e) : 0;
+            return (size_t)(v > 0 ? v : 8);
+        }();
         size_t n_ok = n_frames;
         for (size_t c = 0; c < n_chunks && n_ok == n_frames; ++c) {
             const size_t lo = n_frames * c / n_chunks, hi = n_frames * (c + 1) / n_chunks;
