@@ -190,6 +190,10 @@ int rssync_measure_fp64_peak(double* tflops);
 /* ---- stage probes: expose intermediate results of the device path for parity tests -------- */
 int rssync_probe_gyro(const rssync_problem* p, double* sample_rate, double* first_timestamp,
                       size_t* count, double* spline_records /* count*16 or NULL */);
+/* Host-only (no device needed): the eliminated tridiagonal system of the natural cubic spline through
+ * `count` quaternions (count x 4), as SetGyroQuaternions builds it before the records are finished
+ * on the device: rhs (count x 4) and diag (count); c = rhs / diag (minispline.cpp:3-34). */
+int rssync_probe_spline_system(const double* quats, size_t count, double* rhs, double* diag);
 int rssync_probe_problem_matrix(rssync_problem* p, int64_t frame, double delay, double* rows);
 int rssync_probe_guess_motion(rssync_problem* p, int64_t frame, double delay, int iters, int stream,
                               uint64_t call_no, uint64_t offset_index, double* m3, double* k);

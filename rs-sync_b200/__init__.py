@@ -31,7 +31,7 @@ C_ABI_SYMBOLS = [
     "rssync_set_gyro_var", "rssync_set_track", "rssync_presync", "rssync_sync",
     "rssync_debug_presync", "rssync_presync_grid", "rssync_presync_delays", "rssync_sync_batch",
     "rssync_last_sync_trace", "rssync_set_rng", "rssync_call_counter", "rssync_set_stream",
-    "rssync_flush", "rssync_get_stats", "rssync_measure_fp64_peak", "rssync_probe_gyro",
+    "rssync_flush", "rssync_get_stats", "rssync_measure_fp64_peak", "rssync_probe_gyro", "rssync_probe_spline_system",
     "rssync_probe_problem_matrix", "rssync_probe_guess_motion", "rssync_probe_loss",
     "rssync_probe_lbfgs", "rssync_probe_log1p", "rssync_set_track_batch", "rssync_set_kernel_timing",
     "rssync_sync_batch_ex", "rssync_probe_guess_motion_ex", "rssync_integrate_gyro",
@@ -110,6 +110,7 @@ def load_library():
     L.rssync_get_stats.argtypes = [P, C.POINTER(Stats)]
     L.rssync_measure_fp64_peak.argtypes = [c_double_p]
     L.rssync_probe_gyro.argtypes = [P, c_double_p, c_double_p, C.POINTER(C.c_size_t), c_double_p]
+    L.rssync_probe_spline_system.argtypes = [c_double_p, C.c_size_t, c_double_p, c_double_p]
     L.rssync_probe_problem_matrix.argtypes = [P, C.c_int64, C.c_double, c_double_p]
     L.rssync_probe_guess_motion.argtypes = [P, C.c_int64, C.c_double, C.c_int, C.c_int, C.c_uint64,
                                             C.c_uint64, c_double_p, c_double_p]
@@ -165,6 +166,17 @@ def measure_fp64_peak():
     if rc != OK:
         raise RsSyncError(rc, "FP64 peak measurement failed (no CUDA device?)")
     return v.value
+
+
+def probe_spline_system(quats):
+    """Host-only: the eliminated spline system (rhs n x 4, diag n) SetGyroQuaternions builds on the host."""
+    L = load_library()
+    q = _f64(quats).reshape(-1, 4)
+    rhs, diag = np.empty_like(q), np.empty(q.shape[0])
+    rc = L.rssync_probe_spline_system(_dp(q), q.shape[0], _dp(rhs), _dp(diag))
+    if rc != OK:
+        raise RsSyncError(rc, "spline system probe failed")
+    return rhs, diag
 
 
 def probe_log1p(x):

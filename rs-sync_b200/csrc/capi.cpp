@@ -1668,6 +1668,12 @@ int rssync_probe_gyro(const rssync_problem* p, double* sample_rate, double* firs
     return RSSYNC_OK;
 }
 
+int rssync_probe_spline_system(const double* quats, size_t count, double* rhs, double* diag) {
+    if (!quats || !rhs || !diag || count < 2) return RSSYNC_E_INVALID;
+    rs::build_spline_system(quats, count, rhs, diag);
+    return RSSYNC_OK;
+}
+
 static int probe_frame(rssync_problem* p, int64_t frame, FrameDesc& fd) {
     if (int rc = require_gyro(p, "probe")) return rc;
     auto it = p->frames.find(frame);

@@ -41,3 +41,27 @@ def test_zero_rate_and_bad_orientation(rsb, oracle_loader):
             rsb.integrate_gyro(ts, np.zeros((5, 3)), bad)
         with pytest.raises(oracle_loader.OracleError):
             oracle_loader.integrate_gyro(ts, np.zeros((5, 3)), bad)
+
+
+@pytest.mark.parametrize("n", [2, 3, 4, 5, 7, 16, 17, 18, 19, 20, 33, 64, 257, 4097, 57503])
+def test_host_spline_elimination_matches_the_oracle_bit_for_bit(rsb, oracle_loader, n):
+    """SetGyroQuaternions' host half (host_ingest.cpp: shared elimination factors, the fixed-point
+    shortcut of the sweeps) against the oracle's per-component restatement of minispline.cpp; the
+    device half (c = rhs / diag, b, d; spline_finish_kernel) is restated here with numpy's IEEE
+    operations, the GPU test compares the finished records themselves"""
+    rng = np.random.default_rng(n)
+    q = rng.normal(size=(n, 4))
+    q /= np.linalg.norm(q, axis=1, keepdims=True)
+    rhs, diag = rsb.probe_spline_system(q)
+    c = rhs / diag[:, None]
+    rec = np.empty((n, 16))
+    rec[:, 0:4] = q
+    rec[:, 8:12] = c
+    third = 1.0 / 3.0
+    rec[:-1, 12:16] = third * (c[1:] - c[:-1])                                  # minispline.cpp:40
+    rec[:-1, 4:8] = (q[1:] - q[:-1]) - third * (2.0 * c[:-1] + c[1:])          # :41
+    rec[-1, 12:16] = 0.0                                                         # :43
+    rec[-1, 4:8] = (3.0 * rec[-2, 12:16] + 2.0 * c[-2]) + rec[-2, 4:8]          # :44
+    o = oracle_loader.OracleProblem()
+    o.SetGyroQuaternions(q, n, 1000.0, 0.0)
+    assert np.array_equal(rec, o.spline())
