@@ -341,8 +341,8 @@ def run_b200(args):
                 "peak_source": "measured live: rssync_measure_fp64_peak (dependent DFMA chains, all SMs)",
                 "kernel": "presync_kernel", "kernel_ms": kern_ms, "flop_per_cell": FLOP_PER_CELL,
                 # dram__bytes_read.sum + dram__bytes_write.sum of one launch, ncu --set full
-                # (profiles/r01_presync_v4.md): 57.7 MB + 1.7 MB = inputs once + the framecost scratch
-                "traffic": 59.5e6 if (w.name == "C2" and hi - lo == OFFSETS_PER_GPU) else None,
+                # (profiles/r01_presync_v5.md): 57.6 MB + 1.1 MB = inputs once + the framecost scratch
+                "traffic": 58.7e6 if (w.name == "C2" and hi - lo == OFFSETS_PER_GPU) else None,
                 "exact_estimator_tasks": int(prob.stats()["last_grid_exact_tasks"]),
                 "tasks": int(prob.stats()["last_grid_tasks"]),
                 "hbm": {"algorithmic_bytes": int(input_bytes),
