@@ -1148,6 +1148,7 @@ int rssync_set_track_batch(rssync_problem* p, size_t n_frames, const int64_t* fr
         // staged, overlapping the staging of the next.
         cudaSetDevice(p->device);
         if (int r = wait_arena_copies(p)) return r;
+        if (int r = drain_in_flight(p)) return r;  // an earlier bulk call's chunks: all done by now
         if (!p->copy_stream) CUDA_TRY(p, cudaStreamCreateWithFlags(&p->copy_stream, cudaStreamNonBlocking));
         if (!p->ev_order) CUDA_TRY(p, cudaEventCreateWithFlags(&p->ev_order, cudaEventDisableTiming));
         // frames set one by one before this call are older than it: their upload goes first
