@@ -842,16 +842,26 @@ __device__ __forceinline__ double warp_loss3_reg(const double (&p)[SLOTS][3], do
 
 // ens::L_BFGS on a 3-vector (call site core_private.cpp:264-294); every lane runs the same scalar
 // control flow on identical values, the objective is evaluated cooperatively.
+// `hist`: kLbfgsHistDoubles doubles of shared memory private to the warp.  The stored pairs are
+// indexed dynamically, so as local arrays they would live in local memory -- one copy per LANE of
+// values that are identical in every lane (16 % of the kernel's stall samples were long-scoreboard
+// waits on those loads).  Every lane writes every value itself before it reads it (all lanes write
+// the same bits to the same address), so no warp synchronisation is needed.
+constexpr int kLbfgsHistDoubles = 80;
 template <class EvalF>
-__device__ __forceinline__ double warp_lbfgs(EvalF&& eval, double x[3], int& n_iters, int& n_evals) {
+__device__ __forceinline__ double warp_lbfgs(EvalF&& eval, double x[3], int& n_iters, int& n_evals,
+                                             double* __restrict__ hist) {
     constexpr int numBasis = 10, maxIterations = 200, maxTrials = 50;
     const double minGradientNorm = 1e-4, armijo = 1e-4, wolfe = 0.9, factr = 1e-15,
                  minStep = 1e-20, maxStep = 1e20;
-    double S[numBasis][3] = {}, Y[numBasis][3] = {}, alpha[numBasis];
+    double (*S)[3] = reinterpret_cast<double (*)[3]>(hist);
+    double (*Y)[3] = reinterpret_cast<double (*)[3]>(hist + 3 * numBasis);
+    double* rho_pair = hist + 6 * numBasis;
+    double* alpha = hist + 7 * numBasis;
+    for (int i = 0; i < 7 * numBasis; ++i) hist[i] = 0.0;
     // 1 / (y.s) of each stored pair: the two-loop recursion recomputes this division for every pair
     // at every iteration; the value only depends on the pair, so it is computed once when the pair
     // is stored (same expression, same bits) -- it is the longest dependent chain of an iteration
-    double rho_pair[numBasis] = {};
     double g[3], oldx[3], oldg[3], dir[3], trial[3];
     Loss5 e = eval(x[0], x[1], x[2]);
     double f = e.f;
@@ -979,8 +989,8 @@ __device__ __noinline__ unsigned presync_diagnose(const double* pm, int nslots, 
 // ------------------------------------------------------------------------------------------
 // K1: PreSync / DebugPreSync grid.
 //
-// Work unit = (frame, chunk of up to W consecutive delays), W = warps per block; warp j of the block
-// takes delay j of the chunk.  A block walks a contiguous range of units, so consecutive units
+// Work unit = (frame, chunk of up to 2 W consecutive delays), W = warps per block; warp j of the block
+// takes delays j and j + W of the chunk, one after the other.  A block walks a contiguous range of units, so consecutive units
 // share the frame.  What phase A reads is staged in shared memory by TMA bulk copies issued by one
 // thread: the frame's ray tiles (contiguous in the arena; reloaded only when the frame changes)
 // and the window of spline records the chunk can touch (from the frame's timestamp bounds and the
@@ -1000,7 +1010,11 @@ struct PresyncCfg {
 #ifndef RS_PRESYNC_MINB
 #define RS_PRESYNC_MINB 2
 #endif
+#ifndef RS_PRESYNC_TASKS_PER_WARP
+#define RS_PRESYNC_TASKS_PER_WARP 2
+#endif
     static constexpr int kWarps = SLOTS <= 8 ? RS_PRESYNC_WARPS : 8;
+    static constexpr int kTasksPerWarp = RS_PRESYNC_TASKS_PER_WARP;  // delays per warp and unit
     static constexpr int kMinBlocks = SLOTS <= 8 ? RS_PRESYNC_MINB : 1;
     static constexpr size_t kTileBytes = (size_t)SLOTS * 2048;
     static constexpr size_t kCtlOff = kLog1pTableBytes;
@@ -1078,15 +1092,20 @@ presync_kernel(DeviceData dd, const FrameDesc* __restrict__ frames, int F,
     if (threadIdx.x == 0 && u_begin < u_end)
         presync_stage_unit<SLOTS>(dd, frames, delays, D, chunk, cpf, u_begin, ctl, sTiles, sRec);
     unsigned parity = 0;
+    // a unit holds up to kTasksPerWarp delays per warp: warp j takes delays j, j + W, ... of the
+    // chunk one after the other, so the warps of a block meet (and poll) once per several tasks and
+    // the differences between their tasks' tournament lengths average out
+    const int reps = (chunk + Cfg::kWarps - 1) / Cfg::kWarps;
     for (int u = u_begin; u < u_end; ++u) {
         const int fi = u / cpf, d0 = (u % cpf) * chunk;
-        const int di = d0 + warp;
-        const bool active = warp < chunk && di < D;
         const FrameDesc fd = frames[fi];
         const int nslots = (fd.n + 31) >> 5;
         while (!mbar_try_wait(&ctl->full, parity)) __nanosleep(64);
         parity ^= 1u;
         const int rec_first = *(volatile int*)&ctl->rec_first, rec_cnt = *(volatile int*)&ctl->rec_cnt;
+      for (int rep = 0; rep < reps; ++rep) {
+        const int dj = rep * Cfg::kWarps + warp, di = d0 + dj;
+        const bool active = dj < chunk && di < D;
         unsigned bad = 0;
         double delay = 0.0;
         if (active) {
@@ -1096,8 +1115,8 @@ presync_kernel(DeviceData dd, const FrameDesc* __restrict__ frames, int F,
             bad = __reduce_or_sync(FULL, bad);
         }
         __syncwarp();
-        if (lane == 0) {  // phase A of this unit no longer needs the staging buffers
-            __threadfence_block();
+        if (rep == reps - 1 && lane == 0) {  // the warp's last phase A of this unit: it no longer
+            __threadfence_block();           // needs the staging buffers
             if (atomicAdd(&ctl->arrived, 1u) == (unsigned)(Cfg::kWarps - 1)) {
                 ctl->arrived = 0;
                 if (u + 1 < u_end)
@@ -1149,6 +1168,7 @@ presync_kernel(DeviceData dd, const FrameDesc* __restrict__ frames, int F,
             bad = __reduce_or_sync(FULL, bad);
             if (bad && lane == 0) atomicOr(flags, bad);
         }
+      }
     }
 }
 
@@ -1227,6 +1247,9 @@ sync_motion_fgrad_kernel(DeviceData dd, SyncBatchDev b, const double* __restrict
     double* tab = reinterpret_cast<double*>(smem_raw);
     load_log1p_table(tab);
     const WarpSmem w = warp_smem(smem_raw + kLog1pTableBytes, warp, NP, false);
+    double* hist = reinterpret_cast<double*>(smem_raw + kLog1pTableBytes +
+                                             (size_t)kWarpsPerBlock * warp_smem_bytes(NP, false)) +
+                   warp * kLbfgsHistDoubles;
     for (int t = blockIdx.x * kWarpsPerBlock + warp; t < b.T; t += gridDim.x * kWarpsPerBlock) {
         const SyncTask task = b.tasks[t];
         if (!sp_active[task.sp]) continue;
@@ -1245,7 +1268,7 @@ sync_motion_fgrad_kernel(DeviceData dd, SyncBatchDev b, const double* __restrict
             if (j == 0) {
                 int it, ev;
                 warp_lbfgs([&](double a0, double a1, double a2) { return warp_loss5_reg<SLOTS>(p, a0, a1, a2, k, tab); },
-                           m, it, ev);
+                           m, it, ev, hist);
                 if (lane == 0) {
                     b.m[3 * t] = m[0]; b.m[3 * t + 1] = m[1]; b.m[3 * t + 2] = m[2];
                     if (stats) { stats[2 * t] = it; stats[2 * t + 1] = ev; }
@@ -1538,9 +1561,10 @@ __global__ void probe_lbfgs_kernel(DeviceData dd, FrameDesc fd, int NP, double d
     build_rows_smem<false>(dd, fd, delay, lane, w, NP);
     double m[3] = {mp[0], mp[1], mp[2]};
     int it, ev;
+    __shared__ double hist[kLbfgsHistDoubles];
     const double f = warp_lbfgs(
         [&](double a0, double a1, double a2) { return warp_loss5_smem(w.P, NP, nslots, lane, a0, a1, a2, k, tab); },
-        m, it, ev);
+        m, it, ev, hist);
     if (lane == 0) {
         mp[0] = m[0]; mp[1] = m[1]; mp[2] = m[2];
         *fout = f;
@@ -1653,8 +1677,9 @@ void launch_presync_tasks(const DeviceData& dd, const FrameDesc* d_frames, int F
         using Cfg = PresyncCfg<SL>;
         auto kern = presync_kernel<SL>;
         allow_smem(kern, Cfg::kSmem);
-        // chunks of delays per frame, balanced: cpf = ceil(D / W), chunk = ceil(D / cpf) <= W
-        const int cpf = (D + Cfg::kWarps - 1) / Cfg::kWarps;
+        // chunks of delays per frame, balanced: cpf = ceil(D / (W R)), chunk = ceil(D / cpf) <= W R
+        const int per_unit = Cfg::kWarps * Cfg::kTasksPerWarp;
+        const int cpf = (D + per_unit - 1) / per_unit;
         const int chunk = (D + cpf - 1) / cpf;
         static int sm_count = 0;
         if (!sm_count) {
@@ -1726,7 +1751,8 @@ void launch_sync_motion_fgrad(const DeviceData& dd, const SyncBatchDev& b, const
     if (b.T <= 0) return;
     RS_DISPATCH_SLOTS(b.max_n, {
         auto kern = sync_motion_fgrad_kernel<SL>;
-        const size_t smem = kLog1pTableBytes + (size_t)kWarpsPerBlock * warp_smem_bytes(SL * 32, false);
+        const size_t smem = kLog1pTableBytes + (size_t)kWarpsPerBlock * warp_smem_bytes(SL * 32, false) +
+                            (size_t)kWarpsPerBlock * kLbfgsHistDoubles * sizeof(double);
         allow_smem(kern, smem);
         const int grid = grid_for(kern, smem, b.T);
         kern<<<grid, kWarpsPerBlock * 32, smem, st>>>(dd, b, d_sp_delay, d_sp_x0, d_sp_active, d_task_scratch,
