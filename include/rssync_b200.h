@@ -150,6 +150,14 @@ int rssync_orientation_search(rssync_problem* p, const double* timestamps_s, con
                               double initial_delay, int64_t frame_begin, int64_t frame_end,
                               double search_step, double search_radius, double* out_cost,
                               double* out_delay);
+/* The same with the RNG call number of every variant given explicitly (call_nos[i] keys variant i's
+ * PreSync; the problem's counter is left as it was), so that a subset of the variants evaluated on
+ * another GPU reproduces the single-process search; call_nos == NULL: as above. */
+int rssync_orientation_search_ex(rssync_problem* p, const double* timestamps_s, const double* gyro_xyz,
+                                 size_t count, const char* const* orientations, int n_orient,
+                                 double initial_delay, int64_t frame_begin, int64_t frame_end,
+                                 double search_step, double search_radius, const uint64_t* call_nos,
+                                 double* out_cost, double* out_delay);
 
 /* Pinned RNG of the randomised translation estimator (replaces the reference's
  * random_device-seeded mt19937, inline_utils.hpp:13-17).  Default seed 100, call counter 0; the

@@ -35,7 +35,7 @@ C_ABI_SYMBOLS = [
     "rssync_probe_problem_matrix", "rssync_probe_guess_motion", "rssync_probe_loss",
     "rssync_probe_lbfgs", "rssync_probe_log1p", "rssync_set_track_batch", "rssync_set_kernel_timing",
     "rssync_sync_batch_ex", "rssync_probe_guess_motion_ex", "rssync_integrate_gyro",
-    "rssync_orientation_search", "rssync_presync_windows", "rssync_set_track_pixels",
+    "rssync_orientation_search", "rssync_orientation_search_ex", "rssync_presync_windows", "rssync_set_track_pixels",
 ]
 # Itanium-ABI symbols of the C++ drop-in face (same set the reference's librssync_core exports)
 CXX_ABI_SYMBOLS = [
@@ -126,6 +126,9 @@ def load_library():
     L.rssync_orientation_search.argtypes = [P, c_double_p, c_double_p, C.c_size_t, C.POINTER(C.c_char_p),
                                             C.c_int, C.c_double, C.c_int64, C.c_int64, C.c_double,
                                             C.c_double, c_double_p, c_double_p]
+    L.rssync_orientation_search_ex.argtypes = [P, c_double_p, c_double_p, C.c_size_t, C.POINTER(C.c_char_p),
+                                               C.c_int, C.c_double, C.c_int64, C.c_int64, C.c_double,
+                                               C.c_double, C.POINTER(C.c_uint64), c_double_p, c_double_p]
     _lib = L
     return L
 
@@ -290,16 +293,22 @@ class SyncProblem:
         return self
 
     def orientation_search(self, timestamps_s, gyro_xyz, orientations, initial_delay, frame_begin, frame_end,
-                           search_step, search_radius):
-        """core_testcode.cpp:184-233: PreSync under every gyro_orientation variant.  Returns (costs, delays)."""
+                           search_step, search_radius, call_nos=None):
+        """core_testcode.cpp:184-233: PreSync under every gyro_orientation variant.  Returns (costs, delays).
+        call_nos: explicit RNG call number per variant (the problem's counter is then left alone)."""
         ts = _f64(timestamps_s)
         g = _f64(gyro_xyz)
         n = len(orientations)
         arr = (C.c_char_p * n)(*[o.encode() for o in orientations])
         costs, delays = np.empty(n), np.empty(n)
-        self._check(self.L.rssync_orientation_search(self.h, _dp(ts), _dp(g), ts.shape[0], arr, n, initial_delay,
-                                                     frame_begin, frame_end, search_step, search_radius,
-                                                     _dp(costs), _dp(delays)))
+        cn = None
+        if call_nos is not None:
+            cn_arr = np.ascontiguousarray(call_nos, dtype=np.uint64)
+            assert cn_arr.shape[0] == n
+            cn = cn_arr.ctypes.data_as(C.POINTER(C.c_uint64))
+        self._check(self.L.rssync_orientation_search_ex(self.h, _dp(ts), _dp(g), ts.shape[0], arr, n, initial_delay,
+                                                        frame_begin, frame_end, search_step, search_radius, cn,
+                                                        _dp(costs), _dp(delays)))
         return costs, delays
 
     def set_kernel_timing(self, enabled=True):

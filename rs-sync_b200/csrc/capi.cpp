@@ -1496,6 +1496,14 @@ int rssync_orientation_search(rssync_problem* p, const double* timestamps_s, con
                               size_t count, const char* const* orientations, int n_orient,
                               double initial_delay, int64_t fb, int64_t fe, double step, double radius,
                               double* out_cost, double* out_delay) {
+    return rssync_orientation_search_ex(p, timestamps_s, gyro_xyz, count, orientations, n_orient, initial_delay,
+                                        fb, fe, step, radius, nullptr, out_cost, out_delay);
+}
+
+int rssync_orientation_search_ex(rssync_problem* p, const double* timestamps_s, const double* gyro_xyz,
+                                 size_t count, const char* const* orientations, int n_orient,
+                                 double initial_delay, int64_t fb, int64_t fe, double step, double radius,
+                                 const uint64_t* call_nos, double* out_cost, double* out_delay) {
     if (!p || n_orient < 0) return RSSYNC_E_INVALID;
     if (n_orient == 0) return RSSYNC_OK;
     if (!timestamps_s || !gyro_xyz || !orientations || !out_cost || !out_delay) return RSSYNC_E_INVALID;
@@ -1529,13 +1537,43 @@ int rssync_orientation_search(rssync_problem* p, const double* timestamps_s, con
         std::copy(rq.begin(), rq.end(), pr.sys.begin());
         rs::build_spline_system(pr.sys.data(), pr.nq, pr.sys.data() + 4 * pr.nq, pr.sys.data() + 8 * pr.nq);
     };
-    if (n_orient >= 4) {
-        std::function<void(size_t, size_t)> fn = prepare;
-        WorkerPool::get().run((size_t)n_orient, fn, 1);
-    } else {
-        for (int k = 0; k < n_orient; ++k) prepare((size_t)k, 0);
-    }
+    // The variants are prepared by a few host threads, in order, while this thread feeds the device
+    // with the variants that are ready: the preparation (~10 ms per variant) hides behind the grids.
+    std::mutex mu;
+    std::condition_variable cv;
+    std::vector<char> ready((size_t)n_orient, 0);
+    std::atomic<int> next{0};
+    std::atomic<bool> cancel{false};
+    auto producer = [&]() {
+        for (;;) {
+            const int k = next.fetch_add(1);
+            if (k >= n_orient || cancel.load()) return;
+            prepare((size_t)k, 0);
+            {
+                std::lock_guard<std::mutex> lk(mu);
+                ready[(size_t)k] = 1;
+            }
+            cv.notify_all();
+        }
+    };
+    const unsigned hw = std::thread::hardware_concurrency();
+    const int n_threads = std::max(1, std::min<int>(n_orient, std::min<int>(hw > 2 ? (int)hw - 1 : 1, 8)));
+    std::vector<std::thread> producers;
+    for (int t = 0; t < n_threads; ++t) producers.emplace_back(producer);
+    struct Joiner {
+        std::vector<std::thread>& th;
+        std::atomic<bool>& cancel;
+        ~Joiner() {
+            cancel.store(true);
+            for (auto& t : th) t.join();
+        }
+    } joiner{producers, cancel};
+    const uint64_t saved_call_no = p->call_no;
     for (int k = 0; k < n_orient; ++k) {
+        {
+            std::unique_lock<std::mutex> lk(mu);
+            cv.wait(lk, [&] { return ready[(size_t)k] != 0; });
+        }
         Prep& pr = prep[(size_t)k];
         if (pr.rc) { p->err = pr.err; return pr.rc; }
         if (pr.nq > (size_t)INT32_MAX) { p->err = "set-gyro-quaternions: too many samples"; return RSSYNC_E_INVALID; }
@@ -1556,8 +1594,10 @@ int rssync_orientation_search(rssync_problem* p, const double* timestamps_s, con
                                  p->d_rec.ptr, p->stream);
         CUDA_TRY(p, cudaGetLastError());
         std::vector<double>().swap(pr.sys);
+        if (call_nos) p->call_no = call_nos[k];
         if (int rc = rssync_presync(p, initial_delay, fb, fe, step, radius, &out_cost[k], &out_delay[k])) return rc;
     }
+    if (call_nos) p->call_no = saved_call_no;  // explicit numbers do not advance the counter
     return RSSYNC_OK;
 }
 

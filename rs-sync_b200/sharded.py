@@ -96,15 +96,26 @@ def sync_sharded(problem, initial_delay, frame_begin, frame_end, search_center, 
 
 
 def orientation_search_sharded(problem, search_fn, orientations, *, seed, call_no_base=0, rank=0, world=1,
-                               device="cpu"):
+                               device="cpu", batch_fn=None):
     """The 48-variant orientation search (core_testcode.cpp:184-233) with variant k on rank k % world.
     `search_fn(problem, [orientation])` runs one variant (integrate, ingest, PreSync) and returns
     ([cost], [delay]); the RNG call number of variant k is call_no_base + k on every rank, so the
-    gathered result equals the single-process loop.  Every rank returns all (cost, delay) pairs."""
+    gathered result equals the single-process loop.  `batch_fn(problem, orientations, call_nos)`, when
+    given, runs all of the rank's variants in one call with those explicit call numbers (the engine then
+    prepares the variants on host threads while the device evaluates the ones that are ready).
+    Every rank returns all (cost, delay) pairs."""
     n = len(orientations)
     mine = list(range(rank, n, world))
     cost, delay = np.empty(len(mine)), np.empty(len(mine))
-    for j, k in enumerate(mine):
+    if batch_fn is not None and mine:
+        problem.set_rng(seed, call_no_base)
+        c, d = batch_fn(problem, [orientations[k] for k in mine],
+                        np.array([call_no_base + k for k in mine], dtype=np.uint64))
+        cost[:], delay[:] = c, d
+        mine_loop = []
+    else:
+        mine_loop = list(enumerate(mine))
+    for j, k in mine_loop:
         problem.set_rng(seed, call_no_base + k)
         c, d = search_fn(problem, [orientations[k]])
         cost[j], delay[j] = c[0], d[0]

@@ -346,6 +346,14 @@ def test_orientation_search_matches_oracle(rsb, oracle_loader, synth_mod):
     assert g.call_counter() == 3 + len(orients)
     with pytest.raises(rsb.RsSyncError):
         g.orientation_search(ts, w.omega, ["XYZ", "XQZ"], 0.0, fb, fe, 0.005, 0.05)
+    # explicit call numbers (what a rank of the sharded search passes): a subset of the variants in
+    # one call reproduces their results of the full search and leaves the counter alone
+    before = g.call_counter()
+    sub = [4, 1, 2]
+    cs, ds = g.orientation_search(ts, w.omega, [orients[k] for k in sub], 0.0, fb, fe, 0.005, 0.05,
+                                  call_nos=np.array([3 + k for k in sub], dtype=np.uint64))
+    assert np.array_equal(cs, cg[sub]) and np.array_equal(ds, dg[sub])
+    assert g.call_counter() == before
 
 
 def test_presync_windows_equals_sequence(pair_small):

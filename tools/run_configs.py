@@ -99,8 +99,10 @@ if "C5" in which:
     search = lambda pr, ors: pr.orientation_search(ts, w.omega, ors, 0.0, fb, fe, w.presync_step, w.presync_radius)
     search(p, orients[:1])  # warm-up
     t = time.perf_counter()
+    batch = lambda pr, ors, cn: pr.orientation_search(ts, w.omega, ors, 0.0, fb, fe, w.presync_step, w.presync_radius,
+                                                      call_nos=cn)
     cost, delay = sharded.orientation_search_sharded(p, search, orients, seed=100, call_no_base=0, rank=rank,
-                                                     world=world, device=dev)
+                                                     world=world, device=dev, batch_fn=batch)
     dt = time.perf_counter() - t
     order = np.argsort(cost)
     emit({"config": f"C5: {len(orients)} gyro_orientation variants x PreSync on C2 (3300 x 200 x 200 offsets), variants sharded x{world}",
