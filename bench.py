@@ -246,6 +246,9 @@ def run_b200(args):
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=dev)
+        # one process per GPU on one host: each engine's ingest thread pool gets its share of the cores
+        local_world = int(os.environ.get("LOCAL_WORLD_SIZE", str(world)))
+        os.environ.setdefault("RSSYNC_HOST_THREADS", str(max(1, (os.cpu_count() or 1) // max(local_world, 1))))
 
     def barrier():
         if world > 1:

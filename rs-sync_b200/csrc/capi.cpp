@@ -1014,6 +1014,18 @@ void fill_track(rssync_problem* p, FrameDesc* fd, const double* ts_a, const doub
 // Persistent host worker pool for the bulk ingest (validation, sort + transpose).  Creating
 // std::threads per call costs ~30 us each, which is milliseconds per batch at 16 threads x several
 // parallel regions; the pool's threads sleep on a condition variable between regions.
+// Cores this process may use: RSSYNC_HOST_THREADS when set (one process per GPU shares the host with
+// its siblings, and an oversubscribed pool that spins between regions is worse than a small one),
+// else all of them.
+unsigned host_cores() {
+    if (const char* e = std::getenv("RSSYNC_HOST_THREADS")) {
+        const int v = std::atoi(e);
+        if (v > 0) return (unsigned)v;
+    }
+    const unsigned hw = std::thread::hardware_concurrency();
+    return hw ? hw : 1;
+}
+
 class WorkerPool {
 public:
     static WorkerPool& get() {
@@ -1057,8 +1069,8 @@ private:
         }
     }
     WorkerPool() {
-        unsigned hw = std::thread::hardware_concurrency();
         // one core is left to the gyro worker thread, which runs beside the track ingest
+        const unsigned hw = host_cores();
         const size_t n = std::min<size_t>(hw > 2 ? hw - 1 : 1, 16);
         for (size_t t = 1; t < n; ++t)
             threads_.emplace_back([this, t]() {
@@ -1556,7 +1568,7 @@ int rssync_orientation_search_ex(rssync_problem* p, const double* timestamps_s, 
             cv.notify_all();
         }
     };
-    const unsigned hw = std::thread::hardware_concurrency();
+    const unsigned hw = host_cores();
     const int n_threads = std::max(1, std::min<int>(n_orient, std::min<int>(hw > 2 ? (int)hw - 1 : 1, 8)));
     std::vector<std::thread> producers;
     for (int t = 0; t < n_threads; ++t) producers.emplace_back(producer);

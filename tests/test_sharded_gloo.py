@@ -37,6 +37,17 @@ def _worker(rank, world, port, q):
     oc, od = sharded.orientation_search_sharded(
         o2, lambda pr, ors: loader.orientation_search(pr, ts, w2.omega, ors, 0.0, 200, 212, 0.01, 0.05),
         ["XYZ", "yXz", "ZXY"], seed=100, call_no_base=7, rank=rank, world=world)
+    # the same through the batch form (one call per rank with explicit call numbers)
+    def batch(pr, ors, call_nos):
+        cs, ds = [], []
+        for o_, cn in zip(ors, call_nos):
+            pr.set_rng(100, int(cn))
+            c_, d_ = loader.orientation_search(pr, ts, w2.omega, [o_], 0.0, 200, 212, 0.01, 0.05)
+            cs.append(c_[0]); ds.append(d_[0])
+        return np.array(cs), np.array(ds)
+    bc, bd = sharded.orientation_search_sharded(o2, None, ["XYZ", "yXz", "ZXY"], seed=100, call_no_base=7,
+                                                rank=rank, world=world, batch_fn=batch)
+    assert np.array_equal(bc, oc) and np.array_equal(bd, od)
     if rank == 0:
         q.put((curve, best, c, d, oc, od))
     dist.barrier()

@@ -17,6 +17,7 @@ if world > 1:
     import torch, torch.distributed as dist
     torch.cuda.set_device(int(os.environ.get("LOCAL_RANK", "0")))
     dist.init_process_group("nccl")
+    os.environ.setdefault("RSSYNC_HOST_THREADS", str(max(1, (os.cpu_count() or 1) // int(os.environ.get("LOCAL_WORLD_SIZE", str(world))))))
     dev = torch.device("cuda", int(os.environ.get("LOCAL_RANK", "0")))
     warm = torch.zeros(1, device=dev)
     dist.all_reduce(warm)  # NCCL builds its communicator on the first collective: keep that out of the timings
