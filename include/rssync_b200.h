@@ -113,8 +113,8 @@ int rssync_presync_windows(rssync_problem* p, int n, double initial_delay, const
 int rssync_presync_delays(double initial_delay, double search_step, double search_radius,
                           double* out, int cap);
 
-/* n independent Sync calls advanced in lock-step on the device; result i equals what the i-th of
- * n consecutive rssync_sync calls would return. */
+/* n independent Sync calls advanced side by side on the device (lanes of syncpoints); result i
+ * equals what the i-th of n consecutive rssync_sync calls would return. */
 int rssync_sync_batch(rssync_problem* p, int n, const double* initial_delay,
                       const int64_t* frame_begin, const int64_t* frame_end,
                       const double* search_center, const double* search_radius, double* out_cost,

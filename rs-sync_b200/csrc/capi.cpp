@@ -1503,7 +1503,7 @@ int rssync_integrate_gyro(const double* timestamps_s, const double* gyro_xyz, si
 // The orientation search of core_testcode.cpp:184-233: for every gyro_orientation variant, integrate
 // the raw gyro (optdata_fill_gyro, :37-53), ingest it through the variable-rate SetGyroQuaternions
 // and run PreSync over the frame range.  The per-variant host work (integration, resampling,
-// spline solve) is spread over the worker pool; the 48 loss grids run back to back on the device.
+// spline elimination) runs on host threads beside the 48 loss grids, which run back to back on the device.
 int rssync_orientation_search(rssync_problem* p, const double* timestamps_s, const double* gyro_xyz,
                               size_t count, const char* const* orientations, int n_orient,
                               double initial_delay, int64_t fb, int64_t fe, double step, double radius,

@@ -873,8 +873,8 @@ __device__ __forceinline__ double warp_lbfgs(EvalF&& eval, double x[3], int& n_i
         if (it > 0 && sqrt(dot3(g[0], g[1], g[2], g[0], g[1], g[2])) < minGradientNorm) break;
         if (f != f) break;
         // The two-loop recursion is a chain of dependent scalar FP64 operations (6 per stored pair
-        // and loop); a frame that runs to maxIterations spends ~0.3 ms in it and the whole lock-step
-        // batch waits.  The next pair is therefore loaded (local memory, indices independent of the
+        // and loop); a frame that runs to maxIterations spends ~0.3 ms in it and its whole lane
+        // waits.  The next pair is therefore loaded (shared memory, indices independent of the
         // chain) while the current one is being applied.
         const int cnt = (numBasis > it) ? it : numBasis;  // stored pairs in use
         int tp = (it + (numBasis - 1)) % numBasis;        // newest pair

@@ -13,7 +13,7 @@ rs-sync_b200.synth.  `rmse_vs_linear_fit` is the accuracy figure of the thesis (
 
 Two execution modes give identical numbers: `sequential` issues the reference's call sequence
 (DebugPreSync, then per syncpoint PreSync + 4 x Sync); `batched` evaluates the same calls with
-explicit RNG call numbers, the Sync passes of all syncpoints advanced in lock-step on the device
+explicit RNG call numbers, the Sync passes of all syncpoints advanced side by side on the device
 (and, under torch.distributed, syncpoints sharded over ranks).
 """
 from __future__ import annotations

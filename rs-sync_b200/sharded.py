@@ -4,8 +4,8 @@ units sharded, one small gather per call.
 * PreSync / DebugPreSync: contiguous offset ranges per rank.  Every frame's reduction stays on
   one GPU and the RNG is keyed by the global offset index, so the gathered curve equals the
   single-GPU curve bit for bit.
-* Sync: syncpoint i goes to rank i % world; each rank advances its syncpoints in lock-step on its
-  own device; (cost, delay) pairs are gathered at the end.
+* Sync: syncpoint i goes to rank i % world; each rank advances its syncpoints side by side on its
+  own device (in independent lanes); (cost, delay) pairs are gathered at the end.
 
 The functions only need a `torch.distributed` process group (NCCL on GPUs, gloo in the CPU tests)
 and a problem object with the SyncProblem methods, so the logic is testable without a GPU.
