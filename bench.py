@@ -418,7 +418,14 @@ def read_peaks():
 
 if __name__ == "__main__":
     a = parse()
+    # stdout carries the one JSON line and nothing else: libraries that write to file descriptor 1
+    # (NCCL prints its version banner there) are sent to stderr for the duration of the run
+    sys.stdout.flush()
+    _json_out = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
+    sys.stdout = _json_out
     if a.impl == "reference":
         run_reference(a)
     else:
         run_b200(a)
+    _json_out.flush()
