@@ -203,6 +203,9 @@ struct rssync_problem {
         cudaEvent_t ev;
     };
     cudaStream_t copy_stream = nullptr;
+    static constexpr int kGridStreams = 3;  // side streams of a chunk-by-chunk PreSync grid
+    cudaStream_t grid_stream[kGridStreams] = {nullptr, nullptr, nullptr};
+    cudaEvent_t ev_grid[kGridStreams] = {nullptr, nullptr, nullptr};
     std::vector<InFlight> in_flight;
     std::vector<cudaEvent_t> ev_pool;
     cudaEvent_t ev_order = nullptr;
@@ -465,15 +468,38 @@ int presync_grid_impl(rssync_problem* p, int64_t fb, int64_t fe, const double* d
     const rs::DeviceData dd = p->device_data();
     if (p->kernel_timing) CUDA_TRY(p, cudaEventRecord(p->ev0, p->stream));
     int f0 = 0, waited = 0;
-    for (size_t r = 0; r < run_end.size(); ++r) {
-        if (run_dep[r] > waited) {
-            CUDA_TRY(p, cudaStreamWaitEvent(p->stream, p->in_flight[(size_t)run_dep[r] - 1].ev, 0));
-            waited = run_dep[r];
+    if (run_end.size() == 1) {
+        if (run_dep[0] > 0) {
+            CUDA_TRY(p, cudaStreamWaitEvent(p->stream, p->in_flight[(size_t)run_dep[0] - 1].ev, 0));
+            waited = run_dep[0];
         }
-        rs::launch_presync_tasks(dd, p->d_frames.ptr + f0, run_end[r] - f0, max_n, p->d_delays.ptr, n, p->seed,
-                                 stream_id, call_no, idx_base, p->d_framecost.ptr + f0, F, p->d_flags.ptr,
-                                 p->stream);
-        f0 = run_end[r];
+        rs::launch_presync_tasks(dd, p->d_frames.ptr, F, max_n, p->d_delays.ptr, n, p->seed, stream_id, call_no,
+                                 idx_base, p->d_framecost.ptr, F, p->d_flags.ptr, p->stream);
+    } else {
+        // The runs go round-robin to a few side streams: kernels of one stream run one after the
+        // other, so a single stream would leave the tail of every run (its last blocks) unshared;
+        // from neighbouring streams the next run's blocks move in as the previous run's retire.
+        for (int k = 0; k < rssync_problem::kGridStreams; ++k) {
+            if (!p->grid_stream[k]) CUDA_TRY(p, cudaStreamCreateWithFlags(&p->grid_stream[k], cudaStreamNonBlocking));
+            if (!p->ev_grid[k]) CUDA_TRY(p, cudaEventCreateWithFlags(&p->ev_grid[k], cudaEventDisableTiming));
+        }
+        if (!p->ev_order) CUDA_TRY(p, cudaEventCreateWithFlags(&p->ev_order, cudaEventDisableTiming));
+        CUDA_TRY(p, cudaEventRecord(p->ev_order, p->stream));  // frame table, delays, gyro records
+        for (size_t r = 0; r < run_end.size(); ++r) {
+            cudaStream_t gs = p->grid_stream[r % rssync_problem::kGridStreams];
+            if (r < (size_t)rssync_problem::kGridStreams) CUDA_TRY(p, cudaStreamWaitEvent(gs, p->ev_order, 0));
+            if (run_dep[r] > 0) {
+                CUDA_TRY(p, cudaStreamWaitEvent(gs, p->in_flight[(size_t)run_dep[r] - 1].ev, 0));
+                waited = std::max(waited, run_dep[r]);
+            }
+            rs::launch_presync_tasks(dd, p->d_frames.ptr + f0, run_end[r] - f0, max_n, p->d_delays.ptr, n, p->seed,
+                                     stream_id, call_no, idx_base, p->d_framecost.ptr + f0, F, p->d_flags.ptr, gs);
+            f0 = run_end[r];
+        }
+        for (int k = 0; k < rssync_problem::kGridStreams; ++k) {
+            CUDA_TRY(p, cudaEventRecord(p->ev_grid[k], p->grid_stream[k]));
+            CUDA_TRY(p, cudaStreamWaitEvent(p->stream, p->ev_grid[k], 0));
+        }
     }
     if (p->kernel_timing) CUDA_TRY(p, cudaEventRecord(p->ev1, p->stream));
     rs::launch_presync_reduce(p->d_framecost.ptr, F, n, p->d_costs.ptr, p->stream);
@@ -828,6 +854,10 @@ void rssync_destroy(rssync_problem* p) {
     for (const auto& fl : p->in_flight) cudaEventDestroy(fl.ev);
     for (cudaEvent_t e : p->ev_pool) cudaEventDestroy(e);
     if (p->ev_order) cudaEventDestroy(p->ev_order);
+    for (int k = 0; k < rssync_problem::kGridStreams; ++k) {
+        if (p->grid_stream[k]) cudaStreamDestroy(p->grid_stream[k]);
+        if (p->ev_grid[k]) cudaEventDestroy(p->ev_grid[k]);
+    }
     if (p->gyro_stream) { cudaStreamSynchronize(p->gyro_stream); cudaStreamDestroy(p->gyro_stream); }
     if (p->ev_gyro) cudaEventDestroy(p->ev_gyro);
     p->d_rec.release();
