@@ -12,7 +12,7 @@
 //   B  hypotheses  lanes 0..19 each build one plane normal from two random rows
 //   C  estimator  opt_guess_translational_motion (:34-59) as an fp32x2 tournament with a rigorous
 //                error margin; comparisons it cannot call are settled in binary64
-//   D  loss       robust loss of the winning normal, double-double warp sums (pre_sync body
+//   D  loss       robust loss of the winning normal, fixed-order warp sums (pre_sync body
 //                :79-85 / FrameState::Loss :92-123).
 // Cross-lane work is warp shuffles / REDUX only; the one block-level mechanism is the mbarrier
 // pipeline that stages phase A's inputs (presync_kernel).
@@ -73,8 +73,8 @@ __device__ __forceinline__ double row_inv_norm(double r0, double r1, double r2) 
 }
 
 // ------------------------------------------------------------------------------------------
-// Phase A.  Rows of the problem matrix for the whole frame -> shared memory (storage order; sums
-// over rays are order-independent double-double sums and the estimator's random draws go through
+// Phase A.  Rows of the problem matrix for the whole frame -> shared memory (storage order, which is
+// also the summation order of the contract's sums over rays; the estimator's random draws go through
 // the `pos` plane).  Entries past the frame's last ray are zero rows.
 template <bool WITH_NF>
 __device__ __forceinline__ unsigned build_rows_smem(const DeviceData& dd, const FrameDesc& fd,
