@@ -145,6 +145,7 @@ struct SyncLane {
     std::vector<SyncPointState> st;
     std::vector<int> h_stats, local_sp;
     const unsigned char* h_active = nullptr;
+    bool many_tasks = false;  // which build of the L-BFGS kernel the lane launches (engine.cu LbfgsCfg)
     // one outer iteration (copy in, four kernels, copy out) as an instantiated CUDA graph; valid as
     // long as every captured argument (graph_key) is unchanged, which holds across chained Sync calls
     cudaGraphExec_t graph_exec = nullptr;
@@ -614,7 +615,7 @@ int sync_lane_enqueue_iteration(rssync_problem* p, SyncLane& L, const rs::Device
     // device forms them and evaluates them in one launch; the host takes the first that passes.
     rs::launch_sync_motion_fgrad(dd, L.b, d_delay, d_x0, L.active_dev(), L.d_task_scratch.ptr, L.d_out.ptr,
                                  L.d_out.ptr + n, L.d_trial_delay.ptr, kTrials,
-                                 dbg ? L.d_lbfgs_stats.ptr : nullptr, L.evals_dev(), L.stream);
+                                 dbg ? L.d_lbfgs_stats.ptr : nullptr, L.evals_dev(), L.many_tasks, L.stream);
     if (dbg)
         CUDA_TRY(p, cudaMemcpyAsync(L.h_stats.data(), L.d_lbfgs_stats.ptr, sizeof(int) * 2 * L.T, cudaMemcpyDeviceToHost, L.stream));
     rs::launch_sync_trials(dd, L.b, L.d_trial_delay.ptr, kTrials, L.active_dev(), L.d_task_scratch.ptr,
@@ -654,7 +655,7 @@ int sync_lane_launch(rssync_problem* p, SyncLane& L, const rs::DeviceData& dd, b
             rs::DeviceData dd;
             rs::SyncBatchDev b;
             const void* ptr[8];
-            size_t in_doubles, out_doubles;
+            size_t in_doubles, out_doubles, many_tasks;
         } key;
         std::memset(&key, 0, sizeof(key));
         key.dd = dd;
@@ -664,6 +665,7 @@ int sync_lane_launch(rssync_problem* p, SyncLane& L, const rs::DeviceData& dd, b
         std::memcpy(key.ptr, ptrs, sizeof(ptrs));
         key.in_doubles = L.in_doubles;
         key.out_doubles = L.out_doubles;
+        key.many_tasks = L.many_tasks ? 1 : 0;
         const bool key_ok = L.graph_exec && L.graph_key.size() == sizeof(key) &&
                             std::memcmp(L.graph_key.data(), &key, sizeof(key)) == 0;
         if (!use_graphs || dbg || (!key_ok && L.iters == 1)) {
@@ -766,9 +768,15 @@ int sync_batch_impl(rssync_problem* p, int n, const double* initial, const int64
     const rs::DeviceData dd = p->device_data();
     const int G = sync_lane_count(n);
     if ((int)p->lanes.size() < G) p->lanes.resize(G);
+    // A small batch is bound by the latency of its slowest frames, a large one by throughput: past
+    // ~3 000 frame tasks (two waves of the large-block build on 148 SMs) the small-block build wins.
+    // RSSYNC_LBFGS_BLOCKS=small|large overrides (tests run both).
+    bool many_tasks = tasks.size() >= 3000;
+    if (const char* e = std::getenv("RSSYNC_LBFGS_BLOCKS")) many_tasks = e[0] == 's';
     std::vector<std::vector<int>> lane_sp_begin(G);
     for (int g = 0; g < G; ++g) {
         SyncLane& L = p->lanes[g];
+        L.many_tasks = many_tasks;
         L.s0 = (int)((long long)n * g / G);
         L.n = (int)((long long)n * (g + 1) / G) - L.s0;
         L.t0 = sp_first[L.s0];

@@ -1235,8 +1235,18 @@ sync_init_kernel(DeviceData dd, SyncBatchDev b, const double* __restrict__ sp_de
 #ifndef RS_SYNC_MINB
 #define RS_SYNC_MINB 1
 #endif
-template <int SLOTS>
-__global__ void __launch_bounds__(kWarpsPerBlock * 32, SLOTS <= 8 ? RS_SYNC_MINB : 1)
+// Two builds.  The kernel needs ~200 registers per thread (the frame's rows stay in registers across
+// the L-BFGS evaluations): eight-warp blocks, one per SM, uncapped -- the fastest for a straggler,
+// which is what bounds a small batch (C2: 27 syncpoints); and two-warp blocks capped at 168
+// registers, twelve warps per SM -- each warp ~8 % slower, but half as many waves when the batch
+// has many more frame tasks than the device has warp slots (C4).  The host picks by task count.
+template <bool SMALL>
+struct LbfgsCfg {
+    static constexpr int kWarps = SMALL ? 2 : kWarpsPerBlock;
+    static constexpr int kMinBlocks = SMALL ? 6 : RS_SYNC_MINB;
+};
+template <int SLOTS, bool SMALL>
+__global__ void __launch_bounds__(LbfgsCfg<SMALL>::kWarps * 32, SLOTS <= 8 ? LbfgsCfg<SMALL>::kMinBlocks : 1)
 sync_motion_fgrad_kernel(DeviceData dd, SyncBatchDev b, const double* __restrict__ sp_delay,
                          const double* __restrict__ sp_x0,
                          const unsigned char* __restrict__ sp_active, double* __restrict__ scratch,
@@ -1247,10 +1257,10 @@ sync_motion_fgrad_kernel(DeviceData dd, SyncBatchDev b, const double* __restrict
     double* tab = reinterpret_cast<double*>(smem_raw);
     load_log1p_table(tab);
     const WarpSmem w = warp_smem(smem_raw + kLog1pTableBytes, warp, NP, false);
-    double* hist = reinterpret_cast<double*>(smem_raw + kLog1pTableBytes +
-                                             (size_t)kWarpsPerBlock * warp_smem_bytes(NP, false)) +
+    constexpr int W = LbfgsCfg<SMALL>::kWarps;
+    double* hist = reinterpret_cast<double*>(smem_raw + kLog1pTableBytes + (size_t)W * warp_smem_bytes(NP, false)) +
                    warp * kLbfgsHistDoubles;
-    for (int t = blockIdx.x * kWarpsPerBlock + warp; t < b.T; t += gridDim.x * kWarpsPerBlock) {
+    for (int t = blockIdx.x * W + warp; t < b.T; t += gridDim.x * W) {
         const SyncTask task = b.tasks[t];
         if (!sp_active[task.sp]) continue;
         double m[3] = {b.m[3 * t], b.m[3 * t + 1], b.m[3 * t + 2]};
@@ -1614,7 +1624,7 @@ int slots_for(int max_n) {  // compile-time SLOTS instantiated for the estimator
 }
 
 template <class K>
-int grid_for(K kernel, size_t smem, long long warps_needed) {
+int grid_for(K kernel, size_t smem, long long warps_needed, int warps_per_block = kWarpsPerBlock) {
     static int sm_count = 0;
     if (!sm_count) {
         int dev = 0;
@@ -1630,12 +1640,12 @@ int grid_for(K kernel, size_t smem, long long warps_needed) {
         std::lock_guard<std::mutex> lk(mu);
         int& slot = cache[{reinterpret_cast<const void*>(kernel), smem}];
         if (!slot) {
-            cudaOccupancyMaxActiveBlocksPerMultiprocessor(&slot, kernel, kWarpsPerBlock * 32, smem);
+            cudaOccupancyMaxActiveBlocksPerMultiprocessor(&slot, kernel, warps_per_block * 32, smem);
             if (slot < 1) slot = 1;
         }
         per_sm = slot;
     }
-    long long blocks_needed = (warps_needed + kWarpsPerBlock - 1) / kWarpsPerBlock;
+    long long blocks_needed = (warps_needed + warps_per_block - 1) / warps_per_block;
     long long cap = (long long)sm_count * per_sm;
     long long g = blocks_needed < cap ? blocks_needed : cap;
     return (int)(g < 1 ? 1 : g);
@@ -1747,16 +1757,19 @@ void launch_sync_motion_fgrad(const DeviceData& dd, const SyncBatchDev& b, const
                               const double* d_sp_x0, const unsigned char* d_sp_active,
                               double* d_task_scratch, double* d_out_v, double* d_out_g,
                               double* d_trial_delay, int ntrial, int* d_lbfgs_stats,
-                              unsigned long long* d_evals_total, cudaStream_t st) {
+                              unsigned long long* d_evals_total, bool many_tasks, cudaStream_t st) {
     if (b.T <= 0) return;
-    RS_DISPATCH_SLOTS(b.max_n, {
-        auto kern = sync_motion_fgrad_kernel<SL>;
-        const size_t smem = kLog1pTableBytes + (size_t)kWarpsPerBlock * warp_smem_bytes(SL * 32, false) +
-                            (size_t)kWarpsPerBlock * kLbfgsHistDoubles * sizeof(double);
+    auto launch = [&](auto kern, int W) {
+        const size_t smem = kLog1pTableBytes + (size_t)W * warp_smem_bytes(slots_for(b.max_n) * 32, false) +
+                            (size_t)W * kLbfgsHistDoubles * sizeof(double);
         allow_smem(kern, smem);
-        const int grid = grid_for(kern, smem, b.T);
-        kern<<<grid, kWarpsPerBlock * 32, smem, st>>>(dd, b, d_sp_delay, d_sp_x0, d_sp_active, d_task_scratch,
-                                                      d_lbfgs_stats, d_evals_total);
+        const int grid = grid_for(kern, smem, b.T, W);
+        kern<<<grid, W * 32, smem, st>>>(dd, b, d_sp_delay, d_sp_x0, d_sp_active, d_task_scratch, d_lbfgs_stats,
+                                         d_evals_total);
+    };
+    RS_DISPATCH_SLOTS(b.max_n, {
+        if (many_tasks) launch(sync_motion_fgrad_kernel<SL, true>, LbfgsCfg<true>::kWarps);
+        else launch(sync_motion_fgrad_kernel<SL, false>, LbfgsCfg<false>::kWarps);
     });
     reduce_fgrad_kernel<<<(b.S + 3) / 4, 128, 0, st>>>(b, d_sp_active, d_task_scratch, d_sp_x0, d_out_v,
                                                        d_out_g, d_trial_delay, ntrial);

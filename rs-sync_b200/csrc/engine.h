@@ -88,7 +88,10 @@ void launch_sync_motion_fgrad(const DeviceData& dd, const SyncBatchDev& b, const
                               double* d_task_scratch /* T x 3 */, double* d_out_v, double* d_out_g,
                               double* d_trial_delay /* S x ntrial */, int ntrial,
                               int* d_lbfgs_stats /* T x 2 or null */,
-                              unsigned long long* d_evals_total /* or null */, cudaStream_t st);
+                              unsigned long long* d_evals_total /* or null */,
+                              bool many_tasks /* the batch has many more tasks than the device has warp
+                                                 slots: use the small-block, register-capped build */,
+                              cudaStream_t st);
 // Loss3 summed per syncpoint at ntrial delays per syncpoint (simple_objective, :242-252)
 void launch_sync_trials(const DeviceData& dd, const SyncBatchDev& b, const double* d_trial_delay,
                         int ntrial, const unsigned char* d_sp_active,

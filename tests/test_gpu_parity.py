@@ -219,6 +219,26 @@ def test_sync_batch_equals_sequence(pair_small):
     assert np.array_equal(cb, np.array([s[0] for s in seq]))
 
 
+def test_sync_batch_both_lbfgs_kernel_builds_and_any_lane_count(pair_small, monkeypatch):
+    """the engine picks the L-BFGS kernel build (large / small blocks) by batch size and cuts the
+    batch into lanes: neither may change a bit of any syncpoint's result"""
+    g, o, w = pair_small
+    f0 = int(w.frame_ids[0])
+    fbs = np.array([f0 + 3 * i for i in range(9)])
+    fes = fbs + 25
+    ini = np.linspace(0.034, 0.040, 9)
+    g.set_rng(100, 70)
+    want = g.sync_batch(ini, fbs, fes, 0.0, 0.2)
+    for build in ("small", "large"):
+        monkeypatch.setenv("RSSYNC_LBFGS_BLOCKS", build)
+        g.set_rng(100, 70)
+        got = g.sync_batch(ini, fbs, fes, 0.0, 0.2)
+        assert np.array_equal(got[0], want[0]) and np.array_equal(got[1], want[1])
+    monkeypatch.delenv("RSSYNC_LBFGS_BLOCKS")
+    co, do = o.sync_batch(ini, fbs, fes, 0.0, 0.2, call_nos=70 + np.arange(9, dtype=np.uint64))
+    assert rel_err(want[1], do) <= TOL and rel_err(want[0], co) <= TOL
+
+
 def test_ragged_and_sparse_frames(rsb, oracle_loader):
     """frames with different ray counts, gaps in the frame numbering, re-set frames"""
     w = workload("tiny")
