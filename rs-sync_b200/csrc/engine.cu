@@ -998,6 +998,9 @@ __device__ __noinline__ unsigned presync_diagnose(const double* pm, int nslots, 
 // of unit u issues the copies for unit u + 1, which then overlap phases B-D of unit u.  (With
 // ~200 KB of the SM's 228 KB carved out as shared memory the L1 keeps ~13 KB: un-staged, the same
 // loads hit L1 28 % of the time and wait on L2, profiles/r01_presync_v3c.md.)
+#ifndef RS_POLL_NS
+#define RS_POLL_NS 64  // back-off between polls of the staging mbarrier
+#endif
 #ifndef RS_REC_MAX
 #define RS_REC_MAX 64
 #endif
@@ -1100,7 +1103,7 @@ presync_kernel(DeviceData dd, const FrameDesc* __restrict__ frames, int F,
         const int fi = u / cpf, d0 = (u % cpf) * chunk;
         const FrameDesc fd = frames[fi];
         const int nslots = (fd.n + 31) >> 5;
-        while (!mbar_try_wait(&ctl->full, parity)) __nanosleep(64);
+        while (!mbar_try_wait(&ctl->full, parity)) __nanosleep(RS_POLL_NS);
         parity ^= 1u;
         const int rec_first = *(volatile int*)&ctl->rec_first, rec_cnt = *(volatile int*)&ctl->rec_cnt;
       for (int rep = 0; rep < reps; ++rep) {
