@@ -1189,7 +1189,16 @@ int rssync_set_track_batch(rssync_problem* p, size_t n_frames, const int64_t* fr
     for (size_t i = 0; i < n_frames; ++i) at[i + 1] = at[i] + counts[i];
     std::vector<int> rc(n_frames, 0);
     std::vector<const char*> msg(n_frames, nullptr);
+    // A frame id that appears twice in one batch: the blocks of one ingest launch would write the same
+    // arena range concurrently.  The contract is n_frames SetTrackResult calls in order (the last one
+    // wins, the reference's map semantics), which the frame-by-frame path below gives by construction.
+    bool has_duplicates = false;
     if (n_frames >= 64) {
+        std::vector<int64_t> ids(frames, frames + n_frames);
+        std::sort(ids.begin(), ids.end());
+        has_duplicates = std::adjacent_find(ids.begin(), ids.end()) != ids.end();
+    }
+    if (n_frames >= 64 && !has_duplicates) {
         // Large batch: the sort by ts_a and the transpose into tiles run on the device
         // (ingest_rays_kernel).  The host makes ONE pass over the caller's buffers: each value is
         // checked (the reference's panic conditions, core_private.cpp:199-202) while it is copied

@@ -27,6 +27,7 @@
 #include <cstdio>
 #include <map>
 #include <mutex>
+#include <tuple>
 #include <utility>
 
 #include "device_math.cuh"
@@ -1036,8 +1037,8 @@ struct StageCtl {
 template <int SLOTS>
 __device__ __noinline__ void presync_stage_unit(const DeviceData& dd, const FrameDesc* frames,
                                                    const double* delays, int D, int chunk, int cpf,
-                                                   int u, StageCtl* ctl, double* sTiles, double* sRec) {
-    const int fi = u / cpf, d0 = (u % cpf) * chunk;
+                                                   int fi, int ci, StageCtl* ctl, double* sTiles, double* sRec) {
+    const int d0 = ci * chunk;
     const int d1 = min(D, d0 + chunk);
     const FrameDesc fd = frames[fi];
     double dmin = delays[d0], dmax = dmin;
@@ -1084,7 +1085,10 @@ presync_kernel(DeviceData dd, const FrameDesc* __restrict__ frames, int F,
     double* sRec = reinterpret_cast<double*>(smem_raw + Cfg::kRecOff);
     const WarpSmem w = warp_smem(smem_raw + Cfg::kWarpOff, warp, NP, true);
     const long long U = (long long)F * cpf;
-    const int u_begin = (int)(U * blockIdx.x / gridDim.x), u_end = (int)(U * (blockIdx.x + 1) / gridDim.x);
+    // units are counted in 64 bits: the host accepts grids up to 2^40 tasks (F * ceil(D / chunk) can
+    // pass 2^31)
+    const long long u_begin = U * blockIdx.x / gridDim.x;
+    const int n_units = (int)(U * (blockIdx.x + 1) / gridDim.x - u_begin);  // per block: fits an int
     if (threadIdx.x == 0) {
         mbar_init(&ctl->full, 1);
         ctl->arrived = 0;
@@ -1092,15 +1096,17 @@ presync_kernel(DeviceData dd, const FrameDesc* __restrict__ frames, int F,
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     load_log1p_table(tab);  // ends with __syncthreads()
-    if (threadIdx.x == 0 && u_begin < u_end)
-        presync_stage_unit<SLOTS>(dd, frames, delays, D, chunk, cpf, u_begin, ctl, sTiles, sRec);
+    // (frame, chunk) of the current unit, advanced incrementally (one 64-bit division per block)
+    int fi = (int)(u_begin / cpf), ci = (int)(u_begin % cpf);
+    if (threadIdx.x == 0 && n_units > 0)
+        presync_stage_unit<SLOTS>(dd, frames, delays, D, chunk, cpf, fi, ci, ctl, sTiles, sRec);
     unsigned parity = 0;
     // a unit holds up to kTasksPerWarp delays per warp: warp j takes delays j, j + W, ... of the
     // chunk one after the other, so the warps of a block meet (and poll) once per several tasks and
     // the differences between their tasks' tournament lengths average out
     const int reps = (chunk + Cfg::kWarps - 1) / Cfg::kWarps;
-    for (int u = u_begin; u < u_end; ++u) {
-        const int fi = u / cpf, d0 = (u % cpf) * chunk;
+    for (int u = 0; u < n_units; ++u, fi += (ci + 1 == cpf), ci = (ci + 1 == cpf) ? 0 : ci + 1) {
+        const int d0 = ci * chunk;
         const FrameDesc fd = frames[fi];
         const int nslots = (fd.n + 31) >> 5;
         while (!mbar_try_wait(&ctl->full, parity)) __nanosleep(RS_POLL_NS);
@@ -1122,8 +1128,9 @@ presync_kernel(DeviceData dd, const FrameDesc* __restrict__ frames, int F,
             __threadfence_block();           // needs the staging buffers
             if (atomicAdd(&ctl->arrived, 1u) == (unsigned)(Cfg::kWarps - 1)) {
                 ctl->arrived = 0;
-                if (u + 1 < u_end)
-                    presync_stage_unit<SLOTS>(dd, frames, delays, D, chunk, cpf, u + 1, ctl, sTiles, sRec);
+                if (u + 1 < n_units)
+                    presync_stage_unit<SLOTS>(dd, frames, delays, D, chunk, cpf, fi + (ci + 1 == cpf),
+                                              (ci + 1 == cpf) ? 0 : ci + 1, ctl, sTiles, sRec);
             }
         }
         if (!active) continue;
@@ -1626,30 +1633,43 @@ int slots_for(int max_n) {  // compile-time SLOTS instantiated for the estimator
     return 16;
 }
 
+// Launch-configuration caches.  Both the opt-in to large dynamic shared memory
+// (cudaFuncSetAttribute) and the occupancy of a kernel are properties of a (device, kernel) pair:
+// a process may hold problems on several GPUs (rssync_create_multi), so everything here is keyed
+// by the calling thread's current device.
+int current_device() {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    return dev;
+}
+int sm_count_of(int dev) {
+    static std::mutex mu;
+    static std::map<int, int> cache;
+    std::lock_guard<std::mutex> lk(mu);
+    int& n = cache[dev];
+    if (!n) cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+    return n;
+}
+// resident blocks per SM of `kernel` at this block size / shared memory size (>= 1); one occupancy
+// query per (device, kernel, shared memory size): the Sync driver launches thousands of small
+// kernels per second
+template <class K>
+int blocks_per_sm(K kernel, int threads, size_t smem) {
+    static std::mutex mu;
+    static std::map<std::tuple<int, const void*, size_t>, int> cache;
+    std::lock_guard<std::mutex> lk(mu);
+    int& slot = cache[std::make_tuple(current_device(), reinterpret_cast<const void*>(kernel), smem)];
+    if (!slot) {
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&slot, kernel, threads, smem);
+        if (slot < 1) slot = 1;
+    }
+    return slot;
+}
 template <class K>
 int grid_for(K kernel, size_t smem, long long warps_needed, int warps_per_block = kWarpsPerBlock) {
-    static int sm_count = 0;
-    if (!sm_count) {
-        int dev = 0;
-        cudaGetDevice(&dev);
-        cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev);
-    }
-    // one occupancy query per (kernel, shared memory size): the Sync driver launches thousands of
-    // small kernels per second
-    static std::mutex mu;
-    static std::map<std::pair<const void*, size_t>, int> cache;
-    int per_sm = 0;
-    {
-        std::lock_guard<std::mutex> lk(mu);
-        int& slot = cache[{reinterpret_cast<const void*>(kernel), smem}];
-        if (!slot) {
-            cudaOccupancyMaxActiveBlocksPerMultiprocessor(&slot, kernel, warps_per_block * 32, smem);
-            if (slot < 1) slot = 1;
-        }
-        per_sm = slot;
-    }
+    const int per_sm = blocks_per_sm(kernel, warps_per_block * 32, smem);
     long long blocks_needed = (warps_needed + warps_per_block - 1) / warps_per_block;
-    long long cap = (long long)sm_count * per_sm;
+    long long cap = (long long)sm_count_of(current_device()) * per_sm;
     long long g = blocks_needed < cap ? blocks_needed : cap;
     return (int)(g < 1 ? 1 : g);
 }
@@ -1657,9 +1677,9 @@ int grid_for(K kernel, size_t smem, long long warps_needed, int warps_per_block 
 template <class K>
 void allow_smem(K kernel, size_t smem) {
     static std::mutex mu;
-    static std::map<const void*, size_t> allowed;  // per kernel: the largest size already granted
+    static std::map<std::pair<int, const void*>, size_t> allowed;  // the largest size already granted
     std::lock_guard<std::mutex> lk(mu);
-    size_t& have = allowed[reinterpret_cast<const void*>(kernel)];
+    size_t& have = allowed[{current_device(), reinterpret_cast<const void*>(kernel)}];
     if (smem <= have) return;
     cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     have = smem;
@@ -1694,17 +1714,8 @@ void launch_presync_tasks(const DeviceData& dd, const FrameDesc* d_frames, int F
         const int per_unit = Cfg::kWarps * Cfg::kTasksPerWarp;
         const int cpf = (D + per_unit - 1) / per_unit;
         const int chunk = (D + cpf - 1) / cpf;
-        static int sm_count = 0;
-        if (!sm_count) {
-            int dev = 0;
-            cudaGetDevice(&dev);
-            cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev);
-        }
-        static int per_sm = 0;  // per SLOTS instantiation (the lambda body is instantiated per case)
-        if (!per_sm) {
-            cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, Cfg::kWarps * 32, Cfg::kSmem);
-            if (per_sm < 1) per_sm = 1;
-        }
+        const int sm_count = sm_count_of(current_device());
+        const int per_sm = blocks_per_sm(kern, Cfg::kWarps * 32, Cfg::kSmem);
         const long long units = (long long)F * ((D + chunk - 1) / chunk);
         const int grid = (int)std::max<long long>(1, std::min<long long>(units, (long long)sm_count * per_sm));
         kern<<<grid, Cfg::kWarps * 32, Cfg::kSmem, st>>>(dd, d_frames, F, d_delays, D, chunk,
@@ -1761,7 +1772,10 @@ void launch_sync_motion_fgrad(const DeviceData& dd, const SyncBatchDev& b, const
                               double* d_task_scratch, double* d_out_v, double* d_out_g,
                               double* d_trial_delay, int ntrial, int* d_lbfgs_stats,
                               unsigned long long* d_evals_total, bool many_tasks, cudaStream_t st) {
-    if (b.T <= 0) return;
+    // A lane whose syncpoints hold no frames (T == 0) still needs its sums: the reference adds over
+    // an empty frame list, cost 0 and gradient 0 (core_private.cpp:228-240), and the host's
+    // Backtrack / momentum step reads them -- only the per-task kernel is skipped.
+    if (b.S <= 0) return;
     auto launch = [&](auto kern, int W) {
         const size_t smem = kLog1pTableBytes + (size_t)W * warp_smem_bytes(slots_for(b.max_n) * 32, false) +
                             (size_t)W * kLbfgsHistDoubles * sizeof(double);
@@ -1770,7 +1784,7 @@ void launch_sync_motion_fgrad(const DeviceData& dd, const SyncBatchDev& b, const
         kern<<<grid, W * 32, smem, st>>>(dd, b, d_sp_delay, d_sp_x0, d_sp_active, d_task_scratch, d_lbfgs_stats,
                                          d_evals_total);
     };
-    RS_DISPATCH_SLOTS(b.max_n, {
+    if (b.T > 0) RS_DISPATCH_SLOTS(b.max_n, {
         if (many_tasks) launch(sync_motion_fgrad_kernel<SL, true>, LbfgsCfg<true>::kWarps);
         else launch(sync_motion_fgrad_kernel<SL, false>, LbfgsCfg<false>::kWarps);
     });
@@ -1782,13 +1796,15 @@ void launch_sync_motion_fgrad(const DeviceData& dd, const SyncBatchDev& b, const
 void launch_sync_trials(const DeviceData& dd, const SyncBatchDev& b, const double* d_trial_delay,
                         int ntrial, const unsigned char* d_sp_active, double* d_task_scratch,
                         double* d_out, cudaStream_t st) {
-    if (b.T <= 0 || ntrial <= 0) return;
-    const int NP = slots_for(b.max_n) * 32;
-    const size_t smem = kLog1pTableBytes + (size_t)kWarpsPerBlock * warp_smem_bytes(NP, false);
-    allow_smem(sync_trials_kernel, smem);
-    const int grid = grid_for(sync_trials_kernel, smem, (long long)b.T * ntrial);
-    sync_trials_kernel<<<grid, kWarpsPerBlock * 32, smem, st>>>(dd, b, NP, d_trial_delay, ntrial,
-                                                                d_sp_active, d_task_scratch);
+    if (b.S <= 0 || ntrial <= 0) return;
+    if (b.T > 0) {  // (T == 0: sums over no frames, see launch_sync_motion_fgrad)
+        const int NP = slots_for(b.max_n) * 32;
+        const size_t smem = kLog1pTableBytes + (size_t)kWarpsPerBlock * warp_smem_bytes(NP, false);
+        allow_smem(sync_trials_kernel, smem);
+        const int grid = grid_for(sync_trials_kernel, smem, (long long)b.T * ntrial);
+        sync_trials_kernel<<<grid, kWarpsPerBlock * 32, smem, st>>>(dd, b, NP, d_trial_delay, ntrial,
+                                                                    d_sp_active, d_task_scratch);
+    }
     reduce_trials_kernel<<<(b.S * ntrial + 3) / 4, 128, 0, st>>>(b, ntrial, d_sp_active, d_task_scratch, d_out);
     g_launches += 2;
 }
