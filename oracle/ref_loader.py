@@ -24,10 +24,18 @@ def _dp(a):
     return a.ctypes.data_as(c_double_p)
 
 
-def lib():
+def lib(path=None):
+    """path: an alternative build of the same reference sources (tools/sync_vs_reference.py)"""
     global _LIB
+    if path is not None:
+        return _bind(C.CDLL(path))
     if _LIB is None:
-        L = C.CDLL(PATH)
+        _LIB = _bind(C.CDLL(PATH))
+    return _LIB
+
+
+def _bind(L):
+    if True:
         L.ref_create.restype = C.c_void_p
         L.ref_destroy.argtypes = [C.c_void_p]
         L.ref_set_threads.argtypes = [C.c_int]
@@ -52,15 +60,14 @@ def lib():
         L.ref_loss.argtypes = [C.c_void_p, C.c_int64, C.c_double, c_double_p, C.c_double, c_double_p, c_double_p,
                                c_double_p, c_double_p]
         L.ref_slerp.argtypes = [c_double_p, c_double_p, C.c_double, c_double_p]
-        _LIB = L
-    return _LIB
+    return L
 
 
 class RefProblem:
     """ISyncProblem of the reference itself (SyncProblemPrivate, core_private.hpp:44-61)."""
 
-    def __init__(self, threads=1, seed=100):
-        self.L = lib()
+    def __init__(self, threads=1, seed=100, lib_path=None):
+        self.L = lib(lib_path)
         self.h = C.c_void_p(self.L.ref_create())
         self.L.ref_set_threads(threads)
         self.seed = seed

@@ -432,7 +432,10 @@ int presync_grid_impl(rssync_problem* p, int64_t fb, int64_t fe, const double* d
         std::fill(costs, costs + n, 0.0);
         return RSSYNC_OK;
     }
-    if ((long long)F * n > (1LL << 40)) { p->err = "pre-sync: grid too large"; return RSSYNC_E_INVALID; }
+    if ((long long)F * n > (1LL << 34)) { p->err = "pre-sync: grid too large"; return RSSYNC_E_INVALID; }
+    double span = 0.0;
+    for (const FrameDesc& fd : sel) span = std::max(span, fd.ts_hi - fd.ts_lo);
+    const int max_chunk = rs::presync_max_chunk(delays, n, span, p->sr, max_n);
     CUDA_TRY(p, p->d_frames.reserve(F));
     CUDA_TRY(p, p->d_delays.reserve(n));
     CUDA_TRY(p, p->d_framecost.reserve((size_t)F * n));
@@ -475,7 +478,7 @@ int presync_grid_impl(rssync_problem* p, int64_t fb, int64_t fe, const double* d
             waited = run_dep[0];
         }
         rs::launch_presync_tasks(dd, p->d_frames.ptr, F, max_n, p->d_delays.ptr, n, p->seed, stream_id, call_no,
-                                 idx_base, p->d_framecost.ptr, F, p->d_flags.ptr, p->stream);
+                                 idx_base, p->d_framecost.ptr, F, p->d_flags.ptr, p->stream, nullptr, max_chunk);
     } else {
         // The runs go round-robin to a few side streams: kernels of one stream run one after the
         // other, so a single stream would leave the tail of every run (its last blocks) unshared;
@@ -494,7 +497,8 @@ int presync_grid_impl(rssync_problem* p, int64_t fb, int64_t fe, const double* d
                 waited = std::max(waited, run_dep[r]);
             }
             rs::launch_presync_tasks(dd, p->d_frames.ptr + f0, run_end[r] - f0, max_n, p->d_delays.ptr, n, p->seed,
-                                     stream_id, call_no, idx_base, p->d_framecost.ptr + f0, F, p->d_flags.ptr, gs);
+                                     stream_id, call_no, idx_base, p->d_framecost.ptr + f0, F, p->d_flags.ptr, gs,
+                                     nullptr, max_chunk);
             f0 = run_end[r];
         }
         for (int k = 0; k < rssync_problem::kGridStreams; ++k) {
@@ -1482,7 +1486,10 @@ int rssync_presync_windows(rssync_problem* p, int n, double initial, const int64
     std::vector<double> costs((size_t)n * D, 0.0);
     unsigned flags[2] = {0, 0};
     if (F > 0) {
-        if ((long long)F * D > (1LL << 40)) { p->err = "pre-sync: grid too large"; return RSSYNC_E_INVALID; }
+        if ((long long)F * D > (1LL << 34)) { p->err = "pre-sync: grid too large"; return RSSYNC_E_INVALID; }
+        double span = 0.0;
+        for (const FrameDesc& fd : all) span = std::max(span, fd.ts_hi - fd.ts_lo);
+        const int max_chunk = rs::presync_max_chunk(delays.data(), D, span, p->sr, max_n);
         CUDA_TRY(p, p->d_frames.reserve(F));
         CUDA_TRY(p, p->d_delays.reserve(D));
         CUDA_TRY(p, p->d_framecost.reserve((size_t)F * D));
@@ -1497,7 +1504,7 @@ int rssync_presync_windows(rssync_problem* p, int n, double initial, const int64
         CUDA_TRY(p, cudaMemsetAsync(p->d_flags.ptr, 0, 2 * sizeof(unsigned), p->stream));
         rs::launch_presync_grid(p->device_data(), p->d_frames.ptr, F, max_n, p->d_delays.ptr, D, p->seed,
                                 rs::kStreamPreSync, 0, 0, p->d_framecost.ptr, p->d_costs.ptr, p->d_flags.ptr,
-                                p->stream, nullptr, nullptr, p->d_frame_call.ptr, p->d_win_begin.ptr, n);
+                                p->stream, nullptr, nullptr, p->d_frame_call.ptr, p->d_win_begin.ptr, n, max_chunk);
         CUDA_TRY(p, cudaGetLastError());
         if (int rc = d2h(p, costs.data(), p->d_costs.ptr, sizeof(double) * n * D)) return rc;
         if (int rc = d2h(p, flags, p->d_flags.ptr, 2 * sizeof(unsigned))) return rc;

@@ -24,6 +24,7 @@
 
 #include <algorithm>
 #include <atomic>
+#include <cmath>
 #include <cstdio>
 #include <map>
 #include <mutex>
@@ -47,23 +48,19 @@ constexpr int kWarpsPerBlock = RS_WPB;
 
 std::atomic<uint64_t> g_launches{0};
 
-// per-warp shared-memory slice
+// per-warp shared-memory slice: the raw rows of the problem matrix, SoA [3][NP], in STORAGE order
+// (rays are stored sorted by ts_a).  That is ALL a task keeps in shared memory: the estimator's fp32
+// row-normalised copy lives in registers (load_normalised_rows32), the cold binary64 paths work from
+// registers too.  (r01 kept the fp32 copy and the cold paths' scratch here as well: 8.4 KB per warp
+// instead of 5.25 KB at N = 200, which is what left no room to double-buffer the staged inputs.)
 struct WarpSmem {
-    double* P;  // raw rows, SoA [3][NP], in STORAGE order (rays are stored sorted by ts_a)
-    // estimator kernels only: the row-normalised rows in fp32, laid out [3][NPAIR][32 lanes][2]
-    // so that lane l reads its slots (2p, 2p+1) as one float2.  The same bytes are reused as
-    // 1/|row| doubles + select keys by the exact estimator and as P.M doubles by the loss phase.
-    float* nf;
+    double* P;
 };
 __host__ __device__ constexpr int pairs_for(int NP) { return (NP / 32 + 1) / 2; }
-__host__ __device__ constexpr size_t warp_smem_bytes(int NP, bool ransac) {
-    return (size_t)NP * 3 * 8 + (ransac ? (size_t)pairs_for(NP) * 64 * 3 * 4 : 0);
-}
-__device__ __forceinline__ WarpSmem warp_smem(unsigned char* base, int warp, int NP, bool ransac) {
-    unsigned char* p = base + (size_t)warp * warp_smem_bytes(NP, ransac);
+__host__ __device__ constexpr size_t warp_smem_bytes(int NP) { return (size_t)NP * 3 * 8; }
+__device__ __forceinline__ WarpSmem warp_smem(unsigned char* base, int warp, int NP) {
     WarpSmem w;
-    w.P = reinterpret_cast<double*>(p);
-    w.nf = reinterpret_cast<float*>(w.P + 3 * NP);
+    w.P = reinterpret_cast<double*>(base + (size_t)warp * warp_smem_bytes(NP));
     return w;
 }
 
@@ -76,14 +73,10 @@ __device__ __forceinline__ double row_inv_norm(double r0, double r1, double r2) 
 // ------------------------------------------------------------------------------------------
 // Phase A.  Rows of the problem matrix for the whole frame -> shared memory (storage order, which is
 // also the summation order of the contract's sums over rays; the estimator's random draws go through
-// the `pos` plane).  Entries past the frame's last ray are zero rows.
-template <bool WITH_NF>
-__device__ __forceinline__ unsigned build_rows_smem(const DeviceData& dd, const FrameDesc& fd,
-                                                    double delay, int lane, const WarpSmem& w,
-                                                    int NP) {
-    float fin = 0.f;  // stays finite iff every row is (rows and 1/|row| feed it)
+// the `pos` plane).  Entries past the frame's last ray, up to NP, are zero rows.
+__device__ __forceinline__ void build_rows_smem(const DeviceData& dd, const FrameDesc& fd, double delay,
+                                                int lane, const WarpSmem& w, int NP) {
     const int nslots = (fd.n + 31) >> 5;
-    const int NPAIR = pairs_for(NP);
     for (int s = 0; s < nslots; ++s) {
         const int i = s * 32 + lane;
         const double* t = dd.rays + ((size_t)fd.off + s * 32) * 8 + lane;  // tile [8 fields][32 rays]
@@ -96,43 +89,19 @@ __device__ __forceinline__ unsigned build_rows_smem(const DeviceData& dd, const 
         w.P[i] = row[0];
         w.P[NP + i] = row[1];
         w.P[2 * NP + i] = row[2];
-        if (WITH_NF) {  // fp32 normalised copy for the tournament, see build_rows_staged
-            const float n2 = (float)dot3(row[0], row[1], row[2], row[0], row[1], row[2]);
-            float rs;
-            asm("rsqrt.approx.f32 %0, %1;" : "=f"(rs) : "f"(n2));
-            if (i >= fd.n) rs = 0.f;
-            else if (n2 < 1e-24f) rs = __uint_as_float(0x7fc00000u);
-            const int at = (((s >> 1) * 32 + lane) << 1) + (s & 1);
-            const float f0 = (float)row[0] * rs, f1 = (float)row[1] * rs, f2 = (float)row[2] * rs;
-            w.nf[at] = f0;
-            w.nf[NPAIR * 64 + at] = f1;
-            w.nf[2 * NPAIR * 64 + at] = f2;
-            fin += (fabsf(f0) + fabsf(f1)) + fabsf(f2);  // non-finite row -> NaN
-        }
     }
-    for (int s = nslots; s < (WITH_NF ? 2 * NPAIR : NP / 32); ++s) {
-        const int i = s * 32 + lane;
-        if (i < NP) {
-            w.P[i] = 0.0;
-            w.P[NP + i] = 0.0;
-            w.P[2 * NP + i] = 0.0;
-        }
-        if (WITH_NF) {
-            const int at = (((s >> 1) * 32 + lane) << 1) + (s & 1);
-            w.nf[at] = 0.f;
-            w.nf[NPAIR * 64 + at] = 0.f;
-            w.nf[2 * NPAIR * 64 + at] = 0.f;
-        }
+    for (int i = nslots * 32 + lane; i < NP; i += 32) {
+        w.P[i] = 0.0;
+        w.P[NP + i] = 0.0;
+        w.P[2 * NP + i] = 0.0;
     }
     __syncwarp();
-    return (__float_as_uint(fin) & 0x7f800000u) == 0x7f800000u ? kFlagP : 0u;
 }
 
 // out-of-line copy for kernels whose hot path is the staged variant below
-__device__ __noinline__ unsigned build_rows_global_cold(const DeviceData& dd, const FrameDesc& fd,
-                                                        double delay, int lane, const WarpSmem& w,
-                                                        int NP) {
-    return build_rows_smem<true>(dd, fd, delay, lane, w, NP);
+__device__ __noinline__ void build_rows_global_cold(const DeviceData& dd, const FrameDesc& fd, double delay,
+                                                    int lane, const WarpSmem& w, int NP) {
+    build_rows_smem(dd, fd, delay, lane, w, NP);
 }
 
 // ---- TMA bulk copies + mbarrier (PTX, sm_90+) --------------------------------------------------
@@ -166,7 +135,7 @@ __device__ __forceinline__ void tma_load_1d(void* dst_smem, const void* src_gmem
         : "memory");
 }
 
-// Phase A of the PreSync grid kernel: same arithmetic as build_rows_smem<true>, with the frame's ray
+// Phase A of the PreSync grid kernel: same arithmetic as build_rows_smem, with the frame's ray
 // tiles (sTiles) and the spline records [rec_first, rec_first + rec_cnt) (sRec) staged in shared
 // memory by TMA.  The window is computed from the frame's timestamp bounds with a record of slack, so
 // every evaluation lands inside it and 0 <= x < 2^31 holds; the loop body is therefore branch-free
@@ -194,14 +163,12 @@ __device__ __forceinline__ void spline_eval4_staged(uint32_t sRecAddr, unsigned 
     q[2] = fma(fma(fma(d23.x, h, c23.x), h, b23.x), h, y23.x);
     q[3] = fma(fma(fma(d23.y, h, c23.y), h, b23.y), h, y23.y);
 }
-__device__ __forceinline__ unsigned build_rows_staged(const DeviceData& dd, const FrameDesc& fd,
-                                                      double delay, int lane, const WarpSmem& w, int NP,
-                                                      const double* __restrict__ sTiles,
-                                                      const double* __restrict__ sRec, int rec_first,
-                                                      int rec_cnt) {
-    float fin = 0.f;
+__device__ __forceinline__ void build_rows_staged(const DeviceData& dd, const FrameDesc& fd, double delay,
+                                                  int lane, const WarpSmem& w, int NP,
+                                                  const double* __restrict__ sTiles,
+                                                  const double* __restrict__ sRec, int rec_first,
+                                                  int rec_cnt) {
     const int nslots = (fd.n + 31) >> 5;
-    const int NPAIR = pairs_for(NP);
     const double kTwo52 = 4503599627370496.0;
     const unsigned last = (unsigned)(rec_cnt - 1);
     const uint32_t sRecAddr = smem_u32(sRec);
@@ -230,37 +197,17 @@ __device__ __forceinline__ unsigned build_rows_staged(const DeviceData& dd, cons
         w.P[i] = row[0];
         w.P[NP + i] = row[1];
         w.P[2 * NP + i] = row[2];
-        // fp32 copy of the row-normalised row for the tournament: any accuracy the margin covers
-        // will do, so the norm is taken with rsqrt.approx (rel. error <= 2^-22.4).  Rows that
-        // safe_normalize would leave unscaled (|row| < 1e-12, also out of fp32 range) poison `fin`
-        // and send the task to the exact estimator.
-        const float n2 = (float)dot3(row[0], row[1], row[2], row[0], row[1], row[2]);
-        float rs;
-        asm("rsqrt.approx.f32 %0, %1;" : "=f"(rs) : "f"(n2));
-        if (i >= fd.n) rs = 0.f;
-        else if (n2 < 1e-24f) rs = __uint_as_float(0x7fc00000u);
-        const int at = (((s >> 1) * 32 + lane) << 1) + (s & 1);
-        const float f0 = (float)row[0] * rs, f1 = (float)row[1] * rs, f2 = (float)row[2] * rs;
-        w.nf[at] = f0;
-        w.nf[NPAIR * 64 + at] = f1;
-        w.nf[2 * NPAIR * 64 + at] = f2;
-        fin += (fabsf(f0) + fabsf(f1)) + fabsf(f2);  // non-finite row -> NaN
     }
-    if (__any_sync(FULL, outside != 0u)) return build_rows_global_cold(dd, fd, delay, lane, w, NP);
-    for (int s = nslots; s < 2 * NPAIR; ++s) {
-        const int i = s * 32 + lane;
-        if (i < NP) {
-            w.P[i] = 0.0;
-            w.P[NP + i] = 0.0;
-            w.P[2 * NP + i] = 0.0;
-        }
-        const int at = (((s >> 1) * 32 + lane) << 1) + (s & 1);
-        w.nf[at] = 0.f;
-        w.nf[NPAIR * 64 + at] = 0.f;
-        w.nf[2 * NPAIR * 64 + at] = 0.f;
+    if (__any_sync(FULL, outside != 0u)) {
+        build_rows_global_cold(dd, fd, delay, lane, w, NP);
+        return;
+    }
+    for (int i = nslots * 32 + lane; i < NP; i += 32) {
+        w.P[i] = 0.0;
+        w.P[NP + i] = 0.0;
+        w.P[2 * NP + i] = 0.0;
     }
     __syncwarp();
-    return (__float_as_uint(fin) & 0x7f800000u) == 0x7f800000u ? kFlagP : 0u;
 }
 
 // one hypothesis of opt_guess_translational_motion: plane normal through two random rows
@@ -284,14 +231,20 @@ __device__ __forceinline__ void draw_hypothesis(const DeviceData& dd, const Fram
 // k-th smallest hi word (0-based) among the warp's keys, by quickselect over a per-lane bitmask
 // of still-active slots.  Returns H and, through cl / ce, count(h < H) and count(h == H).
 template <int SLOTS>
-__device__ __forceinline__ unsigned warp_select_hi(const unsigned (&h)[SLOTS], const unsigned* skey,
-                                                   int kth, unsigned bound_hi, int lane, int& cl,
-                                                   int& ce) {
+__device__ __forceinline__ unsigned pick_slot(const unsigned (&h)[SLOTS], int sb) {  // h[sb], sb dynamic
+    unsigned v = h[0];
+#pragma unroll
+    for (int s = 1; s < SLOTS; ++s) v = (sb == s) ? h[s] : v;
+    return v;
+}
+template <int SLOTS>
+__device__ __forceinline__ unsigned warp_select_hi(const unsigned (&h)[SLOTS], int kth, unsigned bound_hi,
+                                                   int lane, int& cl, int& ce) {
     // Quickselect on VALUE bounds: the answer lies in [L, U).  Keys are < 2^31, so the sign bit of a
     // difference is the `<` predicate: two subtract + shift-add pairs per key count (h < pivot) and
     // (h <= pivot) over ALL keys, no per-lane bookkeeping.  The pivot is any key inside [L, U),
-    // found by probing one 32-key batch of the shared copy at a time (a different batch first in
-    // each round).
+    // found by probing one 32-key batch (one slot of every lane) at a time, a different batch
+    // first in each round.
     unsigned L = 0u, U = bound_hi + 1u;
     int round = 0;
     for (;;) {
@@ -299,7 +252,7 @@ __device__ __forceinline__ unsigned warp_select_hi(const unsigned (&h)[SLOTS], c
         for (int j = 0;; ++j) {
             int sb = round + j;
             sb -= (sb / SLOTS) * SLOTS;
-            const unsigned cand = skey[sb * 32 + lane];
+            const unsigned cand = pick_slot<SLOTS>(h, sb);
             const unsigned bal = __ballot_sync(FULL, (cand - L) < (U - L));
             if (bal) {
                 const int rot = (round * 7 + 3) & 31;
@@ -344,7 +297,6 @@ __device__ __noinline__ Vec3 warp_ransac_exact(const DeviceData& dd, const Frame
     double M[3];
     constexpr int NP = SLOTS * 32;
     const int n = fd.n;
-    unsigned* skey = reinterpret_cast<unsigned*>(w.nf);
     const unsigned long long nanbits = 0x7ff8000000000000ULL;
     __syncwarp();
     double np[SLOTS][3];
@@ -393,11 +345,8 @@ __device__ __noinline__ Vec3 warp_ransac_exact(const DeviceData& dd, const Frame
                 nbelow += (int)__reduce_add_sync(FULL, extra);
             }
             if (nbelow > kth) {  // med < least_med: select the exact quartile
-#pragma unroll
-                for (int s = 0; s < SLOTS; ++s) skey[s * 32 + lane] = h[s];
-                __syncwarp();
                 int cl, ce;
-                const unsigned H = warp_select_hi<SLOTS>(h, skey, kth, least_hi, lane, cl, ce);
+                const unsigned H = warp_select_hi<SLOTS>(h, kth, least_hi, lane, cl, ce);
                 // rank (kth - cl) among the ce keys whose hi word is H, ordered by lo word
                 int rem = kth - cl;
                 unsigned cur = 0u, lo_ans = 0u;
@@ -420,7 +369,6 @@ __device__ __noinline__ Vec3 warp_ransac_exact(const DeviceData& dd, const Frame
                 least_hi = H;
                 least_lo = lo_ans;
                 M[0] = vx; M[1] = vy; M[2] = vz;
-                __syncwarp();
             }
         }
     }
@@ -434,7 +382,6 @@ template <int SLOTS>
 __device__ __noinline__ unsigned long long warp_exact_quartile(const WarpSmem& w, int n, int lane,
                                                                double vx, double vy, double vz) {
     constexpr int NP = SLOTS * 32;
-    unsigned* skey = reinterpret_cast<unsigned*>(w.nf);
     const unsigned long long nanbits = 0x7ff8000000000000ULL;
     double r2[SLOTS];
     unsigned h[SLOTS];
@@ -447,12 +394,10 @@ __device__ __noinline__ unsigned long long warp_exact_quartile(const WarpSmem& w
         const double r = dot3(p0 * inv, p1 * inv, p2 * inv, vx, vy, vz);  // :35-36, :48
         r2[s] = r * r;                                                    // :49
         h[s] = (unsigned)__double2hiint(r2[s]) & 0x7fffffffu;
-        skey[i] = h[s];
     }
-    __syncwarp();
     const int kth = n / 4;  // :52
     int cl, ce;
-    const unsigned H = warp_select_hi<SLOTS>(h, skey, kth, 0x7ff80000u, lane, cl, ce);
+    const unsigned H = warp_select_hi<SLOTS>(h, kth, 0x7ff80000u, lane, cl, ce);
     int rem = kth - cl;  // rank among the ce keys whose hi word is H, ordered by lo word
     unsigned cur = 0u, lo_ans = 0u;
     for (;;) {
@@ -471,7 +416,6 @@ __device__ __noinline__ unsigned long long warp_exact_quartile(const WarpSmem& w
         rem -= (int)c;
         cur = mn + 1u;
     }
-    __syncwarp();
     return ((unsigned long long)H << 32) | lo_ans;
 }
 
@@ -598,20 +542,60 @@ __device__ __forceinline__ unsigned warp_select32(const float2 (&s)[NPAIR], int 
     }
 }
 
-// returns false when the winner could not be certified (the caller then runs the exact estimator)
+// The tournament's inputs: the frame's rows, row-normalised, in fp32, in registers -- lane l holds its
+// slots (2p, 2p+1) as one float2 per component.  Any accuracy the margin covers will do, so the norm
+// is taken with rsqrt.approx (rel. error <= 2^-22.4).  Rows that safe_normalize would leave unscaled
+// (|row| < 1e-12, also out of fp32 range) and non-finite rows poison `fin`: returns false, and the
+// task goes to the exact estimator.  Rows past the frame's last ray (zero rows) become +0 keys.
 template <int SLOTS>
-__device__ __forceinline__ bool warp_ransac_fast(const DeviceData& dd, const FrameDesc& fd,
-                                                 const WarpSmem& w, int iters, uint64_t key,
-                                                 int lane, double M[3], int* settled) {
-    constexpr int NP = SLOTS * 32, NPAIR = pairs_for(NP), NK = 2 * NPAIR;
-    const float2* nf2 = reinterpret_cast<const float2*>(w.nf);
-    float2 nx[NPAIR], ny[NPAIR], nz[NPAIR];
+__device__ __forceinline__ bool load_normalised_rows32(const double* __restrict__ sP, int n, int lane,
+                                                       float2 (&nx)[pairs_for(SLOTS * 32)],
+                                                       float2 (&ny)[pairs_for(SLOTS * 32)],
+                                                       float2 (&nz)[pairs_for(SLOTS * 32)]) {
+    constexpr int NP = SLOTS * 32, NPAIR = pairs_for(NP);
+    float fin = 0.f;  // stays finite iff every row is (rows and 1/|row| feed it)
 #pragma unroll
     for (int p = 0; p < NPAIR; ++p) {
-        nx[p] = nf2[p * 32 + lane];
-        ny[p] = nf2[(NPAIR + p) * 32 + lane];
-        nz[p] = nf2[(2 * NPAIR + p) * 32 + lane];
+        float f[2][3];
+#pragma unroll
+        for (int hh = 0; hh < 2; ++hh) {
+            const int s = 2 * p + hh;
+            if (s < SLOTS) {
+                const int i = s * 32 + lane;
+                const double r0 = sP[i], r1 = sP[NP + i], r2 = sP[2 * NP + i];
+                const float n2 = (float)dot3(r0, r1, r2, r0, r1, r2);
+                float rs;
+                asm("rsqrt.approx.f32 %0, %1;" : "=f"(rs) : "f"(n2));
+                if (i >= n) rs = 0.f;
+                else if (n2 < 1e-24f) rs = __uint_as_float(0x7fc00000u);
+                f[hh][0] = (float)r0 * rs;
+                f[hh][1] = (float)r1 * rs;
+                f[hh][2] = (float)r2 * rs;
+                fin += (fabsf(f[hh][0]) + fabsf(f[hh][1])) + fabsf(f[hh][2]);  // non-finite row -> NaN
+            } else {
+                f[hh][0] = f[hh][1] = f[hh][2] = 0.f;
+            }
+        }
+        nx[p] = make_float2(f[0][0], f[1][0]);
+        ny[p] = make_float2(f[0][1], f[1][1]);
+        nz[p] = make_float2(f[0][2], f[1][2]);
     }
+    return __all_sync(FULL, (__float_as_uint(fin) & 0x7f800000u) != 0x7f800000u);
+}
+
+#ifndef RS_COUNT_FMA
+#define RS_COUNT_FMA 1
+#endif
+// Result of the fast path: the winner is certified / it is not (run the exact estimator) / the rows
+// themselves are not finite (exact estimator, and pre_sync's "non-finite numbers in P" condition).
+enum FastStatus { kFastOk = 0, kFastUndecided = 1, kFastRowsNotFinite = 2 };
+template <int SLOTS>
+__device__ __forceinline__ FastStatus warp_ransac_fast(const DeviceData& dd, const FrameDesc& fd,
+                                                       const WarpSmem& w, int iters, uint64_t key,
+                                                       int lane, double M[3], int* settled) {
+    constexpr int NP = SLOTS * 32, NPAIR = pairs_for(NP), NK = 2 * NPAIR;
+    float2 nx[NPAIR], ny[NPAIR], nz[NPAIR];
+    if (!load_normalised_rows32<SLOTS>(w.P, fd.n, lane, nx, ny, nz)) return kFastRowsNotFinite;
     const int n = fd.n;
     const int npad = NK * 32 - n;  // padding keys are +0: always counted, always below
     const int kk = n / 4 + npad;   // :52
@@ -641,6 +625,37 @@ __device__ __forceinline__ bool warp_ransac_fast(const DeviceData& dd, const Fra
                 if (!first) {
                     const float2 nt2 = make_float2(nthr, nthr);
                     unsigned c = 0;
+#if RS_COUNT_FMA
+                    // rejection test on the EXACT squares: e = fma(rho, rho, -thr1) is the correctly
+                    // rounded rho^2 - thr1, whose sign is that of the exact difference, so the count
+                    // is count(rho^2 < thr1) -- one packed instruction instead of a product and a
+                    // sum.  |rho| is at least as close to |r64| as sqrt(fl(rho^2)) is, so the
+                    // rejection argument above holds for these keys as it does for the rounded ones.
+#pragma unroll
+                    for (int p = 0; p < NPAIR; ++p) {
+                        float2 r = __fmul2_rn(nx[p], vx2);
+                        r = __ffma2_rn(ny[p], vy2, r);
+                        r = __ffma2_rn(nz[p], vz2, r);
+                        sq[p] = r;
+                        const float2 e = __ffma2_rn(r, r, nt2);
+                        c += __float_as_uint(e.x) >> 31;
+                        c += __float_as_uint(e.y) >> 31;
+                    }
+                    if ((int)__reduce_add_sync(FULL, c) <= kk) continue;  // rigorously worse than the best so far
+                    // a challenger: from here on its keys are the rounded squares (the select works on
+                    // their bit patterns); recount on those, which may differ from the count above
+                    // where rho^2 rounds up to thr1 -- and is then just as rigorous a rejection
+                    c = 0;
+#pragma unroll
+                    for (int p = 0; p < NPAIR; ++p) {
+                        sq[p] = __fmul2_rn(sq[p], sq[p]);
+                        const float2 e = __fadd2_rn(sq[p], nt2);
+                        c += __float_as_uint(e.x) >> 31;
+                        c += __float_as_uint(e.y) >> 31;
+                    }
+                    chi = (int)__reduce_add_sync(FULL, c);
+                    if (chi <= kk) continue;
+#else
 #pragma unroll
                     for (int p = 0; p < NPAIR; ++p) {
                         float2 r = __fmul2_rn(nx[p], vx2);
@@ -653,6 +668,7 @@ __device__ __forceinline__ bool warp_ransac_fast(const DeviceData& dd, const Fra
                     }
                     chi = (int)__reduce_add_sync(FULL, c);
                     if (chi <= kk) continue;  // rigorously worse than the best so far
+#endif
                     hi_excl = thr1;
                 } else {
                     unsigned mx = 0u;
@@ -665,7 +681,7 @@ __device__ __forceinline__ bool warp_ransac_fast(const DeviceData& dd, const Fra
                         mx = max(mx, max(__float_as_uint(sq[p].x), __float_as_uint(sq[p].y)));
                     }
                     mx = __reduce_max_sync(FULL, mx);
-                    if (mx >= 0x7f800000u) return false;
+                    if (mx >= 0x7f800000u) return kFastUndecided;
                     hi_excl = mx + 1u;
                     chi = NK * 32;
                 }
@@ -691,7 +707,7 @@ __device__ __forceinline__ bool warp_ransac_fast(const DeviceData& dd, const Fra
                          tz = __shfl_sync(FULL, v[2], t_amb);
             const unsigned long long qt = warp_exact_quartile<SLOTS>(w, n, lane, tx, ty, tz);
             const unsigned long long qb = warp_exact_quartile<SLOTS>(w, n, lane, M[0], M[1], M[2]);
-            if (qt >= 0x7ff0000000000000ULL || qb >= 0x7ff0000000000000ULL) return false;
+            if (qt >= 0x7ff0000000000000ULL || qb >= 0x7ff0000000000000ULL) return kFastUndecided;
             if (settled) ++*settled;
             if (qt < qb) {
                 tau = q_amb;
@@ -702,21 +718,22 @@ __device__ __forceinline__ bool warp_ransac_fast(const DeviceData& dd, const Fra
             t = t_amb + 1;
         }
     }
-    return true;
+    return kFastOk;
 }
 
-// Phases B + C of an estimator task
+// Phases B + C of an estimator task.  Returns kFlagP when the rows are not all finite.
 template <int SLOTS>
-__device__ __forceinline__ void warp_ransac(const DeviceData& dd, const FrameDesc& fd,
-                                            const WarpSmem& w, int iters, uint64_t key, int lane,
-                                            bool rows_finite, double M[3], unsigned* n_exact) {
+__device__ __forceinline__ unsigned warp_ransac(const DeviceData& dd, const FrameDesc& fd,
+                                                const WarpSmem& w, int iters, uint64_t key, int lane,
+                                                double M[3], unsigned* n_exact) {
     int settled = 0;
-    const bool ok = rows_finite && warp_ransac_fast<SLOTS>(dd, fd, w, iters, key, lane, M, &settled);
+    const FastStatus st = warp_ransac_fast<SLOTS>(dd, fd, w, iters, key, lane, M, &settled);
     if (n_exact && settled && lane == 0) atomicAdd(n_exact, 1u);  // tasks that needed binary64
-    if (ok) return;
+    if (st == kFastOk) return 0u;
     if (n_exact && !settled && lane == 0) atomicAdd(n_exact, 1u);
     const Vec3 e = warp_ransac_exact<SLOTS>(dd, fd, w, iters, key, lane);
     M[0] = e.x; M[1] = e.y; M[2] = e.z;
+    return st == kFastRowsNotFinite ? kFlagP : 0u;
 }
 
 // ------------------------------------------------------------------------------------------
@@ -975,12 +992,13 @@ __device__ __forceinline__ double warp_norm_PM(const double* sP, int NP, int nsl
 }
 
 // which of pre_sync's panic conditions (core_private.cpp:76-83) a task with a non-finite cost hit
-__device__ __noinline__ unsigned presync_diagnose(const double* pm, int nslots, int lane, double scale,
+__device__ __noinline__ unsigned presync_diagnose(const double* sP, int NP, int nslots, int lane, double scale,
                                                   double m0, double m1, double m2, const double* tab) {
     unsigned bad = 0;
     if (!(is_finite(m0) && is_finite(m1) && is_finite(m2))) bad |= kFlagM;
     for (int s = 0; s < nslots; ++s) {
-        const double r = pm[s * 32 + lane] * scale;
+        const int i = s * 32 + lane;
+        const double r = dot3(sP[i], sP[NP + i], sP[2 * NP + i], m0, m1, m2) * scale;
         if (!is_finite(r)) bad |= kFlagR;
         if (!is_finite(log1p_nonneg(r * r, tab))) bad |= kFlagRho;
     }
@@ -990,54 +1008,74 @@ __device__ __noinline__ unsigned presync_diagnose(const double* pm, int nslots, 
 // ------------------------------------------------------------------------------------------
 // K1: PreSync / DebugPreSync grid.
 //
-// Work unit = (frame, chunk of up to 2 W consecutive delays), W = warps per block; warp j of the block
-// takes delays j and j + W of the chunk, one after the other.  A block walks a contiguous range of units, so consecutive units
-// share the frame.  What phase A reads is staged in shared memory by TMA bulk copies issued by one
-// thread: the frame's ray tiles (contiguous in the arena; reloaded only when the frame changes)
-// and the window of spline records the chunk can touch (from the frame's timestamp bounds and the
-// chunk's delay range).  The buffers are only live during phase A: the last warp to finish phase A
-// of unit u issues the copies for unit u + 1, which then overlap phases B-D of unit u.  (With
-// ~200 KB of the SM's 228 KB carved out as shared memory the L1 keeps ~13 KB: un-staged, the same
-// loads hit L1 28 % of the time and wait on L2, profiles/r01_presync_v3c.md.)
+// Work unit = (frame, chunk of consecutive delays); a block walks a contiguous range of units, so
+// consecutive units mostly share the frame.  What phase A reads is staged in shared memory by TMA bulk
+// copies issued by one thread: the frame's ray tiles (contiguous in the arena) and the window of
+// spline records the chunk can touch (from the frame's timestamp bounds and the chunk's delay
+// range).  (With ~220 KB of the SM's 228 KB carved out as shared memory the L1 keeps a few KB:
+// un-staged, the same loads hit L1 28 % of the time and wait on L2, profiles/r01_presync_v3c.md.)
+//
+// The staging area is a ring of two buffers and the block's warps take tasks from one shared
+// counter, so nobody waits for anybody in the steady state:
+//   * task k of the block is delay k % chunk of unit k / chunk; a warp that finishes a task takes
+//     the next one (atomicAdd on next_task), whatever its neighbours are doing -- the lengths of the
+//     estimator's tournaments differ from task to task, and with a static assignment (r01: warp j
+//     takes delays j and j + W of a 16-delay unit, all warps meet at the unit's end) the block waited
+//     for its slowest warp once per unit: 6 % of the warp samples on the staging mbarrier, 9 % of the
+//     executed instructions in its polling loop (profiles/r01_presync_v6.md);
+//   * unit u lives in buffer u & 1.  A buffer is live only during phase A of its unit's tasks: the
+//     warp that completes the unit's last phase A (done_a counts them, whoever runs them) issues the
+//     copies for unit u + 2 into it (`fence.proxy.async` first).  By then the data of unit u + 1 has
+//     long landed -- it was requested a whole unit earlier -- so in the steady state a warp only
+//     waits on the mbarrier during the block's first unit.  A warp entering unit u first waits until
+//     the buffer has been handed to that unit (ctl->unit[b] == u: with short units a warp can be a
+//     whole ring ahead of the buffer), then for the mbarrier phase of parity (u >> 1) & 1, which is
+//     then unambiguous: the buffer is not handed on before all phase A's of unit u, that warp's
+//     included.
+// Grids with fewer delays per unit than the block has warps (a handful of delays over many frames)
+// would serialise on the two buffers: they run unstaged (`staged` = 0), every task reading global
+// memory through the general path, with no hand-off at all.
+// A window that does not fit the buffer (delay steps of many samples, timestamps outside the gyro
+// span) makes the unit read global memory through the out-of-line general path -- same arithmetic.
 #ifndef RS_POLL_NS
-#define RS_POLL_NS 64  // back-off between polls of the staging mbarrier
+#define RS_POLL_NS 64  // back-off between polls of a staging mbarrier
 #endif
-#ifndef RS_REC_MAX
-#define RS_REC_MAX 64
+#ifndef RS_GRID_WARPS
+#define RS_GRID_WARPS 8
 #endif
-constexpr int kRecMax = RS_REC_MAX;  // spline records per window (8 KB)
+#ifndef RS_GRID_MINB
+#define RS_GRID_MINB 2
+#endif
+#ifndef RS_GRID_RECS
+#define RS_GRID_RECS 144  // spline records per staged window (18 KB)
+#endif
 template <int SLOTS>
-struct PresyncCfg {
-#ifndef RS_PRESYNC_WARPS
-#define RS_PRESYNC_WARPS 8
-#endif
-#ifndef RS_PRESYNC_MINB
-#define RS_PRESYNC_MINB 2
-#endif
-#ifndef RS_PRESYNC_TASKS_PER_WARP
-#define RS_PRESYNC_TASKS_PER_WARP 2
-#endif
-    static constexpr int kWarps = SLOTS <= 8 ? RS_PRESYNC_WARPS : 8;
-    static constexpr int kTasksPerWarp = RS_PRESYNC_TASKS_PER_WARP;  // delays per warp and unit
-    static constexpr int kMinBlocks = SLOTS <= 8 ? RS_PRESYNC_MINB : 1;
+struct GridCfg {
+    static constexpr int kWarps = RS_GRID_WARPS;
+    static constexpr int kMinBlocks = SLOTS <= 8 ? RS_GRID_MINB : 1;
+    static constexpr int kRecs = SLOTS <= 8 ? RS_GRID_RECS : 128;
     static constexpr size_t kTileBytes = (size_t)SLOTS * 2048;
+    static constexpr size_t kBufBytes = kTileBytes + (size_t)kRecs * 128;
     static constexpr size_t kCtlOff = kLog1pTableBytes;
-    static constexpr size_t kTileOff = kCtlOff + 128;
-    static constexpr size_t kRecOff = kTileOff + kTileBytes;
-    static constexpr size_t kWarpOff = kRecOff + (size_t)kRecMax * 128;
-    static constexpr size_t kSmem = kWarpOff + (size_t)kWarps * warp_smem_bytes(SLOTS * 32, true);
+    static constexpr size_t kBufOff = kCtlOff + 256;
+    static constexpr size_t kWarpOff = kBufOff + 2 * kBufBytes;
+    static constexpr size_t kSmem = kWarpOff + (size_t)kWarps * warp_smem_bytes(SLOTS * 32);
 };
-struct StageCtl {
-    unsigned long long full;  // mbarrier: the staged data of the next unit has landed
-    unsigned arrived;         // warps that finished phase A of the current unit
-    int rec_first, rec_cnt;   // staged spline window; rec_cnt = 0: not staged, phase A reads global
-    int frame_loaded;         // index (into `frames`) of the frame whose tiles are staged, -1: none
+struct GridCtl {
+    unsigned long long full[2];  // mbarriers: the staged data of the unit in buffer b has landed
+    int done_a[2];               // phase A's completed in the unit occupying buffer b
+    int next_task;               // the block's task counter
+    int rec_first[2], rec_cnt[2];  // staged spline window; rec_cnt = 0: not staged, phase A reads global
+    int frame[2], d0[2];         // the unit's frame (index into `frames`) and first delay
+    int unit[2];                 // which unit of the block buffer b belongs to (-1: none yet)
+    FrameDesc fd[2];
 };
+static_assert(sizeof(GridCtl) <= 256, "GridCtl must fit its slot");
 
-template <int SLOTS>
-__device__ __noinline__ void presync_stage_unit(const DeviceData& dd, const FrameDesc* frames,
-                                                   const double* delays, int D, int chunk, int cpf,
-                                                   int fi, int ci, StageCtl* ctl, double* sTiles, double* sRec) {
+// issue the copies of unit (fi, ci) into buffer b; one thread
+__device__ __noinline__ void grid_stage_unit(const DeviceData& dd, const FrameDesc* frames,
+                                             const double* delays, int D, int chunk, int fi, int ci, int u,
+                                             GridCtl* ctl, int b, double* sTiles, double* sRec, int rec_cap) {
     const int d0 = ci * chunk;
     const int d1 = min(D, d0 + chunk);
     const FrameDesc fd = frames[fi];
@@ -1049,88 +1087,108 @@ __device__ __noinline__ void presync_stage_unit(const DeviceData& dd, const Fram
     // x = ((ts - q0) + delay) * sr is monotone in ts and in delay, roundings included
     const double x_lo = ((fd.ts_lo - dd.q0) + dmin) * dd.sr, x_hi = ((fd.ts_hi - dd.q0) + dmax) * dd.sr;
     const double r_lo = floor(x_lo) - 1.0, r_hi = floor(x_hi) + 2.0;  // a record of slack either side
-    const bool ok = r_lo >= 0.0 && r_hi <= (double)(dd.nq - 1) && (r_hi - r_lo) < (double)kRecMax;
-    // the buffers were read through the generic proxy; order those reads before the async writes
-    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-    unsigned bytes = 0;
+    const bool ok = r_lo >= 0.0 && r_hi <= (double)(dd.nq - 1) && (r_hi - r_lo) < (double)rec_cap;
     const int first = ok ? (int)r_lo : 0, cnt = ok ? (int)(r_hi - r_lo) + 1 : 0;
-    const bool tiles = ok && ctl->frame_loaded != fi;
-    ctl->rec_first = first;
-    ctl->rec_cnt = cnt;
+    ctl->rec_first[b] = first;
+    ctl->rec_cnt[b] = cnt;
+    ctl->frame[b] = fi;
+    ctl->d0[b] = d0;
+    ctl->fd[b] = fd;
+    __threadfence_block();
+    *(volatile int*)&ctl->unit[b] = u;  // after the unit's parameters: a waiter reads them once it sees u
+    // the buffer was read through the generic proxy; order those reads before the async writes
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     const unsigned tile_bytes = (unsigned)((fd.n + 31) >> 5) * 2048u;
-    if (ok) bytes += (unsigned)cnt * 128u;
-    if (tiles) {
-        bytes += tile_bytes;
-        ctl->frame_loaded = fi;
+    const unsigned bytes = ok ? (unsigned)cnt * 128u + tile_bytes : 0u;
+    mbar_arrive_expect_tx(&ctl->full[b], bytes);
+    if (ok) {
+        tma_load_1d(sRec, dd.rec + (size_t)first * 16, (unsigned)cnt * 128u, &ctl->full[b]);
+        tma_load_1d(sTiles, dd.rays + (size_t)fd.off * 8, tile_bytes, &ctl->full[b]);
     }
-    mbar_arrive_expect_tx(&ctl->full, bytes);
-    if (ok) tma_load_1d(sRec, dd.rec + (size_t)first * 16, (unsigned)cnt * 128u, &ctl->full);
-    if (tiles) tma_load_1d(sTiles, dd.rays + (size_t)fd.off * 8, tile_bytes, &ctl->full);
 }
 
 template <int SLOTS>
-__global__ void __launch_bounds__(PresyncCfg<SLOTS>::kWarps * 32, PresyncCfg<SLOTS>::kMinBlocks)
+__global__ void __launch_bounds__(GridCfg<SLOTS>::kWarps * 32, GridCfg<SLOTS>::kMinBlocks)
 presync_kernel(DeviceData dd, const FrameDesc* __restrict__ frames, int F,
                const double* __restrict__ delays, int D, int chunk, int cpf, uint64_t seed,
                uint64_t stream, uint64_t call_no, const uint64_t* __restrict__ frame_call_no,
                uint64_t idx_base, double* __restrict__ framecost, int cost_stride,
-               unsigned* __restrict__ flags) {
-    using Cfg = PresyncCfg<SLOTS>;
+               unsigned* __restrict__ flags, int staged) {
+    using Cfg = GridCfg<SLOTS>;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     constexpr int NP = SLOTS * 32;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     double* tab = reinterpret_cast<double*>(smem_raw);
-    StageCtl* ctl = reinterpret_cast<StageCtl*>(smem_raw + Cfg::kCtlOff);
-    double* sTiles = reinterpret_cast<double*>(smem_raw + Cfg::kTileOff);
-    double* sRec = reinterpret_cast<double*>(smem_raw + Cfg::kRecOff);
-    const WarpSmem w = warp_smem(smem_raw + Cfg::kWarpOff, warp, NP, true);
+    GridCtl* ctl = reinterpret_cast<GridCtl*>(smem_raw + Cfg::kCtlOff);
+    unsigned char* bufs = smem_raw + Cfg::kBufOff;
+    const WarpSmem w = warp_smem(smem_raw + Cfg::kWarpOff, warp, NP);
+    // units are counted in 64 bits (the host accepts grids up to 2^40 tasks); a block's share fits an int
     const long long U = (long long)F * cpf;
-    // units are counted in 64 bits: the host accepts grids up to 2^40 tasks (F * ceil(D / chunk) can
-    // pass 2^31)
     const long long u_begin = U * blockIdx.x / gridDim.x;
-    const int n_units = (int)(U * (blockIdx.x + 1) / gridDim.x - u_begin);  // per block: fits an int
+    const int n_units = (int)(U * (blockIdx.x + 1) / gridDim.x - u_begin);
+    const int fi0 = (int)(u_begin / cpf), c0 = (int)(u_begin % cpf);
+    auto stage = [&](int u) {
+        const int cu = c0 + u, b = u & 1;
+        double* sTiles = reinterpret_cast<double*>(bufs + (size_t)b * Cfg::kBufBytes);
+        grid_stage_unit(dd, frames, delays, D, chunk, fi0 + cu / cpf, cu % cpf, u, ctl, b, sTiles,
+                        sTiles + SLOTS * 256, Cfg::kRecs);
+    };
     if (threadIdx.x == 0) {
-        mbar_init(&ctl->full, 1);
-        ctl->arrived = 0;
-        ctl->frame_loaded = -1;
+        mbar_init(&ctl->full[0], 1);
+        mbar_init(&ctl->full[1], 1);
+        ctl->done_a[0] = ctl->done_a[1] = 0;
+        ctl->unit[0] = ctl->unit[1] = -1;
+        ctl->next_task = 0;
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     load_log1p_table(tab);  // ends with __syncthreads()
-    // (frame, chunk) of the current unit, advanced incrementally (one 64-bit division per block)
-    int fi = (int)(u_begin / cpf), ci = (int)(u_begin % cpf);
-    if (threadIdx.x == 0 && n_units > 0)
-        presync_stage_unit<SLOTS>(dd, frames, delays, D, chunk, cpf, fi, ci, ctl, sTiles, sRec);
-    unsigned parity = 0;
-    // a unit holds up to kTasksPerWarp delays per warp: warp j takes delays j, j + W, ... of the
-    // chunk one after the other, so the warps of a block meet (and poll) once per several tasks and
-    // the differences between their tasks' tournament lengths average out
-    const int reps = (chunk + Cfg::kWarps - 1) / Cfg::kWarps;
-    for (int u = 0; u < n_units; ++u, fi += (ci + 1 == cpf), ci = (ci + 1 == cpf) ? 0 : ci + 1) {
-        const int d0 = ci * chunk;
-        const FrameDesc fd = frames[fi];
-        const int nslots = (fd.n + 31) >> 5;
-        while (!mbar_try_wait(&ctl->full, parity)) __nanosleep(RS_POLL_NS);
-        parity ^= 1u;
-        const int rec_first = *(volatile int*)&ctl->rec_first, rec_cnt = *(volatile int*)&ctl->rec_cnt;
-      for (int rep = 0; rep < reps; ++rep) {
-        const int dj = rep * Cfg::kWarps + warp, di = d0 + dj;
-        const bool active = dj < chunk && di < D;
-        unsigned bad = 0;
+    if (threadIdx.x == 0 && staged) {
+        if (n_units > 0) stage(0);
+        if (n_units > 1) stage(1);
+    }
+    const int n_tasks = n_units * chunk;  // the host keeps a grid below 2^34 tasks
+    int cur_u = -1, rec_first = 0, rec_cnt = 0, fi = 0, d0 = 0;
+    FrameDesc fd{};
+    for (;;) {
+        int k = 0;
+        if (lane == 0) k = atomicAdd(&ctl->next_task, 1);
+        k = __shfl_sync(FULL, k, 0);
+        if (k >= n_tasks) break;
+        const int u = k / chunk, dj = k - u * chunk;
+        const int b = u & 1;
+        if (u != cur_u && !staged) {
+            cur_u = u;
+            const int cu = c0 + u;
+            fi = fi0 + cu / cpf;
+            d0 = (cu % cpf) * chunk;
+            fd = frames[fi];
+        } else if (u != cur_u) {  // first task this warp takes in unit u
+            cur_u = u;
+            while (*(volatile int*)&ctl->unit[b] != u) __nanosleep(RS_POLL_NS);
+            const unsigned parity = (unsigned)(u >> 1) & 1u;
+            while (!mbar_try_wait(&ctl->full[b], parity)) __nanosleep(RS_POLL_NS);
+            rec_first = *(volatile int*)&ctl->rec_first[b];
+            rec_cnt = *(volatile int*)&ctl->rec_cnt[b];
+            fi = *(volatile int*)&ctl->frame[b];
+            d0 = *(volatile int*)&ctl->d0[b];
+            const volatile FrameDesc* vf = &ctl->fd[b];
+            fd.id = vf->id; fd.off = vf->off; fd.n = vf->n; fd.ts_lo = vf->ts_lo; fd.ts_hi = vf->ts_hi;
+        }
+        const int di = d0 + dj;
+        const bool active = di < D;
         double delay = 0.0;
         if (active) {
             delay = delays[di];
-            bad = rec_cnt ? build_rows_staged(dd, fd, delay, lane, w, NP, sTiles, sRec, rec_first, rec_cnt)
-                          : build_rows_global_cold(dd, fd, delay, lane, w, NP);
-            bad = __reduce_or_sync(FULL, bad);
+            const double* sTiles = reinterpret_cast<const double*>(bufs + (size_t)b * Cfg::kBufBytes);
+            if (rec_cnt) build_rows_staged(dd, fd, delay, lane, w, NP, sTiles, sTiles + SLOTS * 256, rec_first, rec_cnt);
+            else build_rows_global_cold(dd, fd, delay, lane, w, NP);
         }
         __syncwarp();
-        if (rep == reps - 1 && lane == 0) {  // the warp's last phase A of this unit: it no longer
-            __threadfence_block();           // needs the staging buffers
-            if (atomicAdd(&ctl->arrived, 1u) == (unsigned)(Cfg::kWarps - 1)) {
-                ctl->arrived = 0;
-                if (u + 1 < n_units)
-                    presync_stage_unit<SLOTS>(dd, frames, delays, D, chunk, cpf, fi + (ci + 1 == cpf),
-                                              (ci + 1 == cpf) ? 0 : ci + 1, ctl, sTiles, sRec);
+        if (lane == 0 && staged) {  // this phase A no longer needs the staging buffer
+            __threadfence_block();
+            if (atomicAdd(&ctl->done_a[b], 1) == chunk - 1) {  // the unit's last: refill the buffer
+                ctl->done_a[b] = 0;
+                if (u + 2 < n_units) stage(u + 2);
             }
         }
         if (!active) continue;
@@ -1139,7 +1197,7 @@ presync_kernel(DeviceData dd, const FrameDesc* __restrict__ frames, int F,
                                     idx_base + (uint64_t)di),
                          fd.id);
         double M[3];
-        warp_ransac<SLOTS>(dd, fd, w, 20, key, lane, bad == 0u, M, flags + 1);  // core_private.cpp:77
+        unsigned bad = warp_ransac<SLOTS>(dd, fd, w, 20, key, lane, M, flags + 1);  // core_private.cpp:77
         // :79-85
         __syncwarp();
         // rows past the frame's last ray are zero: they add 0 to the norm and log1p(0) = 0 to the loss
@@ -1152,8 +1210,8 @@ presync_kernel(DeviceData dd, const FrameDesc* __restrict__ frames, int F,
         double ss = 0.0;
 #pragma unroll
         for (int s = 0; s < SLOTS; ++s) ss = ss + pmv[s] * pmv[s];
-        const double k = clamp_k(1.0 / sqrt(warp_sum(ss)) * 1e2);  // arma::norm(P * M), :79
-        const double scale = k / sqrt(dot3(M[0], M[1], M[2], M[0], M[1], M[2]));
+        const double kv = clamp_k(1.0 / sqrt(warp_sum(ss)) * 1e2);  // arma::norm(P * M), :79
+        const double scale = kv / sqrt(dot3(M[0], M[1], M[2], M[0], M[1], M[2]));
         double acc = 0.0;
         {
             double rho[SLOTS];
@@ -1170,15 +1228,10 @@ presync_kernel(DeviceData dd, const FrameDesc* __restrict__ frames, int F,
         // the panic conditions of :76-83: non-finite values propagate into the cost, so the stage
         // that produced them is only looked for when the cost (or a row) is not finite
         if (bad || !is_finite(cost)) {
-            double* pm = reinterpret_cast<double*>(w.nf);
-#pragma unroll
-            for (int s = 0; s < SLOTS; ++s) pm[s * 32 + lane] = pmv[s];
-            __syncwarp();
-            bad |= presync_diagnose(pm, nslots, lane, scale, M[0], M[1], M[2], tab);
+            bad |= presync_diagnose(w.P, NP, (fd.n + 31) >> 5, lane, scale, M[0], M[1], M[2], tab);
             bad = __reduce_or_sync(FULL, bad);
             if (bad && lane == 0) atomicOr(flags, bad);
         }
-      }
     }
 }
 
@@ -1220,18 +1273,18 @@ sync_init_kernel(DeviceData dd, SyncBatchDev b, const double* __restrict__ sp_de
     extern __shared__ __align__(16) unsigned char smem_raw[];
     constexpr int NP = SLOTS * 32;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const WarpSmem w = warp_smem(smem_raw, warp, NP, true);
+    const WarpSmem w = warp_smem(smem_raw, warp, NP);
     for (int t = blockIdx.x * kWarpsPerBlock + warp; t < b.T; t += gridDim.x * kWarpsPerBlock) {
         const SyncTask task = b.tasks[t];
         if (!sp_active[task.sp]) continue;
         const int nslots = (task.fd.n + 31) >> 5;
         __syncwarp();
-        const unsigned bad =
-            __reduce_or_sync(FULL, build_rows_smem<true>(dd, task.fd, sp_delay[task.sp], lane, w, NP));
+        build_rows_smem(dd, task.fd, sp_delay[task.sp], lane, w, NP);
         const uint64_t key =
             rng_task_key(rng_prefix(seed, kStreamSyncInit, sp_callno[task.sp], 0), task.fd.id);
         double M[3];
-        warp_ransac<SLOTS>(dd, task.fd, w, 200, key, lane, bad == 0u, M, nullptr);  // core_private.cpp:127
+        warp_ransac<SLOTS>(dd, task.fd, w, 200, key, lane, M, nullptr);  // core_private.cpp:127
+        __syncwarp();
         const double nrm = warp_norm_PM(w.P, NP, nslots, lane, M, nullptr);
         if (lane == 0) {
             b.m[3 * t + 0] = M[0]; b.m[3 * t + 1] = M[1]; b.m[3 * t + 2] = M[2];
@@ -1266,9 +1319,9 @@ sync_motion_fgrad_kernel(DeviceData dd, SyncBatchDev b, const double* __restrict
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     double* tab = reinterpret_cast<double*>(smem_raw);
     load_log1p_table(tab);
-    const WarpSmem w = warp_smem(smem_raw + kLog1pTableBytes, warp, NP, false);
+    const WarpSmem w = warp_smem(smem_raw + kLog1pTableBytes, warp, NP);
     constexpr int W = LbfgsCfg<SMALL>::kWarps;
-    double* hist = reinterpret_cast<double*>(smem_raw + kLog1pTableBytes + (size_t)W * warp_smem_bytes(NP, false)) +
+    double* hist = reinterpret_cast<double*>(smem_raw + kLog1pTableBytes + (size_t)W * warp_smem_bytes(NP)) +
                    warp * kLbfgsHistDoubles;
     for (int t = blockIdx.x * W + warp; t < b.T; t += gridDim.x * W) {
         const SyncTask task = b.tasks[t];
@@ -1282,7 +1335,7 @@ sync_motion_fgrad_kernel(DeviceData dd, SyncBatchDev b, const double* __restrict
                                  : (j == 2) ? x0 - kNumericDiffStep
                                             : x0 + kNumericDiffStep;
             __syncwarp();
-            build_rows_smem<false>(dd, task.fd, delay, lane, w, NP);
+            build_rows_smem(dd, task.fd, delay, lane, w, NP);
             double p[SLOTS][3];
             load_rows<SLOTS>(w.P, NP, lane, p);
             if (j == 0) {
@@ -1345,7 +1398,7 @@ sync_trials_kernel(DeviceData dd, SyncBatchDev b, int NP, const double* __restri
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     double* tab = reinterpret_cast<double*>(smem_raw);
     load_log1p_table(tab);
-    const WarpSmem w = warp_smem(smem_raw + kLog1pTableBytes, warp, NP, false);
+    const WarpSmem w = warp_smem(smem_raw + kLog1pTableBytes, warp, NP);
     const long long total = (long long)b.T * ntrial;
     for (long long q = (long long)blockIdx.x * kWarpsPerBlock + warp; q < total;
          q += (long long)gridDim.x * kWarpsPerBlock) {
@@ -1354,7 +1407,7 @@ sync_trials_kernel(DeviceData dd, SyncBatchDev b, int NP, const double* __restri
         if (!sp_active[task.sp]) continue;
         const int nslots = (task.fd.n + 31) >> 5;
         __syncwarp();
-        build_rows_smem<false>(dd, task.fd, trial_delay[(size_t)task.sp * ntrial + j], lane, w, NP);
+        build_rows_smem(dd, task.fd, trial_delay[(size_t)task.sp * ntrial + j], lane, w, NP);
         const double v = warp_loss3_smem(w.P, NP, nslots, lane, b.m[3 * t], b.m[3 * t + 1],
                                          b.m[3 * t + 2], b.k[t], tab);
         if (lane == 0) scratch[(size_t)t * ntrial + j] = v;
@@ -1542,8 +1595,8 @@ __global__ void spline_finish_kernel(const double* __restrict__ y, const double*
 __global__ void probe_problem_kernel(DeviceData dd, FrameDesc fd, int NP, double delay, double* out) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int lane = threadIdx.x & 31;
-    const WarpSmem w = warp_smem(smem_raw, 0, NP, false);
-    build_rows_smem<false>(dd, fd, delay, lane, w, NP);
+    const WarpSmem w = warp_smem(smem_raw, 0, NP);
+    build_rows_smem(dd, fd, delay, lane, w, NP);
     for (int i = lane; i < fd.n; i += 32) {  // back to the caller's ray order
         const int o = dd.orig[fd.off + i];
         out[3 * o] = w.P[i];
@@ -1563,9 +1616,9 @@ __global__ void probe_loss_kernel(DeviceData dd, FrameDesc fd, int NP, double de
     const int lane = threadIdx.x & 31;
     double* tab = reinterpret_cast<double*>(smem_raw);
     load_log1p_table(tab);
-    const WarpSmem w = warp_smem(smem_raw + kLog1pTableBytes, 0, NP, false);
+    const WarpSmem w = warp_smem(smem_raw + kLog1pTableBytes, 0, NP);
     const int nslots = (fd.n + 31) >> 5;
-    build_rows_smem<false>(dd, fd, delay, lane, w, NP);
+    build_rows_smem(dd, fd, delay, lane, w, NP);
     const double l3 = warp_loss3_smem(w.P, NP, nslots, lane, mp[0], mp[1], mp[2], k, tab);
     const Loss5 e = warp_loss5_smem(w.P, NP, nslots, lane, mp[0], mp[1], mp[2], k, tab);
     if (lane == 0) { out[0] = l3; out[1] = e.f; out[2] = e.g0; out[3] = e.g1; out[4] = e.g2; }
@@ -1576,9 +1629,9 @@ __global__ void probe_lbfgs_kernel(DeviceData dd, FrameDesc fd, int NP, double d
     const int lane = threadIdx.x & 31;
     double* tab = reinterpret_cast<double*>(smem_raw);
     load_log1p_table(tab);
-    const WarpSmem w = warp_smem(smem_raw + kLog1pTableBytes, 0, NP, false);
+    const WarpSmem w = warp_smem(smem_raw + kLog1pTableBytes, 0, NP);
     const int nslots = (fd.n + 31) >> 5;
-    build_rows_smem<false>(dd, fd, delay, lane, w, NP);
+    build_rows_smem(dd, fd, delay, lane, w, NP);
     double m[3] = {mp[0], mp[1], mp[2]};
     int it, ev;
     __shared__ double hist[kLbfgsHistDoubles];
@@ -1597,16 +1650,15 @@ __global__ void probe_guess_kernel(DeviceData dd, FrameDesc fd, double delay, in
     extern __shared__ __align__(16) unsigned char smem_raw[];
     constexpr int NP = SLOTS * 32;
     const int lane = threadIdx.x & 31;
-    const WarpSmem w = warp_smem(smem_raw, 0, NP, true);
+    const WarpSmem w = warp_smem(smem_raw, 0, NP);
     const int nslots = (fd.n + 31) >> 5;
-    const unsigned bad = __reduce_or_sync(FULL, build_rows_smem<true>(dd, fd, delay, lane, w, NP));
+    build_rows_smem(dd, fd, delay, lane, w, NP);
     double M[3];
     if (mode == 2) {
         const Vec3 e = warp_ransac_exact<SLOTS>(dd, fd, w, iters, rng_task_key(key_prefix, fd.id), lane);
         M[0] = e.x; M[1] = e.y; M[2] = e.z;
     } else
-        warp_ransac<SLOTS>(dd, fd, w, iters, rng_task_key(key_prefix, fd.id), lane, bad == 0u, M,
-                           n_exact);
+        warp_ransac<SLOTS>(dd, fd, w, iters, rng_task_key(key_prefix, fd.id), lane, M, n_exact);
     __syncwarp();
     const double nrm = warp_norm_PM(w.P, NP, nslots, lane, M, nullptr);
     if (lane == 0) { out[0] = M[0]; out[1] = M[1]; out[2] = M[2]; out[3] = clamp_k(1.0 / nrm * 1e2); }
@@ -1701,27 +1753,48 @@ void allow_smem(K kernel, size_t smem) {
 uint64_t launch_count() { return g_launches.load(); }
 void count_launches(uint64_t n) { g_launches += n; }
 
+int presync_max_chunk(const double* h_delays, int D, double frame_span_s, double sample_rate, int max_n) {
+    if (D <= 1) return 1;
+    int recs = 0;
+    RS_DISPATCH_SLOTS(max_n, { recs = GridCfg<SL>::kRecs; });
+    // a chunk of c consecutive delays spans at most (c - 1) * max |step| seconds; its window holds
+    // floor(x_hi) + 2 - (floor(x_lo) - 1) + 1 <= (span + range) * sr + 5 records (grid_stage_unit)
+    double step = 0.0;
+    for (int i = 1; i < D; ++i) step = std::max(step, std::fabs(h_delays[i] - h_delays[i - 1]));
+    const double room = ((double)recs - 5.0) / sample_rate - frame_span_s;  // seconds of delay range
+    if (!(room > 0.0) || !(step == step)) return 1;
+    if (step <= 0.0) return D;
+    const double c = std::floor(room / step) + 1.0;
+    return (int)std::max(1.0, std::min(c, (double)D));
+}
+
 void launch_presync_tasks(const DeviceData& dd, const FrameDesc* d_frames, int F, int max_n,
                           const double* d_delays, int D, uint64_t seed, uint64_t stream, uint64_t call_no,
                           uint64_t idx_base, double* d_framecost, int cost_stride, unsigned* d_flags,
-                          cudaStream_t st, const uint64_t* d_frame_call_no) {
+                          cudaStream_t st, const uint64_t* d_frame_call_no, int max_chunk) {
     if (F <= 0 || D <= 0) return;
     RS_DISPATCH_SLOTS(max_n, {
-        using Cfg = PresyncCfg<SL>;
+        using Cfg = GridCfg<SL>;
         auto kern = presync_kernel<SL>;
         allow_smem(kern, Cfg::kSmem);
-        // chunks of delays per frame, balanced: cpf = ceil(D / (W R)), chunk = ceil(D / cpf) <= W R
-        const int per_unit = Cfg::kWarps * Cfg::kTasksPerWarp;
-        const int cpf = (D + per_unit - 1) / per_unit;
-        const int chunk = (D + cpf - 1) / cpf;
         const int sm_count = sm_count_of(current_device());
         const int per_sm = blocks_per_sm(kern, Cfg::kWarps * 32, Cfg::kSmem);
-        const long long units = (long long)F * ((D + chunk - 1) / chunk);
-        const int grid = (int)std::max<long long>(1, std::min<long long>(units, (long long)sm_count * per_sm));
-        kern<<<grid, Cfg::kWarps * 32, Cfg::kSmem, st>>>(dd, d_frames, F, d_delays, D, chunk,
-                                                         (D + chunk - 1) / chunk, seed, stream, call_no,
-                                                         d_frame_call_no, idx_base, d_framecost, cost_stride,
-                                                         d_flags);
+        const long long blocks_cap = (long long)sm_count * per_sm;
+        // Delays per unit: as many as the staged window takes (max_chunk; 0 = unknown, be conservative),
+        // but no more than leaves every block several units (small grids: PreSync on a 60-frame window),
+        // and at least one task per warp when the grid has that many delays.
+        int chunk = std::min(D, max_chunk > 0 ? max_chunk : Cfg::kWarps * 2);
+        const long long cpf_par = (blocks_cap * 4 + F - 1) / F;  // units per frame for 4 units per block
+        const int chunk_par = (int)std::max<long long>(1, (D + cpf_par - 1) / cpf_par);
+        chunk = std::min(chunk, std::max(chunk_par, std::min(D, Cfg::kWarps)));
+        const int cpf = (D + chunk - 1) / chunk;
+        chunk = (D + cpf - 1) / cpf;  // balanced
+        const long long units = (long long)F * cpf;
+        const int grid = (int)std::max<long long>(1, std::min<long long>(units, blocks_cap));
+        const int staged = chunk >= Cfg::kWarps ? 1 : 0;
+        kern<<<grid, Cfg::kWarps * 32, Cfg::kSmem, st>>>(dd, d_frames, F, d_delays, D, chunk, cpf, seed, stream,
+                                                         call_no, d_frame_call_no, idx_base, d_framecost,
+                                                         cost_stride, d_flags, staged);
     });
     g_launches += 1;
 }
@@ -1745,10 +1818,11 @@ void launch_presync_grid(const DeviceData& dd, const FrameDesc* d_frames, int F,
                          const double* d_delays, int D, uint64_t seed, uint64_t stream,
                          uint64_t call_no, uint64_t idx_base, double* d_framecost, double* d_costs,
                          unsigned* d_flags, cudaStream_t st, cudaEvent_t ev_begin, cudaEvent_t ev_end,
-                         const uint64_t* d_frame_call_no, const int* d_win_begin, int n_windows) {
+                         const uint64_t* d_frame_call_no, const int* d_win_begin, int n_windows,
+                         int max_chunk) {
     if (ev_begin && F > 0 && D > 0) cudaEventRecord(ev_begin, st);
     launch_presync_tasks(dd, d_frames, F, max_n, d_delays, D, seed, stream, call_no, idx_base, d_framecost, F,
-                         d_flags, st, d_frame_call_no);
+                         d_flags, st, d_frame_call_no, max_chunk);
     if (ev_end && F > 0 && D > 0) cudaEventRecord(ev_end, st);
     launch_presync_reduce(d_framecost, F, D, d_costs, st, d_win_begin, n_windows);
 }
@@ -1759,7 +1833,7 @@ void launch_sync_init(const DeviceData& dd, const SyncBatchDev& b, const double*
     if (b.T <= 0) return;
     RS_DISPATCH_SLOTS(b.max_n, {
         auto kern = sync_init_kernel<SL>;
-        const size_t smem = (size_t)kWarpsPerBlock * warp_smem_bytes(SL * 32, true);
+        const size_t smem = (size_t)kWarpsPerBlock * warp_smem_bytes(SL * 32);
         allow_smem(kern, smem);
         const int grid = grid_for(kern, smem, b.T);
         kern<<<grid, kWarpsPerBlock * 32, smem, st>>>(dd, b, d_sp_delay, d_sp_callno, d_sp_active, seed);
@@ -1777,7 +1851,7 @@ void launch_sync_motion_fgrad(const DeviceData& dd, const SyncBatchDev& b, const
     // Backtrack / momentum step reads them -- only the per-task kernel is skipped.
     if (b.S <= 0) return;
     auto launch = [&](auto kern, int W) {
-        const size_t smem = kLog1pTableBytes + (size_t)W * warp_smem_bytes(slots_for(b.max_n) * 32, false) +
+        const size_t smem = kLog1pTableBytes + (size_t)W * warp_smem_bytes(slots_for(b.max_n) * 32) +
                             (size_t)W * kLbfgsHistDoubles * sizeof(double);
         allow_smem(kern, smem);
         const int grid = grid_for(kern, smem, b.T, W);
@@ -1799,7 +1873,7 @@ void launch_sync_trials(const DeviceData& dd, const SyncBatchDev& b, const doubl
     if (b.S <= 0 || ntrial <= 0) return;
     if (b.T > 0) {  // (T == 0: sums over no frames, see launch_sync_motion_fgrad)
         const int NP = slots_for(b.max_n) * 32;
-        const size_t smem = kLog1pTableBytes + (size_t)kWarpsPerBlock * warp_smem_bytes(NP, false);
+        const size_t smem = kLog1pTableBytes + (size_t)kWarpsPerBlock * warp_smem_bytes(NP);
         allow_smem(sync_trials_kernel, smem);
         const int grid = grid_for(sync_trials_kernel, smem, (long long)b.T * ntrial);
         sync_trials_kernel<<<grid, kWarpsPerBlock * 32, smem, st>>>(dd, b, NP, d_trial_delay, ntrial,
@@ -1812,7 +1886,7 @@ void launch_sync_trials(const DeviceData& dd, const SyncBatchDev& b, const doubl
 void launch_probe_problem_matrix(const DeviceData& dd, FrameDesc fd, double delay, double* d_P,
                                  cudaStream_t st) {
     const int NP = slots_for(fd.n) * 32;
-    probe_problem_kernel<<<1, 32, warp_smem_bytes(NP, false), st>>>(dd, fd, NP, delay, d_P);
+    probe_problem_kernel<<<1, 32, warp_smem_bytes(NP), st>>>(dd, fd, NP, delay, d_P);
     g_launches += 1;
 }
 void launch_probe_log1p(const double* d_x, int n, double* d_out, cudaStream_t st) {
@@ -1822,13 +1896,13 @@ void launch_probe_log1p(const double* d_x, int n, double* d_out, cudaStream_t st
 void launch_probe_loss(const DeviceData& dd, FrameDesc fd, double delay, const double* d_m, double k,
                        double* d_out, cudaStream_t st) {
     const int NP = slots_for(fd.n) * 32;
-    probe_loss_kernel<<<1, 32, kLog1pTableBytes + warp_smem_bytes(NP, false), st>>>(dd, fd, NP, delay, d_m, k, d_out);
+    probe_loss_kernel<<<1, 32, kLog1pTableBytes + warp_smem_bytes(NP), st>>>(dd, fd, NP, delay, d_m, k, d_out);
     g_launches += 1;
 }
 void launch_probe_lbfgs(const DeviceData& dd, FrameDesc fd, double delay, double* d_m, double k,
                         double* d_f, int* d_stats, cudaStream_t st) {
     const int NP = slots_for(fd.n) * 32;
-    probe_lbfgs_kernel<<<1, 32, kLog1pTableBytes + warp_smem_bytes(NP, false), st>>>(dd, fd, NP, delay, d_m, k, d_f, d_stats);
+    probe_lbfgs_kernel<<<1, 32, kLog1pTableBytes + warp_smem_bytes(NP), st>>>(dd, fd, NP, delay, d_m, k, d_f, d_stats);
     g_launches += 1;
 }
 void launch_probe_guess(const DeviceData& dd, FrameDesc fd, double delay, int iters,
@@ -1836,7 +1910,7 @@ void launch_probe_guess(const DeviceData& dd, FrameDesc fd, double delay, int it
                         cudaStream_t st) {
     RS_DISPATCH_SLOTS(fd.n, {
         auto kern = probe_guess_kernel<SL>;
-        kern<<<1, 32, warp_smem_bytes(SL * 32, true), st>>>(dd, fd, delay, iters, key_prefix, mode,
+        kern<<<1, 32, warp_smem_bytes(SL * 32), st>>>(dd, fd, delay, iters, key_prefix, mode,
                                                             d_mk, d_n_exact);
     });
     g_launches += 1;

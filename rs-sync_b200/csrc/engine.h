@@ -46,7 +46,12 @@ void launch_presync_grid(const DeviceData& dd, const FrameDesc* d_frames, int F,
                          // concatenated, frame f belongs to the call d_frame_call_no[f], window w
                          // covers frames [d_win_begin[w], d_win_begin[w+1]); d_costs is W x D
                          const uint64_t* d_frame_call_no = nullptr, const int* d_win_begin = nullptr,
-                         int n_windows = 0);
+                         int n_windows = 0, int max_chunk = 0);
+
+// How many consecutive delays of the (host copy of the) delay list one work unit of the grid kernel
+// may hold so that the spline window of any frame whose timestamps span at most frame_span_s seconds
+// fits the kernel's staging buffer.  Host-side helper; pass the result as max_chunk.
+int presync_max_chunk(const double* h_delays, int D, double frame_span_s, double sample_rate, int max_n);
 
 // The two halves of launch_presync_grid, for callers that evaluate the frames in several launches
 // (capi.cpp runs the frames of each upload chunk as soon as that chunk has landed): the task kernel
@@ -56,7 +61,7 @@ void launch_presync_grid(const DeviceData& dd, const FrameDesc* d_frames, int F,
 void launch_presync_tasks(const DeviceData& dd, const FrameDesc* d_frames, int F, int max_n,
                           const double* d_delays, int D, uint64_t seed, uint64_t stream, uint64_t call_no,
                           uint64_t idx_base, double* d_framecost, int cost_stride, unsigned* d_flags,
-                          cudaStream_t st, const uint64_t* d_frame_call_no = nullptr);
+                          cudaStream_t st, const uint64_t* d_frame_call_no = nullptr, int max_chunk = 0);
 void launch_presync_reduce(const double* d_framecost, int F, int D, double* d_costs, cudaStream_t st,
                            const int* d_win_begin = nullptr, int n_windows = 0);
 

@@ -12,7 +12,11 @@ measures that on many windows:
     reference    (oracle/_ref/librssync_ref.so: the unmodified reference sources compiled here
                   against oracle/shim; needs /root/reference at BUILD time only)
 
-and writes the distribution of |delay_spec - delay_ref| to profiles/.  CPU only.
+and, as the yardstick, a SECOND build of the same unmodified reference sources in which the compiler
+may contract a*b+c into FMAs (oracle/_ref/librssync_ref_fma.so, `make -C oracle ref_fma`; what a
+-march=native release build does).  It writes the distributions of |delay_spec - delay_ref| and of
+|delay_ref_fma - delay_ref| to profiles/: the second one is how far the reference moves away from
+ITSELF under an equally valid rounding of the same expressions.  CPU only.
 
 usage: python tools/sync_vs_reference.py [--windows 56] [--out profiles/r02_sync_vs_reference.json]
 """
@@ -40,6 +44,9 @@ def main():
         raise SystemExit("oracle/_ref/librssync_ref.so is missing: run `make -C oracle ref` where /root/reference exists")
     synth = importlib.import_module("rs-sync_b200.synth")
     rows = []
+    fma_path = os.path.join(ROOT, "oracle", "_ref", "librssync_ref_fma.so")
+    if not os.path.exists(fma_path):
+        fma_path = None
     t_begin = time.time()
     # C1-shaped data (300 frames x 100 rays, 1 kHz gyro), several world seeds / noise levels, windows
     # of 24 and 60 frames (core_testcode's sync_window), starting delays one PreSync step around the
@@ -51,6 +58,7 @@ def main():
         w = synth.make_workload("C1", **kw)
         o = loader.OracleProblem(threads=a.threads, seed=100).load(w)
         r = ref_loader.RefProblem(threads=a.threads, seed=100).load(w)
+        r2 = ref_loader.RefProblem(threads=a.threads, seed=100, lib_path=fma_path).load(w) if fma_path else None
         td = float(w.true_delay[0])
         for k in range(per_scene):
             if len(rows) >= a.windows:
@@ -61,16 +69,23 @@ def main():
             call = 10 * k + 3
             o.set_rng(100, call)
             r.set_rng(100, call)
-            do = dr = start
+            if r2:
+                r2.set_rng(100, call)
+            do = dr = dr2 = start
             chain = 2 if k % 4 == 0 else 1
             for _ in range(chain):
                 co, do = o.Sync(do, fb, fb + win, td, 0.2)
                 cr, dr = r.Sync(dr, fb, fb + win, td, 0.2)
+                if r2:
+                    _, dr2 = r2.Sync(dr2, fb, fb + win, td, 0.2)
             rows.append(dict(scene=si, frames=win + 1, first_frame=fb, start=start, chain=chain,
                              delay_spec=do, delay_ref=dr, cost_spec=co, cost_ref=cr,
-                             abs_delay_diff=abs(do - dr), rel_cost_diff=abs(co - cr) / abs(cr)))
+                             abs_delay_diff=abs(do - dr), rel_cost_diff=abs(co - cr) / abs(cr),
+                             delay_ref_fma=dr2 if r2 else None,
+                             abs_delay_diff_ref_vs_ref_fma=abs(dr2 - dr) if r2 else None))
             print(f"[{len(rows):3d}/{a.windows}] scene {si} fb {fb} win {win} chain {chain}: "
-                  f"|d_spec - d_ref| = {abs(do - dr):.3e}  rel cost {abs(co - cr) / abs(cr):.2e}", file=sys.stderr, flush=True)
+                  f"|d_spec - d_ref| = {abs(do - dr):.3e}  |d_ref_fma - d_ref| = {abs(dr2 - dr) if r2 else float('nan'):.3e}",
+                  file=sys.stderr, flush=True)
     d = np.array([x["abs_delay_diff"] for x in rows])
     c = np.array([x["rel_cost_diff"] for x in rows])
     summary = dict(
@@ -81,6 +96,13 @@ def main():
         frac_within_1e_5=float(np.mean(d <= 1e-5)), frac_within_1e_4=float(np.mean(d <= 1e-4)),
         max_rel_cost_diff=float(c.max()), median_rel_cost_diff=float(np.median(c)),
         reference_stop_threshold_s=1e-4, seconds=time.time() - t_begin, threads=a.threads)
+    if fma_path:
+        e = np.array([x["abs_delay_diff_ref_vs_ref_fma"] for x in rows])
+        summary["reference_vs_its_own_fma_build"] = dict(
+            what="|Sync delay (reference, -ffp-contract=fast -mfma) - Sync delay (reference, -ffp-contract=off)|, same windows",
+            max_abs_delay_diff=float(e.max()), median_abs_delay_diff=float(np.median(e)),
+            p90_abs_delay_diff=float(np.quantile(e, 0.9)), frac_within_1e_9=float(np.mean(e <= 1e-9)),
+            frac_within_1e_6=float(np.mean(e <= 1e-6)), frac_within_1e_4=float(np.mean(e <= 1e-4)))
     with open(a.out, "w") as f:
         json.dump(dict(summary=summary, rows=rows), f, indent=1)
     print(json.dumps(summary, indent=1))
