@@ -170,39 +170,35 @@ __device__ __forceinline__ void build_rows_staged(const DeviceData& dd, const Fr
                                                   int rec_cnt) {
     const int nslots = (fd.n + 31) >> 5;
     const double kTwo52 = 4503599627370496.0;
-    const unsigned last = (unsigned)(rec_cnt - 1);
     const uint32_t sRecAddr = smem_u32(sRec);
-    unsigned outside = 0u;
     for (int s = 0; s < nslots; ++s) {
         const int i = s * 32 + lane;
         const double* t = sTiles + s * 256 + lane;
         const double xa = ((t[0] - dd.q0) + delay) * dd.sr;   // core_private.cpp:19-20
         const double xb = ((t[32] - dd.q0) + delay) * dd.sr;
         const double fa = __dadd_rd(xa, kTwo52), fb = __dadd_rd(xb, kTwo52);
+        // record index inside the staged window.  No clamp: x is a monotone function of the timestamp
+        // and of the delay, roundings included, the frame's ts_lo / ts_hi bound every timestamp of
+        // its tile and the window was cut from their images with a record of slack either side
+        // (grid_stage_unit), so the index lies in [1, rec_cnt - 3].  RS_CHECKED builds verify it.
         const unsigned ia = (unsigned)(__double2loint(fa) - rec_first);
         const unsigned ib = (unsigned)(__double2loint(fb) - rec_first);
-        outside |= (ia > last ? 1u : 0u) | (ib > last ? 1u : 0u);
-        const unsigned ca = min(ia, last), cb = min(ib, last);
+#ifdef RS_CHECKED
+        if (ia >= (unsigned)rec_cnt || ib >= (unsigned)rec_cnt) __trap();
+#endif
         double qa[4], qb[4], ar[3], br[3], na, nb;
-        spline_eval4_staged(sRecAddr, ca, ca + (unsigned)rec_first, xa - (fa - kTwo52), qa);
-        spline_eval4_staged(sRecAddr, cb, cb + (unsigned)rec_first, xb - (fb - kTwo52), qb);
+        spline_eval4_staged(sRecAddr, ia, ia + (unsigned)rec_first, xa - (fa - kTwo52), qa);
+        spline_eval4_staged(sRecAddr, ib, ib + (unsigned)rec_first, xb - (fb - kTwo52), qb);
         derotate_unnormalised(qa, t[64], t[96], t[128], ar, na);
         derotate_unnormalised(qb, t[160], t[192], t[224], br, nb);
         const double sc = 1.0 / (na * nb);
-        double row[3];
-        row[0] = fma(ar[1], br[2], -(ar[2] * br[1])) * sc;
-        row[1] = fma(ar[2], br[0], -(ar[0] * br[2])) * sc;
-        row[2] = fma(ar[0], br[1], -(ar[1] * br[0])) * sc;
-        if (i >= fd.n) { row[0] = row[1] = row[2] = 0.0; }
-        w.P[i] = row[0];
-        w.P[NP + i] = row[1];
-        w.P[2 * NP + i] = row[2];
+        w.P[i] = fma(ar[1], br[2], -(ar[2] * br[1])) * sc;
+        w.P[NP + i] = fma(ar[2], br[0], -(ar[0] * br[2])) * sc;
+        w.P[2 * NP + i] = fma(ar[0], br[1], -(ar[1] * br[0])) * sc;
     }
-    if (__any_sync(FULL, outside != 0u)) {
-        build_rows_global_cold(dd, fd, delay, lane, w, NP);
-        return;
-    }
-    for (int i = nslots * 32 + lane; i < NP; i += 32) {
+    // entries past the frame's last ray are zero rows: the tail of the last slot (its padding rays
+    // were evaluated like any other) and the slots up to NP
+    for (int i = fd.n + lane; i < NP; i += 32) {
         w.P[i] = 0.0;
         w.P[NP + i] = 0.0;
         w.P[2 * NP + i] = 0.0;
@@ -991,14 +987,14 @@ __device__ __forceinline__ double warp_norm_PM(const double* sP, int NP, int nsl
     return sqrt(warp_sum(ss));
 }
 
-// which of pre_sync's panic conditions (core_private.cpp:76-83) a task with a non-finite cost hit
-__device__ __noinline__ unsigned presync_diagnose(const double* sP, int NP, int nslots, int lane, double scale,
+// which of pre_sync's panic conditions (core_private.cpp:76-83) a task with a non-finite cost hit;
+// pm: P.M of the warp's rays (the loss phase leaves it in the first plane of the rows)
+__device__ __noinline__ unsigned presync_diagnose(const double* pm, int nslots, int lane, double scale,
                                                   double m0, double m1, double m2, const double* tab) {
     unsigned bad = 0;
     if (!(is_finite(m0) && is_finite(m1) && is_finite(m2))) bad |= kFlagM;
     for (int s = 0; s < nslots; ++s) {
-        const int i = s * 32 + lane;
-        const double r = dot3(sP[i], sP[NP + i], sP[2 * NP + i], m0, m1, m2) * scale;
+        const double r = pm[s * 32 + lane] * scale;
         if (!is_finite(r)) bad |= kFlagR;
         if (!is_finite(log1p_nonneg(r * r, tab))) bad |= kFlagRho;
     }
@@ -1049,6 +1045,9 @@ __device__ __noinline__ unsigned presync_diagnose(const double* sP, int NP, int 
 #ifndef RS_GRID_RECS
 #define RS_GRID_RECS 144  // spline records per staged window (18 KB)
 #endif
+#ifndef RS_LOSS_UNROLL
+#define RS_LOSS_UNROLL 4  // slots per iteration of the loss phase
+#endif
 template <int SLOTS>
 struct GridCfg {
     static constexpr int kWarps = RS_GRID_WARPS;
@@ -1087,7 +1086,7 @@ __device__ __noinline__ void grid_stage_unit(const DeviceData& dd, const FrameDe
     // x = ((ts - q0) + delay) * sr is monotone in ts and in delay, roundings included
     const double x_lo = ((fd.ts_lo - dd.q0) + dmin) * dd.sr, x_hi = ((fd.ts_hi - dd.q0) + dmax) * dd.sr;
     const double r_lo = floor(x_lo) - 1.0, r_hi = floor(x_hi) + 2.0;  // a record of slack either side
-    const bool ok = r_lo >= 0.0 && r_hi <= (double)(dd.nq - 1) && (r_hi - r_lo) < (double)rec_cap;
+    const bool ok = dd.sr > 0.0 && r_lo >= 0.0 && r_hi <= (double)(dd.nq - 1) && (r_hi - r_lo) < (double)rec_cap;
     const int first = ok ? (int)r_lo : 0, cnt = ok ? (int)(r_hi - r_lo) + 1 : 0;
     ctl->rec_first[b] = first;
     ctl->rec_cnt[b] = cnt;
@@ -1200,35 +1199,48 @@ presync_kernel(DeviceData dd, const FrameDesc* __restrict__ frames, int F,
         unsigned bad = warp_ransac<SLOTS>(dd, fd, w, 20, key, lane, M, flags + 1);  // core_private.cpp:77
         // :79-85
         __syncwarp();
-        // rows past the frame's last ray are zero: they add 0 to the norm and log1p(0) = 0 to the loss
-        double pmv[SLOTS];
-#pragma unroll
-        for (int s = 0; s < SLOTS; ++s) {
-            const int i = s * 32 + lane;
-            pmv[s] = dot3(w.P[i], w.P[NP + i], w.P[2 * NP + i], M[0], M[1], M[2]);
-        }
+        // rows past the frame's last ray are zero: they add 0 to the norm and log1p(0) = 0 to the loss.
+        // Written as loops over groups of kLossUnroll slots (independent chains inside a group):
+        // the fully unrolled form is 7 KB of straight-line code that every task streams through the
+        // instruction caches once.  P.M of a ray replaces the ray's first row component in shared
+        // memory between the two passes (each lane touches only its own rays).
+        constexpr int LU = RS_LOSS_UNROLL < SLOTS ? RS_LOSS_UNROLL : SLOTS;
         double ss = 0.0;
+#pragma unroll 1
+        for (int s0 = 0; s0 < SLOTS; s0 += LU) {
+            double pm[LU];
 #pragma unroll
-        for (int s = 0; s < SLOTS; ++s) ss = ss + pmv[s] * pmv[s];
+            for (int j = 0; j < LU; ++j) {
+                const int i = (s0 + j) * 32 + lane;
+                pm[j] = 0.0;
+                if (s0 + j < SLOTS) {
+                    pm[j] = dot3(w.P[i], w.P[NP + i], w.P[2 * NP + i], M[0], M[1], M[2]);
+                    w.P[i] = pm[j];
+                }
+            }
+#pragma unroll
+            for (int j = 0; j < LU; ++j) ss = ss + pm[j] * pm[j];
+        }
         const double kv = clamp_k(1.0 / sqrt(warp_sum(ss)) * 1e2);  // arma::norm(P * M), :79
         const double scale = kv / sqrt(dot3(M[0], M[1], M[2], M[0], M[1], M[2]));
         double acc = 0.0;
-        {
-            double rho[SLOTS];
+#pragma unroll 1
+        for (int s0 = 0; s0 < SLOTS; s0 += LU) {
+            double rho[LU];
 #pragma unroll
-            for (int s = 0; s < SLOTS; ++s) {
-                const double r = pmv[s] * scale;
-                rho[s] = sqrt(log1p_nonneg(r * r, tab));
+            for (int j = 0; j < LU; ++j) {
+                const double r = (s0 + j < SLOTS ? w.P[(s0 + j) * 32 + lane] : 0.0) * scale;
+                rho[j] = sqrt(log1p_nonneg(r * r, tab));
             }
 #pragma unroll
-            for (int s = 0; s < SLOTS; ++s) acc = acc + rho[s];
+            for (int j = 0; j < LU; ++j) acc = acc + rho[j];
         }
         const double cost = sqrt(warp_sum(acc));
         if (lane == 0) framecost[(size_t)di * cost_stride + fi] = cost;
         // the panic conditions of :76-83: non-finite values propagate into the cost, so the stage
         // that produced them is only looked for when the cost (or a row) is not finite
         if (bad || !is_finite(cost)) {
-            bad |= presync_diagnose(w.P, NP, (fd.n + 31) >> 5, lane, scale, M[0], M[1], M[2], tab);
+            bad |= presync_diagnose(w.P, (fd.n + 31) >> 5, lane, scale, M[0], M[1], M[2], tab);
             bad = __reduce_or_sync(FULL, bad);
             if (bad && lane == 0) atomicOr(flags, bad);
         }
