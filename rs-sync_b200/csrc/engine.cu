@@ -55,12 +55,14 @@ std::atomic<uint64_t> g_launches{0};
 // instead of 5.25 KB at N = 200, which is what left no room to double-buffer the staged inputs.)
 struct WarpSmem {
     double* P;
+    float* hyp;  // estimator kernels: the current batch of hypotheses in fp32, [3][32]
 };
-__host__ __device__ constexpr int pairs_for(int NP) { return (NP / 32 + 1) / 2; }
-__host__ __device__ constexpr size_t warp_smem_bytes(int NP) { return (size_t)NP * 3 * 8; }
+constexpr size_t kHypBytes = 3 * 32 * 4;
+__host__ __device__ constexpr size_t warp_smem_bytes(int NP) { return (size_t)NP * 3 * 8 + kHypBytes; }
 __device__ __forceinline__ WarpSmem warp_smem(unsigned char* base, int warp, int NP) {
     WarpSmem w;
     w.P = reinterpret_cast<double*>(base + (size_t)warp * warp_smem_bytes(NP));
+    w.hyp = reinterpret_cast<float*>(w.P + 3 * NP);
     return w;
 }
 
@@ -447,65 +449,55 @@ __device__ __forceinline__ float sqrt_approx(float x) {
     return y;
 }
 
-// count of keys <= pv over the warp (keys are non-negative floats: s <= pv <=> s - next(pv) < 0)
-template <int NPAIR>
-__device__ __forceinline__ int warp_count_le(const float2 (&s)[NPAIR], unsigned pv) {
+// ---- order statistics over the warp's keys: SLOTS non-negative floats per lane, compared through
+// their bit patterns --------------------------------------------------------------------------------
+// count of keys <= pv (s <= pv  <=>  s - next(pv) < 0)
+template <int SLOTS>
+__device__ __forceinline__ int warp_count_le(const float (&s)[SLOTS], unsigned pv) {
     const float nt = -__uint_as_float(pv + 1u);
-    const float2 nt2 = make_float2(nt, nt);
     unsigned c = 0;
 #pragma unroll
-    for (int p = 0; p < NPAIR; ++p) {
-        const float2 e = __fadd2_rn(s[p], nt2);
-        c += __float_as_uint(e.x) >> 31;
-        c += __float_as_uint(e.y) >> 31;
-    }
+    for (int i = 0; i < SLOTS; ++i) c += __float_as_uint(s[i] + nt) >> 31;
     return (int)__reduce_add_sync(FULL, c);
 }
-// smallest key >= lo over the warp (at least one exists)
-template <int NPAIR>
-__device__ __forceinline__ unsigned warp_min_ge(const float2 (&s)[NPAIR], unsigned lo) {
+// smallest key >= lo (at least one exists)
+template <int SLOTS>
+__device__ __forceinline__ unsigned warp_min_ge(const float (&s)[SLOTS], unsigned lo) {
     unsigned mn = 0xffffffffu;
 #pragma unroll
-    for (int p = 0; p < NPAIR; ++p) {  // keys below lo wrap to >= 2^31
-        mn = min(mn, __float_as_uint(s[p].x) - lo);
-        mn = min(mn, __float_as_uint(s[p].y) - lo);
-    }
+    for (int i = 0; i < SLOTS; ++i) mn = min(mn, __float_as_uint(s[i]) - lo);  // keys below lo wrap to >= 2^31
     return lo + __reduce_min_sync(FULL, mn);
 }
-// largest key < hi_excl over the warp (at least one exists)
-template <int NPAIR>
-__device__ __forceinline__ unsigned warp_max_lt(const float2 (&s)[NPAIR], unsigned hi_excl) {
+// largest key < hi_excl (at least one exists)
+template <int SLOTS>
+__device__ __forceinline__ unsigned warp_max_lt(const float (&s)[SLOTS], unsigned hi_excl) {
     unsigned mn = 0xffffffffu;
     const unsigned top = hi_excl - 1u;
 #pragma unroll
-    for (int p = 0; p < NPAIR; ++p) {  // keys >= hi_excl wrap to >= 2^31
-        mn = min(mn, top - __float_as_uint(s[p].x));
-        mn = min(mn, top - __float_as_uint(s[p].y));
-    }
+    for (int i = 0; i < SLOTS; ++i) mn = min(mn, top - __float_as_uint(s[i]));  // keys >= hi_excl wrap
     return top - __reduce_min_sync(FULL, mn);
 }
 
-// kk-th smallest (0-based) of the warp's NPAIR*64 fp32 keys (non-negative floats, compared through
-// their bit patterns), given count(key < hi_excl) = chi > kk.  Value-bracket search [lo, hi_excl)
-// with clo = count(key < lo) <= kk < chi.  Pivots: with no scale information (`sample`), the
-// matching order statistic of a 32-key sample (slot 0 of every lane); afterwards interpolation in
-// the sqrt domain (ranks of small residuals grow linearly in |r|), bisection of the bit pattern
-// after two steps of poor progress.  When the wanted key is the lowest or highest of the bracket
-// it is extracted with one warp min.
-template <int NPAIR>
-__device__ __forceinline__ unsigned warp_select32(const float2 (&s)[NPAIR], int kk, unsigned hi_excl,
+// kk-th smallest (0-based) of the warp's SLOTS*32 keys, given count(key < hi_excl) = chi > kk.
+// Value-bracket search [lo, hi_excl) with clo = count(key < lo) <= kk < chi.  Pivots: with no scale
+// information (`sample`), the matching order statistic of a 32-key sample (slot 0 of every lane);
+// afterwards interpolation in the sqrt domain (ranks of small residuals grow linearly in |r|),
+// bisection of the bit pattern after two steps of poor progress.  When the wanted key is the
+// lowest or highest of the bracket it is extracted with one warp min.
+template <int SLOTS>
+__device__ __forceinline__ unsigned warp_select32(const float (&s)[SLOTS], int kk, unsigned hi_excl,
                                                   int chi, int npad, int n, bool sample) {
     unsigned lo = 0u;
     int clo = 0, poor = 0;
     for (;;) {
         if (hi_excl - lo == 1u) return lo;
-        if (kk == clo) return warp_min_ge<NPAIR>(s, lo);
-        if (kk == chi - 1) return warp_max_lt<NPAIR>(s, hi_excl);
+        if (kk == clo) return warp_min_ge<SLOTS>(s, lo);
+        if (kk == chi - 1) return warp_max_lt<SLOTS>(s, hi_excl);
         unsigned pv;
         if (sample) {
             sample = false;
             const int js = min((32 * (kk - npad)) / n, 31);
-            const unsigned k0 = __float_as_uint(s[0].x);
+            const unsigned k0 = __float_as_uint(s[0]);
             unsigned cur = 0u;
             pv = 0u;
             for (int i = 0; i <= js; ++i) {
@@ -525,7 +517,7 @@ __device__ __forceinline__ unsigned warp_select32(const float2 (&s)[NPAIR], int 
         }
         pv = max(pv, lo);
         pv = min(pv, hi_excl - 2u);
-        const int cnt = warp_count_le<NPAIR>(s, pv);
+        const int cnt = warp_count_le<SLOTS>(s, pv);
         if (cnt > kk) {
             poor = (2 * (cnt - clo) > (chi - clo)) ? poor + 1 : 0;
             hi_excl = pv + 1u;
@@ -538,180 +530,168 @@ __device__ __forceinline__ unsigned warp_select32(const float2 (&s)[NPAIR], int 
     }
 }
 
-// The tournament's inputs: the frame's rows, row-normalised, in fp32, in registers -- lane l holds its
-// slots (2p, 2p+1) as one float2 per component.  Any accuracy the margin covers will do, so the norm
-// is taken with rsqrt.approx (rel. error <= 2^-22.4).  Rows that safe_normalize would leave unscaled
+// The tournament's inputs: the frame's rows, row-normalised, in fp32, in registers -- lane l holds
+// the three components of its SLOTS rays.  Any accuracy the margin covers will do, so the norm is
+// taken with rsqrt.approx (rel. error <= 2^-22.4).  Rows that safe_normalize would leave unscaled
 // (|row| < 1e-12, also out of fp32 range) and non-finite rows poison `fin`: returns false, and the
 // task goes to the exact estimator.  Rows past the frame's last ray (zero rows) become +0 keys.
 template <int SLOTS>
 __device__ __forceinline__ bool load_normalised_rows32(const double* __restrict__ sP, int n, int lane,
-                                                       float2 (&nx)[pairs_for(SLOTS * 32)],
-                                                       float2 (&ny)[pairs_for(SLOTS * 32)],
-                                                       float2 (&nz)[pairs_for(SLOTS * 32)]) {
-    constexpr int NP = SLOTS * 32, NPAIR = pairs_for(NP);
+                                                       float (&nx)[SLOTS], float (&ny)[SLOTS],
+                                                       float (&nz)[SLOTS]) {
+    constexpr int NP = SLOTS * 32;
     float fin = 0.f;  // stays finite iff every row is (rows and 1/|row| feed it)
 #pragma unroll
-    for (int p = 0; p < NPAIR; ++p) {
-        float f[2][3];
-#pragma unroll
-        for (int hh = 0; hh < 2; ++hh) {
-            const int s = 2 * p + hh;
-            if (s < SLOTS) {
-                const int i = s * 32 + lane;
-                const double r0 = sP[i], r1 = sP[NP + i], r2 = sP[2 * NP + i];
-                const float n2 = (float)dot3(r0, r1, r2, r0, r1, r2);
-                float rs;
-                asm("rsqrt.approx.f32 %0, %1;" : "=f"(rs) : "f"(n2));
-                if (i >= n) rs = 0.f;
-                else if (n2 < 1e-24f) rs = __uint_as_float(0x7fc00000u);
-                f[hh][0] = (float)r0 * rs;
-                f[hh][1] = (float)r1 * rs;
-                f[hh][2] = (float)r2 * rs;
-                fin += (fabsf(f[hh][0]) + fabsf(f[hh][1])) + fabsf(f[hh][2]);  // non-finite row -> NaN
-            } else {
-                f[hh][0] = f[hh][1] = f[hh][2] = 0.f;
-            }
-        }
-        nx[p] = make_float2(f[0][0], f[1][0]);
-        ny[p] = make_float2(f[0][1], f[1][1]);
-        nz[p] = make_float2(f[0][2], f[1][2]);
+    for (int s = 0; s < SLOTS; ++s) {
+        const int i = s * 32 + lane;
+        const double r0 = sP[i], r1 = sP[NP + i], r2 = sP[2 * NP + i];
+        const float n2 = (float)dot3(r0, r1, r2, r0, r1, r2);
+        float rs;
+        asm("rsqrt.approx.f32 %0, %1;" : "=f"(rs) : "f"(n2));
+        if (i >= n) rs = 0.f;
+        else if (n2 < 1e-24f) rs = __uint_as_float(0x7fc00000u);
+        nx[s] = (float)r0 * rs;
+        ny[s] = (float)r1 * rs;
+        nz[s] = (float)r2 * rs;
+        fin += (fabsf(nx[s]) + fabsf(ny[s])) + fabsf(nz[s]);  // non-finite row -> NaN
     }
     return __all_sync(FULL, (__float_as_uint(fin) & 0x7f800000u) != 0x7f800000u);
 }
 
-#ifndef RS_COUNT_FMA
-#define RS_COUNT_FMA 1
-#endif
 // Result of the fast path: the winner is certified / it is not (run the exact estimator) / the rows
 // themselves are not finite (exact estimator, and pre_sync's "non-finite numbers in P" condition).
 enum FastStatus { kFastOk = 0, kFastUndecided = 1, kFastRowsNotFinite = 2 };
+
+// The tournament proper.  Hypotheses are taken two at a time: the packed fp32x2 instructions carry
+// hypotheses t and t + 1 in their two halves against ONE ray (scalar operand), so a pass over the
+// lane's SLOTS rays costs four packed instructions and two shift-adds per ray for two hypotheses,
+// with one warp reduction for both counts.  (r01 packed two RAYS against one hypothesis: a pass per
+// hypothesis over pairs_for(NP) ray pairs -- eight slots' worth of work for N = 200's seven -- and a
+// reduction each.)  Both counts are against the threshold of the best hypothesis so far:
+//   * both <= kk: both rigorously worse, next pair (the common case);
+//   * the first has more: it is a challenger -- select its quartile, compare, maybe a new best --
+//     and the second is looked at again, as the first of the next pair, against whatever the
+//     threshold is then;
+//   * only the second: the first is rejected, the threshold unchanged, the second is the challenger.
+// The rejection test is made on the EXACT squares: e = fma(rho, rho, -thr1) is the correctly rounded
+// rho^2 - thr1, whose sign is that of the exact difference, so the count is count(rho^2 < thr1);
+// |rho| is at least as close to |r64| as sqrt(fl(rho^2)) is, so the argument at the top of this
+// section holds for these keys as it does for the rounded ones.  A challenger's keys are the rounded
+// squares (the select works on their bit patterns); its count is retaken on those -- it can differ
+// where rho^2 rounds up to thr1, and is then just as rigorous a rejection.
+// `hyp`: 3 x 32 floats of the warp's shared memory (the batch's hypotheses in fp32, by component).
 template <int SLOTS>
 __device__ __forceinline__ FastStatus warp_ransac_fast(const DeviceData& dd, const FrameDesc& fd,
                                                        const WarpSmem& w, int iters, uint64_t key,
                                                        int lane, double M[3], int* settled) {
-    constexpr int NP = SLOTS * 32, NPAIR = pairs_for(NP), NK = 2 * NPAIR;
-    float2 nx[NPAIR], ny[NPAIR], nz[NPAIR];
+    constexpr int NP = SLOTS * 32;
+    float nx[SLOTS], ny[SLOTS], nz[SLOTS];
     if (!load_normalised_rows32<SLOTS>(w.P, fd.n, lane, nx, ny, nz)) return kFastRowsNotFinite;
     const int n = fd.n;
-    const int npad = NK * 32 - n;  // padding keys are +0: always counted, always below
-    const int kk = n / 4 + npad;   // :52
-    unsigned tau = 0x7f800000u;    // fp32 quartile of the best hypothesis so far (+inf: none yet)
-    float nthr = 0.f;              // -(nextafter(up(tau))): s <= up(tau)  <=>  s + nthr < 0
-    unsigned thr1 = 0u;
+    const int npad = NP - n;      // padding keys are +0: always counted, always below
+    const int kk = n / 4 + npad;  // :52
+    unsigned tau = 0x7f800000u;   // fp32 quartile of the best hypothesis so far (+inf: none yet)
+    float nthr = 0.f;             // -thr1
+    unsigned thr1 = 0u;           // nextafter(up(tau)): s <= up(tau)  <=>  s < thr1
     M[0] = M[1] = M[2] = 0.0;
+    float* hyp = w.hyp;
     for (int j0 = 0; j0 < iters; j0 += 32) {
         double v[3] = {0.0, 0.0, 0.0};
         if (j0 + lane < iters) draw_hypothesis(dd, fd, w.P, NP, key, (uint32_t)(j0 + lane), v);
-        const float w0 = (float)v[0], w1 = (float)v[1], w2 = (float)v[2];
+        __syncwarp();
+        hyp[lane] = (float)v[0];
+        hyp[32 + lane] = (float)v[1];
+        hyp[64 + lane] = (float)v[2];
+        __syncwarp();
         const int cnt = (iters - j0) < 32 ? (iters - j0) : 32;
         int t = 0;
         while (t < cnt) {
-            // hot loop: runs until the batch is done or a comparison cannot be called in fp32
-            int t_amb = -1;
-            unsigned q_amb = 0u, uq_amb = 0u;
-            for (; t < cnt; ++t) {
-                const float vx = __shfl_sync(FULL, w0, t), vy = __shfl_sync(FULL, w1, t),
-                            vz = __shfl_sync(FULL, w2, t);
-                const float2 vx2 = make_float2(vx, vx), vy2 = make_float2(vy, vy),
-                             vz2 = make_float2(vz, vz);
-                float2 sq[NPAIR];
-                unsigned hi_excl;
-                int chi;
-                const bool first = tau == 0x7f800000u;
-                if (!first) {
-                    const float2 nt2 = make_float2(nthr, nthr);
-                    unsigned c = 0;
-#if RS_COUNT_FMA
-                    // rejection test on the EXACT squares: e = fma(rho, rho, -thr1) is the correctly
-                    // rounded rho^2 - thr1, whose sign is that of the exact difference, so the count
-                    // is count(rho^2 < thr1) -- one packed instruction instead of a product and a
-                    // sum.  |rho| is at least as close to |r64| as sqrt(fl(rho^2)) is, so the
-                    // rejection argument above holds for these keys as it does for the rounded ones.
+            float sq[SLOTS];  // keys of the hypothesis being examined closely (index tc)
+            int tc, chi;
+            unsigned hi_excl;
+            bool first = false;
+            if (tau == 0x7f800000u) {
+                // no best yet (the task's first hypothesis): its quartile, whatever it is
+                const float vx = hyp[t], vy = hyp[32 + t], vz = hyp[64 + t];
+                unsigned mx = 0u;
 #pragma unroll
-                    for (int p = 0; p < NPAIR; ++p) {
-                        float2 r = __fmul2_rn(nx[p], vx2);
-                        r = __ffma2_rn(ny[p], vy2, r);
-                        r = __ffma2_rn(nz[p], vz2, r);
-                        sq[p] = r;
-                        const float2 e = __ffma2_rn(r, r, nt2);
-                        c += __float_as_uint(e.x) >> 31;
-                        c += __float_as_uint(e.y) >> 31;
-                    }
-                    if ((int)__reduce_add_sync(FULL, c) <= kk) continue;  // rigorously worse than the best so far
-                    // a challenger: from here on its keys are the rounded squares (the select works on
-                    // their bit patterns); recount on those, which may differ from the count above
-                    // where rho^2 rounds up to thr1 -- and is then just as rigorous a rejection
-                    c = 0;
-#pragma unroll
-                    for (int p = 0; p < NPAIR; ++p) {
-                        sq[p] = __fmul2_rn(sq[p], sq[p]);
-                        const float2 e = __fadd2_rn(sq[p], nt2);
-                        c += __float_as_uint(e.x) >> 31;
-                        c += __float_as_uint(e.y) >> 31;
-                    }
-                    chi = (int)__reduce_add_sync(FULL, c);
-                    if (chi <= kk) continue;
-#else
-#pragma unroll
-                    for (int p = 0; p < NPAIR; ++p) {
-                        float2 r = __fmul2_rn(nx[p], vx2);
-                        r = __ffma2_rn(ny[p], vy2, r);
-                        r = __ffma2_rn(nz[p], vz2, r);
-                        sq[p] = __fmul2_rn(r, r);
-                        const float2 e = __fadd2_rn(sq[p], nt2);
-                        c += __float_as_uint(e.x) >> 31;
-                        c += __float_as_uint(e.y) >> 31;
-                    }
-                    chi = (int)__reduce_add_sync(FULL, c);
-                    if (chi <= kk) continue;  // rigorously worse than the best so far
-#endif
-                    hi_excl = thr1;
-                } else {
-                    unsigned mx = 0u;
-#pragma unroll
-                    for (int p = 0; p < NPAIR; ++p) {
-                        float2 r = __fmul2_rn(nx[p], vx2);
-                        r = __ffma2_rn(ny[p], vy2, r);
-                        r = __ffma2_rn(nz[p], vz2, r);
-                        sq[p] = __fmul2_rn(r, r);
-                        mx = max(mx, max(__float_as_uint(sq[p].x), __float_as_uint(sq[p].y)));
-                    }
-                    mx = __reduce_max_sync(FULL, mx);
-                    if (mx >= 0x7f800000u) return kFastUndecided;
-                    hi_excl = mx + 1u;
-                    chi = NK * 32;
+                for (int s = 0; s < SLOTS; ++s) {
+                    const float r = fmaf(nz[s], vz, fmaf(ny[s], vy, nx[s] * vx));
+                    sq[s] = r * r;
+                    mx = max(mx, __float_as_uint(sq[s]));
                 }
-                const unsigned q = warp_select32<NPAIR>(sq, kk, hi_excl, chi, npad, n, first);
-                const unsigned uq = up_bits(q);
-                if (!(uq < tau)) {  // too close to the best so far to call in fp32
-                    t_amb = t;
-                    q_amb = q;
-                    uq_amb = uq;
-                    break;
+                mx = __reduce_max_sync(FULL, mx);
+                if (mx >= 0x7f800000u) return kFastUndecided;
+                hi_excl = mx + 1u;
+                chi = NP;
+                tc = t;
+                first = true;
+                t += 1;
+            } else {
+                const int t1 = (t + 1 < cnt) ? t + 1 : t;  // an odd batch ends with a doubled hypothesis
+                const float2 vx2 = make_float2(hyp[t], hyp[t1]);
+                const float2 vy2 = make_float2(hyp[32 + t], hyp[32 + t1]);
+                const float2 vz2 = make_float2(hyp[64 + t], hyp[64 + t1]);
+                const float2 nt2 = make_float2(nthr, nthr);
+                float2 rr[SLOTS];
+                unsigned c0 = 0, c1 = 0;
+#pragma unroll
+                for (int s = 0; s < SLOTS; ++s) {
+                    float2 r = __fmul2_rn(vx2, make_float2(nx[s], nx[s]));
+                    r = __ffma2_rn(vy2, make_float2(ny[s], ny[s]), r);
+                    r = __ffma2_rn(vz2, make_float2(nz[s], nz[s]), r);
+                    rr[s] = r;
+                    const float2 e = __ffma2_rn(r, r, nt2);
+                    c0 += __float_as_uint(e.x) >> 31;
+                    c1 += __float_as_uint(e.y) >> 31;
                 }
+                const unsigned both = __reduce_add_sync(FULL, c0 | (c1 << 16));
+                const int ca = (int)(both & 0xffffu), cb = (t1 != t) ? (int)(both >> 16) : 0;
+                if (ca <= kk && cb <= kk) {  // both rigorously worse than the best so far
+                    t += 2;
+                    continue;
+                }
+                const bool second = ca <= kk;
+                tc = second ? t1 : t;
+                t += second ? 2 : 1;
+                unsigned c = 0;
+                const float nt = nthr;
+#pragma unroll
+                for (int s = 0; s < SLOTS; ++s) {
+                    const float r = second ? rr[s].y : rr[s].x;
+                    sq[s] = r * r;
+                    c += __float_as_uint(sq[s] + nt) >> 31;
+                }
+                chi = (int)__reduce_add_sync(FULL, c);
+                if (chi <= kk) continue;
+                hi_excl = thr1;
+            }
+            const unsigned q = warp_select32<SLOTS>(sq, kk, hi_excl, chi, npad, n, first);
+            const unsigned uq = up_bits(q);
+            if (uq < tau) {  // rigorously better than the best so far
                 tau = q;
                 thr1 = uq + 1u;
                 nthr = -__uint_as_float(thr1);
-                M[0] = __shfl_sync(FULL, v[0], t);
-                M[1] = __shfl_sync(FULL, v[1], t);
-                M[2] = __shfl_sync(FULL, v[2], t);
+                M[0] = __shfl_sync(FULL, v[0], tc);
+                M[1] = __shfl_sync(FULL, v[1], tc);
+                M[2] = __shfl_sync(FULL, v[2], tc);
+                continue;
             }
-            if (t_amb < 0) break;
-            // cold: settle this one comparison with the exact binary64 quartiles of the two
-            // hypotheses (a tie keeps the earlier one, core_private.cpp:53), then resume
-            const double tx = __shfl_sync(FULL, v[0], t_amb), ty = __shfl_sync(FULL, v[1], t_amb),
-                         tz = __shfl_sync(FULL, v[2], t_amb);
+            // too close to the best so far to call in fp32 (cold): settle this one comparison with
+            // the exact binary64 quartiles of the two hypotheses (a tie keeps the earlier one,
+            // core_private.cpp:53), then resume
+            const double tx = __shfl_sync(FULL, v[0], tc), ty = __shfl_sync(FULL, v[1], tc),
+                         tz = __shfl_sync(FULL, v[2], tc);
             const unsigned long long qt = warp_exact_quartile<SLOTS>(w, n, lane, tx, ty, tz);
             const unsigned long long qb = warp_exact_quartile<SLOTS>(w, n, lane, M[0], M[1], M[2]);
             if (qt >= 0x7ff0000000000000ULL || qb >= 0x7ff0000000000000ULL) return kFastUndecided;
             if (settled) ++*settled;
             if (qt < qb) {
-                tau = q_amb;
-                thr1 = uq_amb + 1u;
+                tau = q;
+                thr1 = uq + 1u;
                 nthr = -__uint_as_float(thr1);
                 M[0] = tx; M[1] = ty; M[2] = tz;
             }
-            t = t_amb + 1;
         }
     }
     return kFastOk;
@@ -1043,7 +1023,7 @@ __device__ __noinline__ unsigned presync_diagnose(const double* pm, int nslots, 
 #define RS_GRID_MINB 2
 #endif
 #ifndef RS_GRID_RECS
-#define RS_GRID_RECS 144  // spline records per staged window (18 KB)
+#define RS_GRID_RECS 128  // spline records per staged window (16 KB)
 #endif
 #ifndef RS_LOSS_UNROLL
 #define RS_LOSS_UNROLL 4  // slots per iteration of the loss phase
@@ -1052,13 +1032,21 @@ template <int SLOTS>
 struct GridCfg {
     static constexpr int kWarps = RS_GRID_WARPS;
     static constexpr int kMinBlocks = SLOTS <= 8 ? RS_GRID_MINB : 1;
-    static constexpr int kRecs = SLOTS <= 8 ? RS_GRID_RECS : 128;
     static constexpr size_t kTileBytes = (size_t)SLOTS * 2048;
+    // spline records per staged window: what kMinBlocks blocks leave of the SM's 228 KB (1 KB per
+    // block is the system's), in steps of 8 records, at most RS_GRID_RECS
+    static constexpr long long kRoom = (228 * 1024) / kMinBlocks - 1024 - (long long)kLog1pTableBytes - 256 -
+                                       (long long)kWarps * (long long)warp_smem_bytes(SLOTS * 32) - 2 * (long long)kTileBytes;
+    static constexpr int kRecsFit = (int)(kRoom / 256 / 8 * 8);
+    static constexpr int kRecs = kRecsFit < RS_GRID_RECS ? kRecsFit : RS_GRID_RECS;
+    static_assert(kRecs >= 40, "grid kernel: no room for a spline window");
     static constexpr size_t kBufBytes = kTileBytes + (size_t)kRecs * 128;
     static constexpr size_t kCtlOff = kLog1pTableBytes;
     static constexpr size_t kBufOff = kCtlOff + 256;
     static constexpr size_t kWarpOff = kBufOff + 2 * kBufBytes;
     static constexpr size_t kSmem = kWarpOff + (size_t)kWarps * warp_smem_bytes(SLOTS * 32);
+    // kMinBlocks blocks must fit the SM's 228 KB (1 KB per block is the system's)
+    static_assert(kMinBlocks * (kSmem + 1024) <= 228 * 1024, "grid kernel: shared memory over budget");
 };
 struct GridCtl {
     unsigned long long full[2];  // mbarriers: the staged data of the unit in buffer b has landed
