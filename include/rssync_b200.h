@@ -41,6 +41,20 @@ enum {
 
 /* CreateSyncProblem()            rssync.h:31.  Uses the calling thread's current CUDA device. */
 int rssync_create(rssync_problem** out);
+/* The same problem spread over n_devices GPUs of this process (the "device-count option" of the
+ * batch extensions; the reference is a single shared-memory process, src/core/core_private.cpp).
+ * devices[0] is the primary: it takes every Set* call and holds the one complete copy of the inputs;
+ * the other devices receive the finished device state (ray arena, spline records) by ncclBroadcast
+ * over NVLink when a compute call finds them stale.  PreSync / DebugPreSync / rssync_presync_grid
+ * shard the delay grid by offset range (one ncclAllGather of the curve slices per call),
+ * rssync_sync_batch* / rssync_presync_windows shard by syncpoint and rssync_orientation_search* by
+ * variant (results assembled on the host, where the solver's control loop produces them); every
+ * result is bit-identical to the single-device one.  A single rssync_sync call runs on devices[0].
+ * NCCL (libnccl.so.2) is loaded at run time, only by this call and only when n_devices > 1.
+ * Leaves devices[0] the calling thread's current device. */
+int rssync_create_multi(const int* devices, int n_devices, rssync_problem** out);
+/* number of devices the problem spans (1 for rssync_create) */
+int rssync_device_count(const rssync_problem* p);
 /* ISyncProblem::~ISyncProblem()  rssync.h:11 */
 void rssync_destroy(rssync_problem* p);
 const char* rssync_last_error(const rssync_problem* p);

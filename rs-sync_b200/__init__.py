@@ -36,6 +36,7 @@ C_ABI_SYMBOLS = [
     "rssync_probe_lbfgs", "rssync_probe_log1p", "rssync_set_track_batch", "rssync_set_kernel_timing",
     "rssync_sync_batch_ex", "rssync_probe_guess_motion_ex", "rssync_integrate_gyro",
     "rssync_orientation_search", "rssync_orientation_search_ex", "rssync_presync_windows", "rssync_set_track_pixels",
+    "rssync_create_multi", "rssync_device_count",
 ]
 # Itanium-ABI symbols of the C++ drop-in face (same set the reference's librssync_core exports)
 CXX_ABI_SYMBOLS = [
@@ -77,6 +78,8 @@ def load_library():
     L = C.CDLL(LIB_PATH)
     P = C.c_void_p
     L.rssync_create.argtypes = [C.POINTER(P)]
+    L.rssync_create_multi.argtypes = [C.POINTER(C.c_int), C.c_int, C.POINTER(P)]
+    L.rssync_device_count.argtypes = [P]
     L.rssync_destroy.argtypes = [P]
     L.rssync_destroy.restype = None
     L.rssync_last_error.argtypes = [P]
@@ -197,10 +200,16 @@ class SyncProblem:
     ({cost, delay} pairs).  Errors that make the reference write panic.txt and exit raise
     RsSyncError carrying the same message."""
 
-    def __init__(self, seed=100):
+    def __init__(self, seed=100, devices=None):
+        """devices: None = the calling thread's current CUDA device (CreateSyncProblem); a list of
+        device ordinals = one problem spread over those GPUs (rssync_create_multi)."""
         self.L = load_library()
         self.h = C.c_void_p()
-        rc = self.L.rssync_create(C.byref(self.h))
+        if devices is None:
+            rc = self.L.rssync_create(C.byref(self.h))
+        else:
+            arr = (C.c_int * len(devices))(*[int(d) for d in devices])
+            rc = self.L.rssync_create_multi(arr, len(devices), C.byref(self.h))
         if rc != OK:
             msg = self.L.rssync_last_error(self.h).decode() if self.h else "no usable CUDA device (no CPU fallback)"
             raise RsSyncError(rc, msg)
@@ -310,6 +319,9 @@ class SyncProblem:
                                                         frame_begin, frame_end, search_step, search_radius, cn,
                                                         _dp(costs), _dp(delays)))
         return costs, delays
+
+    def device_count(self):
+        return self.L.rssync_device_count(self.h)
 
     def set_kernel_timing(self, enabled=True):
         self._check(self.L.rssync_set_kernel_timing(self.h, 1 if enabled else 0))

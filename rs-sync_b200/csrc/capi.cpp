@@ -23,6 +23,7 @@
 
 #include "engine.h"
 #include "host_ingest.h"
+#include "nccl_dyn.h"
 #include "rng.h"
 
 using rs::FrameDesc;
@@ -235,6 +236,21 @@ struct rssync_problem {
 
     uint64_t seed = 100, call_no = 0;
 
+    // ---- several GPUs behind one problem (rssync_create_multi) -----------------------------------
+    // The problem the caller holds is the PRIMARY: it takes every Set* call and holds the one
+    // complete copy of the inputs.  replicas[i] live on the other devices; before a compute call
+    // they receive the primary's finished device state (ray arena, orig / pos planes, spline
+    // records) by ncclBroadcast over NVLink -- `version` counts the primary's input changes,
+    // `synced_version` is the one a replica holds.  comms[0] is the primary's communicator.
+    std::vector<rssync_problem*> replicas;
+    std::vector<void*> comms;
+    bool is_replica = false, owns_stream = false;
+    bool force_single = false;  // the primary works alone (inside a call that has sharded the work itself)
+    uint64_t version = 0, synced_version = 0;
+    DevBuf<unsigned char> d_gather;   // G slices of {costs of the rank's delays, 2 flag words}
+    PinBuf<unsigned char> h_gather;
+    uint64_t nccl_calls = 0, broadcast_bytes = 0;
+
     // scratch
     DevBuf<FrameDesc> d_frames;
     DevBuf<double> d_delays, d_framecost, d_costs;
@@ -414,9 +430,15 @@ int require_gyro(rssync_problem* p, const char* who) {
     return RSSYNC_OK;
 }
 
+int multi_presync_grid(rssync_problem* p, int64_t fb, int64_t fe, const double* delays, int n,
+                       uint64_t stream_id, uint64_t call_no, uint64_t idx_base, double* costs,
+                       unsigned* flags_out);
+bool is_multi(const rssync_problem* p) { return !p->replicas.empty() && !p->force_single; }
+
 int presync_grid_impl(rssync_problem* p, int64_t fb, int64_t fe, const double* delays, int n,
                       uint64_t stream_id, uint64_t call_no, uint64_t idx_base, double* costs,
                       unsigned* flags_out) {
+    if (is_multi(p)) return multi_presync_grid(p, fb, fe, delays, n, stream_id, call_no, idx_base, costs, flags_out);
     if (int rc = require_gyro(p, "pre-sync")) return rc;
     if (n < 0) { p->err = "pre-sync: negative delay count"; return RSSYNC_E_INVALID; }
     if (flags_out) *flags_out = 0;
@@ -833,6 +855,231 @@ int sync_batch_impl(rssync_problem* p, int n, const double* initial, const int64
     return RSSYNC_OK;
 }
 
+// ---- several GPUs behind one problem ------------------------------------------------------------
+// The path shards by independent units: PreSync / DebugPreSync by offset range -- the
+// RNG is keyed by the GLOBAL offset index, every frame's reduction stays on one device, so the
+// sharded curve is bit-identical to one GPU's -- Sync and the windowed PreSync by syncpoint, the
+// orientation search by variant.  Exchanges: one grouped ncclBroadcast of the finished device state
+// whenever the inputs changed, and ONE ncclAllGather of the loss-curve slices per grid call, on
+// device buffers.  Sync's per-syncpoint results are produced by the host-side control loop of each
+// device's driver thread, i.e. they are born on the host: they are assembled there, no collective.
+#define NCCL_TRY(p, expr)                                                                        \
+    do {                                                                                         \
+        int r__ = (expr);                                                                        \
+        if (r__ != 0) {                                                                          \
+            (p)->err = std::string("NCCL error: ") + rs::Nccl::get()->GetErrorString(r__) + " at " #expr; \
+            return RSSYNC_E_CUDA;                                                                \
+        }                                                                                        \
+    } while (0)
+
+struct DeviceGuard {  // restores the calling thread's current device
+    int prev = 0;
+    DeviceGuard() { cudaGetDevice(&prev); }
+    ~DeviceGuard() { cudaSetDevice(prev); }
+};
+inline int n_ranks(const rssync_problem* p) { return 1 + (int)p->replicas.size(); }
+inline rssync_problem* rank_problem(rssync_problem* p, int i) { return i == 0 ? p : p->replicas[(size_t)i - 1]; }
+
+// bring every replica up to the primary's inputs
+int multi_replicate(rssync_problem* p) {
+    bool stale = false;
+    for (const rssync_problem* r : p->replicas) stale = stale || r->synced_version != p->version;
+    if (!stale) return RSSYNC_OK;
+    if (int rc = flush(p)) return rc;  // device 0 holds everything; its stream orders the broadcast behind the ingest
+    const rs::Nccl* nc = rs::Nccl::get();
+    DeviceGuard guard;
+    const size_t rays = p->dev_used;
+    for (rssync_problem* r : p->replicas) {
+        cudaSetDevice(r->device);
+        r->frames = p->frames;
+        r->q0 = p->q0; r->sr = p->sr; r->nq = p->nq;
+        r->used = p->used; r->dev_used = p->dev_used; r->total_rays = p->total_rays; r->garbage = p->garbage;
+        r->seed = p->seed;
+        cudaError_t e = cudaStreamSynchronize(r->stream);  // nothing of an earlier call still reads the buffers
+        if (e == cudaSuccess) e = r->d_rays.reserve(std::max<size_t>(rays, 1) * 8);
+        if (e == cudaSuccess) e = r->d_orig.reserve(std::max<size_t>(rays, 1));
+        if (e == cudaSuccess) e = r->d_pos.reserve(std::max<size_t>(rays, 1));
+        if (e == cudaSuccess) e = r->d_rec.reserve(std::max<size_t>(p->nq, 1) * 16);
+        if (e != cudaSuccess) {
+            p->err = std::string("CUDA error on device ") + std::to_string(r->device) + ": " + cudaGetErrorString(e);
+            return RSSYNC_E_CUDA;
+        }
+    }
+    NCCL_TRY(p, nc->GroupStart());
+    for (int i = 0; i < n_ranks(p); ++i) {
+        rssync_problem* q = rank_problem(p, i);
+        cudaSetDevice(q->device);
+        void* comm = p->comms[(size_t)i];
+        if (rays) {
+            NCCL_TRY(p, nc->Broadcast(q->d_rays.ptr, q->d_rays.ptr, rays * 8 * sizeof(double), rs::Nccl::kChar, 0, comm, q->stream));
+            NCCL_TRY(p, nc->Broadcast(q->d_orig.ptr, q->d_orig.ptr, rays * sizeof(int32_t), rs::Nccl::kChar, 0, comm, q->stream));
+            NCCL_TRY(p, nc->Broadcast(q->d_pos.ptr, q->d_pos.ptr, rays * sizeof(int32_t), rs::Nccl::kChar, 0, comm, q->stream));
+        }
+        if (p->nq)
+            NCCL_TRY(p, nc->Broadcast(q->d_rec.ptr, q->d_rec.ptr, p->nq * 16 * sizeof(double), rs::Nccl::kChar, 0, comm, q->stream));
+    }
+    NCCL_TRY(p, nc->GroupEnd());
+    for (rssync_problem* r : p->replicas) r->synced_version = p->version;
+    p->nccl_calls += 1;
+    p->broadcast_bytes += rays * (8 * sizeof(double) + 2 * sizeof(int32_t)) + p->nq * 16 * sizeof(double);
+    return RSSYNC_OK;
+}
+
+// one rank's share of a grid: kernel + per-delay reduction into d_costs_dst (device), flags into
+// d_flags_dst (2 words, device); nothing is copied back and nothing is waited for
+int grid_enqueue_rank(rssync_problem* q, const std::vector<FrameDesc>& sel, int max_n, const double* delays,
+                      int cnt, uint64_t stream_id, uint64_t call_no, uint64_t idx_base, int max_chunk,
+                      double* d_costs_dst, unsigned* d_flags_dst, bool timed) {
+    const int F = (int)sel.size();
+    CUDA_TRY(q, cudaMemsetAsync(d_flags_dst, 0, 2 * sizeof(unsigned), q->stream));
+    if (cnt <= 0) return RSSYNC_OK;
+    CUDA_TRY(q, q->d_frames.reserve(F));
+    CUDA_TRY(q, q->d_delays.reserve(cnt));
+    CUDA_TRY(q, q->d_framecost.reserve((size_t)F * cnt));
+    if (int rc = h2d(q, q->d_frames.ptr, sel.data(), sizeof(FrameDesc) * F)) return rc;
+    if (int rc = h2d(q, q->d_delays.ptr, delays, sizeof(double) * cnt)) return rc;
+    if (timed) CUDA_TRY(q, cudaEventRecord(q->ev0, q->stream));
+    rs::launch_presync_tasks(q->device_data(), q->d_frames.ptr, F, max_n, q->d_delays.ptr, cnt, q->seed, stream_id,
+                             call_no, idx_base, q->d_framecost.ptr, F, d_flags_dst, q->stream, nullptr, max_chunk);
+    if (timed) CUDA_TRY(q, cudaEventRecord(q->ev1, q->stream));
+    rs::launch_presync_reduce(q->d_framecost.ptr, F, cnt, d_costs_dst, q->stream);
+    CUDA_TRY(q, cudaGetLastError());
+    return RSSYNC_OK;
+}
+
+int multi_presync_grid(rssync_problem* p, int64_t fb, int64_t fe, const double* delays, int n,
+                       uint64_t stream_id, uint64_t call_no, uint64_t idx_base, double* costs,
+                       unsigned* flags_out) {
+    if (int rc = require_gyro(p, "pre-sync")) return rc;
+    if (n < 0) { p->err = "pre-sync: negative delay count"; return RSSYNC_E_INVALID; }
+    if (flags_out) *flags_out = 0;
+    if (n == 0) return RSSYNC_OK;
+    std::vector<FrameDesc> sel;
+    int max_n = 0;
+    if (int rc = select_frames(p, fb, fe, sel, max_n, "pre-sync")) return rc;
+    const int F = (int)sel.size();
+    if (F == 0) {  // the reference sums over no frames: cost 0 for every delay
+        std::fill(costs, costs + n, 0.0);
+        return RSSYNC_OK;
+    }
+    if ((long long)F * n > (1LL << 34)) { p->err = "pre-sync: grid too large"; return RSSYNC_E_INVALID; }
+    if (int rc = multi_replicate(p)) return rc;
+    double span = 0.0;
+    for (const FrameDesc& fd : sel) span = std::max(span, fd.ts_hi - fd.ts_lo);
+    const int max_chunk = rs::presync_max_chunk(delays, n, span, p->sr, max_n);
+    const rs::Nccl* nc = rs::Nccl::get();
+    const int G = n_ranks(p);
+    const int per = (n + G - 1) / G;  // delays per rank (the last ranks may hold fewer, or none)
+    const size_t slice = (size_t)per * sizeof(double) + 2 * sizeof(unsigned);
+    DeviceGuard guard;
+    for (int i = 0; i < G; ++i) {
+        rssync_problem* q = rank_problem(p, i);
+        cudaSetDevice(q->device);
+        const cudaError_t e = q->d_gather.reserve(slice * G);
+        if (e != cudaSuccess) { p->err = std::string("CUDA error: ") + cudaGetErrorString(e); return RSSYNC_E_CUDA; }
+        const int lo = std::min(n, i * per), cnt = std::min(per, n - lo);
+        unsigned char* mine = q->d_gather.ptr + slice * i;
+        const int rc = grid_enqueue_rank(q, sel, max_n, delays + lo, cnt, stream_id, call_no, idx_base + (uint64_t)lo,
+                                         max_chunk, reinterpret_cast<double*>(mine),
+                                         reinterpret_cast<unsigned*>(mine + (size_t)per * sizeof(double)),
+                                         i == 0 && p->kernel_timing);
+        if (rc) { if (q != p) p->err = q->err; return rc; }
+    }
+    // the one exchange of the call: every rank's slice {costs, flags} to every rank, in place
+    NCCL_TRY(p, nc->GroupStart());
+    for (int i = 0; i < G; ++i) {
+        rssync_problem* q = rank_problem(p, i);
+        cudaSetDevice(q->device);
+        NCCL_TRY(p, nc->AllGather(q->d_gather.ptr + slice * i, q->d_gather.ptr, slice, rs::Nccl::kChar, p->comms[(size_t)i], q->stream));
+    }
+    NCCL_TRY(p, nc->GroupEnd());
+    p->nccl_calls += 1;
+    cudaSetDevice(p->device);
+    CUDA_TRY(p, p->h_gather.reserve(slice * G));
+    if (int rc = d2h(p, p->h_gather.ptr, p->d_gather.ptr, slice * G)) return rc;
+    CUDA_TRY(p, cudaStreamSynchronize(p->stream));
+    unsigned flags = 0;
+    uint64_t exact = 0;
+    for (int i = 0; i < G; ++i) {
+        const int lo = std::min(n, i * per), cnt = std::min(per, n - lo);
+        const unsigned char* sl = p->h_gather.ptr + slice * i;
+        if (cnt > 0) std::memcpy(costs + lo, sl, sizeof(double) * (size_t)cnt);
+        unsigned fl[2];
+        std::memcpy(fl, sl + (size_t)per * sizeof(double), sizeof(fl));
+        flags |= fl[0];
+        exact += fl[1];
+    }
+    p->grid_tasks = (uint64_t)F * (uint64_t)n;
+    p->grid_exact_tasks = exact;
+    if (p->kernel_timing) {
+        float ms = 0.f;
+        if (cudaEventElapsedTime(&ms, p->ev0, p->ev1) == cudaSuccess) p->last_grid_ms = ms;
+    }
+    if (flags_out) *flags_out = flags;
+    return RSSYNC_OK;
+}
+
+// run fn(rank, problem, lo, cnt) for every rank's contiguous share of n units, the primary's in the
+// calling thread and each replica's in a thread of its own (the Sync driver is a host-side loop per
+// device); primary_last: the primary takes the LAST share instead of the first
+int multi_for_each_shard(rssync_problem* p, int n, bool primary_last,
+                         const std::function<int(rssync_problem*, int, int)>& fn) {
+    const int G = n_ranks(p);
+    std::vector<int> rcs((size_t)G, RSSYNC_OK);
+    std::vector<std::thread> th;
+    auto share = [&](int i, int& lo, int& cnt) {
+        const int k = primary_last ? (i == 0 ? G - 1 : i - 1) : i;  // position of rank i's share
+        lo = (int)((long long)n * k / G);
+        cnt = (int)((long long)n * (k + 1) / G) - lo;
+    };
+    for (int i = 1; i < G; ++i) {
+        int lo, cnt;
+        share(i, lo, cnt);
+        if (cnt == 0) continue;
+        rssync_problem* q = rank_problem(p, i);
+        th.emplace_back([&, q, i, lo, cnt]() {
+            cudaSetDevice(q->device);
+            rcs[(size_t)i] = fn(q, lo, cnt);
+        });
+    }
+    int lo, cnt;
+    share(0, lo, cnt);
+    p->force_single = true;
+    if (cnt) rcs[0] = fn(p, lo, cnt);
+    p->force_single = false;
+    for (auto& t : th) t.join();
+    for (int i = 0; i < G; ++i)
+        if (rcs[(size_t)i]) {
+            if (i) p->err = rank_problem(p, i)->err;
+            return rcs[(size_t)i];
+        }
+    return RSSYNC_OK;
+}
+
+int multi_sync_batch(rssync_problem* p, int n, const double* initial, const int64_t* fb, const int64_t* fe,
+                     const double* center, const double* radius, double* out_cost, double* out_delay,
+                     const uint64_t* call_nos) {
+    if (int rc = require_gyro(p, "sync")) return rc;
+    if (int rc = multi_replicate(p)) return rc;
+    std::vector<uint64_t> callno((size_t)n);
+    for (int s = 0; s < n; ++s) callno[(size_t)s] = call_nos ? call_nos[s] : p->call_no + (uint64_t)s;
+    if (!call_nos) p->call_no += (uint64_t)n;
+    for (int i = 0; i < n_ranks(p); ++i) rank_problem(p, i)->sync_outer = rank_problem(p, i)->sync_evals = 0;
+    const int rc = multi_for_each_shard(p, n, false, [&](rssync_problem* q, int lo, int cnt) {
+        return sync_batch_impl(q, cnt, initial + lo, fb + lo, fe + lo, center + lo, radius + lo, out_cost + lo,
+                               out_delay + lo, false, callno.data() + lo);
+    });
+    uint64_t outer = 0, evals = 0;
+    for (int i = 0; i < n_ranks(p); ++i) {
+        const rssync_problem* q = rank_problem(p, i);
+        outer = std::max(outer, q->sync_outer);
+        evals += q->sync_evals;
+    }
+    p->sync_outer = outer;
+    p->sync_evals = evals;
+    return rc;
+}
+
 }  // namespace
 
 // =============================================================================================
@@ -856,8 +1103,67 @@ int rssync_create(rssync_problem** out) {
     return RSSYNC_OK;
 }
 
+int rssync_create_multi(const int* devices, int n_devices, rssync_problem** out) {
+    if (!out) return RSSYNC_E_INVALID;
+    *out = nullptr;
+    if (!devices || n_devices < 1) return RSSYNC_E_INVALID;
+    for (int i = 0; i < n_devices; ++i)
+        for (int j = 0; j < i; ++j)
+            if (devices[i] == devices[j]) return RSSYNC_E_INVALID;
+    if (cudaSetDevice(devices[0]) != cudaSuccess) return RSSYNC_E_CUDA;
+    int rc = rssync_create(out);
+    rssync_problem* p = *out;
+    if (rc != RSSYNC_OK || n_devices == 1) return rc;
+    const rs::Nccl* nc = rs::Nccl::get();
+    if (!nc) {
+        p->err = "rssync_create_multi: libnccl.so.2 could not be loaded (needed for more than one device)";
+        return RSSYNC_E_CUDA;
+    }
+    for (int i = 1; i < n_devices; ++i) {
+        rssync_problem* r = nullptr;
+        if (cudaSetDevice(devices[i]) != cudaSuccess) rc = RSSYNC_E_CUDA;
+        if (rc == RSSYNC_OK) rc = rssync_create(&r);
+        if (rc == RSSYNC_OK && cudaStreamCreateWithFlags(&r->stream, cudaStreamNonBlocking) != cudaSuccess) rc = RSSYNC_E_CUDA;
+        if (rc != RSSYNC_OK) {
+            p->err = r && !r->err.empty() ? r->err : std::string("rssync_create_multi: device ") + std::to_string(devices[i]) + " is not usable";
+            if (r) rssync_destroy(r);
+            cudaSetDevice(devices[0]);
+            return rc;
+        }
+        r->is_replica = true;
+        r->owns_stream = true;
+        r->synced_version = ~0ull;
+        p->replicas.push_back(r);
+    }
+    p->comms.assign((size_t)n_devices, nullptr);
+    const int nr = nc->CommInitAll(p->comms.data(), n_devices, devices);
+    cudaSetDevice(devices[0]);
+    if (nr != 0) {
+        p->err = std::string("NCCL error: ") + nc->GetErrorString(nr) + " at ncclCommInitAll";
+        p->comms.clear();
+        return RSSYNC_E_CUDA;
+    }
+    return RSSYNC_OK;
+}
+
+int rssync_device_count(const rssync_problem* p) { return p ? 1 + (int)p->replicas.size() : 0; }
+
 void rssync_destroy(rssync_problem* p) {
     if (!p) return;
+    if (!p->replicas.empty() || !p->comms.empty()) {
+        int prev = 0;
+        cudaGetDevice(&prev);
+        const rs::Nccl* nc = rs::Nccl::get();
+        for (size_t i = 0; i < p->comms.size(); ++i)
+            if (nc && p->comms[i]) {
+                cudaSetDevice(i == 0 ? p->device : p->replicas[i - 1]->device);
+                nc->CommDestroy(p->comms[i]);
+            }
+        for (rssync_problem* r : p->replicas) rssync_destroy(r);
+        p->replicas.clear();
+        p->comms.clear();
+        cudaSetDevice(prev);
+    }
     cudaSetDevice(p->device);
     join_gyro(p);
     if (p->arena_copy_pending) cudaEventSynchronize(p->ev_arena);
@@ -882,6 +1188,8 @@ void rssync_destroy(rssync_problem* p) {
     p->d_frame_call.release(); p->d_win_begin.release();
     p->h_pix.release(); p->d_pix.release(); p->d_pixframes.release(); p->d_stage.release();
     p->d_flags.release(); p->h_stage.release(); p->d_probe.release();
+    p->d_gather.release(); p->h_gather.release();
+    if (p->owns_stream && p->stream) { cudaStreamSynchronize(p->stream); cudaStreamDestroy(p->stream); }
     for (SyncLane& L : p->lanes) L.release();
     if (p->ev_sync_ready) cudaEventDestroy(p->ev_sync_ready);
     if (p->ev0) cudaEventDestroy(p->ev0);
@@ -897,6 +1205,7 @@ int rssync_set_gyro_fixed(rssync_problem* p, const double* quats, size_t count, 
     if (count < 2) { p->err = "set-gyro-quaternions: need at least 2 samples"; return RSSYNC_E_INVALID; }
     if (count > (size_t)INT32_MAX) { p->err = "set-gyro-quaternions: too many samples"; return RSSYNC_E_INVALID; }
     join_gyro(p);
+    p->version++;
     p->sr = sample_rate;       // core_private.cpp:137
     p->q0 = first_timestamp;   // :138
     cudaSetDevice(p->device);
@@ -919,6 +1228,7 @@ int rssync_set_gyro_var(rssync_problem* p, const int64_t* ts, const double* quat
     if (s == rs::IngestStatus::OutOfOrder) return RSSYNC_E_ORDER;
     if (rq.size() / 4 > (size_t)INT32_MAX) { p->err = "set-gyro-quaternions: too many samples"; return RSSYNC_E_INVALID; }
     join_gyro(p);
+    p->version++;
     p->sr = sr;
     p->q0 = q0;
     cudaSetDevice(p->device);
@@ -1175,6 +1485,7 @@ int rssync_set_track(rssync_problem* p, int64_t frame, const double* ts_a, const
     const char* msg = nullptr;
     if (int rc = validate_track(ts_a, ts_b, rays_a, rays_b, count, &msg)) { p->err = msg; return rc; }
     if (int rc = wait_arena_copies(p)) return rc;
+    p->version++;
     FrameDesc* fd = nullptr;
     if (int rc = place_track(p, frame, count, &fd)) return rc;
     fill_track(p, fd, ts_a, ts_b, rays_a, rays_b, count, p->sort_scratch);
@@ -1188,6 +1499,7 @@ int rssync_set_track_batch(rssync_problem* p, size_t n_frames, const int64_t* fr
                            const size_t* counts, const double* ts_a, const double* ts_b,
                            const double* rays_a, const double* rays_b) {
     if (!p || (n_frames && (!frames || !counts))) return RSSYNC_E_INVALID;
+    p->version++;
     DebugTimer tm("set_track_batch");
     std::vector<size_t> at(n_frames + 1, 0);
     for (size_t i = 0; i < n_frames; ++i) at[i + 1] = at[i] + counts[i];
@@ -1330,6 +1642,7 @@ int rssync_set_track_pixels(rssync_problem* p, size_t n_frames, const int64_t* f
     if (!p) return RSSYNC_E_INVALID;
     if (n_frames == 0) return RSSYNC_OK;
     if (!frames || !counts || !frame_ts_a || !frame_ts_b || !points_a || !points_b || !lens) return RSSYNC_E_INVALID;
+    p->version++;
     const double lv[9] = {lens->readout, lens->fx, lens->fy, lens->cx, lens->cy, lens->k1, lens->k2, lens->k3, lens->k4};
     if (!all_finite(lv, 9) || !(image_rows > 0) || !std::isfinite(image_rows) || lens->fx == 0 || lens->fy == 0) {
         p->err = "set-track-pixels: bad lens profile or image height";
@@ -1466,6 +1779,16 @@ int rssync_presync_windows(rssync_problem* p, int n, double initial, const int64
     }
     const int D = rssync_presync_delays(initial, step, radius, nullptr, 0);
     if (D <= 0 || D > (1 << 28)) { p->err = "pre-sync: empty or oversized delay grid"; return RSSYNC_E_INVALID; }
+    if (is_multi(p) && n > 1) {  // windows are independent: shard them, explicit call numbers
+        if (int rc = multi_replicate(p)) return rc;
+        std::vector<uint64_t> callno((size_t)n);
+        for (int i = 0; i < n; ++i) callno[(size_t)i] = call_nos ? call_nos[i] : p->call_no + (uint64_t)i;
+        if (!call_nos) p->call_no += (uint64_t)n;
+        return multi_for_each_shard(p, n, false, [&](rssync_problem* q, int lo, int cnt) {
+            return rssync_presync_windows(q, cnt, initial, fb + lo, fe + lo, step, radius, callno.data() + lo,
+                                          out_cost + lo, out_delay + lo);
+        });
+    }
     std::vector<double> delays(D);
     rssync_presync_delays(initial, step, radius, delays.data(), D);
     std::vector<FrameDesc> all, sel;
@@ -1573,6 +1896,21 @@ int rssync_orientation_search_ex(rssync_problem* p, const double* timestamps_s, 
     if (!p || n_orient < 0) return RSSYNC_E_INVALID;
     if (n_orient == 0) return RSSYNC_OK;
     if (!timestamps_s || !gyro_xyz || !orientations || !out_cost || !out_delay) return RSSYNC_E_INVALID;
+    if (is_multi(p) && n_orient > 1) {
+        // variants are independent: shard them.  Every device sets its own gyro per variant, so the
+        // replicas' inputs are stale afterwards; the primary takes the LAST share, which leaves it
+        // holding the last variant's gyro as the single-device search does.
+        if (int rc = multi_replicate(p)) return rc;
+        std::vector<uint64_t> callno((size_t)n_orient);
+        for (int k = 0; k < n_orient; ++k) callno[(size_t)k] = call_nos ? call_nos[k] : p->call_no + (uint64_t)k;
+        const int rc = multi_for_each_shard(p, n_orient, true, [&](rssync_problem* q, int lo, int cnt) {
+            return rssync_orientation_search_ex(q, timestamps_s, gyro_xyz, count, orientations + lo, cnt, initial_delay,
+                                                fb, fe, step, radius, callno.data() + lo, out_cost + lo, out_delay + lo);
+        });
+        if (!call_nos) p->call_no += (uint64_t)n_orient;
+        for (rssync_problem* r : p->replicas) r->synced_version = ~0ull;
+        return rc;
+    }
     struct Prep {
         std::vector<double> sys;  // samples (nq x 4), rhs (nq x 4), diag (nq): the staging block's layout
         double sr = 0, q0 = 0;
@@ -1651,6 +1989,7 @@ int rssync_orientation_search_ex(rssync_problem* p, const double* timestamps_s, 
         CUDA_TRY(p, p->d_gyro.reserve(pr.sys.size()));
         CUDA_TRY(p, p->d_rec.reserve(pr.nq * 16));
         std::memcpy(p->h_gyro.ptr, pr.sys.data(), pr.sys.size() * sizeof(double));
+        p->version++;
         p->sr = pr.sr;
         p->q0 = pr.q0;
         p->nq = pr.nq;
@@ -1670,6 +2009,7 @@ int rssync_orientation_search_ex(rssync_problem* p, const double* timestamps_s, 
 int rssync_sync(rssync_problem* p, double initial, int64_t fb, int64_t fe, double center,
                 double radius, double* out_cost, double* out_delay) {
     if (!p || !out_cost || !out_delay) return RSSYNC_E_INVALID;
+    // one syncpoint is one unit of work: it runs on the primary device ("replicas only" at this granularity)
     return sync_batch_impl(p, 1, &initial, &fb, &fe, &center, &radius, out_cost, out_delay, true);
 }
 
@@ -1678,6 +2018,7 @@ int rssync_sync_batch(rssync_problem* p, int n, const double* initial, const int
                       double* out_cost, double* out_delay) {
     if (!p || n < 0) return RSSYNC_E_INVALID;
     if (n && (!initial || !fb || !fe || !center || !radius || !out_cost || !out_delay)) return RSSYNC_E_INVALID;
+    if (is_multi(p) && n > 1) return multi_sync_batch(p, n, initial, fb, fe, center, radius, out_cost, out_delay, nullptr);
     return sync_batch_impl(p, n, initial, fb, fe, center, radius, out_cost, out_delay, false);
 }
 
@@ -1686,6 +2027,7 @@ int rssync_sync_batch_ex(rssync_problem* p, int n, const double* initial, const 
                          const uint64_t* call_nos, double* out_cost, double* out_delay) {
     if (!p || n < 0) return RSSYNC_E_INVALID;
     if (n && (!initial || !fb || !fe || !center || !radius || !out_cost || !out_delay)) return RSSYNC_E_INVALID;
+    if (is_multi(p) && n > 1) return multi_sync_batch(p, n, initial, fb, fe, center, radius, out_cost, out_delay, call_nos);
     return sync_batch_impl(p, n, initial, fb, fe, center, radius, out_cost, out_delay, false, call_nos);
 }
 
@@ -1703,6 +2045,7 @@ int rssync_set_rng(rssync_problem* p, uint64_t seed, uint64_t call_no) {
     if (!p) return RSSYNC_E_INVALID;
     p->seed = seed;
     p->call_no = call_no;
+    for (rssync_problem* r : p->replicas) r->seed = seed;
     return RSSYNC_OK;
 }
 uint64_t rssync_call_counter(const rssync_problem* p) { return p ? p->call_no : 0; }

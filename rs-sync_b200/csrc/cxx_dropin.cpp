@@ -25,7 +25,19 @@ namespace {
 class SyncProblemB200 final : public ISyncProblem {
    public:
     SyncProblemB200() {
-        int rc = rssync_create(&p_);
+        // RSSYNC_DEVICES="0,1,2,3": spread the problem over those GPUs (rssync_create_multi), so that an
+        // unmodified core_testcode-style caller uses all of them; unset: the current device
+        std::vector<int> devs;
+        if (const char* e = std::getenv("RSSYNC_DEVICES")) {
+            for (const char* c = e; *c;) {
+                char* end = nullptr;
+                const long v = std::strtol(c, &end, 10);
+                if (end == c) break;
+                devs.push_back((int)v);
+                c = (*end == ',') ? end + 1 : end;
+            }
+        }
+        int rc = devs.size() > 1 ? rssync_create_multi(devs.data(), (int)devs.size(), &p_) : rssync_create(&p_);
         if (rc != RSSYNC_OK)
             panic_to_file(p_ ? rssync_last_error(p_) : "rssync: no usable CUDA device (there is no CPU fallback)");
     }
