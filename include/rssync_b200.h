@@ -202,8 +202,46 @@ typedef struct rssync_stats {
     uint64_t last_grid_tasks;       /* (delay, frame) tasks of the most recent PreSync grid      */
     uint64_t last_grid_exact_tasks; /* of those, tasks whose translation estimate was redone by
                                        the exact binary64 estimator (fp32 tournament undecided) */
+    /* evaluation accounting of the most recent Sync / Sync batch (SURVEY 8d "Algorithmic work for
+     * Sync"), in (syncpoint, frame) tasks: */
+    uint64_t sync_row_builds;   /* problem-matrix builds (opt_compute_problem, core_private.cpp:15-32) */
+    uint64_t sync_loss_evals;   /* objective evaluations outside L-BFGS: x0, x0 -/+ h, Backtrack's
+                                   trial points, the final objective                               */
+    uint64_t sync_init_tasks;   /* estimator runs of the initialisation, 200 hypotheses each (:127)  */
+    uint64_t sync_outer_total;  /* outer iterations summed over the batch's syncpoints             */
+    uint64_t nccl_calls;        /* collectives (grouped calls) issued by a multi-device problem     */
+    uint64_t broadcast_bytes;   /* bytes per replica replicated from the primary so far             */
 } rssync_stats;
 int rssync_get_stats(const rssync_problem* p, rssync_stats* out);
+
+/* ---- moving a problem's finished device state (replication without re-ingesting) ---------
+ * A problem that has ingested its inputs holds, on its device: the ray arena (arena_rays x 8
+ * doubles in 2 KB tiles), the orig / pos planes (arena_rays int32 each) and the spline records
+ * (gyro_samples x 16 doubles).  rssync_device_state flushes pending host data and returns those
+ * device pointers and sizes; rssync_frame_table returns the host-side frame table (returns the
+ * number of frames; fills at most cap); rssync_adopt_state prepares ANOTHER problem (other GPU or
+ * other process) to hold a copy: it registers the frame table and sizes and allocates the buffers,
+ * whose pointers rssync_device_state then returns for the caller to fill by whatever transport
+ * it has (ncclBroadcast over NVLink in bench.py; rssync_create_multi does the same internally).
+ * Results of the adopting problem equal the source's bit for bit. */
+typedef struct rssync_frame_desc {
+    int64_t id;
+    int32_t off, n;
+    double ts_lo, ts_hi;
+} rssync_frame_desc;
+typedef struct rssync_device_state_t {
+    void* rays;
+    void* orig;
+    void* pos;
+    void* spline_records;
+    size_t arena_rays, gyro_samples;
+    double sample_rate, first_timestamp;
+} rssync_device_state_t;
+int rssync_frame_table(const rssync_problem* p, rssync_frame_desc* out, size_t cap);
+int rssync_device_state(rssync_problem* p, rssync_device_state_t* out);
+int rssync_adopt_state(rssync_problem* p, const rssync_frame_desc* frames, size_t n_frames,
+                       size_t arena_rays, size_t gyro_samples, double sample_rate,
+                       double first_timestamp);
 
 /* FP64 FMA throughput of the current device in TFLOP/s (FMA = 2 flop): the measured denominator
  * of the FP64 roofline. */

@@ -36,7 +36,7 @@ C_ABI_SYMBOLS = [
     "rssync_probe_lbfgs", "rssync_probe_log1p", "rssync_set_track_batch", "rssync_set_kernel_timing",
     "rssync_sync_batch_ex", "rssync_probe_guess_motion_ex", "rssync_integrate_gyro",
     "rssync_orientation_search", "rssync_orientation_search_ex", "rssync_presync_windows", "rssync_set_track_pixels",
-    "rssync_create_multi", "rssync_device_count",
+    "rssync_create_multi", "rssync_device_count", "rssync_frame_table", "rssync_device_state", "rssync_adopt_state",
 ]
 # Itanium-ABI symbols of the C++ drop-in face (same set the reference's librssync_core exports)
 CXX_ABI_SYMBOLS = [
@@ -50,7 +50,21 @@ class Stats(C.Structure):
         "kernel_launches", "h2d_bytes", "d2h_bytes", "frames", "rays", "gyro_samples",
         "sync_outer_iters", "sync_lbfgs_evals")] + [("last_grid_kernel_ms", C.c_double),
                                                      ("last_grid_tasks", C.c_uint64),
-                                                     ("last_grid_exact_tasks", C.c_uint64)]
+                                                     ("last_grid_exact_tasks", C.c_uint64)] + [
+        (n, C.c_uint64) for n in ("sync_row_builds", "sync_loss_evals", "sync_init_tasks", "sync_outer_total",
+                                  "nccl_calls", "broadcast_bytes")]
+
+
+class FrameDesc(C.Structure):
+    """rssync_frame_desc: one tracked frame inside the device arena"""
+    _fields_ = [("id", C.c_int64), ("off", C.c_int32), ("n", C.c_int32), ("ts_lo", C.c_double), ("ts_hi", C.c_double)]
+
+
+class DeviceState(C.Structure):
+    """rssync_device_state_t: device pointers and sizes of a problem's finished inputs"""
+    _fields_ = [("rays", C.c_void_p), ("orig", C.c_void_p), ("pos", C.c_void_p), ("spline_records", C.c_void_p),
+                ("arena_rays", C.c_size_t), ("gyro_samples", C.c_size_t), ("sample_rate", C.c_double),
+                ("first_timestamp", C.c_double)]
 
 
 class Lens(C.Structure):
@@ -80,6 +94,9 @@ def load_library():
     L.rssync_create.argtypes = [C.POINTER(P)]
     L.rssync_create_multi.argtypes = [C.POINTER(C.c_int), C.c_int, C.POINTER(P)]
     L.rssync_device_count.argtypes = [P]
+    L.rssync_frame_table.argtypes = [P, C.POINTER(FrameDesc), C.c_size_t]
+    L.rssync_device_state.argtypes = [P, C.POINTER(DeviceState)]
+    L.rssync_adopt_state.argtypes = [P, C.POINTER(FrameDesc), C.c_size_t, C.c_size_t, C.c_size_t, C.c_double, C.c_double]
     L.rssync_destroy.argtypes = [P]
     L.rssync_destroy.restype = None
     L.rssync_last_error.argtypes = [P]
@@ -322,6 +339,32 @@ class SyncProblem:
 
     def device_count(self):
         return self.L.rssync_device_count(self.h)
+
+    # ---- moving the finished device state (replication without re-ingesting) ----------------
+    def frame_table(self):
+        """host-side frame table as a numpy structured array (id, off, n, ts_lo, ts_hi)"""
+        n = self.L.rssync_frame_table(self.h, None, 0)
+        arr = (FrameDesc * max(n, 1))()
+        self.L.rssync_frame_table(self.h, arr, n)
+        dt = np.dtype([("id", "<i8"), ("off", "<i4"), ("n", "<i4"), ("ts_lo", "<f8"), ("ts_hi", "<f8")])
+        return np.frombuffer(bytes(arr), dtype=dt, count=n).copy()
+
+    def device_state(self):
+        """flush, then {rays, orig, pos, spline_records: (device pointer, bytes)} + sizes"""
+        st = DeviceState()
+        self._check(self.L.rssync_device_state(self.h, C.byref(st)))
+        return {"rays": (st.rays, st.arena_rays * 64), "orig": (st.orig, st.arena_rays * 4),
+                "pos": (st.pos, st.arena_rays * 4), "spline_records": (st.spline_records, st.gyro_samples * 128),
+                "arena_rays": st.arena_rays, "gyro_samples": st.gyro_samples, "sample_rate": st.sample_rate,
+                "first_timestamp": st.first_timestamp}
+
+    def adopt_state(self, frame_table, arena_rays, gyro_samples, sample_rate, first_timestamp):
+        """prepare this problem to hold a copy of another problem's device state (the buffers are
+        allocated here; fill them through device_state()'s pointers)"""
+        ft = np.ascontiguousarray(frame_table)
+        self._check(self.L.rssync_adopt_state(self.h, ft.ctypes.data_as(C.POINTER(FrameDesc)), ft.shape[0],
+                                              int(arena_rays), int(gyro_samples), float(sample_rate),
+                                              float(first_timestamp)))
 
     def set_kernel_timing(self, enabled=True):
         self._check(self.L.rssync_set_kernel_timing(self.h, 1 if enabled else 0))

@@ -144,7 +144,7 @@ struct SyncLane {
     size_t in_doubles = 0, out_doubles = 0;
     rs::SyncBatchDev b{};
     std::vector<SyncPointState> st;
-    std::vector<int> h_stats, local_sp;
+    std::vector<int> h_stats, local_sp, sp_frames;  // sp_frames[s]: frames (tasks) of syncpoint s
     const unsigned char* h_active = nullptr;
     bool many_tasks = false;  // which build of the L-BFGS kernel the lane launches (engine.cu LbfgsCfg)
     // one outer iteration (copy in, four kernels, copy out) as an instantiated CUDA graph; valid as
@@ -271,6 +271,11 @@ struct rssync_problem {
     std::vector<std::pair<double, int32_t>> sort_scratch;
     std::vector<double> trace_delay, trace_step;
     uint64_t h2d = 0, d2h = 0, sync_outer = 0, sync_evals = 0;
+    // evaluation accounting of the most recent Sync / Sync batch, in (syncpoint, frame) tasks:
+    // problem-matrix builds, objective evaluations outside L-BFGS (x0, x0 -/+ h, Backtrack's trial
+    // points, the final objective), estimator runs of the initialisation (200 hypotheses each), and
+    // the outer iterations summed over syncpoints
+    uint64_t sync_row_builds = 0, sync_loss_evals = 0, sync_init_tasks = 0, sync_outer_total = 0;
     bool kernel_timing = false;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     double last_grid_ms = 0.0;
@@ -666,6 +671,17 @@ int sync_lane_launch(rssync_problem* p, SyncLane& L, const rs::DeviceData& dd, b
     }
     L.h_active = ha;
     const bool finish = n_active == 0 || L.iters >= 400;  // :309
+    if (!finish) {
+        uint64_t tasks = 0;
+        for (int s = 0; s < n; ++s)
+            if (ha[s]) tasks += (uint64_t)L.sp_frames[(size_t)s];
+        p->sync_row_builds += tasks * (4 + kTrials);  // at the delay (L-BFGS), x0, x0 -/+ h, the trial points
+        p->sync_loss_evals += tasks * (3 + kTrials);
+        p->sync_outer_total += (uint64_t)n_active;
+    } else {
+        p->sync_row_builds += (uint64_t)L.T;  // the final objective (:333)
+        p->sync_loss_evals += (uint64_t)L.T;
+    }
     if (finish) {
         // {simple_objective(gyro_delay), gyro_delay}  (:333)
         for (int s = 0; s < n; ++s) ha[s] = 1;
@@ -788,6 +804,9 @@ int sync_batch_impl(rssync_problem* p, int n, const double* initial, const int64
     if (record_trace) { p->trace_delay.clear(); p->trace_step.clear(); }
     p->sync_outer = 0;
     p->sync_evals = 0;
+    p->sync_row_builds = p->sync_loss_evals = p->sync_outer_total = 0;
+    p->sync_init_tasks = (uint64_t)tasks.size();
+    p->sync_row_builds += (uint64_t)tasks.size();  // GuessMotion / GuessK build the rows once (:125-133 builds them twice)
 
     if (!p->ev_sync_ready) CUDA_TRY(p, cudaEventCreateWithFlags(&p->ev_sync_ready, cudaEventDisableTiming));
     CUDA_TRY(p, cudaEventRecord(p->ev_sync_ready, p->stream));
@@ -810,6 +829,8 @@ int sync_batch_impl(rssync_problem* p, int n, const double* initial, const int64
         int max_n = 0;
         lane_sp_begin[g].resize(L.n + 1);
         for (int s = 0; s <= L.n; ++s) lane_sp_begin[g][s] = sp_first[L.s0 + s] - L.t0;
+        L.sp_frames.resize((size_t)L.n);
+        for (int s = 0; s < L.n; ++s) L.sp_frames[(size_t)s] = sp_first[L.s0 + s + 1] - sp_first[L.s0 + s];
         for (int s = 0; s < L.n; ++s) max_n = std::max(max_n, sp_max_n[L.s0 + s]);
         L.local_sp.resize(L.T);
         for (int t = 0; t < L.T; ++t) {
@@ -1064,19 +1085,24 @@ int multi_sync_batch(rssync_problem* p, int n, const double* initial, const int6
     std::vector<uint64_t> callno((size_t)n);
     for (int s = 0; s < n; ++s) callno[(size_t)s] = call_nos ? call_nos[s] : p->call_no + (uint64_t)s;
     if (!call_nos) p->call_no += (uint64_t)n;
-    for (int i = 0; i < n_ranks(p); ++i) rank_problem(p, i)->sync_outer = rank_problem(p, i)->sync_evals = 0;
+    for (int i = 0; i < n_ranks(p); ++i) {
+        rssync_problem* q = rank_problem(p, i);
+        q->sync_outer = q->sync_evals = q->sync_row_builds = q->sync_loss_evals = q->sync_init_tasks = q->sync_outer_total = 0;
+    }
     const int rc = multi_for_each_shard(p, n, false, [&](rssync_problem* q, int lo, int cnt) {
         return sync_batch_impl(q, cnt, initial + lo, fb + lo, fe + lo, center + lo, radius + lo, out_cost + lo,
                                out_delay + lo, false, callno.data() + lo);
     });
-    uint64_t outer = 0, evals = 0;
+    uint64_t outer = 0, evals = 0, acc[4] = {0, 0, 0, 0};
     for (int i = 0; i < n_ranks(p); ++i) {
         const rssync_problem* q = rank_problem(p, i);
         outer = std::max(outer, q->sync_outer);
         evals += q->sync_evals;
+        acc[0] += q->sync_row_builds; acc[1] += q->sync_loss_evals; acc[2] += q->sync_init_tasks; acc[3] += q->sync_outer_total;
     }
     p->sync_outer = outer;
     p->sync_evals = evals;
+    p->sync_row_builds = acc[0]; p->sync_loss_evals = acc[1]; p->sync_init_tasks = acc[2]; p->sync_outer_total = acc[3];
     return rc;
 }
 
@@ -2063,6 +2089,72 @@ int rssync_flush(rssync_problem* p) {
     return RSSYNC_OK;
 }
 
+int rssync_frame_table(const rssync_problem* p, rssync_frame_desc* out, size_t cap) {
+    if (!p) return 0;
+    size_t i = 0;
+    for (const auto& kv : p->frames) {
+        if (out && i < cap) {
+            const FrameDesc& fd = kv.second;
+            out[i] = rssync_frame_desc{fd.id, fd.off, fd.n, fd.ts_lo, fd.ts_hi};
+        }
+        ++i;
+    }
+    return (int)i;
+}
+
+int rssync_device_state(rssync_problem* p, rssync_device_state_t* out) {
+    if (!p || !out) return RSSYNC_E_INVALID;
+    if (int rc = flush(p)) return rc;
+    CUDA_TRY(p, cudaStreamSynchronize(p->stream));
+    out->rays = p->d_rays.ptr;
+    out->orig = p->d_orig.ptr;
+    out->pos = p->d_pos.ptr;
+    out->spline_records = p->d_rec.ptr;
+    out->arena_rays = p->dev_used;
+    out->gyro_samples = p->nq;
+    out->sample_rate = p->sr;
+    out->first_timestamp = p->q0;
+    return RSSYNC_OK;
+}
+
+int rssync_adopt_state(rssync_problem* p, const rssync_frame_desc* frames, size_t n_frames, size_t arena_rays,
+                       size_t gyro_samples, double sample_rate, double first_timestamp) {
+    if (!p || (n_frames && !frames)) return RSSYNC_E_INVALID;
+    if (gyro_samples > (size_t)INT32_MAX || arena_rays > (size_t)INT32_MAX) { p->err = "adopt-state: too large"; return RSSYNC_E_INVALID; }
+    join_gyro(p);
+    cudaSetDevice(p->device);
+    if (int rc = drain_in_flight(p)) return rc;
+    if (int rc = wait_arena_copies(p)) return rc;
+    CUDA_TRY(p, cudaStreamSynchronize(p->stream));
+    if (p->gyro_stream) CUDA_TRY(p, cudaStreamSynchronize(p->gyro_stream));
+    p->version++;
+    p->pending.clear();
+    p->gyro_dirty = false;
+    p->frames.clear();
+    p->total_rays = 0;
+    for (size_t i = 0; i < n_frames; ++i) {
+        const rssync_frame_desc& f = frames[i];
+        if (f.n < 0 || f.n > rs::kMaxRaysPerFrame || f.off < 0 || (f.off & 31) ||
+            (size_t)f.off + (size_t)(f.n + 31) / 32 * 32 > arena_rays) {
+            p->err = "adopt-state: frame outside the arena";
+            return RSSYNC_E_INVALID;
+        }
+        p->frames[f.id] = FrameDesc{f.id, f.off, f.n, f.ts_lo, f.ts_hi};
+        p->total_rays += (size_t)f.n;
+    }
+    p->used = p->dev_used = arena_rays;
+    p->garbage = 0;
+    p->nq = gyro_samples;
+    p->sr = sample_rate;
+    p->q0 = first_timestamp;
+    CUDA_TRY(p, p->d_rays.reserve(std::max<size_t>(arena_rays, 1) * 8));
+    CUDA_TRY(p, p->d_orig.reserve(std::max<size_t>(arena_rays, 1)));
+    CUDA_TRY(p, p->d_pos.reserve(std::max<size_t>(arena_rays, 1)));
+    CUDA_TRY(p, p->d_rec.reserve(std::max<size_t>(gyro_samples, 1) * 16));
+    // the pinned host mirror belongs to frames set one by one; an adopted arena has none
+    return RSSYNC_OK;
+}
+
 int rssync_get_stats(const rssync_problem* p, rssync_stats* out) {
     if (!p || !out) return RSSYNC_E_INVALID;
     out->kernel_launches = rs::launch_count();
@@ -2076,6 +2168,12 @@ int rssync_get_stats(const rssync_problem* p, rssync_stats* out) {
     out->last_grid_kernel_ms = p->last_grid_ms;
     out->last_grid_tasks = p->grid_tasks;
     out->last_grid_exact_tasks = p->grid_exact_tasks;
+    out->sync_row_builds = p->sync_row_builds;
+    out->sync_loss_evals = p->sync_loss_evals;
+    out->sync_init_tasks = p->sync_init_tasks;
+    out->sync_outer_total = p->sync_outer_total;
+    out->nccl_calls = p->nccl_calls;
+    out->broadcast_bytes = p->broadcast_bytes;
     return RSSYNC_OK;
 }
 

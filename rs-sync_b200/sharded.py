@@ -20,18 +20,21 @@ def shard_range(n, rank, world):
     return n * rank // world, n * (rank + 1) // world
 
 
-def _gather_variable(local, group_size, device, dist):
+def _gather_rows(local, sizes, group_size, device, dist):
+    """ONE collective: rank r contributes sizes[r] rows of `local`'s width (the shard sizes follow
+    from (n, rank, world), so they need no exchange); returns the rows of all ranks, concatenated.
+    The rows are born on the host (the engine's C ABI returns host arrays), NCCL moves device
+    memory: one copy each way around the collective."""
     import torch
-    n = torch.tensor([local.shape[0]], dtype=torch.int64, device=device)
-    sizes = [torch.zeros(1, dtype=torch.int64, device=device) for _ in range(group_size)]
-    dist.all_gather(sizes, n)
-    sizes = [int(s.item()) for s in sizes]
-    m = max(sizes) if sizes else 0
-    buf = torch.zeros(max(m, 1), dtype=torch.float64, device=device)
-    buf[:local.shape[0]] = torch.from_numpy(np.ascontiguousarray(local, dtype=np.float64)).to(device)
-    out = [torch.zeros(max(m, 1), dtype=torch.float64, device=device) for _ in range(group_size)]
+    local = np.ascontiguousarray(local, dtype=np.float64).reshape(local.shape[0], -1)
+    cols = local.shape[1]
+    m = max(max(sizes), 1)
+    buf = torch.zeros((m, cols), dtype=torch.float64, device=device)
+    if local.shape[0]:
+        buf[:local.shape[0]] = torch.from_numpy(local).to(device)
+    out = [torch.empty((m, cols), dtype=torch.float64, device=device) for _ in range(group_size)]
     dist.all_gather(out, buf)
-    return np.concatenate([o[:s].cpu().numpy() for o, s in zip(out, sizes)])
+    return np.concatenate([out[r][:sizes[r]].cpu().numpy() for r in range(group_size)], axis=0)
 
 
 def presync_grid_sharded(problem, frame_begin, frame_end, delays, *, stream=1, call_no=0, rank=0, world=1,
@@ -45,7 +48,8 @@ def presync_grid_sharded(problem, frame_begin, frame_end, delays, *, stream=1, c
     if world == 1:
         return np.asarray(local)
     import torch.distributed as dist
-    return _gather_variable(np.asarray(local), world, device, dist)
+    sizes = [shard_range(delays.shape[0], r, world)[1] - shard_range(delays.shape[0], r, world)[0] for r in range(world)]
+    return _gather_rows(np.asarray(local), sizes, world, device, dist)[:, 0]
 
 
 def argmin_cost_delay(costs, delays):
@@ -85,13 +89,13 @@ def sync_sharded(problem, initial_delay, frame_begin, frame_end, search_center, 
     if world == 1:
         return cost, delay
     import torch.distributed as dist
-    allc = _gather_variable(cost, world, device, dist)
-    alld = _gather_variable(delay, world, device, dist)
+    both = _gather_rows(np.stack([cost, delay], axis=1), [len(range(r, n, world)) for r in range(world)], world,
+                        device, dist)
     # rank r contributed syncpoints r, r+world, ...: undo the round-robin
     order = np.concatenate([np.arange(r, n, world) for r in range(world)])
     outc, outd = np.empty(n), np.empty(n)
-    outc[order] = allc
-    outd[order] = alld
+    outc[order] = both[:, 0]
+    outd[order] = both[:, 1]
     return outc, outd
 
 
@@ -122,10 +126,66 @@ def orientation_search_sharded(problem, search_fn, orientations, *, seed, call_n
     if world == 1:
         return cost, delay
     import torch.distributed as dist
-    allc = _gather_variable(cost, world, device, dist)
-    alld = _gather_variable(delay, world, device, dist)
+    both = _gather_rows(np.stack([cost, delay], axis=1), [len(range(r, n, world)) for r in range(world)], world,
+                        device, dist)
     order = np.concatenate([np.arange(r, n, world) for r in range(world)])
     outc, outd = np.empty(n), np.empty(n)
-    outc[order] = allc
-    outd[order] = alld
+    outc[order] = both[:, 0]
+    outd[order] = both[:, 1]
     return outc, outd
+
+
+class _DevicePtr:
+    """a raw device allocation as something torch can wrap (CUDA array interface, bytes)"""
+
+    def __init__(self, ptr, nbytes):
+        self.__cuda_array_interface__ = {"shape": (int(nbytes),), "typestr": "|u1", "data": (int(ptr), False),
+                                         "version": 2}
+
+
+def device_buffers(problem):
+    """the problem's finished device state as uint8 torch tensors that ALIAS the engine's buffers
+    (ray arena, orig / pos planes, spline records), plus the sizes an adopting problem needs"""
+    import torch
+    st = problem.device_state()
+    bufs = {}
+    for k in ("rays", "orig", "pos", "spline_records"):
+        ptr, nbytes = st[k]
+        bufs[k] = torch.as_tensor(_DevicePtr(ptr, nbytes), device="cuda") if nbytes else None
+    return bufs, st
+
+
+def replicate_state(problem, *, rank, world, device, src=0):
+    """Inputs ingested on rank `src` only: its finished device state goes to every other rank's
+    problem over NVLink (NCCL broadcast of the frame table, then of the four device buffers, which
+    are the engines' own allocations -- no staging copy), instead of every rank validating, staging
+    and uploading the same host data.  Afterwards all ranks compute identical results."""
+    import torch
+    import torch.distributed as dist
+    if world == 1:
+        return
+    if rank == src:
+        ft = problem.frame_table()
+        bufs, st = device_buffers(problem)
+        head = torch.tensor([ft.shape[0], st["arena_rays"], st["gyro_samples"]], dtype=torch.int64, device=device)
+        meta = torch.tensor([st["sample_rate"], st["first_timestamp"]], dtype=torch.float64, device=device)
+    else:
+        head = torch.zeros(3, dtype=torch.int64, device=device)
+        meta = torch.zeros(2, dtype=torch.float64, device=device)
+    dist.broadcast(head, src)
+    dist.broadcast(meta, src)
+    nf, arena, nq = (int(x) for x in head.cpu())
+    if rank == src:
+        ftt = torch.from_numpy(ft.view(np.uint8).reshape(-1).copy()).to(device)
+    else:
+        ftt = torch.empty(nf * 32, dtype=torch.uint8, device=device)
+    dist.broadcast(ftt, src)
+    if rank != src:
+        dt = np.dtype([("id", "<i8"), ("off", "<i4"), ("n", "<i4"), ("ts_lo", "<f8"), ("ts_hi", "<f8")])
+        sr, t0 = (float(x) for x in meta.cpu())
+        problem.adopt_state(np.frombuffer(ftt.cpu().numpy().tobytes(), dtype=dt), arena, nq, sr, t0)
+        bufs, _ = device_buffers(problem)
+    for k in ("rays", "orig", "pos", "spline_records"):
+        if bufs[k] is not None:
+            dist.broadcast(bufs[k], src)
+    torch.cuda.synchronize()

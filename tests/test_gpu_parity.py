@@ -576,3 +576,35 @@ def test_pixel_front_end_matches_host_rays(rsb, oracle_loader, synth_mod):
     with pytest.raises(rsb.RsSyncError):
         pix.set_track_pixels(w.frame_ids[:1], counts[:1], ta[:1], tb[:1], w.px_a[:1], w.px_b[:1],
                              (0.01, 0.0, 1.0, 0, 0, 0, 0, 0, 0), synth_mod.HEIGHT)
+
+
+def test_adopted_device_state_reproduces_the_source(rsb, w_small):
+    """replication without re-ingesting (what bench.py does across ranks with an NCCL broadcast and
+    rssync_create_multi does inside the library): a second problem adopts the frame table and sizes,
+    its buffers are filled device-to-device, and every result equals the source's bit for bit"""
+    import importlib
+    import torch
+    sharded = importlib.import_module("rs-sync_b200.sharded")
+    w = w_small
+    a = rsb.SyncProblem(seed=100).load(w, bulk=True)
+    ft = a.frame_table()
+    assert ft.shape[0] == w.n_frames and np.array_equal(ft["id"], w.frame_ids) and np.all(ft["n"] == w.n_rays)
+    src, st = sharded.device_buffers(a)
+    b = rsb.SyncProblem(seed=100)
+    b.adopt_state(ft, st["arena_rays"], st["gyro_samples"], st["sample_rate"], st["first_timestamp"])
+    dst, st_b = sharded.device_buffers(b)
+    for k in src:
+        assert dst[k].data_ptr() != src[k].data_ptr() and dst[k].numel() == src[k].numel()
+        dst[k].copy_(src[k])
+    torch.cuda.synchronize()
+    fb, fe = int(w.frame_ids[0]), int(w.frame_ids[-1]) + 1
+    delays = np.linspace(-0.05, 0.05, 21)
+    assert np.array_equal(a.presync_grid(fb, fe, delays, call_no=2), b.presync_grid(fb, fe, delays, call_no=2))
+    for p in (a, b):
+        p.set_rng(100, 30)
+    assert a.Sync(0.038, fb, fb + 30, 0.0, 0.2) == b.Sync(0.038, fb, fb + 30, 0.0, 0.2)
+    # the adopting problem stays a full problem: a frame set afterwards lands in its own arena
+    for p in (a, b):
+        p.SetTrackResult(10 ** 5, w.ts_a[3], w.ts_b[3], w.rays_a[3], w.rays_b[3], w.n_rays)
+    assert np.array_equal(a.presync_grid(10 ** 5, 10 ** 5 + 1, delays), b.presync_grid(10 ** 5, 10 ** 5 + 1, delays))
+    assert b.stats()["frames"] == w.n_frames + 1
