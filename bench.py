@@ -44,13 +44,18 @@ def parse():
     ap.add_argument("--no-sync", action="store_true", help="skip the syncpoints/s section")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline section")
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
+    ap.add_argument("--scale-configs", action="store_true",
+                    help="also run C3 (strong scaling) and C4 with 900 syncpoints at N = 1 (they always run for N > 1)")
     return ap.parse_args()
 
 
 def make_workload(name, n_gpus):
     synth = importlib.import_module("rs-sync_b200.synth")
+    # weak scaling widens the grid with the GPU count (radius 0.2 s per GPU); the gyro track is
+    # generated for the widest case (8 GPUs) at every N, so the scene -- and with it the syncpoint
+    # loop's results -- are the same for every N
     radius = 0.2 * n_gpus if name in ("C1", "C2") else None
-    w = synth.make_workload(name, radius=radius)
+    w = synth.make_workload(name, radius=radius, gyro_pad_radius=1.6 if name in ("C1", "C2") else None)
     return w
 
 
@@ -183,24 +188,6 @@ def full_size_parity(prob, w, delays, pkg):
             "ok": bool(worst <= 1e-9)}
 
 
-def cpu_sync_baseline(w):
-    """syncpoints/s of the CPU arm on ONE syncpoint (PreSync on the window + 4 chained Sync, all host
-    threads over frames like the reference's par loops).  The oracle port is used: the reference
-    itself builds dense N x N Jacobian factors per evaluation (core_private.cpp:99-114) and needs
-    minutes per syncpoint at N = 200."""
-    from oracle import loader
-    threads = os.cpu_count() or 1
-    p = loader.OracleProblem(threads=threads, seed=100).load_range(w, w.syncpoints()[0], w.sync_window + 1)
-    pos = w.syncpoints()[0]
-    t = time.perf_counter()
-    d = p.PreSync(0.0, pos, pos + w.sync_window, w.presync_step, 0.2)[1]
-    for _ in range(4):
-        d = p.Sync(d, pos, pos + w.sync_window, 0.0, 0.2)[1]
-    dt = time.perf_counter() - t
-    return {"value": 1.0 / dt, "unit": "syncpoints/s", "cores": threads, "kind": "port",
-            "sample": f"1 of {len(w.syncpoints())} syncpoints ({dt:.2f} s)"}
-
-
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -233,6 +220,133 @@ def run_reference(args):
 
 
 # ------------------------------------------------------------------------------------------
+E_ROW, E_LOSS, E_GRAD = 145.0, 10.0, 14.0   # flop per (frame, ray) row build / loss cell / gradient
+E_EST = lambda iters: 8.0 + 6.0 * iters + 2.0  # row normalisation + iters x (dot3, square) + hypothesis set-up
+
+
+def sync_flops(acc, n_rays, presync_cells):
+    """algorithmic FP64 flop of a syncpoint loop from the engine's evaluation counters"""
+    return (FLOP_PER_CELL * presync_cells +
+            n_rays * (E_ROW * acc["sync_row_builds"] + E_LOSS * acc["sync_loss_evals"] +
+                      (E_LOSS + E_GRAD) * acc["sync_lbfgs_evals"] + E_EST(200) * acc["sync_init_tasks"]))
+
+
+def syncpoint_loop(prob, sps, win, step, radius, idx, n_total):
+    """core_testcode.cpp:303-316 for the syncpoints idx (indices into sps): PreSync on every window in
+    one grid launch, then 4 chained Sync calls advanced as batches.  Call numbers are those of ONE
+    problem running all n_total syncpoints (PreSync s -> s, Sync round r -> n_total (r + 1) + s), so any
+    sharding of idx over ranks computes the same numbers.  Returns (delays, costs, counters)."""
+    idx = np.asarray(idx, dtype=np.int64)
+    acc = {k: 0 for k in ("sync_row_builds", "sync_loss_evals", "sync_lbfgs_evals", "sync_init_tasks", "sync_outer_total")}
+    if idx.size == 0:
+        return np.empty(0), np.empty(0), acc
+    fbs = np.asarray(sps, dtype=np.int64)[idx]
+    _, d = prob.presync_windows(0.0, fbs, fbs + win, step, radius, call_nos=idx.astype(np.uint64))
+    c = None
+    for r in range(4):
+        c, d = prob.sync_batch(d, fbs, fbs + win, 0.0, radius, call_nos=(n_total * (r + 1) + idx).astype(np.uint64))
+        st = prob.stats()
+        for k in acc:
+            acc[k] += int(st[k])
+    return d, c, acc
+
+
+def bench_syncpoints(prob, w, label, rank, world, barrier, dev, fp64_peak, repeat=1):
+    """syncpoints/s of the whole syncpoint loop of workload w, syncpoints sharded round-robin over the
+    ranks, with the evaluation accounting of SURVEY 8(d) and, for N > 1, a comparison of the gathered
+    result with rank 0 computing everything alone."""
+    import torch
+    import torch.distributed as dist
+    sharded = importlib.import_module("rs-sync_b200.sharded")
+    sps = w.syncpoints()
+    S, win = len(sps), w.sync_window
+    mine = np.arange(rank, S, world)
+    syncpoint_loop(prob, sps, win, w.presync_step, 0.2, mine, S)  # warm-up (streams, graphs, first use)
+    best = None
+    for _ in range(repeat):
+        barrier()
+        t0 = time.perf_counter()
+        d, c, acc = syncpoint_loop(prob, sps, win, w.presync_step, 0.2, mine, S)
+        if world > 1:  # the one exchange: (cost, delay) of every syncpoint to every rank
+            both = sharded._gather_rows(np.stack([c, d], axis=1), [len(range(r, S, world)) for r in range(world)],
+                                        world, dev, dist)
+            order = np.concatenate([np.arange(r, S, world) for r in range(world)])
+            allc, alld = np.empty(S), np.empty(S)
+            allc[order], alld[order] = both[:, 0], both[:, 1]
+        else:
+            allc, alld = c, d
+        barrier()
+        dt = time.perf_counter() - t0
+        best = dt if best is None else min(best, dt)
+    t = torch.tensor([best], dtype=torch.float64, device=dev)
+    cnt = torch.tensor([float(acc[k]) for k in sorted(acc)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dist.all_reduce(cnt, op=dist.ReduceOp.SUM)
+    acc = {k: int(v) for k, v in zip(sorted(acc), cnt.cpu().tolist())}
+    secs = float(t[0])
+    presync_cells = S * win * w.n_rays * len(importlib.import_module("rs-sync_b200").presync_delays(0.0, w.presync_step, 0.2))
+    flops = sync_flops(acc, w.n_rays, presync_cells)
+    true = np.array([w.true_delay_at(p) for p in sps])
+    out = {"metric": "sync_syncpoints_per_s", "config": label, "value": S / secs, "unit": "syncpoints/s",
+           "syncpoints": S, "seconds": secs,
+           "what": "per syncpoint: PreSync(radius 200 ms, step 2 ms) on a 60-frame window + 4 chained Sync; "
+                   "Sync calls batched across syncpoints, syncpoints sharded round-robin over the GPUs",
+           "mean_abs_delay_error_ms": float(np.mean(np.abs(alld - true)) * 1e3),
+           "row_builds": acc["sync_row_builds"], "loss_evals": acc["sync_loss_evals"],
+           "lbfgs_evals": acc["sync_lbfgs_evals"], "init_estimates": acc["sync_init_tasks"],
+           "outer_iters": acc["sync_outer_total"], "presync_cells": presync_cells,
+           "algorithmic_gflop": flops / 1e9, "tflops": flops / secs / 1e12,
+           "frac_fp64_peak": flops / secs / 1e12 / (fp64_peak * world) if fp64_peak > 0 else None,
+           "checksum": float(np.sum(alld) + np.sum(allc) * 1e-6)}
+    if world > 1:  # every N must compute the single-GPU numbers: rank 0 recomputes all of them alone
+        ok = True
+        n1 = None
+        if rank == 0:
+            t1 = time.perf_counter()
+            d1, c1, _ = syncpoint_loop(prob, sps, win, w.presync_step, 0.2, np.arange(S), S)
+            n1 = time.perf_counter() - t1
+            ok = bool(np.array_equal(d1, alld) and np.array_equal(c1, allc))
+        barrier()
+        out["equals_one_gpu"] = ok
+        out["n1_seconds_same_run"] = n1
+        out["speedup_vs_one_gpu_same_run"] = (n1 / secs) if n1 else None
+    return out, alld
+
+
+def sync_parity_vs_oracle(w, alld, n_check=2):
+    """the oracle port's sequential PreSync + 4 x Sync on the first syncpoints, same call numbers, against
+    the engine's delays; also the CPU arm of syncpoints/s"""
+    from oracle import loader
+    threads = os.cpu_count() or 1
+    sps = w.syncpoints()
+    S, win = len(sps), w.sync_window
+    worst, secs = 0.0, []
+    for s in range(min(n_check, S)):
+        pos = sps[s]
+        o = loader.OracleProblem(threads=threads, seed=100).load_range(w, pos, win + 1)
+        t = time.perf_counter()
+        o.set_rng(100, s)
+        d = o.PreSync(0.0, pos, pos + win, w.presync_step, 0.2)[1]
+        for r in range(4):
+            o.set_rng(100, S * (r + 1) + s)
+            d = o.Sync(d, pos, pos + win, 0.0, 0.2)[1]
+        secs.append(time.perf_counter() - t)
+        worst = max(worst, abs(d - float(alld[s])) / abs(d))
+    return ({"syncpoints_checked": min(n_check, S), "max_rel_err_vs_oracle": worst, "tolerance": 1e-9, "ok": bool(worst <= 1e-9)},
+            {"value": 1.0 / float(np.mean(secs)), "unit": "syncpoints/s", "cores": threads, "kind": "port",
+             "sample": f"{len(secs)} of {S} syncpoints ({float(np.mean(secs)):.2f} s each)"})
+
+
+def read_traffic():
+    """DRAM bytes of one launch of the dominant kernel, from the tracked ncu capture"""
+    try:
+        with open(os.path.join(ROOT, "profiles", "presync_traffic.json")) as f:
+            return json.load(f)
+    except Exception:
+        return None
+
+
 def run_b200(args):
     import torch
     import torch.distributed as dist
@@ -243,12 +357,13 @@ def run_b200(args):
     n_gpus = max(args.gpus, world)
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    local_world = int(os.environ.get("LOCAL_WORLD_SIZE", str(world)))
+    cores = max(1, (os.cpu_count() or 1))
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=dev)
         # one process per GPU on one host: each engine's ingest thread pool gets its share of the cores
-        local_world = int(os.environ.get("LOCAL_WORLD_SIZE", str(world)))
-        os.environ.setdefault("RSSYNC_HOST_THREADS", str(max(1, (os.cpu_count() or 1) // max(local_world, 1))))
+        os.environ.setdefault("RSSYNC_HOST_THREADS", str(max(1, cores // max(local_world, 1))))
 
     def barrier():
         if world > 1:
@@ -256,6 +371,7 @@ def run_b200(args):
         torch.cuda.synchronize()
 
     pkg = importlib.import_module("rs-sync_b200")
+    sharded = importlib.import_module("rs-sync_b200.sharded")
     w = make_workload(args.workload, n_gpus)
     delays = grid_delays(w, n_gpus)
     lo, hi = OFFSETS_PER_GPU * rank, OFFSETS_PER_GPU * (rank + 1)
@@ -274,15 +390,15 @@ def run_b200(args):
 
     flush_buf = torch.empty(512 * 1024 * 1024 // 4, dtype=torch.float32, device=dev)  # 512 MB > 126 MB L2
     gather_in = torch.empty(hi - lo, dtype=torch.float64, device=dev)
-    gather_out = [torch.empty(hi - lo, dtype=torch.float64, device=dev) for _ in range(world)]
+    gather_out = torch.empty((world, hi - lo), dtype=torch.float64, device=dev)
 
     def step(call_no):
         costs = prob.presync_grid(fb, fe, delays[lo:hi], stream=pkg.STREAM_DEBUG, call_no=call_no,
                                   offset_index_base=lo)
         if world > 1:  # the only exchange: loss-curve slices
             gather_in.copy_(torch.from_numpy(costs))
-            dist.all_gather(gather_out, gather_in)
-            curve = torch.cat(gather_out)
+            dist.all_gather_into_tensor(gather_out, gather_in)
+            curve = gather_out.reshape(-1)
         else:
             curve = torch.from_numpy(costs)
         return int(torch.argmin(curve))
@@ -315,37 +431,59 @@ def run_b200(args):
     value = cells_per_step / (ms_per_step * 1e-3)
 
     # ---- end to end: host buffers in, curve out, through the C ABI --------------------------
+    # N = 1: SetGyroQuaternions + bulk SetTrackResult from host memory, then the grid.  N > 1: the
+    # inputs enter through rank 0 only (one validation / staging / PCIe upload instead of N through the
+    # same host), its finished device state is replicated to the other ranks over NVLink (NCCL
+    # broadcast into the engines' own buffers), then every rank evaluates its offsets.
     e2e_steps = max(3, min(args.steps, 5))
     counts = np.full(w.n_frames, w.n_rays)
     st0 = prob.stats()
+    bcast_bytes = 0
     barrier()
     t0 = time.perf_counter()
     for i in range(e2e_steps):
-        prob.SetGyroQuaternions(w.quats, w.quats.shape[0], w.gyro_rate, w.gyro_t0)
-        prob.set_track_batch(w.frame_ids, counts, w.ts_a, w.ts_b, w.rays_a, w.rays_b)
+        if rank == 0:
+            prob.SetGyroQuaternions(w.quats, w.quats.shape[0], w.gyro_rate, w.gyro_t0)
+            prob.set_track_batch(w.frame_ids, counts, w.ts_a, w.ts_b, w.rays_a, w.rays_b)
+        if world > 1:
+            sharded.replicate_state(prob, rank=rank, world=world, device=dev)
         step(2000 + i)
     barrier()
     e2e_s = (time.perf_counter() - t0) / e2e_steps
     st1 = prob.stats()
-    te = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
     if world > 1:
-        dist.all_reduce(te, op=dist.ReduceOp.MAX)
+        ds = prob.device_state()
+        bcast_bytes = sum(ds[k][1] for k in ("rays", "orig", "pos", "spline_records")) + w.n_frames * 32
+    te = torch.tensor([e2e_s, float(st1["h2d_bytes"] - st0["h2d_bytes"]), float(st1["d2h_bytes"] - st0["d2h_bytes"])],
+                      dtype=torch.float64, device=dev)
+    if world > 1:
+        tm = te.clone()
+        dist.all_reduce(tm, op=dist.ReduceOp.MAX)
+        dist.all_reduce(te, op=dist.ReduceOp.SUM)
+        te[0] = tm[0]
     e2e = {"value": cells_per_step / float(te[0]), "unit": UNIT,
-           "h2d_bytes_per_step": (st1["h2d_bytes"] - st0["h2d_bytes"]) // e2e_steps,
-           "d2h_bytes_per_step": (st1["d2h_bytes"] - st0["d2h_bytes"]) // e2e_steps,
+           "h2d_bytes_per_step": int(te[1]) // e2e_steps, "d2h_bytes_per_step": int(te[2]) // e2e_steps,
            "ms_per_step": float(te[0]) * 1e3,
-           "what": "SetGyroQuaternions + SetTrackResult (bulk) from host buffers, grid through the C ABI, curve back on the host"}
+           "what": ("SetGyroQuaternions + SetTrackResult (bulk) from host buffers, grid through the C ABI, curve back on the host"
+                    if world == 1 else
+                    "rank 0: SetGyroQuaternions + SetTrackResult (bulk) from host buffers; its device state replicated "
+                    "to the other ranks by NCCL broadcast over NVLink; every rank's grid slice through the C ABI; "
+                    "curve gathered; bytes are summed over ranks"),
+           "nvlink_broadcast_bytes_per_step": int(bcast_bytes)}
 
     # ---- roofline of the dominant kernel (presync_kernel) -------------------------------------
     achieved = FLOP_PER_CELL * cells_per_step_rank / (kern_ms * 1e-3) / 1e12
     input_bytes = w.n_frames * ((w.n_rays + 31) // 32 * 32) * 64 + w.quats.shape[0] * 128 + cells_per_step_rank // w.n_rays * 8
+    traffic = read_traffic()
     roofline = {"bound": "fp64", "achieved": achieved, "peak": fp64_peak, "unit": "TFLOP/s",
                 "frac": achieved / fp64_peak if fp64_peak > 0 else None,
                 "peak_source": "measured live: rssync_measure_fp64_peak (dependent DFMA chains, all SMs)",
                 "kernel": "presync_kernel", "kernel_ms": kern_ms, "flop_per_cell": FLOP_PER_CELL,
-                # dram__bytes_read.sum + dram__bytes_write.sum of one launch, ncu --set full
-                # (profiles/r01_presync_v5.md): 57.6 MB + 1.1 MB = inputs once + the framecost scratch
-                "traffic": 58.7e6 if (w.name == "C2" and hi - lo == OFFSETS_PER_GPU) else None,
+                # dram__bytes_read.sum + dram__bytes_write.sum of one launch of this kernel on this
+                # workload, read from the tracked ncu capture (profiles/presync_traffic.json)
+                "traffic": (traffic["dram_bytes_read"] + traffic["dram_bytes_write"])
+                if (traffic and w.name == "C2" and hi - lo == OFFSETS_PER_GPU) else None,
+                "traffic_source": traffic.get("capture") if traffic else None,
                 "exact_estimator_tasks": int(prob.stats()["last_grid_exact_tasks"]),
                 "tasks": int(prob.stats()["last_grid_tasks"]),
                 "hbm": {"algorithmic_bytes": int(input_bytes),
@@ -359,14 +497,21 @@ def run_b200(args):
            "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline}
 
     # ---- Sync: syncpoints/s (PreSync on the window + 4 chained Sync, core_testcode.cpp:303-316)
+    sync_delays = None
     if not args.no_sync:
-        out["sync"] = bench_sync(prob, w, rank, world, barrier, dev)
+        out["sync"], sync_delays = bench_syncpoints(prob, w, "C2: 27 syncpoints (window 60, distance 120)", rank, world,
+                                                    barrier, dev, fp64_peak, repeat=3)
 
-    if rank == 0 and world >= 1 and not args.no_cpu and world == 1:
+    # ---- the sharded configurations north_star names (C3 strong scaling, C4 with 900 syncpoints) --
+    if world > 1 or args.scale_configs:
+        del flush_buf
+        out["scale"] = bench_scale_configs(pkg, sharded, rank, world, barrier, dev, fp64_peak, cores, local_world)
+
+    if rank == 0 and not args.no_cpu and world == 1:
         out["cpu_baseline"] = cpu_baseline(w, delays, args.cpu_seconds)
         out["cpu_baseline"]["parity"] = full_size_parity(prob, w, delays, pkg)
         if not args.no_sync:
-            out["cpu_baseline"]["sync"] = cpu_sync_baseline(w)
+            out["sync"]["parity"], out["cpu_baseline"]["sync"] = sync_parity_vs_oracle(w, sync_delays)
     elif rank == 0 and not args.no_cpu:
         out["cpu_baseline"] = None
     if rank == 0:
@@ -375,37 +520,94 @@ def run_b200(args):
         dist.destroy_process_group()
 
 
-def bench_sync(prob, w, rank, world, barrier, dev):
+def bench_scale_configs(pkg, sharded, rank, world, barrier, dev, fp64_peak, cores, local_world):
+    """C3 (10 000 frames x 500 rays x 2001 offsets, strong scaling: offsets sharded) and C4 (30-minute
+    trace, a syncpoint every 120 frames = 900 syncpoints, sharded).  The inputs are generated and
+    ingested on rank 0 only and replicated to the other GPUs over NVLink; each number is wall time
+    including the gather; rank 0 then repeats the whole configuration alone, in the same run on the
+    same box, for the speed-up."""
     import torch
     import torch.distributed as dist
-    sps = w.syncpoints()
-    mine = sps[rank::world] if world > 1 else sps
-    win = w.sync_window
+    synth = importlib.import_module("rs-sync_b200.synth")
+    res = {}
 
-    def run():
-        fbs = np.array(mine, dtype=np.int64)
-        # PreSync of every syncpoint window, one grid launch
-        d = prob.presync_windows(0.0, fbs, fbs + win, w.presync_step, 0.2)[1]
-        for _ in range(4):  # 4 chained Sync calls per syncpoint, advanced in lock-step
-            _, d = prob.sync_batch(d, fbs, fbs + win, 0.0, 0.2)
-        return d
+    def problem_for(name, **kw):
+        """rank 0 generates + ingests, the others adopt its device state; returns (problem, workload-or-None)"""
+        p = pkg.SyncProblem(seed=100)
+        w = None
+        t0 = time.perf_counter()
+        if rank == 0:
+            w = synth.make_workload(name, procs=max(1, min(cores, 32)), **kw)
+            p.load(w, bulk=True)
+            p.flush()
+        t_gen = time.perf_counter() - t0
+        barrier()
+        t0 = time.perf_counter()
+        sharded.replicate_state(p, rank=rank, world=world, device=dev)
+        barrier()
+        return p, w, t_gen, time.perf_counter() - t0
 
-    prob.set_rng(100, 0)
-    run()  # warm-up
-    prob.set_rng(100, 0)
+    # ---- C3, strong scaling --------------------------------------------------------------------
+    p, w, t_gen, t_rep = problem_for("C3")
+    meta = [None]
+    if rank == 0:
+        meta = [dict(fb=int(w.frame_ids[0]), fe=int(w.frame_ids[-1]) + 1, n_frames=w.n_frames, n_rays=w.n_rays,
+                     true_delay=float(w.true_delay[0]))]
+    if world > 1:
+        dist.broadcast_object_list(meta, src=0)
+    m = meta[0]
+    delays = np.array([0.0 - 1.0 + 2 * 1.0 * i / 2000 for i in range(2001)])  # core_private.cpp:345
+    lo, hi = sharded.shard_range(len(delays), rank, world)
+    p.presync_grid(m["fb"], m["fe"], delays[lo:lo + 8], stream=2, call_no=0, offset_index_base=lo)  # warm-up
     barrier()
     t0 = time.perf_counter()
-    d = run()
+    curve = sharded.presync_grid_sharded(p, m["fb"], m["fe"], delays, stream=2, call_no=1, rank=rank, world=world, device=dev)
     barrier()
     dt = time.perf_counter() - t0
-    t = torch.tensor([dt], dtype=torch.float64, device=dev)
+    tt = torch.tensor([dt], dtype=torch.float64, device=dev)
     if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    err = np.abs(d - np.array([w.true_delay[p - int(w.frame_ids[0])] for p in mine]))
-    return {"metric": "sync_syncpoints_per_s", "value": len(sps) / float(t[0]), "unit": "syncpoints/s",
-            "syncpoints": len(sps), "seconds": float(t[0]),
-            "what": "per syncpoint: PreSync(radius 200 ms, step 2 ms) on a 60-frame window + 4 chained Sync; Sync calls batched across syncpoints",
-            "mean_abs_delay_error_ms": float(np.mean(err) * 1e3)}
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+    dt = float(tt[0])
+    cells = len(delays) * m["n_frames"] * m["n_rays"]
+    c3 = {"config": f"C3: {m['n_frames']} frames x {m['n_rays']} rays x {len(delays)} offsets (radius 1 s, step 1 ms), offsets sharded x{world}",
+          "scaling": "strong", "seconds": dt, "cells_per_s": cells / dt,
+          "frac_fp64_peak": FLOP_PER_CELL * cells / dt / 1e12 / (fp64_peak * world) if fp64_peak > 0 else None,
+          "argmin_delay": float(delays[int(np.argmin(curve))]), "true_delay": m["true_delay"],
+          "checksum": float(np.sum(curve)), "synth_seconds_rank0": t_gen, "replicate_seconds": t_rep}
+    if world > 1:
+        n1, same = None, True
+        if rank == 0:
+            t1 = time.perf_counter()
+            whole = p.presync_grid(m["fb"], m["fe"], delays, stream=2, call_no=1)
+            n1 = time.perf_counter() - t1
+            same = bool(np.array_equal(whole, curve))
+        barrier()
+        c3.update(n1_seconds_same_run=n1, speedup_vs_one_gpu_same_run=(n1 / dt) if n1 else None, equals_one_gpu=same)
+    res["c3_strong"] = c3
+    del p, w
+    torch.cuda.empty_cache()
+
+    # ---- C4 with 900 syncpoints ------------------------------------------------------------------
+    p, w, t_gen, t_rep = problem_for("C4d")
+    meta = [None]
+    if rank == 0:
+        meta = [dict(sps=w.syncpoints(), win=w.sync_window, step=w.presync_step, n_rays=w.n_rays,
+                     true=[w.true_delay_at(s) for s in w.syncpoints()], n_frames=w.n_frames,
+                     gyro_samples=int(w.quats.shape[0]))]
+    if world > 1:
+        dist.broadcast_object_list(meta, src=0)
+    m = meta[0]
+
+    class Meta:  # what bench_syncpoints needs of a workload
+        sync_window, presync_step, n_rays = m["win"], m["step"], m["n_rays"]
+        def syncpoints(self): return m["sps"]
+        def true_delay_at(self, s): return m["true"][m["sps"].index(s)]
+    c4, _ = bench_syncpoints(p, Meta(), f"C4: 30 min 60 fps trace, {len(m['sps'])} syncpoints (window 60, distance 120), "
+                             f"{m['n_frames']} tracked frames x {m['n_rays']} rays, {m['gyro_samples']} gyro samples",
+                             rank, world, barrier, dev, fp64_peak, repeat=2)
+    c4.update(synth_seconds_rank0=t_gen, replicate_seconds=t_rep)
+    res["c4_sync"] = c4
+    return res
 
 
 def read_peaks():

@@ -227,7 +227,10 @@ def camera_centre(t):
 def make_workload(name="C1", *, frames=None, rays=None, first_frame=None, seed=1, fps=60.0,
                   gyro_rate=1000.0, radius=None, step=None, true_delay=0.037, drift=None,
                   noise_px=0.3, outlier_frac=0.10, sync_window=60, syncpoint_distance=120,
-                  windows_only=None):
+                  windows_only=None, procs=1, gyro_pad_radius=None):
+    """procs > 1: the per-frame part (projection, rolling-shutter re-projection, undistortion) is cut
+    into frame chunks and generated by that many forked worker processes -- a frame's data depends only
+    on (seed, frame id) and the shared gyro track, so the result is identical to procs = 1."""
     presets = {
         "C1": dict(frames=300, rays=100, first_frame=0, radius=0.2, step=0.002),
         "C2": dict(frames=3300, rays=200, first_frame=3900, radius=0.2, step=0.002),
@@ -237,6 +240,9 @@ def make_workload(name="C1", *, frames=None, rays=None, first_frame=None, seed=1
         # (107 of them), only the frames inside the sync windows tracked (README.md:66: frames may
         # be skipped), delay drifting -45 -> -40 ms
         "C4s": dict(frames=108000, rays=200, first_frame=0, radius=0.2, step=0.002),
+        # the same trace with a syncpoint every 120 frames (the reference's default distance): 900
+        # syncpoints; only the frames inside the sync windows are tracked
+        "C4d": dict(frames=108000, rays=200, first_frame=0, radius=0.2, step=0.002),
         "tiny": dict(frames=12, rays=40, first_frame=5, radius=0.05, step=0.005),
         "small": dict(frames=64, rays=100, first_frame=100, radius=0.1, step=0.002),
     }
@@ -246,10 +252,12 @@ def make_workload(name="C1", *, frames=None, rays=None, first_frame=None, seed=1
     if first_frame is not None: p["first_frame"] = first_frame
     if radius is not None: p["radius"] = radius
     if step is not None: p["step"] = step
-    if name in ("C4", "C4s") and drift is None:
+    if name in ("C4", "C4s", "C4d") and drift is None:
         drift = (-0.045, -0.040)  # linear drift, thesis Fig. 8
     if name == "C4s":
         syncpoint_distance = 1000 if syncpoint_distance == 120 else syncpoint_distance
+        windows_only = True if windows_only is None else windows_only
+    if name == "C4d":
         windows_only = True if windows_only is None else windows_only
     F, N, f0 = p["frames"], p["rays"], p["first_frame"]
 
@@ -267,7 +275,9 @@ def make_workload(name="C1", *, frames=None, rays=None, first_frame=None, seed=1
             keep[pos:pos + sync_window + 1] = True
         frame_ids, dtrue = frame_ids[keep], dtrue[keep]
         F = int(frame_ids.shape[0])
-    pad = p["radius"] + 1.0 + float(np.max(np.abs(dtrue)))
+    # the gyro track covers the frames +- (search radius + 1 s + |delay|); gyro_pad_radius widens it so
+    # that workloads that differ only in their search radius share one track (and one scene)
+    pad = max(p["radius"], gyro_pad_radius or 0.0) + 1.0 + float(np.max(np.abs(dtrue)))
     g0 = np.floor((t_first - pad) * gyro_rate) / gyro_rate
     ng = int(np.ceil((t_last + 1.0 / fps + pad - g0) * gyro_rate)) + 1
     tg = g0 + np.arange(ng) / gyro_rate
@@ -275,6 +285,24 @@ def make_workload(name="C1", *, frames=None, rays=None, first_frame=None, seed=1
     quats = integrate_gyro(omega, np.full(ng, 1.0 / gyro_rate))
     track = QuatTrack(quats, gyro_rate, g0)
 
+    parts = _frames_parallel(track, frame_ids, dtrue, N, seed, fps, noise_px, outlier_frac, procs)
+    ts_a, ts_b, rays_a, rays_b, pa_x, pa_y, pb_x, pb_y = parts
+
+    return Workload(name=name, fps=fps, gyro_rate=gyro_rate, gyro_t0=float(g0), quats=quats,
+                    omega=omega, frame_ids=frame_ids, ts_a=np.ascontiguousarray(ts_a),
+                    ts_b=np.ascontiguousarray(ts_b), rays_a=np.ascontiguousarray(rays_a),
+                    rays_b=np.ascontiguousarray(rays_b), true_delay=dtrue,
+                    presync_radius=p["radius"], presync_step=p["step"], sync_window=sync_window,
+                    syncpoint_distance=syncpoint_distance,
+                    meta=dict(seed=seed, noise_px=noise_px, outlier_frac=outlier_frac,
+                              span=(int(f0), int(f0 + span_frames))),
+                    px_a=np.ascontiguousarray(np.stack([pa_x, pa_y], axis=-1)),
+                    px_b=np.ascontiguousarray(np.stack([pb_x, pb_y], axis=-1)))
+
+
+def _frames(track, frame_ids, dtrue, N, seed, fps, noise_px, outlier_frac):
+    """rays, timestamps and pixels of the given frames (arrays of shape (F, N[, ...]))"""
+    F = int(frame_ids.shape[0])
     # per-frame draws (seeded per frame so a frame's data does not depend on the range asked for)
     U = np.empty((F, N, 10))
     for i, fid in enumerate(frame_ids):
@@ -312,17 +340,30 @@ def make_workload(name="C1", *, frames=None, rays=None, first_frame=None, seed=1
     pb_y = np.where(outlier, oy, pb_y + ny)
     ts_b = tf_b + READOUT * (pb_y / HEIGHT)
     rays_b = pixel_to_ray(pb_x, pb_y)
+    return ts_a, ts_b, rays_a, rays_b, pa_x, pa_y, pb_x, pb_y
 
-    return Workload(name=name, fps=fps, gyro_rate=gyro_rate, gyro_t0=float(g0), quats=quats,
-                    omega=omega, frame_ids=frame_ids, ts_a=np.ascontiguousarray(ts_a),
-                    ts_b=np.ascontiguousarray(ts_b), rays_a=np.ascontiguousarray(rays_a),
-                    rays_b=np.ascontiguousarray(rays_b), true_delay=dtrue,
-                    presync_radius=p["radius"], presync_step=p["step"], sync_window=sync_window,
-                    syncpoint_distance=syncpoint_distance,
-                    meta=dict(seed=seed, noise_px=noise_px, outlier_frac=outlier_frac,
-                              span=(int(f0), int(f0 + span_frames))),
-                    px_a=np.ascontiguousarray(np.stack([pa_x, pa_y], axis=-1)),
-                    px_b=np.ascontiguousarray(np.stack([pb_x, pb_y], axis=-1)))
+
+_SHARED = {}
+
+
+def _frames_chunk(bounds):
+    lo, hi = bounds
+    a = _SHARED["args"]
+    return _frames(a[0], a[1][lo:hi], a[2][lo:hi], *a[3:])
+
+
+def _frames_parallel(track, frame_ids, dtrue, N, seed, fps, noise_px, outlier_frac, procs):
+    F = int(frame_ids.shape[0])
+    if procs <= 1 or F < 4 * procs:
+        return _frames(track, frame_ids, dtrue, N, seed, fps, noise_px, outlier_frac)
+    import multiprocessing as mp
+    _SHARED["args"] = (track, frame_ids, dtrue, N, seed, fps, noise_px, outlier_frac)
+    n_chunks = procs * 4
+    bounds = [(F * i // n_chunks, F * (i + 1) // n_chunks) for i in range(n_chunks)]
+    with mp.get_context("fork").Pool(procs) as pool:  # fork: the children see _SHARED without pickling it
+        parts = pool.map(_frames_chunk, bounds)
+    _SHARED.clear()
+    return tuple(np.concatenate([p[k] for p in parts], axis=0) for k in range(8))
 
 
 # the 48 axis permutation / sign variants of core_testcode.cpp:186-190.  Our mapping (the
