@@ -545,6 +545,10 @@ int presync_grid_impl(rssync_problem* p, int64_t fb, int64_t fe, const double* d
     if (int rc = d2h(p, costs, p->d_costs.ptr, sizeof(double) * n)) return rc;
     if (int rc = d2h(p, flags, p->d_flags.ptr, 2 * sizeof(unsigned))) return rc;
     CUDA_TRY(p, cudaStreamSynchronize(p->stream));
+    if (const int line = rs::checked_assert_line()) {
+        p->err = "device-side assertion failed at engine.cu:" + std::to_string(line);
+        return RSSYNC_E_CUDA;
+    }
     tm.mark("wait for the device");
     p->grid_tasks = (uint64_t)F * (uint64_t)n;
     p->grid_exact_tasks = flags[1];
@@ -873,6 +877,10 @@ int sync_batch_impl(rssync_problem* p, int n, const double* initial, const int64
         }
         if (!progressed) std::this_thread::yield();
     }
+    if (const int line = rs::checked_assert_line()) {
+        p->err = "device-side assertion failed at engine.cu:" + std::to_string(line);
+        return RSSYNC_E_CUDA;
+    }
     return RSSYNC_OK;
 }
 
@@ -1122,6 +1130,7 @@ int rssync_create(rssync_problem** out) {
     rssync_problem* p = new rssync_problem();
     p->device = dev;
     *out = p;
+    rs::checked_assert_line();  // (arms the device-side assertions of an RS_CHECKED build)
     if (cc_major < 10) {
         p->err = "rssync_b200 needs an sm_100a (Blackwell B200) device; there is no CPU or other-GPU fallback";
         return RSSYNC_E_CUDA;

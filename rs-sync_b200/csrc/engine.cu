@@ -38,6 +38,24 @@ namespace rs {
 namespace {
 
 constexpr unsigned FULL = 0xffffffffu;
+
+// RS_CHECKED builds (make lib OUT=... EXTRA=-DRS_CHECKED) carry device-side assertions on every index
+// that addresses shared memory or the arena, on the staging protocol's counters and on the lengths of
+// the data-dependent loops; a violated assertion traps (the launch fails, the C ABI returns
+// RSSYNC_E_CUDA).  compute-sanitizer is not available on the GPU pool this engine is developed on,
+// so the whole -m gpu test suite is run against such a build instead (profiles/r02_checked_build.md).
+#ifdef RS_CHECKED
+__device__ int* g_assert_slot = nullptr;  // mapped host memory: survives a launch that dies afterwards
+#define RS_ASSERT(cond)                                                      \
+    do {                                                                     \
+        if (!(cond) && g_assert_slot) {                                      \
+            atomicCAS_system(g_assert_slot, 0, __LINE__);                    \
+            __threadfence_system();                                          \
+        }                                                                    \
+    } while (0)
+#else
+#define RS_ASSERT(cond) do { } while (0)
+#endif
 #ifndef RS_WPB
 #define RS_WPB 8
 #endif
@@ -185,9 +203,7 @@ __device__ __forceinline__ void build_rows_staged(const DeviceData& dd, const Fr
         // (grid_stage_unit), so the index lies in [1, rec_cnt - 3].  RS_CHECKED builds verify it.
         const unsigned ia = (unsigned)(__double2loint(fa) - rec_first);
         const unsigned ib = (unsigned)(__double2loint(fb) - rec_first);
-#ifdef RS_CHECKED
-        if (ia >= (unsigned)rec_cnt || ib >= (unsigned)rec_cnt) __trap();
-#endif
+        RS_ASSERT(ia >= 1u && ib >= 1u && ia + 2u < (unsigned)rec_cnt && ib + 2u < (unsigned)rec_cnt && i < NP);
         double qa[4], qb[4], ar[3], br[3], na, nb;
         spline_eval4_staged(sRecAddr, ia, ia + (unsigned)rec_first, xa - (fa - kTwo52), qa);
         spline_eval4_staged(sRecAddr, ib, ib + (unsigned)rec_first, xb - (fb - kTwo52), qb);
@@ -217,6 +233,7 @@ __device__ __forceinline__ void draw_hypothesis(const DeviceData& dd, const Fram
     uint32_t b, kk = 1u;
     do { b = rng_index(key, it, kk++, (uint32_t)fd.n); } while (b == a);  // :43
     const int pa = __ldg(dd.pos + fd.off + a), pb = __ldg(dd.pos + fd.off + b);
+    RS_ASSERT(a < (uint32_t)fd.n && b < (uint32_t)fd.n && (unsigned)pa < (unsigned)fd.n && (unsigned)pb < (unsigned)fd.n);
     const double a0 = sP[pa], a1 = sP[NP + pa], a2 = sP[2 * NP + pa];
     const double b0 = sP[pb], b1 = sP[NP + pb], b2 = sP[2 * NP + pb];
     const double c0 = fma(a1, b2, -(a2 * b1));
@@ -489,7 +506,8 @@ __device__ __forceinline__ unsigned warp_select32(const float (&s)[SLOTS], int k
                                                   int chi, int npad, int n, bool sample) {
     unsigned lo = 0u;
     int clo = 0, poor = 0;
-    for (;;) {
+    for (int round = 0;; ++round) {
+        RS_ASSERT(round < 80 && clo <= kk && kk < chi && lo < hi_excl);  // bisection alone ends within 2 x 32 rounds
         if (hi_excl - lo == 1u) return lo;
         if (kk == clo) return warp_min_ge<SLOTS>(s, lo);
         if (kk == chi - 1) return warp_max_lt<SLOTS>(s, hi_excl);
@@ -947,6 +965,7 @@ __device__ __forceinline__ double warp_lbfgs(EvalF&& eval, double x[3], int& n_i
         const double denom = fmax(fmax(fabs(prevf), fabs(f)), 1.0);
         if ((prevf - f) / denom <= factr) break;
         const int op = it % numBasis;
+        RS_ASSERT(op >= 0 && op < numBasis && cnt <= numBasis);
         for (int c = 0; c < 3; ++c) { S[op][c] = x[c] - oldx[c]; Y[op][c] = g[c] - oldg[c]; }
         const double ys = dot3(Y[op][0], Y[op][1], Y[op][2], S[op][0], S[op][1], S[op][2]);
         rho_pair[op] = (ys != 0) ? (1.0 / ys) : 1.0;
@@ -1151,9 +1170,19 @@ presync_kernel(DeviceData dd, const FrameDesc* __restrict__ frames, int F,
             fd = frames[fi];
         } else if (u != cur_u) {  // first task this warp takes in unit u
             cur_u = u;
-            while (*(volatile int*)&ctl->unit[b] != u) __nanosleep(RS_POLL_NS);
+#ifdef RS_CHECKED
+            unsigned spins = 0;
+#endif
+            for (int have; (have = *(volatile int*)&ctl->unit[b]) != u;) {
+                RS_ASSERT(++spins < (1u << 24) && have < u);  // never handed past a unit still needed
+                __nanosleep(RS_POLL_NS);
+            }
             const unsigned parity = (unsigned)(u >> 1) & 1u;
-            while (!mbar_try_wait(&ctl->full[b], parity)) __nanosleep(RS_POLL_NS);
+            while (!mbar_try_wait(&ctl->full[b], parity)) {
+                RS_ASSERT(++spins < (1u << 24));
+                __nanosleep(RS_POLL_NS);
+            }
+            RS_ASSERT(*(volatile int*)&ctl->unit[b] == u);
             rec_first = *(volatile int*)&ctl->rec_first[b];
             rec_cnt = *(volatile int*)&ctl->rec_cnt[b];
             fi = *(volatile int*)&ctl->frame[b];
@@ -1163,6 +1192,7 @@ presync_kernel(DeviceData dd, const FrameDesc* __restrict__ frames, int F,
         }
         const int di = d0 + dj;
         const bool active = di < D;
+        RS_ASSERT(fi >= 0 && fi < F && dj >= 0 && dj < chunk && fd.n >= 2 && fd.n <= NP);
         double delay = 0.0;
         if (active) {
             delay = delays[di];
@@ -1173,7 +1203,10 @@ presync_kernel(DeviceData dd, const FrameDesc* __restrict__ frames, int F,
         __syncwarp();
         if (lane == 0 && staged) {  // this phase A no longer needs the staging buffer
             __threadfence_block();
-            if (atomicAdd(&ctl->done_a[b], 1) == chunk - 1) {  // the unit's last: refill the buffer
+            RS_ASSERT(*(volatile int*)&ctl->unit[b] == u);  // the buffer was not handed on under this phase A
+            const int done = atomicAdd(&ctl->done_a[b], 1);
+            RS_ASSERT(done >= 0 && done < chunk);
+            if (done == chunk - 1) {  // the unit's last: refill the buffer
                 ctl->done_a[b] = 0;
                 if (u + 2 < n_units) stage(u + 2);
             }
@@ -1749,6 +1782,29 @@ void allow_smem(K kernel, size_t smem) {
     }
 
 }  // namespace
+
+// RS_CHECKED builds: line of the first failed device-side assertion (0: none).  The slot is mapped
+// host memory, one per device, registered with that device's copy of g_assert_slot on first use.
+int checked_assert_line() {
+#ifdef RS_CHECKED
+    static std::mutex mu;
+    static std::map<int, int*> slots;
+    std::lock_guard<std::mutex> lk(mu);
+    const int dev = current_device();
+    int*& h = slots[dev];
+    if (!h) {
+        cudaHostAlloc((void**)&h, sizeof(int), cudaHostAllocMapped);
+        *h = 0;
+        int* d = nullptr;
+        cudaHostGetDevicePointer((void**)&d, h, 0);
+        cudaMemcpyToSymbol(g_assert_slot, &d, sizeof(d));
+        return 0;
+    }
+    return *(volatile int*)h;
+#else
+    return 0;
+#endif
+}
 
 uint64_t launch_count() { return g_launches.load(); }
 void count_launches(uint64_t n) { g_launches += n; }

@@ -150,6 +150,10 @@ void launch_probe_guess(const DeviceData& dd, FrameDesc fd, double delay, int it
 // FP64 FMA peak microbenchmark: returns elapsed ms for `iters` x 8 dependent-chain FMAs per thread
 float run_fp64_peak(int blocks, int threads, int iters, double* d_sink, cudaStream_t st);
 
+// RS_CHECKED builds: source line (engine.cu) of the first failed device-side assertion on the current
+// device, 0 if none; the first call on a device arms the checks.  Always 0 in regular builds.
+int checked_assert_line();
+
 // bookkeeping for gpu_launches reporting
 uint64_t launch_count();
 // kernels launched through a replayed CUDA graph (the launchers only run at capture time)
