@@ -232,6 +232,10 @@ struct rssync_problem {
     std::vector<std::pair<size_t, size_t>> pending;
     size_t dev_used = 0;  // extent of the device arena holding data
     std::map<int64_t, FrameDesc> frames;  // OptData::frame_data
+    // callers set frames in ascending order, mostly: the node after the one placed last is tried
+    // before a tree search (map iterators survive insertions; frames are never erased one by one)
+    std::map<int64_t, FrameDesc>::iterator place_hint;
+    bool place_hint_valid = false;
     size_t total_rays = 0;
 
     uint64_t seed = 100, call_no = 0;
@@ -439,6 +443,8 @@ int multi_presync_grid(rssync_problem* p, int64_t fb, int64_t fe, const double* 
                        uint64_t stream_id, uint64_t call_no, uint64_t idx_base, double* costs,
                        unsigned* flags_out);
 bool is_multi(const rssync_problem* p) { return !p->replicas.empty() && !p->force_single; }
+
+void parallel_copy(void* dst, const void* src, size_t bytes);  // worker pool, below
 
 int presync_grid_impl(rssync_problem* p, int64_t fb, int64_t fe, const double* delays, int n,
                       uint64_t stream_id, uint64_t call_no, uint64_t idx_base, double* costs,
@@ -1247,7 +1253,7 @@ int rssync_set_gyro_fixed(rssync_problem* p, const double* quats, size_t count, 
     if (p->gyro_dirty == false && p->nq) CUDA_TRY(p, cudaStreamSynchronize(p->stream));  // records in flight
     if (p->gyro_stream) CUDA_TRY(p, cudaStreamSynchronize(p->gyro_stream));  // a copy never waited for
     CUDA_TRY(p, p->h_gyro.reserve(count * 9));
-    std::memcpy(p->h_gyro.ptr, quats, 4 * count * sizeof(double));  // the caller's buffer is only borrowed
+    parallel_copy(p->h_gyro.ptr, quats, 4 * count * sizeof(double));  // the caller's buffer is only borrowed
     p->nq = count;
     p->gyro_dirty = true;
     return start_gyro_worker(p, count);  // :139
@@ -1333,7 +1339,16 @@ int stage_track(const double* ts_a, const double* ts_b, const double* rays_a, co
 int place_track(rssync_problem* p, int64_t frame, size_t count, FrameDesc** fd_out) {
     const size_t padded = (count + 31) / 32 * 32;
     size_t off;
-    auto it = p->frames.find(frame);
+    auto it = p->frames.end();
+    if (p->place_hint_valid) {
+        auto nx = std::next(p->place_hint);
+        if (nx != p->frames.end() && nx->first == frame) it = nx;
+    }
+    auto pos = it;  // where a new node goes
+    if (it == p->frames.end()) {
+        pos = p->frames.lower_bound(frame);
+        if (pos != p->frames.end() && pos->first == frame) it = pos;
+    }
     if (it != p->frames.end() && (size_t)((it->second.n + 31) / 32 * 32) == padded) {
         off = (size_t)it->second.off;  // replace in place
         p->total_rays -= (size_t)it->second.n;
@@ -1354,9 +1369,12 @@ int place_track(rssync_problem* p, int64_t frame, size_t count, FrameDesc** fd_o
         }
         p->used = need;
     }
-    FrameDesc& fd = p->frames[frame];  // map nodes are stable: fill_track completes ts_lo / ts_hi
+    if (it == p->frames.end()) it = p->frames.emplace_hint(pos, frame, FrameDesc{});
+    FrameDesc& fd = it->second;  // map nodes are stable: fill_track completes ts_lo / ts_hi
     fd = FrameDesc{frame, (int32_t)off, (int32_t)count, 0.0, 0.0};
     p->total_rays += count;
+    p->place_hint = it;
+    p->place_hint_valid = true;
     *fd_out = &fd;
     return RSSYNC_OK;
 }
@@ -1502,6 +1520,21 @@ private:
     std::atomic<bool> stop_{false};
 };
 
+}  // namespace
+namespace {
+void parallel_copy(void* dst, const void* src, size_t bytes) {
+    constexpr size_t kPiece = 128 * 1024;
+    if (bytes < 4 * kPiece) {
+        std::memcpy(dst, src, bytes);
+        return;
+    }
+    const size_t pieces = (bytes + kPiece - 1) / kPiece;
+    WorkerPool::get().run(pieces, [&](size_t i, size_t) {
+        const size_t a = i * kPiece, b = std::min(bytes, a + kPiece);
+        std::memcpy(static_cast<char*>(dst) + a, static_cast<const char*>(src) + a, b - a);
+    }, 1);
+}
+
 void parallel_frames(size_t n, const std::function<void(size_t, size_t)>& fn) {
     if (n < 64) {
         for (size_t i = 0; i < n; ++i) fn(i, 0);
@@ -1569,12 +1602,12 @@ int rssync_set_track_batch(rssync_problem* p, size_t n_frames, const int64_t* fr
         CUDA_TRY(p, cudaStreamWaitEvent(p->copy_stream, p->ev_order, 0));
         cudaStream_t cs = p->copy_stream;
         const size_t total = at[n_frames];
-        CUDA_TRY(p, p->h_stage.reserve(8 * total + 1));
-        CUDA_TRY(p, p->d_stage.reserve(8 * total + 1));
-        CUDA_TRY(p, p->d_pixframes.reserve(n_frames));
+        // staging layout, per chunk and contiguous so that a chunk is ONE host->device copy:
+        //   [frame records: 4 doubles (one PixelFrame) per frame][ts_a n][ts_b n][rays_a 3n][rays_b 3n]
+        const size_t stage_doubles = 8 * total + 4 * n_frames + 1;
+        CUDA_TRY(p, p->h_stage.reserve(stage_doubles));
+        CUDA_TRY(p, p->d_stage.reserve(stage_doubles));
         if (!p->ev_arena) CUDA_TRY(p, cudaEventCreateWithFlags(&p->ev_arena, cudaEventDisableTiming));
-        std::vector<rs::PixelFrame>& pf = p->pixframes_host;
-        pf.resize(n_frames);
         std::vector<double> lo_ts(n_frames), hi_ts(n_frames);
         // room for the whole batch appended at the end of the arena (the most it can take)
         size_t padded_total = 0;
@@ -1592,45 +1625,47 @@ int rssync_set_track_batch(rssync_problem* p, size_t n_frames, const int64_t* fr
         for (size_t c = 0; c < n_chunks && n_ok == n_frames; ++c) {
             const size_t lo = n_frames * c / n_chunks, hi = n_frames * (c + 1) / n_chunks;
             if (lo == hi) continue;
+            const size_t a0 = at[lo], n = at[hi] - at[lo];          // the chunk's rays
+            const size_t base = 8 * a0 + 4 * lo;                     // its block in the staging buffers
+            double* h_rec = hs + base;                               // frame records
+            double* h_tsa = h_rec + 4 * (hi - lo);
+            double* h_tsb = h_tsa + n;
+            double* h_ra = h_tsb + n;
+            double* h_rb = h_ra + 3 * n;
             parallel_frames(hi - lo, [&](size_t k, size_t) {
-                const size_t i = lo + k, n = counts[i], a = at[i];
-                rc[i] = stage_track(ts_a + a, ts_b + a, rays_a + 3 * a, rays_b + 3 * a, n, hs + a, hs + total + a,
-                                    hs + 2 * total + 3 * a, hs + 5 * total + 3 * a, lo_ts[i], hi_ts[i], &msg[i]);
+                const size_t i = lo + k, cnt = counts[i], l = at[i] - a0;
+                rc[i] = stage_track(ts_a + at[i], ts_b + at[i], rays_a + 3 * at[i], rays_b + 3 * at[i], cnt, h_tsa + l,
+                                    h_tsb + l, h_ra + 3 * l, h_rb + 3 * l, lo_ts[i], hi_ts[i], &msg[i]);
             });
             tm.mark("stage + validate chunk");
             size_t end = hi;
             for (size_t i = lo; i < hi; ++i)
                 if (rc[i]) { end = i; n_ok = i; break; }
+            rssync_problem::InFlight fl{(size_t)-1, 0, nullptr};
+            rs::PixelFrame* pf = reinterpret_cast<rs::PixelFrame*>(h_rec);
             for (size_t i = lo; i < end; ++i) {
                 FrameDesc* fd = nullptr;
                 if (int r = place_track(p, frames[i], counts[i], &fd)) return r;
                 fd->ts_lo = lo_ts[i];
                 fd->ts_hi = hi_ts[i];
-                pf[i] = rs::PixelFrame{fd->off, fd->n, (int64_t)at[i], 0.0, 0.0};
+                pf[i - lo] = rs::PixelFrame{fd->off, fd->n, (int64_t)(at[i] - a0), 0.0, 0.0};
+                // the arena range this chunk writes
+                fl.lo = std::min(fl.lo, (size_t)fd->off);
+                fl.hi = std::max(fl.hi, (size_t)fd->off + (counts[i] + 31) / 32 * 32);
             }
             if (end == lo) break;
             if (int r = reserve_device_arena(p)) return r;
             tm.mark("place chunk");
-            const size_t a = at[lo], n = at[end] - at[lo];
-            auto up = [&](void* dst, const void* src, size_t bytes) {
-                p->h2d += bytes;
-                return cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, cs);
-            };
-            CUDA_TRY(p, up(p->d_pixframes.ptr + lo, pf.data() + lo, (end - lo) * sizeof(rs::PixelFrame)));
-            CUDA_TRY(p, up(ds + a, hs + a, n * sizeof(double)));
-            CUDA_TRY(p, up(ds + total + a, hs + total + a, n * sizeof(double)));
-            CUDA_TRY(p, up(ds + 2 * total + 3 * a, hs + 2 * total + 3 * a, 3 * n * sizeof(double)));
-            CUDA_TRY(p, up(ds + 5 * total + 3 * a, hs + 5 * total + 3 * a, 3 * n * sizeof(double)));
-            rs::launch_ingest_rays(p->d_pixframes.ptr + lo, (int)(end - lo), ds, ds + total, ds + 2 * total,
-                                   ds + 5 * total, p->d_rays.ptr, p->d_orig.ptr, p->d_pos.ptr, cs);
+            const size_t block = 4 * (hi - lo) + 8 * n;  // doubles
+            p->h2d += block * sizeof(double);
+            CUDA_TRY(p, cudaMemcpyAsync(ds + base, hs + base, block * sizeof(double), cudaMemcpyHostToDevice, cs));
+            double* d_rec = ds + base;
+            double* d_tsa = d_rec + 4 * (hi - lo);
+            rs::launch_ingest_rays(reinterpret_cast<const rs::PixelFrame*>(d_rec), (int)(end - lo), d_tsa, d_tsa + n,
+                                   d_tsa + 2 * n, d_tsa + 5 * n, p->d_rays.ptr, p->d_orig.ptr, p->d_pos.ptr, cs);
             CUDA_TRY(p, cudaGetLastError());
             p->dev_used = std::max(p->dev_used, p->used);  // a later growth of the arena keeps this chunk
-            // the arena range this chunk writes, and the event that says it has
-            rssync_problem::InFlight fl{(size_t)-1, 0, nullptr};
-            for (size_t i = lo; i < end; ++i) {
-                fl.lo = std::min(fl.lo, (size_t)pf[i].off);
-                fl.hi = std::max(fl.hi, (size_t)pf[i].off + (counts[i] + 31) / 32 * 32);
-            }
+            // the event that says the chunk's arena range has been written
             if (p->ev_pool.empty()) {
                 CUDA_TRY(p, cudaEventCreateWithFlags(&fl.ev, cudaEventDisableTiming));
             } else {
@@ -2140,6 +2175,7 @@ int rssync_adopt_state(rssync_problem* p, const rssync_frame_desc* frames, size_
     p->pending.clear();
     p->gyro_dirty = false;
     p->frames.clear();
+    p->place_hint_valid = false;
     p->total_rays = 0;
     for (size_t i = 0; i < n_frames; ++i) {
         const rssync_frame_desc& f = frames[i];
