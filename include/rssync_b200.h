@@ -179,6 +179,21 @@ int rssync_orientation_search_ex(rssync_problem* p, const double* timestamps_s, 
 int rssync_set_rng(rssync_problem* p, uint64_t seed, uint64_t call_no);
 uint64_t rssync_call_counter(const rssync_problem* p);
 
+/* Loss mode.  RSSYNC_LOSS_FULL (default) is the reference's loss.  RSSYNC_LOSS_SIMPLIFIED is the
+ * "simplified" variant of the thesis (pdf-p.27-28, section 2.11: the robust loss with the
+ * translation vector removed, a 1-D problem in the delay; no code for it in the reference
+ * checkout, so the definition is this engine's): the residual of a ray pair is |ar x br| itself
+ * -- the de-rotated rays of a purely rotating camera coincide -- instead of its component along
+ * the per-frame translation direction.  With r_i = |P_i| (P = opt_compute_problem's rows):
+ *   PreSync / DebugPreSync, per (delay, frame): k = clamp(100 / |r|_2, 10, 1000),
+ *       cost = sqrt(sum_i sqrt(log1p((r_i k)^2)))   (the aggregation of core_private.cpp:79-85);
+ *   Sync: k per frame from the initial delay, objective sum_frames sum_i log1p((r_i k)^2), the same
+ *       central-difference gradient, Backtrack and momentum loop (core_private.cpp:298-331); no
+ *       translation estimator, no per-frame L-BFGS, no random numbers.
+ * Faster (no estimator); loses accuracy on translation-heavy footage (thesis Fig. 9-10). */
+enum { RSSYNC_LOSS_FULL = 0, RSSYNC_LOSS_SIMPLIFIED = 1 };
+int rssync_set_loss_mode(rssync_problem* p, int mode);
+
 /* Run the problem's kernels on the given cudaStream_t (default: the legacy default stream). */
 int rssync_set_stream(rssync_problem* p, void* cuda_stream);
 /* Record CUDA events around the PreSync grid kernel so rssync_get_stats can report its device

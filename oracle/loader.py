@@ -52,6 +52,7 @@ def lib():
     L.orc_destroy.argtypes = [C.c_void_p]
     L.orc_set_threads.argtypes = [C.c_void_p, C.c_int]
     L.orc_set_rng.argtypes = [C.c_void_p, C.c_uint64, C.c_uint64]
+    L.orc_set_loss_mode.argtypes = [C.c_void_p, C.c_int]
     L.orc_set_strict.argtypes = [C.c_void_p, C.c_int, c_i64_p, C.c_int]
     L.orc_call_no.argtypes = [C.c_void_p]
     L.orc_call_no.restype = C.c_uint64
@@ -141,6 +142,10 @@ class OracleProblem:
         self.L.orc_call_no.restype = C.c_uint64
         self.L.orc_call_no.argtypes = [C.c_void_p]
         return int(self.L.orc_call_no(self.h))
+
+    def set_loss_mode(self, simplified):
+        """simplified (no-translation) loss mode, see rssync_set_loss_mode"""
+        self.L.orc_set_loss_mode(self.h, 1 if simplified else 0)
 
     def set_threads(self, n):
         self.L.orc_set_threads(self.h, n)

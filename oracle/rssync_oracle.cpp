@@ -69,6 +69,11 @@ struct Oracle {
     // compare control flow with the compiled reference bit for bit
     bool strict = false;
     std::vector<int64_t> frame_order;
+    // simplified (no-translation) loss mode, thesis pdf-p.27-28 section 2.11 (no code in the reference
+    // checkout): the residual of a ray pair is |ar x br| itself -- the de-rotated rays of a purely
+    // rotating camera coincide -- instead of its component along the translation direction; no
+    // estimator, no per-frame L-BFGS.  Definition shared with the engine (include/rssync_b200.h).
+    bool simplified = false;
 };
 
 enum { OK = 0, E_INVALID = 1, E_NONFINITE = 2, E_ORDER = 3, E_STATE = 4 };
@@ -181,11 +186,45 @@ double norm_PM(const double* P, int n, const int* order, const double m[3]) {  /
     return std::sqrt(ss.value());
 }
 
+// simplified mode: the residual vector is the row norms; its 2-norm (the analogue of arma::norm(P * M))
+double norm_rows(const double* P, int n, const int* order) {
+    RaySum ss;
+    for (int j = 0; j < n; ++j) {
+        const double* r = P + 3 * order[j];
+        const double nr = std::sqrt(dot3(r, r));
+        ss.add(j, nr * nr);
+    }
+    return std::sqrt(ss.value());
+}
+// sum_i log1p((|P_i| k)^2)
+double loss_rows_P(const double* P, int n, const int* order, double k) {
+    RaySum acc;
+    for (int j = 0; j < n; ++j) {
+        const double* r = P + 3 * order[j];
+        const double v = std::sqrt(dot3(r, r)) * k;
+        acc.add(j, log1p_nonneg(v * v));
+    }
+    return acc.value();
+}
+
 // per-frame body of pre_sync (core_private.cpp:75-85) / DebugPreSync (:350-356)
 double presync_frame_cost(const Oracle& o, const Frame& f, double delay, uint64_t key, int* flags) {
     std::vector<double> P((size_t)f.n * 3), nP, r2;
     problem_matrix(o, f, delay, P.data());
     if (flags && !all_finite(P.data(), P.size())) *flags |= 1;
+    if (o.simplified) {  // same aggregation as :79-85 with the row norms as residuals
+        const double k = clamp_k(1.0 / norm_rows(P.data(), f.n, f.order.data()) * 1e2);
+        RaySum acc;
+        for (int j = 0; j < f.n; ++j) {
+            const double* row = &P[3 * f.order[j]];
+            const double r = std::sqrt(dot3(row, row)) * k;
+            if (flags && !std::isfinite(r)) *flags |= 4;
+            const double rho = log1p_nonneg(r * r);
+            if (flags && !std::isfinite(rho)) *flags |= 8;
+            acc.add(j, std::sqrt(rho));
+        }
+        return std::sqrt(acc.value());
+    }
     double M[3];
     guess_motion(P.data(), f.n, 20, key, M, nP, r2, o.strict);
     if (flags && !all_finite(M, 3)) *flags |= 2;
@@ -301,6 +340,7 @@ double loss3_P(const double* P, int n, const int* order, const double m[3], doub
 double loss3(const Oracle& o, const Frame& f, double delay, const double m[3], double k) {
     std::vector<double> P((size_t)f.n * 3);
     problem_matrix(o, f, delay, P.data());
+    if (o.simplified) return loss_rows_P(P.data(), f.n, f.order.data(), k);
     return o.strict ? orc_strict::loss3_P(P.data(), f.n, m, k) : loss3_P(P.data(), f.n, f.order.data(), m, k);
 }
 
@@ -453,6 +493,11 @@ int sync_impl(Oracle& o, double initial_delay, int64_t fb, int64_t fe, double ce
         FrameState& s = fs[j];
         std::vector<double> P((size_t)s.f->n * 3), nP, r2;
         problem_matrix(o, *s.f, delay, P.data());
+        if (o.simplified) {  // no translation direction: only the scale k, from the row norms
+            s.m[0] = s.m[1] = s.m[2] = 0.0;
+            s.k = clamp_k(1.0 / norm_rows(P.data(), s.f->n, s.f->order.data()) * 1e2);
+            return;
+        }
         uint64_t key = rng_task_key(o.seed, kStreamSyncInit, call_no, 0, s.id);
         guess_motion(P.data(), s.f->n, 200, key, s.m, nP, r2, strict);
         s.k = strict ? clamp_k(1 / orc_strict::norm_PM(P.data(), s.f->n, s.m) * 1e2)
@@ -481,8 +526,9 @@ int sync_impl(Oracle& o, double initial_delay, int64_t fb, int64_t fe, double ce
             std::vector<double> P((size_t)s.f->n * 3);
             double g[3];
             problem_matrix(o, *s.f, x, P.data());
-            v[j] = strict ? orc_strict::loss5_P(P.data(), s.f->n, s.m, s.k, g)
-                          : loss5_P(P.data(), s.f->n, s.f->order.data(), s.m, s.k, g);
+            v[j] = o.simplified ? loss_rows_P(P.data(), s.f->n, s.f->order.data(), s.k)
+                   : strict     ? orc_strict::loss5_P(P.data(), s.f->n, s.m, s.k, g)
+                                : loss5_P(P.data(), s.f->n, s.f->order.data(), s.m, s.k, g);
             l[j] = loss3(o, *s.f, x - h, s.m, s.k);
             r[j] = loss3(o, *s.f, x + h, s.m, s.k);
         });
@@ -508,7 +554,7 @@ int sync_impl(Oracle& o, double initial_delay, int64_t fb, int64_t fe, double ce
         n_outer++;
         // do_opt_motion, :262-296
         std::vector<LbfgsStats> st(fs.size());
-        parallel_for(o.threads, fs.size(), [&](size_t j) {
+        if (!o.simplified) parallel_for(o.threads, fs.size(), [&](size_t j) {
             FrameState& s = fs[j];
             std::vector<double> P((size_t)s.f->n * 3);
             problem_matrix(o, *s.f, delay, P.data());
@@ -572,6 +618,7 @@ void orc_set_strict(void* h, int strict, const int64_t* frame_order, int n) {
     o.strict = strict != 0;
     o.frame_order.assign(frame_order, frame_order + (frame_order ? n : 0));
 }
+void orc_set_loss_mode(void* h, int simplified) { ((Oracle*)h)->simplified = simplified != 0; }
 void orc_set_rng(void* h, uint64_t seed, uint64_t call_no) {
     ((Oracle*)h)->seed = seed;
     ((Oracle*)h)->call_no = call_no;

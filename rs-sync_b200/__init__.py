@@ -37,6 +37,7 @@ C_ABI_SYMBOLS = [
     "rssync_sync_batch_ex", "rssync_probe_guess_motion_ex", "rssync_integrate_gyro",
     "rssync_orientation_search", "rssync_orientation_search_ex", "rssync_presync_windows", "rssync_set_track_pixels",
     "rssync_create_multi", "rssync_device_count", "rssync_frame_table", "rssync_device_state", "rssync_adopt_state",
+    "rssync_set_loss_mode",
 ]
 # Itanium-ABI symbols of the C++ drop-in face (same set the reference's librssync_core exports)
 CXX_ABI_SYMBOLS = [
@@ -123,6 +124,7 @@ def load_library():
                                        C.POINTER(C.c_uint64), c_double_p, c_double_p]
     L.rssync_last_sync_trace.argtypes = [P, c_double_p, c_double_p, C.c_int]
     L.rssync_set_rng.argtypes = [P, C.c_uint64, C.c_uint64]
+    L.rssync_set_loss_mode.argtypes = [P, C.c_int]
     L.rssync_call_counter.argtypes = [P]
     L.rssync_call_counter.restype = C.c_uint64
     L.rssync_set_stream.argtypes = [P, C.c_void_p]
@@ -368,6 +370,10 @@ class SyncProblem:
 
     def set_kernel_timing(self, enabled=True):
         self._check(self.L.rssync_set_kernel_timing(self.h, 1 if enabled else 0))
+
+    def set_loss_mode(self, simplified):
+        """False: the reference's loss; True: the thesis' simplified (no-translation) variant"""
+        self._check(self.L.rssync_set_loss_mode(self.h, 1 if simplified else 0))
 
     def set_rng(self, seed, call_no=0):
         self._check(self.L.rssync_set_rng(self.h, seed, call_no))

@@ -239,6 +239,7 @@ struct rssync_problem {
     size_t total_rays = 0;
 
     uint64_t seed = 100, call_no = 0;
+    bool simplified = false;  // rssync_set_loss_mode
 
     // ---- several GPUs behind one problem (rssync_create_multi) -----------------------------------
     // The problem the caller holds is the PRIMARY: it takes every Set* call and holds the one
@@ -511,7 +512,7 @@ int presync_grid_impl(rssync_problem* p, int64_t fb, int64_t fe, const double* d
             waited = run_dep[0];
         }
         rs::launch_presync_tasks(dd, p->d_frames.ptr, F, max_n, p->d_delays.ptr, n, p->seed, stream_id, call_no,
-                                 idx_base, p->d_framecost.ptr, F, p->d_flags.ptr, p->stream, nullptr, max_chunk);
+                                 idx_base, p->d_framecost.ptr, F, p->d_flags.ptr, p->stream, nullptr, max_chunk, p->simplified);
     } else {
         // The runs go round-robin to a few side streams: kernels of one stream run one after the
         // other, so a single stream would leave the tail of every run (its last blocks) unshared;
@@ -531,7 +532,7 @@ int presync_grid_impl(rssync_problem* p, int64_t fb, int64_t fe, const double* d
             }
             rs::launch_presync_tasks(dd, p->d_frames.ptr + f0, run_end[r] - f0, max_n, p->d_delays.ptr, n, p->seed,
                                      stream_id, call_no, idx_base, p->d_framecost.ptr + f0, F, p->d_flags.ptr, gs,
-                                     nullptr, max_chunk);
+                                     nullptr, max_chunk, p->simplified);
             f0 = run_end[r];
         }
         for (int k = 0; k < rssync_problem::kGridStreams; ++k) {
@@ -627,6 +628,7 @@ int sync_lane_begin(rssync_problem* p, SyncLane& L, const rs::DeviceData& dd, co
     L.b.S = n;
     L.b.m = L.d_m.ptr;
     L.b.k = L.d_k.ptr;
+    L.b.simplified = p->simplified ? 1 : 0;
     L.st.assign(n, SyncPointState());
     L.iters = 0;
     L.phase = SyncLane::Running;
@@ -685,7 +687,7 @@ int sync_lane_launch(rssync_problem* p, SyncLane& L, const rs::DeviceData& dd, b
         uint64_t tasks = 0;
         for (int s = 0; s < n; ++s)
             if (ha[s]) tasks += (uint64_t)L.sp_frames[(size_t)s];
-        p->sync_row_builds += tasks * (4 + kTrials);  // at the delay (L-BFGS), x0, x0 -/+ h, the trial points
+        p->sync_row_builds += tasks * ((p->simplified ? 3 : 4) + kTrials);  // at the delay (L-BFGS), x0, x0 -/+ h, the trial points
         p->sync_loss_evals += tasks * (3 + kTrials);
         p->sync_outer_total += (uint64_t)n_active;
     } else {
@@ -815,7 +817,7 @@ int sync_batch_impl(rssync_problem* p, int n, const double* initial, const int64
     p->sync_outer = 0;
     p->sync_evals = 0;
     p->sync_row_builds = p->sync_loss_evals = p->sync_outer_total = 0;
-    p->sync_init_tasks = (uint64_t)tasks.size();
+    p->sync_init_tasks = p->simplified ? 0 : (uint64_t)tasks.size();
     p->sync_row_builds += (uint64_t)tasks.size();  // GuessMotion / GuessK build the rows once (:125-133 builds them twice)
 
     if (!p->ev_sync_ready) CUDA_TRY(p, cudaEventCreateWithFlags(&p->ev_sync_ready, cudaEventDisableTiming));
@@ -930,6 +932,7 @@ int multi_replicate(rssync_problem* p) {
         r->q0 = p->q0; r->sr = p->sr; r->nq = p->nq;
         r->used = p->used; r->dev_used = p->dev_used; r->total_rays = p->total_rays; r->garbage = p->garbage;
         r->seed = p->seed;
+        r->simplified = p->simplified;
         cudaError_t e = cudaStreamSynchronize(r->stream);  // nothing of an earlier call still reads the buffers
         if (e == cudaSuccess) e = r->d_rays.reserve(std::max<size_t>(rays, 1) * 8);
         if (e == cudaSuccess) e = r->d_orig.reserve(std::max<size_t>(rays, 1));
@@ -975,7 +978,8 @@ int grid_enqueue_rank(rssync_problem* q, const std::vector<FrameDesc>& sel, int 
     if (int rc = h2d(q, q->d_delays.ptr, delays, sizeof(double) * cnt)) return rc;
     if (timed) CUDA_TRY(q, cudaEventRecord(q->ev0, q->stream));
     rs::launch_presync_tasks(q->device_data(), q->d_frames.ptr, F, max_n, q->d_delays.ptr, cnt, q->seed, stream_id,
-                             call_no, idx_base, q->d_framecost.ptr, F, d_flags_dst, q->stream, nullptr, max_chunk);
+                             call_no, idx_base, q->d_framecost.ptr, F, d_flags_dst, q->stream, nullptr, max_chunk,
+                             q->simplified);
     if (timed) CUDA_TRY(q, cudaEventRecord(q->ev1, q->stream));
     rs::launch_presync_reduce(q->d_framecost.ptr, F, cnt, d_costs_dst, q->stream);
     CUDA_TRY(q, cudaGetLastError());
@@ -1897,7 +1901,8 @@ int rssync_presync_windows(rssync_problem* p, int n, double initial, const int64
         CUDA_TRY(p, cudaMemsetAsync(p->d_flags.ptr, 0, 2 * sizeof(unsigned), p->stream));
         rs::launch_presync_grid(p->device_data(), p->d_frames.ptr, F, max_n, p->d_delays.ptr, D, p->seed,
                                 rs::kStreamPreSync, 0, 0, p->d_framecost.ptr, p->d_costs.ptr, p->d_flags.ptr,
-                                p->stream, nullptr, nullptr, p->d_frame_call.ptr, p->d_win_begin.ptr, n, max_chunk);
+                                p->stream, nullptr, nullptr, p->d_frame_call.ptr, p->d_win_begin.ptr, n, max_chunk,
+                                p->simplified);
         CUDA_TRY(p, cudaGetLastError());
         if (int rc = d2h(p, costs.data(), p->d_costs.ptr, sizeof(double) * n * D)) return rc;
         if (int rc = d2h(p, flags, p->d_flags.ptr, 2 * sizeof(unsigned))) return rc;
@@ -2119,6 +2124,13 @@ int rssync_set_rng(rssync_problem* p, uint64_t seed, uint64_t call_no) {
     return RSSYNC_OK;
 }
 uint64_t rssync_call_counter(const rssync_problem* p) { return p ? p->call_no : 0; }
+
+int rssync_set_loss_mode(rssync_problem* p, int mode) {
+    if (!p || (mode != RSSYNC_LOSS_FULL && mode != RSSYNC_LOSS_SIMPLIFIED)) return RSSYNC_E_INVALID;
+    p->simplified = mode == RSSYNC_LOSS_SIMPLIFIED;
+    for (rssync_problem* r : p->replicas) r->simplified = p->simplified;
+    return RSSYNC_OK;
+}
 
 int rssync_set_stream(rssync_problem* p, void* s) {
     if (!p) return RSSYNC_E_INVALID;

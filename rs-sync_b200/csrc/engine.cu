@@ -745,6 +745,33 @@ __device__ __noinline__ double warp_loss3_smem(const double* __restrict__ sP, in
     return warp_sum(acc);
 }
 
+// Simplified (no-translation) loss mode, thesis pdf-p.27-28 section 2.11: the residual of a ray pair
+// is |ar x br| itself -- the de-rotated rays of a purely rotating camera coincide -- instead of its
+// component along the translation direction: sum_i log1p((|P_i| k)^2).  (The reference checkout has
+// no code for it; the definition is this engine's and the oracle's, include/rssync_b200.h.)
+__device__ __noinline__ double warp_loss_rows_smem(const double* __restrict__ sP, int NP, int nslots,
+                                                   int lane, double k, const double* __restrict__ tab) {
+    double acc = 0.0;
+    for (int s = 0; s < nslots; ++s) {
+        const int i = s * 32 + lane;
+        const double p0 = sP[i], p1 = sP[NP + i], p2 = sP[2 * NP + i];
+        const double r = sqrt(dot3(p0, p1, p2, p0, p1, p2)) * k;
+        acc = acc + log1p_nonneg(r * r, tab);
+    }
+    return warp_sum(acc);
+}
+// arma::norm of the residual vector (the row norms)
+__device__ __forceinline__ double warp_norm_rows(const double* sP, int NP, int nslots, int lane) {
+    double ss = 0.0;
+    for (int s = 0; s < nslots; ++s) {
+        const int i = s * 32 + lane;
+        const double p0 = sP[i], p1 = sP[NP + i], p2 = sP[2 * NP + i];
+        const double nr = sqrt(dot3(p0, p1, p2, p0, p1, p2));
+        ss = ss + nr * nr;
+    }
+    return sqrt(warp_sum(ss));
+}
+
 // FrameState::Loss 5-arg (core_private.cpp:92-115): value and d/dm in closed form of the
 // forward-mode chain (inline_utils.hpp:19-48)
 struct Loss5 {
@@ -1113,7 +1140,9 @@ __device__ __noinline__ void grid_stage_unit(const DeviceData& dd, const FrameDe
     }
 }
 
-template <int SLOTS>
+// SIMPLE: the simplified (no-translation) loss mode, a separate instantiation so that the
+// reference's path carries none of its branches
+template <int SLOTS, bool SIMPLE>
 __global__ void __launch_bounds__(GridCfg<SLOTS>::kWarps * 32, GridCfg<SLOTS>::kMinBlocks)
 presync_kernel(DeviceData dd, const FrameDesc* __restrict__ frames, int F,
                const double* __restrict__ delays, int D, int chunk, int cpf, uint64_t seed,
@@ -1121,6 +1150,7 @@ presync_kernel(DeviceData dd, const FrameDesc* __restrict__ frames, int F,
                uint64_t idx_base, double* __restrict__ framecost, int cost_stride,
                unsigned* __restrict__ flags, int staged) {
     using Cfg = GridCfg<SLOTS>;
+    constexpr bool simplified = SIMPLE;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     constexpr int NP = SLOTS * 32;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -1216,8 +1246,9 @@ presync_kernel(DeviceData dd, const FrameDesc* __restrict__ frames, int F,
             rng_task_key(rng_prefix(seed, stream, frame_call_no ? frame_call_no[fi] : call_no,
                                     idx_base + (uint64_t)di),
                          fd.id);
-        double M[3];
-        unsigned bad = warp_ransac<SLOTS>(dd, fd, w, 20, key, lane, M, flags + 1);  // core_private.cpp:77
+        double M[3] = {0.0, 0.0, 0.0};
+        unsigned bad = 0u;
+        if (!simplified) bad = warp_ransac<SLOTS>(dd, fd, w, 20, key, lane, M, flags + 1);  // core_private.cpp:77
         // :79-85
         __syncwarp();
         // rows past the frame's last ray are zero: they add 0 to the norm and log1p(0) = 0 to the loss.
@@ -1235,7 +1266,9 @@ presync_kernel(DeviceData dd, const FrameDesc* __restrict__ frames, int F,
                 const int i = (s0 + j) * 32 + lane;
                 pm[j] = 0.0;
                 if (s0 + j < SLOTS) {
-                    pm[j] = dot3(w.P[i], w.P[NP + i], w.P[2 * NP + i], M[0], M[1], M[2]);
+                    const double p0 = w.P[i], p1 = w.P[NP + i], p2 = w.P[2 * NP + i];
+                    // simplified mode: the residual is the row's norm
+                    pm[j] = simplified ? sqrt(dot3(p0, p1, p2, p0, p1, p2)) : dot3(p0, p1, p2, M[0], M[1], M[2]);
                     w.P[i] = pm[j];
                 }
             }
@@ -1243,7 +1276,7 @@ presync_kernel(DeviceData dd, const FrameDesc* __restrict__ frames, int F,
             for (int j = 0; j < LU; ++j) ss = ss + pm[j] * pm[j];
         }
         const double kv = clamp_k(1.0 / sqrt(warp_sum(ss)) * 1e2);  // arma::norm(P * M), :79
-        const double scale = kv / sqrt(dot3(M[0], M[1], M[2], M[0], M[1], M[2]));
+        const double scale = simplified ? kv : kv / sqrt(dot3(M[0], M[1], M[2], M[0], M[1], M[2]));
         double acc = 0.0;
 #pragma unroll 1
         for (int s0 = 0; s0 < SLOTS; s0 += LU) {
@@ -1261,6 +1294,7 @@ presync_kernel(DeviceData dd, const FrameDesc* __restrict__ frames, int F,
         // the panic conditions of :76-83: non-finite values propagate into the cost, so the stage
         // that produced them is only looked for when the cost (or a row) is not finite
         if (bad || !is_finite(cost)) {
+            if (simplified && !is_finite(ss)) bad |= kFlagP;  // no estimator to notice non-finite rows
             bad |= presync_diagnose(w.P, (fd.n + 31) >> 5, lane, scale, M[0], M[1], M[2], tab);
             bad = __reduce_or_sync(FULL, bad);
             if (bad && lane == 0) atomicOr(flags, bad);
@@ -1313,6 +1347,14 @@ sync_init_kernel(DeviceData dd, SyncBatchDev b, const double* __restrict__ sp_de
         const int nslots = (task.fd.n + 31) >> 5;
         __syncwarp();
         build_rows_smem(dd, task.fd, sp_delay[task.sp], lane, w, NP);
+        if (b.simplified) {  // no translation direction: only the scale, from the row norms
+            const double nr = warp_norm_rows(w.P, NP, nslots, lane);
+            if (lane == 0) {
+                b.m[3 * t + 0] = 0.0; b.m[3 * t + 1] = 0.0; b.m[3 * t + 2] = 0.0;
+                b.k[t] = clamp_k(1.0 / nr * 1e2);
+            }
+            continue;
+        }
         const uint64_t key =
             rng_task_key(rng_prefix(seed, kStreamSyncInit, sp_callno[task.sp], 0), task.fd.id);
         double M[3];
@@ -1362,7 +1404,7 @@ sync_motion_fgrad_kernel(DeviceData dd, SyncBatchDev b, const double* __restrict
         double m[3] = {b.m[3 * t], b.m[3 * t + 1], b.m[3 * t + 2]};
         const double k = b.k[t];
         const double x0 = sp_x0[task.sp];
-        for (int j = 0; j < 4; ++j) {
+        for (int j = b.simplified ? 1 : 0; j < 4; ++j) {  // (simplified mode: no direction to refine)
             const double delay = (j == 0)   ? sp_delay[task.sp]
                                  : (j == 1) ? x0
                                  : (j == 2) ? x0 - kNumericDiffStep
@@ -1380,6 +1422,9 @@ sync_motion_fgrad_kernel(DeviceData dd, SyncBatchDev b, const double* __restrict
                     if (stats) { stats[2 * t] = it; stats[2 * t + 1] = ev; }
                     if (evals_total) atomicAdd(evals_total, (unsigned long long)ev);
                 }
+            } else if (b.simplified) {
+                const double v = warp_loss_rows_smem(w.P, NP, (task.fd.n + 31) >> 5, lane, k, tab);
+                if (lane == 0) scratch[3 * t + (j - 1)] = v;
             } else if (j == 1) {
                 const Loss5 e = warp_loss5_reg<SLOTS>(p, m[0], m[1], m[2], k, tab);
                 if (lane == 0) scratch[3 * t] = e.f;
@@ -1441,8 +1486,9 @@ sync_trials_kernel(DeviceData dd, SyncBatchDev b, int NP, const double* __restri
         const int nslots = (task.fd.n + 31) >> 5;
         __syncwarp();
         build_rows_smem(dd, task.fd, trial_delay[(size_t)task.sp * ntrial + j], lane, w, NP);
-        const double v = warp_loss3_smem(w.P, NP, nslots, lane, b.m[3 * t], b.m[3 * t + 1],
-                                         b.m[3 * t + 2], b.k[t], tab);
+        const double v = b.simplified ? warp_loss_rows_smem(w.P, NP, nslots, lane, b.k[t], tab)
+                                      : warp_loss3_smem(w.P, NP, nslots, lane, b.m[3 * t], b.m[3 * t + 1],
+                                                        b.m[3 * t + 2], b.k[t], tab);
         if (lane == 0) scratch[(size_t)t * ntrial + j] = v;
     }
 }
@@ -1827,11 +1873,11 @@ int presync_max_chunk(const double* h_delays, int D, double frame_span_s, double
 void launch_presync_tasks(const DeviceData& dd, const FrameDesc* d_frames, int F, int max_n,
                           const double* d_delays, int D, uint64_t seed, uint64_t stream, uint64_t call_no,
                           uint64_t idx_base, double* d_framecost, int cost_stride, unsigned* d_flags,
-                          cudaStream_t st, const uint64_t* d_frame_call_no, int max_chunk) {
+                          cudaStream_t st, const uint64_t* d_frame_call_no, int max_chunk, bool simplified) {
     if (F <= 0 || D <= 0) return;
     RS_DISPATCH_SLOTS(max_n, {
         using Cfg = GridCfg<SL>;
-        auto kern = presync_kernel<SL>;
+        auto kern = simplified ? presync_kernel<SL, true> : presync_kernel<SL, false>;
         allow_smem(kern, Cfg::kSmem);
         const int sm_count = sm_count_of(current_device());
         const int per_sm = blocks_per_sm(kern, Cfg::kWarps * 32, Cfg::kSmem);
@@ -1875,10 +1921,10 @@ void launch_presync_grid(const DeviceData& dd, const FrameDesc* d_frames, int F,
                          uint64_t call_no, uint64_t idx_base, double* d_framecost, double* d_costs,
                          unsigned* d_flags, cudaStream_t st, cudaEvent_t ev_begin, cudaEvent_t ev_end,
                          const uint64_t* d_frame_call_no, const int* d_win_begin, int n_windows,
-                         int max_chunk) {
+                         int max_chunk, bool simplified) {
     if (ev_begin && F > 0 && D > 0) cudaEventRecord(ev_begin, st);
     launch_presync_tasks(dd, d_frames, F, max_n, d_delays, D, seed, stream, call_no, idx_base, d_framecost, F,
-                         d_flags, st, d_frame_call_no, max_chunk);
+                         d_flags, st, d_frame_call_no, max_chunk, simplified);
     if (ev_end && F > 0 && D > 0) cudaEventRecord(ev_end, st);
     launch_presync_reduce(d_framecost, F, D, d_costs, st, d_win_begin, n_windows);
 }

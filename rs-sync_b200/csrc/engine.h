@@ -46,7 +46,7 @@ void launch_presync_grid(const DeviceData& dd, const FrameDesc* d_frames, int F,
                          // concatenated, frame f belongs to the call d_frame_call_no[f], window w
                          // covers frames [d_win_begin[w], d_win_begin[w+1]); d_costs is W x D
                          const uint64_t* d_frame_call_no = nullptr, const int* d_win_begin = nullptr,
-                         int n_windows = 0, int max_chunk = 0);
+                         int n_windows = 0, int max_chunk = 0, bool simplified = false);
 
 // How many consecutive delays of the (host copy of the) delay list one work unit of the grid kernel
 // may hold so that the spline window of any frame whose timestamps span at most frame_span_s seconds
@@ -61,7 +61,8 @@ int presync_max_chunk(const double* h_delays, int D, double frame_span_s, double
 void launch_presync_tasks(const DeviceData& dd, const FrameDesc* d_frames, int F, int max_n,
                           const double* d_delays, int D, uint64_t seed, uint64_t stream, uint64_t call_no,
                           uint64_t idx_base, double* d_framecost, int cost_stride, unsigned* d_flags,
-                          cudaStream_t st, const uint64_t* d_frame_call_no = nullptr, int max_chunk = 0);
+                          cudaStream_t st, const uint64_t* d_frame_call_no = nullptr, int max_chunk = 0,
+                          bool simplified = false);
 void launch_presync_reduce(const double* d_framecost, int F, int D, double* d_costs, cudaStream_t st,
                            const int* d_win_begin = nullptr, int n_windows = 0);
 
@@ -79,6 +80,7 @@ struct SyncBatchDev {
     int S;
     double* m;              // T x 3 translation directions (FrameState::motion_vec)
     double* k;              // T   (FrameState::var_k)
+    int simplified;         // simplified (no-translation) loss mode: residual = |row|, m unused
 };
 // GuessMotion + GuessK at sp_delay[sp] (core_private.cpp:125-133, 218-223)
 void launch_sync_init(const DeviceData& dd, const SyncBatchDev& b, const double* d_sp_delay,

@@ -608,3 +608,40 @@ def test_adopted_device_state_reproduces_the_source(rsb, w_small):
         p.SetTrackResult(10 ** 5, w.ts_a[3], w.ts_b[3], w.rays_a[3], w.rays_b[3], w.n_rays)
     assert np.array_equal(a.presync_grid(10 ** 5, 10 ** 5 + 1, delays), b.presync_grid(10 ** 5, 10 ** 5 + 1, delays))
     assert b.stats()["frames"] == w.n_frames + 1
+
+
+def test_simplified_loss_mode_matches_oracle(rsb, oracle_loader, w_small):
+    """the thesis' simplified (no-translation) loss mode (rssync_set_loss_mode): PreSync curve, argmin
+    and the whole Sync trajectory equal the oracle's; switching back restores the reference's loss"""
+    w = w_small
+    g = rsb.SyncProblem(seed=100).load(w, bulk=True)
+    o = oracle_loader.OracleProblem(threads=8, seed=100).load(w)
+    fb, fe = int(w.frame_ids[0]), int(w.frame_ids[-1]) + 1
+    full = g.DebugPreSync(0.0, fb, fe, 0.1, 41)[1]
+    for p in (g, o):
+        p.set_loss_mode(True)
+        p.set_rng(100, 7)
+    dg, cg = g.DebugPreSync(0.0, fb, fe, 0.1, 41)
+    do, co = o.DebugPreSync(0.0, fb, fe, 0.1, 41)
+    assert np.array_equal(dg, do) and rel_err(cg, co) <= TOL
+    assert int(np.argmin(cg)) == int(np.argmin(co))
+    assert abs(dg[int(np.argmin(cg))] - w.true_delay[0]) <= 0.005
+    assert not np.allclose(cg, full)
+    pg = g.PreSync(0.0, fb, fe, w.presync_step, w.presync_radius)
+    po = o.PreSync(0.0, fb, fe, w.presync_step, w.presync_radius)
+    assert pg[1] == po[1] and rel_err(pg[0], po[0]) <= TOL
+    sg = g.Sync(pg[1], fb, fb + 40, 0.0, 0.2)
+    so = o.Sync(po[1], fb, fb + 40, 0.0, 0.2, trace=True)
+    tdg, _ = g.last_sync_trace()
+    assert len(tdg) == len(so[2]) and rel_err(tdg, so[2]) <= TOL
+    assert rel_err(sg[1], so[1]) <= TOL and rel_err(sg[0], so[0]) <= TOL
+    assert abs(sg[1] - w.true_delay[0]) < 3e-3
+    st = g.stats()
+    assert st["sync_lbfgs_evals"] == 0 and st["sync_init_tasks"] == 0 and st["sync_row_builds"] > 0
+    # a batch, windows in one launch
+    fbs = np.array([fb, fb + 12])
+    cb, db = g.sync_batch(np.array([0.036, 0.039]), fbs, fbs + 30, 0.0, 0.2)
+    cbo, dbo = o.sync_batch(np.array([0.036, 0.039]), fbs, fbs + 30, 0.0, 0.2)
+    assert rel_err(db, dbo) <= TOL and rel_err(cb, cbo) <= TOL
+    g.set_loss_mode(False)
+    assert np.array_equal(g.DebugPreSync(0.0, fb, fe, 0.1, 41)[1] != cg, np.ones(41, dtype=bool))

@@ -229,3 +229,20 @@ def test_oracle_reproduces_committed_golden_curve(oracle_loader, w_tiny):
     sc, sd = o.Sync(0.035, fb, fe - 1, 0.0, 0.2)
     assert rel_err(sd, float.fromhex(g["sync_delay_hex"])) <= 1e-9
     assert rel_err(sc, float.fromhex(g["sync_cost_hex"])) <= 1e-9
+
+
+def test_simplified_loss_mode_recovers_the_delay(oracle_loader):
+    """the thesis' simplified (no-translation) variant as the oracle defines it: the loss curve has its
+    minimum near the true delay on a scene with little translation, and Sync refines it"""
+    import importlib
+    synth = importlib.import_module("rs-sync_b200.synth")
+    w = synth.make_workload("small")
+    o = oracle_loader.OracleProblem(threads=4, seed=100).load(w)
+    o.set_loss_mode(True)
+    fb, fe = int(w.frame_ids[0]), int(w.frame_ids[-1]) + 1
+    d, c = o.DebugPreSync(0.0, fb, fe, 0.1, 41)
+    assert abs(d[int(np.argmin(c))] - w.true_delay[0]) <= 0.005
+    cost, delay = o.Sync(float(d[int(np.argmin(c))]), fb, fb + 40, 0.0, 0.2)
+    assert abs(delay - w.true_delay[0]) < 3e-3 and cost > 0
+    o.set_loss_mode(False)
+    assert not np.allclose(o.DebugPreSync(0.0, fb, fe, 0.1, 41)[1], c)
