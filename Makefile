@@ -13,11 +13,11 @@ OBJS     := $(OUT)/engine.o $(OUT)/capi.o $(OUT)/host_ingest.o $(OUT)/cxx_dropin
 all: lib oracle
 lib: $(OUT)/librssync_b200.so
 
-$(OUT)/engine.o: $(SRC)/engine.cu $(SRC)/engine.h $(SRC)/device_math.cuh $(SRC)/rng.h
+$(OUT)/engine.o: $(SRC)/engine.cu $(SRC)/engine.h $(SRC)/device_math.cuh $(SRC)/rng.h $(SRC)/spec_trig.h $(SRC)/gyro_scan.h
 	@mkdir -p $(OUT)
 	$(NVCC) $(NVFLAGS) -Xptxas -v -c $< -o $@ 2> $(OUT)/engine.ptxas.log || (cat $(OUT)/engine.ptxas.log; false)
 
-$(OUT)/%.o: $(SRC)/%.cpp $(SRC)/engine.h $(SRC)/host_ingest.h $(SRC)/rng.h include/rssync_b200.h include/rssync.h
+$(OUT)/%.o: $(SRC)/%.cpp $(SRC)/engine.h $(SRC)/host_ingest.h $(SRC)/rng.h $(SRC)/spec_trig.h $(SRC)/gyro_scan.h $(SRC)/nccl_dyn.h include/rssync_b200.h include/rssync.h
 	@mkdir -p $(OUT)
 	$(NVCC) $(NVFLAGS) -c $< -o $@
 

@@ -149,7 +149,12 @@ int rssync_last_sync_trace(const rssync_problem* p, double* delays, double* step
  * rad/s; timestamps in seconds; quats_out: count x 4 (w,x,y,z).  orientation: a gyro_orientation
  * string of the reference's config (core_testcode.cpp:186-190) or NULL for "XYZ"; character i names
  * the input axis routed to output axis i, lower case flips its sign.  (The reference delegates
- * this mapping to the third-party telemetry-parser crate; the convention here is ours.)  Host code. */
+ * this mapping to the third-party telemetry-parser crate; the convention here is ours.)  Host code;
+ * the orientation search runs the same arithmetic on the device.  Order of operations (part of the
+ * arithmetic contract, because every step normalises): the recurrence runs inside blocks of 512
+ * samples from the identity, the blocks are chained through their last values, and every sample is
+ * its block-local value times its block's prefix, normalised; sin / cos are the contract's
+ * (csrc/spec_trig.h).  Differs from one sequential recurrence with libm by rounding only. */
 int rssync_integrate_gyro(const double* timestamps_s, const double* gyro_xyz, size_t count,
                           const char* orientation, double* quats_out);
 /* The orientation search the reference keeps commented out in core_testcode.cpp:184-233 (README.md:
@@ -282,6 +287,9 @@ int rssync_probe_loss(rssync_problem* p, int64_t frame, double delay, const doub
 int rssync_probe_lbfgs(rssync_problem* p, int64_t frame, double delay, double* m3, double k,
                        double* f, int* iters, int* evals);
 int rssync_probe_log1p(const double* x, int n, double* out);
+/* sin (which = 0), cos (1), acos (2) of the arithmetic contract (csrc/spec_trig.h), evaluated by the
+ * library's host code (on_device = 0, no GPU needed) or by a kernel */
+int rssync_probe_spec_trig(const double* x, int n, int which, int on_device, double* out);
 
 #ifdef __cplusplus
 }

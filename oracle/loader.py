@@ -88,6 +88,7 @@ def lib():
     L.orc_lbfgs.argtypes = [C.c_void_p, C.c_int64, C.c_double, c_double_p, C.c_double, c_double_p,
                             C.POINTER(C.c_int), C.POINTER(C.c_int)]
     L.orc_log1p.argtypes = [c_double_p, C.c_int, c_double_p]
+    L.orc_spec_trig.argtypes = [c_double_p, C.c_int, C.c_int, c_double_p]
     L.orc_integrate_gyro.argtypes = [c_double_p, c_double_p, C.c_size_t, C.c_char_p, c_double_p]
     L.orc_slerp.argtypes = [c_double_p, c_double_p, C.c_double, c_double_p]
     L.orc_rng_index.argtypes = [C.c_uint64, C.c_uint64, C.c_uint64, C.c_uint64, C.c_int64, C.c_uint32,
@@ -324,6 +325,14 @@ def presync_delays(initial, step, radius):
     n = L.orc_presync_delays(initial, step, radius, None, 0)
     out = np.empty(n)
     L.orc_presync_delays(initial, step, radius, _dp(out), n)
+    return out
+
+
+def spec_trig(x, which):
+    """the contract's sin / cos / acos as the oracle restates them (oracle/spec_trig.hpp)"""
+    x = np.ascontiguousarray(x, dtype=np.float64)
+    out = np.empty_like(x)
+    lib().orc_spec_trig(_dp(x), x.size, {"sin": 0, "cos": 1, "acos": 2}[which], _dp(out))
     return out
 
 

@@ -12,6 +12,7 @@
 // reference seeds mt19937 from random_device) and ens::L_BFGS (un-vendored third-party code,
 // restated from its published algorithm).
 #include "oracle_math.hpp"
+#include "spec_trig.hpp"
 #include "oracle_strict.hpp"
 
 #include <algorithm>
@@ -91,8 +92,9 @@ void build_spline(Oracle& o, const double* quats, long n) {
     for (int c = 0; c < 4; ++c) spline_build_1d(quats + c, n, 4, o.rec.data(), c);
 }
 
-// quat_slerp (quat.cpp:55-74).  4-term dot accumulated left to right.
-void slerp(const double p[4], const double qin[4], double t, double out[4]) {
+// quat_slerp (quat.cpp:55-74).  4-term dot accumulated left to right.  spec: the contract's acos / sin
+// (spec_trig.hpp), what the engine computes; otherwise libm, what the reference calls.
+void slerp(const double p[4], const double qin[4], double t, double out[4], bool spec = false) {
     double q[4] = {qin[0], qin[1], qin[2], qin[3]};
     double d = ((p[0] * q[0] + p[1] * q[1]) + p[2] * q[2]) + p[3] * q[3];
     if (d < 0) {
@@ -100,11 +102,11 @@ void slerp(const double p[4], const double qin[4], double t, double out[4]) {
         d = ((p[0] * q[0] + p[1] * q[1]) + p[2] * q[2]) + p[3] * q[3];
     }
     double m1, m2;
-    const double theta = std::acos(d);
+    const double theta = spec ? orc::spec_acos(d) : std::acos(d);
     if (theta > 1e-9) {
-        const double st = std::sin(theta);
-        m1 = std::sin((1 - t) * theta) / st;
-        m2 = std::sin(t * theta) / st;
+        const double st = spec ? orc::spec_sin(theta) : std::sin(theta);
+        m1 = (spec ? orc::spec_sin((1 - t) * theta) : std::sin((1 - t) * theta)) / st;
+        m2 = (spec ? orc::spec_sin(t * theta) : std::sin(t * theta)) / st;
     } else {
         m1 = 1 - t;
         m2 = t;
@@ -668,7 +670,7 @@ int orc_set_gyro_var(void* h, const int64_t* ts, const double* quats, size_t cou
                                       [](int64_t a, uint64_t b) { return (uint64_t)a < b; }) - ts;
         if (idx > 0) {
             double u = 1. * (double)(t - (uint64_t)ts[idx - 1]) / (double)(ts[idx] - ts[idx - 1]);
-            slerp(quats + 4 * (idx - 1), quats + 4 * idx, u, &nq[4 * i]);
+            slerp(quats + 4 * (idx - 1), quats + 4 * idx, u, &nq[4 * i], !o.strict);
         } else {
             for (int c = 0; c < 4; ++c) nq[4 * i + c] = quats[4 * idx + c];
         }
@@ -873,32 +875,50 @@ int orc_integrate_gyro(const double* ts, const double* gyro, size_t count, const
             sgn[i] = at < 3 ? -1.0 : 1.0;
         }
     }
-    double q[4] = {1, 0, 0, 0};
-    for (size_t i = 0; i < count; ++i) {
-        if (i > 0) {
-            const double dt = ts[i] - ts[i - 1];                            // :44
-            double aa[3];
-            for (int c = 0; c < 3; ++c) aa[c] = sgn[c] * gyro[3 * i + src[c]] * dt;
-            const double theta_squared = (aa[0] * aa[0] + aa[1] * aa[1]) + aa[2] * aa[2];  // quat.cpp:6
-            double d[4];
-            if (theta_squared > 0.) {                                        // quat.cpp:8-12
-                const double theta = std::sqrt(theta_squared);
-                const double half_theta = theta * 0.5;
-                const double k = std::sin(half_theta) / theta;
-                d[0] = std::cos(half_theta); d[1] = aa[0] * k; d[2] = aa[1] * k; d[3] = aa[2] * k;
-            } else {                                                         // quat.cpp:13-16
-                d[0] = 1.; d[1] = aa[0] * 0.5; d[2] = aa[1] * 0.5; d[3] = aa[2] * 0.5;
-            }
-            const double p0 = d[0], p1 = d[1], p2 = d[2], p3 = d[3];
-            const double r0 = p0 * q[0] - p1 * q[1] - p2 * q[2] - p3 * q[3];  // quat.cpp:34-37
-            const double r1 = p0 * q[1] + p1 * q[0] + p2 * q[3] - p3 * q[2];
-            const double r2 = p0 * q[2] - p1 * q[3] + p2 * q[0] + p3 * q[1];
-            const double r3 = p0 * q[3] + p1 * q[2] - p2 * q[1] + p3 * q[0];
-            const double nrm = std::sqrt(r0 * r0 + r1 * r1 + r2 * r2 + r3 * r3);
-            q[0] = r0 / nrm; q[1] = r1 / nrm; q[2] = r2 / nrm; q[3] = r3 / nrm;  // :45
+    // The contract's order of operations (shared with the engine, host and device): the recurrence
+    // q_i = normalise(d_i (x) q_{i-1}) runs inside blocks of 512 samples, each from the identity; the
+    // blocks' last values are chained into per-block prefixes; every sample is then its block-local
+    // value times its block's prefix, normalised.  (The reference's caller runs one sequential
+    // recurrence, core_testcode.cpp:41-46; the two differ by rounding only.)
+    const size_t B = 512;
+    auto increment = [&](size_t i, double d[4]) {  // quat_from_aa(w_i dt_i), quat.cpp:5-17; d_0 = identity
+        if (i == 0) { d[0] = 1.; d[1] = d[2] = d[3] = 0.; return; }
+        const double dt = ts[i] - ts[i - 1];                            // :44
+        double aa[3];
+        for (int c = 0; c < 3; ++c) aa[c] = sgn[c] * gyro[3 * i + src[c]] * dt;
+        const double theta_squared = (aa[0] * aa[0] + aa[1] * aa[1]) + aa[2] * aa[2];  // quat.cpp:6
+        if (theta_squared > 0.) {                                        // quat.cpp:8-12
+            const double theta = std::sqrt(theta_squared);
+            const double half_theta = theta * 0.5;
+            const double k = orc::spec_sin(half_theta) / theta;
+            d[0] = orc::spec_cos(half_theta); d[1] = aa[0] * k; d[2] = aa[1] * k; d[3] = aa[2] * k;
+        } else {                                                         // quat.cpp:13-16
+            d[0] = 1.; d[1] = aa[0] * 0.5; d[2] = aa[1] * 0.5; d[3] = aa[2] * 0.5;
         }
-        for (int c = 0; c < 4; ++c) out[4 * i + c] = q[c];
+    };
+    auto mul_norm = [](const double* p, const double* q, double* out) {  // normalise(p (x) q), quat.cpp:34-37
+        const double r0 = ((p[0] * q[0] - p[1] * q[1]) - p[2] * q[2]) - p[3] * q[3];
+        const double r1 = ((p[0] * q[1] + p[1] * q[0]) + p[2] * q[3]) - p[3] * q[2];
+        const double r2 = ((p[0] * q[2] - p[1] * q[3]) + p[2] * q[0]) + p[3] * q[1];
+        const double r3 = ((p[0] * q[3] + p[1] * q[2]) - p[2] * q[1]) + p[3] * q[0];
+        const double nrm = std::sqrt(((r0 * r0 + r1 * r1) + r2 * r2) + r3 * r3);
+        out[0] = r0 / nrm; out[1] = r1 / nrm; out[2] = r2 / nrm; out[3] = r3 / nrm;  // :45
+    };
+    const double ident[4] = {1., 0., 0., 0.};
+    const size_t nb = (count + B - 1) / B;
+    std::vector<double> local(4 * count), prefix(4 * (nb + 1));
+    for (size_t b = 0; b < nb; ++b) {
+        const double* prev = ident;
+        for (size_t i = b * B; i < std::min(count, (b + 1) * B); ++i) {
+            double d[4];
+            increment(i, d);
+            mul_norm(d, prev, &local[4 * i]);
+            prev = &local[4 * i];
+        }
     }
+    for (int c = 0; c < 4; ++c) prefix[c] = ident[c];
+    for (size_t b = 0; b < nb; ++b) mul_norm(&local[4 * (std::min(count, (b + 1) * B) - 1)], &prefix[4 * b], &prefix[4 * (b + 1)]);
+    for (size_t i = 0; i < count; ++i) mul_norm(&local[4 * i], &prefix[4 * (i / B)], out + 4 * i);
     return 0;
 }
 
@@ -906,6 +926,11 @@ void orc_log1p(const double* x, int n, double* out) {
     for (int i = 0; i < n; ++i) out[i] = log1p_nonneg(x[i]);
 }
 void orc_slerp(const double* p, const double* q, double t, double* out) { slerp(p, q, t, out); }
+void orc_slerp_spec(const double* p, const double* q, double t, double* out) { slerp(p, q, t, out, true); }
+// which: 0 sin, 1 cos, 2 acos of the contract
+void orc_spec_trig(const double* x, int n, int which, double* out) {
+    for (int i = 0; i < n; ++i) out[i] = which == 0 ? orc::spec_sin(x[i]) : which == 1 ? orc::spec_cos(x[i]) : orc::spec_acos(x[i]);
+}
 uint32_t orc_rng_index(uint64_t seed, uint64_t stream, uint64_t call_no, uint64_t offset_idx,
                        int64_t frame, uint32_t iter, uint32_t k, uint32_t n) {
     return rng_index(rng_task_key(seed, stream, call_no, offset_idx, frame), iter, k, n);

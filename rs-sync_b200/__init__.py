@@ -37,7 +37,7 @@ C_ABI_SYMBOLS = [
     "rssync_sync_batch_ex", "rssync_probe_guess_motion_ex", "rssync_integrate_gyro",
     "rssync_orientation_search", "rssync_orientation_search_ex", "rssync_presync_windows", "rssync_set_track_pixels",
     "rssync_create_multi", "rssync_device_count", "rssync_frame_table", "rssync_device_state", "rssync_adopt_state",
-    "rssync_set_loss_mode",
+    "rssync_set_loss_mode", "rssync_probe_spec_trig",
 ]
 # Itanium-ABI symbols of the C++ drop-in face (same set the reference's librssync_core exports)
 CXX_ABI_SYMBOLS = [
@@ -144,6 +144,7 @@ def load_library():
     L.rssync_probe_lbfgs.argtypes = [P, C.c_int64, C.c_double, c_double_p, C.c_double, c_double_p,
                                      C.POINTER(C.c_int), C.POINTER(C.c_int)]
     L.rssync_probe_log1p.argtypes = [c_double_p, C.c_int, c_double_p]
+    L.rssync_probe_spec_trig.argtypes = [c_double_p, C.c_int, C.c_int, C.c_int, c_double_p]
     L.rssync_integrate_gyro.argtypes = [c_double_p, c_double_p, C.c_size_t, C.c_char_p, c_double_p]
     L.rssync_orientation_search.argtypes = [P, c_double_p, c_double_p, C.c_size_t, C.POINTER(C.c_char_p),
                                             C.c_int, C.c_double, C.c_int64, C.c_int64, C.c_double,
@@ -202,6 +203,17 @@ def probe_spline_system(quats):
     if rc != OK:
         raise RsSyncError(rc, "spline system probe failed")
     return rhs, diag
+
+
+def probe_spec_trig(x, which, on_device=False):
+    """the contract's sin / cos / acos (which = "sin" | "cos" | "acos"), host code or a device kernel"""
+    L = load_library()
+    x = _f64(x)
+    out = np.empty_like(x)
+    rc = L.rssync_probe_spec_trig(_dp(x), x.size, {"sin": 0, "cos": 1, "acos": 2}[which], 1 if on_device else 0, _dp(out))
+    if rc != OK:
+        raise RsSyncError(rc, "spec trig probe failed")
+    return out
 
 
 def probe_log1p(x):

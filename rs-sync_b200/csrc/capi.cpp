@@ -25,6 +25,7 @@
 #include "host_ingest.h"
 #include "nccl_dyn.h"
 #include "rng.h"
+#include "spec_trig.h"
 
 using rs::FrameDesc;
 
@@ -182,6 +183,7 @@ struct rssync_problem {
     double q0 = 0.0, sr = 0.0;
     size_t nq = 0;
     bool gyro_dirty = false;
+    bool gyro_on_device = false;  // the pending gyro was built from device-side inputs (no 9-double upload)
     // The spline coefficient solve (4 sequential recurrences, ~2.5 ms per minute of 1 kHz gyro) runs
     // on a worker thread so that it overlaps the caller's SetTrackResult calls; it is joined by the
     // first thing that needs the records.
@@ -240,6 +242,13 @@ struct rssync_problem {
 
     uint64_t seed = 100, call_no = 0;
     bool simplified = false;  // rssync_set_loss_mode
+    // device-side gyro ingest (variable-rate SetGyroQuaternions, orientation search): inputs,
+    // per-variant intermediates, and the spline elimination factors of the most recent track length
+    DevBuf<int64_t> d_var_ts;
+    DevBuf<double> d_var_in, d_var_q, d_var_y, d_var_rhs, d_var_rec, d_var_prefix, d_elim, d_os_costs;
+    DevBuf<unsigned char> d_var_orients;
+    DevBuf<unsigned> d_var_flags;
+    size_t elim_n = 0;
 
     // ---- several GPUs behind one problem (rssync_create_multi) -----------------------------------
     // The problem the caller holds is the PRIMARY: it takes every Set* call and holds the one
@@ -374,7 +383,8 @@ int flush(rssync_problem* p, bool keep_in_flight = false) {
     if (p->gyro_dirty) {  // the worker queued the copy and the finishing kernel on gyro_stream
         CUDA_TRY(p, p->gyro_copy_err);
         CUDA_TRY(p, cudaStreamWaitEvent(p->stream, p->ev_gyro, 0));
-        p->h2d += p->nq * 9 * sizeof(double);
+        if (!p->gyro_on_device) p->h2d += p->nq * 9 * sizeof(double);
+        p->gyro_on_device = false;
         p->gyro_dirty = false;
     }
     // frames set one by one after a bulk ingest are newer than it: their upload follows it
@@ -429,6 +439,21 @@ int start_gyro_worker(rssync_problem* p, size_t count) {
         if (e == cudaSuccess) e = cudaEventRecord(p->ev_gyro, p->gyro_stream);
         p->gyro_copy_err = e;
     });
+    return RSSYNC_OK;
+}
+
+// the spline system's elimination factors for n knots on the device: d_elim = {f_down[n], f_up[n], diag[n]}
+int upload_elimination(rssync_problem* p, size_t n, cudaStream_t st) {
+    if (p->elim_n == n && p->d_elim.ptr) return RSSYNC_OK;
+    const std::shared_ptr<const rs::SplineElimination> se = rs::spline_elimination(n);
+    CUDA_TRY(p, cudaStreamSynchronize(st));  // (a reallocation must not pull the buffer from under a running kernel)
+    CUDA_TRY(p, p->d_elim.reserve(3 * n));
+    CUDA_TRY(p, cudaMemcpyAsync(p->d_elim.ptr, se->f_down.data(), n * sizeof(double), cudaMemcpyHostToDevice, st));
+    CUDA_TRY(p, cudaMemcpyAsync(p->d_elim.ptr + n, se->f_up.data(), n * sizeof(double), cudaMemcpyHostToDevice, st));
+    CUDA_TRY(p, cudaMemcpyAsync(p->d_elim.ptr + 2 * n, se->diag.data(), n * sizeof(double), cudaMemcpyHostToDevice, st));
+    CUDA_TRY(p, cudaStreamSynchronize(st));  // the host vectors may go away with the cache entry
+    p->h2d += 3 * n * sizeof(double);
+    p->elim_n = n;
     return RSSYNC_OK;
 }
 
@@ -1234,6 +1259,9 @@ void rssync_destroy(rssync_problem* p) {
     p->h_pix.release(); p->d_pix.release(); p->d_pixframes.release(); p->d_stage.release();
     p->d_flags.release(); p->h_stage.release(); p->d_probe.release();
     p->d_gather.release(); p->h_gather.release();
+    p->d_var_ts.release(); p->d_var_in.release(); p->d_var_q.release(); p->d_var_y.release(); p->d_var_rhs.release();
+    p->d_var_rec.release(); p->d_var_prefix.release(); p->d_elim.release(); p->d_os_costs.release();
+    p->d_var_orients.release(); p->d_var_flags.release();
     if (p->owns_stream && p->stream) { cudaStreamSynchronize(p->stream); cudaStreamDestroy(p->stream); }
     for (SyncLane& L : p->lanes) L.release();
     if (p->ev_sync_ready) cudaEventDestroy(p->ev_sync_ready);
@@ -1260,31 +1288,58 @@ int rssync_set_gyro_fixed(rssync_problem* p, const double* quats, size_t count, 
     parallel_copy(p->h_gyro.ptr, quats, 4 * count * sizeof(double));  // the caller's buffer is only borrowed
     p->nq = count;
     p->gyro_dirty = true;
+    p->gyro_on_device = false;
     return start_gyro_worker(p, count);  // :139
 }
 
 int rssync_set_gyro_var(rssync_problem* p, const int64_t* ts, const double* quats, size_t count) {
     if (!p || !ts || !quats) return RSSYNC_E_INVALID;
-    std::vector<double> rq;
-    double sr = 0, q0 = 0;
-    rs::IngestStatus s = rs::resample_variable_rate(ts, quats, count, rq, sr, q0, p->err);
+    rs::ResamplePlan plan;
+    const rs::IngestStatus s = rs::plan_variable_rate(ts, count, plan, p->err);  // core_private.cpp:146-164
     if (s == rs::IngestStatus::Invalid) return RSSYNC_E_INVALID;
     if (s == rs::IngestStatus::NonFinite) return RSSYNC_E_NONFINITE;
     if (s == rs::IngestStatus::OutOfOrder) return RSSYNC_E_ORDER;
-    if (rq.size() / 4 > (size_t)INT32_MAX) { p->err = "set-gyro-quaternions: too many samples"; return RSSYNC_E_INVALID; }
+    if (count > (size_t)INT32_MAX) { p->err = "set-gyro-quaternions: too many samples"; return RSSYNC_E_INVALID; }
     join_gyro(p);
-    p->version++;
-    p->sr = sr;
-    p->q0 = q0;
     cudaSetDevice(p->device);
     if (p->gyro_dirty == false && p->nq) CUDA_TRY(p, cudaStreamSynchronize(p->stream));
-    if (p->gyro_stream) CUDA_TRY(p, cudaStreamSynchronize(p->gyro_stream));
-    const size_t n_out = rq.size() / 4;
-    CUDA_TRY(p, p->h_gyro.reserve(n_out * 9));
-    std::memcpy(p->h_gyro.ptr, rq.data(), rq.size() * sizeof(double));
-    p->nq = n_out;
-    p->gyro_dirty = true;
-    return start_gyro_worker(p, n_out);  // :189
+    if (!p->gyro_stream) CUDA_TRY(p, cudaStreamCreateWithFlags(&p->gyro_stream, cudaStreamNonBlocking));
+    if (!p->ev_gyro) CUDA_TRY(p, cudaEventCreateWithFlags(&p->ev_gyro, cudaEventDisableTiming));
+    CUDA_TRY(p, cudaStreamSynchronize(p->gyro_stream));
+    // The per-sample half (:166-182: lower_bound + slerp), the elimination sweeps of the spline system
+    // and the record build all run on the device, on the gyro stream; the call waits only for the
+    // resampling's non-finite flag, which the reference reports here (:180-181).
+    const size_t nq = plan.n_out;
+    cudaStream_t gs = p->gyro_stream;
+    CUDA_TRY(p, p->d_var_ts.reserve(count));
+    CUDA_TRY(p, p->d_var_in.reserve(count * 4));
+    CUDA_TRY(p, p->d_gyro.reserve(nq * 9));
+    CUDA_TRY(p, p->d_var_flags.reserve(1));
+    CUDA_TRY(p, cudaMemcpyAsync(p->d_var_ts.ptr, ts, count * sizeof(int64_t), cudaMemcpyHostToDevice, gs));
+    CUDA_TRY(p, cudaMemcpyAsync(p->d_var_in.ptr, quats, count * 4 * sizeof(double), cudaMemcpyHostToDevice, gs));
+    CUDA_TRY(p, cudaMemsetAsync(p->d_var_flags.ptr, 0, sizeof(unsigned), gs));
+    rs::launch_gyro_resample(p->d_var_ts.ptr, (int)count, p->d_var_in.ptr, 1, plan.tick0, plan.rate_hz, (int)nq,
+                             p->d_gyro.ptr, p->d_var_flags.ptr, gs);
+    unsigned bad = 0;
+    CUDA_TRY(p, cudaMemcpyAsync(&bad, p->d_var_flags.ptr, sizeof(unsigned), cudaMemcpyDeviceToHost, gs));
+    if (int rc = upload_elimination(p, nq, gs)) return rc;
+    CUDA_TRY(p, cudaMemcpyAsync(p->d_gyro.ptr + 8 * nq, p->d_elim.ptr + 2 * nq, nq * sizeof(double), cudaMemcpyDeviceToDevice, gs));
+    CUDA_TRY(p, cudaStreamSynchronize(gs));
+    p->h2d += count * (sizeof(int64_t) + 4 * sizeof(double));
+    if (bad) { p->err = "set-gyro-quaternions: non-finite sample after interpolation"; return RSSYNC_E_NONFINITE; }
+    p->version++;
+    p->sr = plan.sample_rate;        // :183
+    p->q0 = plan.first_timestamp;    // :184
+    p->nq = nq;
+    CUDA_TRY(p, p->d_rec.reserve(nq * 16));
+    rs::launch_spline_chains(p->d_gyro.ptr, p->d_elim.ptr, p->d_elim.ptr + nq, (int)nq, 1, p->d_gyro.ptr + 4 * nq, gs);
+    rs::launch_spline_finish(p->d_gyro.ptr, p->d_gyro.ptr + 4 * nq, p->d_gyro.ptr + 8 * nq, (int)nq, p->d_rec.ptr, gs);  // :189
+    CUDA_TRY(p, cudaGetLastError());
+    CUDA_TRY(p, cudaEventRecord(p->ev_gyro, gs));
+    p->gyro_copy_err = cudaSuccess;
+    p->gyro_dirty = true;  // the next compute call makes its stream wait for ev_gyro
+    p->gyro_on_device = true;
+    return RSSYNC_OK;
 }
 
 }  // extern "C"
@@ -1986,98 +2041,136 @@ int rssync_orientation_search_ex(rssync_problem* p, const double* timestamps_s, 
         for (rssync_problem* r : p->replicas) r->synced_version = ~0ull;
         return rc;
     }
-    struct Prep {
-        std::vector<double> sys;  // samples (nq x 4), rhs (nq x 4), diag (nq): the staging block's layout
-        double sr = 0, q0 = 0;
-        size_t nq = 0;
-        int rc = RSSYNC_OK;
-        std::string err;
-    };
-    std::vector<Prep> prep((size_t)n_orient);
+    // Single device.  Everything per variant runs on the device: integration (blocked scan),
+    // resampling onto the uniform grid, the spline system's sweeps, the record build, the loss grid.
+    // The host prepares what does not depend on the variant -- the microsecond timestamps
+    // (core_testcode.cpp:47-50), the resampling plan, the frame table, the delay grid -- queues the whole
+    // search and reads all curves back at the end.
+    if (count < 2 || count > (size_t)INT32_MAX) { p->err = "set-gyro-quaternions: need at least 2 samples"; return RSSYNC_E_INVALID; }
+    if (!(step > 0) || !std::isfinite(radius) || !std::isfinite(initial_delay)) {
+        p->err = "pre-sync: search_step must be > 0 and the search window finite";
+        return RSSYNC_E_INVALID;
+    }
+    std::vector<int> src((size_t)n_orient * 3);
+    std::vector<double> sgn((size_t)n_orient * 3);
+    for (int k = 0; k < n_orient; ++k)
+        if (!rs::parse_orientation(orientations[k], &src[(size_t)k * 3], &sgn[(size_t)k * 3])) {
+            p->err = std::string("orientation-search: malformed gyro_orientation '") +
+                     (orientations[k] ? orientations[k] : "(null)") + "'";
+            return RSSYNC_E_INVALID;
+        }
     std::vector<int64_t> ts_us(count);
     for (size_t i = 0; i < count; ++i) ts_us[i] = (int64_t)(timestamps_s[i] * 1000000);  // :47-50
-    auto prepare = [&](size_t k, size_t) {
-        Prep& pr = prep[k];
-        std::vector<double> quats(count * 4), rq;
-        if (!rs::integrate_gyro(timestamps_s, gyro_xyz, count, orientations[k], quats.data())) {
-            pr.rc = RSSYNC_E_INVALID;
-            pr.err = std::string("orientation-search: malformed gyro_orientation '") +
-                     (orientations[k] ? orientations[k] : "(null)") + "'";
-            return;
-        }
-        rs::IngestStatus st = rs::resample_variable_rate(ts_us.data(), quats.data(), count, rq, pr.sr, pr.q0, pr.err);
-        if (st != rs::IngestStatus::Ok) {
-            pr.rc = st == rs::IngestStatus::NonFinite ? RSSYNC_E_NONFINITE
-                    : st == rs::IngestStatus::OutOfOrder ? RSSYNC_E_ORDER : RSSYNC_E_INVALID;
-            return;
-        }
-        pr.nq = rq.size() / 4;
-        pr.sys.resize(pr.nq * 9);
-        std::copy(rq.begin(), rq.end(), pr.sys.begin());
-        rs::build_spline_system(pr.sys.data(), pr.nq, pr.sys.data() + 4 * pr.nq, pr.sys.data() + 8 * pr.nq);
-    };
-    // The variants are prepared by a few host threads, in order, while this thread feeds the device
-    // with the variants that are ready: the preparation (~10 ms per variant) hides behind the grids.
-    std::mutex mu;
-    std::condition_variable cv;
-    std::vector<char> ready((size_t)n_orient, 0);
-    std::atomic<int> next{0};
-    std::atomic<bool> cancel{false};
-    auto producer = [&]() {
-        for (;;) {
-            const int k = next.fetch_add(1);
-            if (k >= n_orient || cancel.load()) return;
-            prepare((size_t)k, 0);
-            {
-                std::lock_guard<std::mutex> lk(mu);
-                ready[(size_t)k] = 1;
-            }
-            cv.notify_all();
-        }
-    };
-    const unsigned hw = host_cores();
-    const int n_threads = std::max(1, std::min<int>(n_orient, std::min<int>(hw > 2 ? (int)hw - 1 : 1, 8)));
-    std::vector<std::thread> producers;
-    for (int t = 0; t < n_threads; ++t) producers.emplace_back(producer);
-    struct Joiner {
-        std::vector<std::thread>& th;
-        std::atomic<bool>& cancel;
-        ~Joiner() {
-            cancel.store(true);
-            for (auto& t : th) t.join();
-        }
-    } joiner{producers, cancel};
-    const uint64_t saved_call_no = p->call_no;
-    for (int k = 0; k < n_orient; ++k) {
-        {
-            std::unique_lock<std::mutex> lk(mu);
-            cv.wait(lk, [&] { return ready[(size_t)k] != 0; });
-        }
-        Prep& pr = prep[(size_t)k];
-        if (pr.rc) { p->err = pr.err; return pr.rc; }
-        if (pr.nq > (size_t)INT32_MAX) { p->err = "set-gyro-quaternions: too many samples"; return RSSYNC_E_INVALID; }
-        join_gyro(p);
-        cudaSetDevice(p->device);
-        CUDA_TRY(p, cudaStreamSynchronize(p->stream));  // records / staging block in use
-        if (p->gyro_stream) CUDA_TRY(p, cudaStreamSynchronize(p->gyro_stream));
-        CUDA_TRY(p, p->h_gyro.reserve(pr.sys.size()));
-        CUDA_TRY(p, p->d_gyro.reserve(pr.sys.size()));
-        CUDA_TRY(p, p->d_rec.reserve(pr.nq * 16));
-        std::memcpy(p->h_gyro.ptr, pr.sys.data(), pr.sys.size() * sizeof(double));
-        p->version++;
-        p->sr = pr.sr;
-        p->q0 = pr.q0;
-        p->nq = pr.nq;
-        p->gyro_dirty = false;  // queued right here, on the problem's stream
-        if (int rc = h2d(p, p->d_gyro.ptr, p->h_gyro.ptr, pr.sys.size() * sizeof(double))) return rc;
-        rs::launch_spline_finish(p->d_gyro.ptr, p->d_gyro.ptr + 4 * pr.nq, p->d_gyro.ptr + 8 * pr.nq, (int)pr.nq,
-                                 p->d_rec.ptr, p->stream);
-        CUDA_TRY(p, cudaGetLastError());
-        std::vector<double>().swap(pr.sys);
-        if (call_nos) p->call_no = call_nos[k];
-        if (int rc = rssync_presync(p, initial_delay, fb, fe, step, radius, &out_cost[k], &out_delay[k])) return rc;
+    rs::ResamplePlan plan;
+    {
+        const rs::IngestStatus st = rs::plan_variable_rate(ts_us.data(), count, plan, p->err);
+        if (st != rs::IngestStatus::Ok)
+            return st == rs::IngestStatus::NonFinite ? RSSYNC_E_NONFINITE
+                   : st == rs::IngestStatus::OutOfOrder ? RSSYNC_E_ORDER : RSSYNC_E_INVALID;
     }
-    if (call_nos) p->call_no = saved_call_no;  // explicit numbers do not advance the counter
+    const int D = rssync_presync_delays(initial_delay, step, radius, nullptr, 0);
+    if (D <= 0 || D > (1 << 28)) { p->err = "pre-sync: empty or oversized delay grid"; return RSSYNC_E_INVALID; }
+    std::vector<double> delays((size_t)D);
+    rssync_presync_delays(initial_delay, step, radius, delays.data(), D);
+    std::vector<FrameDesc> sel;
+    int max_n = 0;
+    if (int rc = select_frames(p, fb, fe, sel, max_n, "pre-sync")) return rc;
+    const int F = (int)sel.size();
+    join_gyro(p);
+    if (int rc = flush(p)) return rc;  // the tracks, and whatever gyro was pending
+    cudaSetDevice(p->device);
+    cudaStream_t st = p->stream;
+    const size_t nq = plan.n_out, n = count;
+    // variants per pass: bounded by ~2 GB of intermediates
+    const size_t per_var = (n * 4 + nq * (4 + 4 + 16)) * sizeof(double);
+    const int G = (int)std::max<size_t>(1, std::min<size_t>((size_t)n_orient, (size_t(2) << 30) / std::max<size_t>(per_var, 1)));
+    CUDA_TRY(p, p->d_var_ts.reserve(n));
+    CUDA_TRY(p, p->d_var_in.reserve(n * 4));  // timestamps (n) and raw gyro (3 n), seconds / rad/s
+    CUDA_TRY(p, p->d_var_q.reserve((size_t)G * n * 4));
+    CUDA_TRY(p, p->d_var_y.reserve((size_t)G * nq * 4));
+    CUDA_TRY(p, p->d_var_rhs.reserve((size_t)G * nq * 4));
+    CUDA_TRY(p, p->d_var_rec.reserve((size_t)G * nq * 16));
+    CUDA_TRY(p, p->d_var_prefix.reserve(rs::gyro_prefix_doubles((int)n, G)));
+    CUDA_TRY(p, p->d_var_orients.reserve(rs::gyro_orient_bytes(G)));
+    CUDA_TRY(p, p->d_var_flags.reserve((size_t)n_orient * 3));  // per variant: resampling flag, 2 grid words
+    CUDA_TRY(p, p->d_os_costs.reserve((size_t)n_orient * D));
+    CUDA_TRY(p, p->d_frames.reserve(std::max(F, 1)));
+    CUDA_TRY(p, p->d_delays.reserve(D));
+    CUDA_TRY(p, p->d_framecost.reserve((size_t)std::max(F, 1) * D));
+    CUDA_TRY(p, cudaMemcpyAsync(p->d_var_ts.ptr, ts_us.data(), n * sizeof(int64_t), cudaMemcpyHostToDevice, st));
+    CUDA_TRY(p, cudaMemcpyAsync(p->d_var_in.ptr, timestamps_s, n * sizeof(double), cudaMemcpyHostToDevice, st));
+    CUDA_TRY(p, cudaMemcpyAsync(p->d_var_in.ptr + n, gyro_xyz, 3 * n * sizeof(double), cudaMemcpyHostToDevice, st));
+    CUDA_TRY(p, cudaMemsetAsync(p->d_var_flags.ptr, 0, (size_t)n_orient * 3 * sizeof(unsigned), st));
+    p->h2d += n * (sizeof(int64_t) + 4 * sizeof(double));
+    if (F > 0) {
+        if (int rc = h2d(p, p->d_frames.ptr, sel.data(), sizeof(FrameDesc) * F)) return rc;
+        if (int rc = h2d(p, p->d_delays.ptr, delays.data(), sizeof(double) * D)) return rc;
+    }
+    if (int rc = upload_elimination(p, nq, st)) return rc;
+    double span = 0.0;
+    for (const FrameDesc& fd : sel) span = std::max(span, fd.ts_hi - fd.ts_lo);
+    const int max_chunk = rs::presync_max_chunk(delays.data(), D, span, plan.sample_rate, max_n);
+    rs::DeviceData dd = p->device_data();
+    dd.nq = (int)nq;
+    dd.q0 = plan.first_timestamp;
+    dd.sr = plan.sample_rate;
+    for (int k0 = 0; k0 < n_orient; k0 += G) {
+        const int g = std::min(G, n_orient - k0);
+        rs::launch_gyro_integrate(p->d_var_in.ptr, p->d_var_in.ptr + n, (int)n, &src[(size_t)k0 * 3], &sgn[(size_t)k0 * 3], g,
+                                  p->d_var_orients.ptr, p->d_var_q.ptr, p->d_var_prefix.ptr, st);
+        rs::launch_gyro_resample(p->d_var_ts.ptr, (int)n, p->d_var_q.ptr, g, plan.tick0, plan.rate_hz, (int)nq,
+                                 p->d_var_y.ptr, p->d_var_flags.ptr + k0, st);
+        rs::launch_spline_chains(p->d_var_y.ptr, p->d_elim.ptr, p->d_elim.ptr + nq, (int)nq, g, p->d_var_rhs.ptr, st);
+        for (int v = 0; v < g; ++v) {
+            double* rec = p->d_var_rec.ptr + (size_t)v * nq * 16;
+            rs::launch_spline_finish(p->d_var_y.ptr + (size_t)v * nq * 4, p->d_var_rhs.ptr + (size_t)v * nq * 4,
+                                     p->d_elim.ptr + 2 * nq, (int)nq, rec, st);
+            if (F > 0) {
+                dd.rec = rec;
+                const uint64_t call = call_nos ? call_nos[k0 + v] : p->call_no + (uint64_t)(k0 + v);
+                rs::launch_presync_grid(dd, p->d_frames.ptr, F, max_n, p->d_delays.ptr, D, p->seed, rs::kStreamPreSync, call,
+                                        0, p->d_framecost.ptr, p->d_os_costs.ptr + (size_t)(k0 + v) * D,
+                                        p->d_var_flags.ptr + n_orient + 2 * (size_t)(k0 + v), st, nullptr, nullptr, nullptr,
+                                        nullptr, 0, max_chunk, p->simplified);
+            }
+        }
+        CUDA_TRY(p, cudaGetLastError());
+        if (k0 + g >= n_orient) {  // the problem is left holding the last variant's gyro
+            CUDA_TRY(p, p->d_rec.reserve(nq * 16));
+            CUDA_TRY(p, cudaMemcpyAsync(p->d_rec.ptr, p->d_var_rec.ptr + (size_t)(g - 1) * nq * 16, nq * 16 * sizeof(double),
+                                        cudaMemcpyDeviceToDevice, st));
+        }
+    }
+    std::vector<double> costs((size_t)n_orient * D, 0.0);
+    std::vector<unsigned> flags((size_t)n_orient * 3, 0u);
+    if (F > 0)
+        if (int rc = d2h(p, costs.data(), p->d_os_costs.ptr, costs.size() * sizeof(double))) return rc;
+    if (int rc = d2h(p, flags.data(), p->d_var_flags.ptr, flags.size() * sizeof(unsigned))) return rc;
+    CUDA_TRY(p, cudaStreamSynchronize(st));
+    p->version++;
+    p->sr = plan.sample_rate;
+    p->q0 = plan.first_timestamp;
+    p->nq = nq;
+    p->gyro_dirty = false;
+    if (!call_nos) p->call_no += (uint64_t)n_orient;
+    p->grid_tasks = (uint64_t)F * (uint64_t)D;
+    for (int k = 0; k < n_orient; ++k) {
+        if (flags[(size_t)k]) { p->err = "set-gyro-quaternions: non-finite sample after interpolation"; return RSSYNC_E_NONFINITE; }
+        const unsigned fl = flags[(size_t)n_orient + 2 * (size_t)k];
+        if (fl) {  // core_private.cpp:76-83
+            p->err = (fl & rs::kFlagP)   ? "pre-sync: non-finite numbers in P"
+                     : (fl & rs::kFlagM) ? "pre-sync: non-finite numbers in M"
+                     : (fl & rs::kFlagR) ? "pre-sync: non-finite r"
+                                         : "pre-sync: non-finite rho";
+            return RSSYNC_E_NONFINITE;
+        }
+        const double* c = &costs[(size_t)k * D];
+        int best = 0;  // std::min_element over (cost, delay) pairs, :89
+        for (int d = 1; d < D; ++d)
+            if (c[d] < c[best] || (c[d] == c[best] && delays[(size_t)d] < delays[(size_t)best])) best = d;
+        out_cost[k] = c[best];
+        out_delay[k] = delays[(size_t)best];
+    }
     return RSSYNC_OK;
 }
 
@@ -2365,6 +2458,24 @@ int rssync_probe_lbfgs(rssync_problem* p, int64_t frame, double delay, double* m
     if (iters) *iters = st[0];
     if (evals) *evals = st[1];
     return RSSYNC_OK;
+}
+
+int rssync_probe_spec_trig(const double* x, int n, int which, int on_device, double* out) {
+    if (n <= 0) return RSSYNC_OK;
+    if (!x || !out || which < 0 || which > 2) return RSSYNC_E_INVALID;
+    if (!on_device) {
+        for (int i = 0; i < n; ++i) out[i] = which == 0 ? rs::spec_sin(x[i]) : which == 1 ? rs::spec_cos(x[i]) : rs::spec_acos(x[i]);
+        return RSSYNC_OK;
+    }
+    double *dx = nullptr, *dy = nullptr;
+    if (cudaMalloc((void**)&dx, sizeof(double) * n) != cudaSuccess) return RSSYNC_E_CUDA;
+    if (cudaMalloc((void**)&dy, sizeof(double) * n) != cudaSuccess) { cudaFree(dx); return RSSYNC_E_CUDA; }
+    cudaMemcpy(dx, x, sizeof(double) * n, cudaMemcpyHostToDevice);
+    rs::launch_probe_trig(dx, n, which, dy, nullptr);
+    cudaError_t e = cudaMemcpy(out, dy, sizeof(double) * n, cudaMemcpyDeviceToHost);
+    cudaFree(dx);
+    cudaFree(dy);
+    return e == cudaSuccess ? RSSYNC_OK : RSSYNC_E_CUDA;
 }
 
 int rssync_probe_log1p(const double* x, int n, double* out) {

@@ -30,8 +30,10 @@
 #include <mutex>
 #include <tuple>
 #include <utility>
+#include <vector>
 
 #include "device_math.cuh"
+#include "gyro_scan.h"
 
 namespace rs {
 
@@ -1670,6 +1672,127 @@ __global__ void spline_finish_kernel(const double* __restrict__ y, const double*
 }
 
 // ------------------------------------------------------------------------------------------
+// K8: the gyro ingest on the device, for n_var orientation variants at once.
+//
+//  * gyro_local / gyro_prefix / gyro_apply: optdata_fill_gyro (core_testcode.cpp:37-53) as a blocked
+//    scan.  q_i = normalise(d_i (x) q_{i-1}) is not associative once every step normalises, so the
+//    contract fixes the order (gyro_scan.h, shared with the host code and the oracle): the
+//    recurrence inside blocks of kGyroScanBlock samples from the identity (one thread per block
+//    and variant), the blocks' last values chained into prefixes (one thread per variant), then
+//    every sample = normalise(local (x) prefix) in parallel.  sin / cos are the contract's
+//    (spec_trig.h).
+//  * resample: the per-sample half of the variable-rate SetGyroQuaternions (core_private.cpp:166-182):
+//    grid point j = 1e6 (tick0 + j) / rate in integer division, lower_bound over the input
+//    timestamps, quat_slerp (quat.cpp:55-74) with the contract's acos / sin; non-finite results raise
+//    the variant's flag (:180).
+//  * spline_chains: the two elimination sweeps of the spline system (minispline.cpp:22-32).  The
+//    factors depend only on n (host_ingest.cpp); what is left per component is the first-order
+//    recurrence rhs[i] -= rhs[i -+ 1] * f[i], sequential by nature: one thread per (variant,
+//    component) walks it in the reference's order, so the bits are the host sweep's.  48 variants x 4
+//    components run side by side, which is what the orientation search needs; a single long track is
+//    faster on the host (SetGyroQuaternions' fixed-rate form keeps using it).
+struct OrientDev {
+    int src[3];
+    double sgn[3];
+};
+__global__ void gyro_local_kernel(const double* __restrict__ ts, const double* __restrict__ gyro, int n,
+                                  const OrientDev* __restrict__ orients, int n_var, double* __restrict__ local) {
+    const int nb = (n + (int)kGyroScanBlock - 1) / (int)kGyroScanBlock;
+    const int id = blockIdx.x * blockDim.x + threadIdx.x;
+    if (id >= nb * n_var) return;
+    const int v = id / nb, b = id - v * nb;
+    const OrientDev o = orients[v];
+    double prev[4] = {1.0, 0.0, 0.0, 0.0};
+    double* out = local + (size_t)v * n * 4;
+    const int i1 = min(n, (b + 1) * (int)kGyroScanBlock);
+    for (int i = b * (int)kGyroScanBlock; i < i1; ++i) {
+        double d[4], q[4];
+        gyro_increment(ts, gyro, (size_t)i, o.src, o.sgn, d);
+        quat_mul_normalise(d, prev, q);
+        prev[0] = q[0]; prev[1] = q[1]; prev[2] = q[2]; prev[3] = q[3];
+        double2* dst = reinterpret_cast<double2*>(out + (size_t)i * 4);
+        dst[0] = make_double2(q[0], q[1]);
+        dst[1] = make_double2(q[2], q[3]);
+    }
+}
+__global__ void gyro_prefix_kernel(const double* __restrict__ local, int n, int n_var, double* __restrict__ prefix) {
+    const int nb = (n + (int)kGyroScanBlock - 1) / (int)kGyroScanBlock;
+    const int v = blockIdx.x * blockDim.x + threadIdx.x;
+    if (v >= n_var) return;
+    double* pf = prefix + (size_t)v * (nb + 1) * 4;
+    double cur[4] = {1.0, 0.0, 0.0, 0.0};
+    pf[0] = 1.0; pf[1] = 0.0; pf[2] = 0.0; pf[3] = 0.0;
+    for (int b = 0; b < nb; ++b) {
+        const int last = min(n, (b + 1) * (int)kGyroScanBlock) - 1;
+        double nx[4];
+        quat_mul_normalise(local + ((size_t)v * n + last) * 4, cur, nx);
+        for (int c = 0; c < 4; ++c) { cur[c] = nx[c]; pf[(size_t)(b + 1) * 4 + c] = nx[c]; }
+    }
+}
+__global__ void gyro_apply_kernel(const double* __restrict__ prefix, int n, int n_var, double* __restrict__ quats) {
+    const int nb = (n + (int)kGyroScanBlock - 1) / (int)kGyroScanBlock;
+    const long long id = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (id >= (long long)n * n_var) return;
+    const int v = (int)(id / n), i = (int)(id - (long long)v * n);
+    double* q = quats + id * 4;  // in place: the block-local value becomes the sample
+    const double loc[4] = {q[0], q[1], q[2], q[3]};
+    double out[4];
+    quat_mul_normalise(loc, prefix + ((size_t)v * (nb + 1) + i / (int)kGyroScanBlock) * 4, out);
+    q[0] = out[0]; q[1] = out[1]; q[2] = out[2]; q[3] = out[3];
+}
+__global__ void resample_kernel(const int64_t* __restrict__ ts_us, int count, const double* __restrict__ quats,
+                                int n_var, unsigned long long tick0, unsigned rate_hz, int n_out,
+                                double* __restrict__ out, unsigned* __restrict__ nonfinite) {
+    const long long id = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (id >= (long long)n_out * n_var) return;
+    const int v = (int)(id / n_out), j = (int)(id - (long long)v * n_out);
+    const unsigned long long t = 1000000ULL * (tick0 + (unsigned long long)j) / rate_hz;  // core_private.cpp:153-154
+    int lo = 0, hi = count;  // std::lower_bound: first index with ts_us[idx] >= t (as unsigned, :169)
+    while (lo < hi) {
+        const int mid = (lo + hi) >> 1;
+        if ((unsigned long long)ts_us[mid] < t) lo = mid + 1; else hi = mid;
+    }
+    const double* src = quats + (size_t)v * count * 4;
+    double r[4];
+    if (lo > 0) {
+        // lo < count: every grid point is below the last timestamp (plan_variable_rate)
+        const double frac = 1. * (double)(t - (unsigned long long)ts_us[lo - 1]) / (double)(ts_us[lo] - ts_us[lo - 1]);
+        quat_slerp_spec(src + (size_t)(lo - 1) * 4, src + (size_t)lo * 4, frac, r);  // :171-175
+    } else {
+        for (int c = 0; c < 4; ++c) r[c] = src[c];  // :177-178
+    }
+    double* dst = out + id * 4;
+    dst[0] = r[0]; dst[1] = r[1]; dst[2] = r[2]; dst[3] = r[3];
+    if (!(is_finite(r[0]) && is_finite(r[1]) && is_finite(r[2]) && is_finite(r[3]))) atomicOr(nonfinite + v, 1u);  // :180
+}
+__global__ void spline_chains_kernel(const double* __restrict__ y, const double* __restrict__ f_down,
+                                     const double* __restrict__ f_up, int n, int n_var, double* __restrict__ rhs) {
+    const int id = blockIdx.x * blockDim.x + threadIdx.x;
+    if (id >= 4 * n_var) return;
+    const int v = id >> 2, c = id & 3;
+    const double* q = y + (size_t)v * n * 4 + c;
+    double* r = rhs + (size_t)v * n * 4 + c;
+    r[0] = 0.0;
+    r[(size_t)(n - 1) * 4] = 0.0;
+    double prev = 0.0;  // rhs of row i - 1 after the downward sweep
+    for (int i = 1; i + 1 < n; ++i) {  // rhs of row i (:12-19) minus what row i - 1 clears (:25)
+        const double ri = (q[(size_t)(i + 1) * 4] - 2 * q[(size_t)i * 4]) + q[(size_t)(i - 1) * 4];
+        prev = ri - prev * f_down[i - 1];
+        r[(size_t)i * 4] = prev;
+    }
+    double nxt = 0.0;  // rhs of row i after the upward sweep (row n - 1: 0)
+    for (int i = n - 1; i > 1; --i) {  // :31
+        const double cur = r[(size_t)(i - 1) * 4] - nxt * f_up[i];
+        r[(size_t)(i - 1) * 4] = cur;
+        nxt = cur;
+    }
+}
+__global__ void probe_trig_kernel(const double* __restrict__ x, int n, int which, double* __restrict__ out) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = which == 0 ? spec_sin(x[i]) : which == 1 ? spec_cos(x[i]) : spec_acos(x[i]);
+}
+
+// ------------------------------------------------------------------------------------------
 // probes (tests only): one warp
 __global__ void probe_problem_kernel(DeviceData dd, FrameDesc fd, int NP, double delay, double* out) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -2041,6 +2164,46 @@ void launch_spline_finish(const double* d_quats, const double* d_rhs, const doub
     if (n <= 0) return;
     const long long threads = 4LL * n;
     spline_finish_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, st>>>(d_quats, d_rhs, d_diag, n, d_rec);
+    g_launches += 1;
+}
+
+void launch_gyro_integrate(const double* d_ts, const double* d_gyro, int n, const int* h_src, const double* h_sgn,
+                           int n_var, void* d_orients, double* d_quats, double* d_prefix, cudaStream_t st) {
+    if (n <= 0 || n_var <= 0) return;
+    std::vector<OrientDev> o((size_t)n_var);
+    for (int v = 0; v < n_var; ++v)
+        for (int c = 0; c < 3; ++c) { o[(size_t)v].src[c] = h_src[3 * v + c]; o[(size_t)v].sgn[c] = h_sgn[3 * v + c]; }
+    cudaMemcpyAsync(d_orients, o.data(), sizeof(OrientDev) * (size_t)n_var, cudaMemcpyHostToDevice, st);  // pageable: staged before return
+    const int nb = (n + (int)kGyroScanBlock - 1) / (int)kGyroScanBlock;
+    gyro_local_kernel<<<(nb * n_var + 31) / 32, 32, 0, st>>>(d_ts, d_gyro, n, static_cast<const OrientDev*>(d_orients), n_var, d_quats);
+    gyro_prefix_kernel<<<(n_var + 31) / 32, 32, 0, st>>>(d_quats, n, n_var, d_prefix);
+    const long long total = (long long)n * n_var;
+    gyro_apply_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(d_prefix, n, n_var, d_quats);
+    g_launches += 3;
+}
+size_t gyro_orient_bytes(int n_var) { return sizeof(OrientDev) * (size_t)n_var; }
+size_t gyro_prefix_doubles(int n, int n_var) {
+    return (size_t)n_var * ((size_t)(n + (int)kGyroScanBlock - 1) / kGyroScanBlock + 1) * 4;
+}
+
+void launch_gyro_resample(const int64_t* d_ts_us, int count, const double* d_quats, int n_var, uint64_t tick0,
+                          unsigned rate_hz, int n_out, double* d_out, unsigned* d_nonfinite, cudaStream_t st) {
+    if (n_out <= 0 || n_var <= 0) return;
+    const long long total = (long long)n_out * n_var;
+    resample_kernel<<<(unsigned)((total + 127) / 128), 128, 0, st>>>(d_ts_us, count, d_quats, n_var, tick0, rate_hz, n_out,
+                                                                     d_out, d_nonfinite);
+    g_launches += 1;
+}
+
+void launch_spline_chains(const double* d_y, const double* d_f_down, const double* d_f_up, int n, int n_var,
+                          double* d_rhs, cudaStream_t st) {
+    if (n < 2 || n_var <= 0) return;
+    spline_chains_kernel<<<(4 * n_var + 31) / 32, 32, 0, st>>>(d_y, d_f_down, d_f_up, n, n_var, d_rhs);
+    g_launches += 1;
+}
+
+void launch_probe_trig(const double* d_x, int n, int which, double* d_out, cudaStream_t st) {
+    probe_trig_kernel<<<(n + 255) / 256, 256, 0, st>>>(d_x, n, which, d_out);
     g_launches += 1;
 }
 

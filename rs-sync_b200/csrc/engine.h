@@ -111,6 +111,27 @@ void launch_sync_trials(const DeviceData& dd, const SyncBatchDev& b, const doubl
 void launch_spline_finish(const double* d_quats, const double* d_rhs, const double* d_diag, int n,
                           double* d_rec, cudaStream_t st);
 
+// ---- gyro ingest on the device (K8, engine.cu) ---------------------------------------------------
+// optdata_fill_gyro (core_testcode.cpp:37-53) for n_var gyro_orientation variants: d_ts (n doubles,
+// seconds), d_gyro (n x 3), h_src / h_sgn (3 per variant: source axis and sign per output axis) ->
+// d_quats (n_var x n x 4).  d_orients: gyro_orient_bytes(n_var) bytes, d_prefix:
+// gyro_prefix_doubles(n, n_var) doubles of device scratch.
+void launch_gyro_integrate(const double* d_ts, const double* d_gyro, int n, const int* h_src, const double* h_sgn,
+                           int n_var, void* d_orients, double* d_quats, double* d_prefix, cudaStream_t st);
+size_t gyro_orient_bytes(int n_var);
+size_t gyro_prefix_doubles(int n, int n_var);
+// the per-sample half of the variable-rate SetGyroQuaternions (core_private.cpp:166-182): d_quats
+// (n_var x count x 4) at timestamps d_ts_us (count) -> d_out (n_var x n_out x 4) on the grid
+// 1e6 (tick0 + j) / rate_hz; d_nonfinite[v] is set when variant v produced a non-finite sample
+void launch_gyro_resample(const int64_t* d_ts_us, int count, const double* d_quats, int n_var, uint64_t tick0,
+                          unsigned rate_hz, int n_out, double* d_out, unsigned* d_nonfinite, cudaStream_t st);
+// the two elimination sweeps of the spline system (minispline.cpp:22-32) for n_var tracks of n
+// samples: d_y (n_var x n x 4) -> d_rhs (n_var x n x 4); d_f_down / d_f_up: the factors of
+// spline_elimination(n) (host_ingest.h)
+void launch_spline_chains(const double* d_y, const double* d_f_down, const double* d_f_up, int n, int n_var,
+                          double* d_rhs, cudaStream_t st);
+void launch_probe_trig(const double* d_x, int n, int which, double* d_out, cudaStream_t st);
+
 // ---- pixel -> ray front end (track_frames' per-frame tail, core_testcode.cpp:134-161) --------
 struct LensDev {  // Lens, core_testcode.cpp:55-61
     double ro, fx, fy, cx, cy, k1, k2, k3, k4;

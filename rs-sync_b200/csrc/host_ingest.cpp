@@ -6,6 +6,8 @@
 // records travel to the GPU.  Compile with -ffp-contract=off.
 #include "host_ingest.h"
 
+#include "spec_trig.h"
+
 #include <algorithm>
 #include <cmath>
 #include <memory>
@@ -119,81 +121,55 @@ void build_spline_system(const double* quats, size_t n, double* rhs, double* dia
     }
 }
 
-namespace {
-
-// quat_slerp, quat.cpp:55-74
-void slerp4(const double* p, const double* q_in, double t, double* out) {
-    double q[4] = {q_in[0], q_in[1], q_in[2], q_in[3]};
-    double cosang = ((p[0] * q[0] + p[1] * q[1]) + p[2] * q[2]) + p[3] * q[3];
-    if (cosang < 0) {
-        q[0] = -q[0]; q[1] = -q[1]; q[2] = -q[2]; q[3] = -q[3];
-        cosang = ((p[0] * q[0] + p[1] * q[1]) + p[2] * q[2]) + p[3] * q[3];
+bool parse_orientation(const char* orient, int src[3], double sgn[3]) {
+    src[0] = 0; src[1] = 1; src[2] = 2;
+    sgn[0] = sgn[1] = sgn[2] = 1.0;
+    if (!orient) return true;
+    for (int i = 0; i < 3; ++i) {
+        const char ch = orient[i];
+        const char lo = (char)(ch | 0x20);
+        if (lo < 'x' || lo > 'z') return false;
+        src[i] = lo - 'x';
+        sgn[i] = (ch == lo) ? -1.0 : 1.0;
     }
-    const double ang = std::acos(cosang);
-    double wp, wq;
-    if (ang > 1e-9) {
-        const double s = std::sin(ang);
-        wp = std::sin((1 - t) * ang) / s;
-        wq = std::sin(t * ang) / s;
-    } else {
-        wp = 1 - t;
-        wq = t;
-    }
-    for (int c = 0; c < 4; ++c) out[c] = wp * p[c] + wq * q[c];
+    return orient[3] == 0;
 }
-
-}  // namespace
 
 bool integrate_gyro(const double* ts, const double* gyro, size_t count, const char* orient,
                     double* out) {
-    int src[3] = {0, 1, 2};
-    double sgn[3] = {1.0, 1.0, 1.0};
-    if (orient) {
-        for (int i = 0; i < 3; ++i) {
-            const char ch = orient[i];
-            const char lo = (char)(ch | 0x20);
-            if (lo < 'x' || lo > 'z') return false;
-            src[i] = lo - 'x';
-            sgn[i] = (ch == lo) ? -1.0 : 1.0;
-        }
-        if (orient[3] != 0) return false;
-    }
+    int src[3];
+    double sgn[3];
+    if (!parse_orientation(orient, src, sgn)) return false;
     if (count == 0) return true;
-    double q[4] = {1.0, 0.0, 0.0, 0.0};
-    out[0] = 1.0; out[1] = 0.0; out[2] = 0.0; out[3] = 0.0;
-    for (size_t i = 1; i < count; ++i) {
-        const double dt = ts[i] - ts[i - 1];
-        const double a0 = sgn[0] * gyro[3 * i + src[0]] * dt, a1 = sgn[1] * gyro[3 * i + src[1]] * dt,
-                     a2 = sgn[2] * gyro[3 * i + src[2]] * dt;
-        // quat_from_aa, quat.cpp:5-17
-        const double th2 = (a0 * a0 + a1 * a1) + a2 * a2;
-        double d[4];
-        if (th2 > 0.) {
-            const double th = std::sqrt(th2), half = th * 0.5, k = std::sin(half) / th;
-            d[0] = std::cos(half); d[1] = a0 * k; d[2] = a1 * k; d[3] = a2 * k;
-        } else {
-            d[0] = 1.; d[1] = a0 * 0.5; d[2] = a1 * 0.5; d[3] = a2 * 0.5;
-        }
-        // quat_prod(d, q), quat.cpp:33-38, then arma::normalise
-        double r[4];
-        r[0] = ((d[0] * q[0] - d[1] * q[1]) - d[2] * q[2]) - d[3] * q[3];
-        r[1] = ((d[0] * q[1] + d[1] * q[0]) + d[2] * q[3]) - d[3] * q[2];
-        r[2] = ((d[0] * q[2] - d[1] * q[3]) + d[2] * q[0]) + d[3] * q[1];
-        r[3] = ((d[0] * q[3] + d[1] * q[2]) - d[2] * q[1]) + d[3] * q[0];
-        const double nrm = std::sqrt(((r[0] * r[0] + r[1] * r[1]) + r[2] * r[2]) + r[3] * r[3]);
-        for (int c = 0; c < 4; ++c) {
-            q[c] = r[c] / nrm;
-            out[4 * i + c] = q[c];
+    // The contract's order of operations (the device kernels of engine.cu follow the same one, see
+    // gyro_local_kernel): the recurrence runs inside blocks of kGyroScanBlock samples, each from the
+    // identity; the blocks' last values are chained into per-block prefixes; every sample is its
+    // block-local value times its block's prefix, normalised.
+    const size_t B = kGyroScanBlock;
+    const size_t nb = (count + B - 1) / B;
+    std::vector<double> local(4 * count), prefix(4 * (nb + 1));
+    const double ident[4] = {1.0, 0.0, 0.0, 0.0};
+    for (size_t b = 0; b < nb; ++b) {
+        const double* prev = ident;
+        for (size_t i = b * B; i < std::min(count, (b + 1) * B); ++i) {
+            double d[4];
+            gyro_increment(ts, gyro, i, src, sgn, d);
+            quat_mul_normalise(d, prev, &local[4 * i]);
+            prev = &local[4 * i];
         }
     }
+    for (int c = 0; c < 4; ++c) prefix[c] = ident[c];
+    for (size_t b = 0; b < nb; ++b)
+        quat_mul_normalise(&local[4 * (std::min(count, (b + 1) * B) - 1)], &prefix[4 * b], &prefix[4 * (b + 1)]);
+    for (size_t i = 0; i < count; ++i) quat_mul_normalise(&local[4 * i], &prefix[4 * (i / B)], out + 4 * i);
     return true;
 }
 
 // SyncProblemPrivate::SetGyroQuaternions(const int64_t*, const double*, size_t),
-// core_private.cpp:142-190, integer quirks included.
-IngestStatus resample_variable_rate(const int64_t* ts_us, const double* quats, size_t count,
-                                    std::vector<double>& out_quats, double& sample_rate,
-                                    double& first_timestamp, std::string& err) {
+// core_private.cpp:142-190, integer quirks included: everything of it that
+// does not touch the samples -- the rate, the uniform integer-microsecond grid, the order check.  The
+// per-sample half (lower_bound + slerp, :166-182) runs on the device (resample_kernel, engine.cu).
+IngestStatus plan_variable_rate(const int64_t* ts_us, size_t count, ResamplePlan& plan, std::string& err) {
     constexpr uint64_t kMicro = 1000000ULL;
     if (count < 2) { err = "set-gyro-quaternions: need at least 2 samples"; return IngestStatus::Invalid; }
     const uint64_t span = (uint64_t)(ts_us[count - 1] - ts_us[0]);
@@ -202,11 +178,14 @@ IngestStatus resample_variable_rate(const int64_t* ts_us, const double* quats, s
     const int rate_hz = int(std::round((double)rate_uhz / 50. / (double)kMicro) * 50);   // :148-149
     if (rate_hz <= 0) { err = "set-gyro-quaternions: sample rate rounds to zero"; return IngestStatus::Invalid; }
     const uint64_t t_last = (uint64_t)ts_us[count - 1];
-    std::vector<uint64_t> grid;
-    int tick = (int)std::ceil((double)((uint64_t)(ts_us[0] * (int64_t)rate_hz) / kMicro));  // :152
-    while (kMicro * (uint64_t)tick / (uint64_t)rate_hz < t_last) {                           // :153
-        grid.push_back(kMicro * (uint64_t)tick / (uint64_t)rate_hz);
-        ++tick;
+    const int tick0 = (int)std::ceil((double)((uint64_t)(ts_us[0] * (int64_t)rate_hz) / kMicro));  // :152
+    // grid point j is kMicro (tick0 + j) / rate_hz (integer division), for as long as it is < t_last (:153):
+    // the count follows from the monotonicity of the quotient
+    uint64_t n_out = 0;
+    if (kMicro * (uint64_t)tick0 / (uint64_t)rate_hz < t_last) {
+        // largest tick with kMicro tick / rate < t_last  <=>  kMicro tick < t_last rate  <=>  tick <= (t_last rate - 1) / kMicro
+        const uint64_t last_tick = (t_last * (uint64_t)rate_hz - 1) / kMicro;
+        n_out = last_tick - (uint64_t)tick0 + 1;
     }
     for (size_t i = 1; i < count; ++i) {  // :157-164
         if (ts_us[i - 1] > ts_us[i]) {
@@ -215,31 +194,31 @@ IngestStatus resample_variable_rate(const int64_t* ts_us, const double* quats, s
             return IngestStatus::OutOfOrder;
         }
     }
-    if (grid.size() < 2) { err = "set-gyro-quaternions: fewer than 2 resampled samples"; return IngestStatus::Invalid; }
-    out_quats.resize(grid.size() * 4);
-    for (size_t j = 0; j < grid.size(); ++j) {  // :166-182
-        const uint64_t t = grid[j];
-        const int64_t* it = std::lower_bound(ts_us, ts_us + count, t,
-                                             [](int64_t a, uint64_t b) { return (uint64_t)a < b; });
-        const size_t hi = (size_t)(it - ts_us);
-        double* dst = &out_quats[4 * j];
-        if (hi > 0) {
-            const double frac =
-                1. * (double)(t - (uint64_t)ts_us[hi - 1]) / (double)(ts_us[hi] - ts_us[hi - 1]);
-            slerp4(quats + 4 * (hi - 1), quats + 4 * hi, frac, dst);
-        } else {
-            for (int c = 0; c < 4; ++c) dst[c] = quats[4 * hi + c];
-        }
-        if (!(std::isfinite(dst[0]) && std::isfinite(dst[1]) && std::isfinite(dst[2]) && std::isfinite(dst[3]))) {
-            err = "set-gyro-quaternions: non-finite sample after interpolation";  // :180-181
-            return IngestStatus::NonFinite;
-        }
-    }
-    sample_rate = 1. * rate_hz;                              // :183
-    first_timestamp = 1. * (double)grid[0] / (double)kMicro;  // :184
-    if (!std::isfinite(sample_rate)) { err = "set-gyro-quaternions: non-finite sample rate. wtf?"; return IngestStatus::NonFinite; }
-    if (!std::isfinite(first_timestamp)) { err = "set-gyro-quaternions: non-finite first timestamp. wtf?"; return IngestStatus::NonFinite; }
+    if (n_out < 2) { err = "set-gyro-quaternions: fewer than 2 resampled samples"; return IngestStatus::Invalid; }
+    if (n_out > (uint64_t)INT32_MAX) { err = "set-gyro-quaternions: too many samples"; return IngestStatus::Invalid; }
+    plan.rate_hz = (unsigned)rate_hz;
+    plan.tick0 = (uint64_t)tick0;
+    plan.n_out = (size_t)n_out;
+    plan.sample_rate = 1. * rate_hz;                                                              // :183
+    plan.first_timestamp = 1. * (double)(kMicro * (uint64_t)tick0 / (uint64_t)rate_hz) / (double)kMicro;  // :184
+    if (!std::isfinite(plan.sample_rate)) { err = "set-gyro-quaternions: non-finite sample rate. wtf?"; return IngestStatus::NonFinite; }
+    if (!std::isfinite(plan.first_timestamp)) { err = "set-gyro-quaternions: non-finite first timestamp. wtf?"; return IngestStatus::NonFinite; }
     return IngestStatus::Ok;
+}
+
+std::shared_ptr<const SplineElimination> spline_elimination(size_t n) {
+    static std::mutex mu;
+    static std::shared_ptr<const SplineElimination> cached;
+    std::lock_guard<std::mutex> lk(mu);
+    if (!cached || cached->f_down.size() != n) {
+        Elimination e = eliminate(n);
+        auto se = std::make_shared<SplineElimination>();
+        se->f_down = std::move(e.f_down);
+        se->f_up = std::move(e.f_up);
+        se->diag = std::move(e.diag);
+        cached = se;
+    }
+    return cached;
 }
 
 }  // namespace rs

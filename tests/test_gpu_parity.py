@@ -645,3 +645,75 @@ def test_simplified_loss_mode_matches_oracle(rsb, oracle_loader, w_small):
     assert rel_err(db, dbo) <= TOL and rel_err(cb, cbo) <= TOL
     g.set_loss_mode(False)
     assert np.array_equal(g.DebugPreSync(0.0, fb, fe, 0.1, 41)[1] != cg, np.ones(41, dtype=bool))
+
+
+def test_device_gyro_ingest_matches_host_and_oracle(rsb, oracle_loader, synth_mod):
+    """the gyro ingest on the device (engine.cu K8): the contract's trig functions, the blocked
+    integration scan, the variable-rate resampling and the spline elimination sweeps give the bits of
+    the engine's host code and of the oracle"""
+    rng = np.random.default_rng(4)
+    xs = np.concatenate([rng.uniform(-3.3, 3.3, 50000), rng.uniform(0, 0.2, 20000), rng.uniform(-50, 50, 20000)])
+    for which in ("sin", "cos"):
+        assert np.array_equal(rsb.probe_spec_trig(xs, which, on_device=True), rsb.probe_spec_trig(xs, which))
+    ys = np.concatenate([rng.uniform(-1, 1, 50000), 1 - rng.uniform(0, 1e-6, 20000) ** 2, [1.0, -1.0, 0.5, 1.0000000000000002]])
+    assert np.array_equal(rsb.probe_spec_trig(ys, "acos", on_device=True), rsb.probe_spec_trig(ys, "acos"), equal_nan=True)
+    # variable-rate SetGyroQuaternions: a 450 Hz track with jitter, an unaligned first timestamp, 3 blocks of
+    # resampled samples; records == oracle's (resampled samples included)
+    n = 1700
+    ts = (7_000_123 + np.cumsum(rng.integers(2100, 2350, n))).astype(np.int64)
+    q = rng.normal(size=(n, 4)) * 0.05 + np.array([1.0, 0, 0, 0])
+    q /= np.linalg.norm(q, axis=1, keepdims=True)
+    q[::7] *= -1  # sign flips: slerp takes the short way (quat.cpp:58-60)
+    g = rsb.SyncProblem()
+    o = oracle_loader.OracleProblem()
+    g.SetGyroQuaternions(ts, q, n)
+    o.SetGyroQuaternions(ts, q, n)
+    sr, q0, rec = g.probe_gyro()
+    qo, sro, q0o = o.resampled()
+    assert sr == sro == 450.0 and q0 == q0o
+    assert np.array_equal(rec[:, 0:4], qo)
+    assert np.array_equal(rec, o.spline())
+    # a non-finite sample after interpolation is the reference's panic (core_private.cpp:180-181)
+    # (a dot product above 1 is NOT one: acos gives NaN, `theta > 1e-9` is false and quat_slerp falls
+    # back to the linear weights, quat.cpp:61-70 -- same here)
+    odd = q.copy()
+    odd[900] = [2.0, 0, 0, 0]
+    g.SetGyroQuaternions(ts, odd, n)
+    o.SetGyroQuaternions(ts, odd, n)
+    assert np.array_equal(g.probe_gyro()[2], o.spline())
+    g.SetGyroQuaternions(ts, q, n)
+    bad = q.copy()
+    bad[900, 2] = np.inf
+    with pytest.raises(rsb.RsSyncError) as e:
+        g.SetGyroQuaternions(ts, bad, n)
+    assert e.value.code == rsb.E_NONFINITE and "non-finite sample after interpolation" in e.value.message
+    with pytest.raises(oracle_loader.OracleError):
+        o.SetGyroQuaternions(ts, bad, n)
+    # the problem still holds the good track
+    assert np.array_equal(g.probe_gyro()[2], rec)
+
+
+def test_orientation_search_long_track_all_variants(rsb, oracle_loader, synth_mod):
+    """all 48 variants on a track of several scan blocks, through the device pipeline (integration,
+    resampling, elimination, records, grids queued back to back), against the oracle's loop of host
+    calls; the search leaves the problem holding the last variant's gyro"""
+    w = workload("small")
+    ts = w.gyro_t0 + np.arange(w.quats.shape[0]) / w.gyro_rate
+    assert w.quats.shape[0] > 3 * 512
+    orients = synth_mod.ORIENTATIONS
+    g = rsb.SyncProblem(seed=100).load(w, bulk=True)
+    o = oracle_loader.OracleProblem(threads=8, seed=100).load(w)
+    fb, fe = int(w.frame_ids[0]), int(w.frame_ids[0]) + 24
+    g.set_rng(100, 5)
+    o.set_rng(100, 5)
+    cg, dg = g.orientation_search(ts, w.omega, orients, 0.0, fb, fe, 0.004, 0.06)
+    co, do = oracle_loader.orientation_search(o, ts, w.omega, orients, 0.0, fb, fe, 0.004, 0.06)
+    assert np.array_equal(dg, do) and rel_err(cg, co) <= TOL
+    assert orients[int(np.argmin(cg))] == "XYZ"
+    assert g.call_counter() == o.call_counter() == 5 + 48
+    assert np.array_equal(g.probe_gyro()[2], o.spline())
+    # the integration on the device equals the host function of the C ABI
+    qh = rsb.integrate_gyro(ts, w.omega, orients[-1])
+    g2 = rsb.SyncProblem()
+    g2.SetGyroQuaternions((ts * 1000000).astype(np.int64), qh, len(ts))
+    assert np.array_equal(g2.probe_gyro()[2], g.probe_gyro()[2])

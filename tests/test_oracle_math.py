@@ -246,3 +246,31 @@ def test_simplified_loss_mode_recovers_the_delay(oracle_loader):
     assert abs(delay - w.true_delay[0]) < 3e-3 and cost > 0
     o.set_loss_mode(False)
     assert not np.allclose(o.DebugPreSync(0.0, fb, fe, 0.1, 41)[1], c)
+
+
+def _ulps(a, b):
+    a, b = np.asarray(a), np.asarray(b)
+    spacing = np.spacing(np.abs(b))
+    return np.max(np.abs(a - b) / spacing)
+
+
+def test_spec_trig_is_pinned_and_accurate(rsb, oracle_loader):
+    """sin / cos / acos of the arithmetic contract (the gyro ingest's only transcendental functions):
+    the engine's host code and the oracle's restatement give the same bits, within 1 ulp of libm on
+    the ranges the path uses, and the special cases are the reference's (acos of a dot product an ulp
+    above 1 is NaN, quat.cpp:61 / core_private.cpp:180)"""
+    rng = np.random.default_rng(11)
+    xs = np.concatenate([rng.uniform(-3.3, 3.3, 200000), rng.uniform(0, 0.2, 50000), rng.uniform(-1e4, 1e4, 50000),
+                         np.array([0.0, -0.0, np.pi / 4, np.pi / 2, np.pi, 1e-300, 5e-324])])
+    for which, ref in (("sin", np.sin), ("cos", np.cos)):
+        a, b = rsb.probe_spec_trig(xs, which), oracle_loader.spec_trig(xs, which)
+        assert np.array_equal(a, b)
+        ok = np.abs(ref(xs)) > 1e-3  # (ulps of a result near a zero of the function measure the reduction)
+        assert _ulps(a[ok], ref(xs)[ok]) <= 1.0
+    ys = np.concatenate([rng.uniform(-1, 1, 200000), 1 - rng.uniform(0, 1e-6, 50000) ** 2, np.array([0.0, 0.5, -0.5, 1.0, -1.0])])
+    a, b = rsb.probe_spec_trig(ys, "acos"), oracle_loader.spec_trig(ys, "acos")
+    assert np.array_equal(a, b)
+    assert _ulps(a, np.arccos(ys)) <= 1.0
+    bad = rsb.probe_spec_trig(np.array([1.0000000000000002, -1.5, np.nan, np.inf]), "acos")
+    assert np.all(np.isnan(bad))
+    assert np.all(np.isnan(rsb.probe_spec_trig(np.array([np.inf, -np.inf, np.nan, 1e300]), "sin")))
