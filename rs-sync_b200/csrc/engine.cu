@@ -1774,14 +1774,45 @@ __global__ void spline_chains_kernel(const double* __restrict__ y, const double*
     double* r = rhs + (size_t)v * n * 4 + c;
     r[0] = 0.0;
     r[(size_t)(n - 1) * 4] = 0.0;
+    // The chains are dependent (one multiply and one subtraction per row); their operands are not:
+    // U rows' worth of loads are issued before the U dependent steps that consume them, so the
+    // memory latency is paid once per U rows instead of once per row.
+    constexpr int U = 32;
     double prev = 0.0;  // rhs of row i - 1 after the downward sweep
-    for (int i = 1; i + 1 < n; ++i) {  // rhs of row i (:12-19) minus what row i - 1 clears (:25)
+    int i = 1;
+    for (; i + U < n; i += U) {  // rows i .. i + U - 1, all interior (i + U - 1 + 1 < n)
+        double qv[U + 2], fv[U];
+#pragma unroll
+        for (int k = 0; k < U + 2; ++k) qv[k] = q[(size_t)(i - 1 + k) * 4];
+#pragma unroll
+        for (int k = 0; k < U; ++k) fv[k] = f_down[i - 1 + k];
+#pragma unroll
+        for (int k = 0; k < U; ++k) {  // rhs of the row (:12-19) minus what the row above clears (:25)
+            const double ri = (qv[k + 2] - 2 * qv[k + 1]) + qv[k];
+            prev = ri - prev * fv[k];
+            r[(size_t)(i + k) * 4] = prev;
+        }
+    }
+    for (; i + 1 < n; ++i) {
         const double ri = (q[(size_t)(i + 1) * 4] - 2 * q[(size_t)i * 4]) + q[(size_t)(i - 1) * 4];
         prev = ri - prev * f_down[i - 1];
         r[(size_t)i * 4] = prev;
     }
     double nxt = 0.0;  // rhs of row i after the upward sweep (row n - 1: 0)
-    for (int i = n - 1; i > 1; --i) {  // :31
+    i = n - 1;
+    for (; i - U > 1; i -= U) {  // steps i, i - 1, ..., i - U + 1 write rows i - 1 ... i - U
+        double rv[U], fv[U];
+#pragma unroll
+        for (int k = 0; k < U; ++k) rv[k] = r[(size_t)(i - 1 - k) * 4];
+#pragma unroll
+        for (int k = 0; k < U; ++k) fv[k] = f_up[i - k];
+#pragma unroll
+        for (int k = 0; k < U; ++k) {  // :31
+            nxt = rv[k] - nxt * fv[k];
+            r[(size_t)(i - 1 - k) * 4] = nxt;
+        }
+    }
+    for (; i > 1; --i) {
         const double cur = r[(size_t)(i - 1) * 4] - nxt * f_up[i];
         r[(size_t)(i - 1) * 4] = cur;
         nxt = cur;
