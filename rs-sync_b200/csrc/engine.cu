@@ -580,7 +580,9 @@ __device__ __forceinline__ bool load_normalised_rows32(const double* __restrict_
 
 // Result of the fast path: the winner is certified / it is not (run the exact estimator) / the rows
 // themselves are not finite (exact estimator, and pre_sync's "non-finite numbers in P" condition).
-enum FastStatus { kFastOk = 0, kFastUndecided = 1, kFastRowsNotFinite = 2 };
+// kFastRetry: the run started from a prior threshold that turned out too tight (see `prior`): run again
+// without one.
+enum FastStatus { kFastOk = 0, kFastUndecided = 1, kFastRowsNotFinite = 2, kFastRetry = 3 };
 
 // The tournament proper.  Hypotheses are taken two at a time: the packed fp32x2 instructions carry
 // hypotheses t and t + 1 in their two halves against ONE ray (scalar operand), so a pass over the
@@ -600,10 +602,23 @@ enum FastStatus { kFastOk = 0, kFastUndecided = 1, kFastRowsNotFinite = 2 };
 // squares (the select works on their bit patterns); its count is retaken on those -- it can differ
 // where rho^2 rounds up to thr1, and is then just as rigorous a rejection.
 // `hyp`: 3 x 32 floats of the warp's shared memory (the batch's hypotheses in fp32, by component).
+//
+// `prior` (0: none): a threshold to START from instead of the first hypothesis' quartile -- the grid
+// kernel passes twice the winning quartile of the neighbouring delay of the same frame.  It acts as a
+// best hypothesis that nobody holds: everything whose count below it does not exceed kk is rejected
+// at once, exactly as against a real best (its exact rho^2 quartile is >= prior), and the first
+// hypothesis that passes becomes the real best if its quartile is rigorously below the prior
+// (up(q) < prior) -- then every earlier rejection also holds against it, because thr1 only went down.
+// The sequential tournament raises its threshold-to-beat from nothing, so early hypotheses of median
+// quality all pay for a select (3.6 selects per task on C2); from a good prior only hypotheses near
+// the best do (2.3).  If nothing passes, or the first one that does is too close to the prior to
+// call, the prior was too tight: kFastRetry, and the caller runs the plain tournament.  *tau_out:
+// the winner's fp32 quartile (the next task's prior).
 template <int SLOTS>
 __device__ __forceinline__ FastStatus warp_ransac_fast(const DeviceData& dd, const FrameDesc& fd,
                                                        const WarpSmem& w, int iters, uint64_t key,
-                                                       int lane, double M[3], int* settled) {
+                                                       int lane, double M[3], int* settled,
+                                                       unsigned prior, unsigned* tau_out) {
     constexpr int NP = SLOTS * 32;
     float nx[SLOTS], ny[SLOTS], nz[SLOTS];
     if (!load_normalised_rows32<SLOTS>(w.P, fd.n, lane, nx, ny, nz)) return kFastRowsNotFinite;
@@ -613,6 +628,12 @@ __device__ __forceinline__ FastStatus warp_ransac_fast(const DeviceData& dd, con
     unsigned tau = 0x7f800000u;   // fp32 quartile of the best hypothesis so far (+inf: none yet)
     float nthr = 0.f;             // -thr1
     unsigned thr1 = 0u;           // nextafter(up(tau)): s <= up(tau)  <=>  s < thr1
+    bool has_real = true;         // false while `tau` is the prior and no hypothesis holds it
+    if (prior) {
+        tau = thr1 = prior;
+        nthr = -__uint_as_float(prior);
+        has_real = false;
+    }
     M[0] = M[1] = M[2] = 0.0;
     float* hyp = w.hyp;
     for (int j0 = 0; j0 < iters; j0 += 32) {
@@ -692,11 +713,13 @@ __device__ __forceinline__ FastStatus warp_ransac_fast(const DeviceData& dd, con
                 tau = q;
                 thr1 = uq + 1u;
                 nthr = -__uint_as_float(thr1);
+                has_real = true;
                 M[0] = __shfl_sync(FULL, v[0], tc);
                 M[1] = __shfl_sync(FULL, v[1], tc);
                 M[2] = __shfl_sync(FULL, v[2], tc);
                 continue;
             }
+            if (!has_real) return kFastRetry;  // too close to a prior nobody holds: nothing to settle against
             // too close to the best so far to call in fp32 (cold): settle this one comparison with
             // the exact binary64 quartiles of the two hypotheses (a tie keeps the earlier one,
             // core_private.cpp:53), then resume
@@ -714,16 +737,26 @@ __device__ __forceinline__ FastStatus warp_ransac_fast(const DeviceData& dd, con
             }
         }
     }
+    if (!has_real) return kFastRetry;  // nothing passed the prior
+    if (tau_out) *tau_out = tau;
     return kFastOk;
 }
 
-// Phases B + C of an estimator task.  Returns kFlagP when the rows are not all finite.
+// Phases B + C of an estimator task.  Returns kFlagP when the rows are not all finite.  prior / tau_out:
+// see warp_ransac_fast (*tau_out = 0 when the winner did not come out of the fast path).
 template <int SLOTS>
 __device__ __forceinline__ unsigned warp_ransac(const DeviceData& dd, const FrameDesc& fd,
                                                 const WarpSmem& w, int iters, uint64_t key, int lane,
-                                                double M[3], unsigned* n_exact) {
+                                                double M[3], unsigned* n_exact, unsigned prior = 0u,
+                                                unsigned* tau_out = nullptr) {
     int settled = 0;
-    const FastStatus st = warp_ransac_fast<SLOTS>(dd, fd, w, iters, key, lane, M, &settled);
+    FastStatus st = kFastRetry;
+    unsigned tau = 0u;
+    for (int attempt = 0; attempt < 2 && st == kFastRetry; ++attempt) {  // (one inlined copy of the tournament)
+        st = warp_ransac_fast<SLOTS>(dd, fd, w, iters, key, lane, M, &settled, attempt == 0 ? prior : 0u, &tau);
+        if (!prior) break;
+    }
+    if (tau_out) *tau_out = (st == kFastOk) ? tau : 0u;
     if (n_exact && settled && lane == 0) atomicAdd(n_exact, 1u);  // tasks that needed binary64
     if (st == kFastOk) return 0u;
     if (n_exact && !settled && lane == 0) atomicAdd(n_exact, 1u);
@@ -1076,6 +1109,12 @@ __device__ __noinline__ unsigned presync_diagnose(const double* pm, int nslots, 
 #ifndef RS_LOSS_UNROLL
 #define RS_LOSS_UNROLL 4  // slots per iteration of the loss phase
 #endif
+#ifndef RS_GRID_GRAB
+#define RS_GRID_GRAB 4    // consecutive tasks a warp takes from the block's counter at a time
+#endif
+#ifndef RS_GRID_PRIOR
+#define RS_GRID_PRIOR 1   // start each tournament from the neighbouring delay's winning quartile
+#endif
 template <int SLOTS>
 struct GridCfg {
     static constexpr int kWarps = RS_GRID_WARPS;
@@ -1187,11 +1226,18 @@ presync_kernel(DeviceData dd, const FrameDesc* __restrict__ frames, int F,
     const int n_tasks = n_units * chunk;  // the host keeps a grid below 2^34 tasks
     int cur_u = -1, rec_first = 0, rec_cnt = 0, fi = 0, d0 = 0;
     FrameDesc fd{};
-    for (;;) {
-        int k = 0;
-        if (lane == 0) k = atomicAdd(&ctl->next_task, 1);
-        k = __shfl_sync(FULL, k, 0);
-        if (k >= n_tasks) break;
+    // A warp takes kGrab consecutive tasks at a time: consecutive delays of one frame, so that the
+    // estimator of each can start from its predecessor's winning quartile (warp_ransac_fast, `prior`).
+    unsigned prior = 0u;
+    int prior_u = -1, prior_dj = -2;
+    for (int k_next = 0, k_end = 0;;) {
+        if (k_next == k_end) {
+            if (lane == 0) k_next = atomicAdd(&ctl->next_task, RS_GRID_GRAB);
+            k_next = __shfl_sync(FULL, k_next, 0);
+            k_end = min(k_next + RS_GRID_GRAB, n_tasks);
+            if (k_next >= n_tasks) break;
+        }
+        const int k = k_next++;
         const int u = k / chunk, dj = k - u * chunk;
         const int b = u & 1;
         if (u != cur_u && !staged) {
@@ -1250,7 +1296,17 @@ presync_kernel(DeviceData dd, const FrameDesc* __restrict__ frames, int F,
                          fd.id);
         double M[3] = {0.0, 0.0, 0.0};
         unsigned bad = 0u;
-        if (!simplified) bad = warp_ransac<SLOTS>(dd, fd, w, 20, key, lane, M, flags + 1);  // core_private.cpp:77
+        if (!simplified) {
+            // prior: twice the neighbouring delay's winning quartile (one more exponent; the winning
+            // quartile moves by less than 2 x between neighbouring delays 98.75 % of the time)
+            const bool neighbour = RS_GRID_PRIOR && prior && prior_u == u && prior_dj + 1 == dj && prior < 0x7e000000u;
+            unsigned tau = 0u;
+            bad = warp_ransac<SLOTS>(dd, fd, w, 20, key, lane, M, flags + 1, neighbour ? prior + 0x00800000u : 0u,
+                                     &tau);  // core_private.cpp:77
+            prior = tau;
+            prior_u = u;
+            prior_dj = dj;
+        }
         // :79-85
         __syncwarp();
         // rows past the frame's last ray are zero: they add 0 to the norm and log1p(0) = 0 to the loss.
