@@ -273,7 +273,6 @@ struct rssync_problem {
     PinBuf<double> h_pix;
     DevBuf<double> d_pix, d_stage;
     DevBuf<rs::PixelFrame> d_pixframes;
-    std::vector<rs::PixelFrame> pixframes_host;  // source of an async copy: lives with the problem
     DevBuf<int> d_win_begin;
     DevBuf<unsigned> d_flags;
     PinBuf<double> h_stage;

@@ -1115,6 +1115,9 @@ __device__ __noinline__ unsigned presync_diagnose(const double* pm, int nslots, 
 #ifndef RS_GRID_PRIOR
 #define RS_GRID_PRIOR 1   // start each tournament from the neighbouring delay's winning quartile
 #endif
+#ifndef RS_PRIOR_BUMP
+#define RS_PRIOR_BUMP 0x00800000u  // added to the prior's bit pattern: one exponent = x 2
+#endif
 template <int SLOTS>
 struct GridCfg {
     static constexpr int kWarps = RS_GRID_WARPS;
@@ -1301,7 +1304,7 @@ presync_kernel(DeviceData dd, const FrameDesc* __restrict__ frames, int F,
             // quartile moves by less than 2 x between neighbouring delays 98.75 % of the time)
             const bool neighbour = RS_GRID_PRIOR && prior && prior_u == u && prior_dj + 1 == dj && prior < 0x7e000000u;
             unsigned tau = 0u;
-            bad = warp_ransac<SLOTS>(dd, fd, w, 20, key, lane, M, flags + 1, neighbour ? prior + 0x00800000u : 0u,
+            bad = warp_ransac<SLOTS>(dd, fd, w, 20, key, lane, M, flags + 1, neighbour ? prior + RS_PRIOR_BUMP : 0u,
                                      &tau);  // core_private.cpp:77
             prior = tau;
             prior_u = u;
