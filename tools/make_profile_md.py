@@ -31,7 +31,7 @@ args = fn_ranges(os.path.join(ROOT, "rs-sync_b200/csrc/engine.cu"), "engine.cu")
 summ = subprocess.run([sys.executable, os.path.join(ROOT, "profiles/ncu_summary.py"), rep], capture_output=True, text=True).stdout
 summ = "\n".join(summ.split("\n")[1:])
 lines_out = subprocess.run([sys.executable, os.path.join(ROOT, "profiles/ncu_lines.py"), rep,
-                            os.path.join(ROOT, "rs-sync_b200/lib/engine.o"), "presync_kernelILi7E", "--top", "0",
+                            os.path.join(ROOT, "rs-sync_b200/lib/engine.o"), "presync_kernelILi7ELb0E", "--top", "0",
                             "--stalls"] + args, capture_output=True, text=True).stdout
 tab = []
 for l in lines_out.split("\n"):
