@@ -2278,6 +2278,17 @@ int rssync_adopt_state(rssync_problem* p, const rssync_frame_desc* frames, size_
     p->version++;
     p->pending.clear();
     p->gyro_dirty = false;
+    // the same table as last time (a caller replicating fresh data of an unchanged frame set): keep the map
+    bool same = p->frames.size() == n_frames;
+    if (same) {
+        size_t i = 0;
+        for (auto it = p->frames.begin(); it != p->frames.end() && same; ++it, ++i) {
+            const FrameDesc& a = it->second;
+            const rssync_frame_desc& b = frames[i];
+            same = a.id == b.id && a.off == b.off && a.n == b.n && a.ts_lo == b.ts_lo && a.ts_hi == b.ts_hi;
+        }
+    }
+    if (!same) {
     p->frames.clear();
     p->place_hint_valid = false;
     p->total_rays = 0;
@@ -2290,6 +2301,7 @@ int rssync_adopt_state(rssync_problem* p, const rssync_frame_desc* frames, size_
         }
         p->frames[f.id] = FrameDesc{f.id, f.off, f.n, f.ts_lo, f.ts_hi};
         p->total_rays += (size_t)f.n;
+    }
     }
     p->used = p->dev_used = arena_rays;
     p->garbage = 0;
