@@ -224,6 +224,17 @@ E_ROW, E_LOSS, E_GRAD = 145.0, 10.0, 14.0   # flop per (frame, ray)
 E_EST = lambda iters: 8.0 + 6.0 * iters + 2.0  # row normalisation + iters x (dot3, square) + hypothesis set-up
 
 
+def host_wait(rank, key):
+    """rank 0 has finished a solo measurement: release the other ranks, which wait on the host (the
+    c10d store) rather than inside an NCCL barrier's spinning kernel"""
+    import torch.distributed as dist
+    store = dist.distributed_c10d._get_default_store()
+    if rank == 0:
+        store.set("rssync_" + key, "1")
+    else:
+        store.wait(["rssync_" + key])
+
+
 def sync_flops(acc, n_rays, presync_cells):
     """algorithmic FP64 flop of a syncpoint loop from the engine's evaluation counters"""
     return (FLOP_PER_CELL * presync_cells +
@@ -303,10 +314,13 @@ def bench_syncpoints(prob, w, label, rank, world, barrier, dev, fp64_peak, repea
         ok = True
         n1 = None
         if rank == 0:
-            t1 = time.perf_counter()
-            d1, c1, _ = syncpoint_loop(prob, sps, win, w.presync_step, 0.2, np.arange(S), S)
-            n1 = time.perf_counter() - t1
+            for _ in range(repeat):  # the same best-of as the sharded run
+                t1 = time.perf_counter()
+                d1, c1, _ = syncpoint_loop(prob, sps, win, w.presync_step, 0.2, np.arange(S), S)
+                dt1 = time.perf_counter() - t1
+                n1 = dt1 if n1 is None else min(n1, dt1)
             ok = bool(np.array_equal(d1, alld) and np.array_equal(c1, allc))
+        host_wait(rank, "sync_solo_" + label[:2])
         barrier()
         out["equals_one_gpu"] = ok
         out["n1_seconds_same_run"] = n1
@@ -515,6 +529,19 @@ def run_b200(args):
         del flush_buf
         out["scale"] = bench_scale_configs(pkg, sharded, rank, world, barrier, dev, fp64_peak, cores, local_world)
 
+    # ---- the same N GPUs driven by ONE process through the C ABI (rssync_create_multi) -------------
+    if world > 1:
+        barrier()
+        # the other ranks wait on the HOST (the c10d store), not in an NCCL barrier whose spinning
+        # kernel would share their GPUs with the run
+        store = dist.distributed_c10d._get_default_store()
+        if rank == 0:
+            out["one_process_all_gpus"] = bench_in_library_multi(pkg, w, delays, fb, fe, prob, world, args.steps)
+            store.set("rssync_in_library_done", "1")
+        else:
+            store.wait(["rssync_in_library_done"])
+        barrier()
+
     if rank == 0 and not args.no_cpu and world == 1:
         out["cpu_baseline"] = cpu_baseline(w, delays, args.cpu_seconds)
         out["cpu_baseline"]["parity"] = full_size_parity(prob, w, delays, pkg)
@@ -526,6 +553,39 @@ def run_b200(args):
         print(json.dumps(out))
     if world > 1:
         dist.destroy_process_group()
+
+
+def bench_in_library_multi(pkg, w, delays, fb, fe, single, n_dev, steps):
+    """The headline grid (201 offsets per GPU) through ONE problem spread over all N devices by the
+    library itself (rssync_create_multi: what a C++ caller gets with RSSYNC_DEVICES): offsets sharded
+    inside the library, one ncclAllGather per call on device buffers.  Run by rank 0 while the other
+    ranks wait; the curve is compared bit for bit with the same grid on rank 0's single device."""
+    mp = pkg.SyncProblem(seed=100, devices=list(range(n_dev)))
+    mp.load(w, bulk=True)
+    for i in range(3):
+        mp.presync_grid(fb, fe, delays, stream=pkg.STREAM_DEBUG, call_no=i)
+    t0 = time.perf_counter()
+    for i in range(steps):
+        curve = mp.presync_grid(fb, fe, delays, stream=pkg.STREAM_DEBUG, call_no=3000 + i)
+    dt = (time.perf_counter() - t0) / steps
+    same = bool(np.array_equal(curve, single.presync_grid(fb, fe, delays, stream=pkg.STREAM_DEBUG, call_no=3000 + steps - 1)))
+    # end to end: the inputs enter the primary, are replicated by the library (ncclBroadcast), the grid runs
+    counts = np.full(w.n_frames, w.n_rays)
+    t0 = time.perf_counter()
+    for i in range(3):
+        mp.SetGyroQuaternions(w.quats, w.quats.shape[0], w.gyro_rate, w.gyro_t0)
+        mp.set_track_batch(w.frame_ids, counts, w.ts_a, w.ts_b, w.rays_a, w.rays_b)
+        mp.presync_grid(fb, fe, delays, stream=pkg.STREAM_DEBUG, call_no=4000 + i)
+    e2e = (time.perf_counter() - t0) / 3
+    st = mp.stats()
+    cells = len(delays) * w.n_frames * w.n_rays
+    res = {"devices": mp.device_count(), "ms_per_step": dt * 1e3, "value": cells / dt, "unit": UNIT,
+           "e2e_ms_per_step": e2e * 1e3, "e2e_value": cells / e2e, "equals_one_gpu": same,
+           "nccl_calls": int(st["nccl_calls"]), "timing": "wall clock around the C-ABI call (host buffers out)",
+           "what": "one process, one rssync_problem over all devices; offsets sharded inside the library, one "
+                   "ncclAllGather per call; inputs replicated from the primary by a grouped ncclBroadcast"}
+    mp.close()
+    return res
 
 
 def bench_scale_configs(pkg, sharded, rank, world, barrier, dev, fp64_peak, cores, local_world):
@@ -589,6 +649,7 @@ def bench_scale_configs(pkg, sharded, rank, world, barrier, dev, fp64_peak, core
             whole = p.presync_grid(m["fb"], m["fe"], delays, stream=2, call_no=1)
             n1 = time.perf_counter() - t1
             same = bool(np.array_equal(whole, curve))
+        host_wait(rank, "c3_solo")
         barrier()
         c3.update(n1_seconds_same_run=n1, speedup_vs_one_gpu_same_run=(n1 / dt) if n1 else None, equals_one_gpu=same)
     res["c3_strong"] = c3
