@@ -132,7 +132,8 @@ struct SyncPointState {
 // One lane of the Sync batch driver (sync_batch_impl): a contiguous group of syncpoints with its
 // own stream, device scratch and pinned I/O blocks.
 struct SyncLane {
-    enum Phase { Running, Final, Done };
+    enum Phase { Running, MoreTrials, Final, Done };
+    int n_eval = 10;  // Backtrack trial points evaluated speculatively per iteration (see sync_lane_step)
     cudaStream_t stream = nullptr;
     cudaEvent_t ev = nullptr;
     int s0 = 0, n = 0, t0 = 0, T = 0, iters = 0;
@@ -289,6 +290,7 @@ struct rssync_problem {
     // points, the final objective), estimator runs of the initialisation (200 hypotheses each), and
     // the outer iterations summed over syncpoints
     uint64_t sync_row_builds = 0, sync_loss_evals = 0, sync_init_tasks = 0, sync_outer_total = 0;
+    uint64_t sync_trial_hist[16] = {0};  // index of the Backtrack trial point accepted (kTrials: none), since creation
     bool kernel_timing = false;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     double last_grid_ms = 0.0;
@@ -632,7 +634,7 @@ int sync_lane_begin(rssync_problem* p, SyncLane& L, const rs::DeviceData& dd, co
     //   in : delay[n], x0[n] (doubles), active[n] (bytes); host block 0 serves the iterations (it
     //        is rewritten only after the previous iteration's event), block 1 the initialisation
     //   out: v[n], g[n], trial losses[n x kTrials] (doubles), objective evaluations so far (u64)
-    L.in_doubles = 2 * (size_t)n + ((size_t)n + 7) / 8;
+    L.in_doubles = 2 * (size_t)n + ((size_t)n + 7) / 8 + 1;  // + the number of trial points to evaluate
     L.out_doubles = (2 + (size_t)kTrials) * n + 1;
     CUDA_TRY(p, L.d_in.reserve(L.in_doubles));
     CUDA_TRY(p, L.h_in.reserve(2 * L.in_doubles));
@@ -664,6 +666,8 @@ int sync_lane_begin(rssync_problem* p, SyncLane& L, const rs::DeviceData& dd, co
         hd[n + s] = L.st[s].delay;
         reinterpret_cast<unsigned char*>(hd + 2 * n)[s] = 1;
     }
+    L.n_eval = kTrials;
+    hd[L.in_doubles - 1] = (double)kTrials;
     CUDA_TRY(p, cudaMemcpyAsync(L.d_in.ptr, hd, L.in_doubles * sizeof(double), cudaMemcpyHostToDevice, L.stream));
     p->h2d += L.in_doubles * sizeof(double);
     rs::launch_sync_init(dd, L.b, L.d_in.ptr, L.d_sp_callno.ptr, L.active_dev(), p->seed, L.stream);
@@ -686,9 +690,29 @@ int sync_lane_enqueue_iteration(rssync_problem* p, SyncLane& L, const rs::Device
     if (dbg)
         CUDA_TRY(p, cudaMemcpyAsync(L.h_stats.data(), L.d_lbfgs_stats.ptr, sizeof(int) * 2 * L.T, cudaMemcpyDeviceToHost, L.stream));
     rs::launch_sync_trials(dd, L.b, L.d_trial_delay.ptr, kTrials, L.active_dev(), L.d_task_scratch.ptr,
+                           L.d_out.ptr + 2 * n, L.stream, L.d_in.ptr + L.in_doubles - 1);
+    CUDA_TRY(p, cudaGetLastError());
+    CUDA_TRY(p, cudaMemcpyAsync(L.h_out.ptr, L.d_out.ptr, L.out_doubles * sizeof(double), cudaMemcpyDeviceToHost, L.stream));
+    return RSSYNC_OK;
+}
+
+// Backtrack got further than the trial points evaluated speculatively: evaluate all of them for the
+// lane (same gradient, same trial delays -- they are still on the device) and read them back
+int sync_lane_more_trials(rssync_problem* p, SyncLane& L, const rs::DeviceData& dd) {
+    const int n = L.n;
+    rs::launch_sync_trials(dd, L.b, L.d_trial_delay.ptr, kTrials, L.active_dev(), L.d_task_scratch.ptr,
                            L.d_out.ptr + 2 * n, L.stream);
     CUDA_TRY(p, cudaGetLastError());
     CUDA_TRY(p, cudaMemcpyAsync(L.h_out.ptr, L.d_out.ptr, L.out_doubles * sizeof(double), cudaMemcpyDeviceToHost, L.stream));
+    CUDA_TRY(p, cudaEventRecord(L.ev, L.stream));
+    p->d2h += L.out_doubles * sizeof(double);
+    uint64_t tasks = 0;
+    for (int s = 0; s < n; ++s)
+        if (L.h_active[s]) tasks += (uint64_t)L.sp_frames[(size_t)s];
+    p->sync_row_builds += tasks * (uint64_t)(kTrials - L.n_eval);  // (the kernel recomputes the first ones too;
+    p->sync_loss_evals += tasks * (uint64_t)(kTrials - L.n_eval);  //  only the new ones are counted as work)
+    L.n_eval = kTrials;
+    L.phase = SyncLane::MoreTrials;
     return RSSYNC_OK;
 }
 
@@ -705,14 +729,15 @@ int sync_lane_launch(rssync_problem* p, SyncLane& L, const rs::DeviceData& dd, b
         hd[s] = L.st[s].delay;
         hd[n + s] = L.st[s].delay - .3 * L.st[s].v;  // x0 = delay - delay_b * v, :299 (delay_b :260)
     }
+    hd[L.in_doubles - 1] = (double)L.n_eval;
     L.h_active = ha;
     const bool finish = n_active == 0 || L.iters >= 400;  // :309
     if (!finish) {
         uint64_t tasks = 0;
         for (int s = 0; s < n; ++s)
             if (ha[s]) tasks += (uint64_t)L.sp_frames[(size_t)s];
-        p->sync_row_builds += tasks * ((p->simplified ? 3 : 4) + kTrials);  // at the delay (L-BFGS), x0, x0 -/+ h, the trial points
-        p->sync_loss_evals += tasks * (3 + kTrials);
+        p->sync_row_builds += tasks * (uint64_t)((p->simplified ? 3 : 4) + L.n_eval);  // at the delay (L-BFGS), x0, x0 -/+ h, the trial points
+        p->sync_loss_evals += tasks * (uint64_t)(3 + L.n_eval);
         p->sync_outer_total += (uint64_t)n_active;
     } else {
         p->sync_row_builds += (uint64_t)L.T;  // the final objective (:333)
@@ -775,8 +800,15 @@ int sync_lane_launch(rssync_problem* p, SyncLane& L, const rs::DeviceData& dd, b
     return RSSYNC_OK;
 }
 
-// host half of one outer iteration: Backtrack's acceptance test, momentum, stopping rules
-void sync_lane_step(rssync_problem* p, SyncLane& L, bool record_trace, bool dbg) {
+// host half of one outer iteration: Backtrack's acceptance test, momentum, stopping rules.
+// Backtrack::Step (backtrack.cpp:3-13) takes the FIRST of the trial points t = 1e-3, 1e-4, ... that
+// satisfies the Armijo condition.  All ten are known once the gradient is, so the device evaluates
+// them without a host round trip -- but only the first n_eval of them: Backtrack stops at the same
+// index iteration after iteration (the fourth on GoPro-shaped data: the gradient is ~1e3 1/s, so
+// the first three steps overshoot by orders of magnitude), and every trial point costs a problem
+// matrix per frame.  n_eval follows the index last accepted (+ 2); returns false when no evaluated
+// point passed and points remain, in which case the caller has the rest evaluated and calls again.
+bool sync_lane_step(rssync_problem* p, SyncLane& L, bool record_trace, bool dbg) {
     const int n = L.n;
     const double* h_v = L.h_out.ptr;
     const double* h_g = h_v + n;
@@ -791,17 +823,34 @@ void sync_lane_step(rssync_problem* p, SyncLane& L, bool record_trace, bool dbg)
         std::fprintf(stderr, "sync lane %d it %d: L-BFGS max iters %d, max evals %d\n", L.s0, L.iters, max_it, max_ev);
     }
     const double delay_b = .3;  // :260
+    if (L.n_eval < kTrials)  // does every syncpoint's Backtrack end inside what was evaluated?
+        for (int s = 0; s < n; ++s) {
+            if (L.st[s].done) continue;
+            const double v = h_v[s], g = h_g[s], mm = g * g;
+            double t = 1e-3;
+            bool found = false;
+            for (int i = 0; i < L.n_eval && !found; ++i) {
+                found = v - h_trial_out[(size_t)s * kTrials + i] >= t * 2e-4 * mm;
+                t *= .1;
+            }
+            if (!found) return false;
+        }
+    int furthest = 0;
     for (int s = 0; s < n; ++s) {
         SyncPointState& st = L.st[s];
         if (st.done) continue;
         const double v = h_v[s], g = h_g[s];
         const double mm = g * g;
         double t = 1e-3;
-        for (int i = 0; i < kTrials; ++i) {
+        int accepted = kTrials;
+        for (int i = 0; i < L.n_eval; ++i) {
             const double v1 = h_trial_out[(size_t)s * kTrials + i];
-            if (v - v1 >= t * 2e-4 * mm) break;
+            if (v - v1 >= t * 2e-4 * mm) { accepted = i; break; }
             t *= .1;
         }
+        // (none passed among all ten: t has been multiplied ten times, backtrack.cpp:9-12 returns that step)
+        p->sync_trial_hist[accepted]++;
+        furthest = std::max(furthest, accepted);
         const double step = -t * g;
         st.v = delay_b * st.v + step;  // :301
         st.delay += st.v;              // :302
@@ -814,6 +863,9 @@ void sync_lane_step(rssync_problem* p, SyncLane& L, bool record_trace, bool dbg)
         if (st.converge > 5) st.done = true;                        // :322
         if (std::fabs(st.delay - st.center) > st.radius) st.done = true;  // :326
     }
+    static const bool all_trials = std::getenv("RSSYNC_ALL_TRIALS") != nullptr;
+    L.n_eval = all_trials ? kTrials : std::min(kTrials, std::max(2, furthest + 2));
+    return true;
 }
 
 int sync_batch_impl(rssync_problem* p, int n, const double* initial, const int64_t* fb,
@@ -904,7 +956,11 @@ int sync_batch_impl(rssync_problem* p, int n, const double* initial, const int64
                 --running;
                 continue;
             }
-            sync_lane_step(p, L, record_trace, dbg);
+            if (!sync_lane_step(p, L, record_trace, dbg)) {
+                if (int rc = sync_lane_more_trials(p, L, dd)) return rc;
+                continue;
+            }
+            L.phase = SyncLane::Running;
             if (int rc = sync_lane_launch(p, L, dd, dbg)) return rc;
         }
         if (!progressed) std::this_thread::yield();
@@ -912,6 +968,11 @@ int sync_batch_impl(rssync_problem* p, int n, const double* initial, const int64
     if (const int line = rs::checked_assert_line()) {
         p->err = "device-side assertion failed at engine.cu:" + std::to_string(line);
         return RSSYNC_E_CUDA;
+    }
+    if (dbg) {
+        std::fprintf(stderr, "sync: Backtrack trial accepted (cumulative):");
+        for (int i = 0; i <= kTrials; ++i) std::fprintf(stderr, " %llu", (unsigned long long)p->sync_trial_hist[i]);
+        std::fprintf(stderr, "\n");
     }
     return RSSYNC_OK;
 }

@@ -1532,7 +1532,7 @@ __global__ void reduce_fgrad_kernel(SyncBatchDev b, const unsigned char* __restr
 __global__ void __launch_bounds__(kWarpsPerBlock * 32)
 sync_trials_kernel(DeviceData dd, SyncBatchDev b, int NP, const double* __restrict__ trial_delay,
                    int ntrial, const unsigned char* __restrict__ sp_active,
-                   double* __restrict__ scratch) {
+                   double* __restrict__ scratch, const double* __restrict__ n_eval) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     double* tab = reinterpret_cast<double*>(smem_raw);
@@ -1542,6 +1542,9 @@ sync_trials_kernel(DeviceData dd, SyncBatchDev b, int NP, const double* __restri
     for (long long q = (long long)blockIdx.x * kWarpsPerBlock + warp; q < total;
          q += (long long)gridDim.x * kWarpsPerBlock) {
         const int t = (int)(q / ntrial), j = (int)(q % ntrial);
+        // only the first *n_eval trial points are evaluated (the host's guess of how far Backtrack
+        // will get; it asks for the rest when the guess was short)
+        if (n_eval && j >= (int)*n_eval) continue;
         const SyncTask task = b.tasks[t];
         if (!sp_active[task.sp]) continue;
         const int nslots = (task.fd.n + 31) >> 5;
@@ -1556,12 +1559,13 @@ sync_trials_kernel(DeviceData dd, SyncBatchDev b, int NP, const double* __restri
 
 __global__ void reduce_trials_kernel(SyncBatchDev b, int ntrial,
                                      const unsigned char* __restrict__ sp_active,
-                                     const double* __restrict__ scratch, double* __restrict__ out) {
+                                     const double* __restrict__ scratch, double* __restrict__ out,
+                                     const double* __restrict__ n_eval) {
     const int lane = threadIdx.x & 31;
     const int q = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (q >= b.S * ntrial) return;
     const int sp = q / ntrial, j = q % ntrial;
-    if (!sp_active[sp]) return;
+    if (!sp_active[sp] || (n_eval && j >= (int)*n_eval)) return;
     DD acc = dd_zero();
     for (int t = b.sp_begin[sp] + lane; t < b.sp_begin[sp + 1]; t += 32)
         dd_add(acc, scratch[(size_t)t * ntrial + j]);
@@ -2184,7 +2188,7 @@ void launch_sync_motion_fgrad(const DeviceData& dd, const SyncBatchDev& b, const
 
 void launch_sync_trials(const DeviceData& dd, const SyncBatchDev& b, const double* d_trial_delay,
                         int ntrial, const unsigned char* d_sp_active, double* d_task_scratch,
-                        double* d_out, cudaStream_t st) {
+                        double* d_out, cudaStream_t st, const double* d_n_eval) {
     if (b.S <= 0 || ntrial <= 0) return;
     if (b.T > 0) {  // (T == 0: sums over no frames, see launch_sync_motion_fgrad)
         const int NP = slots_for(b.max_n) * 32;
@@ -2192,9 +2196,10 @@ void launch_sync_trials(const DeviceData& dd, const SyncBatchDev& b, const doubl
         allow_smem(sync_trials_kernel, smem);
         const int grid = grid_for(sync_trials_kernel, smem, (long long)b.T * ntrial);
         sync_trials_kernel<<<grid, kWarpsPerBlock * 32, smem, st>>>(dd, b, NP, d_trial_delay, ntrial,
-                                                                    d_sp_active, d_task_scratch);
+                                                                    d_sp_active, d_task_scratch, d_n_eval);
     }
-    reduce_trials_kernel<<<(b.S * ntrial + 3) / 4, 128, 0, st>>>(b, ntrial, d_sp_active, d_task_scratch, d_out);
+    reduce_trials_kernel<<<(b.S * ntrial + 3) / 4, 128, 0, st>>>(b, ntrial, d_sp_active, d_task_scratch, d_out,
+                                                                 d_n_eval);
     g_launches += 2;
 }
 

@@ -100,10 +100,11 @@ void launch_sync_motion_fgrad(const DeviceData& dd, const SyncBatchDev& b, const
                                                  slots: use the small-block, register-capped build */,
                               cudaStream_t st);
 // Loss3 summed per syncpoint at ntrial delays per syncpoint (simple_objective, :242-252)
+// d_n_eval (device, optional): only the first (int)*d_n_eval of the ntrial points are evaluated
 void launch_sync_trials(const DeviceData& dd, const SyncBatchDev& b, const double* d_trial_delay,
                         int ntrial, const unsigned char* d_sp_active,
                         double* d_task_scratch /* T x ntrial */, double* d_out /* S x ntrial */,
-                        cudaStream_t st);
+                        cudaStream_t st, const double* d_n_eval = nullptr);
 
 // ---- gyro spline: finish the records on the device (host_ingest.h build_spline_system) ---------
 // d_quats: n x 4 samples; d_rhs: n x 4, d_diag: n (the eliminated system); d_rec: n records of 16
