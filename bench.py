@@ -44,8 +44,9 @@ def parse():
     ap.add_argument("--no-sync", action="store_true", help="skip the syncpoints/s section")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline section")
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
-    ap.add_argument("--scale-configs", action="store_true",
-                    help="also run C3 (strong scaling) and C4 with 900 syncpoints at N = 1 (they always run for N > 1)")
+    ap.add_argument("--scale-configs", action="store_true", help="(kept for old command lines: now the default)")
+    ap.add_argument("--no-scale", action="store_true",
+                    help="skip C3 (strong scaling) and C4 with 900 syncpoints (about 25 s at N = 1)")
     return ap.parse_args()
 
 
@@ -525,7 +526,7 @@ def run_b200(args):
                                                     barrier, dev, fp64_peak, repeat=3)
 
     # ---- the sharded configurations north_star names (C3 strong scaling, C4 with 900 syncpoints) --
-    if world > 1 or args.scale_configs:
+    if not args.no_scale:
         del flush_buf
         out["scale"] = bench_scale_configs(pkg, sharded, rank, world, barrier, dev, fp64_peak, cores, local_world)
 

@@ -20,6 +20,12 @@
 #include <thread>
 #include <utility>
 #include <vector>
+#if defined(__x86_64__)
+#include <immintrin.h>
+#endif
+#ifndef RSSYNC_STAGE_DEFAULT
+#define RSSYNC_STAGE_DEFAULT 2  // staging copy: 0 scalar, 1 AVX2, 2 AVX2 with non-temporal stores
+#endif
 
 #include "engine.h"
 #include "host_ingest.h"
@@ -1420,7 +1426,7 @@ int validate_track(const double* ts_a, const double* ts_b, const double* rays_a,
 
 // copy n doubles, report whether all are finite, and fold them into [lo, hi] when asked to:
 // x * 0.0 is +-0 for finite x and NaN otherwise, so one accumulator carries the check
-inline bool copy_checked(double* dst, const double* src, size_t n, double* lo, double* hi) {
+inline bool copy_checked_scalar(double* dst, const double* src, size_t n, double* lo, double* hi) {
     double acc = 0.0, l = lo ? *lo : 0.0, h = hi ? *hi : 0.0;
     for (size_t i = 0; i < n; ++i) {
         const double v = src[i];
@@ -1430,6 +1436,66 @@ inline bool copy_checked(double* dst, const double* src, size_t n, double* lo, d
     }
     if (lo) { *lo = l; *hi = h; }
     return acc == 0.0;
+}
+#if defined(__x86_64__)
+// The same with four doubles per instruction (the scalar form is a floating-point reduction, which the
+// compiler may not vectorise).  NT: non-temporal stores -- the staging buffer is written once and read
+// next by the copy engine, so the lines need not be fetched for ownership nor kept in the cache.
+template <bool NT>
+__attribute__((target("avx2"))) bool copy_checked_avx2(double* dst, const double* src, size_t n, double* lo, double* hi) {
+    double acc = 0.0, l = lo ? *lo : 0.0, h = hi ? *hi : 0.0;
+    size_t i = 0;
+    for (; i < n && (reinterpret_cast<uintptr_t>(dst + i) & 31); ++i) {
+        const double v = src[i];
+        dst[i] = v;
+        acc += v * 0.0;
+        l = v < l ? v : l;
+        h = v > h ? v : h;
+    }
+    __m256d va = _mm256_setzero_pd(), vl = _mm256_set1_pd(l), vh = _mm256_set1_pd(h);
+    const __m256d zero = _mm256_setzero_pd();
+    for (; i + 4 <= n; i += 4) {
+        const __m256d v = _mm256_loadu_pd(src + i);
+        if (NT) _mm256_stream_pd(dst + i, v);
+        else _mm256_store_pd(dst + i, v);
+        va = _mm256_add_pd(va, _mm256_mul_pd(v, zero));
+        vl = _mm256_min_pd(v, vl);  // v < vl ? v : vl, as the scalar form
+        vh = _mm256_max_pd(v, vh);
+    }
+    double ta[4], tl[4], th[4];
+    _mm256_storeu_pd(ta, va);
+    _mm256_storeu_pd(tl, vl);
+    _mm256_storeu_pd(th, vh);
+    for (int k = 0; k < 4; ++k) {
+        acc += ta[k];
+        l = tl[k] < l ? tl[k] : l;
+        h = th[k] > h ? th[k] : h;
+    }
+    for (; i < n; ++i) {
+        const double v = src[i];
+        dst[i] = v;
+        acc += v * 0.0;
+        l = v < l ? v : l;
+        h = v > h ? v : h;
+    }
+    if (NT) _mm_sfence();  // the stores are globally visible before the copy engine is pointed at them
+    if (lo) { *lo = l; *hi = h; }
+    return acc == 0.0;
+}
+#endif
+inline bool copy_checked(double* dst, const double* src, size_t n, double* lo, double* hi) {
+#if defined(__x86_64__)
+    // RSSYNC_STAGE = scalar | avx2 | nt (measurement knob)
+    static const int mode = [] {
+        if (!__builtin_cpu_supports("avx2")) return 0;
+        const char* e = std::getenv("RSSYNC_STAGE");
+        if (!e) return RSSYNC_STAGE_DEFAULT;
+        return e[0] == 's' ? 0 : e[0] == 'a' ? 1 : 2;
+    }();
+    if (mode == 1) return copy_checked_avx2<false>(dst, src, n, lo, hi);
+    if (mode == 2) return copy_checked_avx2<true>(dst, src, n, lo, hi);
+#endif
+    return copy_checked_scalar(dst, src, n, lo, hi);
 }
 
 // SetTrackResult, stage 1 of the bulk form: validate_track fused with the copy into the staging
