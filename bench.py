@@ -416,6 +416,7 @@ def run_b200(args):
             curve = gather_out.reshape(-1)
         else:
             curve = torch.from_numpy(costs)
+        step.curve = curve.clone()
         return int(torch.argmin(curve))
 
     sampler = ClockSampler(local)
@@ -473,6 +474,13 @@ def run_b200(args):
     barrier()
     e2e_s = (time.perf_counter() - t0) / e2e_steps
     st1 = prob.stats()
+    # the curve that came out of the pipelined path (grid behind the ingest / the replication still in
+    # flight) against the same call on the now resident state
+    e2e_curve = step.curve
+    step(2000 + e2e_steps - 1)
+    e2e_same = torch.tensor([1.0 if torch.equal(e2e_curve, step.curve) else 0.0], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(e2e_same, op=dist.ReduceOp.MIN)
     if world > 1:
         ds = prob.device_state()
         bcast_bytes = sum(ds[k][1] for k in ("rays", "orig", "pos", "spline_records")) + w.n_frames * 32
@@ -492,6 +500,7 @@ def run_b200(args):
                     "to the other ranks by NCCL broadcast over NVLink; every rank's grid slice through the C ABI; "
                     "curve gathered; bytes are summed over ranks"),
            "nvlink_broadcast_bytes_per_step": int(bcast_bytes),
+           "equals_resident_state": bool(float(e2e_same[0]) == 1.0),
            "ms_each_step_rank0": [round(1e3 * (b - a), 3) for a, b in zip([t0] + e2e_marks[:-1], e2e_marks)]}
 
     # ---- roofline of the dominant kernel (presync_kernel) -------------------------------------

@@ -263,6 +263,23 @@ int rssync_adopt_state(rssync_problem* p, const rssync_frame_desc* frames, size_
                        size_t arena_rays, size_t gyro_samples, double sample_rate,
                        double first_timestamp);
 
+/* Pipelined form of the same, for a source that has just taken a bulk SetTrackResult whose chunks are
+ * still on their way to its device.  rssync_device_state_pipelined returns the pointers WITHOUT
+ * waiting for the device, plus the arena ranges [lo, hi) (in rays) of the ingest chunks in flight
+ * (n_chunks of them; at most cap are written).  rssync_stream_wait_chunk makes `stream` (a
+ * cudaStream_t of the caller) wait for chunk k to have landed (k = -1: for everything queued on the
+ * problem's own stream so far, i.e. the spline records and frames set one by one), so the caller can
+ * send each chunk on as soon as it is there.  On the receiving side, rssync_expect_chunk tells the
+ * adopting problem that the arena range [lo, hi) is being written by work queued on `stream`: a
+ * PreSync grid that follows evaluates each frame as soon as the chunks covering it have arrived, as
+ * it does behind its own ingest.  rssync_note_reader: work queued on `stream` still reads this
+ * problem's device state; the next Set* call waits for it before overwriting anything. */
+int rssync_device_state_pipelined(rssync_problem* p, rssync_device_state_t* out, size_t* chunk_lo,
+                                  size_t* chunk_hi, size_t cap, size_t* n_chunks);
+int rssync_stream_wait_chunk(rssync_problem* p, int k, void* stream);
+int rssync_expect_chunk(rssync_problem* p, size_t lo, size_t hi, void* stream);
+int rssync_note_reader(rssync_problem* p, void* stream);
+
 /* FP64 FMA throughput of the current device in TFLOP/s (FMA = 2 flop): the measured denominator
  * of the FP64 roofline. */
 int rssync_measure_fp64_peak(double* tflops);

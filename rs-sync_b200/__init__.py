@@ -37,6 +37,7 @@ C_ABI_SYMBOLS = [
     "rssync_sync_batch_ex", "rssync_probe_guess_motion_ex", "rssync_integrate_gyro",
     "rssync_orientation_search", "rssync_orientation_search_ex", "rssync_presync_windows", "rssync_set_track_pixels",
     "rssync_create_multi", "rssync_device_count", "rssync_frame_table", "rssync_device_state", "rssync_adopt_state",
+    "rssync_device_state_pipelined", "rssync_stream_wait_chunk", "rssync_expect_chunk", "rssync_note_reader",
     "rssync_set_loss_mode", "rssync_probe_spec_trig",
 ]
 # Itanium-ABI symbols of the C++ drop-in face (same set the reference's librssync_core exports)
@@ -98,6 +99,11 @@ def load_library():
     L.rssync_frame_table.argtypes = [P, C.POINTER(FrameDesc), C.c_size_t]
     L.rssync_device_state.argtypes = [P, C.POINTER(DeviceState)]
     L.rssync_adopt_state.argtypes = [P, C.POINTER(FrameDesc), C.c_size_t, C.c_size_t, C.c_size_t, C.c_double, C.c_double]
+    L.rssync_device_state_pipelined.argtypes = [P, C.POINTER(DeviceState), C.POINTER(C.c_size_t), C.POINTER(C.c_size_t),
+                                                C.c_size_t, C.POINTER(C.c_size_t)]
+    L.rssync_stream_wait_chunk.argtypes = [P, C.c_int, C.c_void_p]
+    L.rssync_expect_chunk.argtypes = [P, C.c_size_t, C.c_size_t, C.c_void_p]
+    L.rssync_note_reader.argtypes = [P, C.c_void_p]
     L.rssync_destroy.argtypes = [P]
     L.rssync_destroy.restype = None
     L.rssync_last_error.argtypes = [P]
@@ -371,6 +377,36 @@ class SyncProblem:
                 "pos": (st.pos, st.arena_rays * 4), "spline_records": (st.spline_records, st.gyro_samples * 128),
                 "arena_rays": st.arena_rays, "gyro_samples": st.gyro_samples, "sample_rate": st.sample_rate,
                 "first_timestamp": st.first_timestamp}
+
+    @staticmethod
+    def _state_dict(st):
+        return {"rays": (st.rays, st.arena_rays * 64), "orig": (st.orig, st.arena_rays * 4),
+                "pos": (st.pos, st.arena_rays * 4), "spline_records": (st.spline_records, st.gyro_samples * 128),
+                "arena_rays": st.arena_rays, "gyro_samples": st.gyro_samples, "sample_rate": st.sample_rate,
+                "first_timestamp": st.first_timestamp}
+
+    def device_state_pipelined(self):
+        """device_state() without waiting for the device, plus the arena ranges [(lo, hi), ...] of the
+        bulk-ingest chunks still in flight (stream_wait_chunk(k, stream) orders a stream behind chunk k)"""
+        st = DeviceState()
+        cap = 64
+        lo, hi, n = (C.c_size_t * cap)(), (C.c_size_t * cap)(), C.c_size_t(0)
+        self._check(self.L.rssync_device_state_pipelined(self.h, C.byref(st), lo, hi, cap, C.byref(n)))
+        d = self._state_dict(st)
+        if n.value > cap:  # more chunks than we asked for: treat the ingest as one piece
+            d["chunks"] = None
+        else:
+            d["chunks"] = [(int(lo[k]), int(hi[k])) for k in range(n.value)]
+        return d
+
+    def stream_wait_chunk(self, k, stream):
+        self._check(self.L.rssync_stream_wait_chunk(self.h, int(k), C.c_void_p(int(stream))))
+
+    def expect_chunk(self, lo, hi, stream):
+        self._check(self.L.rssync_expect_chunk(self.h, int(lo), int(hi), C.c_void_p(int(stream))))
+
+    def note_reader(self, stream):
+        self._check(self.L.rssync_note_reader(self.h, C.c_void_p(int(stream))))
 
     def adopt_state(self, frame_table, arena_rays, gyro_samples, sample_rate, first_timestamp):
         """prepare this problem to hold a copy of another problem's device state (the buffers are

@@ -204,6 +204,9 @@ struct rssync_problem {
     // wait for them
     cudaEvent_t ev_arena = nullptr;
     bool arena_copy_pending = false;
+    // a foreign stream still reading the device state (rssync_note_reader: a replication in flight)
+    cudaEvent_t ev_reader = nullptr;
+    bool reader_pending = false;
     // The bulk ingest runs on its own stream, one event per chunk of frames: a PreSync grid that
     // follows evaluates the frames of a chunk as soon as that chunk has landed instead of waiting
     // for the whole upload (the upload of C2 takes 2 ms at the 24 GB/s this host's PCIe delivers,
@@ -214,6 +217,7 @@ struct rssync_problem {
         cudaEvent_t ev;
     };
     cudaStream_t copy_stream = nullptr;
+    cudaStream_t repl_stream = nullptr;  // multi-device problems: the replication's collectives
     static constexpr int kGridStreams = 3;  // side streams of a chunk-by-chunk PreSync grid
     cudaStream_t grid_stream[kGridStreams] = {nullptr, nullptr, nullptr};
     cudaEvent_t ev_grid[kGridStreams] = {nullptr, nullptr, nullptr};
@@ -333,12 +337,20 @@ int d2h(rssync_problem* p, void* dst, const void* src, size_t bytes) {
 void join_gyro(rssync_problem* p) {
     if (p->gyro_worker.joinable()) p->gyro_worker.join();
 }
+// a replication still reading this problem's device state on a foreign stream (rssync_note_reader)
+int wait_reader(rssync_problem* p) {
+    if (p->reader_pending) {
+        CUDA_TRY(p, cudaEventSynchronize(p->ev_reader));
+        p->reader_pending = false;
+    }
+    return RSSYNC_OK;
+}
 int wait_arena_copies(rssync_problem* p) {
     if (p->arena_copy_pending) {
         CUDA_TRY(p, cudaEventSynchronize(p->ev_arena));
         p->arena_copy_pending = false;
     }
-    return RSSYNC_OK;
+    return wait_reader(p);
 }
 
 // the problem's stream waits (on the device) for every bulk-ingest chunk still in flight
@@ -479,6 +491,83 @@ bool is_multi(const rssync_problem* p) { return !p->replicas.empty() && !p->forc
 
 void parallel_copy(void* dst, const void* src, size_t bytes);  // worker pool, below
 
+// The kernel launches of one PreSync grid over the frames `sel` (already in p->d_frames) and the n
+// delays in p->d_delays, into p->d_framecost; the per-delay reduction is the caller's.
+int enqueue_grid_kernels(rssync_problem* p, const std::vector<FrameDesc>& sel, int max_n, int n, uint64_t stream_id,
+                         uint64_t call_no, uint64_t idx_base, unsigned* d_flags, int max_chunk, bool timed,
+                         size_t* n_launches, int* n_waited) {
+    const int F = (int)sel.size();
+    // Frames still being uploaded by a bulk ingest: cut the frame list into runs by the ingest chunk
+    // they wait for, and launch each run behind that chunk's event, so the grid works on the first
+    // chunks while the last ones are on the bus.  (Frame costs do not depend on how frames are
+    // grouped into launches.)  dep[f] = 1 + index of the last in-flight chunk overlapping frame f.
+    std::vector<int> run_end, run_dep;
+    if (!p->in_flight.empty()) {
+        int cur = -1;
+        for (int f = 0; f < F; ++f) {
+            const size_t a = (size_t)sel[f].off, b = a + (size_t)(sel[f].n + 31) / 32 * 32;
+            int dep = 0;
+            for (size_t k = p->in_flight.size(); k-- > 0;)
+                if (a < p->in_flight[k].hi && p->in_flight[k].lo < b) { dep = (int)k + 1; break; }
+            dep = std::max(dep, cur < 0 ? 0 : run_dep.back());  // events complete in order: keep runs monotone
+            if (dep != cur) {
+                if (cur >= 0) run_end.push_back(f);
+                run_dep.push_back(dep);
+                cur = dep;
+            }
+        }
+        run_end.push_back(F);
+        if (run_end.size() > 16) { run_end.assign(1, F); run_dep.assign(1, (int)p->in_flight.size()); }
+    } else {
+        run_end.assign(1, F);
+        run_dep.assign(1, 0);
+    }
+    const rs::DeviceData dd = p->device_data();
+    if (timed) CUDA_TRY(p, cudaEventRecord(p->ev0, p->stream));
+    int f0 = 0, waited = 0;
+    if (run_end.size() == 1) {
+        if (run_dep[0] > 0) {
+            CUDA_TRY(p, cudaStreamWaitEvent(p->stream, p->in_flight[(size_t)run_dep[0] - 1].ev, 0));
+            waited = run_dep[0];
+        }
+        rs::launch_presync_tasks(dd, p->d_frames.ptr, F, max_n, p->d_delays.ptr, n, p->seed, stream_id, call_no,
+                                 idx_base, p->d_framecost.ptr, F, d_flags, p->stream, nullptr, max_chunk, p->simplified);
+    } else {
+        // The runs go round-robin to a few side streams: kernels of one stream run one after the
+        // other, so a single stream would leave the tail of every run (its last blocks) unshared;
+        // from neighbouring streams the next run's blocks move in as the previous run's retire.
+        for (int k = 0; k < rssync_problem::kGridStreams; ++k) {
+            if (!p->grid_stream[k]) CUDA_TRY(p, cudaStreamCreateWithFlags(&p->grid_stream[k], cudaStreamNonBlocking));
+            if (!p->ev_grid[k]) CUDA_TRY(p, cudaEventCreateWithFlags(&p->ev_grid[k], cudaEventDisableTiming));
+        }
+        if (!p->ev_order) CUDA_TRY(p, cudaEventCreateWithFlags(&p->ev_order, cudaEventDisableTiming));
+        CUDA_TRY(p, cudaEventRecord(p->ev_order, p->stream));  // frame table, delays, gyro records
+        for (size_t r = 0; r < run_end.size(); ++r) {
+            cudaStream_t gs = p->grid_stream[r % rssync_problem::kGridStreams];
+            if (r < (size_t)rssync_problem::kGridStreams) CUDA_TRY(p, cudaStreamWaitEvent(gs, p->ev_order, 0));
+            if (run_dep[r] > 0) {
+                CUDA_TRY(p, cudaStreamWaitEvent(gs, p->in_flight[(size_t)run_dep[r] - 1].ev, 0));
+                waited = std::max(waited, run_dep[r]);
+            }
+            rs::launch_presync_tasks(dd, p->d_frames.ptr + f0, run_end[r] - f0, max_n, p->d_delays.ptr, n, p->seed,
+                                     stream_id, call_no, idx_base, p->d_framecost.ptr + f0, F, d_flags, gs,
+                                     nullptr, max_chunk, p->simplified);
+            f0 = run_end[r];
+        }
+        for (int k = 0; k < rssync_problem::kGridStreams; ++k) {
+            CUDA_TRY(p, cudaEventRecord(p->ev_grid[k], p->grid_stream[k]));
+            CUDA_TRY(p, cudaStreamWaitEvent(p->stream, p->ev_grid[k], 0));
+        }
+    }
+    if (timed) CUDA_TRY(p, cudaEventRecord(p->ev1, p->stream));
+    if (n_launches) *n_launches = run_end.size();
+    if (n_waited) *n_waited = waited;
+    // the chunks this call waited for are done with; later ones (frames outside this call) stay
+    for (int k = 0; k < waited; ++k) p->ev_pool.push_back(p->in_flight[(size_t)k].ev);
+    p->in_flight.erase(p->in_flight.begin(), p->in_flight.begin() + waited);
+    return RSSYNC_OK;
+}
+
 int presync_grid_impl(rssync_problem* p, int64_t fb, int64_t fe, const double* delays, int n,
                       uint64_t stream_id, uint64_t call_no, uint64_t idx_base, double* costs,
                       unsigned* flags_out) {
@@ -510,76 +599,15 @@ int presync_grid_impl(rssync_problem* p, int64_t fb, int64_t fe, const double* d
     if (int rc = h2d(p, p->d_frames.ptr, sel.data(), sizeof(FrameDesc) * F)) return rc;
     if (int rc = h2d(p, p->d_delays.ptr, delays, sizeof(double) * n)) return rc;
     CUDA_TRY(p, cudaMemsetAsync(p->d_flags.ptr, 0, 2 * sizeof(unsigned), p->stream));
-    // Frames still being uploaded by a bulk ingest: cut the frame list into runs by the ingest chunk
-    // they wait for, and launch each run behind that chunk's event, so the grid works on the first
-    // chunks while the last ones are on the bus.  (Frame costs do not depend on how frames are
-    // grouped into launches.)  dep[f] = 1 + index of the last in-flight chunk overlapping frame f.
-    std::vector<int> run_end, run_dep;
-    if (!p->in_flight.empty()) {
-        int cur = -1;
-        for (int f = 0; f < F; ++f) {
-            const size_t a = (size_t)sel[f].off, b = a + (size_t)(sel[f].n + 31) / 32 * 32;
-            int dep = 0;
-            for (size_t k = p->in_flight.size(); k-- > 0;)
-                if (a < p->in_flight[k].hi && p->in_flight[k].lo < b) { dep = (int)k + 1; break; }
-            dep = std::max(dep, cur < 0 ? 0 : run_dep.back());  // events complete in order: keep runs monotone
-            if (dep != cur) {
-                if (cur >= 0) run_end.push_back(f);
-                run_dep.push_back(dep);
-                cur = dep;
-            }
-        }
-        run_end.push_back(F);
-        if (run_end.size() > 16) { run_end.assign(1, F); run_dep.assign(1, (int)p->in_flight.size()); }
-    } else {
-        run_end.assign(1, F);
-        run_dep.assign(1, 0);
-    }
-    const rs::DeviceData dd = p->device_data();
-    if (p->kernel_timing) CUDA_TRY(p, cudaEventRecord(p->ev0, p->stream));
-    int f0 = 0, waited = 0;
-    if (run_end.size() == 1) {
-        if (run_dep[0] > 0) {
-            CUDA_TRY(p, cudaStreamWaitEvent(p->stream, p->in_flight[(size_t)run_dep[0] - 1].ev, 0));
-            waited = run_dep[0];
-        }
-        rs::launch_presync_tasks(dd, p->d_frames.ptr, F, max_n, p->d_delays.ptr, n, p->seed, stream_id, call_no,
-                                 idx_base, p->d_framecost.ptr, F, p->d_flags.ptr, p->stream, nullptr, max_chunk, p->simplified);
-    } else {
-        // The runs go round-robin to a few side streams: kernels of one stream run one after the
-        // other, so a single stream would leave the tail of every run (its last blocks) unshared;
-        // from neighbouring streams the next run's blocks move in as the previous run's retire.
-        for (int k = 0; k < rssync_problem::kGridStreams; ++k) {
-            if (!p->grid_stream[k]) CUDA_TRY(p, cudaStreamCreateWithFlags(&p->grid_stream[k], cudaStreamNonBlocking));
-            if (!p->ev_grid[k]) CUDA_TRY(p, cudaEventCreateWithFlags(&p->ev_grid[k], cudaEventDisableTiming));
-        }
-        if (!p->ev_order) CUDA_TRY(p, cudaEventCreateWithFlags(&p->ev_order, cudaEventDisableTiming));
-        CUDA_TRY(p, cudaEventRecord(p->ev_order, p->stream));  // frame table, delays, gyro records
-        for (size_t r = 0; r < run_end.size(); ++r) {
-            cudaStream_t gs = p->grid_stream[r % rssync_problem::kGridStreams];
-            if (r < (size_t)rssync_problem::kGridStreams) CUDA_TRY(p, cudaStreamWaitEvent(gs, p->ev_order, 0));
-            if (run_dep[r] > 0) {
-                CUDA_TRY(p, cudaStreamWaitEvent(gs, p->in_flight[(size_t)run_dep[r] - 1].ev, 0));
-                waited = std::max(waited, run_dep[r]);
-            }
-            rs::launch_presync_tasks(dd, p->d_frames.ptr + f0, run_end[r] - f0, max_n, p->d_delays.ptr, n, p->seed,
-                                     stream_id, call_no, idx_base, p->d_framecost.ptr + f0, F, p->d_flags.ptr, gs,
-                                     nullptr, max_chunk, p->simplified);
-            f0 = run_end[r];
-        }
-        for (int k = 0; k < rssync_problem::kGridStreams; ++k) {
-            CUDA_TRY(p, cudaEventRecord(p->ev_grid[k], p->grid_stream[k]));
-            CUDA_TRY(p, cudaStreamWaitEvent(p->stream, p->ev_grid[k], 0));
-        }
-    }
-    if (p->kernel_timing) CUDA_TRY(p, cudaEventRecord(p->ev1, p->stream));
+    size_t n_launches = 0;
+    int waited = 0;
+    if (int rc = enqueue_grid_kernels(p, sel, max_n, n, stream_id, call_no, idx_base, p->d_flags.ptr, max_chunk,
+                                      p->kernel_timing, &n_launches, &waited))
+        return rc;
     rs::launch_presync_reduce(p->d_framecost.ptr, F, n, p->d_costs.ptr, p->stream);
     CUDA_TRY(p, cudaGetLastError());
-    if (tm.on) std::fprintf(stderr, "[presync_grid] %zu launch(es) behind %d in-flight chunk(s)\n", run_end.size(), waited);
+    if (tm.on) std::fprintf(stderr, "[presync_grid] %zu launch(es) behind %d in-flight chunk(s)\n", n_launches, waited);
     tm.mark("launch");
-    // the chunks this call waited for are done with; later ones (frames outside this call) stay
-    for (int k = 0; k < waited; ++k) p->ev_pool.push_back(p->in_flight[(size_t)k].ev);
-    p->in_flight.erase(p->in_flight.begin(), p->in_flight.begin() + waited);
     unsigned flags[2] = {0, 0};
     if (int rc = d2h(p, costs, p->d_costs.ptr, sizeof(double) * n)) return rc;
     if (int rc = d2h(p, flags, p->d_flags.ptr, 2 * sizeof(unsigned))) return rc;
@@ -1013,10 +1041,42 @@ int multi_replicate(rssync_problem* p) {
     bool stale = false;
     for (const rssync_problem* r : p->replicas) stale = stale || r->synced_version != p->version;
     if (!stale) return RSSYNC_OK;
-    if (int rc = flush(p)) return rc;  // device 0 holds everything; its stream orders the broadcast behind the ingest
+    // Device 0 holds everything.  A bulk SetTrackResult may still be on its way there, chunk by chunk:
+    // the chunks are sent on in a few pieces, each as soon as it has landed, on streams of their own,
+    // and every replica is told which arena ranges are still coming (rssync_expect_chunk) -- its grid
+    // then starts on the first frames while the last are on the bus, as the primary's does.
+    if (int rc = flush(p, /*keep_in_flight=*/true)) return rc;
     const rs::Nccl* nc = rs::Nccl::get();
     DeviceGuard guard;
     const size_t rays = p->dev_used;
+    // The pieces cover the whole arena: first whatever no chunk in flight covers (k_last = -1: it is on
+    // the device already -- an ingest that had to grow the arena waited for its first chunks, frames
+    // set one by one were uploaded by the flush above), then the chunks in flight, a few at a time.
+    struct Piece { int k_last; size_t lo, hi; };
+    std::vector<Piece> pieces;
+    const size_t nfl = p->in_flight.size();
+    {
+        std::vector<std::pair<size_t, size_t>> busy;
+        for (const auto& f : p->in_flight) busy.emplace_back(f.lo, f.hi);
+        std::sort(busy.begin(), busy.end());
+        size_t at = 0;
+        for (const auto& b : busy) {
+            if (b.first > at) pieces.push_back(Piece{-1, at, b.first});
+            at = std::max(at, b.second);
+        }
+        if (rays > at) pieces.push_back(Piece{-1, at, rays});
+    }
+    const size_t n_groups = std::min<size_t>(nfl, 4);
+    for (size_t g = 0; g < n_groups; ++g) {
+        const size_t a = nfl * g / n_groups, b = nfl * (g + 1) / n_groups;
+        Piece pc{(int)b - 1, p->in_flight[a].lo, p->in_flight[a].hi};
+        for (size_t k = a; k < b; ++k) {
+            pc.lo = std::min(pc.lo, p->in_flight[k].lo);
+            pc.hi = std::max(pc.hi, p->in_flight[k].hi);
+        }
+        if (pc.lo < pc.hi) pieces.push_back(pc);
+    }
+    if (pieces.size() > 16) pieces.assign(1, Piece{(int)nfl - 1, 0, rays});  // scattered updates: one piece, last
     for (rssync_problem* r : p->replicas) {
         cudaSetDevice(r->device);
         r->frames = p->frames;
@@ -1025,6 +1085,9 @@ int multi_replicate(rssync_problem* p) {
         r->seed = p->seed;
         r->simplified = p->simplified;
         cudaError_t e = cudaStreamSynchronize(r->stream);  // nothing of an earlier call still reads the buffers
+        if (e == cudaSuccess && r->repl_stream) e = cudaStreamSynchronize(r->repl_stream);
+        for (const auto& f : r->in_flight) r->ev_pool.push_back(f.ev);
+        r->in_flight.clear();
         if (e == cudaSuccess) e = r->d_rays.reserve(std::max<size_t>(rays, 1) * 8);
         if (e == cudaSuccess) e = r->d_orig.reserve(std::max<size_t>(rays, 1));
         if (e == cudaSuccess) e = r->d_pos.reserve(std::max<size_t>(rays, 1));
@@ -1034,23 +1097,48 @@ int multi_replicate(rssync_problem* p) {
             return RSSYNC_E_CUDA;
         }
     }
-    NCCL_TRY(p, nc->GroupStart());
     for (int i = 0; i < n_ranks(p); ++i) {
         rssync_problem* q = rank_problem(p, i);
         cudaSetDevice(q->device);
-        void* comm = p->comms[(size_t)i];
-        if (rays) {
-            NCCL_TRY(p, nc->Broadcast(q->d_rays.ptr, q->d_rays.ptr, rays * 8 * sizeof(double), rs::Nccl::kChar, 0, comm, q->stream));
-            NCCL_TRY(p, nc->Broadcast(q->d_orig.ptr, q->d_orig.ptr, rays * sizeof(int32_t), rs::Nccl::kChar, 0, comm, q->stream));
-            NCCL_TRY(p, nc->Broadcast(q->d_pos.ptr, q->d_pos.ptr, rays * sizeof(int32_t), rs::Nccl::kChar, 0, comm, q->stream));
-        }
-        if (p->nq)
-            NCCL_TRY(p, nc->Broadcast(q->d_rec.ptr, q->d_rec.ptr, p->nq * 16 * sizeof(double), rs::Nccl::kChar, 0, comm, q->stream));
+        if (!q->repl_stream) CUDA_TRY(p, cudaStreamCreateWithFlags(&q->repl_stream, cudaStreamNonBlocking));
     }
-    NCCL_TRY(p, nc->GroupEnd());
+    // the primary's sending stream follows what its own stream holds (spline records, frames set one by one)
+    if (int rc = rssync_stream_wait_chunk(p, -1, p->repl_stream)) return rc;
+    auto broadcast = [&](const Piece* pc) -> int {  // pc == nullptr: the spline records
+        NCCL_TRY(p, nc->GroupStart());
+        for (int i = 0; i < n_ranks(p); ++i) {
+            rssync_problem* q = rank_problem(p, i);
+            cudaSetDevice(q->device);
+            void* comm = p->comms[(size_t)i];
+            if (!pc) {
+                NCCL_TRY(p, nc->Broadcast(q->d_rec.ptr, q->d_rec.ptr, p->nq * 16 * sizeof(double), rs::Nccl::kChar, 0, comm, q->repl_stream));
+                continue;
+            }
+            const size_t lo = pc->lo, n = pc->hi - pc->lo;
+            NCCL_TRY(p, nc->Broadcast(q->d_rays.ptr + lo * 8, q->d_rays.ptr + lo * 8, n * 8 * sizeof(double), rs::Nccl::kChar, 0, comm, q->repl_stream));
+            NCCL_TRY(p, nc->Broadcast(q->d_orig.ptr + lo, q->d_orig.ptr + lo, n * sizeof(int32_t), rs::Nccl::kChar, 0, comm, q->repl_stream));
+            NCCL_TRY(p, nc->Broadcast(q->d_pos.ptr + lo, q->d_pos.ptr + lo, n * sizeof(int32_t), rs::Nccl::kChar, 0, comm, q->repl_stream));
+        }
+        NCCL_TRY(p, nc->GroupEnd());
+        p->nccl_calls += 1;
+        for (rssync_problem* r : p->replicas)
+            if (int rc = rssync_expect_chunk(r, pc ? pc->lo : 0, pc ? pc->hi : rays, r->repl_stream)) {
+                p->err = r->err;
+                return rc;
+            }
+        return RSSYNC_OK;
+    };
+    if (p->nq)
+        if (int rc = broadcast(nullptr)) return rc;  // every frame waits at least for the records
+    for (const Piece& pc : pieces) {
+        if (pc.k_last >= 0)
+            if (int rc = rssync_stream_wait_chunk(p, pc.k_last, p->repl_stream)) return rc;
+        if (int rc = broadcast(&pc)) return rc;
+    }
+    if (int rc = rssync_note_reader(p, p->repl_stream)) return rc;  // the next Set* call waits for these sends
     for (rssync_problem* r : p->replicas) r->synced_version = p->version;
-    p->nccl_calls += 1;
-    p->broadcast_bytes += rays * (8 * sizeof(double) + 2 * sizeof(int32_t)) + p->nq * 16 * sizeof(double);
+    p->broadcast_bytes += p->nq * 16 * sizeof(double);
+    for (const Piece& pc : pieces) p->broadcast_bytes += (pc.hi - pc.lo) * (8 * sizeof(double) + 2 * sizeof(int32_t));
     return RSSYNC_OK;
 }
 
@@ -1067,11 +1155,9 @@ int grid_enqueue_rank(rssync_problem* q, const std::vector<FrameDesc>& sel, int 
     CUDA_TRY(q, q->d_framecost.reserve((size_t)F * cnt));
     if (int rc = h2d(q, q->d_frames.ptr, sel.data(), sizeof(FrameDesc) * F)) return rc;
     if (int rc = h2d(q, q->d_delays.ptr, delays, sizeof(double) * cnt)) return rc;
-    if (timed) CUDA_TRY(q, cudaEventRecord(q->ev0, q->stream));
-    rs::launch_presync_tasks(q->device_data(), q->d_frames.ptr, F, max_n, q->d_delays.ptr, cnt, q->seed, stream_id,
-                             call_no, idx_base, q->d_framecost.ptr, F, d_flags_dst, q->stream, nullptr, max_chunk,
-                             q->simplified);
-    if (timed) CUDA_TRY(q, cudaEventRecord(q->ev1, q->stream));
+    if (int rc = enqueue_grid_kernels(q, sel, max_n, cnt, stream_id, call_no, idx_base, d_flags_dst, max_chunk, timed,
+                                      nullptr, nullptr))
+        return rc;
     rs::launch_presync_reduce(q->d_framecost.ptr, F, cnt, d_costs_dst, q->stream);
     CUDA_TRY(q, cudaGetLastError());
     return RSSYNC_OK;
@@ -1094,6 +1180,17 @@ int multi_presync_grid(rssync_problem* p, int64_t fb, int64_t fe, const double* 
     }
     if ((long long)F * n > (1LL << 34)) { p->err = "pre-sync: grid too large"; return RSSYNC_E_INVALID; }
     if (int rc = multi_replicate(p)) return rc;
+    static const bool dbg_sync = std::getenv("RSSYNC_DEBUG_MULTI") != nullptr;
+    auto dbg_check = [&](const char* what) {
+        if (!dbg_sync) return;
+        for (int i = 0; i < n_ranks(p); ++i) {
+            cudaSetDevice(rank_problem(p, i)->device);
+            const cudaError_t e = cudaDeviceSynchronize();
+            std::fprintf(stderr, "[multi] %s: device %d: %s (in flight %zu)\n", what, rank_problem(p, i)->device,
+                         cudaGetErrorString(e), rank_problem(p, i)->in_flight.size());
+        }
+    };
+    dbg_check("after replicate");
     double span = 0.0;
     for (const FrameDesc& fd : sel) span = std::max(span, fd.ts_hi - fd.ts_lo);
     const int max_chunk = rs::presync_max_chunk(delays, n, span, p->sr, max_n);
@@ -1114,6 +1211,7 @@ int multi_presync_grid(rssync_problem* p, int64_t fb, int64_t fe, const double* 
                                          reinterpret_cast<unsigned*>(mine + (size_t)per * sizeof(double)),
                                          i == 0 && p->kernel_timing);
         if (rc) { if (q != p) p->err = q->err; return rc; }
+        dbg_check("after a rank's grid");
     }
     // the one exchange of the call: every rank's slice {costs, flags} to every rank, in place
     NCCL_TRY(p, nc->GroupStart());
@@ -1290,6 +1388,12 @@ void rssync_destroy(rssync_problem* p) {
         int prev = 0;
         cudaGetDevice(&prev);
         const rs::Nccl* nc = rs::Nccl::get();
+        for (size_t i = 0; i <= p->replicas.size(); ++i) {  // no collective still queued when the communicators go
+            rssync_problem* q = i == 0 ? p : p->replicas[i - 1];
+            cudaSetDevice(q->device);
+            if (q->repl_stream) cudaStreamSynchronize(q->repl_stream);
+            cudaStreamSynchronize(q->stream);
+        }
         for (size_t i = 0; i < p->comms.size(); ++i)
             if (nc && p->comms[i]) {
                 cudaSetDevice(i == 0 ? p->device : p->replicas[i - 1]->device);
@@ -1304,7 +1408,9 @@ void rssync_destroy(rssync_problem* p) {
     join_gyro(p);
     if (p->arena_copy_pending) cudaEventSynchronize(p->ev_arena);
     if (p->ev_arena) cudaEventDestroy(p->ev_arena);
+    if (p->ev_reader) cudaEventDestroy(p->ev_reader);
     if (p->copy_stream) { cudaStreamSynchronize(p->copy_stream); cudaStreamDestroy(p->copy_stream); }
+    if (p->repl_stream) { cudaStreamSynchronize(p->repl_stream); cudaStreamDestroy(p->repl_stream); }
     for (const auto& fl : p->in_flight) cudaEventDestroy(fl.ev);
     for (cudaEvent_t e : p->ev_pool) cudaEventDestroy(e);
     if (p->ev_order) cudaEventDestroy(p->ev_order);
@@ -1348,6 +1454,7 @@ int rssync_set_gyro_fixed(rssync_problem* p, const double* quats, size_t count, 
     p->sr = sample_rate;       // core_private.cpp:137
     p->q0 = first_timestamp;   // :138
     cudaSetDevice(p->device);
+    if (int rc = wait_reader(p)) return rc;
     if (p->gyro_dirty == false && p->nq) CUDA_TRY(p, cudaStreamSynchronize(p->stream));  // records in flight
     if (p->gyro_stream) CUDA_TRY(p, cudaStreamSynchronize(p->gyro_stream));  // a copy never waited for
     CUDA_TRY(p, p->h_gyro.reserve(count * 9));
@@ -1368,6 +1475,7 @@ int rssync_set_gyro_var(rssync_problem* p, const int64_t* ts, const double* quat
     if (count > (size_t)INT32_MAX) { p->err = "set-gyro-quaternions: too many samples"; return RSSYNC_E_INVALID; }
     join_gyro(p);
     cudaSetDevice(p->device);
+    if (int rc = wait_reader(p)) return rc;
     if (p->gyro_dirty == false && p->nq) CUDA_TRY(p, cudaStreamSynchronize(p->stream));
     if (!p->gyro_stream) CUDA_TRY(p, cudaStreamCreateWithFlags(&p->gyro_stream, cudaStreamNonBlocking));
     if (!p->ev_gyro) CUDA_TRY(p, cudaEventCreateWithFlags(&p->ev_gyro, cudaEventDisableTiming));
@@ -2389,6 +2497,65 @@ int rssync_device_state(rssync_problem* p, rssync_device_state_t* out) {
     out->gyro_samples = p->nq;
     out->sample_rate = p->sr;
     out->first_timestamp = p->q0;
+    return RSSYNC_OK;
+}
+
+int rssync_device_state_pipelined(rssync_problem* p, rssync_device_state_t* out, size_t* chunk_lo, size_t* chunk_hi,
+                                  size_t cap, size_t* n_chunks) {
+    if (!p || !out || !n_chunks || (cap && (!chunk_lo || !chunk_hi))) return RSSYNC_E_INVALID;
+    if (int rc = flush(p, /*keep_in_flight=*/true)) return rc;  // no host synchronisation with the device
+    out->rays = p->d_rays.ptr;
+    out->orig = p->d_orig.ptr;
+    out->pos = p->d_pos.ptr;
+    out->spline_records = p->d_rec.ptr;
+    out->arena_rays = p->dev_used;
+    out->gyro_samples = p->nq;
+    out->sample_rate = p->sr;
+    out->first_timestamp = p->q0;
+    *n_chunks = p->in_flight.size();
+    for (size_t k = 0; k < p->in_flight.size() && k < cap; ++k) {
+        chunk_lo[k] = p->in_flight[k].lo;
+        chunk_hi[k] = p->in_flight[k].hi;
+    }
+    return RSSYNC_OK;
+}
+
+int rssync_stream_wait_chunk(rssync_problem* p, int k, void* stream) {
+    if (!p) return RSSYNC_E_INVALID;
+    CUDA_TRY(p, cudaSetDevice(p->device));
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    if (k < 0) {  // whatever the problem's stream holds now (spline records, frames set one by one)
+        if (!p->ev_order) CUDA_TRY(p, cudaEventCreateWithFlags(&p->ev_order, cudaEventDisableTiming));
+        CUDA_TRY(p, cudaEventRecord(p->ev_order, p->stream));
+        CUDA_TRY(p, cudaStreamWaitEvent(st, p->ev_order, 0));
+        return RSSYNC_OK;
+    }
+    if ((size_t)k >= p->in_flight.size()) { p->err = "stream-wait-chunk: no such chunk in flight"; return RSSYNC_E_INVALID; }
+    CUDA_TRY(p, cudaStreamWaitEvent(st, p->in_flight[(size_t)k].ev, 0));
+    return RSSYNC_OK;
+}
+
+int rssync_expect_chunk(rssync_problem* p, size_t lo, size_t hi, void* stream) {
+    if (!p || lo > hi) return RSSYNC_E_INVALID;
+    CUDA_TRY(p, cudaSetDevice(p->device));
+    rssync_problem::InFlight fl{lo, hi, nullptr};
+    if (p->ev_pool.empty()) {
+        CUDA_TRY(p, cudaEventCreateWithFlags(&fl.ev, cudaEventDisableTiming));
+    } else {
+        fl.ev = p->ev_pool.back();
+        p->ev_pool.pop_back();
+    }
+    CUDA_TRY(p, cudaEventRecord(fl.ev, static_cast<cudaStream_t>(stream)));
+    p->in_flight.push_back(fl);
+    return RSSYNC_OK;
+}
+
+int rssync_note_reader(rssync_problem* p, void* stream) {
+    if (!p) return RSSYNC_E_INVALID;
+    CUDA_TRY(p, cudaSetDevice(p->device));
+    if (!p->ev_reader) CUDA_TRY(p, cudaEventCreateWithFlags(&p->ev_reader, cudaEventDisableTiming));
+    CUDA_TRY(p, cudaEventRecord(p->ev_reader, static_cast<cudaStream_t>(stream)));
+    p->reader_pending = true;
     return RSSYNC_OK;
 }
 

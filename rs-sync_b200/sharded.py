@@ -151,7 +151,10 @@ def device_buffers(problem):
     bufs = {}
     for k in ("rays", "orig", "pos", "spline_records"):
         ptr, nbytes = st[k]
-        bufs[k] = torch.as_tensor(_DevicePtr(ptr, nbytes), device="cuda") if nbytes else None
+        t = _wrapped.get((didx, k))
+        if nbytes and (t is None or t.data_ptr() != ptr or t.numel() != nbytes):
+            t = _wrapped[(didx, k)] = torch.as_tensor(_DevicePtr(ptr, nbytes), device="cuda")
+        bufs[k] = t if nbytes else None
     return bufs, st
 
 
@@ -159,31 +162,82 @@ _FT_DTYPE = np.dtype([("id", "<i8"), ("off", "<i4"), ("n", "<i4"), ("ts_lo", "<f
 _last_table = {}  # id(problem) -> bytes of the frame table it holds / last sent
 
 
-def replicate_state(problem, *, rank, world, device, src=0):
+_side_streams = {}  # device index -> the stream the replication's collectives are issued on
+_wrapped = {}       # (device index, buffer name) -> torch view of the engine's buffer (re-made when it moves)
+
+
+def _merge_chunks(chunks, groups, arena=None, max_pieces=16):
+    """in-flight chunks [(lo, hi), ...] (stream order) -> the pieces [(k_last, lo, hi)] to send:
+    consecutive chunks go together, at most `groups` pieces, each once the last of its chunks has
+    landed (k_last).  With `arena` given, the parts of [0, arena) that no chunk in flight covers come
+    first, with k_last = -1: they are already on the device (an ingest that had to grow the arena has
+    waited for its first chunks; frames set one by one are uploaded by the flush)."""
+    n = len(chunks)
+    out = []
+    if arena is not None:
+        at = 0
+        for lo, hi in sorted(chunks):
+            if lo > at:
+                out.append((-1, at, lo))
+            at = max(at, hi)
+        if arena > at:
+            out.append((-1, at, arena))
+    g_n = min(groups, n)
+    for g in range(g_n):
+        a, b = n * g // g_n, n * (g + 1) // g_n
+        out.append((b - 1, min(c[0] for c in chunks[a:b]), max(c[1] for c in chunks[a:b])))
+    if len(out) > max_pieces:  # scattered updates: one piece behind the last chunk
+        return [(n - 1, 0, arena)]
+    return out
+
+
+def replicate_state(problem, *, rank, world, device, src=0, groups=2):
     """Inputs ingested on rank `src` only: its finished device state goes to every other rank's
     problem over NVLink (NCCL broadcasts straight into the engines' own allocations -- no staging
     copy), instead of every rank validating, staging and uploading the same host data.  Afterwards
-    all ranks compute identical results.  Per call: one 48-byte header, the frame table only when it
-    changed since the last call, and the four device buffers; the only host synchronisation is the
-    receivers' read of the header."""
+    all ranks compute identical results.
+
+    Pipelined behind the source's ingest: a bulk SetTrackResult is still on its way to the source's
+    device, chunk by chunk, when this is called; each group of chunks is broadcast as soon as it
+    has landed (on a side stream, so that neither the source's nor the receivers' own stream waits
+    for the whole upload), and the receivers' engines are told which arena ranges are still coming
+    (expect_chunk), so the PreSync grid that follows starts on the first frames while the last are
+    on the bus -- on every rank, as it does on the source.  Per call: one header, the frame table
+    only when it changed since the last call, the spline records, three broadcasts per group (two
+    groups: the grid, not the bus, is what the receivers wait for, and every collective costs host
+    time on both sides); the only host synchronisation is the receivers' read of the header."""
     import torch
     import torch.distributed as dist
     if world == 1:
         return
     key = id(problem)
+    didx = torch.device(device).index or 0
+    side = _side_streams.get(didx)
+    if side is None:
+        side = _side_streams[didx] = torch.cuda.Stream(device=device)
+    max_groups = 16
     if rank == src:
         ft = problem.frame_table()
         raw = ft.tobytes()
         changed = _last_table.get(key) != raw
-        bufs, st = device_buffers(problem)
-        head = torch.tensor([ft.shape[0], st["arena_rays"], st["gyro_samples"], st["sample_rate"],
-                             st["first_timestamp"], 1.0 if changed else 0.0], dtype=torch.float64, device=device)
+        st = problem.device_state_pipelined()
+        chunks = st["chunks"] or []
+        pieces = _merge_chunks(chunks, groups, st["arena_rays"], max_groups)
+        head = [ft.shape[0], st["arena_rays"], st["gyro_samples"], st["sample_rate"], st["first_timestamp"],
+                1.0 if changed else 0.0, len(pieces)]
+        for _, lo, hi in pieces:
+            head += [lo, hi]
+        head += [0.0] * (7 + 2 * max_groups - len(head))
+        head = torch.tensor(head, dtype=torch.float64, device=device)
     else:
-        head = torch.empty(6, dtype=torch.float64, device=device)
+        head = torch.empty(7 + 2 * max_groups, dtype=torch.float64, device=device)
     dist.broadcast(head, src)
     if rank != src:
         h = head.cpu().tolist()
         nf, arena, nq, changed = int(h[0]), int(h[1]), int(h[2]), h[5] != 0.0
+        pieces = [(None, int(h[7 + 2 * g]), int(h[8 + 2 * g])) for g in range(int(h[6]))]
+    else:
+        arena = st["arena_rays"]
     if changed:
         if rank == src:
             ftt = torch.from_numpy(np.frombuffer(raw, dtype=np.uint8).copy()).to(device)
@@ -197,7 +251,30 @@ def replicate_state(problem, *, rank, world, device, src=0):
     if rank != src:
         table = np.frombuffer(_last_table[key], dtype=_FT_DTYPE)
         problem.adopt_state(table, arena, nq, h[3], h[4])
-        bufs, _ = device_buffers(problem)
+        st = problem.device_state()
+    bufs = {}
     for k in ("rays", "orig", "pos", "spline_records"):
-        if bufs[k] is not None:
-            dist.broadcast(bufs[k], src)  # enqueued behind the ingest; later work on this stream waits for it
+        ptr, nbytes = st[k]
+        bufs[k] = torch.as_tensor(_DevicePtr(ptr, nbytes), device="cuda") if nbytes else None
+    handle = side.cuda_stream
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):
+        if rank == src:
+            problem.stream_wait_chunk(-1, handle)
+        if bufs["spline_records"] is not None:
+            dist.broadcast(bufs["spline_records"], src)
+        if rank != src:
+            problem.expect_chunk(0, arena, handle)  # every frame waits at least for the records
+        for k_last, lo, hi in pieces:
+            if hi <= lo:
+                continue
+            if rank == src and k_last is not None and k_last >= 0:
+                problem.stream_wait_chunk(k_last, handle)
+            works = [dist.broadcast(bufs[name][lo * width:hi * width], src, async_op=True)
+                     for name, width in (("rays", 64), ("orig", 4), ("pos", 4)) if bufs[name] is not None]
+            if works:
+                works[-1].wait()  # the side stream follows the collectives' stream (in order: the last covers all)
+            if rank != src:
+                problem.expect_chunk(lo, hi, handle)
+        if rank == src:
+            problem.note_reader(handle)  # the next Set* call waits for these sends

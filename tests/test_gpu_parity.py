@@ -610,6 +610,61 @@ def test_adopted_device_state_reproduces_the_source(rsb, w_small):
     assert b.stats()["frames"] == w.n_frames + 1
 
 
+def test_pipelined_replication_behind_a_bulk_ingest(rsb, w_small, synth_mod):
+    """the pipelined form (sharded.replicate_state across ranks): the source has just taken a bulk
+    SetTrackResult whose chunks are still in flight; each chunk is copied on, on a side stream, as soon
+    as it has landed, and the adopting problem's grid starts behind the chunks it was told to expect"""
+    import importlib
+    import torch
+    sharded = importlib.import_module("rs-sync_b200.sharded")
+    w = w_small
+    counts = np.full(w.n_frames, w.n_rays)
+    fb, fe = int(w.frame_ids[0]), int(w.frame_ids[-1]) + 1
+    delays = np.linspace(-0.05, 0.05, 21)
+    a = rsb.SyncProblem(seed=100).load(w, bulk=True)
+    want = a.presync_grid(fb, fe, delays, call_no=2)
+    b = rsb.SyncProblem(seed=100)
+    side = torch.cuda.Stream()
+    w2 = synth_mod.make_workload("small", seed=9)
+    fresh = rsb.SyncProblem(seed=100)  # its first ingest, into an arena that grows on the way
+    for rep, (a, ww) in enumerate(((a, w), (a, w2), (a, w), (fresh, w))):
+        a.SetGyroQuaternions(ww.quats, ww.quats.shape[0], ww.gyro_rate, ww.gyro_t0)
+        a.set_track_batch(ww.frame_ids, counts, ww.ts_a, ww.ts_b, ww.rays_a, ww.rays_b)
+        st = a.device_state_pipelined()
+        chunks = st["chunks"]
+        assert chunks and all(lo < hi <= st["arena_rays"] for lo, hi in chunks)
+        b.adopt_state(a.frame_table(), st["arena_rays"], st["gyro_samples"], st["sample_rate"], st["first_timestamp"])
+        dst, _ = sharded.device_buffers(b)
+        src = {k: torch.as_tensor(sharded._DevicePtr(*st[k]), device="cuda") for k in ("rays", "orig", "pos", "spline_records")}
+        skip = 3 if rep == 2 else 0
+        if skip:  # as if the first chunks were no longer in flight (an ingest that had to wait for them)
+            torch.cuda.synchronize()
+        pieces = [(k if k < 0 else k + skip, lo, hi)
+                  for k, lo, hi in sharded._merge_chunks(chunks[skip:], 3, st["arena_rays"])]
+        assert pieces[-1][0] == len(chunks) - 1 and (pieces[0][0] == -1) == bool(skip)
+        covered = np.zeros(st["arena_rays"], dtype=bool)  # every ray of the arena is in some piece
+        for _, lo, hi in pieces:
+            covered[lo:hi] = True
+        assert covered.all()
+        with torch.cuda.stream(side):
+            a.stream_wait_chunk(-1, side.cuda_stream)
+            dst["spline_records"].copy_(src["spline_records"], non_blocking=True)
+            b.expect_chunk(0, st["arena_rays"], side.cuda_stream)
+            for k_last, lo, hi in pieces:
+                if k_last >= 0:
+                    a.stream_wait_chunk(k_last, side.cuda_stream)
+                for name, width in (("rays", 64), ("orig", 4), ("pos", 4)):
+                    dst[name][lo * width:hi * width].copy_(src[name][lo * width:hi * width], non_blocking=True)
+                b.expect_chunk(lo, hi, side.cuda_stream)
+            a.note_reader(side.cuda_stream)
+        ga = a.presync_grid(fb, fe, delays, call_no=2)
+        gb = b.presync_grid(fb, fe, delays, call_no=2)
+        assert np.array_equal(ga, gb)
+        assert np.array_equal(ga, want) == (rep != 1)
+    with pytest.raises(rsb.RsSyncError):
+        a.stream_wait_chunk(99, side.cuda_stream)
+
+
 def test_simplified_loss_mode_matches_oracle(rsb, oracle_loader, w_small):
     """the thesis' simplified (no-translation) loss mode (rssync_set_loss_mode): PreSync curve, argmin
     and the whole Sync trajectory equal the oracle's; switching back restores the reference's loss"""

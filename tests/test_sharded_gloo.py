@@ -94,3 +94,23 @@ def test_shard_range_partitions():
             parts = [sharded.shard_range(n, r, world) for r in range(world)]
             assert parts[0][0] == 0 and parts[-1][1] == n
             assert all(parts[i][1] == parts[i + 1][0] for i in range(world - 1))
+
+
+def test_replication_pieces_cover_the_arena():
+    """sharded._merge_chunks: the pieces of a pipelined replication cover every ray of the arena once
+    the chunks still in flight are grouped; what no chunk covers goes first (already on the device)"""
+    import importlib
+    sh = importlib.import_module("rs-sync_b200.sharded")
+    assert sh._merge_chunks([], 4, 100) == [(-1, 0, 100)]
+    assert sh._merge_chunks([], 4, 0) == []
+    assert sh._merge_chunks([(0, 25), (25, 50), (50, 75), (75, 100)], 4, 100) == [(0, 0, 25), (1, 25, 50), (2, 50, 75), (3, 75, 100)]
+    assert sh._merge_chunks([(60, 70), (70, 80), (80, 100)], 2, 100) == [(-1, 0, 60), (0, 60, 70), (2, 70, 100)]
+    assert sh._merge_chunks([(10, 20), (40, 50)], 4, 100) == [(-1, 0, 10), (-1, 20, 40), (-1, 50, 100), (0, 10, 20), (1, 40, 50)]
+    assert sh._merge_chunks([(i, i + 1) for i in range(0, 60, 2)], 4, 100) == [(29, 0, 100)]  # scattered: one piece, last
+    for chunks in ([(0, 8), (8, 16), (16, 24), (24, 32), (32, 40)], [(32, 40), (0, 8)], [(5, 9)]):
+        covered = [0] * 40
+        for k, lo, hi in sh._merge_chunks(chunks, 3, 40):
+            assert -1 <= k < len(chunks)
+            for i in range(lo, hi):
+                covered[i] += 1
+        assert min(covered) >= 1
