@@ -581,12 +581,14 @@ def bench_in_library_multi(pkg, w, delays, fb, fe, single, n_dev, steps):
     same = bool(np.array_equal(curve, single.presync_grid(fb, fe, delays, stream=pkg.STREAM_DEBUG, call_no=3000 + steps - 1)))
     # end to end: the inputs enter the primary, are replicated by the library (ncclBroadcast), the grid runs
     counts = np.full(w.n_frames, w.n_rays)
-    t0 = time.perf_counter()
-    for i in range(3):
+    for i in range(-1, 3):  # one untimed pass first (the broadcast channels are set up on first use)
+        if i == 0:
+            t0 = time.perf_counter()
         mp.SetGyroQuaternions(w.quats, w.quats.shape[0], w.gyro_rate, w.gyro_t0)
         mp.set_track_batch(w.frame_ids, counts, w.ts_a, w.ts_b, w.rays_a, w.rays_b)
-        mp.presync_grid(fb, fe, delays, stream=pkg.STREAM_DEBUG, call_no=4000 + i)
+        e2e_curve = mp.presync_grid(fb, fe, delays, stream=pkg.STREAM_DEBUG, call_no=3000 + steps - 1)
     e2e = (time.perf_counter() - t0) / 3
+    same = same and bool(np.array_equal(e2e_curve, curve))  # the pipelined replication delivers the same state
     st = mp.stats()
     cells = len(delays) * w.n_frames * w.n_rays
     res = {"devices": mp.device_count(), "ms_per_step": dt * 1e3, "value": cells / dt, "unit": UNIT,

@@ -27,6 +27,8 @@
 #define RSSYNC_STAGE_DEFAULT 2  // staging copy: 0 scalar, 1 AVX2, 2 AVX2 with non-temporal stores
 #endif
 
+#include <nvtx3/nvToolsExt.h>  // header-only; a no-op unless a profiler is attached
+
 #include "engine.h"
 #include "host_ingest.h"
 #include "nccl_dyn.h"
@@ -94,7 +96,7 @@ struct PinBuf {
         T* np = nullptr;
         cudaError_t e = cudaHostAlloc((void**)&np, want * sizeof(T), cudaHostAllocDefault);
         if (e != cudaSuccess) return e;
-        if (ptr && keep) std::memcpy(np, ptr, keep * sizeof(T));
+        if (ptr && keep) std::memcpy(np, ptr, std::min(keep, cap) * sizeof(T));
         if (ptr) cudaFreeHost(ptr);
         ptr = np;
         cap = want;
@@ -108,6 +110,15 @@ struct PinBuf {
 };
 
 // RSSYNC_DEBUG_TIMING=1: wall-clock marks of the host-side ingest on stderr
+// NVTX range around a C-ABI call: the calls show up by name on a profiler's timeline
+struct NvtxRange {
+    explicit NvtxRange(const char* name) { nvtxRangePushA(name); }
+    ~NvtxRange() { nvtxRangePop(); }
+    NvtxRange(const NvtxRange&) = delete;
+    NvtxRange& operator=(const NvtxRange&) = delete;
+};
+#define RS_NVTX_RANGE() NvtxRange nvtx_range_(__func__)
+
 struct DebugTimer {
     bool on;
     std::chrono::steady_clock::time_point t0;
@@ -1038,6 +1049,7 @@ inline rssync_problem* rank_problem(rssync_problem* p, int i) { return i == 0 ? 
 
 // bring every replica up to the primary's inputs
 int multi_replicate(rssync_problem* p) {
+    RS_NVTX_RANGE();
     bool stale = false;
     for (const rssync_problem* r : p->replicas) stale = stale || r->synced_version != p->version;
     if (!stale) return RSSYNC_OK;
@@ -1446,6 +1458,7 @@ const char* rssync_last_error(const rssync_problem* p) { return p ? p->err.c_str
 
 int rssync_set_gyro_fixed(rssync_problem* p, const double* quats, size_t count, double sample_rate,
                           double first_timestamp) {
+    RS_NVTX_RANGE();
     if (!p || !quats) return RSSYNC_E_INVALID;
     if (count < 2) { p->err = "set-gyro-quaternions: need at least 2 samples"; return RSSYNC_E_INVALID; }
     if (count > (size_t)INT32_MAX) { p->err = "set-gyro-quaternions: too many samples"; return RSSYNC_E_INVALID; }
@@ -1466,6 +1479,7 @@ int rssync_set_gyro_fixed(rssync_problem* p, const double* quats, size_t count, 
 }
 
 int rssync_set_gyro_var(rssync_problem* p, const int64_t* ts, const double* quats, size_t count) {
+    RS_NVTX_RANGE();
     if (!p || !ts || !quats) return RSSYNC_E_INVALID;
     rs::ResamplePlan plan;
     const rs::IngestStatus s = rs::plan_variable_rate(ts, count, plan, p->err);  // core_private.cpp:146-164
@@ -1629,7 +1643,9 @@ int stage_track(const double* ts_a, const double* ts_b, const double* rays_a, co
 }
 
 // stage 2 (serial bookkeeping): where the frame lives in the arena
-int place_track(rssync_problem* p, int64_t frame, size_t count, FrameDesc** fd_out) {
+// host_mirror: the frame is filled on the host (frames set one by one, small batches) and needs its
+// range of the pinned mirror of the arena; a bulk ingest goes through its own staging buffer instead
+int place_track(rssync_problem* p, int64_t frame, size_t count, FrameDesc** fd_out, bool host_mirror = true) {
     const size_t padded = (count + 31) / 32 * 32;
     size_t off;
     auto it = p->frames.end();
@@ -1652,15 +1668,14 @@ int place_track(rssync_problem* p, int64_t frame, size_t count, FrameDesc** fd_o
         }
         off = p->used;
         if (off + padded > (size_t)INT32_MAX) { p->err = "set-track-result: ray arena full"; return RSSYNC_E_INVALID; }
-        const size_t need = off + padded;
-        if (need > p->h_orig.cap) {
-            const size_t want = std::max<size_t>(need, std::max<size_t>(p->h_orig.cap * 2, 1u << 16));
-            cudaSetDevice(p->device);
-            CUDA_TRY(p, p->h_rays.reserve(want * 8, p->used * 8));
-            CUDA_TRY(p, p->h_orig.reserve(want, p->used));
-            CUDA_TRY(p, p->h_pos.reserve(want, p->used));
-        }
-        p->used = need;
+        p->used = off + padded;
+    }
+    if (host_mirror && off + padded > p->h_orig.cap) {  // (also a frame replaced in place that came in bulk)
+        const size_t want = std::max<size_t>(std::max(off + padded, p->used), std::max<size_t>(p->h_orig.cap * 2, 1u << 16));
+        cudaSetDevice(p->device);
+        CUDA_TRY(p, p->h_rays.reserve(want * 8, p->used * 8));
+        CUDA_TRY(p, p->h_orig.reserve(want, p->used));
+        CUDA_TRY(p, p->h_pos.reserve(want, p->used));
     }
     if (it == p->frames.end()) it = p->frames.emplace_hint(pos, frame, FrameDesc{});
     FrameDesc& fd = it->second;  // map nodes are stable: fill_track completes ts_lo / ts_hi
@@ -1859,6 +1874,7 @@ int rssync_set_track(rssync_problem* p, int64_t frame, const double* ts_a, const
 int rssync_set_track_batch(rssync_problem* p, size_t n_frames, const int64_t* frames,
                            const size_t* counts, const double* ts_a, const double* ts_b,
                            const double* rays_a, const double* rays_b) {
+    RS_NVTX_RANGE();
     if (!p || (n_frames && (!frames || !counts))) return RSSYNC_E_INVALID;
     p->version++;
     DebugTimer tm("set_track_batch");
@@ -1902,10 +1918,21 @@ int rssync_set_track_batch(rssync_problem* p, size_t n_frames, const int64_t* fr
         CUDA_TRY(p, p->d_stage.reserve(stage_doubles));
         if (!p->ev_arena) CUDA_TRY(p, cudaEventCreateWithFlags(&p->ev_arena, cudaEventDisableTiming));
         std::vector<double> lo_ts(n_frames), hi_ts(n_frames);
-        // room for the whole batch appended at the end of the arena (the most it can take)
-        size_t padded_total = 0;
-        for (size_t i = 0; i < n_frames; ++i) padded_total += (counts[i] + 31) / 32 * 32;
-        if (int r = reserve_device_arena(p, p->used + padded_total)) return r;
+        // room for what this batch appends at the end of the arena: every frame that is new or changes
+        // its padded size (the others are replaced in place) -- reserved up front, because growing
+        // the arena moves it, which has to wait for the chunks already in flight
+        size_t padded_new = 0;
+        {
+            auto it = p->frames.begin();
+            for (size_t i = 0; i < n_frames; ++i) {
+                const size_t padded = (counts[i] + 31) / 32 * 32;
+                if (it == p->frames.end() || it->first != frames[i]) it = p->frames.find(frames[i]);
+                const bool in_place = it != p->frames.end() && (size_t)((it->second.n + 31) / 32 * 32) == padded;
+                if (!in_place) padded_new += padded;
+                if (it != p->frames.end()) ++it;  // batches mostly come in frame order
+            }
+        }
+        if (int r = reserve_device_arena(p, p->used + padded_new)) return r;
         tm.mark("reserve");
         double* hs = p->h_stage.ptr;
         double* ds = p->d_stage.ptr;
@@ -1938,7 +1965,7 @@ int rssync_set_track_batch(rssync_problem* p, size_t n_frames, const int64_t* fr
             rs::PixelFrame* pf = reinterpret_cast<rs::PixelFrame*>(h_rec);
             for (size_t i = lo; i < end; ++i) {
                 FrameDesc* fd = nullptr;
-                if (int r = place_track(p, frames[i], counts[i], &fd)) return r;
+                if (int r = place_track(p, frames[i], counts[i], &fd, /*host_mirror=*/false)) return r;
                 fd->ts_lo = lo_ts[i];
                 fd->ts_hi = hi_ts[i];
                 pf[i - lo] = rs::PixelFrame{fd->off, fd->n, (int64_t)(at[i] - a0), 0.0, 0.0};
@@ -2002,6 +2029,7 @@ extern "C" {
 int rssync_set_track_pixels(rssync_problem* p, size_t n_frames, const int64_t* frames, const size_t* counts,
                             const double* frame_ts_a, const double* frame_ts_b, const double* points_a,
                             const double* points_b, const rssync_lens* lens, double image_rows) {
+    RS_NVTX_RANGE();
     if (!p) return RSSYNC_E_INVALID;
     if (n_frames == 0) return RSSYNC_OK;
     if (!frames || !counts || !frame_ts_a || !frame_ts_b || !points_a || !points_b || !lens) return RSSYNC_E_INVALID;
@@ -2057,7 +2085,7 @@ int rssync_set_track_pixels(rssync_problem* p, size_t n_frames, const int64_t* f
     std::vector<rs::PixelFrame> pf(n_frames);
     for (size_t i = 0; i < n_frames; ++i) {
         FrameDesc* fd = nullptr;
-        if (int rc = place_track(p, frames[i], counts[i], &fd)) return rc;
+        if (int rc = place_track(p, frames[i], counts[i], &fd, /*host_mirror=*/false)) return rc;
         fd->ts_lo = lo[i];
         fd->ts_hi = hi[i];
         pf[i] = rs::PixelFrame{fd->off, fd->n, (int64_t)at[i], frame_ts_a[i], frame_ts_b[i]};
@@ -2098,6 +2126,7 @@ int rssync_presync_delays(double initial, double step, double radius, double* ou
 
 int rssync_presync(rssync_problem* p, double initial, int64_t fb, int64_t fe, double step,
                    double radius, double* out_cost, double* out_delay) {
+    RS_NVTX_RANGE();
     if (!p || !out_cost || !out_delay) return RSSYNC_E_INVALID;
     if (!(step > 0) || !std::isfinite(radius) || !std::isfinite(initial)) {
         p->err = "pre-sync: search_step must be > 0 and the search window finite";
@@ -2132,6 +2161,7 @@ int rssync_presync(rssync_problem* p, double initial, int64_t fb, int64_t fe, do
 int rssync_presync_windows(rssync_problem* p, int n, double initial, const int64_t* fb, const int64_t* fe,
                            double step, double radius, const uint64_t* call_nos, double* out_cost,
                            double* out_delay) {
+    RS_NVTX_RANGE();
     if (!p || n < 0) return RSSYNC_E_INVALID;
     if (n == 0) return RSSYNC_OK;
     if (!fb || !fe || !out_cost || !out_delay) return RSSYNC_E_INVALID;
@@ -2219,6 +2249,7 @@ int rssync_presync_windows(rssync_problem* p, int n, double initial, const int64
 
 int rssync_debug_presync(rssync_problem* p, double initial, int64_t fb, int64_t fe, double radius,
                          double* delays, double* costs, int point_count) {
+    RS_NVTX_RANGE();
     if (!p || (point_count > 0 && (!delays || !costs))) return RSSYNC_E_INVALID;
     if (point_count <= 0) return RSSYNC_OK;
     for (int i = 0; i < point_count; ++i)
@@ -2230,6 +2261,7 @@ int rssync_debug_presync(rssync_problem* p, double initial, int64_t fb, int64_t 
 int rssync_presync_grid(rssync_problem* p, int64_t fb, int64_t fe, const double* delays, int n,
                         int stream, uint64_t call_no, uint64_t idx_base, double* costs,
                         unsigned* nonfinite_flags) {
+    RS_NVTX_RANGE();
     if (!p || (n > 0 && (!delays || !costs))) return RSSYNC_E_INVALID;
     return presync_grid_impl(p, fb, fe, delays, n, (uint64_t)stream, call_no, idx_base, costs, nonfinite_flags);
 }
@@ -2257,6 +2289,7 @@ int rssync_orientation_search_ex(rssync_problem* p, const double* timestamps_s, 
                                  size_t count, const char* const* orientations, int n_orient,
                                  double initial_delay, int64_t fb, int64_t fe, double step, double radius,
                                  const uint64_t* call_nos, double* out_cost, double* out_delay) {
+    RS_NVTX_RANGE();
     if (!p || n_orient < 0) return RSSYNC_E_INVALID;
     if (n_orient == 0) return RSSYNC_OK;
     if (!timestamps_s || !gyro_xyz || !orientations || !out_cost || !out_delay) return RSSYNC_E_INVALID;
@@ -2410,6 +2443,7 @@ int rssync_orientation_search_ex(rssync_problem* p, const double* timestamps_s, 
 
 int rssync_sync(rssync_problem* p, double initial, int64_t fb, int64_t fe, double center,
                 double radius, double* out_cost, double* out_delay) {
+    RS_NVTX_RANGE();
     if (!p || !out_cost || !out_delay) return RSSYNC_E_INVALID;
     // one syncpoint is one unit of work: it runs on the primary device ("replicas only" at this granularity)
     return sync_batch_impl(p, 1, &initial, &fb, &fe, &center, &radius, out_cost, out_delay, true);
@@ -2427,6 +2461,7 @@ int rssync_sync_batch(rssync_problem* p, int n, const double* initial, const int
 int rssync_sync_batch_ex(rssync_problem* p, int n, const double* initial, const int64_t* fb,
                          const int64_t* fe, const double* center, const double* radius,
                          const uint64_t* call_nos, double* out_cost, double* out_delay) {
+    RS_NVTX_RANGE();
     if (!p || n < 0) return RSSYNC_E_INVALID;
     if (n && (!initial || !fb || !fe || !center || !radius || !out_cost || !out_delay)) return RSSYNC_E_INVALID;
     if (is_multi(p) && n > 1) return multi_sync_batch(p, n, initial, fb, fe, center, radius, out_cost, out_delay, call_nos);
@@ -2466,6 +2501,7 @@ int rssync_set_stream(rssync_problem* p, void* s) {
 }
 
 int rssync_flush(rssync_problem* p) {
+    RS_NVTX_RANGE();
     if (!p) return RSSYNC_E_INVALID;
     if (int rc = flush(p)) return rc;
     CUDA_TRY(p, cudaStreamSynchronize(p->stream));
@@ -2486,6 +2522,7 @@ int rssync_frame_table(const rssync_problem* p, rssync_frame_desc* out, size_t c
 }
 
 int rssync_device_state(rssync_problem* p, rssync_device_state_t* out) {
+    RS_NVTX_RANGE();
     if (!p || !out) return RSSYNC_E_INVALID;
     if (int rc = flush(p)) return rc;
     CUDA_TRY(p, cudaStreamSynchronize(p->stream));
@@ -2561,6 +2598,7 @@ int rssync_note_reader(rssync_problem* p, void* stream) {
 
 int rssync_adopt_state(rssync_problem* p, const rssync_frame_desc* frames, size_t n_frames, size_t arena_rays,
                        size_t gyro_samples, double sample_rate, double first_timestamp) {
+    RS_NVTX_RANGE();
     if (!p || (n_frames && !frames)) return RSSYNC_E_INVALID;
     if (gyro_samples > (size_t)INT32_MAX || arena_rays > (size_t)INT32_MAX) { p->err = "adopt-state: too large"; return RSSYNC_E_INVALID; }
     join_gyro(p);

@@ -151,10 +151,7 @@ def device_buffers(problem):
     bufs = {}
     for k in ("rays", "orig", "pos", "spline_records"):
         ptr, nbytes = st[k]
-        t = _wrapped.get((didx, k))
-        if nbytes and (t is None or t.data_ptr() != ptr or t.numel() != nbytes):
-            t = _wrapped[(didx, k)] = torch.as_tensor(_DevicePtr(ptr, nbytes), device="cuda")
-        bufs[k] = t if nbytes else None
+        bufs[k] = torch.as_tensor(_DevicePtr(ptr, nbytes), device="cuda") if nbytes else None
     return bufs, st
 
 
@@ -255,7 +252,10 @@ def replicate_state(problem, *, rank, world, device, src=0, groups=2):
     bufs = {}
     for k in ("rays", "orig", "pos", "spline_records"):
         ptr, nbytes = st[k]
-        bufs[k] = torch.as_tensor(_DevicePtr(ptr, nbytes), device="cuda") if nbytes else None
+        t = _wrapped.get((didx, k))
+        if nbytes and (t is None or t.data_ptr() != ptr or t.numel() != nbytes):
+            t = _wrapped[(didx, k)] = torch.as_tensor(_DevicePtr(ptr, nbytes), device="cuda")
+        bufs[k] = t if nbytes else None
     handle = side.cuda_stream
     side.wait_stream(torch.cuda.current_stream())
     with torch.cuda.stream(side):
