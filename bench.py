@@ -638,7 +638,8 @@ def bench_scale_configs(pkg, sharded, rank, world, barrier, dev, fp64_peak, core
     m = meta[0]
     delays = np.array([0.0 - 1.0 + 2 * 1.0 * i / 2000 for i in range(2001)])  # core_private.cpp:345
     lo, hi = sharded.shard_range(len(delays), rank, world)
-    p.presync_grid(m["fb"], m["fe"], delays[lo:lo + 8], stream=2, call_no=0, offset_index_base=lo)  # warm-up
+    # warm-up: a few tens of milliseconds of the same grid (the device has idled while rank 0 generated the inputs)
+    p.presync_grid(m["fb"], m["fe"], delays[lo:min(hi, lo + 256)], stream=2, call_no=0, offset_index_base=lo)
     barrier()
     t0 = time.perf_counter()
     curve = sharded.presync_grid_sharded(p, m["fb"], m["fe"], delays, stream=2, call_no=1, rank=rank, world=world, device=dev)
