@@ -407,9 +407,11 @@ def run_b200(args):
     gather_in = torch.empty(hi - lo, dtype=torch.float64, device=dev)
     gather_out = torch.empty((world, hi - lo), dtype=torch.float64, device=dev)
 
-    def step(call_no):
+    def step(call_no, marks=None):
         costs = prob.presync_grid(fb, fe, delays[lo:hi], stream=pkg.STREAM_DEBUG, call_no=call_no,
                                   offset_index_base=lo)
+        if marks is not None:
+            marks.append(time.perf_counter())
         if world > 1:  # the only exchange: loss-curve slices
             gather_in.copy_(torch.from_numpy(costs))
             dist.all_gather_into_tensor(gather_out, gather_in)
@@ -455,13 +457,22 @@ def run_b200(args):
     counts = np.full(w.n_frames, w.n_rays)
     st0 = prob.stats()
     bcast_bytes = 0
+    marks_on = bool(os.environ.get("RSSYNC_BENCH_MARKS"))
     def e2e_step(call_no):
+        m = [time.perf_counter()]
         if rank == 0:
             prob.SetGyroQuaternions(w.quats, w.quats.shape[0], w.gyro_rate, w.gyro_t0)
             prob.set_track_batch(w.frame_ids, counts, w.ts_a, w.ts_b, w.rays_a, w.rays_b)
+        m.append(time.perf_counter())
         if world > 1:
             sharded.replicate_state(prob, rank=rank, world=world, device=dev)
-        step(call_no)
+        m.append(time.perf_counter())
+        step(call_no, m)
+        if marks_on:
+            m.append(time.perf_counter())
+            d = np.diff(m) * 1e3
+            print(f"[e2e marks] rank {rank} call {call_no}: ingest {d[0]:.2f} replicate {d[1]:.2f} grid {d[2]:.2f} "
+                  f"gather {d[3]:.2f} ms", file=sys.stderr, flush=True)
 
     e2e_step(1999)  # untimed warm-up of this path (NCCL sets up its broadcast channels on first use)
     st0 = prob.stats()

@@ -23,6 +23,10 @@
 #if defined(__x86_64__)
 #include <immintrin.h>
 #endif
+#if defined(__linux__)
+#include <pthread.h>
+#include <sched.h>
+#endif
 #ifndef RSSYNC_STAGE_DEFAULT
 #define RSSYNC_STAGE_DEFAULT 2  // staging copy: 0 scalar, 1 AVX2, 2 AVX2 with non-temporal stores
 #endif
@@ -226,6 +230,7 @@ struct rssync_problem {
     struct InFlight {
         size_t lo, hi;
         cudaEvent_t ev;
+        bool foreign = false;  // delivered, or sent on, by a collective's kernel (rssync_expect_chunk / _stream_wait_chunk)
     };
     cudaStream_t copy_stream = nullptr;
     cudaStream_t repl_stream = nullptr;  // multi-device problems: the replication's collectives
@@ -502,6 +507,14 @@ bool is_multi(const rssync_problem* p) { return !p->replicas.empty() && !p->forc
 
 void parallel_copy(void* dst, const void* src, size_t bytes);  // worker pool, below
 
+int spare_sms_for_collectives() {
+    static const int n = [] {
+        const char* e = std::getenv("RSSYNC_SPARE_SMS");
+        return e ? std::max(0, std::atoi(e)) : 0;  // measured on 2 and 8 GPUs: 8 spare SMs cost 3 % of the grid and gain nothing
+    }();
+    return n;
+}
+
 // The kernel launches of one PreSync grid over the frames `sel` (already in p->d_frames) and the n
 // delays in p->d_delays, into p->d_framecost; the per-delay reduction is the caller's.
 int enqueue_grid_kernels(rssync_problem* p, const std::vector<FrameDesc>& sel, int max_n, int n, uint64_t stream_id,
@@ -560,9 +573,16 @@ int enqueue_grid_kernels(rssync_problem* p, const std::vector<FrameDesc>& sel, i
                 CUDA_TRY(p, cudaStreamWaitEvent(gs, p->in_flight[(size_t)run_dep[r] - 1].ev, 0));
                 waited = std::max(waited, run_dep[r]);
             }
+            // A run that is followed by chunks a collective still has to deliver can leave a few SMs
+            // free (RSSYNC_SPARE_SMS; default 0): the grid's blocks are persistent and fill the device,
+            // and the collective's kernel for the next chunks starts while this run is resident.
+            // Measured (r02, 2 and 8 GPUs): the collectives are not held up in practice.
+            int spare = 0;
+            for (size_t k = (size_t)run_dep[r]; k < p->in_flight.size(); ++k)
+                if (p->in_flight[k].foreign) spare = spare_sms_for_collectives();
             rs::launch_presync_tasks(dd, p->d_frames.ptr + f0, run_end[r] - f0, max_n, p->d_delays.ptr, n, p->seed,
                                      stream_id, call_no, idx_base, p->d_framecost.ptr + f0, F, d_flags, gs,
-                                     nullptr, max_chunk, p->simplified);
+                                     nullptr, max_chunk, p->simplified, spare);
             f0 = run_end[r];
         }
         for (int k = 0; k < rssync_problem::kGridStreams; ++k) {
@@ -1739,6 +1759,53 @@ unsigned host_cores() {
     return hw ? hw : 1;
 }
 
+// CPUs of the NUMA node the calling thread runs on (empty: one node, or unknown).  The staging copy
+// is bound by host memory bandwidth; on a two-socket host, workers on the other socket would pull
+// the caller's buffers and push the pinned staging buffer across the inter-socket link.
+std::vector<int> numa_local_cpus() {
+#if defined(__linux__)
+    if (std::getenv("RSSYNC_NO_NUMA_PIN")) return {};
+    const int cpu = sched_getcpu();
+    if (cpu < 0) return {};
+    std::vector<int> local;
+    int nodes = 0;
+    for (int node = 0; node < 64; ++node) {
+        char path[96];
+        std::snprintf(path, sizeof(path), "/sys/devices/system/node/node%d/cpulist", node);
+        FILE* f = std::fopen(path, "r");
+        if (!f) break;
+        ++nodes;
+        std::vector<int> cpus;
+        int a = 0, b = 0;
+        for (;;) {
+            if (std::fscanf(f, "%d", &a) != 1) break;
+            b = a;
+            int c = std::fgetc(f);
+            if (c == '-') {
+                if (std::fscanf(f, "%d", &b) != 1) break;
+                c = std::fgetc(f);
+            }
+            for (int k = a; k <= b; ++k) cpus.push_back(k);
+            if (c != ',') break;
+        }
+        std::fclose(f);
+        if (std::find(cpus.begin(), cpus.end(), cpu) != cpus.end()) local = cpus;
+    }
+    if (nodes < 2) return {};
+    cpu_set_t allowed;
+    CPU_ZERO(&allowed);
+    if (sched_getaffinity(0, sizeof(allowed), &allowed) == 0) {
+        std::vector<int> keep;
+        for (int c : local)
+            if (c < CPU_SETSIZE && CPU_ISSET(c, &allowed)) keep.push_back(c);
+        local.swap(keep);
+    }
+    return local.size() >= 4 ? local : std::vector<int>{};
+#else
+    return {};
+#endif
+}
+
 class WorkerPool {
 public:
     static WorkerPool& get() {
@@ -1783,10 +1850,20 @@ private:
     }
     WorkerPool() {
         // one core is left to the gyro worker thread, which runs beside the track ingest
-        const unsigned hw = host_cores();
+        const std::vector<int> local = numa_local_cpus();
+        const unsigned hw = local.empty() ? host_cores() : std::min<unsigned>(host_cores(), (unsigned)local.size());
         const size_t n = std::min<size_t>(hw > 2 ? hw - 1 : 1, 16);
         for (size_t t = 1; t < n; ++t)
-            threads_.emplace_back([this, t]() {
+            threads_.emplace_back([this, t, local]() {
+#if defined(__linux__)
+                if (!local.empty()) {  // stay on the caller's NUMA node
+                    cpu_set_t set;
+                    CPU_ZERO(&set);
+                    for (int c : local)
+                        if (c < CPU_SETSIZE) CPU_SET(c, &set);
+                    pthread_setaffinity_np(pthread_self(), sizeof(set), &set);
+                }
+#endif
                 uint64_t seen = 0;
                 for (;;) {
                     if (!spin_until([&] { return generation_.load(std::memory_order_acquire) != seen || stop_.load(); })) {
@@ -1961,7 +2038,7 @@ int rssync_set_track_batch(rssync_problem* p, size_t n_frames, const int64_t* fr
             size_t end = hi;
             for (size_t i = lo; i < hi; ++i)
                 if (rc[i]) { end = i; n_ok = i; break; }
-            rssync_problem::InFlight fl{(size_t)-1, 0, nullptr};
+            rssync_problem::InFlight fl{(size_t)-1, 0, nullptr, false};
             rs::PixelFrame* pf = reinterpret_cast<rs::PixelFrame*>(h_rec);
             for (size_t i = lo; i < end; ++i) {
                 FrameDesc* fd = nullptr;
@@ -2569,13 +2646,14 @@ int rssync_stream_wait_chunk(rssync_problem* p, int k, void* stream) {
     }
     if ((size_t)k >= p->in_flight.size()) { p->err = "stream-wait-chunk: no such chunk in flight"; return RSSYNC_E_INVALID; }
     CUDA_TRY(p, cudaStreamWaitEvent(st, p->in_flight[(size_t)k].ev, 0));
+    p->in_flight[(size_t)k].foreign = true;  // a collective's kernel will send this chunk on: see enqueue_grid_kernels
     return RSSYNC_OK;
 }
 
 int rssync_expect_chunk(rssync_problem* p, size_t lo, size_t hi, void* stream) {
     if (!p || lo > hi) return RSSYNC_E_INVALID;
     CUDA_TRY(p, cudaSetDevice(p->device));
-    rssync_problem::InFlight fl{lo, hi, nullptr};
+    rssync_problem::InFlight fl{lo, hi, nullptr, true};
     if (p->ev_pool.empty()) {
         CUDA_TRY(p, cudaEventCreateWithFlags(&fl.ev, cudaEventDisableTiming));
     } else {

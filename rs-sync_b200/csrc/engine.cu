@@ -2090,7 +2090,8 @@ int presync_max_chunk(const double* h_delays, int D, double frame_span_s, double
 void launch_presync_tasks(const DeviceData& dd, const FrameDesc* d_frames, int F, int max_n,
                           const double* d_delays, int D, uint64_t seed, uint64_t stream, uint64_t call_no,
                           uint64_t idx_base, double* d_framecost, int cost_stride, unsigned* d_flags,
-                          cudaStream_t st, const uint64_t* d_frame_call_no, int max_chunk, bool simplified) {
+                          cudaStream_t st, const uint64_t* d_frame_call_no, int max_chunk, bool simplified,
+                          int spare_sms) {
     if (F <= 0 || D <= 0) return;
     RS_DISPATCH_SLOTS(max_n, {
         using Cfg = GridCfg<SL>;
@@ -2098,7 +2099,7 @@ void launch_presync_tasks(const DeviceData& dd, const FrameDesc* d_frames, int F
         allow_smem(kern, Cfg::kSmem);
         const int sm_count = sm_count_of(current_device());
         const int per_sm = blocks_per_sm(kern, Cfg::kWarps * 32, Cfg::kSmem);
-        const long long blocks_cap = (long long)sm_count * per_sm;
+        const long long blocks_cap = (long long)std::max(1, sm_count - std::max(0, spare_sms)) * per_sm;
         // Delays per unit: as many as the staged window takes (max_chunk; 0 = unknown, be conservative),
         // but no more than leaves every block several units (small grids: PreSync on a 60-frame window),
         // and at least one task per warp when the grid has that many delays.

@@ -62,7 +62,7 @@ void launch_presync_tasks(const DeviceData& dd, const FrameDesc* d_frames, int F
                           const double* d_delays, int D, uint64_t seed, uint64_t stream, uint64_t call_no,
                           uint64_t idx_base, double* d_framecost, int cost_stride, unsigned* d_flags,
                           cudaStream_t st, const uint64_t* d_frame_call_no = nullptr, int max_chunk = 0,
-                          bool simplified = false);
+                          bool simplified = false, int spare_sms = 0);  // spare_sms: SMs this launch leaves free
 void launch_presync_reduce(const double* d_framecost, int F, int D, double* d_costs, cudaStream_t st,
                            const int* d_win_begin = nullptr, int n_windows = 0);
 

@@ -3,6 +3,10 @@ sys.path.insert(0, os.getcwd())
 import numpy as np, torch, torch.distributed as dist
 rank=int(os.environ["RANK"]); world=int(os.environ["WORLD_SIZE"]); local=int(os.environ["LOCAL_RANK"])
 torch.cuda.set_device(local); dev=torch.device("cuda",local)
+if rank != 0 and os.environ.get("BLOCKING"):
+    import ctypes
+    torch.cuda.init()
+    print("blocking sync:", ctypes.CDLL("libcudart.so.12").cudaSetDeviceFlags(ctypes.c_uint(4)), flush=True)
 dist.init_process_group("nccl", device_id=dev)
 pkg=importlib.import_module("rs-sync_b200"); sharded=importlib.import_module("rs-sync_b200.sharded"); synth=importlib.import_module("rs-sync_b200.synth")
 w=synth.make_workload("C2")
