@@ -377,8 +377,10 @@ def run_b200(args):
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=dev)
-        # one process per GPU on one host: each engine's ingest thread pool gets its share of the cores
-        os.environ.setdefault("RSSYNC_HOST_THREADS", str(max(1, cores // max(local_world, 1))))
+        # one process per GPU on one host, and the inputs enter through rank 0 only: its ingest thread
+        # pool gets the cores the other ranks' (waiting) main threads leave, theirs get two
+        share = max(2, cores - (local_world - 1)) if rank == 0 else 2
+        os.environ.setdefault("RSSYNC_HOST_THREADS", str(share))
 
     def barrier():
         if world > 1:
@@ -474,7 +476,8 @@ def run_b200(args):
             print(f"[e2e marks] rank {rank} call {call_no}: ingest {d[0]:.2f} replicate {d[1]:.2f} grid {d[2]:.2f} "
                   f"gather {d[3]:.2f} ms", file=sys.stderr, flush=True)
 
-    e2e_step(1999)  # untimed warm-up of this path (NCCL sets up its broadcast channels on first use)
+    for c in (1998, 1999):  # untimed warm-up of this path (NCCL sets up its broadcast channels on first use)
+        e2e_step(c)
     st0 = prob.stats()
     barrier()
     t0 = time.perf_counter()
@@ -651,27 +654,31 @@ def bench_scale_configs(pkg, sharded, rank, world, barrier, dev, fp64_peak, core
     lo, hi = sharded.shard_range(len(delays), rank, world)
     # warm-up: a few tens of milliseconds of the same grid (the device has idled while rank 0 generated the inputs)
     p.presync_grid(m["fb"], m["fe"], delays[lo:min(hi, lo + 256)], stream=2, call_no=0, offset_index_base=lo)
-    barrier()
-    t0 = time.perf_counter()
-    curve = sharded.presync_grid_sharded(p, m["fb"], m["fe"], delays, stream=2, call_no=1, rank=rank, world=world, device=dev)
-    barrier()
-    dt = time.perf_counter() - t0
-    tt = torch.tensor([dt], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-    dt = float(tt[0])
+    each = []
+    for _ in range(2):  # twice, the better one counts (both are reported)
+        barrier()
+        t0 = time.perf_counter()
+        curve = sharded.presync_grid_sharded(p, m["fb"], m["fe"], delays, stream=2, call_no=1, rank=rank, world=world, device=dev)
+        barrier()
+        tt = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        each.append(float(tt[0]))
+    dt = min(each)
     cells = len(delays) * m["n_frames"] * m["n_rays"]
     c3 = {"config": f"C3: {m['n_frames']} frames x {m['n_rays']} rays x {len(delays)} offsets (radius 1 s, step 1 ms), offsets sharded x{world}",
           "scaling": "strong", "seconds": dt, "cells_per_s": cells / dt,
           "frac_fp64_peak": FLOP_PER_CELL * cells / dt / 1e12 / (fp64_peak * world) if fp64_peak > 0 else None,
           "argmin_delay": float(delays[int(np.argmin(curve))]), "true_delay": m["true_delay"],
-          "checksum": float(np.sum(curve)), "synth_seconds_rank0": t_gen, "replicate_seconds": t_rep}
+          "seconds_each": each, "checksum": float(np.sum(curve)), "synth_seconds_rank0": t_gen, "replicate_seconds": t_rep}
     if world > 1:
         n1, same = None, True
         if rank == 0:
-            t1 = time.perf_counter()
-            whole = p.presync_grid(m["fb"], m["fe"], delays, stream=2, call_no=1)
-            n1 = time.perf_counter() - t1
+            n1 = None
+            for _ in range(2):
+                t1 = time.perf_counter()
+                whole = p.presync_grid(m["fb"], m["fe"], delays, stream=2, call_no=1)
+                n1 = min(n1, time.perf_counter() - t1) if n1 else time.perf_counter() - t1
             same = bool(np.array_equal(whole, curve))
         host_wait(rank, "c3_solo")
         barrier()
