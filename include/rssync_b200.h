@@ -304,6 +304,13 @@ int rssync_probe_loss(rssync_problem* p, int64_t frame, double delay, const doub
 int rssync_probe_lbfgs(rssync_problem* p, int64_t frame, double delay, double* m3, double k,
                        double* f, int* iters, int* evals);
 int rssync_probe_log1p(const double* x, int n, double* out);
+/* Host-only: the checked staging copy of the bulk SetTrackResult (n doubles src -> dst; *all_finite = 0
+ * when a value is NaN or infinite; [*lo, *hi] widened to the values when both are given), in one of
+ * its three forms: mode 0 scalar, 1 AVX2, 2 AVX2 with non-temporal stores.  The forms are
+ * interchangeable bit for bit (tests). */
+int rssync_probe_stage_copy(const double* src, size_t n, int mode, double* dst, double* lo, double* hi,
+                            int* all_finite);
+
 /* sin (which = 0), cos (1), acos (2) of the arithmetic contract (csrc/spec_trig.h), evaluated by the
  * library's host code (on_device = 0, no GPU needed) or by a kernel */
 int rssync_probe_spec_trig(const double* x, int n, int which, int on_device, double* out);

@@ -38,6 +38,7 @@ C_ABI_SYMBOLS = [
     "rssync_orientation_search", "rssync_orientation_search_ex", "rssync_presync_windows", "rssync_set_track_pixels",
     "rssync_create_multi", "rssync_device_count", "rssync_frame_table", "rssync_device_state", "rssync_adopt_state",
     "rssync_device_state_pipelined", "rssync_stream_wait_chunk", "rssync_expect_chunk", "rssync_note_reader",
+    "rssync_probe_stage_copy",
     "rssync_set_loss_mode", "rssync_probe_spec_trig",
 ]
 # Itanium-ABI symbols of the C++ drop-in face (same set the reference's librssync_core exports)
@@ -104,6 +105,8 @@ def load_library():
     L.rssync_stream_wait_chunk.argtypes = [P, C.c_int, C.c_void_p]
     L.rssync_expect_chunk.argtypes = [P, C.c_size_t, C.c_size_t, C.c_void_p]
     L.rssync_note_reader.argtypes = [P, C.c_void_p]
+    L.rssync_probe_stage_copy.argtypes = [C.POINTER(C.c_double), C.c_size_t, C.c_int, C.POINTER(C.c_double),
+                                          C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_int)]
     L.rssync_destroy.argtypes = [P]
     L.rssync_destroy.restype = None
     L.rssync_last_error.argtypes = [P]
@@ -220,6 +223,29 @@ def probe_spec_trig(x, which, on_device=False):
     if rc != OK:
         raise RsSyncError(rc, "spec trig probe failed")
     return out
+
+
+def probe_stage_copy(x, mode, bounds=None, misalign=0):
+    """host-only: the bulk ingest's checked staging copy of `x` in form `mode` (0 scalar, 1 AVX2, 2 AVX2
+    with non-temporal stores); returns (copy, all_finite, lo, hi) -- [lo, hi] starts at `bounds` and is
+    widened to the values (None: not tracked).  `misalign`: destination offset in doubles from a
+    64-byte boundary."""
+    L = load_library()
+    x = _f64(x)
+    buf = np.zeros(x.size + 16, dtype=np.float64)
+    start = (-(buf.ctypes.data // 8) % 8 + misalign) % 8 if misalign else (-(buf.ctypes.data // 8)) % 8
+    dst = buf[start:start + x.size]
+    ok = C.c_int(0)
+    if bounds is None:
+        rc = L.rssync_probe_stage_copy(_dp(x), x.size, mode, _dp(dst), None, None, C.byref(ok))
+        lo = hi = None
+    else:
+        lo_c, hi_c = C.c_double(bounds[0]), C.c_double(bounds[1])
+        rc = L.rssync_probe_stage_copy(_dp(x), x.size, mode, _dp(dst), C.byref(lo_c), C.byref(hi_c), C.byref(ok))
+        lo, hi = lo_c.value, hi_c.value
+    if rc != OK:
+        raise RsSyncError(rc, "stage copy probe failed (form not supported on this CPU?)")
+    return dst.copy(), bool(ok.value), lo, hi
 
 
 def probe_log1p(x):

@@ -2881,6 +2881,23 @@ int rssync_probe_lbfgs(rssync_problem* p, int64_t frame, double delay, double* m
     return RSSYNC_OK;
 }
 
+int rssync_probe_stage_copy(const double* src, size_t n, int mode, double* dst, double* lo, double* hi,
+                            int* all_finite_out) {
+    if (!src || !dst || !all_finite_out || (lo == nullptr) != (hi == nullptr)) return RSSYNC_E_INVALID;
+    bool ok;
+#if defined(__x86_64__)
+    if (mode != 0 && !__builtin_cpu_supports("avx2")) return RSSYNC_E_INVALID;
+    if (mode == 1) ok = copy_checked_avx2<false>(dst, src, n, lo, hi);
+    else if (mode == 2) ok = copy_checked_avx2<true>(dst, src, n, lo, hi);
+    else
+#else
+    if (mode != 0) return RSSYNC_E_INVALID;
+#endif
+        ok = copy_checked_scalar(dst, src, n, lo, hi);
+    *all_finite_out = ok ? 1 : 0;
+    return RSSYNC_OK;
+}
+
 int rssync_probe_spec_trig(const double* x, int n, int which, int on_device, double* out) {
     if (n <= 0) return RSSYNC_OK;
     if (!x || !out || which < 0 || which > 2) return RSSYNC_E_INVALID;

@@ -218,7 +218,9 @@ def replicate_state(problem, *, rank, world, device, src=0, groups=2):
         raw = ft.tobytes()
         changed = _last_table.get(key) != raw
         st = problem.device_state_pipelined()
-        chunks = st["chunks"] or []
+        if st["chunks"] is None:  # more chunks in flight than the call reports: wait for the ingest instead
+            st = problem.device_state()
+        chunks = st.get("chunks") or []
         pieces = _merge_chunks(chunks, groups, st["arena_rays"], max_groups)
         head = [ft.shape[0], st["arena_rays"], st["gyro_samples"], st["sample_rate"], st["first_timestamp"],
                 1.0 if changed else 0.0, len(pieces)]

@@ -94,3 +94,42 @@ def test_product_does_not_import_oracle():
                 for needle in ("import oracle", "from oracle", "oracle/", "oracle.loader", "liboracle", "orc_",
                                "rssync_oracle", "oracle_math"):
                     assert needle not in body, (os.path.join(dirpath, f), needle)
+
+
+def test_staging_copy_forms_are_interchangeable(rsb):
+    """the bulk SetTrackResult's checked staging copy (host code, no device): scalar, AVX2 and AVX2 with
+    non-temporal stores give the same bytes, the same finite / non-finite verdict and the same bounds,
+    for every length and destination alignment, with NaN / inf / signed zeros anywhere"""
+    import struct
+    import numpy as np
+    rng = np.random.default_rng(3)
+    try:
+        rsb.probe_stage_copy(np.zeros(4), 1)
+    except rsb.RsSyncError:
+        pytest.skip("no AVX2 on this host")
+    for n in (0, 1, 3, 4, 5, 31, 200, 600, 1031):
+        for mis in (0, 1, 3, 5):
+            base = rng.standard_normal(n) * 10.0 ** rng.integers(-300, 300, size=n)
+            cases = [base]
+            if n:
+                for bad in (np.nan, np.inf, -np.inf):
+                    c = base.copy()
+                    c[rng.integers(0, n)] = bad
+                    cases.append(c)
+                z = base.copy()
+                z[rng.integers(0, n)] = -0.0
+                z[rng.integers(0, n)] = 0.0
+                cases.append(z)
+                cases.append(np.full(n, -0.0))
+            for x in cases:
+                b0 = (float(x[0]), float(x[0])) if n and np.isfinite(x[0]) else (0.0, 0.0)
+                ref = rsb.probe_stage_copy(x, 0, bounds=b0, misalign=mis)
+                assert ref[1] == bool(np.all(np.isfinite(x)))
+                for mode in (1, 2):
+                    got = rsb.probe_stage_copy(x, mode, bounds=b0, misalign=mis)
+                    assert got[0].tobytes() == ref[0].tobytes() == x.tobytes()
+                    assert got[1] == ref[1]
+                    if ref[1]:  # bounds are only used when the data passed the check
+                        assert struct.pack("dd", got[2], got[3]) == struct.pack("dd", ref[2], ref[3])
+                        assert got[2] == min(b0[0], x.min()) and got[3] == max(b0[1], x.max()) if n else True
+                    assert rsb.probe_stage_copy(x, mode, misalign=mis)[1] == ref[1]
