@@ -2424,6 +2424,8 @@ int rssync_orientation_search_ex(rssync_problem* p, const double* timestamps_s, 
     if (int rc = flush(p)) return rc;  // the tracks, and whatever gyro was pending
     cudaSetDevice(p->device);
     cudaStream_t st = p->stream;
+    // the variants' spline records overwrite the problem's own: not before a replication still reading them
+    if (p->reader_pending) CUDA_TRY(p, cudaStreamWaitEvent(st, p->ev_reader, 0));
     const size_t nq = plan.n_out, n = count;
     // variants per pass: bounded by ~2 GB of intermediates
     const size_t per_var = (n * 4 + nq * (4 + 4 + 16)) * sizeof(double);
