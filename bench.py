@@ -198,7 +198,8 @@ def run_reference(args):
     threads = os.cpu_count() or 1
     p, kind = cpu_problem(w, threads)
     rate, _ = time_cpu(p, w, delays, 1)
-    budget = min(20.0, 100.0 / max(1, args.steps + args.warmup))
+    budget = min(20.0, 100.0 / max(1, args.steps + args.warmup))  # seconds of CPU work per step
+    budget = float(os.environ.get("RSSYNC_REF_BUDGET", budget))   # (the CPU test suite shortens it)
     n_off = cpu_sample_shape(w, delays, rate, budget)
     for i in range(args.warmup):
         time_cpu(p, w, delays, n_off, call_no=i)

@@ -72,3 +72,28 @@ def test_no_presync_uses_infinite_radius(driver, oracle_loader, tmp_path):
     for _ in range(4):
         d = o2.Sync(d, int(w.frame_ids[0]), int(w.frame_ids[0]) + 8, 0.035, np.inf)[1]
     assert r["delay_ms"][0] == 1000.0 * d
+
+
+def test_bench_reference_arm_line():
+    """`bench.py --impl reference` (the CPU arm the driver runs beside the GPU arm): one JSON line on
+    stdout with the GPU arm's metric / unit / config keys, impl = reference, a cpu_baseline describing
+    the run and an e2e block that moves no bytes.  Shortened sample, smallest workload."""
+    import json
+    import os
+    import subprocess
+    import sys
+    from conftest import ROOT
+    env = dict(os.environ, RSSYNC_REF_BUDGET="0.5")
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--workload", "C1",
+                        "--steps", "2", "--warmup", "1"], capture_output=True, text=True, env=env, cwd=ROOT, timeout=300)
+    assert r.returncode == 0, r.stderr[-2000:]
+    lines = [l for l in r.stdout.splitlines() if l.strip()]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and d["metric"] == "presync_loss_evals_per_s" and d["unit"] == "cells/s"
+    assert d["higher_is_better"] is True and d["steps"] == 2 and d["warmup"] == 1 and d["n_gpus"] == 1
+    assert d["value"] > 0 and d["ms_per_step"] > 0 and d["dtype"] == "f64" and d["vs_baseline"] is None
+    assert d["cpu_baseline"]["kind"] in ("reference", "port") and d["cpu_baseline"]["cores"] >= 1
+    assert d["cpu_baseline"]["value"] == d["value"] and "offsets" in d["cpu_baseline"]["sample"]
+    assert d["e2e"] == {"value": d["value"], "unit": "cells/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    assert "workload" in d["config"]
