@@ -170,7 +170,13 @@ def main(argv=None):
     syn = config["input"].get("synthetic", {})
     w = synth.make_workload(argv[1] if len(argv) > 1 else syn.get("workload", "C1"))
     config["input"].setdefault("frame_range", list(w.meta["span"]))
-    prob = pkg.SyncProblem(seed=int(syn.get("seed", 100))).load(w, bulk=True)
+    # several GPUs in this one process: `"devices": [0, 1, ...]` under input.synthetic, or the C++
+    # drop-in's RSSYNC_DEVICES=0,1,... (rssync_create_multi; results are the single-GPU results)
+    import os
+    devices = syn.get("devices")
+    if devices is None and os.environ.get("RSSYNC_DEVICES"):
+        devices = [int(d) for d in os.environ["RSSYNC_DEVICES"].split(",") if d.strip()]
+    prob = pkg.SyncProblem(seed=int(syn.get("seed", 100)), devices=devices or None).load(w, bulk=True)
     res = run(prob, config, presync_delays=pkg.presync_delays)
     print(json.dumps({"syncpoints": len(res["syncpoints"]), "rmse_ms": res["rmse_ms"],
                       "first_delay_ms": float(res["delay_ms"][0]), "last_delay_ms": float(res["delay_ms"][-1])}))
