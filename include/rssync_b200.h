@@ -304,6 +304,14 @@ int rssync_probe_loss(rssync_problem* p, int64_t frame, double delay, const doub
 int rssync_probe_lbfgs(rssync_problem* p, int64_t frame, double delay, double* m3, double k,
                        double* f, int* iters, int* evals);
 int rssync_probe_log1p(const double* x, int n, double* out);
+/* Host-only: the pieces a multi-device problem's replication sends for n ingest chunks in flight
+ * ([lo, hi) arena ranges in stream order) over an arena of arena_rays, grouped into at most `groups`
+ * pieces behind whatever is already on the device (k_last = -1).  Returns the number of pieces
+ * (at most cap are written), -1 on bad arguments. */
+int rssync_probe_replication_plan(const size_t* lo, const size_t* hi, size_t n, size_t arena_rays,
+                                  size_t groups, int* k_last, size_t* piece_lo, size_t* piece_hi,
+                                  size_t cap);
+
 /* Host-only: the checked staging copy of the bulk SetTrackResult (n doubles src -> dst; *all_finite = 0
  * when a value is NaN or infinite; [*lo, *hi] widened to the values when both are given), in one of
  * its three forms: mode 0 scalar, 1 AVX2, 2 AVX2 with non-temporal stores.  The forms are

@@ -38,7 +38,7 @@ C_ABI_SYMBOLS = [
     "rssync_orientation_search", "rssync_orientation_search_ex", "rssync_presync_windows", "rssync_set_track_pixels",
     "rssync_create_multi", "rssync_device_count", "rssync_frame_table", "rssync_device_state", "rssync_adopt_state",
     "rssync_device_state_pipelined", "rssync_stream_wait_chunk", "rssync_expect_chunk", "rssync_note_reader",
-    "rssync_probe_stage_copy",
+    "rssync_probe_stage_copy", "rssync_probe_replication_plan",
     "rssync_set_loss_mode", "rssync_probe_spec_trig",
 ]
 # Itanium-ABI symbols of the C++ drop-in face (same set the reference's librssync_core exports)
@@ -105,6 +105,9 @@ def load_library():
     L.rssync_stream_wait_chunk.argtypes = [P, C.c_int, C.c_void_p]
     L.rssync_expect_chunk.argtypes = [P, C.c_size_t, C.c_size_t, C.c_void_p]
     L.rssync_note_reader.argtypes = [P, C.c_void_p]
+    L.rssync_probe_replication_plan.argtypes = [C.POINTER(C.c_size_t), C.POINTER(C.c_size_t), C.c_size_t, C.c_size_t,
+                                                C.c_size_t, C.POINTER(C.c_int), C.POINTER(C.c_size_t),
+                                                C.POINTER(C.c_size_t), C.c_size_t]
     L.rssync_probe_stage_copy.argtypes = [C.POINTER(C.c_double), C.c_size_t, C.c_int, C.POINTER(C.c_double),
                                           C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_int)]
     L.rssync_destroy.argtypes = [P]
@@ -223,6 +226,20 @@ def probe_spec_trig(x, which, on_device=False):
     if rc != OK:
         raise RsSyncError(rc, "spec trig probe failed")
     return out
+
+
+def probe_replication_plan(chunks, arena_rays, groups):
+    """host-only: the library's replication pieces [(k_last, lo, hi), ...] for `chunks` in flight"""
+    L = load_library()
+    n = len(chunks)
+    lo = (C.c_size_t * max(n, 1))(*[c[0] for c in chunks])
+    hi = (C.c_size_t * max(n, 1))(*[c[1] for c in chunks])
+    cap = 64
+    k, plo, phi = (C.c_int * cap)(), (C.c_size_t * cap)(), (C.c_size_t * cap)()
+    m = L.rssync_probe_replication_plan(lo, hi, n, int(arena_rays), int(groups), k, plo, phi, cap)
+    if m < 0 or m > cap:
+        raise RsSyncError(E_INVALID, "replication plan probe failed")
+    return [(int(k[i]), int(plo[i]), int(phi[i])) for i in range(m)]
 
 
 def probe_stage_copy(x, mode, bounds=None, misalign=0):

@@ -1068,6 +1068,40 @@ inline int n_ranks(const rssync_problem* p) { return 1 + (int)p->replicas.size()
 inline rssync_problem* rank_problem(rssync_problem* p, int i) { return i == 0 ? p : p->replicas[(size_t)i - 1]; }
 
 // bring every replica up to the primary's inputs
+// The pieces a replication sends, covering the whole arena [0, rays): first whatever no chunk in
+// flight covers (k_last = -1: it is on the device already -- an ingest that had to grow the arena
+// waited for its first chunks, frames set one by one were uploaded by the flush), then the chunks in
+// flight (stream order), consecutive ones together in at most `groups` pieces, each to be sent once
+// its last chunk (k_last) has landed.  More than 16 pieces (scattered updates): one piece, sent last.
+struct ReplicationPiece { int k_last; size_t lo, hi; };
+std::vector<ReplicationPiece> plan_replication(const std::vector<std::pair<size_t, size_t>>& flying, size_t rays,
+                                               size_t groups) {
+    std::vector<ReplicationPiece> pieces;
+    const size_t nfl = flying.size();
+    {
+        std::vector<std::pair<size_t, size_t>> busy = flying;
+        std::sort(busy.begin(), busy.end());
+        size_t at = 0;
+        for (const auto& b : busy) {
+            if (b.first > at) pieces.push_back(ReplicationPiece{-1, at, b.first});
+            at = std::max(at, b.second);
+        }
+        if (rays > at) pieces.push_back(ReplicationPiece{-1, at, rays});
+    }
+    const size_t n_groups = std::min<size_t>(nfl, groups);
+    for (size_t g = 0; g < n_groups; ++g) {
+        const size_t a = nfl * g / n_groups, b = nfl * (g + 1) / n_groups;
+        ReplicationPiece pc{(int)b - 1, flying[a].first, flying[a].second};
+        for (size_t k = a; k < b; ++k) {
+            pc.lo = std::min(pc.lo, flying[k].first);
+            pc.hi = std::max(pc.hi, flying[k].second);
+        }
+        if (pc.lo < pc.hi) pieces.push_back(pc);
+    }
+    if (pieces.size() > 16) pieces.assign(1, ReplicationPiece{(int)nfl - 1, 0, rays});
+    return pieces;
+}
+
 int multi_replicate(rssync_problem* p) {
     RS_NVTX_RANGE();
     bool stale = false;
@@ -1081,34 +1115,10 @@ int multi_replicate(rssync_problem* p) {
     const rs::Nccl* nc = rs::Nccl::get();
     DeviceGuard guard;
     const size_t rays = p->dev_used;
-    // The pieces cover the whole arena: first whatever no chunk in flight covers (k_last = -1: it is on
-    // the device already -- an ingest that had to grow the arena waited for its first chunks, frames
-    // set one by one were uploaded by the flush above), then the chunks in flight, a few at a time.
-    struct Piece { int k_last; size_t lo, hi; };
-    std::vector<Piece> pieces;
-    const size_t nfl = p->in_flight.size();
-    {
-        std::vector<std::pair<size_t, size_t>> busy;
-        for (const auto& f : p->in_flight) busy.emplace_back(f.lo, f.hi);
-        std::sort(busy.begin(), busy.end());
-        size_t at = 0;
-        for (const auto& b : busy) {
-            if (b.first > at) pieces.push_back(Piece{-1, at, b.first});
-            at = std::max(at, b.second);
-        }
-        if (rays > at) pieces.push_back(Piece{-1, at, rays});
-    }
-    const size_t n_groups = std::min<size_t>(nfl, 4);
-    for (size_t g = 0; g < n_groups; ++g) {
-        const size_t a = nfl * g / n_groups, b = nfl * (g + 1) / n_groups;
-        Piece pc{(int)b - 1, p->in_flight[a].lo, p->in_flight[a].hi};
-        for (size_t k = a; k < b; ++k) {
-            pc.lo = std::min(pc.lo, p->in_flight[k].lo);
-            pc.hi = std::max(pc.hi, p->in_flight[k].hi);
-        }
-        if (pc.lo < pc.hi) pieces.push_back(pc);
-    }
-    if (pieces.size() > 16) pieces.assign(1, Piece{(int)nfl - 1, 0, rays});  // scattered updates: one piece, last
+    std::vector<std::pair<size_t, size_t>> flying;
+    for (const auto& f : p->in_flight) flying.emplace_back(f.lo, f.hi);
+    const std::vector<ReplicationPiece> pieces = plan_replication(flying, rays, 4);
+    using Piece = ReplicationPiece;
     for (rssync_problem* r : p->replicas) {
         cudaSetDevice(r->device);
         r->frames = p->frames;
@@ -2881,6 +2891,20 @@ int rssync_probe_lbfgs(rssync_problem* p, int64_t frame, double delay, double* m
     if (iters) *iters = st[0];
     if (evals) *evals = st[1];
     return RSSYNC_OK;
+}
+
+int rssync_probe_replication_plan(const size_t* lo, const size_t* hi, size_t n, size_t arena_rays, size_t groups,
+                                  int* k_last, size_t* piece_lo, size_t* piece_hi, size_t cap) {
+    if ((n && (!lo || !hi)) || groups == 0 || (cap && (!k_last || !piece_lo || !piece_hi))) return -1;
+    std::vector<std::pair<size_t, size_t>> flying;
+    for (size_t k = 0; k < n; ++k) flying.emplace_back(lo[k], hi[k]);
+    const std::vector<ReplicationPiece> pieces = plan_replication(flying, arena_rays, groups);
+    for (size_t i = 0; i < pieces.size() && i < cap; ++i) {
+        k_last[i] = pieces[i].k_last;
+        piece_lo[i] = pieces[i].lo;
+        piece_hi[i] = pieces[i].hi;
+    }
+    return (int)pieces.size();
 }
 
 int rssync_probe_stage_copy(const double* src, size_t n, int mode, double* dst, double* lo, double* hi,

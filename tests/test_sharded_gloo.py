@@ -114,3 +114,30 @@ def test_replication_pieces_cover_the_arena():
             for i in range(lo, hi):
                 covered[i] += 1
         assert min(covered) >= 1
+
+
+def test_library_and_python_replication_plans_agree(rsb):
+    """the planner inside the library (rssync_create_multi problems, plan_replication in capi.cpp) and
+    sharded._merge_chunks state the same rule: same pieces for the same chunks in flight (host-only)"""
+    import importlib
+    import random
+    sh = importlib.import_module("rs-sync_b200.sharded")
+    rnd = random.Random(5)
+    cases = [([], 0), ([], 1000), ([(0, 250), (250, 500), (500, 750), (750, 1000)], 1000),
+             ([(600, 700), (700, 800), (800, 1000)], 1000), ([(100, 200), (400, 500)], 1000),
+             ([(i, i + 1) for i in range(0, 60, 2)], 100)]
+    for _ in range(200):
+        arena = rnd.randrange(1, 5000)
+        n = rnd.randrange(0, 12)
+        if rnd.random() < 0.5:  # contiguous chunks of one batch appended somewhere in the arena
+            cuts = sorted(rnd.sample(range(arena + 1), min(n + 1, arena + 1)))
+            chunks = [(a, b) for a, b in zip(cuts, cuts[1:])]
+        else:                   # scattered, possibly overlapping ranges in any order
+            chunks = []
+            for _ in range(n):
+                a = rnd.randrange(0, arena)
+                chunks.append((a, rnd.randrange(a + 1, arena + 1)))
+        cases.append((chunks, arena))
+    for chunks, arena in cases:
+        for groups in (1, 2, 4):
+            assert rsb.probe_replication_plan(chunks, arena, groups) == sh._merge_chunks(chunks, groups, arena), (chunks, arena, groups)
